@@ -1,0 +1,150 @@
+"""Pins the oracle (oracle/ref_block.py): (1) against the committed golden vectors that
+oracle/make_golden.py produced from the reference's own unmodified modules, (2) bit-for-bit
+against the live reference when /root/reference is mounted (build container only), and
+(3) against the reference's own closed-form scheduler expectations (tests/test_scheduler.py)."""
+import os
+
+import pytest
+import torch
+
+import ref_block as rb
+import ref_import
+
+TOL = dict(rtol=2e-5, atol=2e-6)  # golden vectors may come from another host's BLAS
+
+
+def _tiny(golden_dir):
+    g = torch.load(os.path.join(golden_dir, "tiny_train_fp32.pt"))
+    c = g["case"]
+    P = rb.init_params(g["cfg"], c["lora_rank"], seed=c["seed_w"])
+    batch = rb.synthetic_batch(g["cfg"], c["b"], c["f"], c["h"], c["w"], c["n_ctx"], c["seed_x"], c["valid_ctx"])
+    return g, P, batch, torch.tensor(c["t"])
+
+
+def _oracle_loss_grads(P, cfg, batch, t):
+    P = {k: v.clone().requires_grad_(rb.is_trainable(k)) for k, v in P.items()}
+    loss, out = rb.train_step_loss(P, cfg, batch["latents"], batch["ref_image_latents"], batch["pose_latents"],
+                                   batch["prompt_embeds"], batch["prompt_mask"], t, batch["noise"])
+    loss.backward()
+    return loss.detach(), out.detach(), {k: v.grad for k, v in P.items() if v.grad is not None}
+
+
+def test_train_step_matches_golden(golden_dir):
+    g, P, batch, t = _tiny(golden_dir)
+    loss, out, grads = _oracle_loss_grads(P, g["cfg"], batch, t)
+    torch.testing.assert_close(out, g["out"], **TOL)
+    torch.testing.assert_close(loss, g["loss"], **TOL)
+    assert set(grads) == set(g["grads"])
+    assert any("lora_A" in k for k in grads) and any("caption_projection" in k for k in grads)
+    for k in grads:
+        torch.testing.assert_close(grads[k], g["grads"][k], rtol=1e-4, atol=1e-7, msg=lambda m, k=k: f"{k}: {m}")
+        assert float(g["grads"][k].abs().max()) > 0, k  # LoRA-B randomised => dA != 0
+
+
+def test_rope_table_matches_golden(golden_dir):
+    g = torch.load(os.path.join(golden_dir, "rope_table.pt"))
+    for ck, cc, ss in (("coords", "cos", "sin"), ("fcoords", "cos_f", "sin_f")):
+        cos, sin = rb.rope_table(g[ck], 2048, 10000.0, [20, 2048, 2048], torch.float32)
+        torch.testing.assert_close(cos, g[cc], rtol=0, atol=1e-6)
+        torch.testing.assert_close(sin, g[ss], rtol=0, atol=1e-6)
+    assert torch.all(g["cos"][..., :2] == 1) and torch.all(g["sin"][..., :2] == 0)  # front pad (2048 % 6)
+
+
+def test_sampling_forward_matches_golden(golden_dir):
+    g = torch.load(os.path.join(golden_dir, "tiny_sampling_fp32.pt"))
+    P = rb.init_params(g["cfg"], 0, seed=3)
+    b = rb.synthetic_batch(g["cfg"], 2, 2, 4, 4, 24, 99, None)
+    tokens, coords = rb.patchify(b["latents"])
+    fc = coords.float()
+    fc[:, 0] = fc[:, 0] * (1.0 / 25)
+    x = tokens.clone()
+    with torch.no_grad():
+        out = rb.transformer_forward(P, g["cfg"], x, fc, b["ref_image_latents"], b["pose_latents"],
+                                     b["prompt_embeds"].expand(2, -1, -1), torch.tensor([[0.9], [0.9]]),
+                                     b["prompt_mask"].expand(2, -1), skip_layer_mask=g["skip"],
+                                     skip_layer_strategy=rb.STG_ATTENTION_VALUES)
+    torch.testing.assert_close(out, g["out"], **TOL)
+    torch.testing.assert_close(x, g["tokens_after"], rtol=0, atol=0)  # input mutated in place
+    assert not torch.equal(x, tokens)
+
+
+@pytest.mark.parametrize("sampler", ["Uniform", "LinearQuadratic"])
+def test_scheduler_matches_golden_and_closed_form(golden_dir, sampler):
+    g = torch.load(os.path.join(golden_dir, "scheduler.pt"))
+    grid = rb.uniform_timesteps(20) if sampler == "Uniform" else rb.linear_quadratic_timesteps(20)
+    torch.testing.assert_close(grid, g[sampler + "_timesteps"], rtol=0, atol=1e-7)
+    lat, v = g["lat"], g["v"]
+    torch.testing.assert_close(rb.rf_step(grid, v, grid[3], lat), g[sampler + "_global"], rtol=0, atol=1e-7)
+    tt = g[sampler + "_pertoken_t"]
+    torch.testing.assert_close(rb.rf_step(grid, v, tt, lat), g[sampler + "_pertoken"], rtol=0, atol=1e-7)
+    # closed form of the reference's tests/test_scheduler.py:17-96
+    for i, t in enumerate(grid):
+        nxt = grid[i + 1] if i < len(grid) - 1 else 0.0
+        torch.testing.assert_close(rb.rf_step(grid, v, t, lat), lat - (t - nxt) * v, rtol=0, atol=1e-6)
+        tok = torch.full((2, 64), float(t))
+        tok[:, 0] = 0.0
+        got = rb.rf_step(grid, v, tok, lat)
+        torch.testing.assert_close(got[:, 1:], (lat - (t - nxt) * v)[:, 1:], rtol=0, atol=1e-6)
+        torch.testing.assert_close(got[:, 0], lat[:, 0], rtol=0, atol=1e-6)
+
+
+def test_rf_noise_and_target():
+    g = torch.Generator().manual_seed(0)
+    x0, n = torch.randn(2, 5, 4, generator=g), torch.randn(2, 5, 4, generator=g)
+    t = torch.tensor([0.25, 0.9])
+    xt = rb.rf_add_noise(x0, n, t)
+    torch.testing.assert_close(xt, (1 - t)[:, None, None] * x0 + t[:, None, None] * n)
+    torch.testing.assert_close(rb.rf_velocity_target(x0, n, t), n - x0)
+    # d x_t / dt == velocity target
+    torch.testing.assert_close((rb.rf_add_noise(x0, n, t + 1e-3) - xt) / 1e-3, n - x0, rtol=1e-2, atol=1e-3)
+
+
+@pytest.mark.skipif(not ref_import.available(), reason="reference tree not mounted")
+def test_bit_equal_to_live_reference(golden_dir):
+    """Tier two == tier one, bit for bit, same process / same BLAS (fp32 CPU), and bf16 flow."""
+    import make_golden as mg
+    ns = ref_import.load()
+    g, P, batch, t = _tiny(golden_dir)
+    for dtype in (torch.float32, torch.bfloat16):
+        Pd = {k: (v if "lora_" in k else v.to(dtype)) for k, v in P.items()}
+        model = mg.build_reference_model(ns, g["cfg"], g["case"]["lora_rank"], Pd)
+        if dtype == torch.bfloat16:
+            model = model.to(torch.bfloat16)
+            for n_, p_ in model.named_parameters():
+                if "lora_" in n_:
+                    p_.data = Pd[n_.replace("base_model.model.", "")].clone()  # adapters stay fp32 (peft)
+        rl, ro, rg = mg.reference_loss_and_grads(ns, model, g["cfg"], batch, t)
+        ol, oo, og = _oracle_loss_grads(Pd, g["cfg"], batch, t)
+        assert torch.equal(ro, oo), dtype
+        assert torch.equal(rl, ol), dtype
+        assert set(rg) == set(og)
+        for k in rg:
+            assert torch.equal(rg[k], og[k]), (dtype, k)
+        assert ol.dtype == dtype
+
+
+@pytest.mark.skipif(not ref_import.available(), reason="reference tree not mounted")
+def test_reference_train_step_rng_path(golden_dir):
+    """The reference's train_step (training.py:94-166) == oracle once its two random draws are replayed."""
+    import make_golden as mg
+    ns = ref_import.load()
+    tr = ref_import.load_training()
+    g, P, batch, _ = _tiny(golden_dir)
+    model = mg.build_reference_model(ns, g["cfg"], g["case"]["lora_rank"], P)
+
+    class Cfg:
+        rf_log_normal_mu, rf_log_normal_sigma = -0.5, 1.0
+        rf_quantile_min, rf_quantile_max = 0.005, 0.999
+        transformer_loss_weight = 1.0
+    torch.manual_seed(11)
+    loss, _, _, _ = tr.train_step(model, {k: batch[k] for k in ("latents", "ref_image_latents", "pose_latents")},
+                                  ns.RectifiedFlowScheduler(), ns.SymmetricPatchifier(patch_size=1), Cfg(),
+                                  batch["prompt_embeds"], batch["prompt_mask"], device=torch.device("cpu"))
+    torch.manual_seed(11)
+    raw = torch.distributions.LogNormal(torch.tensor(-0.5), torch.tensor(1.0)).sample((2,))
+    t_raw = raw / (1 + raw)
+    t = t_raw.clamp(min=float(torch.quantile(t_raw, 0.005)), max=float(torch.quantile(t_raw, 0.999)))
+    noise = torch.randn_like(rb.patchify(batch["latents"])[0])  # strided like the reference's tokens
+    ol, _ = rb.train_step_loss(P, g["cfg"], batch["latents"], batch["ref_image_latents"], batch["pose_latents"],
+                               batch["prompt_embeds"], batch["prompt_mask"], t, noise)
+    assert torch.equal(loss.detach(), ol.detach())
