@@ -1,0 +1,126 @@
+/* b200ltx.h — C ABI of libb200ltx.so: the sm_100a kernels behind the LTX-Video-2B transformer
+ * block forward/backward (the hot path of lusinlu/Video-Generation-for-Human-Avatars).
+ *
+ * The reference is 100 % Python and owns no FFI: its "binding surface" for this path is the
+ * nn.Module / attention-processor protocol (ltx_video/models/transformers/attention.py:532-552,
+ * 660-718, 935-955).  Each entry point below replaces the library kernels PyTorch launches for the
+ * cited reference lines; the ctypes stub a maintainer adds is shown in INTEGRATION.md and lives in
+ * video-generation-for-human-avatars_b200/lib.py.
+ *
+ * Conventions
+ *   - plain pointers + sizes only; every pointer is DEVICE memory owned by the caller.  The
+ *     library never allocates, frees or retains device memory.
+ *   - bf16 tensors are row-major with an explicit row pitch `ld*` in ELEMENTS; pointers must be
+ *     16-byte aligned and pitches multiples of 8 elements.
+ *   - all work is enqueued on `stream` (a cudaStream_t passed as void*); no implicit sync.
+ *   - return 0 on success; < 0 = argument / shape / alignment contract violation (nothing was
+ *     launched); > 0 = cudaError_t of the launch.  b200_last_error() gives a thread-local message.
+ *   - there is NO CPU fallback: on a non-sm_100 device b200_device_check() fails and launches
+ *     return cudaErrorNoKernelImageForDevice.
+ */
+#ifndef B200LTX_H_
+#define B200LTX_H_
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+int b200_version(void);
+const char* b200_last_error(void);
+int b200_device_check(void);
+
+/* GEMM epilogue selector for b200_gemm_bf16 */
+#define B200_EPI_NONE 0
+#define B200_EPI_GELU 1      /* out = gelu_tanh(acc + bias); if aux != NULL the bf16 pre-activation is stored there */
+#define B200_EPI_GELU_GRAD 2 /* out = acc * gelu_tanh'(aux) */
+
+/* C[M,N] = epi( A * B^T (+ A2 * B2^T) ), bf16 operands, fp32 accumulation in TMEM (tcgen05).
+ *   A : [M,K] row-major (a_rows_are_k = 0) or [K,M] row-major (a_rows_are_k = 1)
+ *   B : [N,K] row-major (b_rows_are_k = 0, the nn.Linear weight layout) or [K,N] (b_rows_are_k = 1)
+ *   A2/B2/K2 : optional second operand pair with the same layouts, accumulated into the same tile
+ *              (the LoRA up-projection (s x A^T) B^T of peft lora.Linear; K2 = 0 to disable)
+ *   epilogue order: + bias[N] -> GELU / GELU' -> * gate[row / rows_per_gate, N] -> + res[M,N]
+ *   C is bf16 (out_is_f32 = 0) or fp32 (1).  block_n = 0 picks the tile width (64/128/256).
+ * Replaces: nn.Linear (cuBLASLt) + bias + F.gelu + AdaLN gate + residual adds of
+ *   attention.py:996-1014,1089,265-268,285,305-308,1238-1263; transformer3d.py:470,494-499,561;
+ *   and, with the [K,*] layouts, the dgrad / wgrad GEMMs autograd runs for them (training.py:203). */
+int b200_gemm_bf16(const void* A, int64_t lda, int a_rows_are_k, const void* B, int64_t ldb,
+                   int b_rows_are_k, const void* A2, int64_t lda2, const void* B2, int64_t ldb2,
+                   int K2, void* C, int64_t ldc, int out_is_f32, int M, int N, int K, int epilogue,
+                   const void* bias, const void* gate, int64_t gate_stride, int64_t rows_per_gate,
+                   const void* res, int64_t ldres, void* aux, int64_t ldaux, int block_n,
+                   void* stream);
+
+/* Flash attention forward, head_dim 64, non-causal.  q/k/v/o token-major [B*N, ld], head h in
+ * columns [64h, 64h+64).  key_bias: optional fp32 [B,Nk] additive score bias (the -10000 mask bias).
+ * lse: optional fp32 [B,H,Nq] log-sum-exp for the backward.
+ * Replaces F.scaled_dot_product_attention, attention.py:1057-1064 (+ mask prep :981-989). */
+int b200_fa_fwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,
+                void* o, int64_t ldo, float* lse, const float* key_bias, int B, int H, int Nq, int Nk,
+                int head_dim, float scale, void* stream);
+
+/* delta[b,h,q] = sum_d o * do  (backward pre-pass). */
+int b200_attn_delta(const void* o, int64_t ldo, const void* dout, int64_t lddo, float* delta, int B,
+                    int H, int Nq, void* stream);
+
+/* Flash attention backward.  dq_accum is fp32 [B*Nq, lddq] and MUST be zeroed by the caller (key-tile
+ * CTAs reduce into it with red.global.add); dk/dv are bf16.  Replaces the SDPA backward autograd
+ * runs under training.py:203. */
+int b200_fa_bwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,
+                const void* dout, int64_t lddo, const float* lse, const float* delta,
+                const float* key_bias, float* dq_accum, int64_t lddq, void* dk, int64_t lddk, void* dv,
+                int64_t lddv, int B, int H, int Nq, int Nk, int head_dim, float scale, void* stream);
+
+/* y = norm(x) * (1 + scale[b]) + shift[b]; RMSNorm (layernorm = 0) or LayerNorm (1), no affine.
+ * scale/shift: bf16 rows of D, one per `rows_per_mod` consecutive rows, `mod_stride` elements apart
+ * (pointers into the [B,6,D] AdaLN tensor); either may be NULL.
+ * Replaces diffusers RMSNorm + AdaLN modulate, attention.py:223-236, 288-290; norm_out + modulate,
+ * transformer3d.py:554-559. */
+int b200_norm_mod_fwd(const void* x, int64_t ldx, void* y, int64_t ldy, const void* scale,
+                      const void* shift, int64_t mod_stride, int64_t rows, int D,
+                      int64_t rows_per_mod, float eps, int layernorm, void* stream);
+/* dx = dres + d(norm_mod)/dx applied to dy  (dres may be NULL). */
+int b200_norm_mod_bwd(const void* dy, int64_t lddy, const void* x, int64_t ldx, const void* scale,
+                      int64_t mod_stride, const void* dres, int64_t lddres, void* dx, int64_t lddx,
+                      int64_t rows, int D, int64_t rows_per_mod, float eps, int layernorm,
+                      void* stream);
+
+/* q_norm / k_norm (RMSNorm over the full width with weight) followed by interleaved-pair RoPE.
+ * cos/sin: bf16 [rows, D] tables (NULL for attn2: no RoPE).  q and k rows are independent row sets.
+ * Replaces attention.py:996-1012 (q_norm/k_norm) and apply_rotary_emb :917-932. */
+int b200_qknorm_rope_fwd(const void* xq, int64_t ldq, const void* xk, int64_t ldk, const void* wq,
+                         const void* wk, const void* cos_t, const void* sin_t, int64_t ldcs, void* oq,
+                         int64_t ldoq, void* ok, int64_t ldok, int64_t rows_q, int64_t rows_k, int D,
+                         float eps, void* stream);
+int b200_qknorm_rope_bwd(const void* dq, int64_t lddq, int dq_is_f32, const void* dk, int64_t lddk,
+                         int dk_is_f32, const void* xq, int64_t ldq, const void* xk, int64_t ldk,
+                         const void* wq, const void* wk, const void* cos_t, const void* sin_t,
+                         int64_t ldcs, void* oq, int64_t ldoq, void* ok, int64_t ldok, int64_t rows_q,
+                         int64_t rows_k, int D, float eps, void* stream);
+
+/* Rectified flow: x_t = (1-t) x0 + t eps, v = eps - x0 (either output may be NULL); t fp32 [batch].
+ * Replaces RectifiedFlowScheduler.add_noise / build_velocity_target, rf.py:376-386, 400-426. */
+int b200_rf_noise(const void* x0, const void* noise, const float* t, void* xt, void* v, int64_t batch,
+                  int64_t per_sample, void* stream);
+/* loss = mean((out - target)^2); dout = grad_scale * 2 (out - target) / numel (dout may be NULL).
+ * Replaces F.mse_loss + its backward, training.py:159-160, 203. */
+int64_t b200_rf_loss_workspace_bytes(void);
+int b200_rf_loss(const void* out, const void* target, void* dout, float* loss, int64_t numel,
+                 float grad_scale, void* workspace, int64_t workspace_bytes, void* stream);
+
+/* In-place conditioning lerp on tokens [B,N,C]: frame 0 <- lerp(tok, ref, w_ref), frames >= 1 <-
+ * lerp(tok, pose, w_pose); ref [B,C,1,HW], pose [B,C,F,HW].  Replaces transformer3d.py:447-466. */
+int b200_lerp_condition(void* tokens, const void* ref, const void* pose, int B, int N, int C, int HW,
+                        float w_ref, float w_pose, void* stream);
+
+/* out[m,:] = x[m,:] * g[m / rows_per_mod,:]  (AdaLN gate applied to an incoming gradient). */
+int b200_rowscale(const void* x, int64_t ldx, const void* g, int64_t gstride, void* out, int64_t ldo,
+                  int64_t rows, int D, int64_t rows_per_mod, void* stream);
+/* out[n] = sum_m x[m,n]  (bias gradients of the trainable caption projection). */
+int b200_colsum(const void* x, int64_t ldx, float* out, int64_t rows, int N, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200LTX_H_ */

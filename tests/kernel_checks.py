@@ -1,0 +1,341 @@
+"""Per-kernel parity checks (CUDA path through the C ABI vs a plain torch fp32 reference of the
+same op).  Used by tests/test_kernels_gpu.py and by tools/gpu_selftest.py (which runs each group
+in its own process so that one faulting kernel cannot hide the others)."""
+import math
+
+import torch
+import torch.nn.functional as F
+
+BF16 = torch.bfloat16
+
+
+def _rel(a, b):
+    a, b = a.float(), b.float()
+    return float((a - b).norm() / (b.norm() + 1e-12))
+
+
+def _maxabs(a, b):
+    return float((a.float() - b.float()).abs().max())
+
+
+def _assert_close(name, got, ref, rel=1e-2, info=""):
+    r, m = _rel(got, ref), _maxabs(got, ref)
+    ok = r <= rel and math.isfinite(r)
+    print(f"  {name:46s} rel={r:.3e} maxabs={m:.3e} {'ok' if ok else 'FAIL'} {info}", flush=True)
+    assert ok, f"{name}: rel {r} > {rel} (maxabs {m}) {info}"
+
+
+def _randn(*shape, seed=0, scale=1.0):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    return (torch.randn(*shape, generator=g) * scale).to("cuda", BF16)
+
+
+# --------------------------------------------------------------------------------------------
+def check_gemm_layouts():
+    from b200_ltx import ops
+    cases = [(128, 256, 64), (256, 512, 256), (200, 136, 72), (96, 64, 128), (640, 2048, 512), (1, 2048, 256),
+             (6144 // 4, 768, 1024)]
+    for bn in (0, 64, 128, 256):
+        for (M, N, K) in cases:
+            for a_k in (False, True):
+                if a_k and M % 8:
+                    continue
+                for b_k in (False, True):
+                    a = _randn(M, K, seed=1)
+                    b = _randn(N, K, seed=2)
+                    ref = a.float() @ b.float().t()
+                    aa = a.t().contiguous() if a_k else a
+                    bb = b.t().contiguous() if b_k else b
+                    out = ops.gemm(aa, bb, a_rows_are_k=a_k, b_rows_are_k=b_k, block_n=bn)
+                    _assert_close(f"gemm {M}x{N}x{K} bn={bn} aK={int(a_k)} bK={int(b_k)}", out, ref, 6e-3)
+    torch.cuda.synchronize()
+
+
+def check_gemm_epilogues():
+    from b200_ltx import ops
+    M, N, K, K2 = 384, 512, 256, 64
+    a, b = _randn(M, K, seed=1), _randn(N, K, seed=2, scale=0.05)
+    a2, b2 = _randn(M, K2, seed=3), _randn(N, K2, seed=4, scale=0.05)
+    bias = _randn(N, seed=5)
+    gate = _randn(3, 6 * N, seed=6)[:, 2 * N:3 * N]          # strided view, like ada[:, 2]
+    res = _randn(M, N, seed=7)
+    base = a.float() @ b.float().t()
+    _assert_close("gemm dual-K", ops.gemm(a, b, a2=a2, b2=b2), base + a2.float() @ b2.float().t(), 6e-3)
+    _assert_close("gemm bias", ops.gemm(a, b, bias=bias), base + bias.float(), 6e-3)
+    ref = gate.float().repeat_interleave(128, 0) * (base + bias.float()) + res.float()
+    _assert_close("gemm bias+gate+res", ops.gemm(a, b, bias=bias, gate=gate, rows_per_gate=128, res=res), ref, 6e-3)
+    pre = torch.empty(M, N, device="cuda", dtype=BF16)
+    act = ops.gemm(a, b, bias=bias, epilogue=ops.EPI_GELU, aux=pre)
+    pre_ref = (base + bias.float())
+    _assert_close("gemm gelu pre-activation", pre, pre_ref, 6e-3)
+    _assert_close("gemm gelu", act, F.gelu(pre.float(), approximate="tanh"), 6e-3)
+    h = pre.float().requires_grad_(True)
+    F.gelu(h, approximate="tanh").sum().backward()
+    _assert_close("gemm gelu'", ops.gemm(a, b, epilogue=ops.EPI_GELU_GRAD, aux=pre), base * h.grad, 8e-3)
+    o32 = ops.gemm(a, b, out_dtype=torch.float32)
+    _assert_close("gemm fp32 out", o32, base, 1e-5 + 6e-3)
+    acc = res.clone()
+    ops.gemm(a, b, out=acc, res=acc)
+    _assert_close("gemm accumulate in place", acc, base + res.float(), 6e-3)
+    # column-slice output + row-strided input (packed qkv buffers)
+    buf = torch.zeros(M, 3 * N, device="cuda", dtype=BF16)
+    ops.gemm(a, b, out=buf[:, N:2 * N], bias=bias)
+    _assert_close("gemm strided out", buf[:, N:2 * N], base + bias.float(), 6e-3)
+    assert float(buf[:, :N].abs().max()) == 0 and float(buf[:, 2 * N:].abs().max()) == 0
+    wide = _randn(M, 3 * K, seed=9)
+    _assert_close("gemm strided in", ops.gemm(wide[:, K:2 * K], b), wide[:, K:2 * K].float() @ b.float().t(), 6e-3)
+    # per-row gate (per-token timesteps)
+    g2 = _randn(M, N, seed=10)
+    _assert_close("gemm per-row gate", ops.gemm(a, b, gate=g2, rows_per_gate=1), g2.float() * base, 6e-3)
+    torch.cuda.synchronize()
+
+
+def check_linear_fn():
+    """LinearFn / FeedForwardFn forward + backward vs autograd on the same math in fp32."""
+    from b200_ltx import ops
+    M, K, N, r, s = 320, 256, 512, 32, 0.5
+    x = _randn(M, K, seed=1).requires_grad_(True)
+    W = _randn(N, K, seed=2, scale=0.06).requires_grad_(True)
+    b = _randn(N, seed=3, scale=0.1).requires_grad_(True)
+    A = (_randn(r, K, seed=4, scale=0.06).float()).requires_grad_(True)
+    B = (_randn(N, r, seed=5, scale=0.06).float()).requires_grad_(True)
+    gate = _randn(2, N, seed=6)
+    res = _randn(M, N, seed=7).requires_grad_(True)
+    dy = _randn(M, N, seed=8)
+    y = ops.LinearFn.apply(x, W, b, A, B, s, gate, 160, res)
+    y.backward(dy)
+    xr, Wr, br, Ar, Br, rr = [t.detach().float().requires_grad_(True) for t in (x, W, b, A, B, res)]
+    yr = gate.float().repeat_interleave(160, 0) * (xr @ Wr.t() + br + s * (xr @ Ar.t()) @ Br.t()) + rr
+    yr.backward(dy.float())
+    _assert_close("LinearFn y", y, yr, 8e-3)
+    for nm, g, gr in (("dx", x.grad, xr.grad), ("dW", W.grad, Wr.grad), ("db", b.grad, br.grad),
+                      ("dA", A.grad, Ar.grad), ("dB", B.grad, Br.grad), ("dres", res.grad, rr.grad)):
+        _assert_close("LinearFn " + nm, g, gr, 1.5e-2)
+    # feed-forward
+    Dff = 1024
+    W1 = _randn(Dff, K, seed=11, scale=0.06).requires_grad_(True)
+    b1 = _randn(Dff, seed=12, scale=0.1).requires_grad_(True)
+    W2 = _randn(K, Dff, seed=13, scale=0.03).requires_grad_(True)
+    b2 = _randn(K, seed=14, scale=0.1).requires_grad_(True)
+    x2 = _randn(M, K, seed=15).requires_grad_(True)
+    gate2 = _randn(2, K, seed=16)
+    res2 = _randn(M, K, seed=17).requires_grad_(True)
+    dy2 = _randn(M, K, seed=18)
+    y2 = ops.FeedForwardFn.apply(x2, W1, b1, W2, b2, gate2, 160, res2)
+    y2.backward(dy2)
+    refs = [t.detach().float().requires_grad_(True) for t in (x2, W1, b1, W2, b2, res2)]
+    xr, W1r, b1r, W2r, b2r, rr = refs
+    yr = gate2.float().repeat_interleave(160, 0) * (F.gelu(xr @ W1r.t() + b1r, approximate="tanh") @ W2r.t() + b2r) + rr
+    yr.backward(dy2.float())
+    _assert_close("FeedForwardFn y", y2, yr, 8e-3)
+    for nm, t, tr in zip(("dx", "dW1", "db1", "dW2", "db2", "dres"), (x2, W1, b1, W2, b2, res2), refs):
+        _assert_close("FeedForwardFn " + nm, t.grad, tr.grad, 1.5e-2)
+    torch.cuda.synchronize()
+
+
+def check_norm_mod():
+    from b200_ltx import ops
+    for (rows, D, rpm, ln) in [(96, 256, 48, False), (515, 2048, 515, False), (130, 2048, 1, False),
+                               (96, 256, 96, True), (257, 2048, 257, True), (64, 1024, 16, False)]:
+        nb = (rows + rpm - 1) // rpm
+        x = _randn(rows, D, seed=1, scale=2.0)
+        ada = _randn(nb, 6 * D, seed=2, scale=0.3)
+        shift, scale = ada[:, :D], ada[:, D:2 * D]
+        eps = 1e-6
+        xf = x.float().requires_grad_(True)
+        if ln:
+            n = F.layer_norm(xf, (D,), None, None, eps)
+        else:
+            n = xf * torch.rsqrt(xf.pow(2).mean(-1, keepdim=True) + eps)
+        sc = scale.float().repeat_interleave(rpm, 0)[:rows]
+        sh = shift.float().repeat_interleave(rpm, 0)[:rows]
+        yr = n * (1 + sc) + sh
+        y = ops.norm_mod_fwd(x, scale, shift, rpm, eps, ln)
+        _assert_close(f"norm_mod fwd rows={rows} D={D} rpm={rpm} ln={int(ln)}", y, yr, 5e-3)
+        dy = _randn(rows, D, seed=3)
+        dres = _randn(rows, D, seed=4)
+        yr.backward(dy.float())
+        dx = ops.norm_mod_bwd(dy, x, scale, rpm, eps, ln, dres=dres)
+        _assert_close(f"norm_mod bwd rows={rows} D={D} rpm={rpm} ln={int(ln)}", dx, xf.grad + dres.float(), 6e-3)
+    torch.cuda.synchronize()
+
+
+def _rope_ref(x, cos, sin):
+    p = x.unflatten(-1, (-1, 2))
+    a, b = p.unbind(-1)
+    rot = torch.stack((-b, a), dim=-1).flatten(-2)
+    return x * cos + rot * sin
+
+
+def check_qknorm_rope():
+    from b200_ltx import ops
+    for (rq, rk, D, rope) in [(96, 96, 256, True), (300, 300, 2048, True), (200, 48, 2048, False)]:
+        packed = _randn(max(rq, rk), 3 * D, seed=1, scale=1.5)
+        xq, xk = packed[:rq, :D], packed[:rk, D:2 * D]
+        wq, wk = (1 + 0.1 * _randn(D, seed=2).float()).to(BF16), (1 + 0.1 * _randn(D, seed=3).float()).to(BF16)
+        ang = torch.rand(rq, D // 2, device="cuda") * 6.28
+        cos = ang.cos().repeat_interleave(2, -1).to(BF16) if rope else None
+        sin = ang.sin().repeat_interleave(2, -1).to(BF16) if rope else None
+        oq = torch.empty(rq, D, device="cuda", dtype=BF16)
+        ok = torch.empty(rk, D, device="cuda", dtype=BF16)
+        ops.qknorm_rope_fwd(xq, xk, wq, wk, cos, sin, oq, ok)
+        outs, leaves = [], []
+        for x, w in ((xq, wq), (xk, wk)):
+            xf = x.float().requires_grad_(True)
+            y = xf * torch.rsqrt(xf.pow(2).mean(-1, keepdim=True) + 1e-5) * w.float()
+            if rope:
+                y = _rope_ref(y, cos.float(), sin.float())
+            outs.append(y)
+            leaves.append(xf)
+        _assert_close(f"qknorm_rope fwd q rows={rq} D={D} rope={int(rope)}", oq, outs[0], 5e-3)
+        _assert_close(f"qknorm_rope fwd k rows={rk} D={D} rope={int(rope)}", ok, outs[1], 5e-3)
+        dq = torch.randn(rq, D, device="cuda")             # fp32, like the attention backward emits
+        dk = _randn(rk, D, seed=5)
+        outs[0].backward(dq)
+        outs[1].backward(dk.float())
+        gq = torch.empty(rq, D, device="cuda", dtype=BF16)
+        gk = torch.empty(rk, D, device="cuda", dtype=BF16)
+        ops.qknorm_rope_bwd(dq, dk, xq, xk, wq, wk, cos, sin, gq, gk)
+        _assert_close(f"qknorm_rope bwd q rows={rq} D={D} rope={int(rope)}", gq, leaves[0].grad, 6e-3)
+        _assert_close(f"qknorm_rope bwd k rows={rk} D={D} rope={int(rope)}", gk, leaves[1].grad, 6e-3)
+    torch.cuda.synchronize()
+
+
+def _attn_ref(q, k, v, B, H, Nq, Nk, bias, scale):
+    qh = q.float().view(B, Nq, H, 64).transpose(1, 2)
+    kh = k.float().view(B, Nk, H, 64).transpose(1, 2)
+    vh = v.float().view(B, Nk, H, 64).transpose(1, 2)
+    s = qh @ kh.transpose(-1, -2) * scale
+    if bias is not None:
+        s = s + bias.float()[:, None, None, :]
+    p = s.softmax(-1)
+    o = (p @ vh).transpose(1, 2).reshape(B * Nq, H * 64)
+    return o, torch.logsumexp(s, -1)
+
+
+ATTN_CASES = [(1, 2, 128, 128, False), (2, 4, 96, 96, False), (1, 2, 300, 300, False), (2, 4, 96, 24, True),
+              (1, 32, 512, 256, True), (1, 4, 1024, 1024, False), (2, 3, 200, 333, True)]
+
+
+def check_attention_fwd():
+    from b200_ltx import ops
+    for (B, H, Nq, Nk, use_bias) in ATTN_CASES:
+        D = H * 64
+        qkv = _randn(B * max(Nq, Nk), 3 * D, seed=1)
+        q, k, v = qkv[:B * Nq, :D], qkv[:B * Nk, D:2 * D], qkv[:B * Nk, 2 * D:]
+        bias = None
+        if use_bias:
+            bias = torch.zeros(B, Nk, device="cuda")
+            bias[:, (Nk * 2) // 3:] = -10000.0
+            bias[:, 0] = 0.5
+        o, lse = ops.fa_fwd(q, k, v, B, H, Nq, Nk, bias, 0.125)
+        oref, lref = _attn_ref(q, k, v, B, H, Nq, Nk, bias, 0.125)
+        tag = f"B={B} H={H} Nq={Nq} Nk={Nk} bias={int(use_bias)}"
+        _assert_close("fa_fwd o " + tag, o, oref, 8e-3)
+        _assert_close("fa_fwd lse " + tag, lse, lref, 1e-3)
+    # large-magnitude scores exercise the lazy rescale
+    B, H, N = 1, 2, 512
+    q, k, v = _randn(N, 128, seed=3, scale=6.0), _randn(N, 128, seed=4, scale=6.0), _randn(N, 128, seed=5)
+    o, lse = ops.fa_fwd(q, k, v, B, H, N, N, None, 0.125)
+    oref, lref = _attn_ref(q, k, v, B, H, N, N, None, 0.125)
+    _assert_close("fa_fwd o (peaked softmax)", o, oref, 1e-2)
+    _assert_close("fa_fwd lse (peaked softmax)", lse, lref, 1e-3)
+    torch.cuda.synchronize()
+
+
+def check_attention_bwd():
+    from b200_ltx import ops
+    for (B, H, Nq, Nk, use_bias) in ATTN_CASES:
+        D = H * 64
+        q, k, v = _randn(B * Nq, D, seed=1), _randn(B * Nk, D, seed=2), _randn(B * Nk, D, seed=3)
+        do = _randn(B * Nq, D, seed=4)
+        bias = None
+        if use_bias:
+            bias = torch.zeros(B, Nk, device="cuda")
+            bias[:, (Nk * 2) // 3:] = -10000.0
+        o, lse = ops.fa_fwd(q, k, v, B, H, Nq, Nk, bias, 0.125)
+        dk = torch.empty_like(k)
+        dv = torch.empty_like(v)
+        dq = ops.fa_bwd(q, k, v, o, do, lse, B, H, Nq, Nk, dk, dv, bias, 0.125)
+        qf, kf, vf = [t.float().requires_grad_(True) for t in (q, k, v)]
+        oref, _ = _attn_ref(qf, kf, vf, B, H, Nq, Nk, bias, 0.125)
+        oref.backward(do.float())
+        tag = f"B={B} H={H} Nq={Nq} Nk={Nk} bias={int(use_bias)}"
+        _assert_close("fa_bwd dq " + tag, dq, qf.grad, 1.2e-2)
+        _assert_close("fa_bwd dk " + tag, dk, kf.grad, 1.2e-2)
+        _assert_close("fa_bwd dv " + tag, dv, vf.grad, 1.2e-2)
+    torch.cuda.synchronize()
+
+
+def check_attn_core_fn():
+    from b200_ltx import ops
+    B, H, Nq = 2, 4, 96
+    D = H * 64
+    qkv = _randn(B * Nq, 3 * D, seed=1).requires_grad_(True)
+    wq = (1 + 0.1 * _randn(D, seed=2).float()).to(BF16)
+    wk = (1 + 0.1 * _randn(D, seed=3).float()).to(BF16)
+    ang = torch.rand(B * Nq, D // 2, device="cuda") * 6.28
+    cos, sin = ang.cos().repeat_interleave(2, -1).to(BF16), ang.sin().repeat_interleave(2, -1).to(BF16)
+    o = ops.AttnCoreFn.apply(qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:], wq, wk, cos, sin, None, B, H, Nq, Nq, 0.125)
+    do = _randn(B * Nq, D, seed=4)
+    o.backward(do)
+    x = qkv.detach().float().requires_grad_(True)
+
+    def nrm(t, w):
+        y = t * torch.rsqrt(t.pow(2).mean(-1, keepdim=True) + 1e-5) * w.float()
+        return _rope_ref(y, cos.float(), sin.float())
+    oref, _ = _attn_ref(nrm(x[:, :D], wq), nrm(x[:, D:2 * D], wk), x[:, 2 * D:], B, H, Nq, Nq, None, 0.125)
+    oref.backward(do.float())
+    _assert_close("AttnCoreFn o", o, oref, 8e-3)
+    _assert_close("AttnCoreFn dqkv", qkv.grad, x.grad, 1.5e-2)
+    torch.cuda.synchronize()
+
+
+def check_rf_and_misc():
+    from b200_ltx import ops
+    B, N, C = 3, 96, 128
+    x0, eps = _randn(B, N, C, seed=1), _randn(B, N, C, seed=2)
+    t = torch.tensor([0.1, 0.5, 0.93], device="cuda")
+    xt, v = ops.rf_noise(x0, eps, t)
+    tt = t[:, None, None]
+    assert torch.equal(xt, ((1 - tt) * x0 + tt * eps).to(BF16)), "rf_noise x_t must be bit-exact"
+    assert torch.equal(v, (-1.0 * x0.float() + 1.0 * eps.float()).to(BF16)), "rf_noise v must be bit-exact"
+    out = _randn(B, N, C, seed=3)
+    loss, dout = ops.rf_loss(out, v, 1.0)
+    of = out.float().requires_grad_(True)
+    lr = F.mse_loss(of, v.float())
+    lr.backward()
+    _assert_close("rf_loss value", loss, lr, 1e-5)
+    _assert_close("rf_loss grad", dout, of.grad, 4e-3)
+    # conditioning lerp: bit-exact against torch.lerp in bf16
+    Fr, H, W = 3, 4, 8
+    tok = _randn(B, Fr * H * W, C, seed=4)
+    ref = _randn(B, C, 1, H, W, seed=5)
+    pose = _randn(B, C, Fr, H, W, seed=6)
+    want = tok.clone()
+    vw = want.view(B, Fr, H, W, C).permute(0, 4, 1, 2, 3)
+    vw[:, :, 0:1] = torch.lerp(vw[:, :, 0:1], ref, 0.85)
+    vw[:, :, 1:] = torch.lerp(vw[:, :, 1:], pose[:, :, 1:], 0.5)
+    got = ops.lerp_condition_(tok.clone(), ref, pose)
+    d = _maxabs(got, want)
+    print(f"  lerp_condition maxabs diff vs torch.lerp bf16: {d:.3e}", flush=True)
+    assert d <= 2 ** -6, d  # at most one bf16 ulp of O(1) values
+    assert _rel(got, want) < 2e-3
+    x = _randn(200, 256, seed=7)
+    g = _randn(4, 6 * 256, seed=8)[:, 512:768]
+    _assert_close("rowscale", ops.rowscale(x, g, 50), x.float() * g.float().repeat_interleave(50, 0), 4e-3)
+    _assert_close("colsum", ops.colsum(x), x.float().sum(0), 1e-5)
+    torch.cuda.synchronize()
+
+
+GROUPS = {
+    "gemm_layouts": check_gemm_layouts,
+    "gemm_epilogues": check_gemm_epilogues,
+    "linear_fn": check_linear_fn,
+    "norm_mod": check_norm_mod,
+    "qknorm_rope": check_qknorm_rope,
+    "attention_fwd": check_attention_fwd,
+    "attention_bwd": check_attention_bwd,
+    "attn_core_fn": check_attn_core_fn,
+    "rf_and_misc": check_rf_and_misc,
+}

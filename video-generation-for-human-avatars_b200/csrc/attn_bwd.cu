@@ -1,0 +1,301 @@
+// attn_bwd.cu — tcgen05 / TMEM flash-attention backward, head_dim 64, non-causal (sm_100a).
+//
+// Gradient of softmax(q k^T * scale + key_bias) v with respect to q, k, v — what autograd runs
+// through F.scaled_dot_product_attention in the reference's LoRA train step
+// (training.py:203 -> attention.py:1057).  Same token-major [B*N, ld] layout as attn_fwd.cu.
+//
+// One CTA owns one 128-key tile of one head and walks over the 128-query tiles.  Everything is
+// computed transposed (keys on TMEM lanes) so that each compute thread owns one key row:
+//   S^T  = K Q^T              (128 x 128 x 64, both operands K-major)
+//   dP^T = V dO^T             (128 x 128 x 64)
+//   P^T  = exp2(S^T*c + bias - lse) ; dS^T = P^T * (dP^T - delta) * scale    -> shared memory, bf16
+//   dV  += P^T  dO            (A = P^T  K-major from smem, B = dO tile read MN-major)
+//   dK  += dS^T Q             (A = dS^T K-major,            B = Q  tile read MN-major)
+//   dQ   = dS   K             (A = the same dS^T bytes read MN-major, B = K tile read MN-major)
+// dV/dK accumulate in TMEM over the whole loop; dQ is a per-(q tile, k tile) partial that is
+// reduced across key-tile CTAs with vectorised fp32 red.global.add into a caller-zeroed buffer.
+// TMEM: S^T 128 | dP^T 128 | dV 64 | dK 64 | dQ 64 = 448 of 512 columns.
+#include "api_internal.h"
+#include "common.cuh"
+#include "tmap.h"
+
+namespace b200 {
+
+int make_tmap_tokens(CUtensorMap* out, const void* base, int B, int N, int64_t ld, int width,
+                     int box_rows);
+
+struct FaBwdParams {
+  int B, H, Nq, Nk, q_tiles;
+  const float* lse;    // [B,H,Nq]
+  const float* delta;  // [B,H,Nq]
+  const float* key_bias;
+  float* dq;  // fp32 [B*Nq, lddq], caller-zeroed
+  int64_t lddq;
+  bf16* dk;
+  int64_t lddk;
+  bf16* dv;
+  int64_t lddv;
+  float scale, scale_log2;
+};
+
+constexpr int FA_BWD_SMEM = 16384 * 2 /*K,V*/ + 2 * 32768 /*Q,dO x2*/ + 2 * 32768 /*P^T,dS^T*/ +
+                            2 * 2 * 512 /*lse, delta x2*/ + 128;
+constexpr float kLog2eB = 1.4426950408889634f;
+
+__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c),
+               "f"(d)
+               : "memory");
+}
+
+__global__ void __launch_bounds__(192, 1)
+fa_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+              const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmdO,
+              const __grid_constant__ FaBwdParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t sbase = smem_u32(smem_raw);
+  const uint32_t sK = sbase, sV = sbase + 16384, sQdO = sbase + 32768;  // stage s: Q at +s*32768, dO at +16384
+  const uint32_t sPt = sQdO + 65536, sdSt = sPt + 32768;
+  const uint32_t sStat = sdSt + 32768;  // [2 stages][lse 128 | delta 128] fp32
+  const uint32_t bar = sStat + 2048;
+  const uint32_t kv_full = bar, qd_full0 = bar + 8, qd_empty0 = bar + 24, s_full = bar + 40,
+                 pds_full = bar + 48, mma2_done = bar + 56, tmem_slot = bar + 64;
+  float* stat = reinterpret_cast<float*>(smem_raw + (sStat - sbase));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int kt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+  const int T = p.q_tiles;
+
+  if (threadIdx.x == 0) {
+    if (sbase & 1023u) {
+      printf("b200 fa_bwd: dynamic shared memory base is not 1024-byte aligned\n");
+      __trap();
+    }
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmK);
+    tma_prefetch_desc(&tmV);
+    tma_prefetch_desc(&tmdO);
+    mbar_init(kv_full, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(qd_full0 + 8 * s, 1);
+      mbar_init(qd_empty0 + 8 * s, 1);
+    }
+    mbar_init(s_full, 1);
+    mbar_init(pds_full, 128);
+    mbar_init(mma2_done, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  const uint32_t tSt = tmem_base, tdPt = tmem_base + 128, tdV = tmem_base + 256,
+                 tdK = tmem_base + 320, tdQ = tmem_base + 384;
+
+  if (warp == 0 && lane == 0) {
+    mbar_expect_tx(kv_full, 32768);
+    tma_load_3d(sK, &tmK, kv_full, h * 64, kt * 128, b);
+    tma_load_3d(sV, &tmV, kv_full, h * 64, kt * 128, b);
+    for (int i = 0; i < T; ++i) {
+      const int s = i & 1;
+      mbar_wait(qd_empty0 + 8 * s, ((i >> 1) & 1) ^ 1);
+      mbar_expect_tx(qd_full0 + 8 * s, 32768);
+      tma_load_3d(sQdO + s * 32768, &tmQ, qd_full0 + 8 * s, h * 64, i * 128, b);
+      tma_load_3d(sQdO + s * 32768 + 16384, &tmdO, qd_full0 + 8 * s, h * 64, i * 128, b);
+    }
+  } else if (warp == 1 && lane == 0) {
+    const uint32_t idesc_s = make_idesc_bf16(128, 128, 0, 0);   // K-major x K-major
+    const uint32_t idesc_kv = make_idesc_bf16(128, 64, 0, 1);   // A K-major, B MN-major
+    const uint32_t idesc_dq = make_idesc_bf16(128, 64, 1, 1);   // A MN-major, B MN-major
+    mbar_wait(kv_full, 0);
+    for (int i = 0; i < T; ++i) {
+      const int s = i & 1;
+      const uint32_t sQ = sQdO + s * 32768, sdO = sQ + 16384;
+      mbar_wait(qd_full0 + 8 * s, (i >> 1) & 1);
+      tc_fence_after();
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        umma_ss(tSt, make_smem_desc(sK + k * 32, 16, 1024), make_smem_desc(sQ + k * 32, 16, 1024),
+                idesc_s, k > 0 ? 1u : 0u);
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        umma_ss(tdPt, make_smem_desc(sV + k * 32, 16, 1024), make_smem_desc(sdO + k * 32, 16, 1024),
+                idesc_s, k > 0 ? 1u : 0u);
+      umma_commit(s_full);
+      mbar_wait(pds_full, i & 1);
+      tc_fence_after();
+#pragma unroll
+      for (int k = 0; k < 8; ++k)  // dV += P^T dO   (K = queries)
+        umma_ss(tdV, make_smem_desc(sPt + (k >> 2) * 16384 + (k & 3) * 32, 16, 1024),
+                make_smem_desc(sdO + k * 2048, 8192, 1024), idesc_kv, (i > 0 || k > 0) ? 1u : 0u);
+#pragma unroll
+      for (int k = 0; k < 8; ++k)  // dK += dS^T Q
+        umma_ss(tdK, make_smem_desc(sdSt + (k >> 2) * 16384 + (k & 3) * 32, 16, 1024),
+                make_smem_desc(sQ + k * 2048, 8192, 1024), idesc_kv, (i > 0 || k > 0) ? 1u : 0u);
+#pragma unroll
+      for (int k = 0; k < 8; ++k)  // dQ = dS K      (K = keys; A = dS^T bytes read MN-major)
+        umma_ss(tdQ, make_smem_desc(sdSt + k * 2048, 16384, 1024),
+                make_smem_desc(sK + k * 2048, 8192, 1024), idesc_dq, k > 0 ? 1u : 0u);
+      umma_commit(qd_empty0 + 8 * s);
+      umma_commit(mma2_done);
+    }
+  } else if (warp >= 2) {
+    const int quad = warp & 3;
+    const int row = quad * 32 + lane;  // key row of S^T / dP^T, query row of dQ
+    const int ctid = threadIdx.x - 64;  // 0..127 among the compute threads
+    const uint32_t lane_bits = (uint32_t)(quad * 32) << 16;
+    const int key = kt * 128 + row;
+    const bool key_ok = key < p.Nk;
+    const float kbias = (p.key_bias && key_ok) ? p.key_bias[(int64_t)b * p.Nk + key] * kLog2eB : 0.f;
+    const float* lse_g = p.lse + ((int64_t)b * p.H + h) * p.Nq;
+    const float* del_g = p.delta + ((int64_t)b * p.H + h) * p.Nq;
+    for (int i = 0; i < T; ++i) {
+      const int s = i & 1;
+      const int q0 = i * 128;
+      float* st = stat + s * 256;
+      {
+        const int q = q0 + ctid;
+        st[ctid] = q < p.Nq ? lse_g[q] * kLog2eB : INFINITY;  // +inf => P = 0 for padded queries
+        st[128 + ctid] = q < p.Nq ? del_g[q] : 0.f;
+      }
+      named_bar_sync(1, 128);
+      mbar_wait(s_full, i & 1);
+      tc_fence_after();
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        uint32_t rs[32], rd[32];
+        tmem_ld32(tSt + lane_bits + c * 32, rs);
+        tmem_ld32(tdPt + lane_bits + c * 32, rd);
+        tmem_ld_wait();
+        float pv[32], ds[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const float lse2 = st[c * 32 + j], dl = st[128 + c * 32 + j];
+          float pr = exp2f(__uint_as_float(rs[j]) * p.scale_log2 + kbias - lse2);
+          if (!key_ok) pr = 0.f;
+          pv[j] = pr;
+          ds[j] = pr * (__uint_as_float(rd[j]) - dl) * p.scale;
+        }
+        const uint32_t off0 = (c >> 1) * 16384;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          const uint32_t o = off0 + sw128_off(row, (c & 1) * 4 + g);
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sPt + o),
+                       "r"(pack_bf16x2(pv[g * 8 + 0], pv[g * 8 + 1])),
+                       "r"(pack_bf16x2(pv[g * 8 + 2], pv[g * 8 + 3])),
+                       "r"(pack_bf16x2(pv[g * 8 + 4], pv[g * 8 + 5])),
+                       "r"(pack_bf16x2(pv[g * 8 + 6], pv[g * 8 + 7]))
+                       : "memory");
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sdSt + o),
+                       "r"(pack_bf16x2(ds[g * 8 + 0], ds[g * 8 + 1])),
+                       "r"(pack_bf16x2(ds[g * 8 + 2], ds[g * 8 + 3])),
+                       "r"(pack_bf16x2(ds[g * 8 + 4], ds[g * 8 + 5])),
+                       "r"(pack_bf16x2(ds[g * 8 + 6], ds[g * 8 + 7]))
+                       : "memory");
+        }
+      }
+      fence_proxy_async_smem();
+      tc_fence_before();
+      mbar_arrive(pds_full);
+      // dQ partial of this (q tile, key tile): TMEM -> fp32 atomics
+      mbar_wait(mma2_done, i & 1);
+      tc_fence_after();
+      const int q = q0 + row;
+#pragma unroll 1
+      for (int c = 0; c < 2; ++c) {
+        uint32_t r[32];
+        tmem_ld32(tdQ + lane_bits + c * 32, r);
+        tmem_ld_wait();
+        if (q < p.Nq) {
+          float* dst = p.dq + ((int64_t)b * p.Nq + q) * p.lddq + h * 64 + c * 32;
+#pragma unroll
+          for (int g = 0; g < 8; ++g)
+            red_add_v4(dst + g * 4, __uint_as_float(r[g * 4 + 0]), __uint_as_float(r[g * 4 + 1]),
+                       __uint_as_float(r[g * 4 + 2]), __uint_as_float(r[g * 4 + 3]));
+        }
+      }
+      tc_fence_before();
+    }
+    // dK, dV of this key tile
+    if (T > 0) {
+      bf16* dkr = p.dk + ((int64_t)b * p.Nk + key) * p.lddk + h * 64;
+      bf16* dvr = p.dv + ((int64_t)b * p.Nk + key) * p.lddv + h * 64;
+#pragma unroll 1
+      for (int c = 0; c < 2; ++c) {
+        uint32_t rv[32], rk[32];
+        tmem_ld32(tdV + lane_bits + c * 32, rv);
+        tmem_ld32(tdK + lane_bits + c * 32, rk);
+        tmem_ld_wait();
+        if (key_ok) {
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            uint4 u;
+            u.x = pack_bf16x2(__uint_as_float(rv[g * 8 + 0]), __uint_as_float(rv[g * 8 + 1]));
+            u.y = pack_bf16x2(__uint_as_float(rv[g * 8 + 2]), __uint_as_float(rv[g * 8 + 3]));
+            u.z = pack_bf16x2(__uint_as_float(rv[g * 8 + 4]), __uint_as_float(rv[g * 8 + 5]));
+            u.w = pack_bf16x2(__uint_as_float(rv[g * 8 + 6]), __uint_as_float(rv[g * 8 + 7]));
+            *reinterpret_cast<uint4*>(dvr + c * 32 + g * 8) = u;
+            u.x = pack_bf16x2(__uint_as_float(rk[g * 8 + 0]), __uint_as_float(rk[g * 8 + 1]));
+            u.y = pack_bf16x2(__uint_as_float(rk[g * 8 + 2]), __uint_as_float(rk[g * 8 + 3]));
+            u.z = pack_bf16x2(__uint_as_float(rk[g * 8 + 4]), __uint_as_float(rk[g * 8 + 5]));
+            u.w = pack_bf16x2(__uint_as_float(rk[g * 8 + 6]), __uint_as_float(rk[g * 8 + 7]));
+            *reinterpret_cast<uint4*>(dkr + c * 32 + g * 8) = u;
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+}  // namespace b200
+
+using namespace b200;
+
+static inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+extern "C" int b200_fa_bwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v,
+                           int64_t ldv, const void* dout, int64_t lddo, const float* lse,
+                           const float* delta, const float* key_bias, float* dq_accum, int64_t lddq,
+                           void* dk, int64_t lddk, void* dv, int64_t lddv, int B, int H, int Nq, int Nk,
+                           int head_dim, float scale, void* stream) {
+  if (!(q && k && v && dout && lse && delta && dq_accum && dk && dv)) return arg_error("fa_bwd: null pointer");
+  if (head_dim != 64) return arg_error("fa_bwd: only head_dim 64 is built (LTXV-2B: 32 heads x 64)");
+  if (B < 0 || H <= 0 || Nq < 0 || Nk < 0) return arg_error("fa_bwd: bad shape");
+  if (B == 0 || Nk == 0) return 0;
+  if (ldq % 8 || ldk % 8 || ldv % 8 || lddo % 8 || lddk % 8 || lddv % 8 || lddq % 4 || !al16(q) ||
+      !al16(k) || !al16(v) || !al16(dout) || !al16(dq_accum) || !al16(dk) || !al16(dv))
+    return arg_error("fa_bwd: tensors must be 16-byte aligned with 16-byte-multiple pitches");
+  CUtensorMap tmQ, tmK, tmV, tmdO;
+  int rc;
+  if ((rc = make_tmap_tokens(&tmQ, q, B, Nq, ldq, H * 64, 128)) ||
+      (rc = make_tmap_tokens(&tmK, k, B, Nk, ldk, H * 64, 128)) ||
+      (rc = make_tmap_tokens(&tmV, v, B, Nk, ldv, H * 64, 128)) ||
+      (rc = make_tmap_tokens(&tmdO, dout, B, Nq, lddo, H * 64, 128)))
+    return arg_error("fa_bwd: cuTensorMapEncodeTiled failed", rc);
+  FaBwdParams p;
+  p.B = B; p.H = H; p.Nq = Nq; p.Nk = Nk;
+  p.q_tiles = (Nq + 127) / 128;
+  p.lse = lse; p.delta = delta; p.key_bias = key_bias;
+  p.dq = dq_accum; p.lddq = lddq;
+  p.dk = (bf16*)dk; p.lddk = lddk; p.dv = (bf16*)dv; p.lddv = lddv;
+  p.scale = scale; p.scale_log2 = scale * kLog2eB;
+  static bool attr_set = false;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(fa_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_BWD_SMEM) != cudaSuccess)
+      return launch_status("fa_bwd: cudaFuncSetAttribute");
+    attr_set = true;
+  }
+  dim3 grid((Nk + 127) / 128, H, B);
+  fa_bwd_kernel<<<grid, 192, FA_BWD_SMEM, (cudaStream_t)stream>>>(tmQ, tmK, tmV, tmdO, p);
+  return launch_status("fa_bwd");
+}

@@ -72,7 +72,7 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
 }
 // Bounded wait: a protocol bug must trap (context error) rather than hang the GPU.
 #ifndef B200_WAIT_TIMEOUT_CYCLES
-#define B200_WAIT_TIMEOUT_CYCLES (8000000000ll)
+#define B200_WAIT_TIMEOUT_CYCLES (4000000000ll)
 #endif
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;

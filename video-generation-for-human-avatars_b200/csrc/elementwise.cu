@@ -1,0 +1,646 @@
+// elementwise.cu — the HBM-bound kernels of the LTXV block path (sm_100a).
+//
+// All kernels are one-pass: a warp owns a row of D <= 2048 bf16 channels in registers
+// (8 x 16-byte vector loads per lane), reduces with warp shuffles and writes once.
+//
+//   rmsnorm_mod fwd/bwd   norm1/norm2 (RMSNorm, no affine, eps 1e-6) + AdaLN-single modulation
+//                         reference: attention.py:223-236, 288-290; LayerNorm flavour for the
+//                         output head, transformer3d.py:554-559
+//   qknorm_rope fwd/bwd   q_norm/k_norm (RMSNorm over the full width, affine, eps 1e-5) + 3-D RoPE
+//                         reference: attention.py:996-1012, 917-932
+//   rf_noise / rf_loss    x_t, velocity target, MSE and dLoss/dOut   (rf.py:376-426, training.py:138-164)
+//   lerp_condition        in-place ref/pose lerp on the token tensor (transformer3d.py:447-466)
+//   rowscale, colsum, attn_delta, cvt helpers
+#include "api_internal.h"
+#include "common.cuh"
+
+namespace b200 {
+
+constexpr int kMaxChunks = 8;  // 8 chunks x 32 lanes x 8 elements = 2048 channels
+
+struct Row8 {
+  float v[8];
+};
+
+__device__ __forceinline__ Row8 ld_bf16x8(const bf16* p) {
+  uint4 u = *reinterpret_cast<const uint4*>(p);
+  Row8 r;
+  r.v[0] = bf16_lo(u.x); r.v[1] = bf16_hi(u.x);
+  r.v[2] = bf16_lo(u.y); r.v[3] = bf16_hi(u.y);
+  r.v[4] = bf16_lo(u.z); r.v[5] = bf16_hi(u.z);
+  r.v[6] = bf16_lo(u.w); r.v[7] = bf16_hi(u.w);
+  return r;
+}
+__device__ __forceinline__ Row8 ld_f32x8(const float* p) {
+  float4 a = *reinterpret_cast<const float4*>(p);
+  float4 b = *reinterpret_cast<const float4*>(p + 4);
+  Row8 r;
+  r.v[0] = a.x; r.v[1] = a.y; r.v[2] = a.z; r.v[3] = a.w;
+  r.v[4] = b.x; r.v[5] = b.y; r.v[6] = b.z; r.v[7] = b.w;
+  return r;
+}
+__device__ __forceinline__ void st_bf16x8(bf16* p, const Row8& r) {
+  uint4 u;
+  u.x = pack_bf16x2(r.v[0], r.v[1]);
+  u.y = pack_bf16x2(r.v[2], r.v[3]);
+  u.z = pack_bf16x2(r.v[4], r.v[5]);
+  u.w = pack_bf16x2(r.v[6], r.v[7]);
+  *reinterpret_cast<uint4*>(p) = u;
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// ---------------------------------------------------------------------------------------------
+// y = norm(x) * (1 + scale[b]) + shift[b]     (ln = 0: RMSNorm, ln = 1: LayerNorm, no affine)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) norm_mod_fwd_kernel(
+    const bf16* __restrict__ x, int64_t ldx, bf16* __restrict__ y, int64_t ldy,
+    const bf16* __restrict__ scale, const bf16* __restrict__ shift, int64_t mod_stride,
+    int64_t rows, int D, int64_t rows_per_mod, float eps, int ln) {
+  int64_t row = (int64_t)blockIdx.x * 4 + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  int lane = threadIdx.x & 31;
+  const bf16* xr = x + row * ldx;
+  Row8 xv[kMaxChunks];
+  float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+  for (int c = 0; c < kMaxChunks; ++c) {
+    int col = (c * 32 + lane) * 8;
+    if (col < D) {
+      xv[c] = ld_bf16x8(xr + col);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { s1 += xv[c].v[i]; s2 += xv[c].v[i] * xv[c].v[i]; }
+    }
+  }
+  s2 = warp_sum(s2);
+  float mean = 0.f, rstd;
+  if (ln) {
+    s1 = warp_sum(s1);
+    mean = s1 / D;
+    float var = fmaxf(s2 / D - mean * mean, 0.f);
+    rstd = rsqrtf(var + eps);
+  } else {
+    rstd = rsqrtf(s2 / D + eps);
+  }
+  int64_t mb = row / rows_per_mod;
+  const bf16* sc = scale ? scale + mb * mod_stride : nullptr;
+  const bf16* sh = shift ? shift + mb * mod_stride : nullptr;
+  bf16* yr = y + row * ldy;
+#pragma unroll
+  for (int c = 0; c < kMaxChunks; ++c) {
+    int col = (c * 32 + lane) * 8;
+    if (col < D) {
+      Row8 o;
+      Row8 a, b;
+      if (sc) a = ld_bf16x8(sc + col);
+      if (sh) b = ld_bf16x8(sh + col);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        float n = (xv[c].v[i] - mean) * rstd;
+        if (sc) n *= (1.f + a.v[i]);
+        if (sh) n += b.v[i];
+        o.v[i] = n;
+      }
+      st_bf16x8(yr + col, o);
+    }
+  }
+}
+
+// dx = dres + rstd * (g - mean(g) [ln] - xhat * mean(g * xhat)),   g = dy * (1 + scale)
+__global__ void __launch_bounds__(128) norm_mod_bwd_kernel(
+    const bf16* __restrict__ dy, int64_t lddy, const bf16* __restrict__ x, int64_t ldx,
+    const bf16* __restrict__ scale, int64_t mod_stride, const bf16* __restrict__ dres,
+    int64_t lddres, bf16* __restrict__ dx, int64_t lddx, int64_t rows, int D,
+    int64_t rows_per_mod, float eps, int ln) {
+  int64_t row = (int64_t)blockIdx.x * 4 + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  int lane = threadIdx.x & 31;
+  const bf16* xr = x + row * ldx;
+  const bf16* gr = dy + row * lddy;
+  int64_t mb = row / rows_per_mod;
+  const bf16* sc = scale ? scale + mb * mod_stride : nullptr;
+  Row8 xv[kMaxChunks], gv[kMaxChunks];
+  float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+  for (int c = 0; c < kMaxChunks; ++c) {
+    int col = (c * 32 + lane) * 8;
+    if (col < D) {
+      xv[c] = ld_bf16x8(xr + col);
+      gv[c] = ld_bf16x8(gr + col);
+      if (sc) {
+        Row8 a = ld_bf16x8(sc + col);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) gv[c].v[i] *= (1.f + a.v[i]);
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { s1 += xv[c].v[i]; s2 += xv[c].v[i] * xv[c].v[i]; }
+    }
+  }
+  s2 = warp_sum(s2);
+  float mean = 0.f, rstd;
+  if (ln) {
+    s1 = warp_sum(s1);
+    mean = s1 / D;
+    rstd = rsqrtf(fmaxf(s2 / D - mean * mean, 0.f) + eps);
+  } else {
+    rstd = rsqrtf(s2 / D + eps);
+  }
+  float gsum = 0.f, gx = 0.f;
+#pragma unroll
+  for (int c = 0; c < kMaxChunks; ++c) {
+    int col = (c * 32 + lane) * 8;
+    if (col < D) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        float xh = (xv[c].v[i] - mean) * rstd;
+        xv[c].v[i] = xh;
+        gsum += gv[c].v[i];
+        gx += gv[c].v[i] * xh;
+      }
+    }
+  }
+  gx = warp_sum(gx) / D;
+  gsum = ln ? warp_sum(gsum) / D : 0.f;
+  bf16* outr = dx + row * lddx;
+  const bf16* rr = dres ? dres + row * lddres : nullptr;
+#pragma unroll
+  for (int c = 0; c < kMaxChunks; ++c) {
+    int col = (c * 32 + lane) * 8;
+    if (col < D) {
+      Row8 o, r;
+      if (rr) r = ld_bf16x8(rr + col);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        float d = rstd * (gv[c].v[i] - gsum - xv[c].v[i] * gx);
+        if (rr) d += r.v[i];
+        o.v[i] = d;
+      }
+      st_bf16x8(outr + col, o);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// q/k RMSNorm (affine) + RoPE.  One warp per (row, tensor).  cos/sin may be null (attn2).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) qknorm_rope_fwd_kernel(
+    const bf16* __restrict__ xq, int64_t ldq, const bf16* __restrict__ xk, int64_t ldk,
+    const bf16* __restrict__ wq, const bf16* __restrict__ wk, const bf16* __restrict__ cosp,
+    const bf16* __restrict__ sinp, int64_t ldcs, bf16* __restrict__ oq, int64_t ldoq,
+    bf16* __restrict__ ok, int64_t ldok, int64_t rows_q, int64_t rows_k, int D, float eps) {
+  int64_t w = (int64_t)blockIdx.x * 4 + (threadIdx.x >> 5);
+  if (w >= rows_q + rows_k) return;
+  bool is_k = w >= rows_q;
+  int64_t row = is_k ? w - rows_q : w;
+  const bf16* xr = is_k ? xk + row * ldk : xq + row * ldq;
+  const bf16* wt = is_k ? wk : wq;
+  bf16* outr = is_k ? ok + row * ldok : oq + row * ldoq;
+  int lane = threadIdx.x & 31;
+  Row8 xv[kMaxChunks];
+  float s2 = 0.f;
+#pragma unroll
+  for (int c = 0; c < kMaxChunks; ++c) {
+    int col = (c * 32 + lane) * 8;
+    if (col < D) {
+      xv[c] = ld_bf16x8(xr + col);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) s2 += xv[c].v[i] * xv[c].v[i];
+    }
+  }
+  float rstd = rsqrtf(warp_sum(s2) / D + eps);
+#pragma unroll
+  for (int c = 0; c < kMaxChunks; ++c) {
+    int col = (c * 32 + lane) * 8;
+    if (col < D) {
+      Row8 wv = ld_bf16x8(wt + col), o;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) xv[c].v[i] = xv[c].v[i] * rstd * wv.v[i];
+      if (cosp) {
+        Row8 cv = ld_bf16x8(cosp + row * ldcs + col), sv = ld_bf16x8(sinp + row * ldcs + col);
+#pragma unroll
+        for (int i = 0; i < 8; i += 2) {
+          float a = xv[c].v[i], b = xv[c].v[i + 1];
+          o.v[i] = a * cv.v[i] - b * sv.v[i];
+          o.v[i + 1] = b * cv.v[i + 1] + a * sv.v[i + 1];
+        }
+      } else {
+        o = xv[c];
+      }
+      st_bf16x8(outr + col, o);
+    }
+  }
+}
+
+// gradient wrt the pre-norm projections.  dq/dk may be fp32 (attention backward accumulates dq in
+// fp32) or bf16.  dx = rstd * (w*dy - xhat * mean(w*dy*xhat)),  dy = RoPE^T(dout)
+__global__ void __launch_bounds__(128) qknorm_rope_bwd_kernel(
+    const void* __restrict__ dq, int64_t lddq, int dq_f32, const void* __restrict__ dk, int64_t lddk,
+    int dk_f32, const bf16* __restrict__ xq, int64_t ldq, const bf16* __restrict__ xk, int64_t ldk,
+    const bf16* __restrict__ wq, const bf16* __restrict__ wk, const bf16* __restrict__ cosp,
+    const bf16* __restrict__ sinp, int64_t ldcs, bf16* __restrict__ oq, int64_t ldoq,
+    bf16* __restrict__ ok, int64_t ldok, int64_t rows_q, int64_t rows_k, int D, float eps) {
+  int64_t w = (int64_t)blockIdx.x * 4 + (threadIdx.x >> 5);
+  if (w >= rows_q + rows_k) return;
+  bool is_k = w >= rows_q;
+  int64_t row = is_k ? w - rows_q : w;
+  const bf16* xr = is_k ? xk + row * ldk : xq + row * ldq;
+  const bf16* wt = is_k ? wk : wq;
+  const void* gp = is_k ? dk : dq;
+  int64_t ldg = is_k ? lddk : lddq;
+  int g_f32 = is_k ? dk_f32 : dq_f32;
+  bf16* outr = is_k ? ok + row * ldok : oq + row * ldoq;
+  int lane = threadIdx.x & 31;
+  Row8 xv[kMaxChunks], gv[kMaxChunks];
+  float s2 = 0.f;
+#pragma unroll
+  for (int c = 0; c < kMaxChunks; ++c) {
+    int col = (c * 32 + lane) * 8;
+    if (col < D) {
+      xv[c] = ld_bf16x8(xr + col);
+      Row8 g = g_f32 ? ld_f32x8(reinterpret_cast<const float*>(gp) + row * ldg + col)
+                     : ld_bf16x8(reinterpret_cast<const bf16*>(gp) + row * ldg + col);
+      if (cosp) {
+        Row8 cv = ld_bf16x8(cosp + row * ldcs + col), sv = ld_bf16x8(sinp + row * ldcs + col);
+#pragma unroll
+        for (int i = 0; i < 8; i += 2) {
+          float a = g.v[i], b = g.v[i + 1];
+          gv[c].v[i] = a * cv.v[i] + b * sv.v[i + 1];
+          gv[c].v[i + 1] = b * cv.v[i + 1] - a * sv.v[i];
+        }
+      } else {
+        gv[c] = g;
+      }
+      Row8 wv = ld_bf16x8(wt + col);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        gv[c].v[i] *= wv.v[i];
+        s2 += xv[c].v[i] * xv[c].v[i];
+      }
+    }
+  }
+  float rstd = rsqrtf(warp_sum(s2) / D + eps);
+  float gx = 0.f;
+#pragma unroll
+  for (int c = 0; c < kMaxChunks; ++c) {
+    int col = (c * 32 + lane) * 8;
+    if (col < D) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        xv[c].v[i] *= rstd;
+        gx += gv[c].v[i] * xv[c].v[i];
+      }
+    }
+  }
+  gx = warp_sum(gx) / D;
+#pragma unroll
+  for (int c = 0; c < kMaxChunks; ++c) {
+    int col = (c * 32 + lane) * 8;
+    if (col < D) {
+      Row8 o;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) o.v[i] = rstd * (gv[c].v[i] - xv[c].v[i] * gx);
+      st_bf16x8(outr + col, o);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// rectified flow:  x_t = (1-t) x0 + t eps ;  v = eps - x0      (fp32 math, bf16 out)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) rf_noise_kernel(const bf16* __restrict__ x0,
+                                                       const bf16* __restrict__ noise,
+                                                       const float* __restrict__ t,
+                                                       bf16* __restrict__ xt, bf16* __restrict__ v,
+                                                       int64_t n8, int64_t per_sample8) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n8;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    float tt = t[i / per_sample8];
+    Row8 a = ld_bf16x8(x0 + i * 8), e = ld_bf16x8(noise + i * 8), o1, o2;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      o1.v[j] = (1.f - tt) * a.v[j] + tt * e.v[j];
+      o2.v[j] = -1.f * a.v[j] + 1.f * e.v[j];
+    }
+    if (xt) st_bf16x8(xt + i * 8, o1);
+    if (v) st_bf16x8(v + i * 8, o2);
+  }
+}
+
+// partial[b] = sum (out - v)^2 over the block's slice ; dout = gscale * 2 (out - v) / numel
+__global__ void __launch_bounds__(256) rf_loss_kernel(const bf16* __restrict__ out,
+                                                      const bf16* __restrict__ target,
+                                                      bf16* __restrict__ dout,
+                                                      float* __restrict__ partial, int64_t n8,
+                                                      float gcoef) {
+  float acc = 0.f;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n8;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    Row8 a = ld_bf16x8(out + i * 8), b = ld_bf16x8(target + i * 8), g;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float d = a.v[j] - b.v[j];
+      acc += d * d;
+      g.v[j] = gcoef * d;
+    }
+    if (dout) st_bf16x8(dout + i * 8, g);
+  }
+  __shared__ float red[8];
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float v = threadIdx.x < 8 ? red[threadIdx.x] : 0.f;
+    v = warp_sum(v);
+    if (threadIdx.x == 0) partial[blockIdx.x] = v;
+  }
+}
+__global__ void __launch_bounds__(256) rf_loss_final_kernel(const float* __restrict__ partial,
+                                                            int nparts, float inv_numel,
+                                                            float* __restrict__ loss) {
+  float acc = 0.f;
+  for (int i = threadIdx.x; i < nparts; i += 256) acc += partial[i];
+  __shared__ float red[8];
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float v = threadIdx.x < 8 ? red[threadIdx.x] : 0.f;
+    v = warp_sum(v);
+    if (threadIdx.x == 0) *loss = v * inv_numel;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// in-place conditioning lerp on tokens [B, N, C]: frame 0 <- lerp(tok, ref, 0.85), frames >= 1 <-
+// lerp(tok, pose, 0.5).  ref [B, C, 1, HW], pose [B, C, F, HW] are channel-major, so a 32x32 tile
+// goes through shared memory.  torch.lerp(a, b, w>=0.5) = b - (b - a) * (1 - w).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) lerp_condition_kernel(bf16* __restrict__ tok,
+                                                             const bf16* __restrict__ ref,
+                                                             const bf16* __restrict__ pose, int N,
+                                                             int C, int HW, float w_ref,
+                                                             float w_pose) {
+  __shared__ float tile[32][33];
+  int b = blockIdx.z;
+  int n0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+  for (int i = ty; i < 32; i += 8) {  // read cond[c0+i][n0+tx]
+    int c = c0 + i, n = n0 + tx;
+    float v = 0.f;
+    if (c < C && n < N) {
+      v = n < HW ? __bfloat162float(ref[((int64_t)b * C + c) * HW + n])
+                 : __bfloat162float(pose[((int64_t)b * C + c) * N + n]);
+    }
+    tile[i][tx] = v;
+  }
+  __syncthreads();
+  for (int i = ty; i < 32; i += 8) {  // write tok[n0+i][c0+tx]
+    int n = n0 + i, c = c0 + tx;
+    if (c < C && n < N) {
+      int64_t idx = ((int64_t)b * N + n) * C + c;
+      float a = __bfloat162float(tok[idx]);
+      float bb = tile[tx][i];
+      float w = n < HW ? w_ref : w_pose;
+      float r = w < 0.5f ? a + w * (bb - a) : bb - (bb - a) * (1.f - w);
+      tok[idx] = __float2bfloat16(r);
+    }
+  }
+}
+
+// out[m, :] = x[m, :] * g[m / rows_per_mod, :]
+__global__ void __launch_bounds__(256) rowscale_kernel(const bf16* __restrict__ x, int64_t ldx,
+                                                       const bf16* __restrict__ g, int64_t gstride,
+                                                       bf16* __restrict__ out, int64_t ldo,
+                                                       int64_t rows, int D8, int64_t rows_per_mod) {
+  int64_t total = rows * D8;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t r = i / D8;
+    int c = (int)(i - r * D8) * 8;
+    Row8 a = ld_bf16x8(x + r * ldx + c), b = ld_bf16x8(g + (r / rows_per_mod) * gstride + c), o;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o.v[j] = a.v[j] * b.v[j];
+    st_bf16x8(out + r * ldo + c, o);
+  }
+}
+
+// out[n] = sum_m x[m, n]   (bias gradients).  grid.x tiles columns by 64, block 256 = 64 cols x 4
+__global__ void __launch_bounds__(256) colsum_kernel(const bf16* __restrict__ x, int64_t ldx,
+                                                     float* __restrict__ out, int64_t rows, int N) {
+  __shared__ float red[4][64];
+  int c = blockIdx.x * 64 + (threadIdx.x & 63);
+  int part = threadIdx.x >> 6;
+  float acc = 0.f;
+  if (c < N)
+    for (int64_t r = part; r < rows; r += 4) acc += __bfloat162float(x[r * ldx + c]);
+  red[part][threadIdx.x & 63] = acc;
+  __syncthreads();
+  if (part == 0 && c < N) out[c] = red[0][threadIdx.x] + red[1][threadIdx.x] + red[2][threadIdx.x] + red[3][threadIdx.x];
+}
+
+// delta[b, h, q] = sum_d o[b, q, h, d] * do[b, q, h, d]   (dh = 64: 8 lanes x 8 elements per head)
+__global__ void __launch_bounds__(256) attn_delta_kernel(const bf16* __restrict__ o, int64_t ldo,
+                                                         const bf16* __restrict__ dout, int64_t lddo,
+                                                         float* __restrict__ delta, int B, int H,
+                                                         int Nq) {
+  int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int64_t item = gid >> 3;  // (b, q, h)
+  int sub = gid & 7;
+  int64_t total = (int64_t)B * Nq * H;
+  float acc = 0.f;
+  if (item < total) {
+    int h = (int)(item % H);
+    int64_t bq = item / H;
+    Row8 a = ld_bf16x8(o + bq * ldo + h * 64 + sub * 8);
+    Row8 b = ld_bf16x8(dout + bq * lddo + h * 64 + sub * 8);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc += a.v[j] * b.v[j];
+  }
+  acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+  acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+  acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+  if (item < total && sub == 0) {
+    int h = (int)(item % H);
+    int64_t bq = item / H;
+    int64_t b = bq / Nq, q = bq - b * Nq;
+    delta[(b * H + h) * Nq + q] = acc;
+  }
+}
+
+}  // namespace b200
+
+using namespace b200;
+
+#define CHECK_ARG(cond, msg)            \
+  do {                                  \
+    if (!(cond)) return arg_error(msg); \
+  } while (0)
+
+static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+extern "C" int b200_norm_mod_fwd(const void* x, int64_t ldx, void* y, int64_t ldy, const void* scale,
+                                 const void* shift, int64_t mod_stride, int64_t rows, int D,
+                                 int64_t rows_per_mod, float eps, int layernorm, void* stream) {
+  CHECK_ARG(x && y && rows >= 0 && D > 0, "norm_mod_fwd: null pointer or bad shape");
+  CHECK_ARG(D % 8 == 0 && D <= 2048, "norm_mod_fwd: D must be a multiple of 8 and <= 2048");
+  CHECK_ARG(ldx % 8 == 0 && ldy % 8 == 0 && mod_stride % 8 == 0 && aligned16(x) && aligned16(y) &&
+                aligned16(scale) && aligned16(shift),
+            "norm_mod_fwd: 16-byte alignment required");
+  CHECK_ARG(rows_per_mod > 0, "norm_mod_fwd: rows_per_mod must be positive");
+  if (rows == 0) return 0;
+  norm_mod_fwd_kernel<<<(unsigned)((rows + 3) / 4), 128, 0, (cudaStream_t)stream>>>(
+      (const bf16*)x, ldx, (bf16*)y, ldy, (const bf16*)scale, (const bf16*)shift, mod_stride, rows,
+      D, rows_per_mod, eps, layernorm);
+  return launch_status("norm_mod_fwd");
+}
+
+extern "C" int b200_norm_mod_bwd(const void* dy, int64_t lddy, const void* x, int64_t ldx,
+                                 const void* scale, int64_t mod_stride, const void* dres,
+                                 int64_t lddres, void* dx, int64_t lddx, int64_t rows, int D,
+                                 int64_t rows_per_mod, float eps, int layernorm, void* stream) {
+  CHECK_ARG(dy && x && dx && rows >= 0 && D > 0, "norm_mod_bwd: null pointer or bad shape");
+  CHECK_ARG(D % 8 == 0 && D <= 2048, "norm_mod_bwd: D must be a multiple of 8 and <= 2048");
+  CHECK_ARG(lddy % 8 == 0 && ldx % 8 == 0 && lddx % 8 == 0 && lddres % 8 == 0 &&
+                mod_stride % 8 == 0 && aligned16(dy) && aligned16(x) && aligned16(dx) &&
+                aligned16(dres) && aligned16(scale),
+            "norm_mod_bwd: 16-byte alignment required");
+  CHECK_ARG(rows_per_mod > 0, "norm_mod_bwd: rows_per_mod must be positive");
+  if (rows == 0) return 0;
+  norm_mod_bwd_kernel<<<(unsigned)((rows + 3) / 4), 128, 0, (cudaStream_t)stream>>>(
+      (const bf16*)dy, lddy, (const bf16*)x, ldx, (const bf16*)scale, mod_stride,
+      (const bf16*)dres, lddres, (bf16*)dx, lddx, rows, D, rows_per_mod, eps, layernorm);
+  return launch_status("norm_mod_bwd");
+}
+
+extern "C" int b200_qknorm_rope_fwd(const void* xq, int64_t ldq, const void* xk, int64_t ldk,
+                                    const void* wq, const void* wk, const void* cos_t,
+                                    const void* sin_t, int64_t ldcs, void* oq, int64_t ldoq, void* ok,
+                                    int64_t ldok, int64_t rows_q, int64_t rows_k, int D, float eps,
+                                    void* stream) {
+  CHECK_ARG(rows_q >= 0 && rows_k >= 0 && D > 0, "qknorm_rope_fwd: bad shape");
+  CHECK_ARG((rows_q == 0 || (xq && oq && wq)) && (rows_k == 0 || (xk && ok && wk)),
+            "qknorm_rope_fwd: null pointer");
+  CHECK_ARG(D % 8 == 0 && D <= 2048, "qknorm_rope_fwd: D must be a multiple of 8 and <= 2048");
+  CHECK_ARG((cos_t == nullptr) == (sin_t == nullptr), "qknorm_rope_fwd: cos/sin must come together");
+  CHECK_ARG(!cos_t || rows_q == rows_k || rows_q == 0 || rows_k == 0,
+            "qknorm_rope_fwd: RoPE needs the same rows for q and k");
+  CHECK_ARG(ldq % 8 == 0 && ldk % 8 == 0 && ldoq % 8 == 0 && ldok % 8 == 0 && ldcs % 8 == 0 &&
+                aligned16(xq) && aligned16(xk) && aligned16(oq) && aligned16(ok) && aligned16(wq) &&
+                aligned16(wk) && aligned16(cos_t) && aligned16(sin_t),
+            "qknorm_rope_fwd: 16-byte alignment required");
+  int64_t total = rows_q + rows_k;
+  if (total == 0) return 0;
+  qknorm_rope_fwd_kernel<<<(unsigned)((total + 3) / 4), 128, 0, (cudaStream_t)stream>>>(
+      (const bf16*)xq, ldq, (const bf16*)xk, ldk, (const bf16*)wq, (const bf16*)wk,
+      (const bf16*)cos_t, (const bf16*)sin_t, ldcs, (bf16*)oq, ldoq, (bf16*)ok, ldok, rows_q, rows_k,
+      D, eps);
+  return launch_status("qknorm_rope_fwd");
+}
+
+extern "C" int b200_qknorm_rope_bwd(const void* dq, int64_t lddq, int dq_is_f32, const void* dk,
+                                    int64_t lddk, int dk_is_f32, const void* xq, int64_t ldq,
+                                    const void* xk, int64_t ldk, const void* wq, const void* wk,
+                                    const void* cos_t, const void* sin_t, int64_t ldcs, void* oq,
+                                    int64_t ldoq, void* ok, int64_t ldok, int64_t rows_q,
+                                    int64_t rows_k, int D, float eps, void* stream) {
+  CHECK_ARG(rows_q >= 0 && rows_k >= 0 && D > 0, "qknorm_rope_bwd: bad shape");
+  CHECK_ARG((rows_q == 0 || (xq && oq && wq && dq)) && (rows_k == 0 || (xk && ok && wk && dk)),
+            "qknorm_rope_bwd: null pointer");
+  CHECK_ARG(D % 8 == 0 && D <= 2048, "qknorm_rope_bwd: D must be a multiple of 8 and <= 2048");
+  CHECK_ARG((cos_t == nullptr) == (sin_t == nullptr), "qknorm_rope_bwd: cos/sin must come together");
+  CHECK_ARG(!cos_t || rows_q == rows_k || rows_q == 0 || rows_k == 0,
+            "qknorm_rope_bwd: RoPE needs the same rows for q and k");
+  CHECK_ARG(lddq % 8 == 0 && lddk % 8 == 0 && ldq % 8 == 0 && ldk % 8 == 0 && ldoq % 8 == 0 &&
+                ldok % 8 == 0 && ldcs % 8 == 0 && aligned16(dq) && aligned16(dk) && aligned16(xq) &&
+                aligned16(xk) && aligned16(oq) && aligned16(ok) && aligned16(wq) && aligned16(wk) &&
+                aligned16(cos_t) && aligned16(sin_t),
+            "qknorm_rope_bwd: 16-byte alignment required");
+  int64_t total = rows_q + rows_k;
+  if (total == 0) return 0;
+  qknorm_rope_bwd_kernel<<<(unsigned)((total + 3) / 4), 128, 0, (cudaStream_t)stream>>>(
+      dq, lddq, dq_is_f32, dk, lddk, dk_is_f32, (const bf16*)xq, ldq, (const bf16*)xk, ldk,
+      (const bf16*)wq, (const bf16*)wk, (const bf16*)cos_t, (const bf16*)sin_t, ldcs, (bf16*)oq, ldoq,
+      (bf16*)ok, ldok, rows_q, rows_k, D, eps);
+  return launch_status("qknorm_rope_bwd");
+}
+
+extern "C" int b200_rf_noise(const void* x0, const void* noise, const float* t, void* xt, void* v,
+                             int64_t batch, int64_t per_sample, void* stream) {
+  CHECK_ARG(x0 && noise && t && batch >= 0 && per_sample >= 0, "rf_noise: null pointer or bad shape");
+  CHECK_ARG(per_sample % 8 == 0 && aligned16(x0) && aligned16(noise) && aligned16(xt) && aligned16(v),
+            "rf_noise: per-sample size must be a multiple of 8, pointers 16-byte aligned");
+  int64_t n8 = batch * per_sample / 8;
+  if (n8 == 0) return 0;
+  int blocks = (int)((n8 + 255) / 256 < 148 * 8 ? (n8 + 255) / 256 : 148 * 8);
+  rf_noise_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>((const bf16*)x0, (const bf16*)noise, t,
+                                                            (bf16*)xt, (bf16*)v, n8, per_sample / 8);
+  return launch_status("rf_noise");
+}
+
+extern "C" int64_t b200_rf_loss_workspace_bytes(void) { return 148 * 8 * sizeof(float); }
+
+extern "C" int b200_rf_loss(const void* out, const void* target, void* dout, float* loss,
+                            int64_t numel, float grad_scale, void* workspace,
+                            int64_t workspace_bytes, void* stream) {
+  CHECK_ARG(out && target && loss && workspace && numel > 0, "rf_loss: null pointer or empty input");
+  CHECK_ARG(numel % 8 == 0 && aligned16(out) && aligned16(target) && aligned16(dout),
+            "rf_loss: numel must be a multiple of 8, pointers 16-byte aligned");
+  CHECK_ARG(workspace_bytes >= b200_rf_loss_workspace_bytes(), "rf_loss: workspace too small");
+  int64_t n8 = numel / 8;
+  int blocks = (int)((n8 + 255) / 256 < 148 * 8 ? (n8 + 255) / 256 : 148 * 8);
+  rf_loss_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>((const bf16*)out, (const bf16*)target,
+                                                           (bf16*)dout, (float*)workspace, n8,
+                                                           grad_scale * 2.f / (float)numel);
+  rf_loss_final_kernel<<<1, 256, 0, (cudaStream_t)stream>>>((const float*)workspace, blocks,
+                                                            1.f / (float)numel, loss);
+  return launch_status("rf_loss");
+}
+
+extern "C" int b200_lerp_condition(void* tokens, const void* ref, const void* pose, int B, int N,
+                                   int C, int HW, float w_ref, float w_pose, void* stream) {
+  CHECK_ARG(tokens && ref && pose && B >= 0 && N >= 0 && C > 0 && HW > 0,
+            "lerp_condition: null pointer or bad shape");
+  CHECK_ARG(N % HW == 0, "lerp_condition: N must be frames x HW");
+  if (B == 0 || N == 0) return 0;
+  dim3 grid((N + 31) / 32, (C + 31) / 32, B);
+  lerp_condition_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((bf16*)tokens, (const bf16*)ref,
+                                                                (const bf16*)pose, N, C, HW, w_ref,
+                                                                w_pose);
+  return launch_status("lerp_condition");
+}
+
+extern "C" int b200_rowscale(const void* x, int64_t ldx, const void* g, int64_t gstride, void* out,
+                             int64_t ldo, int64_t rows, int D, int64_t rows_per_mod, void* stream) {
+  CHECK_ARG(x && g && out && rows >= 0 && D > 0 && rows_per_mod > 0, "rowscale: bad arguments");
+  CHECK_ARG(D % 8 == 0 && ldx % 8 == 0 && ldo % 8 == 0 && gstride % 8 == 0 && aligned16(x) &&
+                aligned16(g) && aligned16(out),
+            "rowscale: 16-byte alignment required");
+  int64_t total = rows * (D / 8);
+  if (total == 0) return 0;
+  int blocks = (int)((total + 255) / 256 < 148 * 8 ? (total + 255) / 256 : 148 * 8);
+  rowscale_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>((const bf16*)x, ldx, (const bf16*)g,
+                                                            gstride, (bf16*)out, ldo, rows, D / 8,
+                                                            rows_per_mod);
+  return launch_status("rowscale");
+}
+
+extern "C" int b200_colsum(const void* x, int64_t ldx, float* out, int64_t rows, int N, void* stream) {
+  CHECK_ARG(x && out && rows >= 0 && N > 0, "colsum: bad arguments");
+  colsum_kernel<<<(N + 63) / 64, 256, 0, (cudaStream_t)stream>>>((const bf16*)x, ldx, out, rows, N);
+  return launch_status("colsum");
+}
+
+extern "C" int b200_attn_delta(const void* o, int64_t ldo, const void* dout, int64_t lddo,
+                               float* delta, int B, int H, int Nq, void* stream) {
+  CHECK_ARG(o && dout && delta && B >= 0 && H > 0 && Nq >= 0, "attn_delta: bad arguments");
+  CHECK_ARG(ldo % 8 == 0 && lddo % 8 == 0 && aligned16(o) && aligned16(dout),
+            "attn_delta: 16-byte alignment required");
+  int64_t threads = (int64_t)B * Nq * H * 8;
+  if (threads == 0) return 0;
+  attn_delta_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      (const bf16*)o, ldo, (const bf16*)dout, lddo, delta, B, H, Nq);
+  return launch_status("attn_delta");
+}

@@ -1,0 +1,385 @@
+// gemm.cu — tcgen05 / TMEM / TMA bf16 GEMM with fused epilogues (sm_100a).
+//
+//   C[M,N] = epilogue( A[M,K] * B[N,K]^T  (+ A2[M,K2] * B2[N,K2]^T) )
+//
+// Replaces, on the LTXV block path, every nn.Linear the reference runs through cuBLASLt plus the
+// element-wise kernels around it (reference: attention.py:996-1014, 1089, 1238-1263;
+// transformer3d.py:470, 494-499, 561; peft lora.Linear forward, training.py:61-68):
+//   * second operand pair  = the LoRA up-projection (s*x*A^T)*B^T accumulated into the same TMEM tile
+//   * bias, GELU-tanh (+ pre-activation stash), GELU' (backward), per-sample AdaLN gate, residual
+//   * either operand may be stored "MN-major" (reduction dim strided), which is how dgrad
+//     (dY * W) and wgrad (dY^T * X) read the very same row-major tensors without a transpose.
+//
+// Structure: persistent CTAs (one per SM), 128 x BN output tiles, BLOCK_K = 64, warp-specialised:
+//   warp 0 lane 0 : TMA producer           (cp.async.bulk.tensor, 128B swizzle, mbarrier tx)
+//   warp 1 lane 0 : tcgen05.mma issuer     (M=128, N=BN, K=16 per instruction, fp32 accum in TMEM)
+//   warp 2        : TMEM allocator
+//   warps 4..7    : epilogue (tcgen05.ld 32x32b -> registers -> fused math -> 16-byte global stores)
+// Accumulators are double-buffered in TMEM (2 x BN columns) so the epilogue of tile i overlaps the
+// main loop of tile i+1.
+#include "api_internal.h"
+#include "common.cuh"
+#include "tmap.h"
+
+namespace b200 {
+
+enum { EPI_NONE = 0, EPI_GELU = 1, EPI_GELU_GRAD = 2 };
+
+struct GemmParams {
+  int M, N;
+  int m_tiles, n_tiles;
+  int kb1, kb2;  // 64-wide k blocks taken from (A,B) and from (A2,B2)
+  int epi, out_f32;
+  void* C;
+  int64_t ldc;
+  const bf16* bias;
+  const bf16* gate;
+  int64_t gate_stride, rows_per_gate;
+  const bf16* res;
+  int64_t ldres;
+  bf16* aux;
+  int64_t ldaux;
+};
+
+__device__ __forceinline__ float tanh_fast(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float gelu_tanh(float x) {
+  float u = 0.7978845608028654f * (x + 0.044715f * x * x * x);
+  return 0.5f * x * (1.f + tanh_fast(u));
+}
+__device__ __forceinline__ float gelu_tanh_grad(float x) {
+  float x2 = x * x;
+  float u = 0.7978845608028654f * (x + 0.044715f * x * x2);
+  float t = tanh_fast(u);
+  float du = 0.7978845608028654f * (1.f + 3.f * 0.044715f * x2);
+  return 0.5f * (1.f + t) + 0.5f * x * (1.f - t * t) * du;
+}
+
+template <int BN>
+struct GemmCfg {
+  static constexpr int BM = 128, BK = 64;
+  static constexpr int A_BYTES = BM * BK * 2;
+  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int STAGE = A_BYTES + B_BYTES;
+  static constexpr int NSTAGE = BN == 256 ? 4 : (BN == 128 ? 6 : 8);
+  static constexpr int TMEM_COLS = 2 * BN;
+  static constexpr int SMEM = NSTAGE * STAGE + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+template <int BN, bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(256, 1)
+gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+            const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB2,
+            const __grid_constant__ GemmParams p) {
+  using Cfg = GemmCfg<BN>;
+  constexpr int NSTAGE = Cfg::NSTAGE;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_base = sbase + NSTAGE * Cfg::STAGE;
+  auto full_bar = [&](int s) { return bar_base + s * 8; };
+  auto empty_bar = [&](int s) { return bar_base + (NSTAGE + s) * 8; };
+  auto tfull_bar = [&](int a) { return bar_base + (2 * NSTAGE + a) * 8; };
+  auto tempty_bar = [&](int a) { return bar_base + (2 * NSTAGE + 2 + a) * 8; };
+  const uint32_t tmem_slot = bar_base + (2 * NSTAGE + 4) * 8;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    if (p.kb2) {
+      tma_prefetch_desc(&tmA2);
+      tma_prefetch_desc(&tmB2);
+    }
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < NSTAGE; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tfull_bar(a), 1);
+      mbar_init(tempty_bar(a), 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  const int total_tiles = p.m_tiles * p.n_tiles;
+  const int kblocks = p.kb1 + p.kb2;
+
+  if (warp == 0 && lane == 0) {
+    // ------------------------------ TMA producer ------------------------------
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int mt = tile % p.m_tiles, nt = tile / p.m_tiles;
+      for (int kb = 0; kb < kblocks; ++kb) {
+        mbar_wait(empty_bar(stage), phase ^ 1);
+        mbar_expect_tx(full_bar(stage), Cfg::STAGE);
+        const bool second = kb >= p.kb1;
+        const CUtensorMap* ma = second ? &tmA2 : &tmA;
+        const CUtensorMap* mb = second ? &tmB2 : &tmB;
+        const int kk = (second ? kb - p.kb1 : kb) * 64;
+        const uint32_t sa = sbase + stage * Cfg::STAGE, sb = sa + Cfg::A_BYTES;
+        if (!A_MN) {
+          tma_load_2d(sa, ma, full_bar(stage), kk, mt * 128);
+        } else {
+          tma_load_2d(sa, ma, full_bar(stage), mt * 128, kk);
+          tma_load_2d(sa + 8192, ma, full_bar(stage), mt * 128 + 64, kk);
+        }
+        if (!B_MN) {
+          tma_load_2d(sb, mb, full_bar(stage), kk, nt * BN);
+        } else {
+#pragma unroll
+          for (int j = 0; j < BN / 64; ++j)
+            tma_load_2d(sb + j * 8192, mb, full_bar(stage), nt * BN + j * 64, kk);
+        }
+        if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1 && lane == 0) {
+    // ------------------------------ MMA issuer --------------------------------
+    const uint32_t idesc = make_idesc_bf16(128, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
+    int stage = 0, acc = 0;
+    uint32_t phase = 0, acc_phase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      mbar_wait(tempty_bar(acc), acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * BN;
+      for (int kb = 0; kb < kblocks; ++kb) {
+        mbar_wait(full_bar(stage), phase);
+        tc_fence_after();
+        const uint32_t sa = sbase + stage * Cfg::STAGE, sb = sa + Cfg::A_BYTES;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const uint64_t da = A_MN ? make_smem_desc(sa + k * 2048, 8192, 1024)
+                                   : make_smem_desc(sa + k * 32, 16, 1024);
+          const uint64_t db = B_MN ? make_smem_desc(sb + k * 2048, 8192, 1024)
+                                   : make_smem_desc(sb + k * 32, 16, 1024);
+          umma_ss(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+        }
+        umma_commit(empty_bar(stage));
+        if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+      }
+      umma_commit(tfull_bar(acc));
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+  } else if (warp >= 4) {
+    // ------------------------------ epilogue ----------------------------------
+    const int ew = warp - 4;  // TMEM lane quadrant (== warp % 4)
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int mt = tile % p.m_tiles, nt = tile / p.m_tiles;
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tc_fence_after();
+      const int64_t row = (int64_t)mt * 128 + ew * 32 + lane;
+      const bool row_ok = row < p.M;
+      const bf16* gate_row = p.gate ? p.gate + (row_ok ? row / p.rows_per_gate : 0) * p.gate_stride : nullptr;
+      const bf16* res_row = p.res ? p.res + row * p.ldres : nullptr;
+      bf16* aux_row = p.aux ? p.aux + row * p.ldaux : nullptr;
+      const uint32_t t_row = tmem_base + ((uint32_t)(ew * 32) << 16) + acc * BN;
+#pragma unroll 1
+      for (int c = 0; c < BN; c += 32) {
+        const int n0 = nt * BN + c;
+        if (n0 >= p.N) break;
+        uint32_t r[32];
+        tmem_ld32(t_row + c, r);
+        tmem_ld_wait();
+        if (row_ok) {
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            const int n = n0 + g * 8;
+            if (n < p.N) {
+              float v[8];
+#pragma unroll
+              for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[g * 8 + i]);
+              if (p.bias) {
+                uint4 u = __ldg(reinterpret_cast<const uint4*>(p.bias + n));
+                v[0] += bf16_lo(u.x); v[1] += bf16_hi(u.x); v[2] += bf16_lo(u.y); v[3] += bf16_hi(u.y);
+                v[4] += bf16_lo(u.z); v[5] += bf16_hi(u.z); v[6] += bf16_lo(u.w); v[7] += bf16_hi(u.w);
+              }
+              if (p.epi == EPI_GELU) {
+                if (aux_row) {
+                  uint4 u;
+                  u.x = pack_bf16x2(v[0], v[1]); u.y = pack_bf16x2(v[2], v[3]);
+                  u.z = pack_bf16x2(v[4], v[5]); u.w = pack_bf16x2(v[6], v[7]);
+                  *reinterpret_cast<uint4*>(aux_row + n) = u;
+                  v[0] = bf16_lo(u.x); v[1] = bf16_hi(u.x); v[2] = bf16_lo(u.y); v[3] = bf16_hi(u.y);
+                  v[4] = bf16_lo(u.z); v[5] = bf16_hi(u.z); v[6] = bf16_lo(u.w); v[7] = bf16_hi(u.w);
+                }
+#pragma unroll
+                for (int i = 0; i < 8; ++i) v[i] = gelu_tanh(v[i]);
+              } else if (p.epi == EPI_GELU_GRAD) {
+                uint4 u = *reinterpret_cast<const uint4*>(aux_row + n);
+                float h[8] = {bf16_lo(u.x), bf16_hi(u.x), bf16_lo(u.y), bf16_hi(u.y),
+                              bf16_lo(u.z), bf16_hi(u.z), bf16_lo(u.w), bf16_hi(u.w)};
+#pragma unroll
+                for (int i = 0; i < 8; ++i) v[i] *= gelu_tanh_grad(h[i]);
+              }
+              if (gate_row) {
+                uint4 u = __ldg(reinterpret_cast<const uint4*>(gate_row + n));
+                v[0] *= bf16_lo(u.x); v[1] *= bf16_hi(u.x); v[2] *= bf16_lo(u.y); v[3] *= bf16_hi(u.y);
+                v[4] *= bf16_lo(u.z); v[5] *= bf16_hi(u.z); v[6] *= bf16_lo(u.w); v[7] *= bf16_hi(u.w);
+              }
+              if (res_row) {
+                uint4 u = *reinterpret_cast<const uint4*>(res_row + n);
+                v[0] += bf16_lo(u.x); v[1] += bf16_hi(u.x); v[2] += bf16_lo(u.y); v[3] += bf16_hi(u.y);
+                v[4] += bf16_lo(u.z); v[5] += bf16_hi(u.z); v[6] += bf16_lo(u.w); v[7] += bf16_hi(u.w);
+              }
+              if (p.out_f32) {
+                float* o = reinterpret_cast<float*>(p.C) + row * p.ldc + n;
+                *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
+                *reinterpret_cast<float4*>(o + 4) = make_float4(v[4], v[5], v[6], v[7]);
+              } else {
+                uint4 u;
+                u.x = pack_bf16x2(v[0], v[1]); u.y = pack_bf16x2(v[2], v[3]);
+                u.z = pack_bf16x2(v[4], v[5]); u.w = pack_bf16x2(v[6], v[7]);
+                *reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(p.C) + row * p.ldc + n) = u;
+              }
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(acc));
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+static int g_num_sms = 0;
+static int num_sms() {
+  if (!g_num_sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (g_num_sms <= 0) g_num_sms = 148;
+  }
+  return g_num_sms;
+}
+
+template <int BN, bool A_MN, bool B_MN>
+static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmA2,
+                       const CUtensorMap& tmB2, const GemmParams& p, cudaStream_t stream) {
+  using Cfg = GemmCfg<BN>;
+  static bool attr_set = false;
+  auto kern = gemm_kernel<BN, A_MN, B_MN>;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
+    if (e != cudaSuccess) return launch_status("gemm: cudaFuncSetAttribute");
+    attr_set = true;
+  }
+  int tiles = p.m_tiles * p.n_tiles;
+  int grid = tiles < num_sms() ? tiles : num_sms();
+  kern<<<grid, 256, Cfg::SMEM, stream>>>(tmA, tmB, tmA2, tmB2, p);
+  return launch_status("gemm_bf16");
+}
+
+}  // namespace b200
+
+using namespace b200;
+
+static inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+// See include/b200ltx.h for the contract.
+extern "C" int b200_gemm_bf16(const void* A, int64_t lda, int a_kmajor_rows_are_k, const void* B,
+                              int64_t ldb, int b_rows_are_k, const void* A2, int64_t lda2,
+                              const void* B2, int64_t ldb2, int K2, void* C, int64_t ldc,
+                              int out_is_f32, int M, int N, int K, int epilogue, const void* bias,
+                              const void* gate, int64_t gate_stride, int64_t rows_per_gate,
+                              const void* res, int64_t ldres, void* aux, int64_t ldaux,
+                              int block_n, void* stream) {
+  const bool a_mn = a_kmajor_rows_are_k != 0, b_mn = b_rows_are_k != 0;
+  if (!(A && B && C)) return arg_error("gemm_bf16: null operand");
+  if (M < 0 || N < 0 || K < 0 || K2 < 0) return arg_error("gemm_bf16: negative dimension");
+  if (M == 0 || N == 0) return 0;
+  if (K == 0 && K2 == 0) return arg_error("gemm_bf16: empty reduction");
+  if (N % 8 || K % 8 || K2 % 8 || (a_mn && M % 8))
+    return arg_error("gemm_bf16: N, K, K2 (and M for a [K,M] A operand) must be multiples of 8");
+  if (lda % 8 || ldb % 8 || ldc % (out_is_f32 ? 4 : 8) || !al16(A) || !al16(B) || !al16(C))
+    return arg_error("gemm_bf16: operands must be 16-byte aligned with 16-byte-multiple pitches");
+  if (K2 > 0 && (!(A2 && B2) || lda2 % 8 || ldb2 % 8 || !al16(A2) || !al16(B2)))
+    return arg_error("gemm_bf16: bad second operand pair");
+  if (epilogue < EPI_NONE || epilogue > EPI_GELU_GRAD) return arg_error("gemm_bf16: unknown epilogue");
+  if (epilogue == EPI_GELU_GRAD && !aux) return arg_error("gemm_bf16: GELU_GRAD needs aux (pre-activation)");
+  if ((aux && (ldaux % 8 || !al16(aux))) || (res && (ldres % 8 || !al16(res))) ||
+      (bias && !al16(bias)) || (gate && (gate_stride % 8 || !al16(gate) || rows_per_gate <= 0)))
+    return arg_error("gemm_bf16: epilogue operands must be 16-byte aligned");
+
+  int bn = block_n;
+  if (bn == 0) {
+    const int mt = (M + 127) / 128;
+    bn = 64;
+    for (int cand : {256, 128}) {
+      if (N >= cand && mt * ((N + cand - 1) / cand) >= 96) { bn = cand; break; }
+    }
+    if (bn == 64 && N > 64 && mt * ((N + 127) / 128) >= 48) bn = 128;
+  }
+  if (bn != 64 && bn != 128 && bn != 256) return arg_error("gemm_bf16: block_n must be 0, 64, 128 or 256");
+
+  GemmParams p;
+  p.M = M; p.N = N;
+  p.m_tiles = (M + 127) / 128;
+  p.n_tiles = (N + bn - 1) / bn;
+  p.kb1 = (K + 63) / 64;
+  p.kb2 = (K2 + 63) / 64;
+  p.epi = epilogue; p.out_f32 = out_is_f32;
+  p.C = C; p.ldc = ldc;
+  p.bias = (const bf16*)bias;
+  p.gate = (const bf16*)gate; p.gate_stride = gate_stride; p.rows_per_gate = rows_per_gate > 0 ? rows_per_gate : 1;
+  p.res = (const bf16*)res; p.ldres = ldres;
+  p.aux = (bf16*)aux; p.ldaux = ldaux;
+
+  CUtensorMap tmA, tmB, tmA2, tmB2;
+  int rc;
+  auto mapA = [&](CUtensorMap* t, const void* ptr, int64_t ld, int kdim) {
+    return a_mn ? make_tmap_2d_bf16(t, ptr, kdim, M, ld, 64, 64) : make_tmap_2d_bf16(t, ptr, M, kdim, ld, 128, 64);
+  };
+  auto mapB = [&](CUtensorMap* t, const void* ptr, int64_t ld, int kdim) {
+    return b_mn ? make_tmap_2d_bf16(t, ptr, kdim, N, ld, 64, 64) : make_tmap_2d_bf16(t, ptr, N, kdim, ld, bn, 64);
+  };
+  if (K > 0) {
+    if ((rc = mapA(&tmA, A, lda, K)) || (rc = mapB(&tmB, B, ldb, K))) return arg_error("gemm_bf16: cuTensorMapEncodeTiled failed", rc);
+  }
+  if (K2 > 0) {
+    if ((rc = mapA(&tmA2, A2, lda2, K2)) || (rc = mapB(&tmB2, B2, ldb2, K2))) return arg_error("gemm_bf16: cuTensorMapEncodeTiled failed (pair 2)", rc);
+  } else {
+    tmA2 = tmA; tmB2 = tmB;
+  }
+  if (K == 0) { tmA = tmA2; tmB = tmB2; }
+
+  cudaStream_t st = (cudaStream_t)stream;
+#define DISPATCH(BN_)                                                                     \
+  if (bn == BN_) {                                                                        \
+    if (!a_mn && !b_mn) return launch_gemm<BN_, false, false>(tmA, tmB, tmA2, tmB2, p, st); \
+    if (!a_mn && b_mn) return launch_gemm<BN_, false, true>(tmA, tmB, tmA2, tmB2, p, st);   \
+    if (a_mn && !b_mn) return launch_gemm<BN_, true, false>(tmA, tmB, tmA2, tmB2, p, st);   \
+    return launch_gemm<BN_, true, true>(tmA, tmB, tmA2, tmB2, p, st);                       \
+  }
+  DISPATCH(256)
+  DISPATCH(128)
+  DISPATCH(64)
+#undef DISPATCH
+  return arg_error("gemm_bf16: unreachable");
+}

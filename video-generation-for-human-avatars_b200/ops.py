@@ -1,0 +1,410 @@
+"""Tensor-level wrappers over the C ABI (lib.py) and the autograd Functions built from them.
+
+Every function here launches hand-written sm_100a kernels from libb200ltx.so on the current CUDA
+stream.  PyTorch supplies device memory, streams and the autograd graph only."""
+from typing import Optional, Tuple
+
+import torch
+
+from . import lib as _lib
+
+EPI_NONE, EPI_GELU, EPI_GELU_GRAD = 0, 1, 2
+LORA_PAD = 64  # LoRA rank is zero-padded to one 64-wide k-block of the GEMM
+BF16 = torch.bfloat16
+
+# counts kernels launched through the C ABI (bench.py reports it as gpu_launches)
+launch_count = 0
+
+
+def _L():
+    return _lib.load()
+
+
+def _s() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _p(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def _chk2d(t: torch.Tensor, name: str, dtype=BF16):
+    if t.dim() != 2 or t.stride(1) != 1 or t.dtype != dtype or not t.is_cuda:
+        raise _lib.B200Error(f"{name}: expected a CUDA {dtype} matrix with unit inner stride, got "
+                             f"{tuple(t.shape)} {t.dtype} strides {t.stride()} on {t.device}")
+
+
+def _count(n=1):
+    global launch_count
+    launch_count += n
+
+
+# ---------------------------------------------------------------------------------------------
+# raw ops
+# ---------------------------------------------------------------------------------------------
+def gemm(a: torch.Tensor, b: torch.Tensor, *, a_rows_are_k=False, b_rows_are_k=False,
+         a2: Optional[torch.Tensor] = None, b2: Optional[torch.Tensor] = None,
+         out: Optional[torch.Tensor] = None, out_dtype=BF16, bias=None, gate=None, rows_per_gate=0,
+         res=None, aux=None, epilogue=EPI_NONE, block_n=0) -> torch.Tensor:
+    """out[M,N] = epi(a @ b^T (+ a2 @ b2^T)); see b200_gemm_bf16 in include/b200ltx.h."""
+    _chk2d(a, "gemm a")
+    _chk2d(b, "gemm b")
+    M, K = (a.shape[1], a.shape[0]) if a_rows_are_k else a.shape
+    N, Kb = (b.shape[1], b.shape[0]) if b_rows_are_k else b.shape
+    if K != Kb:
+        raise _lib.B200Error(f"gemm: reduction mismatch {K} vs {Kb}")
+    K2 = 0
+    if a2 is not None:
+        _chk2d(a2, "gemm a2")
+        _chk2d(b2, "gemm b2")
+        M2, K2 = (a2.shape[1], a2.shape[0]) if a_rows_are_k else a2.shape
+        N2, K2b = (b2.shape[1], b2.shape[0]) if b_rows_are_k else b2.shape
+        if (M2, N2, K2) != (M, N, K2b):
+            raise _lib.B200Error("gemm: second operand pair shape mismatch")
+    if out is None:
+        out = torch.empty((M, N), device=a.device, dtype=out_dtype)
+    _chk2d(out, "gemm out", out.dtype)
+    if out.dtype not in (BF16, torch.float32) or tuple(out.shape) != (M, N):
+        raise _lib.B200Error("gemm: bad output tensor")
+    for t, nm in ((res, "res"), (aux, "aux")):
+        if t is not None:
+            _chk2d(t, "gemm " + nm)
+            if tuple(t.shape) != (M, N):
+                raise _lib.B200Error(f"gemm: {nm} shape mismatch")
+    gate_stride = 0
+    if gate is not None:
+        _chk2d(gate, "gemm gate")
+        gate_stride = gate.stride(0)
+        if gate.shape[1] != N or rows_per_gate <= 0 or gate.shape[0] * rows_per_gate < M:
+            raise _lib.B200Error("gemm: gate shape / rows_per_gate mismatch")
+    if bias is not None and (bias.dtype != BF16 or bias.numel() != N or not bias.is_contiguous()):
+        raise _lib.B200Error("gemm: bias must be a contiguous bf16 vector of length N")
+    rc = _L().b200_gemm_bf16(
+        _p(a), a.stride(0), int(a_rows_are_k), _p(b), b.stride(0), int(b_rows_are_k),
+        _p(a2), a2.stride(0) if a2 is not None else 0, _p(b2), b2.stride(0) if b2 is not None else 0, K2,
+        _p(out), out.stride(0), int(out.dtype == torch.float32), M, N, K, epilogue,
+        _p(bias), _p(gate), gate_stride, rows_per_gate, _p(res), res.stride(0) if res is not None else 0,
+        _p(aux), aux.stride(0) if aux is not None else 0, block_n, _s())
+    _lib.check(rc, "b200_gemm_bf16")
+    _count()
+    return out
+
+
+def norm_mod_fwd(x, scale, shift, rows_per_mod, eps, layernorm=False, out=None):
+    _chk2d(x, "norm_mod x")
+    rows, D = x.shape
+    if out is None:
+        out = torch.empty((rows, D), device=x.device, dtype=BF16)
+    mod_stride = 0
+    for t in (scale, shift):
+        if t is not None:
+            _chk2d(t, "norm_mod scale/shift")
+            mod_stride = t.stride(0)
+    if scale is not None and shift is not None and scale.stride(0) != shift.stride(0):
+        raise _lib.B200Error("norm_mod: scale and shift must share a row stride")
+    rc = _L().b200_norm_mod_fwd(_p(x), x.stride(0), _p(out), out.stride(0), _p(scale), _p(shift),
+                                mod_stride, rows, D, rows_per_mod, eps, int(layernorm), _s())
+    _lib.check(rc, "b200_norm_mod_fwd")
+    _count()
+    return out
+
+
+def norm_mod_bwd(dy, x, scale, rows_per_mod, eps, layernorm=False, dres=None):
+    _chk2d(dy, "norm_mod_bwd dy")
+    _chk2d(x, "norm_mod_bwd x")
+    rows, D = x.shape
+    dx = torch.empty((rows, D), device=x.device, dtype=BF16)
+    if dres is not None:
+        _chk2d(dres, "norm_mod_bwd dres")
+    rc = _L().b200_norm_mod_bwd(_p(dy), dy.stride(0), _p(x), x.stride(0), _p(scale),
+                                scale.stride(0) if scale is not None else 0, _p(dres),
+                                dres.stride(0) if dres is not None else 0, _p(dx), dx.stride(0), rows, D,
+                                rows_per_mod, eps, int(layernorm), _s())
+    _lib.check(rc, "b200_norm_mod_bwd")
+    _count()
+    return dx
+
+
+def qknorm_rope_fwd(xq, xk, wq, wk, cos, sin, oq, ok, eps=1e-5):
+    rows_q = xq.shape[0] if xq is not None else 0
+    rows_k = xk.shape[0] if xk is not None else 0
+    D = (xq if xq is not None else xk).shape[1]
+    rc = _L().b200_qknorm_rope_fwd(
+        _p(xq), xq.stride(0) if xq is not None else 0, _p(xk), xk.stride(0) if xk is not None else 0,
+        _p(wq), _p(wk), _p(cos), _p(sin), cos.stride(0) if cos is not None else 0,
+        _p(oq), oq.stride(0) if oq is not None else 0, _p(ok), ok.stride(0) if ok is not None else 0,
+        rows_q, rows_k, D, eps, _s())
+    _lib.check(rc, "b200_qknorm_rope_fwd")
+    _count()
+
+
+def qknorm_rope_bwd(dq, dk, xq, xk, wq, wk, cos, sin, oq, ok, eps=1e-5):
+    rows_q = xq.shape[0] if xq is not None else 0
+    rows_k = xk.shape[0] if xk is not None else 0
+    D = (xq if xq is not None else xk).shape[1]
+    rc = _L().b200_qknorm_rope_bwd(
+        _p(dq), dq.stride(0) if dq is not None else 0, int(dq is not None and dq.dtype == torch.float32),
+        _p(dk), dk.stride(0) if dk is not None else 0, int(dk is not None and dk.dtype == torch.float32),
+        _p(xq), xq.stride(0) if xq is not None else 0, _p(xk), xk.stride(0) if xk is not None else 0,
+        _p(wq), _p(wk), _p(cos), _p(sin), cos.stride(0) if cos is not None else 0,
+        _p(oq), oq.stride(0) if oq is not None else 0, _p(ok), ok.stride(0) if ok is not None else 0,
+        rows_q, rows_k, D, eps, _s())
+    _lib.check(rc, "b200_qknorm_rope_bwd")
+    _count()
+
+
+def fa_fwd(q, k, v, B, H, Nq, Nk, key_bias=None, scale=0.125, need_lse=True):
+    """q [B*Nq, >=H*64], k/v [B*Nk, >=H*64] (row-strided views allowed) -> o [B*Nq, H*64], lse."""
+    for t, nm in ((q, "q"), (k, "k"), (v, "v")):
+        _chk2d(t, "fa_fwd " + nm)
+    o = torch.empty((B * Nq, H * 64), device=q.device, dtype=BF16)
+    lse = torch.empty((B, H, Nq), device=q.device, dtype=torch.float32) if need_lse else None
+    if key_bias is not None and (key_bias.dtype != torch.float32 or tuple(key_bias.shape) != (B, Nk)
+                                 or not key_bias.is_contiguous()):
+        raise _lib.B200Error("fa_fwd: key_bias must be contiguous fp32 [B, Nk]")
+    rc = _L().b200_fa_fwd(_p(q), q.stride(0), _p(k), k.stride(0), _p(v), v.stride(0), _p(o), o.stride(0),
+                          _p(lse), _p(key_bias), B, H, Nq, Nk, 64, scale, _s())
+    _lib.check(rc, "b200_fa_fwd")
+    _count()
+    return o, lse
+
+
+def fa_bwd(q, k, v, o, do, lse, B, H, Nq, Nk, dk, dv, key_bias=None, scale=0.125):
+    """Returns dq as fp32 [B*Nq, H*64]; writes bf16 dk/dv into the given (possibly strided) views."""
+    _chk2d(do, "fa_bwd do")
+    delta = torch.empty((B, H, Nq), device=q.device, dtype=torch.float32)
+    rc = _L().b200_attn_delta(_p(o), o.stride(0), _p(do), do.stride(0), _p(delta), B, H, Nq, _s())
+    _lib.check(rc, "b200_attn_delta")
+    dq = torch.zeros((B * Nq, H * 64), device=q.device, dtype=torch.float32)
+    rc = _L().b200_fa_bwd(_p(q), q.stride(0), _p(k), k.stride(0), _p(v), v.stride(0), _p(do), do.stride(0),
+                          _p(lse), _p(delta), _p(key_bias), _p(dq), dq.stride(0), _p(dk), dk.stride(0),
+                          _p(dv), dv.stride(0), B, H, Nq, Nk, 64, scale, _s())
+    _lib.check(rc, "b200_fa_bwd")
+    _count(2)
+    return dq
+
+
+def rf_noise(x0, noise, t, want_xt=True, want_v=True):
+    if x0.dtype != BF16 or noise.dtype != BF16 or not x0.is_contiguous() or not noise.is_contiguous():
+        raise _lib.B200Error("rf_noise: contiguous bf16 tensors required")
+    t = t.to(device=x0.device, dtype=torch.float32).contiguous()
+    xt = torch.empty_like(x0) if want_xt else None
+    v = torch.empty_like(x0) if want_v else None
+    B = x0.shape[0]
+    rc = _L().b200_rf_noise(_p(x0), _p(noise), _p(t), _p(xt), _p(v), B, x0.numel() // max(B, 1), _s())
+    _lib.check(rc, "b200_rf_noise")
+    _count()
+    return xt, v
+
+
+def rf_loss(out, target, grad_scale=1.0, want_grad=True):
+    if out.dtype != BF16 or target.dtype != BF16 or not out.is_contiguous() or not target.is_contiguous():
+        raise _lib.B200Error("rf_loss: contiguous bf16 tensors required")
+    dout = torch.empty_like(out) if want_grad else None
+    loss = torch.empty((), device=out.device, dtype=torch.float32)
+    nbytes = _L().b200_rf_loss_workspace_bytes()
+    ws = torch.empty(nbytes, device=out.device, dtype=torch.uint8)
+    rc = _L().b200_rf_loss(_p(out), _p(target), _p(dout), _p(loss), out.numel(), grad_scale, _p(ws), nbytes, _s())
+    _lib.check(rc, "b200_rf_loss")
+    _count(2)
+    return loss, dout
+
+
+def lerp_condition_(tokens, ref, pose, w_ref=0.85, w_pose=0.5):
+    """In-place on tokens [B,N,C] (contiguous bf16); ref [B,C,1,H,W], pose [B,C,F,H,W]."""
+    B, N, C = tokens.shape
+    HW = ref.shape[3] * ref.shape[4]
+    for t in (tokens, ref, pose):
+        if t.dtype != BF16 or not t.is_contiguous():
+            raise _lib.B200Error("lerp_condition: contiguous bf16 tensors required")
+    if pose.shape[2] * HW != N or ref.shape[2] != 1:
+        raise _lib.B200Error("lerp_condition: pose/ref shapes do not match the token count")
+    rc = _L().b200_lerp_condition(_p(tokens), _p(ref), _p(pose), B, N, C, HW, w_ref, w_pose, _s())
+    _lib.check(rc, "b200_lerp_condition")
+    _count()
+    return tokens
+
+
+def rowscale(x, g, rows_per_mod):
+    _chk2d(x, "rowscale x")
+    _chk2d(g, "rowscale g")
+    out = torch.empty((x.shape[0], x.shape[1]), device=x.device, dtype=BF16)
+    rc = _L().b200_rowscale(_p(x), x.stride(0), _p(g), g.stride(0), _p(out), out.stride(0), x.shape[0],
+                            x.shape[1], rows_per_mod, _s())
+    _lib.check(rc, "b200_rowscale")
+    _count()
+    return out
+
+
+def colsum(x):
+    _chk2d(x, "colsum x")
+    out = torch.empty((x.shape[1],), device=x.device, dtype=torch.float32)
+    rc = _L().b200_colsum(_p(x), x.stride(0), _p(out), x.shape[0], x.shape[1], _s())
+    _lib.check(rc, "b200_colsum")
+    _count()
+    return out
+
+
+# ---------------------------------------------------------------------------------------------
+# LoRA staging: fp32 peft adapters -> zero-padded bf16 GEMM operands
+# ---------------------------------------------------------------------------------------------
+def stage_lora(A: torch.Tensor, B: torch.Tensor, scaling: float) -> Tuple[torch.Tensor, torch.Tensor]:
+    """A [r, K] -> A_pad [64, K] ; B [N, r] -> (scaling * B)_pad [N, 64], both bf16."""
+    r = A.shape[0]
+    if r > LORA_PAD:
+        raise _lib.B200Error(f"LoRA rank {r} > {LORA_PAD} is not built")
+    a_pad = torch.zeros((LORA_PAD, A.shape[1]), device=A.device, dtype=BF16)
+    a_pad[:r] = A.detach()
+    b_pad = torch.zeros((B.shape[0], LORA_PAD), device=B.device, dtype=BF16)
+    b_pad[:, :r] = B.detach() * scaling
+    return a_pad, b_pad
+
+
+# ---------------------------------------------------------------------------------------------
+# autograd Functions
+# ---------------------------------------------------------------------------------------------
+class LinearFn(torch.autograd.Function):
+    """y = gate * (x W^T + b + s (x A^T) B^T) + res    (every piece after x W^T optional).
+
+    One GEMM forward (LoRA up-projection, bias, AdaLN gate and residual fused in the epilogue)
+    plus a 64-wide GEMM for the LoRA down-projection.  Backward: dgrad reads W as an MN-major B
+    operand (no transposed copy), the LoRA dt*A term rides in the same GEMM; wgrad / LoRA grads use
+    the [K,M]-layout A operand."""
+
+    @staticmethod
+    def forward(ctx, x, W, b, A, B, scaling, gate, rows_per_gate, res):
+        has_lora = A is not None
+        t = a_pad = b_pad = None
+        if has_lora:
+            a_pad, b_pad = stage_lora(A, B, scaling)
+            t = gemm(x, a_pad, block_n=64)
+        y = gemm(x, W, a2=t, b2=b_pad, bias=b, gate=gate, rows_per_gate=rows_per_gate, res=res)
+        ctx.save_for_backward(x, W, t, a_pad, b_pad, gate)
+        ctx.meta = (has_lora, scaling, rows_per_gate, A.shape[0] if has_lora else 0,
+                    b is not None, res is not None)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, W, t, a_pad, b_pad, gate = ctx.saved_tensors
+        has_lora, scaling, rpg, r, has_bias, has_res = ctx.meta
+        need = ctx.needs_input_grad
+        dy = dy if dy.stride(1) == 1 else dy.contiguous()
+        g = rowscale(dy, gate, rpg) if gate is not None else dy
+        dx = dW = db = dA = dB = None
+        dt = None
+        if has_lora and (need[0] or need[3]):
+            dt = gemm(g, b_pad, b_rows_are_k=True, block_n=64)          # [M,64] = g (sB)
+        if need[0]:
+            dx = gemm(g, W, b_rows_are_k=True, a2=dt, b2=a_pad if has_lora else None)
+        if has_lora and need[3]:
+            dA = gemm(dt, x, a_rows_are_k=True, b_rows_are_k=True, out_dtype=torch.float32)[:r]
+        if has_lora and need[4]:
+            dB = gemm(g, t, a_rows_are_k=True, b_rows_are_k=True, out_dtype=torch.float32, block_n=64)[:, :r]
+            dB = dB * scaling if scaling != 1.0 else dB
+        if need[1]:
+            dW = gemm(g, x, a_rows_are_k=True, b_rows_are_k=True)
+        if has_bias and need[2]:
+            db = colsum(g).to(BF16)
+        dres = dy if (has_res and need[8]) else None
+        return dx, dW, db, dA, dB, None, None, None, dres
+
+
+class FeedForwardFn(torch.autograd.Function):
+    """y = gate * (gelu_tanh(x W1^T + b1) W2^T + b2) + res.   Saves only the bf16 pre-activation;
+    GELU' is applied in the epilogue of the W2 dgrad GEMM."""
+
+    @staticmethod
+    def forward(ctx, x, W1, b1, W2, b2, gate, rows_per_gate, res):
+        M = x.shape[0]
+        pre = torch.empty((M, W1.shape[0]), device=x.device, dtype=BF16)
+        act = gemm(x, W1, bias=b1, epilogue=EPI_GELU, aux=pre)
+        y = gemm(act, W2, bias=b2, gate=gate, rows_per_gate=rows_per_gate, res=res)
+        train_w = W1.requires_grad or W2.requires_grad
+        ctx.save_for_backward(x, W1, W2, pre, gate, act if train_w else None)
+        ctx.meta = (rows_per_gate, res is not None)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, W1, W2, pre, gate, act = ctx.saved_tensors
+        rpg, has_res = ctx.meta
+        need = ctx.needs_input_grad
+        dy = dy if dy.stride(1) == 1 else dy.contiguous()
+        g = rowscale(dy, gate, rpg) if gate is not None else dy
+        dh = gemm(g, W2, b_rows_are_k=True, epilogue=EPI_GELU_GRAD, aux=pre)   # [M, Dff]
+        dx = gemm(dh, W1, b_rows_are_k=True) if need[0] else None
+        dW1 = db1 = dW2 = db2 = None
+        if need[1]:
+            dW1 = gemm(dh, x, a_rows_are_k=True, b_rows_are_k=True)
+        if need[2]:
+            db1 = colsum(dh).to(BF16)
+        if need[3]:
+            dW2 = gemm(g, act, a_rows_are_k=True, b_rows_are_k=True)
+        if need[4]:
+            db2 = colsum(g).to(BF16)
+        dres = dy if (has_res and need[7]) else None
+        return dx, dW1, db1, dW2, db2, None, None, dres
+
+
+class NormModFn(torch.autograd.Function):
+    """y = norm(x) * (1 + scale) + shift  with RMSNorm / LayerNorm (no affine)."""
+
+    @staticmethod
+    def forward(ctx, x, scale, shift, rows_per_mod, eps, layernorm):
+        y = norm_mod_fwd(x, scale, shift, rows_per_mod, eps, layernorm)
+        ctx.save_for_backward(x, scale)
+        ctx.meta = (rows_per_mod, eps, layernorm)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, scale = ctx.saved_tensors
+        rpm, eps, ln = ctx.meta
+        if ctx.needs_input_grad[1] or ctx.needs_input_grad[2]:
+            raise _lib.B200Error("NormModFn: gradients of the AdaLN scale/shift are not built "
+                                 "(train_mode='full' is outside the round-1 scope)")
+        dy = dy if dy.stride(1) == 1 else dy.contiguous()
+        return norm_mod_bwd(dy, x, scale, rpm, eps, ln), None, None, None, None, None
+
+
+class AttnCoreFn(torch.autograd.Function):
+    """o = softmax(rope(qnorm(q)) rope(knorm(k))^T / 8 + key_bias) v  on token-major tensors.
+
+    q_pre [B*Nq, D], k_pre / v [B*Nk, D] may be column slices of packed projection buffers.  The
+    backward keeps dq in fp32 between the attention and the qk-norm kernels and returns gradients
+    for the pre-norm projections."""
+
+    @staticmethod
+    def forward(ctx, q_pre, k_pre, v, wq, wk, cos, sin, key_bias, B, H, Nq, Nk, scale):
+        D = H * 64
+        qk = torch.empty((B * Nq + B * Nk, D), device=q_pre.device, dtype=BF16)
+        q, k = qk[:B * Nq], qk[B * Nq:]
+        qknorm_rope_fwd(q_pre, k_pre, wq, wk, cos, sin, q, k)
+        o, lse = fa_fwd(q, k, v, B, H, Nq, Nk, key_bias, scale)
+        ctx.save_for_backward(q_pre, k_pre, v, wq, wk, cos, sin, key_bias, qk, o, lse)
+        ctx.meta = (B, H, Nq, Nk, scale)
+        return o
+
+    @staticmethod
+    def backward(ctx, do):
+        q_pre, k_pre, v, wq, wk, cos, sin, key_bias, qk, o, lse = ctx.saved_tensors
+        B, H, Nq, Nk, scale = ctx.meta
+        if ctx.needs_input_grad[3] or ctx.needs_input_grad[4]:
+            raise _lib.B200Error("AttnCoreFn: q_norm/k_norm weight gradients are not built "
+                                 "(train_mode='full' is outside the round-1 scope)")
+        D = H * 64
+        q, k = qk[:B * Nq], qk[B * Nq:]
+        do = do if do.stride(1) == 1 else do.contiguous()
+        dk = torch.empty((B * Nk, D), device=do.device, dtype=BF16)
+        dv = torch.empty((B * Nk, D), device=do.device, dtype=BF16)
+        dq32 = fa_bwd(q, k, v, o, do, lse, B, H, Nq, Nk, dk, dv, key_bias, scale)
+        dq_pre = torch.empty((B * Nq, D), device=do.device, dtype=BF16)
+        dk_pre = torch.empty((B * Nk, D), device=do.device, dtype=BF16)
+        qknorm_rope_bwd(dq32, dk, q_pre, k_pre, wq, wk, cos, sin, dq_pre, dk_pre)
+        return dq_pre, dk_pre, dv, None, None, None, None, None, None, None, None, None, None
+
+
+def linear(x, W, b=None, lora=None, gate=None, rows_per_gate=0, res=None):
+    A, B, s = lora if lora is not None else (None, None, 1.0)
+    return LinearFn.apply(x, W, b, A, B, s, gate, rows_per_gate, res)
