@@ -1,0 +1,310 @@
+#!/usr/bin/env python
+"""bench.py — LTXV-2B LoRA(attn2) + caption-projection rectified-flow train step, latent tokens/s.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload cfg2|cfg3|cfg1] [--impl b200|reference]
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A step = one optimiser micro-step of the hot path on one synthetic batch per GPU: noising + velocity
+target, Transformer3DModel forward (28 blocks), loss, backward, bucketed gradient all-reduce (N > 1)
+and the AdamW update of the 27.3 M trainable parameters.  Prints ONE JSON line (rank 0).
+
+  value  : whole-job latent tokens/s with the batch already resident in HBM
+  e2e    : the same metric through the public API with the batch copied from pinned host memory
+           every step and the loss read back every step
+  roofline     : the dominant kernel family, timed live with CUDA events inside the timed region
+  cpu_baseline : the oracle (plain-torch restatement of the reference, fp32) on the host cores,
+                 on a bounded sample (BASELINE config 1: 256 latent tokens)
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (batch per GPU, latent F, H, W, description)
+    "cfg1": (1, 4, 8, 8, "LTXV-2B LoRA train step bs1 25x256x256 (256 latent tokens)"),
+    "cfg2": (1, 16, 16, 24, "LTXV-2B bf16 LoRA train step bs1 121x512x768 (6144 latent tokens)"),
+    "cfg3": (4, 13, 16, 16, "LTXV-2B bf16 LoRA train step bs4/GPU 97x512x512 (4x3328 latent tokens)"),
+}
+METRIC = "LTXV-2B train-step latent tok/s"
+UNIT = "latent tokens/s"
+N_CTX, VALID_CTX, LORA_RANK = 256, 15, 32
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"tflops": d.get("bf16_tflops_sustained", d.get("bf16_tflops")), "gbs": d.get("hbm_gbs"),
+                "source": "MEASURED_PEAKS.json (bf16_tflops_sustained / hbm_gbs), of measured"}
+    return {"tflops": 1400.0, "gbs": 6650.0, "source": "B200_PROFILING.md fallback (~1.4 PF sustained, 6.65 TB/s), of fallback"}
+
+
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=lambda: [self.lines.append(l) for l in self.proc.stdout], daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        for l in self.lines:
+            f = [x.strip() for x in l.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx = float(f[1])
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------
+# CPU reference arm: the oracle port (plain-torch restatement of the reference), fp32, host cores
+# ---------------------------------------------------------------------------------------------
+def cpu_reference(steps, warmup, quiet=True):
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import ref_block as rb
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    cfg = dict(rb.LTXV_2B)
+    b, f, h, w, _ = WORKLOADS["cfg1"]
+    P = rb.init_params(cfg, LORA_RANK, seed=0)
+    P = {k: v.requires_grad_(rb.is_trainable(k)) for k, v in P.items()}
+    batch = rb.synthetic_batch(cfg, b, f, h, w, N_CTX, 1234, VALID_CTX)
+    t = torch.tensor([0.4] * b)
+    times = []
+    for i in range(warmup + steps):
+        for v in P.values():
+            v.grad = None
+        t0 = time.perf_counter()
+        loss, _ = rb.train_step_loss(P, cfg, batch["latents"], batch["ref_image_latents"], batch["pose_latents"],
+                                     batch["prompt_embeds"], batch["prompt_mask"], t, batch["noise"])
+        loss.backward()
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+    tokens = b * f * h * w
+    sec = sum(times) / len(times)
+    return {"value": tokens / sec, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"BASELINE config 1: {tokens} latent tokens (25x256x256, bs1), fp32, all 28 blocks, LoRA r=32 + "
+                      f"caption projection fwd+bwd, {steps} timed step(s) after {warmup} warm-up, {sec:.2f} s/step",
+            "ms_per_step": sec * 1e3}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps, warmup = min(args.steps, 3), min(args.warmup, 1)
+    cb = cpu_reference(steps, warmup)
+    line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus,
+            "steps": steps, "warmup": warmup, "ms_per_step": cb["ms_per_step"], "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOADS[args.workload][4], "sample": cb["sample"]},
+            "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------
+# b200 arm
+# ---------------------------------------------------------------------------------------------
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    from b200_ltx import api, lib, lora, ops, train
+    from b200_ltx.dp import GradBucketer
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    lib.require_device()
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+    B, F, H, W, desc = WORKLOADS[args.workload]
+    N = F * H * W
+    cfg = dict(api.LTXV_2B_CONFIG)
+    if args.layers:
+        cfg["num_layers"] = args.layers  # debugging only; flagged in the JSON line
+
+    torch.manual_seed(0)
+    model = api.build_model(cfg, device=dev)
+    model = lora.apply_training_strategy(model, LORA_RANK, LORA_RANK)
+    g = torch.Generator(device="cpu").manual_seed(1)
+    for n, p in model.named_parameters():
+        if "lora_B" in n:
+            p.data.copy_(torch.randn(p.shape, generator=g) * 0.02)  # non-zero B: dA != 0
+    model.train()
+    named = [(n, p) for n, p in model.named_parameters() if p.requires_grad]
+    bucketer = GradBucketer(named) if world > 1 else None
+    opt = torch.optim.AdamW([p for _, p in named], lr=1e-4, fused=True)
+    sched, patch = api.RectifiedFlowScheduler(), api.SymmetricPatchifier(1)
+
+    class Cfg:
+        rf_log_normal_mu, rf_log_normal_sigma = -0.5, 1.0
+        rf_quantile_min, rf_quantile_max = 0.005, 0.999
+        transformer_loss_weight = 1.0
+
+    gd = torch.Generator(device="cpu").manual_seed(1234 + rank)
+    host = {"latents": torch.randn(B, 128, F, H, W, generator=gd).bfloat16().pin_memory(),
+            "pose_latents": torch.randn(B, 128, F, H, W, generator=gd).bfloat16().pin_memory(),
+            "ref_image_latents": torch.randn(B, 128, 1, H, W, generator=gd).bfloat16().pin_memory()}
+    prompt = torch.randn(1, N_CTX, cfg["caption_channels"], generator=torch.Generator().manual_seed(5)).bfloat16().to(dev)
+    mask = torch.ones(1, N_CTX, dtype=torch.long)
+    mask[:, VALID_CTX:] = 0
+    mask = mask.to(dev)
+    h2d_bytes = sum(v.numel() * v.element_size() for v in host.values())
+    loss_host = torch.empty((), dtype=torch.float32).pin_memory()
+
+    def step(batch):
+        if bucketer is not None:
+            bucketer.zero_grad()
+        else:
+            opt.zero_grad(set_to_none=True)
+        loss, _, _, _ = train.train_step(model, batch, sched, patch, Cfg, prompt, mask, device=dev)
+        loss.backward()
+        if bucketer is not None:
+            bucketer.finish()
+        opt.step()
+        return loss
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        sync_all()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        sync_all()
+        return float(ms)
+
+    resident = {k: v.to(dev) for k, v in host.items()}
+
+    # warm-up, with every kernel family timed to find the dominant one
+    ops.timer = ops.KernelTimer()
+    for _ in range(max(args.warmup, 3)):
+        last = step(resident)
+    fam = ops.timer.summary()
+    ops.timer = None
+    dominant = max((f for f in fam if fam[f]["unit"] == "flop"), key=lambda f: fam[f]["ms"])
+    share = {f: round(d["ms"] / sum(x["ms"] for x in fam.values()), 4) for f, d in sorted(fam.items(), key=lambda kv: -kv[1]["ms"])}
+
+    # timed region 1: device-resident inputs
+    sampler = ClockSampler(torch.cuda.current_device() if "CUDA_VISIBLE_DEVICES" not in os.environ else local)
+    sampler.start()
+    ops.timer = ops.KernelTimer([dominant])
+    l0 = ops.launch_count
+    ms_total = timed(lambda: step(resident), args.steps)
+    launches = (ops.launch_count - l0) // args.steps
+    dom = ops.timer.summary()[dominant]
+    ops.timer = None
+    clocks = sampler.stop()
+
+    # timed region 2: end to end (pinned host -> device every step, loss read back every step)
+    def e2e_step():
+        batch = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
+        loss = step(batch)
+        loss_host.copy_(loss.detach().float(), non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return float(loss_host)
+    for _ in range(2):
+        e2e_step()
+    ms_e2e = timed(e2e_step, args.steps)
+
+    tokens_step = B * N * world
+    value = tokens_step / (ms_total / args.steps / 1e3)
+    e2e_value = tokens_step / (ms_e2e / args.steps / 1e3)
+    peaks = load_peaks()
+    achieved = dom["work"] / (dom["ms"] / 1e3) / 1e12
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tp):
+        traffic = json.load(open(tp)).get(dominant)
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+                "config": {"workload": desc, "tokens_per_gpu_step": B * N, "caption_tokens": N_CTX,
+                           "valid_caption_tokens": VALID_CTX, "lora_rank": LORA_RANK, "layers": cfg["num_layers"],
+                           "optimizer": "AdamW(fused) on 27.3M trainable params, inside the timed step",
+                           "parallelism": f"dp{world}",
+                           "l2": "not flushed: every step streams 3.85 GB of weights plus >10 GB of activations, far larger than the 126 MB L2"},
+                "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
+                        "h2d_bytes_per_step": h2d_bytes * world, "d2h_bytes_per_step": 4 * world},
+                "gpu_launches": launches,
+                "roofline": {"kernel": dominant, "bound": "tensor", "achieved": achieved, "peak": peaks["tflops"],
+                             "unit": "TFLOP/s", "frac": achieved / peaks["tflops"], "traffic": traffic,
+                             "peak_source": peaks["source"], "launches_timed": dom["launches"],
+                             "avg_launch_ms": dom["ms"] / dom["launches"],
+                             "time_share_by_family": share},
+                "clocks": clocks, "loss": float(last)}
+        if args.layers:
+            line["config"]["INVALID_reduced_layers"] = True
+        if world == 1 and not args.no_cpu_baseline:
+            cb = cpu_reference(2, 1)
+            line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="cfg2", choices=list(WORKLOADS))
+    ap.add_argument("--layers", type=int, default=0, help="debug only: fewer blocks (marks the line INVALID)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

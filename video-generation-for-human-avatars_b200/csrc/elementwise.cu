@@ -321,8 +321,9 @@ __global__ void __launch_bounds__(256) rf_noise_kernel(const bf16* __restrict__ 
     Row8 a = ld_bf16x8(x0 + i * 8), e = ld_bf16x8(noise + i * 8), o1, o2;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      o1.v[j] = (1.f - tt) * a.v[j] + tt * e.v[j];
-      o2.v[j] = -1.f * a.v[j] + 1.f * e.v[j];
+      // separate roundings (no FMA contraction): bit-identical to torch's alphas * x0 + sigmas * eps
+      o1.v[j] = __fadd_rn(__fmul_rn(1.f - tt, a.v[j]), __fmul_rn(tt, e.v[j]));
+      o2.v[j] = __fadd_rn(-a.v[j], e.v[j]);
     }
     if (xt) st_bf16x8(xt + i * 8, o1);
     if (v) st_bf16x8(v + i * 8, o2);

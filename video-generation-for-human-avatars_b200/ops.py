@@ -39,6 +39,46 @@ def _count(n=1):
     launch_count += n
 
 
+class KernelTimer:
+    """CUDA-event timing of kernel families on the launching stream (bench.py roofline numbers).
+    `families=None` records everything; otherwise only the named families."""
+
+    def __init__(self, families=None):
+        self.families = set(families) if families else None
+        self.records = []  # (family, work, unit, start_event, end_event)
+
+    def want(self, family):
+        return self.families is None or family in self.families
+
+    def summary(self):
+        torch.cuda.synchronize()
+        out = {}
+        for fam, work, unit, e0, e1 in self.records:
+            d = out.setdefault(fam, {"ms": 0.0, "work": 0.0, "launches": 0, "unit": unit})
+            d["ms"] += e0.elapsed_time(e1)
+            d["work"] += work
+            d["launches"] += 1
+        return out
+
+
+timer: Optional[KernelTimer] = None
+
+
+def _call(family, work, unit, cfn, *args, launches=1):
+    """Invoke one C-ABI entry point; optionally bracket it with CUDA events on the current stream."""
+    t = timer
+    if t is not None and t.want(family):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        rc = cfn(*args)
+        e1.record()
+        t.records.append((family, work, unit, e0, e1))
+    else:
+        rc = cfn(*args)
+    _lib.check(rc, cfn.__name__)
+    _count(launches)
+
+
 # ---------------------------------------------------------------------------------------------
 # raw ops
 # ---------------------------------------------------------------------------------------------
@@ -79,14 +119,12 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, a_rows_are_k=False, b_rows_are_k=F
             raise _lib.B200Error("gemm: gate shape / rows_per_gate mismatch")
     if bias is not None and (bias.dtype != BF16 or bias.numel() != N or not bias.is_contiguous()):
         raise _lib.B200Error("gemm: bias must be a contiguous bf16 vector of length N")
-    rc = _L().b200_gemm_bf16(
+    _call("gemm", 2.0 * M * N * (K + K2), "flop", _L().b200_gemm_bf16,
         _p(a), a.stride(0), int(a_rows_are_k), _p(b), b.stride(0), int(b_rows_are_k),
         _p(a2), a2.stride(0) if a2 is not None else 0, _p(b2), b2.stride(0) if b2 is not None else 0, K2,
         _p(out), out.stride(0), int(out.dtype == torch.float32), M, N, K, epilogue,
         _p(bias), _p(gate), gate_stride, rows_per_gate, _p(res), res.stride(0) if res is not None else 0,
         _p(aux), aux.stride(0) if aux is not None else 0, block_n, _s())
-    _lib.check(rc, "b200_gemm_bf16")
-    _count()
     return out
 
 
@@ -102,10 +140,8 @@ def norm_mod_fwd(x, scale, shift, rows_per_mod, eps, layernorm=False, out=None):
             mod_stride = t.stride(0)
     if scale is not None and shift is not None and scale.stride(0) != shift.stride(0):
         raise _lib.B200Error("norm_mod: scale and shift must share a row stride")
-    rc = _L().b200_norm_mod_fwd(_p(x), x.stride(0), _p(out), out.stride(0), _p(scale), _p(shift),
+    _call("norm_mod_fwd", 4.0 * rows * D, "byte", _L().b200_norm_mod_fwd, _p(x), x.stride(0), _p(out), out.stride(0), _p(scale), _p(shift),
                                 mod_stride, rows, D, rows_per_mod, eps, int(layernorm), _s())
-    _lib.check(rc, "b200_norm_mod_fwd")
-    _count()
     return out
 
 
@@ -116,12 +152,10 @@ def norm_mod_bwd(dy, x, scale, rows_per_mod, eps, layernorm=False, dres=None):
     dx = torch.empty((rows, D), device=x.device, dtype=BF16)
     if dres is not None:
         _chk2d(dres, "norm_mod_bwd dres")
-    rc = _L().b200_norm_mod_bwd(_p(dy), dy.stride(0), _p(x), x.stride(0), _p(scale),
+    _call("norm_mod_bwd", (8.0 if dres is not None else 6.0) * rows * D, "byte", _L().b200_norm_mod_bwd, _p(dy), dy.stride(0), _p(x), x.stride(0), _p(scale),
                                 scale.stride(0) if scale is not None else 0, _p(dres),
                                 dres.stride(0) if dres is not None else 0, _p(dx), dx.stride(0), rows, D,
                                 rows_per_mod, eps, int(layernorm), _s())
-    _lib.check(rc, "b200_norm_mod_bwd")
-    _count()
     return dx
 
 
@@ -129,28 +163,24 @@ def qknorm_rope_fwd(xq, xk, wq, wk, cos, sin, oq, ok, eps=1e-5):
     rows_q = xq.shape[0] if xq is not None else 0
     rows_k = xk.shape[0] if xk is not None else 0
     D = (xq if xq is not None else xk).shape[1]
-    rc = _L().b200_qknorm_rope_fwd(
+    _call("qknorm_rope_fwd", (4.0 + (4.0 if cos is not None else 0.0)) * (rows_q + rows_k) * D, "byte", _L().b200_qknorm_rope_fwd,
         _p(xq), xq.stride(0) if xq is not None else 0, _p(xk), xk.stride(0) if xk is not None else 0,
         _p(wq), _p(wk), _p(cos), _p(sin), cos.stride(0) if cos is not None else 0,
         _p(oq), oq.stride(0) if oq is not None else 0, _p(ok), ok.stride(0) if ok is not None else 0,
         rows_q, rows_k, D, eps, _s())
-    _lib.check(rc, "b200_qknorm_rope_fwd")
-    _count()
 
 
 def qknorm_rope_bwd(dq, dk, xq, xk, wq, wk, cos, sin, oq, ok, eps=1e-5):
     rows_q = xq.shape[0] if xq is not None else 0
     rows_k = xk.shape[0] if xk is not None else 0
     D = (xq if xq is not None else xk).shape[1]
-    rc = _L().b200_qknorm_rope_bwd(
+    _call("qknorm_rope_bwd", 10.0 * (rows_q + rows_k) * D, "byte", _L().b200_qknorm_rope_bwd,
         _p(dq), dq.stride(0) if dq is not None else 0, int(dq is not None and dq.dtype == torch.float32),
         _p(dk), dk.stride(0) if dk is not None else 0, int(dk is not None and dk.dtype == torch.float32),
         _p(xq), xq.stride(0) if xq is not None else 0, _p(xk), xk.stride(0) if xk is not None else 0,
         _p(wq), _p(wk), _p(cos), _p(sin), cos.stride(0) if cos is not None else 0,
         _p(oq), oq.stride(0) if oq is not None else 0, _p(ok), ok.stride(0) if ok is not None else 0,
         rows_q, rows_k, D, eps, _s())
-    _lib.check(rc, "b200_qknorm_rope_bwd")
-    _count()
 
 
 def fa_fwd(q, k, v, B, H, Nq, Nk, key_bias=None, scale=0.125, need_lse=True):
@@ -162,10 +192,8 @@ def fa_fwd(q, k, v, B, H, Nq, Nk, key_bias=None, scale=0.125, need_lse=True):
     if key_bias is not None and (key_bias.dtype != torch.float32 or tuple(key_bias.shape) != (B, Nk)
                                  or not key_bias.is_contiguous()):
         raise _lib.B200Error("fa_fwd: key_bias must be contiguous fp32 [B, Nk]")
-    rc = _L().b200_fa_fwd(_p(q), q.stride(0), _p(k), k.stride(0), _p(v), v.stride(0), _p(o), o.stride(0),
+    _call("fa_fwd", 4.0 * B * H * Nq * Nk * 64, "flop", _L().b200_fa_fwd, _p(q), q.stride(0), _p(k), k.stride(0), _p(v), v.stride(0), _p(o), o.stride(0),
                           _p(lse), _p(key_bias), B, H, Nq, Nk, 64, scale, _s())
-    _lib.check(rc, "b200_fa_fwd")
-    _count()
     return o, lse
 
 
@@ -173,14 +201,11 @@ def fa_bwd(q, k, v, o, do, lse, B, H, Nq, Nk, dk, dv, key_bias=None, scale=0.125
     """Returns dq as fp32 [B*Nq, H*64]; writes bf16 dk/dv into the given (possibly strided) views."""
     _chk2d(do, "fa_bwd do")
     delta = torch.empty((B, H, Nq), device=q.device, dtype=torch.float32)
-    rc = _L().b200_attn_delta(_p(o), o.stride(0), _p(do), do.stride(0), _p(delta), B, H, Nq, _s())
-    _lib.check(rc, "b200_attn_delta")
+    _call("attn_delta", 4.0 * B * Nq * H * 64, "byte", _L().b200_attn_delta, _p(o), o.stride(0), _p(do), do.stride(0), _p(delta), B, H, Nq, _s())
     dq = torch.zeros((B * Nq, H * 64), device=q.device, dtype=torch.float32)
-    rc = _L().b200_fa_bwd(_p(q), q.stride(0), _p(k), k.stride(0), _p(v), v.stride(0), _p(do), do.stride(0),
+    _call("fa_bwd", 8.0 * B * H * Nq * Nk * 64, "flop", _L().b200_fa_bwd, _p(q), q.stride(0), _p(k), k.stride(0), _p(v), v.stride(0), _p(do), do.stride(0),
                           _p(lse), _p(delta), _p(key_bias), _p(dq), dq.stride(0), _p(dk), dk.stride(0),
                           _p(dv), dv.stride(0), B, H, Nq, Nk, 64, scale, _s())
-    _lib.check(rc, "b200_fa_bwd")
-    _count(2)
     return dq
 
 
@@ -191,9 +216,7 @@ def rf_noise(x0, noise, t, want_xt=True, want_v=True):
     xt = torch.empty_like(x0) if want_xt else None
     v = torch.empty_like(x0) if want_v else None
     B = x0.shape[0]
-    rc = _L().b200_rf_noise(_p(x0), _p(noise), _p(t), _p(xt), _p(v), B, x0.numel() // max(B, 1), _s())
-    _lib.check(rc, "b200_rf_noise")
-    _count()
+    _call("rf_noise", 2.0 * x0.numel() * (2 + int(want_xt) + int(want_v)), "byte", _L().b200_rf_noise, _p(x0), _p(noise), _p(t), _p(xt), _p(v), B, x0.numel() // max(B, 1), _s())
     return xt, v
 
 
@@ -204,9 +227,7 @@ def rf_loss(out, target, grad_scale=1.0, want_grad=True):
     loss = torch.empty((), device=out.device, dtype=torch.float32)
     nbytes = _L().b200_rf_loss_workspace_bytes()
     ws = torch.empty(nbytes, device=out.device, dtype=torch.uint8)
-    rc = _L().b200_rf_loss(_p(out), _p(target), _p(dout), _p(loss), out.numel(), grad_scale, _p(ws), nbytes, _s())
-    _lib.check(rc, "b200_rf_loss")
-    _count(2)
+    _call("rf_loss", 2.0 * out.numel() * (2 + int(want_grad)), "byte", _L().b200_rf_loss, _p(out), _p(target), _p(dout), _p(loss), out.numel(), grad_scale, _p(ws), nbytes, _s(), launches=2)
     return loss, dout
 
 
@@ -219,9 +240,7 @@ def lerp_condition_(tokens, ref, pose, w_ref=0.85, w_pose=0.5):
             raise _lib.B200Error("lerp_condition: contiguous bf16 tensors required")
     if pose.shape[2] * HW != N or ref.shape[2] != 1:
         raise _lib.B200Error("lerp_condition: pose/ref shapes do not match the token count")
-    rc = _L().b200_lerp_condition(_p(tokens), _p(ref), _p(pose), B, N, C, HW, w_ref, w_pose, _s())
-    _lib.check(rc, "b200_lerp_condition")
-    _count()
+    _call("lerp_condition", 6.0 * tokens.numel(), "byte", _L().b200_lerp_condition, _p(tokens), _p(ref), _p(pose), B, N, C, HW, w_ref, w_pose, _s())
     return tokens
 
 
@@ -229,19 +248,15 @@ def rowscale(x, g, rows_per_mod):
     _chk2d(x, "rowscale x")
     _chk2d(g, "rowscale g")
     out = torch.empty((x.shape[0], x.shape[1]), device=x.device, dtype=BF16)
-    rc = _L().b200_rowscale(_p(x), x.stride(0), _p(g), g.stride(0), _p(out), out.stride(0), x.shape[0],
+    _call("rowscale", 4.0 * x.numel(), "byte", _L().b200_rowscale, _p(x), x.stride(0), _p(g), g.stride(0), _p(out), out.stride(0), x.shape[0],
                             x.shape[1], rows_per_mod, _s())
-    _lib.check(rc, "b200_rowscale")
-    _count()
     return out
 
 
 def colsum(x):
     _chk2d(x, "colsum x")
     out = torch.empty((x.shape[1],), device=x.device, dtype=torch.float32)
-    rc = _L().b200_colsum(_p(x), x.stride(0), _p(out), x.shape[0], x.shape[1], _s())
-    _lib.check(rc, "b200_colsum")
-    _count()
+    _call("colsum", 2.0 * x.numel(), "byte", _L().b200_colsum, _p(x), x.stride(0), _p(out), x.shape[0], x.shape[1], _s())
     return out
 
 
@@ -408,3 +423,47 @@ class AttnCoreFn(torch.autograd.Function):
 def linear(x, W, b=None, lora=None, gate=None, rows_per_gate=0, res=None):
     A, B, s = lora if lora is not None else (None, None, 1.0)
     return LinearFn.apply(x, W, b, A, B, s, gate, rows_per_gate, res)
+
+
+class SelfAttnFn(torch.autograd.Function):
+    """attn1 of a block with frozen projections, as one autograd node:
+
+        y = gate * (FA(rope(qnorm(x Wq^T)), rope(knorm(x Wk^T)), x Wv^T) Wo^T + bo) + res
+
+    Forward: 3 projection GEMMs into one packed [M,3D] buffer, qk-norm+RoPE, flash attention, output
+    GEMM with the AdaLN gate and the residual in its epilogue.  Backward: one dgrad GEMM over the
+    packed [M,3D] gradient against the cached [3D,D] concatenation of the frozen weights."""
+
+    @staticmethod
+    def forward(ctx, x, Wq, bq, Wk, bk, Wv, bv, Wqkv, wqn, wkn, cos, sin, Wo, bo, gate, rows_per_gate, res,
+                key_bias, B, H, N, scale):
+        M, D = x.shape[0], H * 64
+        qkv = torch.empty((M, 3 * D), device=x.device, dtype=BF16)
+        gemm(x, Wq, out=qkv[:, :D], bias=bq)
+        gemm(x, Wk, out=qkv[:, D:2 * D], bias=bk)
+        gemm(x, Wv, out=qkv[:, 2 * D:], bias=bv)
+        qk = torch.empty((M, 2 * D), device=x.device, dtype=BF16)
+        qknorm_rope_fwd(qkv[:, :D], qkv[:, D:2 * D], wqn, wkn, cos, sin, qk[:, :D], qk[:, D:])
+        o, lse = fa_fwd(qk[:, :D], qk[:, D:], qkv[:, 2 * D:], B, H, N, N, key_bias, scale)
+        y = gemm(o, Wo, bias=bo, gate=gate, rows_per_gate=rows_per_gate, res=res)
+        ctx.save_for_backward(qkv, qk, o, lse, Wqkv, wqn, wkn, cos, sin, Wo, gate, key_bias)
+        ctx.meta = (B, H, N, scale, rows_per_gate, res is not None)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        qkv, qk, o, lse, Wqkv, wqn, wkn, cos, sin, Wo, gate, key_bias = ctx.saved_tensors
+        B, H, N, scale, rpg, has_res = ctx.meta
+        D = H * 64
+        M = qkv.shape[0]
+        dy = dy if dy.stride(1) == 1 else dy.contiguous()
+        g = rowscale(dy, gate, rpg) if gate is not None else dy
+        do = gemm(g, Wo, b_rows_are_k=True)
+        dqkv = torch.empty((M, 3 * D), device=dy.device, dtype=BF16)
+        dk_post = torch.empty((M, D), device=dy.device, dtype=BF16)
+        dq32 = fa_bwd(qk[:, :D], qk[:, D:], qkv[:, 2 * D:], o, do, lse, B, H, N, N, dk_post, dqkv[:, 2 * D:],
+                      key_bias, scale)
+        qknorm_rope_bwd(dq32, dk_post, qkv[:, :D], qkv[:, D:2 * D], wqn, wkn, cos, sin, dqkv[:, :D], dqkv[:, D:2 * D])
+        dx = gemm(dqkv, Wqkv, b_rows_are_k=True) if ctx.needs_input_grad[0] else None
+        dres = dy if (has_res and ctx.needs_input_grad[16]) else None
+        return (dx,) + (None,) * 15 + (dres,) + (None,) * 5
