@@ -13,7 +13,8 @@
 //   dK  += dS^T Q             (A = dS^T K-major,            B = Q  tile read MN-major)
 //   dQ   = dS   K             (A = the same dS^T bytes read MN-major, B = K tile read MN-major)
 // dV/dK accumulate in TMEM over the whole loop; dQ is a per-(q tile, k tile) partial that is
-// reduced across key-tile CTAs with vectorised fp32 red.global.add into a caller-zeroed buffer.
+// reduced across key-tile CTAs with TMA reduce-add (cp.reduce.async.bulk.tensor) into a caller-zeroed
+// fp32 buffer (per-lane red.global.add measured ~10 k cycles per tile: the atomics were the bottleneck).
 // TMEM: S^T 128 | dP^T 128 | dV 64 | dK 64 | dQ 64 = 448 of 512 columns.
 #include "api_internal.h"
 #include "common.cuh"
@@ -39,8 +40,14 @@ struct FaBwdParams {
 };
 
 constexpr int FA_BWD_SMEM = 16384 * 2 /*K,V*/ + 2 * 32768 /*Q,dO x2*/ + 2 * 32768 /*P^T,dS^T*/ +
-                            2 * 2 * 512 /*lse, delta x2*/ + 128;
+                            32768 /*dQ staging*/ + 2 * 2 * 512 /*lse, delta x2*/ + 128;
 constexpr float kLog2eB = 1.4426950408889634f;
+
+__device__ __forceinline__ float ex2_approx_b(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 
 __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c),
@@ -51,12 +58,13 @@ __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float 
 __global__ void __launch_bounds__(192, 1)
 fa_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
               const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmdO,
-              const __grid_constant__ FaBwdParams p) {
+              const __grid_constant__ CUtensorMap tmdQ, const __grid_constant__ FaBwdParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t sbase = smem_u32(smem_raw);
   const uint32_t sK = sbase, sV = sbase + 16384, sQdO = sbase + 32768;  // stage s: Q at +s*32768, dO at +16384
   const uint32_t sPt = sQdO + 65536, sdSt = sPt + 32768;
-  const uint32_t sStat = sdSt + 32768;  // [2 stages][lse 128 | delta 128] fp32
+  const uint32_t sdQ = sdSt + 32768;    // fp32 [2 halves of 32 cols][128 q rows][128 B], 128B-swizzled
+  const uint32_t sStat = sdQ + 32768;   // [2 stages][lse 128 | delta 128] fp32
   const uint32_t bar = sStat + 2048;
   const uint32_t kv_full = bar, qd_full0 = bar + 8, qd_empty0 = bar + 24, s_full = bar + 40,
                  pds_full = bar + 48, mma2_done = bar + 56, tmem_slot = bar + 64;
@@ -74,6 +82,7 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
     tma_prefetch_desc(&tmK);
     tma_prefetch_desc(&tmV);
     tma_prefetch_desc(&tmdO);
+    tma_prefetch_desc(&tmdQ);
     mbar_init(kv_full, 1);
     for (int s = 0; s < 2; ++s) {
       mbar_init(qd_full0 + 8 * s, 1);
@@ -112,7 +121,9 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
     const uint32_t idesc_kv = make_idesc_bf16(128, 64, 0, 1);   // A K-major, B MN-major
     const uint32_t idesc_dq = make_idesc_bf16(128, 64, 1, 1);   // A MN-major, B MN-major
     mbar_wait(kv_full, 0);
-    for (int i = 0; i < T; ++i) {
+    // S^T / dP^T of tile i+1 are issued right behind dV/dK/dQ of tile i, so the tensor pipe keeps
+    // running while the compute warps drain dQ_i and the next S^T is ready when they come back.
+    auto issue_scores = [&](int i) {
       const int s = i & 1;
       const uint32_t sQ = sQdO + s * 32768, sdO = sQ + 16384;
       mbar_wait(qd_full0 + 8 * s, (i >> 1) & 1);
@@ -126,6 +137,11 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
         umma_ss(tdPt, make_smem_desc(sV + k * 32, 16, 1024), make_smem_desc(sdO + k * 32, 16, 1024),
                 idesc_s, k > 0 ? 1u : 0u);
       umma_commit(s_full);
+    };
+    if (T > 0) issue_scores(0);
+    for (int i = 0; i < T; ++i) {
+      const int s = i & 1;
+      const uint32_t sQ = sQdO + s * 32768, sdO = sQ + 16384;
       mbar_wait(pds_full, i & 1);
       tc_fence_after();
 #pragma unroll
@@ -142,6 +158,7 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
                 make_smem_desc(sK + k * 2048, 8192, 1024), idesc_dq, k > 0 ? 1u : 0u);
       umma_commit(qd_empty0 + 8 * s);
       umma_commit(mma2_done);
+      if (i + 1 < T) issue_scores(i + 1);
     }
   } else if (warp >= 2) {
     const int quad = warp & 3;
@@ -153,14 +170,20 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
     const float kbias = (p.key_bias && key_ok) ? p.key_bias[(int64_t)b * p.Nk + key] * kLog2eB : 0.f;
     const float* lse_g = p.lse + ((int64_t)b * p.H + h) * p.Nq;
     const float* del_g = p.delta + ((int64_t)b * p.H + h) * p.Nq;
+    // lse / delta of tile i+1 are fetched one tile ahead (their global-load latency is off the
+    // critical path); +inf lse => P = 0 for padded queries
+    float nxt_lse = ctid < p.Nq ? lse_g[ctid] * kLog2eB : INFINITY;
+    float nxt_del = ctid < p.Nq ? del_g[ctid] : 0.f;
     for (int i = 0; i < T; ++i) {
       const int s = i & 1;
       const int q0 = i * 128;
       float* st = stat + s * 256;
+      st[ctid] = nxt_lse;
+      st[128 + ctid] = nxt_del;
       {
-        const int q = q0 + ctid;
-        st[ctid] = q < p.Nq ? lse_g[q] * kLog2eB : INFINITY;  // +inf => P = 0 for padded queries
-        st[128 + ctid] = q < p.Nq ? del_g[q] : 0.f;
+        const int qn = q0 + 128 + ctid;
+        nxt_lse = qn < p.Nq ? lse_g[qn] * kLog2eB : INFINITY;
+        nxt_del = qn < p.Nq ? del_g[qn] : 0.f;
       }
       named_bar_sync(1, 128);
       mbar_wait(s_full, i & 1);
@@ -171,55 +194,70 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
         tmem_ld32(tSt + lane_bits + c * 32, rs);
         tmem_ld32(tdPt + lane_bits + c * 32, rd);
         tmem_ld_wait();
-        float pv[32], ds[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const float lse2 = st[c * 32 + j], dl = st[128 + c * 32 + j];
-          float pr = exp2f(__uint_as_float(rs[j]) * p.scale_log2 + kbias - lse2);
-          if (!key_ok) pr = 0.f;
-          pv[j] = pr;
-          ds[j] = pr * (__uint_as_float(rd[j]) - dl) * p.scale;
-        }
         const uint32_t off0 = (c >> 1) * 16384;
+        const float4* lse4 = reinterpret_cast<const float4*>(st + c * 32);
+        const float4* del4 = reinterpret_cast<const float4*>(st + 128 + c * 32);
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
+          float pv[8], ds[8];
+#pragma unroll
+          for (int h4 = 0; h4 < 2; ++h4) {
+            const float4 ls = lse4[g * 2 + h4], dl = del4[g * 2 + h4];  // broadcast LDS.128
+            const float lsv[4] = {ls.x, ls.y, ls.z, ls.w}, dlv[4] = {dl.x, dl.y, dl.z, dl.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const int j = g * 8 + h4 * 4 + e;
+              float pr = ex2_approx_b(fmaf(__uint_as_float(rs[j]), p.scale_log2, kbias - lsv[e]));
+              if (!key_ok) pr = 0.f;
+              pv[h4 * 4 + e] = pr;
+              ds[h4 * 4 + e] = pr * (__uint_as_float(rd[j]) - dlv[e]) * p.scale;
+            }
+          }
           const uint32_t o = off0 + sw128_off(row, (c & 1) * 4 + g);
           asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sPt + o),
-                       "r"(pack_bf16x2(pv[g * 8 + 0], pv[g * 8 + 1])),
-                       "r"(pack_bf16x2(pv[g * 8 + 2], pv[g * 8 + 3])),
-                       "r"(pack_bf16x2(pv[g * 8 + 4], pv[g * 8 + 5])),
-                       "r"(pack_bf16x2(pv[g * 8 + 6], pv[g * 8 + 7]))
+                       "r"(pack_bf16x2(pv[0], pv[1])), "r"(pack_bf16x2(pv[2], pv[3])),
+                       "r"(pack_bf16x2(pv[4], pv[5])), "r"(pack_bf16x2(pv[6], pv[7]))
                        : "memory");
           asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sdSt + o),
-                       "r"(pack_bf16x2(ds[g * 8 + 0], ds[g * 8 + 1])),
-                       "r"(pack_bf16x2(ds[g * 8 + 2], ds[g * 8 + 3])),
-                       "r"(pack_bf16x2(ds[g * 8 + 4], ds[g * 8 + 5])),
-                       "r"(pack_bf16x2(ds[g * 8 + 6], ds[g * 8 + 7]))
+                       "r"(pack_bf16x2(ds[0], ds[1])), "r"(pack_bf16x2(ds[2], ds[3])),
+                       "r"(pack_bf16x2(ds[4], ds[5])), "r"(pack_bf16x2(ds[6], ds[7]))
                        : "memory");
         }
       }
       fence_proxy_async_smem();
       tc_fence_before();
       mbar_arrive(pds_full);
-      // dQ partial of this (q tile, key tile): TMEM -> fp32 atomics
+      // dQ partial of this (q tile, key tile): TMEM -> swizzled fp32 staging tile -> one TMA
+      // reduce-add (cp.reduce.async.bulk.tensor .add) into the fp32 dQ accumulator in global memory.
       mbar_wait(mma2_done, i & 1);
       tc_fence_after();
-      const int q = q0 + row;
-#pragma unroll 1
-      for (int c = 0; c < 2; ++c) {
-        uint32_t r[32];
-        tmem_ld32(tdQ + lane_bits + c * 32, r);
+      {
+        uint32_t r0[32], r1[32];
+        tmem_ld32(tdQ + lane_bits, r0);
+        tmem_ld32(tdQ + lane_bits + 32, r1);
         tmem_ld_wait();
-        if (q < p.Nq) {
-          float* dst = p.dq + ((int64_t)b * p.Nq + q) * p.lddq + h * 64 + c * 32;
+        tc_fence_before();
+        if (ctid == 0) tma_store_wait_read<0>();  // the previous tile's reduce has finished reading sdQ
+        named_bar_sync(2, 128);
 #pragma unroll
-          for (int g = 0; g < 8; ++g)
-            red_add_v4(dst + g * 4, __uint_as_float(r[g * 4 + 0]), __uint_as_float(r[g * 4 + 1]),
-                       __uint_as_float(r[g * 4 + 2]), __uint_as_float(r[g * 4 + 3]));
+        for (int g = 0; g < 8; ++g) {
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sdQ + sw128_off(row, g)),
+                       "r"(r0[g * 4 + 0]), "r"(r0[g * 4 + 1]), "r"(r0[g * 4 + 2]), "r"(r0[g * 4 + 3])
+                       : "memory");
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sdQ + 16384 + sw128_off(row, g)),
+                       "r"(r1[g * 4 + 0]), "r"(r1[g * 4 + 1]), "r"(r1[g * 4 + 2]), "r"(r1[g * 4 + 3])
+                       : "memory");
+        }
+        fence_proxy_async_smem();
+        named_bar_sync(3, 128);
+        if (ctid == 0) {
+          tma_reduce_add_3d(&tmdQ, sdQ, h * 64, q0, b);
+          tma_reduce_add_3d(&tmdQ, sdQ + 16384, h * 64 + 32, q0, b);
+          tma_store_commit();
         }
       }
-      tc_fence_before();
     }
+    if (ctid == 0) tma_store_wait_all<0>();
     // dK, dV of this key tile
     if (T > 0) {
       bf16* dkr = p.dk + ((int64_t)b * p.Nk + key) * p.lddk + h * 64;
@@ -282,6 +320,14 @@ extern "C" int b200_fa_bwd(const void* q, int64_t ldq, const void* k, int64_t ld
       (rc = make_tmap_tokens(&tmV, v, B, Nk, ldv, H * 64, 128)) ||
       (rc = make_tmap_tokens(&tmdO, dout, B, Nq, lddo, H * 64, 128)))
     return arg_error("fa_bwd: cuTensorMapEncodeTiled failed", rc);
+  CUtensorMap tmdQ;
+  {
+    uint64_t dims[3] = {(uint64_t)H * 64, (uint64_t)Nq, (uint64_t)B};
+    uint64_t str[2] = {(uint64_t)lddq * 4, (uint64_t)Nq * (uint64_t)lddq * 4};
+    uint32_t box[3] = {32, 128, 1};
+    if ((rc = make_tmap(&tmdQ, dq_accum, TM_F32, 3, dims, str, box, true)))
+      return arg_error("fa_bwd: cuTensorMapEncodeTiled failed (dq)", rc);
+  }
   FaBwdParams p;
   p.B = B; p.H = H; p.Nq = Nq; p.Nk = Nk;
   p.q_tiles = (Nq + 127) / 128;
@@ -296,6 +342,6 @@ extern "C" int b200_fa_bwd(const void* q, int64_t ldq, const void* k, int64_t ld
     attr_set = true;
   }
   dim3 grid((Nk + 127) / 128, H, B);
-  fa_bwd_kernel<<<grid, 192, FA_BWD_SMEM, (cudaStream_t)stream>>>(tmQ, tmK, tmV, tmdO, p);
+  fa_bwd_kernel<<<grid, 192, FA_BWD_SMEM, (cudaStream_t)stream>>>(tmQ, tmK, tmV, tmdO, tmdQ, p);
   return launch_status("fa_bwd");
 }

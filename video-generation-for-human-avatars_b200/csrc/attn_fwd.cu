@@ -36,6 +36,118 @@ constexpr int FA_SMEM_TILES = 16384 /*Q*/ + 2 * 32768 /*K,V x2*/ + 32768 /*P*/;
 constexpr int FA_FWD_SMEM = FA_SMEM_TILES + 128;
 constexpr float kLog2e = 1.4426950408889634f;
 
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+
+// ---- fast path (no key bias, full tile): the per-element code is FMNMX / FFMA+MUFU+FADD only.  The
+// next 32-column TMEM chunk is in flight while the current one is processed.
+__device__ __forceinline__ float tile_max_fast(uint32_t t_row, float sl2) {
+  float a0 = -INFINITY, a1 = -INFINITY, a2 = -INFINITY, a3 = -INFINITY;
+  uint32_t ra[32], rb[32];
+  tmem_ld32(t_row, ra);
+  tmem_ld_wait();
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    uint32_t(&cur)[32] = (c & 1) ? rb : ra;
+    uint32_t(&nxt)[32] = (c & 1) ? ra : rb;
+    if (c < 3) tmem_ld32(t_row + (c + 1) * 32, nxt);
+#pragma unroll
+    for (int i = 0; i < 32; i += 4) {
+      a0 = fmaxf(a0, __uint_as_float(cur[i]));
+      a1 = fmaxf(a1, __uint_as_float(cur[i + 1]));
+      a2 = fmaxf(a2, __uint_as_float(cur[i + 2]));
+      a3 = fmaxf(a3, __uint_as_float(cur[i + 3]));
+    }
+    if (c < 3) tmem_ld_wait();
+  }
+  return fmaxf(fmaxf(a0, a1), fmaxf(a2, a3)) * sl2;
+}
+
+__device__ __forceinline__ void store_p8(uint32_t addr, const float (&pv)[8]) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pack_bf16x2(pv[0], pv[1])),
+               "r"(pack_bf16x2(pv[2], pv[3])), "r"(pack_bf16x2(pv[4], pv[5])),
+               "r"(pack_bf16x2(pv[6], pv[7]))
+               : "memory");
+}
+
+__device__ __forceinline__ void tile_exp_fast(uint32_t t_row, uint32_t sP, int row, float sl2, float neg_m,
+                                              float& l0, float& l1, float& l2, float& l3) {
+  uint32_t ra[32], rb[32];
+  tmem_ld32(t_row, ra);
+  tmem_ld_wait();
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    uint32_t(&cur)[32] = (c & 1) ? rb : ra;
+    uint32_t(&nxt)[32] = (c & 1) ? ra : rb;
+    if (c < 3) tmem_ld32(t_row + (c + 1) * 32, nxt);
+    const uint32_t sub = sP + (c >> 1) * 16384;
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      float pv[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) pv[i] = ex2_approx(fmaf(__uint_as_float(cur[g * 8 + i]), sl2, neg_m));
+      l0 += pv[0] + pv[4];
+      l1 += pv[1] + pv[5];
+      l2 += pv[2] + pv[6];
+      l3 += pv[3] + pv[7];
+      store_p8(sub + sw128_off(row, (c & 1) * 4 + g), pv);
+    }
+    if (c < 3) tmem_ld_wait();
+  }
+}
+
+// ---- general path (additive key bias and/or ragged last tile): kept out of line so that it does not
+// weigh on the fast path's registers.
+__device__ __noinline__ float tile_max_general(uint32_t t_row, float sl2, const float* kb, int key0, int Nk) {
+  float mx = -INFINITY;
+#pragma unroll 1
+  for (int c = 0; c < 4; ++c) {
+    uint32_t r[32];
+    tmem_ld32(t_row + c * 32, r);
+    tmem_ld_wait();
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+      const int key = key0 + c * 32 + i;
+      float sc = __uint_as_float(r[i]) * sl2;
+      if (kb != nullptr && key < Nk) sc += __ldg(kb + key) * kLog2e;
+      if (key >= Nk) sc = -INFINITY;
+      mx = fmaxf(mx, sc);
+    }
+  }
+  return mx;
+}
+
+__device__ __noinline__ float tile_exp_general(uint32_t t_row, uint32_t sP, int row, float sl2, float neg_m,
+                                               const float* kb, int key0, int Nk) {
+  float l = 0.f;
+#pragma unroll 1
+  for (int c = 0; c < 4; ++c) {
+    uint32_t r[32];
+    tmem_ld32(t_row + c * 32, r);
+    tmem_ld_wait();
+    const uint32_t sub = sP + (c >> 1) * 16384;
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      float pv[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int key = key0 + c * 32 + g * 8 + i;
+        float x = __uint_as_float(r[g * 8 + i]) * sl2;
+        if (kb != nullptr && key < Nk) x += __ldg(kb + key) * kLog2e;
+        if (key >= Nk) x = -INFINITY;
+        pv[i] = ex2_approx(x + neg_m);
+        l += pv[i];
+      }
+      store_p8(sub + sw128_off(row, (c & 1) * 4 + g), pv);
+    }
+  }
+  return l;
+}
+
 __global__ void __launch_bounds__(192, 2)
 fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
               const __grid_constant__ CUtensorMap tmV, const __grid_constant__ FaFwdParams p) {
@@ -116,28 +228,17 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
     const int row = quad * 32 + lane;
     const uint32_t lane_bits = (uint32_t)(quad * 32) << 16;
     const float* kb = p.key_bias ? p.key_bias + (int64_t)b * p.Nk : nullptr;
-    float m_used = -INFINITY, l = 0.f;
+    const float sl2 = p.scale_log2;
+    float m_used = -INFINITY;
+    float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;
     for (int j = 0; j < T; ++j) {
       const int key0 = j * 128;
-      const bool tail = key0 + 128 > p.Nk;
+      const bool general = (kb != nullptr) || (key0 + 128 > p.Nk);  // bias or ragged last tile
       mbar_wait(s_full, j & 1);
       tc_fence_after();
-      // pass 1: row max of the scaled, biased scores
-      float mx = -INFINITY;
-#pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        uint32_t r[32];
-        tmem_ld32(tS + lane_bits + c * 32, r);
-        tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          float sc = __uint_as_float(r[i]) * p.scale_log2;
-          const int key = key0 + c * 32 + i;
-          if (kb) sc += (key < p.Nk ? __ldg(kb + key) : 0.f) * kLog2e;
-          if (tail && key >= p.Nk) sc = -INFINITY;
-          mx = fmaxf(mx, sc);
-        }
-      }
+      // pass 1: row max
+      const float mx = general ? tile_max_general(tS + lane_bits, sl2, kb, key0, p.Nk)
+                               : tile_max_fast(tS + lane_bits, sl2);
       const float m_new = fmaxf(m_used, mx);
       const bool need = m_new > m_used + 8.f;
       const bool warp_need = __any_sync(0xffffffffu, need);
@@ -146,9 +247,9 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
         tc_fence_after();
       }
       if (warp_need) {
-        const float alpha = exp2f(m_used - m_new);  // 0 on the first tile (m_used = -inf)
+        const float alpha = ex2_approx(m_used - m_new);  // 0 on the first tile (m_used = -inf)
         m_used = m_new;
-        l *= alpha;
+        l0 *= alpha; l1 *= alpha; l2 *= alpha; l3 *= alpha;
         if (j > 0) {
 #pragma unroll 1
           for (int c = 0; c < 2; ++c) {
@@ -162,38 +263,16 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
           tmem_st_wait();
         }
       }
-      // pass 2: P = exp2(s - m), row sum, bf16 P into the swizzled A-operand tile
-#pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        uint32_t r[32];
-        tmem_ld32(tS + lane_bits + c * 32, r);
-        tmem_ld_wait();
-        float pv[32];
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          float sc = __uint_as_float(r[i]) * p.scale_log2;
-          const int key = key0 + c * 32 + i;
-          if (kb) sc += (key < p.Nk ? __ldg(kb + key) : 0.f) * kLog2e;
-          if (tail && key >= p.Nk) sc = -INFINITY;
-          pv[i] = exp2f(sc - m_used);
-          l += pv[i];
-        }
-        const uint32_t sub = sP + (c >> 1) * 16384;
-#pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          const uint32_t addr = sub + sw128_off(row, (c & 1) * 4 + g);
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr),
-                       "r"(pack_bf16x2(pv[g * 8 + 0], pv[g * 8 + 1])),
-                       "r"(pack_bf16x2(pv[g * 8 + 2], pv[g * 8 + 3])),
-                       "r"(pack_bf16x2(pv[g * 8 + 4], pv[g * 8 + 5])),
-                       "r"(pack_bf16x2(pv[g * 8 + 6], pv[g * 8 + 7]))
-                       : "memory");
-        }
-      }
+      // pass 2: P = exp2(s * c - m), row sum, bf16 P into the swizzled A-operand tile
+      if (general)
+        l0 += tile_exp_general(tS + lane_bits, sP, row, sl2, -m_used, kb, key0, p.Nk);
+      else
+        tile_exp_fast(tS + lane_bits, sP, row, sl2, -m_used, l0, l1, l2, l3);
       fence_proxy_async_smem();
       tc_fence_before();
       mbar_arrive(p_full);
     }
+    const float l = (l0 + l1) + (l2 + l3);
     // epilogue: O / l -> bf16, lse
     mbar_wait(pv_done, (T - 1) & 1);
     tc_fence_after();
@@ -271,6 +350,7 @@ extern "C" int b200_fa_fwd(const void* q, int64_t ldq, const void* k, int64_t ld
   if (!attr_set) {
     if (cudaFuncSetAttribute(fa_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_FWD_SMEM) != cudaSuccess)
       return launch_status("fa_fwd: cudaFuncSetAttribute");
+    cudaFuncSetAttribute(fa_fwd_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     attr_set = true;
   }
   dim3 grid((Nq + 127) / 128, H, B);

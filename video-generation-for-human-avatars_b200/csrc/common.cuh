@@ -70,15 +70,17 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// Bounded wait: a protocol bug must trap (context error) rather than hang the GPU.
-#ifndef B200_WAIT_TIMEOUT_CYCLES
-#define B200_WAIT_TIMEOUT_CYCLES (4000000000ll)
+// Bounded wait: a protocol bug must trap (context error) rather than hang the GPU.  The bound is an
+// iteration count (each failed try_wait already sleeps ~100 cycles in hardware), so the spin loop
+// is just TRYWAIT + branch and does not steal issue slots from the math warps.
+#ifndef B200_WAIT_MAX_SPINS
+#define B200_WAIT_MAX_SPINS (1u << 25)
 #endif
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
-  long long t0 = clock64();
+  uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > B200_WAIT_TIMEOUT_CYCLES) {
+    if (++spins > B200_WAIT_MAX_SPINS) {
       printf("b200: mbarrier wait timeout (block %d,%d thread %d bar 0x%x parity %u)\n",
              blockIdx.x, blockIdx.y, threadIdx.x, bar, parity);
       __trap();
@@ -147,6 +149,14 @@ __device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* m, uint32_t
       "cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];" ::
           "l"(m),
       "r"(src), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_reduce_add_3d(const CUtensorMap* m, uint32_t src, int c0, int c1,
+                                                  int c2) {
+  asm volatile(
+      "cp.reduce.async.bulk.tensor.3d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3, %4}], [%1];" ::
+          "l"(m),
+      "r"(src), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
 __device__ __forceinline__ void tma_store_commit() {

@@ -14,7 +14,8 @@
 //   warp 0 lane 0 : TMA producer           (cp.async.bulk.tensor, 128B swizzle, mbarrier tx)
 //   warp 1 lane 0 : tcgen05.mma issuer     (M=128, N=BN, K=16 per instruction, fp32 accum in TMEM)
 //   warp 2        : TMEM allocator
-//   warps 4..7    : epilogue (tcgen05.ld 32x32b -> registers -> fused math -> 16-byte global stores)
+//   warps 4..11   : epilogue (tcgen05.ld 32x32b -> registers -> fused math -> 16-byte global stores);
+//                   two warps per TMEM lane quadrant, each draining half of the tile's columns
 // Accumulators are double-buffered in TMEM (2 x BN columns) so the epilogue of tile i overlaps the
 // main loop of tile i+1.
 #include "api_internal.h"
@@ -70,7 +71,7 @@ struct GemmCfg {
 };
 
 template <int BN, bool A_MN, bool B_MN>
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(384, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
             const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB2,
             const __grid_constant__ GemmParams p) {
@@ -101,7 +102,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
-      mbar_init(tempty_bar(a), 4);
+      mbar_init(tempty_bar(a), 8);
     }
     fence_barrier_init();
   }
@@ -178,7 +179,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     }
   } else if (warp >= 4) {
     // ------------------------------ epilogue ----------------------------------
-    const int ew = warp - 4;  // TMEM lane quadrant (== warp % 4)
+    const int ew = (warp - 4) & 3;     // TMEM lane quadrant (== warp % 4)
+    const int chalf = (warp - 4) >> 2;  // which half of the tile's columns this warp drains
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -192,7 +194,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       bf16* aux_row = p.aux ? p.aux + row * p.ldaux : nullptr;
       const uint32_t t_row = tmem_base + ((uint32_t)(ew * 32) << 16) + acc * BN;
 #pragma unroll 1
-      for (int c = 0; c < BN; c += 32) {
+      for (int c = chalf * (BN / 2); c < (chalf + 1) * (BN / 2); c += 32) {
         const int n0 = nt * BN + c;
         if (n0 >= p.N) break;
         uint32_t r[32];
@@ -292,7 +294,7 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
   }
   int tiles = p.m_tiles * p.n_tiles;
   int grid = tiles < num_sms() ? tiles : num_sms();
-  kern<<<grid, 256, Cfg::SMEM, stream>>>(tmA, tmB, tmA2, tmB2, p);
+  kern<<<grid, 384, Cfg::SMEM, stream>>>(tmA, tmB, tmA2, tmB2, p);
   return launch_status("gemm_bf16");
 }
 
