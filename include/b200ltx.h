@@ -42,6 +42,9 @@ int b200_device_check(void);
  *              (the LoRA up-projection (s x A^T) B^T of peft lora.Linear; K2 = 0 to disable)
  *   epilogue order: + bias[N] -> GELU / GELU' -> * gate[row / rows_per_gate, N] -> + res[M,N]
  *   C is bf16 (out_is_f32 = 0) or fp32 (1).  block_n = 0 picks the tile width (64/128/256).
+ *   split_k: <= 1 = off; n > 1 = split the reduction over n CTAs per tile (skinny wgrad-type GEMMs);
+ *            only for a plain fp32 output, which the CALLER MUST ZERO (partials are accumulated with
+ *            red.global.add.f32).
  * Replaces: nn.Linear (cuBLASLt) + bias + F.gelu + AdaLN gate + residual adds of
  *   attention.py:996-1014,1089,265-268,285,305-308,1238-1263; transformer3d.py:470,494-499,561;
  *   and, with the [K,*] layouts, the dgrad / wgrad GEMMs autograd runs for them (training.py:203). */
@@ -50,7 +53,7 @@ int b200_gemm_bf16(const void* A, int64_t lda, int a_rows_are_k, const void* B, 
                    int K2, void* C, int64_t ldc, int out_is_f32, int M, int N, int K, int epilogue,
                    const void* bias, const void* gate, int64_t gate_stride, int64_t rows_per_gate,
                    const void* res, int64_t ldres, void* aux, int64_t ldaux, int block_n,
-                   void* stream);
+                   int split_k, void* stream);
 
 /* Flash attention forward, head_dim 64, non-causal.  q/k/v/o token-major [B*N, ld], head h in
  * columns [64h, 64h+64).  key_bias: optional fp32 [B,Nk] additive score bias (the -10000 mask bias).

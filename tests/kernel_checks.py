@@ -74,6 +74,11 @@ def check_gemm_epilogues():
     _assert_close("gemm gelu'", ops.gemm(a, b, epilogue=ops.EPI_GELU_GRAD, aux=pre), base * h.grad, 8e-3)
     o32 = ops.gemm(a, b, out_dtype=torch.float32)
     _assert_close("gemm fp32 out", o32, base, 1e-5 + 6e-3)
+    # split-K (skinny wgrad shapes): [K,M] x [K,N] with a long reduction, fp32 atomics into zeros
+    for (Ms, Ns, Ks, sp) in [(64, 2048, 6144, 0), (2048, 64, 6144, 0), (256, 256, 1000, 3), (128, 128, 64, 4)]:
+        at, bt = _randn(Ks, Ms, seed=21, scale=0.1), _randn(Ks, Ns, seed=22, scale=0.1)
+        got = ops.gemm(at, bt, a_rows_are_k=True, b_rows_are_k=True, out_dtype=torch.float32, split_k=sp)
+        _assert_close(f"gemm split-K {Ms}x{Ns}x{Ks} sp={sp}", got, at.float().t() @ bt.float(), 6e-3)
     acc = res.clone()
     ops.gemm(a, b, out=acc, res=acc)
     _assert_close("gemm accumulate in place", acc, base + res.float(), 6e-3)

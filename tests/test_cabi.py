@@ -35,7 +35,7 @@ def test_argument_contract_rejected_before_launch():
     h = lib.load()
     # null operands / misaligned pitch -> negative code, message set, nothing launched (works without a GPU)
     rc = h.b200_gemm_bf16(None, 8, 0, None, 8, 0, None, 0, None, 0, 0, None, 8, 0, 128, 128, 64, 0,
-                          None, None, 0, 0, None, 0, None, 0, 0, None)
+                          None, None, 0, 0, None, 0, None, 0, 0, 1, None)
     assert rc < 0 and b"null" in h.b200_last_error()
     rc = h.b200_fa_fwd(16, 64, 16, 64, 16, 64, 16, 64, None, None, 1, 1, 128, 128, 128, 0.125, None)
     assert rc < 0 and b"head_dim" in h.b200_last_error()

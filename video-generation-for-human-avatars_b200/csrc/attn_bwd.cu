@@ -55,7 +55,7 @@ __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float 
                : "memory");
 }
 
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(320, 1)
 fa_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
               const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmdO,
               const __grid_constant__ CUtensorMap tmdQ, const __grid_constant__ FaBwdParams p) {
@@ -89,7 +89,7 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
       mbar_init(qd_empty0 + 8 * s, 1);
     }
     mbar_init(s_full, 1);
-    mbar_init(pds_full, 128);
+    mbar_init(pds_full, 256);
     mbar_init(mma2_done, 1);
     fence_barrier_init();
   }
@@ -161,40 +161,45 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
       if (i + 1 < T) issue_scores(i + 1);
     }
   } else if (warp >= 2) {
+    // 8 compute warps = 2 per TMEM lane quadrant (two warps per SM sub-partition hide each other's
+    // issue latency); the pair splits the 128 query columns of S^T / dP^T (and the 64 columns of the
+    // dQ / dK / dV accumulators) in halves.
     const int quad = warp & 3;
-    const int row = quad * 32 + lane;  // key row of S^T / dP^T, query row of dQ
-    const int ctid = threadIdx.x - 64;  // 0..127 among the compute threads
+    const int half = (warp - 2) >> 2;
+    const int row = quad * 32 + lane;   // key row of S^T / dP^T, query row of dQ
+    const int ctid = threadIdx.x - 64;  // 0..255 among the compute threads
     const uint32_t lane_bits = (uint32_t)(quad * 32) << 16;
     const int key = kt * 128 + row;
     const bool key_ok = key < p.Nk;
-    const float kbias = (p.key_bias && key_ok) ? p.key_bias[(int64_t)b * p.Nk + key] * kLog2eB : 0.f;
-    const float* lse_g = p.lse + ((int64_t)b * p.H + h) * p.Nq;
-    const float* del_g = p.delta + ((int64_t)b * p.H + h) * p.Nq;
-    // lse / delta of tile i+1 are fetched one tile ahead (their global-load latency is off the
-    // critical path); +inf lse => P = 0 for padded queries
-    float nxt_lse = ctid < p.Nq ? lse_g[ctid] * kLog2eB : INFINITY;
-    float nxt_del = ctid < p.Nq ? del_g[ctid] : 0.f;
+    // -inf bias => P = 0 for padded keys, without a select in the inner loop
+    const float kbias = !key_ok ? -INFINITY
+                                : (p.key_bias ? p.key_bias[(int64_t)b * p.Nk + key] * kLog2eB : 0.f);
+    const float* stat_g = (ctid < 128 ? p.lse : p.delta) + ((int64_t)b * p.H + h) * p.Nq;
+    const float stat_mul = ctid < 128 ? kLog2eB : p.scale;   // lse -> log2 units, delta -> pre-scaled
+    const float stat_pad = ctid < 128 ? INFINITY : 0.f;      // +inf lse => P = 0 for padded queries
+    const int sq = ctid & 127;
+    // lse / delta of tile i+1 are fetched one tile ahead (global-load latency off the critical path)
+    float nxt = sq < p.Nq ? stat_g[sq] * stat_mul : stat_pad;
     for (int i = 0; i < T; ++i) {
       const int s = i & 1;
       const int q0 = i * 128;
       float* st = stat + s * 256;
-      st[ctid] = nxt_lse;
-      st[128 + ctid] = nxt_del;
+      st[ctid] = nxt;  // [0,128): lse * log2e ; [128,256): delta * scale
       {
-        const int qn = q0 + 128 + ctid;
-        nxt_lse = qn < p.Nq ? lse_g[qn] * kLog2eB : INFINITY;
-        nxt_del = qn < p.Nq ? del_g[qn] : 0.f;
+        const int qn = q0 + 128 + sq;
+        nxt = qn < p.Nq ? stat_g[qn] * stat_mul : stat_pad;
       }
-      named_bar_sync(1, 128);
+      named_bar_sync(1, 256);
       mbar_wait(s_full, i & 1);
       tc_fence_after();
 #pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
+      for (int cc = 0; cc < 2; ++cc) {
+        const int c = half * 2 + cc;  // 32-column chunk of the 128 query columns
         uint32_t rs[32], rd[32];
         tmem_ld32(tSt + lane_bits + c * 32, rs);
         tmem_ld32(tdPt + lane_bits + c * 32, rd);
         tmem_ld_wait();
-        const uint32_t off0 = (c >> 1) * 16384;
+        const uint32_t off0 = half * 16384;
         const float4* lse4 = reinterpret_cast<const float4*>(st + c * 32);
         const float4* del4 = reinterpret_cast<const float4*>(st + 128 + c * 32);
 #pragma unroll
@@ -207,13 +212,12 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
               const int j = g * 8 + h4 * 4 + e;
-              float pr = ex2_approx_b(fmaf(__uint_as_float(rs[j]), p.scale_log2, kbias - lsv[e]));
-              if (!key_ok) pr = 0.f;
+              const float pr = ex2_approx_b(fmaf(__uint_as_float(rs[j]), p.scale_log2, kbias - lsv[e]));
               pv[h4 * 4 + e] = pr;
-              ds[h4 * 4 + e] = pr * (__uint_as_float(rd[j]) - dlv[e]) * p.scale;
+              ds[h4 * 4 + e] = pr * fmaf(__uint_as_float(rd[j]), p.scale, -dlv[e]);
             }
           }
-          const uint32_t o = off0 + sw128_off(row, (c & 1) * 4 + g);
+          const uint32_t o = off0 + sw128_off(row, cc * 4 + g);
           asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sPt + o),
                        "r"(pack_bf16x2(pv[0], pv[1])), "r"(pack_bf16x2(pv[2], pv[3])),
                        "r"(pack_bf16x2(pv[4], pv[5])), "r"(pack_bf16x2(pv[6], pv[7]))
@@ -227,29 +231,24 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
       fence_proxy_async_smem();
       tc_fence_before();
       mbar_arrive(pds_full);
-      // dQ partial of this (q tile, key tile): TMEM -> swizzled fp32 staging tile -> one TMA
-      // reduce-add (cp.reduce.async.bulk.tensor .add) into the fp32 dQ accumulator in global memory.
+      // dQ partial of this (q tile, key tile): TMEM -> swizzled fp32 staging tile -> TMA reduce-add
+      // (cp.reduce.async.bulk.tensor .add) into the fp32 dQ accumulator in global memory.
       mbar_wait(mma2_done, i & 1);
       tc_fence_after();
       {
-        uint32_t r0[32], r1[32];
-        tmem_ld32(tdQ + lane_bits, r0);
-        tmem_ld32(tdQ + lane_bits + 32, r1);
+        uint32_t r0[32];
+        tmem_ld32(tdQ + lane_bits + half * 32, r0);
         tmem_ld_wait();
         tc_fence_before();
         if (ctid == 0) tma_store_wait_read<0>();  // the previous tile's reduce has finished reading sdQ
-        named_bar_sync(2, 128);
+        named_bar_sync(2, 256);
 #pragma unroll
-        for (int g = 0; g < 8; ++g) {
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sdQ + sw128_off(row, g)),
+        for (int g = 0; g < 8; ++g)
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sdQ + half * 16384 + sw128_off(row, g)),
                        "r"(r0[g * 4 + 0]), "r"(r0[g * 4 + 1]), "r"(r0[g * 4 + 2]), "r"(r0[g * 4 + 3])
                        : "memory");
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sdQ + 16384 + sw128_off(row, g)),
-                       "r"(r1[g * 4 + 0]), "r"(r1[g * 4 + 1]), "r"(r1[g * 4 + 2]), "r"(r1[g * 4 + 3])
-                       : "memory");
-        }
         fence_proxy_async_smem();
-        named_bar_sync(3, 128);
+        named_bar_sync(3, 256);
         if (ctid == 0) {
           tma_reduce_add_3d(&tmdQ, sdQ, h * 64, q0, b);
           tma_reduce_add_3d(&tmdQ, sdQ + 16384, h * 64 + 32, q0, b);
@@ -258,31 +257,28 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
       }
     }
     if (ctid == 0) tma_store_wait_all<0>();
-    // dK, dV of this key tile
+    // dK, dV of this key tile: each warp of a pair writes 32 of the 64 head columns
     if (T > 0) {
-      bf16* dkr = p.dk + ((int64_t)b * p.Nk + key) * p.lddk + h * 64;
-      bf16* dvr = p.dv + ((int64_t)b * p.Nk + key) * p.lddv + h * 64;
-#pragma unroll 1
-      for (int c = 0; c < 2; ++c) {
-        uint32_t rv[32], rk[32];
-        tmem_ld32(tdV + lane_bits + c * 32, rv);
-        tmem_ld32(tdK + lane_bits + c * 32, rk);
-        tmem_ld_wait();
-        if (key_ok) {
+      bf16* dkr = p.dk + ((int64_t)b * p.Nk + key) * p.lddk + h * 64 + half * 32;
+      bf16* dvr = p.dv + ((int64_t)b * p.Nk + key) * p.lddv + h * 64 + half * 32;
+      uint32_t rv[32], rk[32];
+      tmem_ld32(tdV + lane_bits + half * 32, rv);
+      tmem_ld32(tdK + lane_bits + half * 32, rk);
+      tmem_ld_wait();
+      if (key_ok) {
 #pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            uint4 u;
-            u.x = pack_bf16x2(__uint_as_float(rv[g * 8 + 0]), __uint_as_float(rv[g * 8 + 1]));
-            u.y = pack_bf16x2(__uint_as_float(rv[g * 8 + 2]), __uint_as_float(rv[g * 8 + 3]));
-            u.z = pack_bf16x2(__uint_as_float(rv[g * 8 + 4]), __uint_as_float(rv[g * 8 + 5]));
-            u.w = pack_bf16x2(__uint_as_float(rv[g * 8 + 6]), __uint_as_float(rv[g * 8 + 7]));
-            *reinterpret_cast<uint4*>(dvr + c * 32 + g * 8) = u;
-            u.x = pack_bf16x2(__uint_as_float(rk[g * 8 + 0]), __uint_as_float(rk[g * 8 + 1]));
-            u.y = pack_bf16x2(__uint_as_float(rk[g * 8 + 2]), __uint_as_float(rk[g * 8 + 3]));
-            u.z = pack_bf16x2(__uint_as_float(rk[g * 8 + 4]), __uint_as_float(rk[g * 8 + 5]));
-            u.w = pack_bf16x2(__uint_as_float(rk[g * 8 + 6]), __uint_as_float(rk[g * 8 + 7]));
-            *reinterpret_cast<uint4*>(dkr + c * 32 + g * 8) = u;
-          }
+        for (int g = 0; g < 4; ++g) {
+          uint4 u;
+          u.x = pack_bf16x2(__uint_as_float(rv[g * 8 + 0]), __uint_as_float(rv[g * 8 + 1]));
+          u.y = pack_bf16x2(__uint_as_float(rv[g * 8 + 2]), __uint_as_float(rv[g * 8 + 3]));
+          u.z = pack_bf16x2(__uint_as_float(rv[g * 8 + 4]), __uint_as_float(rv[g * 8 + 5]));
+          u.w = pack_bf16x2(__uint_as_float(rv[g * 8 + 6]), __uint_as_float(rv[g * 8 + 7]));
+          *reinterpret_cast<uint4*>(dvr + g * 8) = u;
+          u.x = pack_bf16x2(__uint_as_float(rk[g * 8 + 0]), __uint_as_float(rk[g * 8 + 1]));
+          u.y = pack_bf16x2(__uint_as_float(rk[g * 8 + 2]), __uint_as_float(rk[g * 8 + 3]));
+          u.z = pack_bf16x2(__uint_as_float(rk[g * 8 + 4]), __uint_as_float(rk[g * 8 + 5]));
+          u.w = pack_bf16x2(__uint_as_float(rk[g * 8 + 6]), __uint_as_float(rk[g * 8 + 7]));
+          *reinterpret_cast<uint4*>(dkr + g * 8) = u;
         }
       }
     }
@@ -342,6 +338,6 @@ extern "C" int b200_fa_bwd(const void* q, int64_t ldq, const void* k, int64_t ld
     attr_set = true;
   }
   dim3 grid((Nk + 127) / 128, H, B);
-  fa_bwd_kernel<<<grid, 192, FA_BWD_SMEM, (cudaStream_t)stream>>>(tmQ, tmK, tmV, tmdO, tmdQ, p);
+  fa_bwd_kernel<<<grid, 320, FA_BWD_SMEM, (cudaStream_t)stream>>>(tmQ, tmK, tmV, tmdO, tmdQ, p);
   return launch_status("fa_bwd");
 }

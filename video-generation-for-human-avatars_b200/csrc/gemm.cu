@@ -30,6 +30,7 @@ struct GemmParams {
   int M, N;
   int m_tiles, n_tiles;
   int kb1, kb2;  // 64-wide k blocks taken from (A,B) and from (A2,B2)
+  int splits;    // split-K factor: work item = (tile, split); > 1 only for plain fp32 outputs (atomic accumulate)
   int epi, out_f32;
   void* C;
   int64_t ldc;
@@ -116,16 +117,20 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
-  const int total_tiles = p.m_tiles * p.n_tiles;
-  const int kblocks = p.kb1 + p.kb2;
+  const int tiles_mn = p.m_tiles * p.n_tiles;
+  const int total_tiles = tiles_mn * p.splits;  // work items
+  const int kb_all = p.kb1 + p.kb2;
+  const int kb_per = (kb_all + p.splits - 1) / p.splits;
 
   if (warp == 0 && lane == 0) {
     // ------------------------------ TMA producer ------------------------------
     int stage = 0;
     uint32_t phase = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    for (int work = blockIdx.x; work < total_tiles; work += gridDim.x) {
+      const int tile = work % tiles_mn, split = work / tiles_mn;
       const int mt = tile % p.m_tiles, nt = tile / p.m_tiles;
-      for (int kb = 0; kb < kblocks; ++kb) {
+      const int kb_begin = split * kb_per, kb_end = min(kb_all, kb_begin + kb_per);
+      for (int kb = kb_begin; kb < kb_end; ++kb) {
         mbar_wait(empty_bar(stage), phase ^ 1);
         mbar_expect_tx(full_bar(stage), Cfg::STAGE);
         const bool second = kb >= p.kb1;
@@ -154,11 +159,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     const uint32_t idesc = make_idesc_bf16(128, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
     int stage = 0, acc = 0;
     uint32_t phase = 0, acc_phase = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    for (int work = blockIdx.x; work < total_tiles; work += gridDim.x) {
+      const int split = work / tiles_mn;
+      const int kb_begin = split * kb_per, kb_end = min(kb_all, kb_begin + kb_per);
       mbar_wait(tempty_bar(acc), acc_phase ^ 1);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + acc * BN;
-      for (int kb = 0; kb < kblocks; ++kb) {
+      for (int kb = kb_begin; kb < kb_end; ++kb) {
         mbar_wait(full_bar(stage), phase);
         tc_fence_after();
         const uint32_t sa = sbase + stage * Cfg::STAGE, sb = sa + Cfg::A_BYTES;
@@ -168,7 +175,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                                    : make_smem_desc(sa + k * 32, 16, 1024);
           const uint64_t db = B_MN ? make_smem_desc(sb + k * 2048, 8192, 1024)
                                    : make_smem_desc(sb + k * 32, 16, 1024);
-          umma_ss(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+          umma_ss(d_tmem, da, db, idesc, (kb > kb_begin || k > 0) ? 1u : 0u);
         }
         umma_commit(empty_bar(stage));
         if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
@@ -183,7 +190,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     const int chalf = (warp - 4) >> 2;  // which half of the tile's columns this warp drains
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    for (int work = blockIdx.x; work < total_tiles; work += gridDim.x) {
+      const int tile = work % tiles_mn;
       const int mt = tile % p.m_tiles, nt = tile / p.m_tiles;
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
@@ -243,8 +251,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
               }
               if (p.out_f32) {
                 float* o = reinterpret_cast<float*>(p.C) + row * p.ldc + n;
-                *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
-                *reinterpret_cast<float4*>(o + 4) = make_float4(v[4], v[5], v[6], v[7]);
+                if (p.splits > 1) {  // split-K partial: accumulate into the caller-zeroed output
+                  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(o), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]) : "memory");
+                  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(o + 4), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7]) : "memory");
+                } else {
+                  *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
+                  *reinterpret_cast<float4*>(o + 4) = make_float4(v[4], v[5], v[6], v[7]);
+                }
               } else {
                 uint4 u;
                 u.x = pack_bf16x2(v[0], v[1]); u.y = pack_bf16x2(v[2], v[3]);
@@ -292,7 +305,7 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
     if (e != cudaSuccess) return launch_status("gemm: cudaFuncSetAttribute");
     attr_set = true;
   }
-  int tiles = p.m_tiles * p.n_tiles;
+  int tiles = p.m_tiles * p.n_tiles * p.splits;
   int grid = tiles < num_sms() ? tiles : num_sms();
   kern<<<grid, 384, Cfg::SMEM, stream>>>(tmA, tmB, tmA2, tmB2, p);
   return launch_status("gemm_bf16");
@@ -311,7 +324,7 @@ extern "C" int b200_gemm_bf16(const void* A, int64_t lda, int a_kmajor_rows_are_
                               int out_is_f32, int M, int N, int K, int epilogue, const void* bias,
                               const void* gate, int64_t gate_stride, int64_t rows_per_gate,
                               const void* res, int64_t ldres, void* aux, int64_t ldaux,
-                              int block_n, void* stream) {
+                              int block_n, int split_k, void* stream) {
   const bool a_mn = a_kmajor_rows_are_k != 0, b_mn = b_rows_are_k != 0;
   if (!(A && B && C)) return arg_error("gemm_bf16: null operand");
   if (M < 0 || N < 0 || K < 0 || K2 < 0) return arg_error("gemm_bf16: negative dimension");
@@ -347,6 +360,16 @@ extern "C" int b200_gemm_bf16(const void* A, int64_t lda, int a_kmajor_rows_are_
   p.kb1 = (K + 63) / 64;
   p.kb2 = (K2 + 63) / 64;
   p.epi = epilogue; p.out_f32 = out_is_f32;
+  {
+    const bool plain = out_is_f32 && epilogue == EPI_NONE && !bias && !gate && !res && !aux;
+    const int kb_all = p.kb1 + p.kb2;
+    int sp = split_k <= 1 ? 1 : split_k;
+    if (sp > 1 && !plain) return arg_error("gemm_bf16: split_k > 1 needs a plain fp32 output (no epilogue operands)");
+    if (sp > kb_all) sp = kb_all;
+    // every split must own at least one k block
+    while (sp > 1 && (sp - 1) * ((kb_all + sp - 1) / sp) >= kb_all) --sp;
+    p.splits = sp;
+  }
   p.C = C; p.ldc = ldc;
   p.bias = (const bf16*)bias;
   p.gate = (const bf16*)gate; p.gate_stride = gate_stride; p.rows_per_gate = rows_per_gate > 0 ? rows_per_gate : 1;

@@ -18,7 +18,7 @@ PROTOTYPES = {
     "b200_version": (I, []),
     "b200_last_error": (c_char_p, []),
     "b200_device_check": (I, []),
-    "b200_gemm_bf16": (I, [P, L, I, P, L, I, P, L, P, L, I, P, L, I, I, I, I, I, P, P, L, L, P, L, P, L, I, P]),
+    "b200_gemm_bf16": (I, [P, L, I, P, L, I, P, L, P, L, I, P, L, I, I, I, I, I, P, P, L, L, P, L, P, L, I, I, P]),
     "b200_fa_fwd": (I, [P, L, P, L, P, L, P, L, P, P, I, I, I, I, I, F, P]),
     "b200_attn_delta": (I, [P, L, P, L, P, I, I, I, P]),
     "b200_fa_bwd": (I, [P, L, P, L, P, L, P, L, P, P, P, P, L, P, L, P, L, I, I, I, I, I, F, P]),

@@ -85,7 +85,7 @@ def _call(family, work, unit, cfn, *args, launches=1):
 def gemm(a: torch.Tensor, b: torch.Tensor, *, a_rows_are_k=False, b_rows_are_k=False,
          a2: Optional[torch.Tensor] = None, b2: Optional[torch.Tensor] = None,
          out: Optional[torch.Tensor] = None, out_dtype=BF16, bias=None, gate=None, rows_per_gate=0,
-         res=None, aux=None, epilogue=EPI_NONE, block_n=0) -> torch.Tensor:
+         res=None, aux=None, epilogue=EPI_NONE, block_n=0, split_k=1) -> torch.Tensor:
     """out[M,N] = epi(a @ b^T (+ a2 @ b2^T)); see b200_gemm_bf16 in include/b200ltx.h."""
     _chk2d(a, "gemm a")
     _chk2d(b, "gemm b")
@@ -101,8 +101,17 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, a_rows_are_k=False, b_rows_are_k=F
         N2, K2b = (b2.shape[1], b2.shape[0]) if b_rows_are_k else b2.shape
         if (M2, N2, K2) != (M, N, K2b):
             raise _lib.B200Error("gemm: second operand pair shape mismatch")
+    if split_k == 0:  # auto: split skinny fp32 reductions (LoRA / caption wgrad) over idle SMs
+        split_k = 1
+        plain = out_dtype == torch.float32 and out is None and bias is None and gate is None and res is None \
+            and aux is None and epilogue == EPI_NONE
+        bn = block_n or (64 if N <= 64 else 128)
+        tiles = ((M + 127) // 128) * ((N + bn - 1) // bn)
+        kb = (K + 63) // 64 + (K2 + 63) // 64
+        if plain and tiles <= 48 and kb >= 16:
+            split_k = max(1, min(148 // tiles, kb // 4))
     if out is None:
-        out = torch.empty((M, N), device=a.device, dtype=out_dtype)
+        out = (torch.zeros if split_k > 1 else torch.empty)((M, N), device=a.device, dtype=out_dtype)
     _chk2d(out, "gemm out", out.dtype)
     if out.dtype not in (BF16, torch.float32) or tuple(out.shape) != (M, N):
         raise _lib.B200Error("gemm: bad output tensor")
@@ -124,7 +133,7 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, a_rows_are_k=False, b_rows_are_k=F
         _p(a2), a2.stride(0) if a2 is not None else 0, _p(b2), b2.stride(0) if b2 is not None else 0, K2,
         _p(out), out.stride(0), int(out.dtype == torch.float32), M, N, K, epilogue,
         _p(bias), _p(gate), gate_stride, rows_per_gate, _p(res), res.stride(0) if res is not None else 0,
-        _p(aux), aux.stride(0) if aux is not None else 0, block_n, _s())
+        _p(aux), aux.stride(0) if aux is not None else 0, block_n, split_k, _s())
     return out
 
 
@@ -313,9 +322,9 @@ class LinearFn(torch.autograd.Function):
         if need[0]:
             dx = gemm(g, W, b_rows_are_k=True, a2=dt, b2=a_pad if has_lora else None)
         if has_lora and need[3]:
-            dA = gemm(dt, x, a_rows_are_k=True, b_rows_are_k=True, out_dtype=torch.float32)[:r]
+            dA = gemm(dt, x, a_rows_are_k=True, b_rows_are_k=True, out_dtype=torch.float32, split_k=0)[:r]
         if has_lora and need[4]:
-            dB = gemm(g, t, a_rows_are_k=True, b_rows_are_k=True, out_dtype=torch.float32, block_n=64)[:, :r]
+            dB = gemm(g, t, a_rows_are_k=True, b_rows_are_k=True, out_dtype=torch.float32, block_n=64, split_k=0)[:, :r]
             dB = dB * scaling if scaling != 1.0 else dB
         if need[1]:
             dW = gemm(g, x, a_rows_are_k=True, b_rows_are_k=True)
