@@ -228,7 +228,11 @@ def run_b200(args):
     fam = ops.timer.summary()
     ops.timer = None
     dominant = max((f for f in fam if fam[f]["unit"] == "flop"), key=lambda f: fam[f]["ms"])
-    share = {f: round(d["ms"] / sum(x["ms"] for x in fam.values()), 4) for f, d in sorted(fam.items(), key=lambda kv: -kv[1]["ms"])}
+    fam_total_ms = sum(x["ms"] for x in fam.values())
+    share = {f: round(d["ms"] / fam_total_ms, 4) for f, d in sorted(fam.items(), key=lambda kv: -kv[1]["ms"])}
+    b200_kernel_ms_per_step = fam_total_ms / max(args.warmup, 3)
+    fam_tflops = {f: round(d["work"] / d["ms"] / 1e9, 1) for f, d in fam.items() if d["unit"] == "flop"}
+    fam_gbs = {f: round(d["work"] / d["ms"] / 1e6, 1) for f, d in fam.items() if d["unit"] == "byte"}
 
     # timed region 1: device-resident inputs
     sampler = ClockSampler(torch.cuda.current_device() if "CUDA_VISIBLE_DEVICES" not in os.environ else local)
@@ -278,7 +282,8 @@ def run_b200(args):
                              "unit": "TFLOP/s", "frac": achieved / peaks["tflops"], "traffic": traffic,
                              "peak_source": peaks["source"], "launches_timed": dom["launches"],
                              "avg_launch_ms": dom["ms"] / dom["launches"],
-                             "time_share_by_family": share},
+                             "time_share_by_family": share, "b200_kernel_ms_per_step": b200_kernel_ms_per_step,
+                             "family_tflops": fam_tflops, "family_gbs": fam_gbs},
                 "clocks": clocks, "loss": float(last)}
         if args.layers:
             line["config"]["INVALID_reduced_layers"] = True

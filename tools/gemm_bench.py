@@ -1,0 +1,38 @@
+"""Micro-benchmark of the GEMM shapes of one LTXV-2B block at cfg2 (M = 6144), warm, CUDA events."""
+import sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from b200_ltx import ops
+
+M, D, F = 6144, 2048, 8192
+dev = "cuda"
+def r(*s): return (torch.randn(*s, device=dev) * 0.05).bfloat16()
+x, xf = r(M, D), r(M, F)
+W_dd, W_fd, W_df, W_3d = r(D, D), r(F, D), r(D, F), r(3 * D, D)
+bias_d, bias_f, bias_3d = r(D), r(F), r(3 * D)
+gate, res, pre = r(1, D), r(M, D), r(M, F)
+big3 = r(M, 3 * D)
+cases = [
+    ("fwd N=2048 K=2048 bias", lambda bn: ops.gemm(x, W_dd, bias=bias_d, block_n=bn), 2 * M * D * D),
+    ("fwd N=2048 K=2048 bias+gate+res", lambda bn: ops.gemm(x, W_dd, bias=bias_d, gate=gate, rows_per_gate=M, res=res, block_n=bn), 2 * M * D * D),
+    ("fwd N=6144 K=2048 bias (qkv)", lambda bn: ops.gemm(x, W_3d, bias=bias_3d, block_n=bn), 2 * M * 3 * D * D),
+    ("fwd N=8192 K=2048 gelu+aux", lambda bn: ops.gemm(x, W_fd, bias=bias_f, epilogue=ops.EPI_GELU, aux=pre, block_n=bn), 2 * M * F * D),
+    ("fwd N=2048 K=8192 gate+res", lambda bn: ops.gemm(xf, W_df, bias=bias_d, gate=gate, rows_per_gate=M, res=res, block_n=bn), 2 * M * F * D),
+    ("dgrad N=2048 K=2048", lambda bn: ops.gemm(x, W_dd, b_rows_are_k=True, block_n=bn), 2 * M * D * D),
+    ("dgrad N=2048 K=6144 (qkv)", lambda bn: ops.gemm(big3, W_3d, b_rows_are_k=True, block_n=bn), 2 * M * 3 * D * D),
+    ("dgrad N=8192 K=2048 gelu'", lambda bn: ops.gemm(x, W_df, b_rows_are_k=True, epilogue=ops.EPI_GELU_GRAD, aux=pre, block_n=bn), 2 * M * F * D),
+    ("dgrad N=2048 K=8192", lambda bn: ops.gemm(xf, W_fd, b_rows_are_k=True, block_n=bn), 2 * M * F * D),
+]
+flush = torch.empty(256 << 20, device=dev, dtype=torch.uint8)
+for name, fn, flops in cases:
+    for bn in (128, 256):
+        for _ in range(3): fn(bn)
+        ts = []
+        for _ in range(10):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); fn(bn); e1.record(); torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        ts.sort()
+        t = ts[len(ts) // 2]
+        print(f"{name:36s} bn={bn:3d} {t*1e3:8.1f} us {flops / t / 1e9:8.1f} TF/s", flush=True)

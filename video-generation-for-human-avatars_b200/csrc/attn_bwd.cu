@@ -16,6 +16,10 @@
 // reduced across key-tile CTAs with TMA reduce-add (cp.reduce.async.bulk.tensor) into a caller-zeroed
 // fp32 buffer (per-lane red.global.add measured ~10 k cycles per tile: the atomics were the bottleneck).
 // TMEM: S^T 128 | dP^T 128 | dV 64 | dK 64 | dQ 64 = 448 of 512 columns.
+//
+// Pipeline: P^T/dS^T are double-buffered in shared memory, so while the 8 compute warps turn
+// S^T/dP^T(i+1) into P^T/dS^T(i+1) the tensor pipe runs dV/dK/dQ(i); dQ(i-1) is drained to global
+// memory right after P^T/dS^T(i) are handed over.
 #include "api_internal.h"
 #include "common.cuh"
 #include "tmap.h"
@@ -39,8 +43,8 @@ struct FaBwdParams {
   float scale, scale_log2;
 };
 
-constexpr int FA_BWD_SMEM = 16384 * 2 /*K,V*/ + 2 * 32768 /*Q,dO x2*/ + 2 * 32768 /*P^T,dS^T*/ +
-                            32768 /*dQ staging*/ + 2 * 2 * 512 /*lse, delta x2*/ + 128;
+constexpr int FA_BWD_SMEM = 16384 * 2 /*K,V*/ + 2 * 32768 /*Q,dO x2*/ + 4 * 32768 /*P^T,dS^T x2*/ +
+                            2 * 2 * 512 /*lse, delta x2*/ + 128;  // dQ staging aliases the consumed P^T buffer
 constexpr float kLog2eB = 1.4426950408889634f;
 
 __device__ __forceinline__ float ex2_approx_b(float x) {
@@ -55,19 +59,22 @@ __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float 
                : "memory");
 }
 
-__global__ void __launch_bounds__(320, 1)
+constexpr int FA_BWD_THREADS = 64 + 512;  // TMA warp, MMA warp, 16 compute warps
+
+__global__ void __launch_bounds__(FA_BWD_THREADS, 1)
 fa_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
               const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmdO,
               const __grid_constant__ CUtensorMap tmdQ, const __grid_constant__ FaBwdParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t sbase = smem_u32(smem_raw);
   const uint32_t sK = sbase, sV = sbase + 16384, sQdO = sbase + 32768;  // stage s: Q at +s*32768, dO at +16384
-  const uint32_t sPt = sQdO + 65536, sdSt = sPt + 32768;
-  const uint32_t sdQ = sdSt + 32768;    // fp32 [2 halves of 32 cols][128 q rows][128 B], 128B-swizzled
-  const uint32_t sStat = sdQ + 32768;   // [2 stages][lse 128 | delta 128] fp32
+  // buffer u (= tile & 1): P^T at sPD + u*65536, dS^T at +32768.  Once dV(i) has been accumulated the
+  // P^T buffer of tile i is dead and doubles as the fp32 dQ(i) staging tile for the TMA reduce-add.
+  const uint32_t sPD = sQdO + 65536;
+  const uint32_t sStat = sPD + 131072;  // [2 stages][lse 128 | delta 128] fp32
   const uint32_t bar = sStat + 2048;
   const uint32_t kv_full = bar, qd_full0 = bar + 8, qd_empty0 = bar + 24, s_full = bar + 40,
-                 pds_full = bar + 48, mma2_done = bar + 56, tmem_slot = bar + 64;
+                 pds_full = bar + 48, mma2_done = bar + 56, dq_free = bar + 64, tmem_slot = bar + 72;
   float* stat = reinterpret_cast<float*>(smem_raw + (sStat - sbase));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int kt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
@@ -89,8 +96,9 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
       mbar_init(qd_empty0 + 8 * s, 1);
     }
     mbar_init(s_full, 1);
-    mbar_init(pds_full, 256);
+    mbar_init(pds_full, 512);
     mbar_init(mma2_done, 1);
+    mbar_init(dq_free, 512);
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -142,8 +150,10 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
     for (int i = 0; i < T; ++i) {
       const int s = i & 1;
       const uint32_t sQ = sQdO + s * 32768, sdO = sQ + 16384;
-      mbar_wait(pds_full, i & 1);
+      const uint32_t sPt = sPD + s * 65536, sdSt = sPt + 32768;
+      mbar_wait(pds_full, i & 1);  // P^T/dS^T(i) are in shared memory; S^T/dP^T in TMEM are consumed
       tc_fence_after();
+      if (i + 1 < T) issue_scores(i + 1);  // compute warps start tile i+1 while dV/dK/dQ(i) run below
 #pragma unroll
       for (int k = 0; k < 8; ++k)  // dV += P^T dO   (K = queries)
         umma_ss(tdV, make_smem_desc(sPt + (k >> 2) * 16384 + (k & 3) * 32, 16, 1024),
@@ -152,54 +162,87 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
       for (int k = 0; k < 8; ++k)  // dK += dS^T Q
         umma_ss(tdK, make_smem_desc(sdSt + (k >> 2) * 16384 + (k & 3) * 32, 16, 1024),
                 make_smem_desc(sQ + k * 2048, 8192, 1024), idesc_kv, (i > 0 || k > 0) ? 1u : 0u);
+      if (i > 0) {
+        mbar_wait(dq_free, (i - 1) & 1);  // dQ(i-1) has been read out of TMEM
+        tc_fence_after();
+      }
 #pragma unroll
       for (int k = 0; k < 8; ++k)  // dQ = dS K      (K = keys; A = dS^T bytes read MN-major)
         umma_ss(tdQ, make_smem_desc(sdSt + k * 2048, 16384, 1024),
                 make_smem_desc(sK + k * 2048, 8192, 1024), idesc_dq, k > 0 ? 1u : 0u);
       umma_commit(qd_empty0 + 8 * s);
       umma_commit(mma2_done);
-      if (i + 1 < T) issue_scores(i + 1);
     }
   } else if (warp >= 2) {
-    // 8 compute warps = 2 per TMEM lane quadrant (two warps per SM sub-partition hide each other's
-    // issue latency); the pair splits the 128 query columns of S^T / dP^T (and the 64 columns of the
-    // dQ / dK / dV accumulators) in halves.
+    // 16 compute warps = 4 per TMEM lane quadrant (four warps per SM sub-partition hide each other's
+    // MUFU / LDS / TMEM latencies); warp `part` of a quadrant owns one 32-column chunk of the 128 query
+    // columns of S^T / dP^T and 16 of the 64 columns of the dQ / dK / dV accumulators.
     const int quad = warp & 3;
-    const int half = (warp - 2) >> 2;
+    const int part = (warp - 2) >> 2;   // 0..3
     const int row = quad * 32 + lane;   // key row of S^T / dP^T, query row of dQ
-    const int ctid = threadIdx.x - 64;  // 0..255 among the compute threads
+    const int ctid = threadIdx.x - 64;  // 0..511 among the compute threads
     const uint32_t lane_bits = (uint32_t)(quad * 32) << 16;
     const int key = kt * 128 + row;
     const bool key_ok = key < p.Nk;
     // -inf bias => P = 0 for padded keys, without a select in the inner loop
     const float kbias = !key_ok ? -INFINITY
                                 : (p.key_bias ? p.key_bias[(int64_t)b * p.Nk + key] * kLog2eB : 0.f);
+    const bool has_bias = __any_sync(0xffffffffu, kbias != 0.f);  // warp-uniform fast-path switch
     const float* stat_g = (ctid < 128 ? p.lse : p.delta) + ((int64_t)b * p.H + h) * p.Nq;
     const float stat_mul = ctid < 128 ? kLog2eB : p.scale;   // lse -> log2 units, delta -> pre-scaled
     const float stat_pad = ctid < 128 ? INFINITY : 0.f;      // +inf lse => P = 0 for padded queries
     const int sq = ctid & 127;
+    const bool stat_thread = ctid < 256;
     // lse / delta of tile i+1 are fetched one tile ahead (global-load latency off the critical path)
-    float nxt = sq < p.Nq ? stat_g[sq] * stat_mul : stat_pad;
+    float nxt = (stat_thread && sq < p.Nq) ? stat_g[sq] * stat_mul : stat_pad;
+    // dQ(j): TMEM -> swizzled fp32 staging tile (the dead P^T buffer of tile j) -> TMA reduce-add
+    // (cp.reduce.async.bulk.tensor .add) into the fp32 dQ accumulator in global memory.
+    auto drain_dq = [&](int j) {
+      mbar_wait(mma2_done, j & 1);
+      tc_fence_after();
+      uint32_t r0[16];
+      tmem_ld16(tdQ + lane_bits + part * 16, r0);
+      tmem_ld_wait();
+      tc_fence_before();
+      mbar_arrive(dq_free);  // the dQ columns may be overwritten by dQ(j+1)
+      const uint32_t stage = sPD + (j & 1) * 65536;
+#pragma unroll
+      for (int g = 0; g < 4; ++g)
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stage + (part >> 1) * 16384 +
+                                                                      sw128_off(row, (part & 1) * 4 + g)),
+                     "r"(r0[g * 4 + 0]), "r"(r0[g * 4 + 1]), "r"(r0[g * 4 + 2]), "r"(r0[g * 4 + 3])
+                     : "memory");
+      fence_proxy_async_smem();
+      named_bar_sync(3, 512);
+      if (ctid == 0) {
+        tma_reduce_add_3d(&tmdQ, stage, h * 64, j * 128, b);
+        tma_reduce_add_3d(&tmdQ, stage + 16384, h * 64 + 32, j * 128, b);
+        tma_store_commit();
+      }
+    };
     for (int i = 0; i < T; ++i) {
       const int s = i & 1;
       const int q0 = i * 128;
       float* st = stat + s * 256;
-      st[ctid] = nxt;  // [0,128): lse * log2e ; [128,256): delta * scale
-      {
+      const uint32_t sPt = sPD + s * 65536, sdSt = sPt + 32768;
+      if (stat_thread) {
+        st[ctid] = nxt;  // [0,128): lse * log2e ; [128,256): delta * scale
         const int qn = q0 + 128 + sq;
         nxt = qn < p.Nq ? stat_g[qn] * stat_mul : stat_pad;
       }
-      named_bar_sync(1, 256);
+      // P^T/dS^T buffer s was last read by dV/dK/dQ(i-2) (mma2_done(i-2) was awaited when dQ(i-2) was
+      // drained) and by the TMA reduce of dQ(i-2) staged in it:
+      if (ctid == 0) tma_store_wait_read<0>();
+      named_bar_sync(1, 512);
       mbar_wait(s_full, i & 1);
       tc_fence_after();
-#pragma unroll 1
-      for (int cc = 0; cc < 2; ++cc) {
-        const int c = half * 2 + cc;  // 32-column chunk of the 128 query columns
+      {
+        const int c = part;  // this warp's 32-column chunk of the 128 query columns
         uint32_t rs[32], rd[32];
         tmem_ld32(tSt + lane_bits + c * 32, rs);
         tmem_ld32(tdPt + lane_bits + c * 32, rd);
         tmem_ld_wait();
-        const uint32_t off0 = half * 16384;
+        const uint32_t off0 = (c >> 1) * 16384;
         const float4* lse4 = reinterpret_cast<const float4*>(st + c * 32);
         const float4* del4 = reinterpret_cast<const float4*>(st + 128 + c * 32);
 #pragma unroll
@@ -212,12 +255,14 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
               const int j = g * 8 + h4 * 4 + e;
-              const float pr = ex2_approx_b(fmaf(__uint_as_float(rs[j]), p.scale_log2, kbias - lsv[e]));
+              const float arg = has_bias ? fmaf(__uint_as_float(rs[j]), p.scale_log2, kbias - lsv[e])
+                                         : fmaf(__uint_as_float(rs[j]), p.scale_log2, -lsv[e]);
+              const float pr = ex2_approx_b(arg);
               pv[h4 * 4 + e] = pr;
               ds[h4 * 4 + e] = pr * fmaf(__uint_as_float(rd[j]), p.scale, -dlv[e]);
             }
           }
-          const uint32_t o = off0 + sw128_off(row, cc * 4 + g);
+          const uint32_t o = off0 + sw128_off(row, (c & 1) * 4 + g);
           asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sPt + o),
                        "r"(pack_bf16x2(pv[0], pv[1])), "r"(pack_bf16x2(pv[2], pv[3])),
                        "r"(pack_bf16x2(pv[4], pv[5])), "r"(pack_bf16x2(pv[6], pv[7]))
@@ -231,43 +276,21 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
       fence_proxy_async_smem();
       tc_fence_before();
       mbar_arrive(pds_full);
-      // dQ partial of this (q tile, key tile): TMEM -> swizzled fp32 staging tile -> TMA reduce-add
-      // (cp.reduce.async.bulk.tensor .add) into the fp32 dQ accumulator in global memory.
-      mbar_wait(mma2_done, i & 1);
-      tc_fence_after();
-      {
-        uint32_t r0[32];
-        tmem_ld32(tdQ + lane_bits + half * 32, r0);
-        tmem_ld_wait();
-        tc_fence_before();
-        if (ctid == 0) tma_store_wait_read<0>();  // the previous tile's reduce has finished reading sdQ
-        named_bar_sync(2, 256);
-#pragma unroll
-        for (int g = 0; g < 8; ++g)
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sdQ + half * 16384 + sw128_off(row, g)),
-                       "r"(r0[g * 4 + 0]), "r"(r0[g * 4 + 1]), "r"(r0[g * 4 + 2]), "r"(r0[g * 4 + 3])
-                       : "memory");
-        fence_proxy_async_smem();
-        named_bar_sync(3, 256);
-        if (ctid == 0) {
-          tma_reduce_add_3d(&tmdQ, sdQ, h * 64, q0, b);
-          tma_reduce_add_3d(&tmdQ, sdQ + 16384, h * 64 + 32, q0, b);
-          tma_store_commit();
-        }
-      }
+      if (i > 0) drain_dq(i - 1);  // overlaps with S^T/dP^T(i+1) and dV/dK/dQ(i) on the tensor pipe
     }
+    if (T > 0) drain_dq(T - 1);
     if (ctid == 0) tma_store_wait_all<0>();
-    // dK, dV of this key tile: each warp of a pair writes 32 of the 64 head columns
+    // dK, dV of this key tile: each of the 4 warps of a quadrant writes 16 of the 64 head columns
     if (T > 0) {
-      bf16* dkr = p.dk + ((int64_t)b * p.Nk + key) * p.lddk + h * 64 + half * 32;
-      bf16* dvr = p.dv + ((int64_t)b * p.Nk + key) * p.lddv + h * 64 + half * 32;
-      uint32_t rv[32], rk[32];
-      tmem_ld32(tdV + lane_bits + half * 32, rv);
-      tmem_ld32(tdK + lane_bits + half * 32, rk);
+      bf16* dkr = p.dk + ((int64_t)b * p.Nk + key) * p.lddk + h * 64 + part * 16;
+      bf16* dvr = p.dv + ((int64_t)b * p.Nk + key) * p.lddv + h * 64 + part * 16;
+      uint32_t rv[16], rk[16];
+      tmem_ld16(tdV + lane_bits + part * 16, rv);
+      tmem_ld16(tdK + lane_bits + part * 16, rk);
       tmem_ld_wait();
       if (key_ok) {
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
+        for (int g = 0; g < 2; ++g) {
           uint4 u;
           u.x = pack_bf16x2(__uint_as_float(rv[g * 8 + 0]), __uint_as_float(rv[g * 8 + 1]));
           u.y = pack_bf16x2(__uint_as_float(rv[g * 8 + 2]), __uint_as_float(rv[g * 8 + 3]));
@@ -338,6 +361,6 @@ extern "C" int b200_fa_bwd(const void* q, int64_t ldq, const void* k, int64_t ld
     attr_set = true;
   }
   dim3 grid((Nk + 127) / 128, H, B);
-  fa_bwd_kernel<<<grid, 320, FA_BWD_SMEM, (cudaStream_t)stream>>>(tmQ, tmK, tmV, tmdO, tmdQ, p);
+  fa_bwd_kernel<<<grid, FA_BWD_THREADS, FA_BWD_SMEM, (cudaStream_t)stream>>>(tmQ, tmK, tmV, tmdO, tmdQ, p);
   return launch_status("fa_bwd");
 }

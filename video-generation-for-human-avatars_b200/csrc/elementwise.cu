@@ -31,6 +31,14 @@ __device__ __forceinline__ Row8 ld_bf16x8(const bf16* p) {
   r.v[6] = bf16_lo(u.w); r.v[7] = bf16_hi(u.w);
   return r;
 }
+__device__ __forceinline__ Row8 unpack8(const uint4& u) {
+  Row8 r;
+  r.v[0] = bf16_lo(u.x); r.v[1] = bf16_hi(u.x);
+  r.v[2] = bf16_lo(u.y); r.v[3] = bf16_hi(u.y);
+  r.v[4] = bf16_lo(u.z); r.v[5] = bf16_hi(u.z);
+  r.v[6] = bf16_lo(u.w); r.v[7] = bf16_hi(u.w);
+  return r;
+}
 __device__ __forceinline__ Row8 ld_f32x8(const float* p) {
   float4 a = *reinterpret_cast<const float4*>(p);
   float4 b = *reinterpret_cast<const float4*>(p + 4);
@@ -56,13 +64,12 @@ __device__ __forceinline__ float warp_sum(float v) {
 // ---------------------------------------------------------------------------------------------
 // y = norm(x) * (1 + scale[b]) + shift[b]     (ln = 0: RMSNorm, ln = 1: LayerNorm, no affine)
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) norm_mod_fwd_kernel(
+__global__ void __launch_bounds__(128, 4) norm_mod_fwd_kernel(
     const bf16* __restrict__ x, int64_t ldx, bf16* __restrict__ y, int64_t ldy,
     const bf16* __restrict__ scale, const bf16* __restrict__ shift, int64_t mod_stride,
     int64_t rows, int D, int64_t rows_per_mod, float eps, int ln) {
-  int64_t row = (int64_t)blockIdx.x * 4 + (threadIdx.x >> 5);
-  if (row >= rows) return;
-  int lane = threadIdx.x & 31;
+  const int lane = threadIdx.x & 31;
+  for (int64_t row = (int64_t)blockIdx.x * 4 + (threadIdx.x >> 5); row < rows; row += (int64_t)gridDim.x * 4) {
   const bf16* xr = x + row * ldx;
   Row8 xv[kMaxChunks];
   float s1 = 0.f, s2 = 0.f;
@@ -107,78 +114,94 @@ __global__ void __launch_bounds__(128) norm_mod_fwd_kernel(
       st_bf16x8(yr + col, o);
     }
   }
+  }
 }
 
 // dx = dres + rstd * (g - mean(g) [ln] - xhat * mean(g * xhat)),   g = dy * (1 + scale)
-__global__ void __launch_bounds__(128) norm_mod_bwd_kernel(
+__global__ void __launch_bounds__(128, 4) norm_mod_bwd_kernel(
     const bf16* __restrict__ dy, int64_t lddy, const bf16* __restrict__ x, int64_t ldx,
     const bf16* __restrict__ scale, int64_t mod_stride, const bf16* __restrict__ dres,
     int64_t lddres, bf16* __restrict__ dx, int64_t lddx, int64_t rows, int D,
     int64_t rows_per_mod, float eps, int ln) {
-  int64_t row = (int64_t)blockIdx.x * 4 + (threadIdx.x >> 5);
-  if (row >= rows) return;
-  int lane = threadIdx.x & 31;
-  const bf16* xr = x + row * ldx;
-  const bf16* gr = dy + row * lddy;
-  int64_t mb = row / rows_per_mod;
-  const bf16* sc = scale ? scale + mb * mod_stride : nullptr;
-  Row8 xv[kMaxChunks], gv[kMaxChunks];
-  float s1 = 0.f, s2 = 0.f;
+  const int lane = threadIdx.x & 31;
+  for (int64_t row = (int64_t)blockIdx.x * 4 + (threadIdx.x >> 5); row < rows; row += (int64_t)gridDim.x * 4) {
+    const bf16* xr = x + row * ldx;
+    const bf16* gr = dy + row * lddy;
+    const int64_t mb = row / rows_per_mod;
+    const bf16* sc = scale ? scale + mb * mod_stride : nullptr;
+    // x and dy stay packed (bf16) in registers: 64 registers instead of 128, so 4 blocks fit per SM
+    uint4 xp[kMaxChunks], gp[kMaxChunks];
+    float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-  for (int c = 0; c < kMaxChunks; ++c) {
-    int col = (c * 32 + lane) * 8;
-    if (col < D) {
-      xv[c] = ld_bf16x8(xr + col);
-      gv[c] = ld_bf16x8(gr + col);
-      if (sc) {
-        Row8 a = ld_bf16x8(sc + col);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) gv[c].v[i] *= (1.f + a.v[i]);
-      }
-#pragma unroll
-      for (int i = 0; i < 8; ++i) { s1 += xv[c].v[i]; s2 += xv[c].v[i] * xv[c].v[i]; }
-    }
-  }
-  s2 = warp_sum(s2);
-  float mean = 0.f, rstd;
-  if (ln) {
-    s1 = warp_sum(s1);
-    mean = s1 / D;
-    rstd = rsqrtf(fmaxf(s2 / D - mean * mean, 0.f) + eps);
-  } else {
-    rstd = rsqrtf(s2 / D + eps);
-  }
-  float gsum = 0.f, gx = 0.f;
-#pragma unroll
-  for (int c = 0; c < kMaxChunks; ++c) {
-    int col = (c * 32 + lane) * 8;
-    if (col < D) {
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        float xh = (xv[c].v[i] - mean) * rstd;
-        xv[c].v[i] = xh;
-        gsum += gv[c].v[i];
-        gx += gv[c].v[i] * xh;
+    for (int c = 0; c < kMaxChunks; ++c) {
+      const int col = (c * 32 + lane) * 8;
+      if (col < D) {
+        xp[c] = *reinterpret_cast<const uint4*>(xr + col);
+        gp[c] = *reinterpret_cast<const uint4*>(gr + col);
       }
     }
-  }
-  gx = warp_sum(gx) / D;
-  gsum = ln ? warp_sum(gsum) / D : 0.f;
-  bf16* outr = dx + row * lddx;
-  const bf16* rr = dres ? dres + row * lddres : nullptr;
 #pragma unroll
-  for (int c = 0; c < kMaxChunks; ++c) {
-    int col = (c * 32 + lane) * 8;
-    if (col < D) {
-      Row8 o, r;
-      if (rr) r = ld_bf16x8(rr + col);
+    for (int c = 0; c < kMaxChunks; ++c) {
+      const int col = (c * 32 + lane) * 8;
+      if (col < D) {
+        const Row8 xv = unpack8(xp[c]);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        float d = rstd * (gv[c].v[i] - gsum - xv[c].v[i] * gx);
-        if (rr) d += r.v[i];
-        o.v[i] = d;
+        for (int i = 0; i < 8; ++i) { s1 += xv.v[i]; s2 += xv.v[i] * xv.v[i]; }
       }
-      st_bf16x8(outr + col, o);
+    }
+    s2 = warp_sum(s2);
+    float mean = 0.f, rstd;
+    if (ln) {
+      s1 = warp_sum(s1);
+      mean = s1 / D;
+      rstd = rsqrtf(fmaxf(s2 / D - mean * mean, 0.f) + eps);
+    } else {
+      rstd = rsqrtf(s2 / D + eps);
+    }
+    float gsum = 0.f, gx = 0.f;
+#pragma unroll
+    for (int c = 0; c < kMaxChunks; ++c) {
+      const int col = (c * 32 + lane) * 8;
+      if (col < D) {
+        const Row8 xv = unpack8(xp[c]);
+        Row8 gv = unpack8(gp[c]);
+        if (sc) {
+          const Row8 a = ld_bf16x8(sc + col);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) gv.v[i] *= (1.f + a.v[i]);
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          gsum += gv.v[i];
+          gx += gv.v[i] * ((xv.v[i] - mean) * rstd);
+        }
+      }
+    }
+    gx = warp_sum(gx) / D;
+    gsum = ln ? warp_sum(gsum) / D : 0.f;
+    bf16* outr = dx + row * lddx;
+    const bf16* rr = dres ? dres + row * lddres : nullptr;
+#pragma unroll
+    for (int c = 0; c < kMaxChunks; ++c) {
+      const int col = (c * 32 + lane) * 8;
+      if (col < D) {
+        const Row8 xv = unpack8(xp[c]);
+        Row8 gv = unpack8(gp[c]);
+        if (sc) {
+          const Row8 a = ld_bf16x8(sc + col);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) gv.v[i] *= (1.f + a.v[i]);
+        }
+        Row8 o, r;
+        if (rr) r = ld_bf16x8(rr + col);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          float d = rstd * (gv.v[i] - gsum - (xv.v[i] - mean) * rstd * gx);
+          if (rr) d += r.v[i];
+          o.v[i] = d;
+        }
+        st_bf16x8(outr + col, o);
+      }
     }
   }
 }
@@ -186,19 +209,18 @@ __global__ void __launch_bounds__(128) norm_mod_bwd_kernel(
 // ---------------------------------------------------------------------------------------------
 // q/k RMSNorm (affine) + RoPE.  One warp per (row, tensor).  cos/sin may be null (attn2).
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) qknorm_rope_fwd_kernel(
+__global__ void __launch_bounds__(128, 4) qknorm_rope_fwd_kernel(
     const bf16* __restrict__ xq, int64_t ldq, const bf16* __restrict__ xk, int64_t ldk,
     const bf16* __restrict__ wq, const bf16* __restrict__ wk, const bf16* __restrict__ cosp,
     const bf16* __restrict__ sinp, int64_t ldcs, bf16* __restrict__ oq, int64_t ldoq,
     bf16* __restrict__ ok, int64_t ldok, int64_t rows_q, int64_t rows_k, int D, float eps) {
-  int64_t w = (int64_t)blockIdx.x * 4 + (threadIdx.x >> 5);
-  if (w >= rows_q + rows_k) return;
+  const int lane = threadIdx.x & 31;
+  for (int64_t w = (int64_t)blockIdx.x * 4 + (threadIdx.x >> 5); w < rows_q + rows_k; w += (int64_t)gridDim.x * 4) {
   bool is_k = w >= rows_q;
   int64_t row = is_k ? w - rows_q : w;
   const bf16* xr = is_k ? xk + row * ldk : xq + row * ldq;
   const bf16* wt = is_k ? wk : wq;
   bf16* outr = is_k ? ok + row * ldok : oq + row * ldoq;
-  int lane = threadIdx.x & 31;
   Row8 xv[kMaxChunks];
   float s2 = 0.f;
 #pragma unroll
@@ -232,18 +254,19 @@ __global__ void __launch_bounds__(128) qknorm_rope_fwd_kernel(
       st_bf16x8(outr + col, o);
     }
   }
+  }
 }
 
 // gradient wrt the pre-norm projections.  dq/dk may be fp32 (attention backward accumulates dq in
 // fp32) or bf16.  dx = rstd * (w*dy - xhat * mean(w*dy*xhat)),  dy = RoPE^T(dout)
-__global__ void __launch_bounds__(128) qknorm_rope_bwd_kernel(
+__global__ void __launch_bounds__(128, 4) qknorm_rope_bwd_kernel(
     const void* __restrict__ dq, int64_t lddq, int dq_f32, const void* __restrict__ dk, int64_t lddk,
     int dk_f32, const bf16* __restrict__ xq, int64_t ldq, const bf16* __restrict__ xk, int64_t ldk,
     const bf16* __restrict__ wq, const bf16* __restrict__ wk, const bf16* __restrict__ cosp,
     const bf16* __restrict__ sinp, int64_t ldcs, bf16* __restrict__ oq, int64_t ldoq,
     bf16* __restrict__ ok, int64_t ldok, int64_t rows_q, int64_t rows_k, int D, float eps) {
-  int64_t w = (int64_t)blockIdx.x * 4 + (threadIdx.x >> 5);
-  if (w >= rows_q + rows_k) return;
+  const int lane = threadIdx.x & 31;
+  for (int64_t w = (int64_t)blockIdx.x * 4 + (threadIdx.x >> 5); w < rows_q + rows_k; w += (int64_t)gridDim.x * 4) {
   bool is_k = w >= rows_q;
   int64_t row = is_k ? w - rows_q : w;
   const bf16* xr = is_k ? xk + row * ldk : xq + row * ldq;
@@ -252,14 +275,14 @@ __global__ void __launch_bounds__(128) qknorm_rope_bwd_kernel(
   int64_t ldg = is_k ? lddk : lddq;
   int g_f32 = is_k ? dk_f32 : dq_f32;
   bf16* outr = is_k ? ok + row * ldok : oq + row * ldoq;
-  int lane = threadIdx.x & 31;
-  Row8 xv[kMaxChunks], gv[kMaxChunks];
+  uint4 xp[kMaxChunks];  // x stays packed (bf16): 32 registers
+  Row8 gv[kMaxChunks];
   float s2 = 0.f;
 #pragma unroll
   for (int c = 0; c < kMaxChunks; ++c) {
     int col = (c * 32 + lane) * 8;
     if (col < D) {
-      xv[c] = ld_bf16x8(xr + col);
+      xp[c] = *reinterpret_cast<const uint4*>(xr + col);
       Row8 g = g_f32 ? ld_f32x8(reinterpret_cast<const float*>(gp) + row * ldg + col)
                      : ld_bf16x8(reinterpret_cast<const bf16*>(gp) + row * ldg + col);
       if (cosp) {
@@ -274,10 +297,11 @@ __global__ void __launch_bounds__(128) qknorm_rope_bwd_kernel(
         gv[c] = g;
       }
       Row8 wv = ld_bf16x8(wt + col);
+      const Row8 xv = unpack8(xp[c]);
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         gv[c].v[i] *= wv.v[i];
-        s2 += xv[c].v[i] * xv[c].v[i];
+        s2 += xv.v[i] * xv.v[i];
       }
     }
   }
@@ -287,11 +311,9 @@ __global__ void __launch_bounds__(128) qknorm_rope_bwd_kernel(
   for (int c = 0; c < kMaxChunks; ++c) {
     int col = (c * 32 + lane) * 8;
     if (col < D) {
+      const Row8 xv = unpack8(xp[c]);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        xv[c].v[i] *= rstd;
-        gx += gv[c].v[i] * xv[c].v[i];
-      }
+      for (int i = 0; i < 8; ++i) gx += gv[c].v[i] * (xv.v[i] * rstd);
     }
   }
   gx = warp_sum(gx) / D;
@@ -299,11 +321,13 @@ __global__ void __launch_bounds__(128) qknorm_rope_bwd_kernel(
   for (int c = 0; c < kMaxChunks; ++c) {
     int col = (c * 32 + lane) * 8;
     if (col < D) {
+      const Row8 xv = unpack8(xp[c]);
       Row8 o;
 #pragma unroll
-      for (int i = 0; i < 8; ++i) o.v[i] = rstd * (gv[c].v[i] - xv[c].v[i] * gx);
+      for (int i = 0; i < 8; ++i) o.v[i] = rstd * (gv[c].v[i] - xv.v[i] * rstd * gx);
       st_bf16x8(outr + col, o);
     }
+  }
   }
 }
 
@@ -480,6 +504,13 @@ using namespace b200;
     if (!(cond)) return arg_error(msg); \
   } while (0)
 
+// persistent row kernels: 4 rows per block per pass, a few blocks per SM, grid-stride over the rows
+static inline unsigned row_grid(int64_t rows) {
+  int64_t blocks = (rows + 3) / 4;
+  const int64_t cap = 148 * 6;
+  return (unsigned)(blocks < cap ? blocks : cap);
+}
+
 static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
 extern "C" int b200_norm_mod_fwd(const void* x, int64_t ldx, void* y, int64_t ldy, const void* scale,
@@ -492,7 +523,7 @@ extern "C" int b200_norm_mod_fwd(const void* x, int64_t ldx, void* y, int64_t ld
             "norm_mod_fwd: 16-byte alignment required");
   CHECK_ARG(rows_per_mod > 0, "norm_mod_fwd: rows_per_mod must be positive");
   if (rows == 0) return 0;
-  norm_mod_fwd_kernel<<<(unsigned)((rows + 3) / 4), 128, 0, (cudaStream_t)stream>>>(
+  norm_mod_fwd_kernel<<<row_grid(rows), 128, 0, (cudaStream_t)stream>>>(
       (const bf16*)x, ldx, (bf16*)y, ldy, (const bf16*)scale, (const bf16*)shift, mod_stride, rows,
       D, rows_per_mod, eps, layernorm);
   return launch_status("norm_mod_fwd");
@@ -510,7 +541,7 @@ extern "C" int b200_norm_mod_bwd(const void* dy, int64_t lddy, const void* x, in
             "norm_mod_bwd: 16-byte alignment required");
   CHECK_ARG(rows_per_mod > 0, "norm_mod_bwd: rows_per_mod must be positive");
   if (rows == 0) return 0;
-  norm_mod_bwd_kernel<<<(unsigned)((rows + 3) / 4), 128, 0, (cudaStream_t)stream>>>(
+  norm_mod_bwd_kernel<<<row_grid(rows), 128, 0, (cudaStream_t)stream>>>(
       (const bf16*)dy, lddy, (const bf16*)x, ldx, (const bf16*)scale, mod_stride,
       (const bf16*)dres, lddres, (bf16*)dx, lddx, rows, D, rows_per_mod, eps, layernorm);
   return launch_status("norm_mod_bwd");
@@ -534,7 +565,7 @@ extern "C" int b200_qknorm_rope_fwd(const void* xq, int64_t ldq, const void* xk,
             "qknorm_rope_fwd: 16-byte alignment required");
   int64_t total = rows_q + rows_k;
   if (total == 0) return 0;
-  qknorm_rope_fwd_kernel<<<(unsigned)((total + 3) / 4), 128, 0, (cudaStream_t)stream>>>(
+  qknorm_rope_fwd_kernel<<<row_grid(total), 128, 0, (cudaStream_t)stream>>>(
       (const bf16*)xq, ldq, (const bf16*)xk, ldk, (const bf16*)wq, (const bf16*)wk,
       (const bf16*)cos_t, (const bf16*)sin_t, ldcs, (bf16*)oq, ldoq, (bf16*)ok, ldok, rows_q, rows_k,
       D, eps);
@@ -561,7 +592,7 @@ extern "C" int b200_qknorm_rope_bwd(const void* dq, int64_t lddq, int dq_is_f32,
             "qknorm_rope_bwd: 16-byte alignment required");
   int64_t total = rows_q + rows_k;
   if (total == 0) return 0;
-  qknorm_rope_bwd_kernel<<<(unsigned)((total + 3) / 4), 128, 0, (cudaStream_t)stream>>>(
+  qknorm_rope_bwd_kernel<<<row_grid(total), 128, 0, (cudaStream_t)stream>>>(
       dq, lddq, dq_is_f32, dk, lddk, dk_is_f32, (const bf16*)xq, ldq, (const bf16*)xk, ldk,
       (const bf16*)wq, (const bf16*)wk, (const bf16*)cos_t, (const bf16*)sin_t, ldcs, (bf16*)oq, ldoq,
       (bf16*)ok, ldok, rows_q, rows_k, D, eps);

@@ -68,15 +68,20 @@ def _frozen_plain(mod) -> bool:
     return lora is None and not W.requires_grad and (b is None or not b.requires_grad)
 
 
-def _cached_wqkv(attn) -> torch.Tensor:
-    """[3D, D] concatenation of the frozen q/k/v weights (read as the [K,N] operand of the fused dgrad)."""
-    ws = [linear_parts(m)[0] for m in (attn.to_q, attn.to_k, attn.to_v)]
-    key = tuple((w.data_ptr(), w._version) for w in ws)
+def _cached_wqkv(attn):
+    """[3D, D] concatenation of the frozen q/k/v weights (+ [3D] biases): one forward GEMM, and the
+    [K,N] operand of the fused dgrad.  Re-built if the parameters are replaced or modified in place."""
+    parts = [linear_parts(m) for m in (attn.to_q, attn.to_k, attn.to_v)]
+    key = tuple((w.data_ptr(), w._version, None if b is None else (b.data_ptr(), b._version)) for w, b, _ in parts)
     cache = attn.__dict__.get("_b200_wqkv")
     if cache is None or cache[0] != key:
-        cache = (key, torch.cat([w.detach() for w in ws], dim=0).contiguous())
+        W = torch.cat([w.detach() for w, _, _ in parts], dim=0).contiguous()
+        bias = None
+        if parts[0][1] is not None:
+            bias = torch.cat([b.detach() for _, b, _ in parts], dim=0).contiguous()
+        cache = (key, W, bias)
         attn.__dict__["_b200_wqkv"] = cache
-    return cache[1]
+    return cache[1], cache[2]
 
 
 # ---------------------------------------------------------------------------------------------
@@ -123,10 +128,10 @@ def attention_forward(attn, hidden_states, freqs_cis=None, encoder_hidden_states
             and linear_parts(attn.to_out[0])[2] is None and not linear_parts(attn.to_out[0])[0].requires_grad
             and not wqn.requires_grad and not wkn.requires_grad)
     if fast:
-        (Wq, bq, _), (Wk, bk, _), (Wv, bv, _) = (linear_parts(m) for m in (attn.to_q, attn.to_k, attn.to_v))
         Wo, bo, _ = linear_parts(attn.to_out[0])
-        y = ops.SelfAttnFn.apply(x2d, Wq, bq, Wk, bk, Wv, bv, _cached_wqkv(attn), wqn, wkn, cos, sin, Wo, bo,
-                                 gate, rows_per_gate, res, kb, B, H, Nq, scale)
+        Wqkv, bqkv = _cached_wqkv(attn)
+        y = ops.SelfAttnFn.apply(x2d, Wqkv, bqkv, wqn, wkn, cos, sin, Wo, bo, gate, rows_per_gate, res, kb, B, H,
+                                 Nq, scale)
         return y.view(B, Nq, -1)
 
     q_pre = apply_linear(attn.to_q, x2d)

@@ -439,18 +439,15 @@ class SelfAttnFn(torch.autograd.Function):
 
         y = gate * (FA(rope(qnorm(x Wq^T)), rope(knorm(x Wk^T)), x Wv^T) Wo^T + bo) + res
 
-    Forward: 3 projection GEMMs into one packed [M,3D] buffer, qk-norm+RoPE, flash attention, output
+    Forward: one projection GEMM into a packed [M,3D] buffer, qk-norm+RoPE, flash attention, output
     GEMM with the AdaLN gate and the residual in its epilogue.  Backward: one dgrad GEMM over the
     packed [M,3D] gradient against the cached [3D,D] concatenation of the frozen weights."""
 
     @staticmethod
-    def forward(ctx, x, Wq, bq, Wk, bk, Wv, bv, Wqkv, wqn, wkn, cos, sin, Wo, bo, gate, rows_per_gate, res,
-                key_bias, B, H, N, scale):
+    def forward(ctx, x, Wqkv, bqkv, wqn, wkn, cos, sin, Wo, bo, gate, rows_per_gate, res, key_bias, B, H, N,
+                scale):
         M, D = x.shape[0], H * 64
-        qkv = torch.empty((M, 3 * D), device=x.device, dtype=BF16)
-        gemm(x, Wq, out=qkv[:, :D], bias=bq)
-        gemm(x, Wk, out=qkv[:, D:2 * D], bias=bk)
-        gemm(x, Wv, out=qkv[:, 2 * D:], bias=bv)
+        qkv = gemm(x, Wqkv, bias=bqkv)  # one [M,3D] GEMM against the cached [3D,D] weight concatenation
         qk = torch.empty((M, 2 * D), device=x.device, dtype=BF16)
         qknorm_rope_fwd(qkv[:, :D], qkv[:, D:2 * D], wqn, wkn, cos, sin, qk[:, :D], qk[:, D:])
         o, lse = fa_fwd(qk[:, :D], qk[:, D:], qkv[:, 2 * D:], B, H, N, N, key_bias, scale)
@@ -474,5 +471,5 @@ class SelfAttnFn(torch.autograd.Function):
                       key_bias, scale)
         qknorm_rope_bwd(dq32, dk_post, qkv[:, :D], qkv[:, D:2 * D], wqn, wkn, cos, sin, dqkv[:, :D], dqkv[:, D:2 * D])
         dx = gemm(dqkv, Wqkv, b_rows_are_k=True) if ctx.needs_input_grad[0] else None
-        dres = dy if (has_res and ctx.needs_input_grad[16]) else None
-        return (dx,) + (None,) * 15 + (dres,) + (None,) * 5
+        dres = dy if (has_res and ctx.needs_input_grad[11]) else None
+        return (dx,) + (None,) * 10 + (dres,) + (None,) * 5
