@@ -74,8 +74,8 @@ __device__ __forceinline__ void store_p8(uint32_t addr, const float (&pv)[8]) {
                : "memory");
 }
 
-__device__ __forceinline__ void tile_exp_fast(uint32_t t_row, uint32_t sP, int row, float sl2, float neg_m,
-                                              float& l0, float& l1, float& l2, float& l3) {
+__device__ __forceinline__ void tile_exp_fast(uint32_t t_row, float sl2, float neg_m, float& l0, float& l1,
+                                              float& l2, float& l3) {
   uint32_t ra[32], rb[32];
   tmem_ld32(t_row, ra);
   tmem_ld_wait();
@@ -84,7 +84,9 @@ __device__ __forceinline__ void tile_exp_fast(uint32_t t_row, uint32_t sP, int r
     uint32_t(&cur)[32] = (c & 1) ? rb : ra;
     uint32_t(&nxt)[32] = (c & 1) ? ra : rb;
     if (c < 3) tmem_ld32(t_row + (c + 1) * 32, nxt);
-    const uint32_t sub = sP + (c >> 1) * 16384;
+    // P chunk c (32 keys -> 16 packed bf16x2 columns) overwrites S columns [16c, 16c+16), which belong
+    // to S chunk c/2 <= c and have already been read.
+    uint32_t pk[16];
 #pragma unroll
     for (int g = 0; g < 4; ++g) {
       float pv[8];
@@ -94,9 +96,13 @@ __device__ __forceinline__ void tile_exp_fast(uint32_t t_row, uint32_t sP, int r
       l1 += pv[1] + pv[5];
       l2 += pv[2] + pv[6];
       l3 += pv[3] + pv[7];
-      store_p8(sub + sw128_off(row, (c & 1) * 4 + g), pv);
+      pk[g * 4 + 0] = pack_bf16x2(pv[0], pv[1]);
+      pk[g * 4 + 1] = pack_bf16x2(pv[2], pv[3]);
+      pk[g * 4 + 2] = pack_bf16x2(pv[4], pv[5]);
+      pk[g * 4 + 3] = pack_bf16x2(pv[6], pv[7]);
     }
-    if (c < 3) tmem_ld_wait();
+    if (c < 3) tmem_ld_wait();  // chunk c+1 is in registers before any column it covers could be reused
+    tmem_st16(t_row + c * 16, pk);
   }
 }
 
@@ -121,15 +127,15 @@ __device__ __noinline__ float tile_max_general(uint32_t t_row, float sl2, const 
   return mx;
 }
 
-__device__ __noinline__ float tile_exp_general(uint32_t t_row, uint32_t sP, int row, float sl2, float neg_m,
-                                               const float* kb, int key0, int Nk) {
+__device__ __noinline__ float tile_exp_general(uint32_t t_row, float sl2, float neg_m, const float* kb,
+                                               int key0, int Nk) {
   float l = 0.f;
 #pragma unroll 1
   for (int c = 0; c < 4; ++c) {
     uint32_t r[32];
     tmem_ld32(t_row + c * 32, r);
     tmem_ld_wait();
-    const uint32_t sub = sP + (c >> 1) * 16384;
+    uint32_t pk[16];
 #pragma unroll
     for (int g = 0; g < 4; ++g) {
       float pv[8];
@@ -142,8 +148,12 @@ __device__ __noinline__ float tile_exp_general(uint32_t t_row, uint32_t sP, int 
         pv[i] = ex2_approx(x + neg_m);
         l += pv[i];
       }
-      store_p8(sub + sw128_off(row, (c & 1) * 4 + g), pv);
+      pk[g * 4 + 0] = pack_bf16x2(pv[0], pv[1]);
+      pk[g * 4 + 1] = pack_bf16x2(pv[2], pv[3]);
+      pk[g * 4 + 2] = pack_bf16x2(pv[4], pv[5]);
+      pk[g * 4 + 3] = pack_bf16x2(pv[6], pv[7]);
     }
+    tmem_st16(t_row + c * 16, pk);
   }
   return l;
 }
@@ -218,8 +228,8 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
       tc_fence_after();
 #pragma unroll
       for (int k = 0; k < 8; ++k)
-        umma_ss(tO, make_smem_desc(sP + (k >> 2) * 16384 + (k & 3) * 32, 16, 1024),
-                make_smem_desc(sV + k * 2048, 8192, 1024), idesc_pv, (j > 0 || k > 0) ? 1u : 0u);
+        umma_ts(tO, tS + k * 8, make_smem_desc(sV + k * 2048, 8192, 1024), idesc_pv,
+                (j > 0 || k > 0) ? 1u : 0u);  // A = P (bf16x2 packed, 8 TMEM columns per K=16 step)
       umma_commit(kv_empty0 + 8 * s);
       umma_commit(pv_done);
     }
@@ -265,10 +275,10 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
       }
       // pass 2: P = exp2(s * c - m), row sum, bf16 P into the swizzled A-operand tile
       if (general)
-        l0 += tile_exp_general(tS + lane_bits, sP, row, sl2, -m_used, kb, key0, p.Nk);
+        l0 += tile_exp_general(tS + lane_bits, sl2, -m_used, kb, key0, p.Nk);
       else
-        tile_exp_fast(tS + lane_bits, sP, row, sl2, -m_used, l0, l1, l2, l3);
-      fence_proxy_async_smem();
+        tile_exp_fast(tS + lane_bits, sl2, -m_used, l0, l1, l2, l3);
+      tmem_st_wait();
       tc_fence_before();
       mbar_arrive(p_full);
     }

@@ -16,7 +16,7 @@
 
 namespace b200 {
 
-constexpr int kMaxChunks = 8;  // 8 chunks x 32 lanes x 8 elements = 2048 channels
+// a lane holds up to 8 chunks x 8 elements of its row: 8 x 32 lanes x 8 = 2048 channels
 
 struct Row8 {
   float v[8];
@@ -64,6 +64,7 @@ __device__ __forceinline__ float warp_sum(float v) {
 // ---------------------------------------------------------------------------------------------
 // y = norm(x) * (1 + scale[b]) + shift[b]     (ln = 0: RMSNorm, ln = 1: LayerNorm, no affine)
 // ---------------------------------------------------------------------------------------------
+template <int NC, bool EXACT>
 __global__ void __launch_bounds__(128, 4) norm_mod_fwd_kernel(
     const bf16* __restrict__ x, int64_t ldx, bf16* __restrict__ y, int64_t ldy,
     const bf16* __restrict__ scale, const bf16* __restrict__ shift, int64_t mod_stride,
@@ -71,12 +72,12 @@ __global__ void __launch_bounds__(128, 4) norm_mod_fwd_kernel(
   const int lane = threadIdx.x & 31;
   for (int64_t row = (int64_t)blockIdx.x * 4 + (threadIdx.x >> 5); row < rows; row += (int64_t)gridDim.x * 4) {
   const bf16* xr = x + row * ldx;
-  Row8 xv[kMaxChunks];
+  Row8 xv[NC];
   float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-  for (int c = 0; c < kMaxChunks; ++c) {
+  for (int c = 0; c < NC; ++c) {
     int col = (c * 32 + lane) * 8;
-    if (col < D) {
+    if (EXACT || col < D) {
       xv[c] = ld_bf16x8(xr + col);
 #pragma unroll
       for (int i = 0; i < 8; ++i) { s1 += xv[c].v[i]; s2 += xv[c].v[i] * xv[c].v[i]; }
@@ -97,9 +98,9 @@ __global__ void __launch_bounds__(128, 4) norm_mod_fwd_kernel(
   const bf16* sh = shift ? shift + mb * mod_stride : nullptr;
   bf16* yr = y + row * ldy;
 #pragma unroll
-  for (int c = 0; c < kMaxChunks; ++c) {
+  for (int c = 0; c < NC; ++c) {
     int col = (c * 32 + lane) * 8;
-    if (col < D) {
+    if (EXACT || col < D) {
       Row8 o;
       Row8 a, b;
       if (sc) a = ld_bf16x8(sc + col);
@@ -118,6 +119,7 @@ __global__ void __launch_bounds__(128, 4) norm_mod_fwd_kernel(
 }
 
 // dx = dres + rstd * (g - mean(g) [ln] - xhat * mean(g * xhat)),   g = dy * (1 + scale)
+template <int NC, bool EXACT>
 __global__ void __launch_bounds__(128, 4) norm_mod_bwd_kernel(
     const bf16* __restrict__ dy, int64_t lddy, const bf16* __restrict__ x, int64_t ldx,
     const bf16* __restrict__ scale, int64_t mod_stride, const bf16* __restrict__ dres,
@@ -130,20 +132,20 @@ __global__ void __launch_bounds__(128, 4) norm_mod_bwd_kernel(
     const int64_t mb = row / rows_per_mod;
     const bf16* sc = scale ? scale + mb * mod_stride : nullptr;
     // x and dy stay packed (bf16) in registers: 64 registers instead of 128, so 4 blocks fit per SM
-    uint4 xp[kMaxChunks], gp[kMaxChunks];
+    uint4 xp[NC], gp[NC];
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-    for (int c = 0; c < kMaxChunks; ++c) {
+    for (int c = 0; c < NC; ++c) {
       const int col = (c * 32 + lane) * 8;
-      if (col < D) {
+      if (EXACT || col < D) {
         xp[c] = *reinterpret_cast<const uint4*>(xr + col);
         gp[c] = *reinterpret_cast<const uint4*>(gr + col);
       }
     }
 #pragma unroll
-    for (int c = 0; c < kMaxChunks; ++c) {
+    for (int c = 0; c < NC; ++c) {
       const int col = (c * 32 + lane) * 8;
-      if (col < D) {
+      if (EXACT || col < D) {
         const Row8 xv = unpack8(xp[c]);
 #pragma unroll
         for (int i = 0; i < 8; ++i) { s1 += xv.v[i]; s2 += xv.v[i] * xv.v[i]; }
@@ -160,9 +162,9 @@ __global__ void __launch_bounds__(128, 4) norm_mod_bwd_kernel(
     }
     float gsum = 0.f, gx = 0.f;
 #pragma unroll
-    for (int c = 0; c < kMaxChunks; ++c) {
+    for (int c = 0; c < NC; ++c) {
       const int col = (c * 32 + lane) * 8;
-      if (col < D) {
+      if (EXACT || col < D) {
         const Row8 xv = unpack8(xp[c]);
         Row8 gv = unpack8(gp[c]);
         if (sc) {
@@ -182,9 +184,9 @@ __global__ void __launch_bounds__(128, 4) norm_mod_bwd_kernel(
     bf16* outr = dx + row * lddx;
     const bf16* rr = dres ? dres + row * lddres : nullptr;
 #pragma unroll
-    for (int c = 0; c < kMaxChunks; ++c) {
+    for (int c = 0; c < NC; ++c) {
       const int col = (c * 32 + lane) * 8;
-      if (col < D) {
+      if (EXACT || col < D) {
         const Row8 xv = unpack8(xp[c]);
         Row8 gv = unpack8(gp[c]);
         if (sc) {
@@ -209,6 +211,7 @@ __global__ void __launch_bounds__(128, 4) norm_mod_bwd_kernel(
 // ---------------------------------------------------------------------------------------------
 // q/k RMSNorm (affine) + RoPE.  One warp per (row, tensor).  cos/sin may be null (attn2).
 // ---------------------------------------------------------------------------------------------
+template <int NC, bool EXACT>
 __global__ void __launch_bounds__(128, 4) qknorm_rope_fwd_kernel(
     const bf16* __restrict__ xq, int64_t ldq, const bf16* __restrict__ xk, int64_t ldk,
     const bf16* __restrict__ wq, const bf16* __restrict__ wk, const bf16* __restrict__ cosp,
@@ -221,12 +224,12 @@ __global__ void __launch_bounds__(128, 4) qknorm_rope_fwd_kernel(
   const bf16* xr = is_k ? xk + row * ldk : xq + row * ldq;
   const bf16* wt = is_k ? wk : wq;
   bf16* outr = is_k ? ok + row * ldok : oq + row * ldoq;
-  Row8 xv[kMaxChunks];
+  Row8 xv[NC];
   float s2 = 0.f;
 #pragma unroll
-  for (int c = 0; c < kMaxChunks; ++c) {
+  for (int c = 0; c < NC; ++c) {
     int col = (c * 32 + lane) * 8;
-    if (col < D) {
+    if (EXACT || col < D) {
       xv[c] = ld_bf16x8(xr + col);
 #pragma unroll
       for (int i = 0; i < 8; ++i) s2 += xv[c].v[i] * xv[c].v[i];
@@ -234,9 +237,9 @@ __global__ void __launch_bounds__(128, 4) qknorm_rope_fwd_kernel(
   }
   float rstd = rsqrtf(warp_sum(s2) / D + eps);
 #pragma unroll
-  for (int c = 0; c < kMaxChunks; ++c) {
+  for (int c = 0; c < NC; ++c) {
     int col = (c * 32 + lane) * 8;
-    if (col < D) {
+    if (EXACT || col < D) {
       Row8 wv = ld_bf16x8(wt + col), o;
 #pragma unroll
       for (int i = 0; i < 8; ++i) xv[c].v[i] = xv[c].v[i] * rstd * wv.v[i];
@@ -259,6 +262,7 @@ __global__ void __launch_bounds__(128, 4) qknorm_rope_fwd_kernel(
 
 // gradient wrt the pre-norm projections.  dq/dk may be fp32 (attention backward accumulates dq in
 // fp32) or bf16.  dx = rstd * (w*dy - xhat * mean(w*dy*xhat)),  dy = RoPE^T(dout)
+template <int NC, bool EXACT>
 __global__ void __launch_bounds__(128, 4) qknorm_rope_bwd_kernel(
     const void* __restrict__ dq, int64_t lddq, int dq_f32, const void* __restrict__ dk, int64_t lddk,
     int dk_f32, const bf16* __restrict__ xq, int64_t ldq, const bf16* __restrict__ xk, int64_t ldk,
@@ -275,13 +279,13 @@ __global__ void __launch_bounds__(128, 4) qknorm_rope_bwd_kernel(
   int64_t ldg = is_k ? lddk : lddq;
   int g_f32 = is_k ? dk_f32 : dq_f32;
   bf16* outr = is_k ? ok + row * ldok : oq + row * ldoq;
-  uint4 xp[kMaxChunks];  // x stays packed (bf16): 32 registers
-  Row8 gv[kMaxChunks];
+  uint4 xp[NC];  // x stays packed (bf16): 32 registers
+  Row8 gv[NC];
   float s2 = 0.f;
 #pragma unroll
-  for (int c = 0; c < kMaxChunks; ++c) {
+  for (int c = 0; c < NC; ++c) {
     int col = (c * 32 + lane) * 8;
-    if (col < D) {
+    if (EXACT || col < D) {
       xp[c] = *reinterpret_cast<const uint4*>(xr + col);
       Row8 g = g_f32 ? ld_f32x8(reinterpret_cast<const float*>(gp) + row * ldg + col)
                      : ld_bf16x8(reinterpret_cast<const bf16*>(gp) + row * ldg + col);
@@ -308,9 +312,9 @@ __global__ void __launch_bounds__(128, 4) qknorm_rope_bwd_kernel(
   float rstd = rsqrtf(warp_sum(s2) / D + eps);
   float gx = 0.f;
 #pragma unroll
-  for (int c = 0; c < kMaxChunks; ++c) {
+  for (int c = 0; c < NC; ++c) {
     int col = (c * 32 + lane) * 8;
-    if (col < D) {
+    if (EXACT || col < D) {
       const Row8 xv = unpack8(xp[c]);
 #pragma unroll
       for (int i = 0; i < 8; ++i) gx += gv[c].v[i] * (xv.v[i] * rstd);
@@ -318,9 +322,9 @@ __global__ void __launch_bounds__(128, 4) qknorm_rope_bwd_kernel(
   }
   gx = warp_sum(gx) / D;
 #pragma unroll
-  for (int c = 0; c < kMaxChunks; ++c) {
+  for (int c = 0; c < NC; ++c) {
     int col = (c * 32 + lane) * 8;
-    if (col < D) {
+    if (EXACT || col < D) {
       const Row8 xv = unpack8(xp[c]);
       Row8 o;
 #pragma unroll
@@ -504,6 +508,27 @@ using namespace b200;
     if (!(cond)) return arg_error(msg); \
   } while (0)
 
+// Row kernels are instantiated per chunk count (D = NC * 256 exactly) so that the per-chunk code is
+// branch-free and all 16-byte loads of a row are in flight together; any other D <= 2048 takes the
+// predicated 8-chunk instantiation.
+#define ROW_DISPATCH(KERNEL, D, GRID, STREAM, ...)                                            \
+  do {                                                                                        \
+    if ((D) % 256 == 0) {                                                                     \
+      switch ((D) / 256) {                                                                    \
+        case 1: KERNEL<1, true><<<GRID, 128, 0, STREAM>>>(__VA_ARGS__); break;                \
+        case 2: KERNEL<2, true><<<GRID, 128, 0, STREAM>>>(__VA_ARGS__); break;                \
+        case 3: KERNEL<3, true><<<GRID, 128, 0, STREAM>>>(__VA_ARGS__); break;                \
+        case 4: KERNEL<4, true><<<GRID, 128, 0, STREAM>>>(__VA_ARGS__); break;                \
+        case 5: KERNEL<5, true><<<GRID, 128, 0, STREAM>>>(__VA_ARGS__); break;                \
+        case 6: KERNEL<6, true><<<GRID, 128, 0, STREAM>>>(__VA_ARGS__); break;                \
+        case 7: KERNEL<7, true><<<GRID, 128, 0, STREAM>>>(__VA_ARGS__); break;                \
+        default: KERNEL<8, true><<<GRID, 128, 0, STREAM>>>(__VA_ARGS__); break;               \
+      }                                                                                       \
+    } else {                                                                                  \
+      KERNEL<8, false><<<GRID, 128, 0, STREAM>>>(__VA_ARGS__);                                \
+    }                                                                                         \
+  } while (0)
+
 // persistent row kernels: 4 rows per block per pass, a few blocks per SM, grid-stride over the rows
 static inline unsigned row_grid(int64_t rows) {
   int64_t blocks = (rows + 3) / 4;
@@ -523,7 +548,7 @@ extern "C" int b200_norm_mod_fwd(const void* x, int64_t ldx, void* y, int64_t ld
             "norm_mod_fwd: 16-byte alignment required");
   CHECK_ARG(rows_per_mod > 0, "norm_mod_fwd: rows_per_mod must be positive");
   if (rows == 0) return 0;
-  norm_mod_fwd_kernel<<<row_grid(rows), 128, 0, (cudaStream_t)stream>>>(
+  ROW_DISPATCH(norm_mod_fwd_kernel, D, row_grid(rows), (cudaStream_t)stream,
       (const bf16*)x, ldx, (bf16*)y, ldy, (const bf16*)scale, (const bf16*)shift, mod_stride, rows,
       D, rows_per_mod, eps, layernorm);
   return launch_status("norm_mod_fwd");
@@ -541,7 +566,7 @@ extern "C" int b200_norm_mod_bwd(const void* dy, int64_t lddy, const void* x, in
             "norm_mod_bwd: 16-byte alignment required");
   CHECK_ARG(rows_per_mod > 0, "norm_mod_bwd: rows_per_mod must be positive");
   if (rows == 0) return 0;
-  norm_mod_bwd_kernel<<<row_grid(rows), 128, 0, (cudaStream_t)stream>>>(
+  ROW_DISPATCH(norm_mod_bwd_kernel, D, row_grid(rows), (cudaStream_t)stream,
       (const bf16*)dy, lddy, (const bf16*)x, ldx, (const bf16*)scale, mod_stride,
       (const bf16*)dres, lddres, (bf16*)dx, lddx, rows, D, rows_per_mod, eps, layernorm);
   return launch_status("norm_mod_bwd");
@@ -565,7 +590,7 @@ extern "C" int b200_qknorm_rope_fwd(const void* xq, int64_t ldq, const void* xk,
             "qknorm_rope_fwd: 16-byte alignment required");
   int64_t total = rows_q + rows_k;
   if (total == 0) return 0;
-  qknorm_rope_fwd_kernel<<<row_grid(total), 128, 0, (cudaStream_t)stream>>>(
+  ROW_DISPATCH(qknorm_rope_fwd_kernel, D, row_grid(total), (cudaStream_t)stream,
       (const bf16*)xq, ldq, (const bf16*)xk, ldk, (const bf16*)wq, (const bf16*)wk,
       (const bf16*)cos_t, (const bf16*)sin_t, ldcs, (bf16*)oq, ldoq, (bf16*)ok, ldok, rows_q, rows_k,
       D, eps);
@@ -592,7 +617,7 @@ extern "C" int b200_qknorm_rope_bwd(const void* dq, int64_t lddq, int dq_is_f32,
             "qknorm_rope_bwd: 16-byte alignment required");
   int64_t total = rows_q + rows_k;
   if (total == 0) return 0;
-  qknorm_rope_bwd_kernel<<<row_grid(total), 128, 0, (cudaStream_t)stream>>>(
+  ROW_DISPATCH(qknorm_rope_bwd_kernel, D, row_grid(total), (cudaStream_t)stream,
       dq, lddq, dq_is_f32, dk, lddk, dk_is_f32, (const bf16*)xq, ldq, (const bf16*)xk, ldk,
       (const bf16*)wq, (const bf16*)wk, (const bf16*)cos_t, (const bf16*)sin_t, ldcs, (bf16*)oq, ldoq,
       (bf16*)ok, ldok, rows_q, rows_k, D, eps);

@@ -41,6 +41,7 @@ struct GemmParams {
   int64_t ldres;
   bf16* aux;
   int64_t ldaux;
+  int tma_store;  // bf16 outputs (C, and the GELU pre-activation) leave through smem staging + TMA stores
 };
 
 __device__ __forceinline__ float tanh_fast(float x) {
@@ -60,6 +61,43 @@ __device__ __forceinline__ float gelu_tanh_grad(float x) {
   return 0.5f * (1.f + t) + 0.5f * x * (1.f - t * t) * du;
 }
 
+// Fused epilogue math on 8 consecutive columns of one output row: + bias -> GELU (on the bf16-rounded
+// pre-activation, which is returned in `pre`) / GELU' -> * gate -> + residual.
+__device__ __forceinline__ void epi_math8(float (&v)[8], uint4& pre, int n, bool ld_ok, const GemmParams& p,
+                                          const bf16* gate_row, const bf16* res_row, const bf16* aux_row) {
+  if (p.bias) {
+    uint4 u = __ldg(reinterpret_cast<const uint4*>(p.bias + n));
+    v[0] += bf16_lo(u.x); v[1] += bf16_hi(u.x); v[2] += bf16_lo(u.y); v[3] += bf16_hi(u.y);
+    v[4] += bf16_lo(u.z); v[5] += bf16_hi(u.z); v[6] += bf16_lo(u.w); v[7] += bf16_hi(u.w);
+  }
+  if (p.epi == EPI_GELU) {
+    if (p.aux) {
+      pre.x = pack_bf16x2(v[0], v[1]); pre.y = pack_bf16x2(v[2], v[3]);
+      pre.z = pack_bf16x2(v[4], v[5]); pre.w = pack_bf16x2(v[6], v[7]);
+      v[0] = bf16_lo(pre.x); v[1] = bf16_hi(pre.x); v[2] = bf16_lo(pre.y); v[3] = bf16_hi(pre.y);
+      v[4] = bf16_lo(pre.z); v[5] = bf16_hi(pre.z); v[6] = bf16_lo(pre.w); v[7] = bf16_hi(pre.w);
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = gelu_tanh(v[i]);
+  } else if (p.epi == EPI_GELU_GRAD) {
+    uint4 u = ld_ok ? *reinterpret_cast<const uint4*>(aux_row + n) : make_uint4(0, 0, 0, 0);
+    float h[8] = {bf16_lo(u.x), bf16_hi(u.x), bf16_lo(u.y), bf16_hi(u.y),
+                  bf16_lo(u.z), bf16_hi(u.z), bf16_lo(u.w), bf16_hi(u.w)};
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] *= gelu_tanh_grad(h[i]);
+  }
+  if (gate_row) {
+    uint4 u = __ldg(reinterpret_cast<const uint4*>(gate_row + n));
+    v[0] *= bf16_lo(u.x); v[1] *= bf16_hi(u.x); v[2] *= bf16_lo(u.y); v[3] *= bf16_hi(u.y);
+    v[4] *= bf16_lo(u.z); v[5] *= bf16_hi(u.z); v[6] *= bf16_lo(u.w); v[7] *= bf16_hi(u.w);
+  }
+  if (res_row && ld_ok) {
+    uint4 u = *reinterpret_cast<const uint4*>(res_row + n);
+    v[0] += bf16_lo(u.x); v[1] += bf16_hi(u.x); v[2] += bf16_lo(u.y); v[3] += bf16_hi(u.y);
+    v[4] += bf16_lo(u.z); v[5] += bf16_hi(u.z); v[6] += bf16_lo(u.w); v[7] += bf16_hi(u.w);
+  }
+}
+
 template <int BN>
 struct GemmCfg {
   static constexpr int BM = 128, BK = 64;
@@ -68,19 +106,22 @@ struct GemmCfg {
   static constexpr int STAGE = A_BYTES + B_BYTES;
   static constexpr int NSTAGE = BN == 256 ? 4 : (BN == 128 ? 6 : 8);
   static constexpr int TMEM_COLS = 2 * BN;
-  static constexpr int SMEM = NSTAGE * STAGE + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int STAGING = 8 * 4096;  // one 32-row x 128-byte swizzled slab per epilogue warp
+  static constexpr int SMEM = NSTAGE * STAGE + STAGING + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
 template <int BN, bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(384, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
             const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB2,
+            const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmAux,
             const __grid_constant__ GemmParams p) {
   using Cfg = GemmCfg<BN>;
   constexpr int NSTAGE = Cfg::NSTAGE;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t bar_base = sbase + NSTAGE * Cfg::STAGE;
+  const uint32_t stage_base = sbase + NSTAGE * Cfg::STAGE;
+  const uint32_t bar_base = stage_base + Cfg::STAGING;
   auto full_bar = [&](int s) { return bar_base + s * 8; };
   auto empty_bar = [&](int s) { return bar_base + (NSTAGE + s) * 8; };
   auto tfull_bar = [&](int a) { return bar_base + (2 * NSTAGE + a) * 8; };
@@ -201,6 +242,53 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       const bf16* res_row = p.res ? p.res + row * p.ldres : nullptr;
       bf16* aux_row = p.aux ? p.aux + row * p.ldaux : nullptr;
       const uint32_t t_row = tmem_base + ((uint32_t)(ew * 32) << 16) + acc * BN;
+      if (BN >= 128 && p.tma_store) {
+        // Coalesced path: each warp packs a 32-row x 64-column bf16 slab into its swizzled staging
+        // buffer and hands it to the TMA (cp.async.bulk.tensor store clips rows/columns past M, N).
+        const uint32_t stg = stage_base + (warp - 4) * 4096;
+        const int row0 = mt * 128 + ew * 32;
+        const bool two_pass = (p.epi == EPI_GELU) && p.aux;  // pre-activation slab first, then the output
+#pragma unroll 1
+        for (int c = chalf * (BN / 2); c < (chalf + 1) * (BN / 2); c += 64) {
+          const int n_slab = nt * BN + c;
+          if (n_slab >= p.N) break;
+#pragma unroll 1
+          for (int pass = two_pass ? 0 : 1; pass < 2; ++pass) {
+            if (lane == 0) tma_store_wait_read<0>();  // the previous slab has left the staging buffer
+            __syncwarp();
+#pragma unroll
+            for (int hc = 0; hc < 2; ++hc) {
+              uint32_t r[32];
+              tmem_ld32(t_row + c + hc * 32, r);
+              tmem_ld_wait();
+#pragma unroll
+              for (int g = 0; g < 4; ++g) {
+                const int n = n_slab + hc * 32 + g * 8;
+                float v[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[g * 8 + i]);
+                uint4 u, pre = make_uint4(0, 0, 0, 0);
+                if (n < p.N) epi_math8(v, pre, n, row_ok, p, gate_row, res_row, aux_row);
+                if (pass == 0) {
+                  u = pre;
+                } else {
+                  u.x = pack_bf16x2(v[0], v[1]); u.y = pack_bf16x2(v[2], v[3]);
+                  u.z = pack_bf16x2(v[4], v[5]); u.w = pack_bf16x2(v[6], v[7]);
+                }
+                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stg + sw128_off(lane, hc * 4 + g)),
+                             "r"(u.x), "r"(u.y), "r"(u.z), "r"(u.w)
+                             : "memory");
+              }
+            }
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+              tma_store_2d(pass == 0 ? &tmAux : &tmC, stg, n_slab, row0);
+              tma_store_commit();
+            }
+          }
+        }
+      } else
 #pragma unroll 1
       for (int c = chalf * (BN / 2); c < (chalf + 1) * (BN / 2); c += 32) {
         const int n0 = nt * BN + c;
@@ -274,6 +362,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
+    if (lane == 0) tma_store_wait_all<0>();
   }
   tc_fence_before();
   __syncthreads();
@@ -296,7 +385,8 @@ static int num_sms() {
 
 template <int BN, bool A_MN, bool B_MN>
 static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmA2,
-                       const CUtensorMap& tmB2, const GemmParams& p, cudaStream_t stream) {
+                       const CUtensorMap& tmB2, const CUtensorMap& tmC, const CUtensorMap& tmAux,
+                       const GemmParams& p, cudaStream_t stream) {
   using Cfg = GemmCfg<BN>;
   static bool attr_set = false;
   auto kern = gemm_kernel<BN, A_MN, B_MN>;
@@ -307,7 +397,7 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
   }
   int tiles = p.m_tiles * p.n_tiles * p.splits;
   int grid = tiles < num_sms() ? tiles : num_sms();
-  kern<<<grid, 384, Cfg::SMEM, stream>>>(tmA, tmB, tmA2, tmB2, p);
+  kern<<<grid, 384, Cfg::SMEM, stream>>>(tmA, tmB, tmA2, tmB2, tmC, tmAux, p);
   return launch_status("gemm_bf16");
 }
 
@@ -393,14 +483,23 @@ extern "C" int b200_gemm_bf16(const void* A, int64_t lda, int a_kmajor_rows_are_
     tmA2 = tmA; tmB2 = tmB;
   }
   if (K == 0) { tmA = tmA2; tmB = tmB2; }
+  // bf16 outputs of the wide tiles leave through swizzled smem slabs + TMA stores (coalesced 128-byte
+  // rows instead of 16-byte-per-lane row-strided stores)
+  CUtensorMap tmC = tmA, tmAux = tmA;
+  p.tma_store = (!out_is_f32 && bn >= 128) ? 1 : 0;
+  if (p.tma_store) {
+    if ((rc = make_tmap_2d_bf16(&tmC, C, M, N, ldc, 32, 64))) return arg_error("gemm_bf16: cuTensorMapEncodeTiled failed (C)", rc);
+    if (epilogue == EPI_GELU && aux && (rc = make_tmap_2d_bf16(&tmAux, aux, M, N, ldaux, 32, 64)))
+      return arg_error("gemm_bf16: cuTensorMapEncodeTiled failed (aux)", rc);
+  }
 
   cudaStream_t st = (cudaStream_t)stream;
 #define DISPATCH(BN_)                                                                     \
   if (bn == BN_) {                                                                        \
-    if (!a_mn && !b_mn) return launch_gemm<BN_, false, false>(tmA, tmB, tmA2, tmB2, p, st); \
-    if (!a_mn && b_mn) return launch_gemm<BN_, false, true>(tmA, tmB, tmA2, tmB2, p, st);   \
-    if (a_mn && !b_mn) return launch_gemm<BN_, true, false>(tmA, tmB, tmA2, tmB2, p, st);   \
-    return launch_gemm<BN_, true, true>(tmA, tmB, tmA2, tmB2, p, st);                       \
+    if (!a_mn && !b_mn) return launch_gemm<BN_, false, false>(tmA, tmB, tmA2, tmB2, tmC, tmAux, p, st); \
+    if (!a_mn && b_mn) return launch_gemm<BN_, false, true>(tmA, tmB, tmA2, tmB2, tmC, tmAux, p, st);   \
+    if (a_mn && !b_mn) return launch_gemm<BN_, true, false>(tmA, tmB, tmA2, tmB2, tmC, tmAux, p, st);   \
+    return launch_gemm<BN_, true, true>(tmA, tmB, tmA2, tmB2, tmC, tmAux, p, st);                       \
   }
   DISPATCH(256)
   DISPATCH(128)
