@@ -9,13 +9,13 @@
 //   S^T  = K Q^T              (128 x 128 x 64, both operands K-major)
 //   dP^T = V dO^T             (128 x 128 x 64)
 //   P^T  = exp2(S^T*c + bias - lse) ; dS^T = P^T * (dP^T - delta) * scale    -> shared memory, bf16
-//   dV  += P^T  dO            (A = P^T  K-major from smem, B = dO tile read MN-major)
+//   dV  += P^T  dO            (A = P^T  packed bf16 in TMEM,  B = dO tile read MN-major)
 //   dK  += dS^T Q             (A = dS^T K-major,            B = Q  tile read MN-major)
 //   dQ   = dS   K             (A = the same dS^T bytes read MN-major, B = K tile read MN-major)
 // dV/dK accumulate in TMEM over the whole loop; dQ is a per-(q tile, k tile) partial that is
 // reduced across key-tile CTAs with TMA reduce-add (cp.reduce.async.bulk.tensor) into a caller-zeroed
 // fp32 buffer (per-lane red.global.add measured ~10 k cycles per tile: the atomics were the bottleneck).
-// TMEM: S^T 128 | dP^T 128 | dV 64 | dK 64 | dQ 64 = 448 of 512 columns.
+// TMEM: S^T 128 | dP^T 128 | dV 64 | dK 64 | dQ 64 | P^T (bf16x2) 64 = 512 columns.
 //
 // Pipeline: P^T/dS^T are double-buffered in shared memory, so while the 8 compute warps turn
 // S^T/dP^T(i+1) into P^T/dS^T(i+1) the tensor pipe runs dV/dK/dQ(i); dQ(i-1) is drained to global
@@ -43,8 +43,8 @@ struct FaBwdParams {
   float scale, scale_log2;
 };
 
-constexpr int FA_BWD_SMEM = 16384 * 2 /*K,V*/ + 2 * 32768 /*Q,dO x2*/ + 4 * 32768 /*P^T,dS^T x2*/ +
-                            2 * 2 * 512 /*lse, delta x2*/ + 128;  // dQ staging aliases the consumed P^T buffer
+constexpr int FA_BWD_SMEM = 16384 * 2 /*K,V*/ + 2 * 32768 /*Q,dO x2*/ + 2 * 32768 /*dS^T x2*/ +
+                            32768 /*dQ staging*/ + 2 * 2 * 512 /*lse, delta x2*/ + 128;
 constexpr float kLog2eB = 1.4426950408889634f;
 
 __device__ __forceinline__ float ex2_approx_b(float x) {
@@ -68,10 +68,10 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t sbase = smem_u32(smem_raw);
   const uint32_t sK = sbase, sV = sbase + 16384, sQdO = sbase + 32768;  // stage s: Q at +s*32768, dO at +16384
-  // buffer u (= tile & 1): P^T at sPD + u*65536, dS^T at +32768.  Once dV(i) has been accumulated the
-  // P^T buffer of tile i is dead and doubles as the fp32 dQ(i) staging tile for the TMA reduce-add.
-  const uint32_t sPD = sQdO + 65536;
-  const uint32_t sStat = sPD + 131072;  // [2 stages][lse 128 | delta 128] fp32
+  // dS^T is double-buffered in shared memory (buffer = tile & 1); P^T lives in TMEM (A operand of dV).
+  const uint32_t sDS = sQdO + 65536;
+  const uint32_t sStage = sDS + 65536;   // fp32 dQ staging tile for the TMA reduce-add
+  const uint32_t sStat = sStage + 32768;  // [2 stages][lse 128 | delta 128] fp32
   const uint32_t bar = sStat + 2048;
   const uint32_t kv_full = bar, qd_full0 = bar + 8, qd_empty0 = bar + 24, s_full = bar + 40,
                  pds_full = bar + 48, mma2_done = bar + 56, dq_free = bar + 64, tmem_slot = bar + 72;
@@ -111,7 +111,7 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
   const uint32_t tSt = tmem_base, tdPt = tmem_base + 128, tdV = tmem_base + 256,
-                 tdK = tmem_base + 320, tdQ = tmem_base + 384;
+                 tdK = tmem_base + 320, tdQ = tmem_base + 384, tPt = tmem_base + 448;
 
   if (warp == 0 && lane == 0) {
     mbar_expect_tx(kv_full, 32768);
@@ -150,14 +150,16 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
     for (int i = 0; i < T; ++i) {
       const int s = i & 1;
       const uint32_t sQ = sQdO + s * 32768, sdO = sQ + 16384;
-      const uint32_t sPt = sPD + s * 65536, sdSt = sPt + 32768;
-      mbar_wait(pds_full, i & 1);  // P^T/dS^T(i) are in shared memory; S^T/dP^T in TMEM are consumed
+      const uint32_t sdSt = sDS + s * 32768;
+      mbar_wait(pds_full, i & 1);  // P^T(i) is in TMEM, dS^T(i) in shared memory; S^T/dP^T are consumed
       tc_fence_after();
-      if (i + 1 < T) issue_scores(i + 1);  // compute warps start tile i+1 while dV/dK/dQ(i) run below
 #pragma unroll
-      for (int k = 0; k < 8; ++k)  // dV += P^T dO   (K = queries)
-        umma_ss(tdV, make_smem_desc(sPt + (k >> 2) * 16384 + (k & 3) * 32, 16, 1024),
-                make_smem_desc(sdO + k * 2048, 8192, 1024), idesc_kv, (i > 0 || k > 0) ? 1u : 0u);
+      for (int k = 0; k < 8; ++k)  // dV += P^T dO   (A = packed bf16 P^T straight from TMEM, K = queries)
+        umma_ts(tdV, tPt + k * 8, make_smem_desc(sdO + k * 2048, 8192, 1024), idesc_kv,
+                (i > 0 || k > 0) ? 1u : 0u);
+      // S^T/dP^T(i+1) go behind dV(i): once they complete, P^T(i) has been consumed and the compute
+      // warps may overwrite it while dK/dQ(i) run below
+      if (i + 1 < T) issue_scores(i + 1);
 #pragma unroll
       for (int k = 0; k < 8; ++k)  // dK += dS^T Q
         umma_ss(tdK, make_smem_desc(sdSt + (k >> 2) * 16384 + (k & 3) * 32, 16, 1024),
@@ -205,7 +207,9 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
       tmem_ld_wait();
       tc_fence_before();
       mbar_arrive(dq_free);  // the dQ columns may be overwritten by dQ(j+1)
-      const uint32_t stage = sPD + (j & 1) * 65536;
+      const uint32_t stage = sStage;
+      if (ctid == 0) tma_store_wait_read<0>();  // the previous reduce-add has finished reading the staging tile
+      named_bar_sync(2, 512);
 #pragma unroll
       for (int g = 0; g < 4; ++g)
         asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stage + (part >> 1) * 16384 +
@@ -224,15 +228,13 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
       const int s = i & 1;
       const int q0 = i * 128;
       float* st = stat + s * 256;
-      const uint32_t sPt = sPD + s * 65536, sdSt = sPt + 32768;
+      const uint32_t sdSt = sDS + s * 32768;
       if (stat_thread) {
         st[ctid] = nxt;  // [0,128): lse * log2e ; [128,256): delta * scale
         const int qn = q0 + 128 + sq;
         nxt = qn < p.Nq ? stat_g[qn] * stat_mul : stat_pad;
       }
-      // P^T/dS^T buffer s was last read by dV/dK/dQ(i-2) (mma2_done(i-2) was awaited when dQ(i-2) was
-      // drained) and by the TMA reduce of dQ(i-2) staged in it:
-      if (ctid == 0) tma_store_wait_read<0>();
+      // dS^T buffer s was last read by dK/dQ(i-2); mma2_done(i-2) was awaited when dQ(i-2) was drained
       named_bar_sync(1, 512);
       mbar_wait(s_full, i & 1);
       tc_fence_after();
@@ -245,6 +247,7 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
         const uint32_t off0 = (c >> 1) * 16384;
         const float4* lse4 = reinterpret_cast<const float4*>(st + c * 32);
         const float4* del4 = reinterpret_cast<const float4*>(st + 128 + c * 32);
+        uint32_t pk[16];  // this warp's 32 query columns of P^T as packed bf16x2 -> 16 TMEM columns
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
           float pv[8], ds[8];
@@ -263,17 +266,19 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
             }
           }
           const uint32_t o = off0 + sw128_off(row, (c & 1) * 4 + g);
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sPt + o),
-                       "r"(pack_bf16x2(pv[0], pv[1])), "r"(pack_bf16x2(pv[2], pv[3])),
-                       "r"(pack_bf16x2(pv[4], pv[5])), "r"(pack_bf16x2(pv[6], pv[7]))
-                       : "memory");
+          pk[g * 4 + 0] = pack_bf16x2(pv[0], pv[1]);
+          pk[g * 4 + 1] = pack_bf16x2(pv[2], pv[3]);
+          pk[g * 4 + 2] = pack_bf16x2(pv[4], pv[5]);
+          pk[g * 4 + 3] = pack_bf16x2(pv[6], pv[7]);
           asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sdSt + o),
                        "r"(pack_bf16x2(ds[0], ds[1])), "r"(pack_bf16x2(ds[2], ds[3])),
                        "r"(pack_bf16x2(ds[4], ds[5])), "r"(pack_bf16x2(ds[6], ds[7]))
                        : "memory");
         }
+        tmem_st16(tPt + lane_bits + c * 16, pk);
       }
       fence_proxy_async_smem();
+      tmem_st_wait();
       tc_fence_before();
       mbar_arrive(pds_full);
       if (i > 0) drain_dq(i - 1);  // overlaps with S^T/dP^T(i+1) and dV/dK/dQ(i) on the tensor pipe

@@ -43,12 +43,17 @@ class KernelTimer:
     """CUDA-event timing of kernel families on the launching stream (bench.py roofline numbers).
     `families=None` records everything; otherwise only the named families."""
 
-    def __init__(self, families=None):
+    def __init__(self, families=None, every=1):
         self.families = set(families) if families else None
+        self.every = max(1, every)  # time one launch in `every` (event records cost ~2 us each)
+        self._seen = 0
         self.records = []  # (family, work, unit, start_event, end_event)
 
     def want(self, family):
-        return self.families is None or family in self.families
+        if self.families is not None and family not in self.families:
+            return False
+        self._seen += 1
+        return self._seen % self.every == 0
 
     def summary(self):
         torch.cuda.synchronize()
