@@ -42,21 +42,10 @@ class GradBucketer:
         self._bucket_of = {id(p): b for b in self.buckets for p in b["params"]}
         self._hooks = [p.register_post_accumulate_grad_hook(self._on_grad) for b in self.buckets for p in b["params"]]
 
-    def _sync_side_streams(self, b):
-        """Gradients of a bucket may have been produced on b200_ltx's side stream (cross-attention K/V
-        projections); the collective is ordered after the *current* stream only, so join them first."""
-        if b["device"].type != "cuda":
-            return
-        from . import modules
-        cur = torch.cuda.current_stream(b["device"])
-        for s in modules.all_side_streams():
-            cur.wait_stream(s)
-
     def _on_grad(self, p):
         b = self._bucket_of[id(p)]
         b["pending"] -= 1
         if b["pending"] == 0 and self.world > 1:
-            self._sync_side_streams(b)
             self._handles.append(dist.all_reduce(b["flat"], op=dist.ReduceOp.SUM, group=self.group, async_op=True))
 
     def zero_grad(self):

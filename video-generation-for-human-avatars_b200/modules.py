@@ -85,52 +85,6 @@ def _cached_wqkv(attn):
 
 
 # ---------------------------------------------------------------------------------------------
-# cross-attention K/V off the critical path
-# ---------------------------------------------------------------------------------------------
-# The attn2 key/value projections of all blocks depend only on the projected caption tokens, are tiny
-# (256 rows) and therefore latency-bound.  They are issued up front on a side stream so that they (and,
-# because autograd replays a node on the stream of its forward, their backward and LoRA wgrads) overlap
-# the large kernels of the main stream instead of serialising ~10 small launches per block.
-_side_streams = {}
-_cross_kv = {}  # id(attn2 module) -> (k_pre, v, ready_event), valid for the current forward only
-
-
-def side_stream(device) -> "torch.cuda.Stream":
-    key = torch.device(device).index if torch.device(device).index is not None else torch.cuda.current_device()
-    if key not in _side_streams:
-        _side_streams[key] = torch.cuda.Stream(device=key)
-    return _side_streams[key]
-
-
-def all_side_streams():
-    return list(_side_streams.values())
-
-
-def _precompute_cross_kv(model, ctx):
-    _cross_kv.clear()
-    if ctx is None or getattr(model, "gradient_checkpointing", False):
-        return
-    B, L, Dc = ctx.shape
-    main = torch.cuda.current_stream()
-    side = side_stream(ctx.device)
-    side.wait_stream(main)
-    src2d = ctx.reshape(B * L, Dc)
-    with torch.cuda.stream(side):
-        for blk in model.transformer_blocks:
-            attn = blk.attn2
-            if attn is None or getattr(attn, "processor", None).__class__ is not B200AttnProcessor:
-                continue
-            k_pre = apply_linear(attn.to_k, src2d)
-            v = apply_linear(attn.to_v, src2d)
-            ev = torch.cuda.Event()
-            ev.record(side)
-            k_pre.record_stream(main)
-            v.record_stream(main)
-            _cross_kv[id(attn)] = (k_pre, v, ev)
-    src2d.record_stream(side)
-
-
-# ---------------------------------------------------------------------------------------------
 # functional forward
 # ---------------------------------------------------------------------------------------------
 def _key_bias(mask_bias: Optional[torch.Tensor], B: int, Nk: int) -> Optional[torch.Tensor]:
@@ -181,13 +135,8 @@ def attention_forward(attn, hidden_states, freqs_cis=None, encoder_hidden_states
         return y.view(B, Nq, -1)
 
     q_pre = apply_linear(attn.to_q, x2d)
-    pre = _cross_kv.get(id(attn)) if not is_self else None
-    if pre is not None and pre[0].shape[0] == src2d.shape[0]:
-        k_pre, v, ev = pre
-        torch.cuda.current_stream().wait_event(ev)
-    else:
-        k_pre = apply_linear(attn.to_k, src2d)
-        v = apply_linear(attn.to_v, src2d)
+    k_pre = apply_linear(attn.to_k, src2d)
+    v = apply_linear(attn.to_v, src2d)
     o = ops.AttnCoreFn.apply(q_pre, k_pre, v, wqn, wkn, cos, sin, kb, B, H, Nq, Nk, scale)
     if skip_layer_mask is not None and strat in (SkipLayerStrategy.AttentionSkip, SkipLayerStrategy.AttentionValues):
         m = skip_layer_mask.reshape(B, 1, 1).to(o.dtype)
@@ -337,7 +286,6 @@ def transformer_forward(model, hidden_states, indices_grid, ref_image_hidden_sta
         e2d = encoder_hidden_states.reshape(B * L, encoder_hidden_states.shape[-1])
         ctx = ops.FeedForwardFn.apply(e2d, W1, b1, W2, b2, None, 0, None).view(B, L, D)
 
-    _precompute_cross_kv(model, ctx)
     h = x.view(B, N, D)
     for i, block in enumerate(model.transformer_blocks):
         slm = skip_layer_mask[i] if skip_layer_mask is not None else None
@@ -351,7 +299,6 @@ def transformer_forward(model, hidden_states, indices_grid, ref_image_hidden_sta
                       cross_attention_kwargs=cross_attention_kwargs, class_labels=class_labels,
                       skip_layer_mask=slm, skip_layer_strategy=skip_layer_strategy)
 
-    _cross_kv.clear()
     T = emb.shape[1]
     ss = (model.scale_shift_table[None, None] + emb[:, :, None]).reshape(B * T, 2 * D)
     hn = ops.NormModFn.apply(h.reshape(B * N, D), ss[:, D:], ss[:, :D], N // T, 1e-6, True)
