@@ -31,6 +31,8 @@ WORKLOADS = {
     "cfg1": (1, 4, 8, 8, "LTXV-2B LoRA train step bs1 25x256x256 (256 latent tokens)"),
     "cfg2": (1, 16, 16, 24, "LTXV-2B bf16 LoRA train step bs1 121x512x768 (6144 latent tokens)"),
     "cfg3": (4, 13, 16, 16, "LTXV-2B bf16 LoRA train step bs4/GPU 97x512x512 (4x3328 latent tokens)"),
+    # long clip: ONE sample sequence-sharded over all ranks (ring attn1); strong scaling, not the default
+    "cfg5": (1, 33, 16, 24, "LTXV-2B bf16 LoRA train step bs1 257x512x768 (12672 latent tokens), sequence-sharded ring attn1"),
 }
 METRIC = "LTXV-2B train-step latent tok/s"
 UNIT = "latent tokens/s"
@@ -167,6 +169,9 @@ def run_b200(args):
             p.data.copy_(torch.randn(p.shape, generator=g) * 0.02)  # non-zero B: dA != 0
     model.train()
     named = [(n, p) for n, p in model.named_parameters() if p.requires_grad]
+    seq_parallel = args.workload == "cfg5"
+    if seq_parallel and world > 1:
+        api.enable_sequence_parallel(model)  # gradients are per-shard partial means: the bucketer averages them
     bucketer = GradBucketer(named) if world > 1 else None
     opt = torch.optim.AdamW([p for _, p in named], lr=1e-4, fused=True)
     sched, patch = api.RectifiedFlowScheduler(), api.SymmetricPatchifier(1)
@@ -176,7 +181,7 @@ def run_b200(args):
         rf_quantile_min, rf_quantile_max = 0.005, 0.999
         transformer_loss_weight = 1.0
 
-    gd = torch.Generator(device="cpu").manual_seed(1234 + rank)
+    gd = torch.Generator(device="cpu").manual_seed(1234 + (0 if seq_parallel else rank))  # SP ranks share the clip
     host = {"latents": torch.randn(B, 128, F, H, W, generator=gd).bfloat16().pin_memory(),
             "pose_latents": torch.randn(B, 128, F, H, W, generator=gd).bfloat16().pin_memory(),
             "ref_image_latents": torch.randn(B, 128, 1, H, W, generator=gd).bfloat16().pin_memory()}
@@ -256,7 +261,7 @@ def run_b200(args):
         e2e_step()
     ms_e2e = timed(e2e_step, args.steps)
 
-    tokens_step = B * N * world
+    tokens_step = B * N * (1 if seq_parallel else world)
     value = tokens_step / (ms_total / args.steps / 1e3)
     e2e_value = tokens_step / (ms_e2e / args.steps / 1e3)
     peaks = load_peaks()
@@ -269,11 +274,13 @@ def run_b200(args):
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps, "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-                "config": {"workload": desc, "tokens_per_gpu_step": B * N, "caption_tokens": N_CTX,
+                "scaling": "strong" if seq_parallel else "weak", "vs_baseline": None, "dtype": "bf16",
+                "data": "synthetic",
+                "config": {"workload": desc, "tokens_per_gpu_step": B * N // (world if seq_parallel else 1),
+                           "caption_tokens": N_CTX,
                            "valid_caption_tokens": VALID_CTX, "lora_rank": LORA_RANK, "layers": cfg["num_layers"],
                            "optimizer": "AdamW(fused) on 27.3M trainable params, inside the timed step",
-                           "parallelism": f"dp{world}",
+                           "parallelism": f"sp{world} (ring attn1)" if seq_parallel else f"dp{world}",
                            "l2": "not flushed: every step streams 3.85 GB of weights plus >10 GB of activations, far larger than the 126 MB L2"},
                 "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
                         "h2d_bytes_per_step": h2d_bytes * world, "d2h_bytes_per_step": 4 * world},

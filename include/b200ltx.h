@@ -63,6 +63,14 @@ int b200_fa_fwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const vo
                 void* o, int64_t ldo, float* lse, const float* key_bias, int B, int H, int Nq, int Nk,
                 int head_dim, float scale, void* stream);
 
+/* Online-softmax merge of a partial attention result (o_i bf16, lse_i) over a disjoint key shard into
+ * fp32 accumulators (o_acc, lse_acc); first != 0 initialises them; out (bf16, may be NULL) receives the
+ * merged rows.  One call per hop of the sequence-sharded ring attn1 (no reference counterpart: the
+ * reference runs one F.scaled_dot_product_attention over all tokens, attention.py:1057). */
+int b200_attn_merge(float* o_acc, int64_t ldacc, float* lse_acc, const void* o_i, int64_t ldo,
+                    const float* lse_i, void* out, int64_t ldout, int B, int H, int N, int first,
+                    void* stream);
+
 /* delta[b,h,q] = sum_d o * do  (backward pre-pass). */
 int b200_attn_delta(const void* o, int64_t ldo, const void* dout, int64_t lddo, float* delta, int B,
                     int H, int Nq, void* stream);
@@ -113,9 +121,11 @@ int b200_rf_loss(const void* out, const void* target, void* dout, float* loss, i
                  float grad_scale, void* workspace, int64_t workspace_bytes, void* stream);
 
 /* In-place conditioning lerp on tokens [B,N,C]: frame 0 <- lerp(tok, ref, w_ref), frames >= 1 <-
- * lerp(tok, pose, w_pose); ref [B,C,1,HW], pose [B,C,F,HW].  Replaces transformer3d.py:447-466. */
+ * lerp(tok, pose, w_pose); ref [B,C,1,HW], pose [B,C,F,HW] with F*HW = N_total.  `tokens` may be a
+ * contiguous shard [token_offset, token_offset + N) of the clip (sequence-sharded attn1).
+ * Replaces transformer3d.py:447-466. */
 int b200_lerp_condition(void* tokens, const void* ref, const void* pose, int B, int N, int C, int HW,
-                        float w_ref, float w_pose, void* stream);
+                        float w_ref, float w_pose, int token_offset, int N_total, void* stream);
 
 /* out[m,:] = x[m,:] * g[m / rows_per_mod,:]  (AdaLN gate applied to an incoming gradient). */
 int b200_rowscale(const void* x, int64_t ldx, const void* g, int64_t gstride, void* out, int64_t ldo,

@@ -296,6 +296,46 @@ def check_attn_core_fn():
     torch.cuda.synchronize()
 
 
+def check_key_sharded_merge():
+    """The ring-attention building blocks on ONE device: attend to two disjoint key shards, fold the
+    partials with attn_merge, accumulate dq over the shards with fa_bwd(dq_accum=...) -- must equal
+    the single-pass kernels' reference (plain torch fp32 over all keys)."""
+    from b200_ltx import ops
+    for (B, H, Nq, n_sh, shards) in [(1, 2, 200, 136, 2), (2, 4, 96, 96, 3), (1, 32, 384, 264, 2)]:
+        D = H * 64
+        Nk = n_sh * shards
+        q, do = _randn(B * Nq, D, seed=1), _randn(B * Nq, D, seed=4)
+        k, v = _randn(B, Nk, D, seed=2), _randn(B, Nk, D, seed=3)
+        ks = [k[:, i * n_sh:(i + 1) * n_sh].reshape(B * n_sh, D).contiguous() for i in range(shards)]
+        vs = [v[:, i * n_sh:(i + 1) * n_sh].reshape(B * n_sh, D).contiguous() for i in range(shards)]
+        o_acc = torch.empty(B * Nq, D, device="cuda")
+        lse_acc = torch.empty(B, H, Nq, device="cuda")
+        out = torch.empty(B * Nq, D, device="cuda", dtype=BF16)
+        for i in range(shards):
+            o_i, lse_i = ops.fa_fwd(q, ks[i], vs[i], B, H, Nq, n_sh, None, 0.125)
+            ops.attn_merge(o_acc, lse_acc, o_i, lse_i, B, H, Nq, i == 0, out if i == shards - 1 else None)
+        qf, kf, vf = q.float().requires_grad_(True), k.reshape(B * Nk, D).float().requires_grad_(True), \
+            v.reshape(B * Nk, D).float().requires_grad_(True)
+        oref, lref = _attn_ref(qf, kf, vf, B, H, Nq, Nk, None, 0.125)
+        oref.backward(do.float())
+        tag = f"B={B} H={H} Nq={Nq} shards={shards}x{n_sh}"
+        _assert_close("merged o " + tag, out, oref, 8e-3)
+        _assert_close("merged o (fp32 acc) " + tag, o_acc, oref, 8e-3)
+        _assert_close("merged lse " + tag, lse_acc, lref, 1e-3)
+        delta = ops.attn_delta(out, do, B, H, Nq)
+        dq = torch.zeros(B * Nq, D, device="cuda")
+        dks, dvs = [], []
+        for i in range(shards):
+            dk, dv = torch.empty_like(ks[i]), torch.empty_like(vs[i])
+            ops.fa_bwd(q, ks[i], vs[i], out, do, lse_acc, B, H, Nq, n_sh, dk, dv, None, 0.125, delta=delta, dq_accum=dq)
+            dks.append(dk.view(B, n_sh, D))
+            dvs.append(dv.view(B, n_sh, D))
+        _assert_close("sharded dq " + tag, dq, qf.grad, 1.2e-2)
+        _assert_close("sharded dk " + tag, torch.cat(dks, 1).reshape(B * Nk, D), kf.grad, 1.2e-2)
+        _assert_close("sharded dv " + tag, torch.cat(dvs, 1).reshape(B * Nk, D), vf.grad, 1.2e-2)
+    torch.cuda.synchronize()
+
+
 def check_rf_and_misc():
     from b200_ltx import ops
     B, N, C = 3, 96, 128
@@ -342,5 +382,6 @@ GROUPS = {
     "attention_fwd": check_attention_fwd,
     "attention_bwd": check_attention_bwd,
     "attn_core_fn": check_attn_core_fn,
+    "key_sharded_merge": check_key_sharded_merge,
     "rf_and_misc": check_rf_and_misc,
 }

@@ -60,9 +60,9 @@ def oracle_loss_grads(P, cfg, batch, t, dtype, device):
     return loss.detach(), out.detach(), grads
 
 
-def b200_loss_grads(model, batch, t):
+def b200_loss_grads(model, batch, t, device="cuda"):
     from b200_ltx import api, train
-    dev = "cuda"
+    dev = device
 
     class Cfg:
         transformer_loss_weight = 1.0

@@ -411,7 +411,7 @@ __global__ void __launch_bounds__(256) lerp_condition_kernel(bf16* __restrict__ 
                                                              const bf16* __restrict__ ref,
                                                              const bf16* __restrict__ pose, int N,
                                                              int C, int HW, float w_ref,
-                                                             float w_pose) {
+                                                             float w_pose, int n_off, int N_total) {
   __shared__ float tile[32][33];
   int b = blockIdx.z;
   int n0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
@@ -420,8 +420,9 @@ __global__ void __launch_bounds__(256) lerp_condition_kernel(bf16* __restrict__ 
     int c = c0 + i, n = n0 + tx;
     float v = 0.f;
     if (c < C && n < N) {
-      v = n < HW ? __bfloat162float(ref[((int64_t)b * C + c) * HW + n])
-                 : __bfloat162float(pose[((int64_t)b * C + c) * N + n]);
+      const int ng = n + n_off;  // global token index (tokens may be a contiguous shard of the clip)
+      v = ng < HW ? __bfloat162float(ref[((int64_t)b * C + c) * HW + ng])
+                  : __bfloat162float(pose[((int64_t)b * C + c) * N_total + ng]);
     }
     tile[i][tx] = v;
   }
@@ -432,7 +433,7 @@ __global__ void __launch_bounds__(256) lerp_condition_kernel(bf16* __restrict__ 
       int64_t idx = ((int64_t)b * N + n) * C + c;
       float a = __bfloat162float(tok[idx]);
       float bb = tile[tx][i];
-      float w = n < HW ? w_ref : w_pose;
+      float w = (n + n_off) < HW ? w_ref : w_pose;
       float r = w < 0.5f ? a + w * (bb - a) : bb - (bb - a) * (1.f - w);
       tok[idx] = __float2bfloat16(r);
     }
@@ -497,6 +498,45 @@ __global__ void __launch_bounds__(256) attn_delta_kernel(const bf16* __restrict_
     int64_t b = bq / Nq, q = bq - b * Nq;
     delta[(b * H + h) * Nq + q] = acc;
   }
+}
+
+// Online-softmax merge of two normalised partial attention results over disjoint key sets:
+//   lse' = log(exp(lse_a) + exp(lse_i)) ; o' = o_a * exp(lse_a - lse') + o_i * exp(lse_i - lse')
+// o_acc fp32 [B*N, H*64] and lse_acc fp32 [B,H,N] are updated in place; when out != null the merged
+// result is also written as bf16 (last hop).  8 lanes x 8 channels per (token, head), like attn_delta.
+__global__ void __launch_bounds__(256) attn_merge_kernel(float* __restrict__ o_acc, int64_t ldacc,
+                                                         float* __restrict__ lse_acc,
+                                                         const bf16* __restrict__ o_i, int64_t ldo,
+                                                         const float* __restrict__ lse_i,
+                                                         bf16* __restrict__ out, int64_t ldout, int B,
+                                                         int H, int N, int first) {
+  int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int64_t item = gid >> 3;
+  int sub = gid & 7;
+  const bool ok = item < (int64_t)B * N * H;
+  int64_t li = 0;
+  float ln = 0.f;
+  if (ok) {
+    int h = (int)(item % H);
+    int64_t bq = item / H;
+    int64_t b = bq / N, q = bq - b * N;
+    li = (b * H + h) * N + q;
+    float la = first ? -INFINITY : lse_acc[li];
+    float lb = lse_i[li];
+    float lm = fmaxf(la, lb);
+    ln = lm + logf(expf(la - lm) + expf(lb - lm));
+    float wa = first ? 0.f : expf(la - ln), wb = expf(lb - ln);
+    float* acc = o_acc + bq * ldacc + h * 64 + sub * 8;
+    Row8 vi = ld_bf16x8(o_i + bq * ldo + h * 64 + sub * 8), r, va;
+    if (!first) va = ld_f32x8(acc);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) r.v[j] = (first ? 0.f : va.v[j] * wa) + vi.v[j] * wb;
+    *reinterpret_cast<float4*>(acc) = make_float4(r.v[0], r.v[1], r.v[2], r.v[3]);
+    *reinterpret_cast<float4*>(acc + 4) = make_float4(r.v[4], r.v[5], r.v[6], r.v[7]);
+    if (out) st_bf16x8(out + bq * ldout + h * 64 + sub * 8, r);
+  }
+  __syncwarp();  // all 8 lanes of an item have read lse_acc before lane 0 overwrites it
+  if (ok && sub == 0) lse_acc[li] = ln;
 }
 
 }  // namespace b200
@@ -657,15 +697,17 @@ extern "C" int b200_rf_loss(const void* out, const void* target, void* dout, flo
 }
 
 extern "C" int b200_lerp_condition(void* tokens, const void* ref, const void* pose, int B, int N,
-                                   int C, int HW, float w_ref, float w_pose, void* stream) {
+                                   int C, int HW, float w_ref, float w_pose, int token_offset,
+                                   int N_total, void* stream) {
   CHECK_ARG(tokens && ref && pose && B >= 0 && N >= 0 && C > 0 && HW > 0,
             "lerp_condition: null pointer or bad shape");
-  CHECK_ARG(N % HW == 0, "lerp_condition: N must be frames x HW");
+  CHECK_ARG(N_total % HW == 0 && token_offset >= 0 && token_offset + N <= N_total,
+            "lerp_condition: N_total must be frames x HW and the shard must lie inside it");
   if (B == 0 || N == 0) return 0;
   dim3 grid((N + 31) / 32, (C + 31) / 32, B);
   lerp_condition_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((bf16*)tokens, (const bf16*)ref,
                                                                 (const bf16*)pose, N, C, HW, w_ref,
-                                                                w_pose);
+                                                                w_pose, token_offset, N_total);
   return launch_status("lerp_condition");
 }
 
@@ -688,6 +730,19 @@ extern "C" int b200_colsum(const void* x, int64_t ldx, float* out, int64_t rows,
   CHECK_ARG(x && out && rows >= 0 && N > 0, "colsum: bad arguments");
   colsum_kernel<<<(N + 63) / 64, 256, 0, (cudaStream_t)stream>>>((const bf16*)x, ldx, out, rows, N);
   return launch_status("colsum");
+}
+
+extern "C" int b200_attn_merge(float* o_acc, int64_t ldacc, float* lse_acc, const void* o_i, int64_t ldo,
+                               const float* lse_i, void* out, int64_t ldout, int B, int H, int N, int first,
+                               void* stream) {
+  CHECK_ARG(o_acc && lse_acc && o_i && lse_i && B >= 0 && H > 0 && N >= 0, "attn_merge: bad arguments");
+  CHECK_ARG(ldacc % 4 == 0 && ldo % 8 == 0 && ldout % 8 == 0 && aligned16(o_acc) && aligned16(o_i) && aligned16(out),
+            "attn_merge: 16-byte alignment required");
+  int64_t threads = (int64_t)B * N * H * 8;
+  if (threads == 0) return 0;
+  attn_merge_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      o_acc, ldacc, lse_acc, (const bf16*)o_i, ldo, lse_i, (bf16*)out, ldout, B, H, N, first);
+  return launch_status("attn_merge");
 }
 
 extern "C" int b200_attn_delta(const void* o, int64_t ldo, const void* dout, int64_t lddo,

@@ -20,6 +20,7 @@ PROTOTYPES = {
     "b200_device_check": (I, []),
     "b200_gemm_bf16": (I, [P, L, I, P, L, I, P, L, P, L, I, P, L, I, I, I, I, I, P, P, L, L, P, L, P, L, I, I, P]),
     "b200_fa_fwd": (I, [P, L, P, L, P, L, P, L, P, P, I, I, I, I, I, F, P]),
+    "b200_attn_merge": (I, [P, L, P, P, L, P, P, L, I, I, I, I, P]),
     "b200_attn_delta": (I, [P, L, P, L, P, I, I, I, P]),
     "b200_fa_bwd": (I, [P, L, P, L, P, L, P, L, P, P, P, P, L, P, L, P, L, I, I, I, I, I, F, P]),
     "b200_norm_mod_fwd": (I, [P, L, P, L, P, P, L, L, I, L, F, I, P]),
@@ -29,7 +30,7 @@ PROTOTYPES = {
     "b200_rf_noise": (I, [P, P, P, P, P, L, L, P]),
     "b200_rf_loss_workspace_bytes": (L, []),
     "b200_rf_loss": (I, [P, P, P, P, L, F, P, L, P]),
-    "b200_lerp_condition": (I, [P, P, P, I, I, I, I, F, F, P]),
+    "b200_lerp_condition": (I, [P, P, P, I, I, I, I, F, F, I, I, P]),
     "b200_rowscale": (I, [P, L, P, L, P, L, L, I, L, P]),
     "b200_colsum": (I, [P, L, P, L, I, P]),
 }

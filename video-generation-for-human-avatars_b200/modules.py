@@ -124,6 +124,7 @@ def attention_forward(attn, hidden_states, freqs_cis=None, encoder_hidden_states
     wqn, wkn = attn.q_norm.weight, attn.k_norm.weight
     scale = float(attn.scale)
 
+    sp = attn.__dict__.get("_b200_sp") if is_self else None
     fast = (is_self and skip_layer_mask is None and all(_frozen_plain(m) for m in (attn.to_q, attn.to_k, attn.to_v))
             and linear_parts(attn.to_out[0])[2] is None and not linear_parts(attn.to_out[0])[0].requires_grad
             and not wqn.requires_grad and not wkn.requires_grad)
@@ -131,8 +132,10 @@ def attention_forward(attn, hidden_states, freqs_cis=None, encoder_hidden_states
         Wo, bo, _ = linear_parts(attn.to_out[0])
         Wqkv, bqkv = _cached_wqkv(attn)
         y = ops.SelfAttnFn.apply(x2d, Wqkv, bqkv, wqn, wkn, cos, sin, Wo, bo, gate, rows_per_gate, res, kb, B, H,
-                                 Nq, scale)
+                                 Nq, scale, sp)
         return y.view(B, Nq, -1)
+    if sp is not None:
+        raise B200Error("sequence-sharded attn1 needs frozen, adapter-free attn1 projections and no skip-layer mask")
 
     q_pre = apply_linear(attn.to_q, x2d)
     k_pre = apply_linear(attn.to_k, src2d)
@@ -261,7 +264,12 @@ def transformer_forward(model, hidden_states, indices_grid, ref_image_hidden_sta
                         adapters.append(lora)
         ops.prestage_lora(adapters)  # all fp32 adapters -> padded bf16 GEMM operands in a few launches
         tok = hidden_states if hidden_states.is_contiguous() else hidden_states.contiguous()
-        ops.lerp_condition_(tok, ref_image_hidden_states.to(dt).contiguous(), pose_hidden_states.to(dt).contiguous())
+        # sequence-sharded call: `hidden_states` / `indices_grid` are this rank's contiguous token shard,
+        # the conditioning latents are the whole clip
+        sp = model.__dict__.get("_b200_sp")
+        tok_off = sp.rank * N if sp is not None else 0
+        ops.lerp_condition_(tok, ref_image_hidden_states.to(dt).contiguous(), pose_hidden_states.to(dt).contiguous(),
+                            token_offset=tok_off)
         if tok is not hidden_states:
             hidden_states.copy_(tok)  # keep the reference's side effect on the caller's tensor
     x = apply_linear(model.patchify_proj, tok.view(B * N, C))

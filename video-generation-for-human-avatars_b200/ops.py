@@ -211,12 +211,26 @@ def fa_fwd(q, k, v, B, H, Nq, Nk, key_bias=None, scale=0.125, need_lse=True):
     return o, lse
 
 
-def fa_bwd(q, k, v, o, do, lse, B, H, Nq, Nk, dk, dv, key_bias=None, scale=0.125):
-    """Returns dq as fp32 [B*Nq, H*64]; writes bf16 dk/dv into the given (possibly strided) views."""
-    _chk2d(do, "fa_bwd do")
-    delta = torch.empty((B, H, Nq), device=q.device, dtype=torch.float32)
+def attn_delta(o, do, B, H, Nq):
+    delta = torch.empty((B, H, Nq), device=o.device, dtype=torch.float32)
     _call("attn_delta", 4.0 * B * Nq * H * 64, "byte", _L().b200_attn_delta, _p(o), o.stride(0), _p(do), do.stride(0), _p(delta), B, H, Nq, _s())
-    dq = torch.zeros((B * Nq, H * 64), device=q.device, dtype=torch.float32)
+    return delta
+
+
+def attn_merge(o_acc, lse_acc, o_i, lse_i, B, H, N, first, out=None):
+    """(o_acc, lse_acc) <- online-softmax merge with the partial result (o_i, lse_i); see b200_attn_merge."""
+    _call("attn_merge", (4.0 + 2.0 + 4.0) * B * N * H * 64, "byte", _L().b200_attn_merge, _p(o_acc), o_acc.stride(0),
+          _p(lse_acc), _p(o_i), o_i.stride(0), _p(lse_i), _p(out), out.stride(0) if out is not None else 0, B, H, N,
+          int(first), _s())
+
+
+def fa_bwd(q, k, v, o, do, lse, B, H, Nq, Nk, dk, dv, key_bias=None, scale=0.125, delta=None, dq_accum=None):
+    """Returns dq as fp32 [B*Nq, H*64]; writes bf16 dk/dv into the given (possibly strided) views.
+    `delta` / `dq_accum` may be supplied to accumulate dq over several key shards (ring attention)."""
+    _chk2d(do, "fa_bwd do")
+    if delta is None:
+        delta = attn_delta(o, do, B, H, Nq)
+    dq = dq_accum if dq_accum is not None else torch.zeros((B * Nq, H * 64), device=q.device, dtype=torch.float32)
     _call("fa_bwd", 8.0 * B * H * Nq * Nk * 64, "flop", _L().b200_fa_bwd, _p(q), q.stride(0), _p(k), k.stride(0), _p(v), v.stride(0), _p(do), do.stride(0),
                           _p(lse), _p(delta), _p(key_bias), _p(dq), dq.stride(0), _p(dk), dk.stride(0),
                           _p(dv), dv.stride(0), B, H, Nq, Nk, 64, scale, _s())
@@ -245,16 +259,18 @@ def rf_loss(out, target, grad_scale=1.0, want_grad=True):
     return loss, dout
 
 
-def lerp_condition_(tokens, ref, pose, w_ref=0.85, w_pose=0.5):
-    """In-place on tokens [B,N,C] (contiguous bf16); ref [B,C,1,H,W], pose [B,C,F,H,W]."""
+def lerp_condition_(tokens, ref, pose, w_ref=0.85, w_pose=0.5, token_offset=0):
+    """In-place on tokens [B,N,C] (contiguous bf16); ref [B,C,1,H,W], pose [B,C,F,H,W].  `tokens` may be
+    the contiguous shard [token_offset, token_offset+N) of the F*H*W tokens (sequence sharding)."""
     B, N, C = tokens.shape
     HW = ref.shape[3] * ref.shape[4]
+    N_total = pose.shape[2] * HW
     for t in (tokens, ref, pose):
         if t.dtype != BF16 or not t.is_contiguous():
             raise _lib.B200Error("lerp_condition: contiguous bf16 tensors required")
-    if pose.shape[2] * HW != N or ref.shape[2] != 1:
+    if token_offset + N > N_total or ref.shape[2] != 1:
         raise _lib.B200Error("lerp_condition: pose/ref shapes do not match the token count")
-    _call("lerp_condition", 6.0 * tokens.numel(), "byte", _L().b200_lerp_condition, _p(tokens), _p(ref), _p(pose), B, N, C, HW, w_ref, w_pose, _s())
+    _call("lerp_condition", 6.0 * tokens.numel(), "byte", _L().b200_lerp_condition, _p(tokens), _p(ref), _p(pose), B, N, C, HW, w_ref, w_pose, token_offset, N_total, _s())
     return tokens
 
 
@@ -484,31 +500,44 @@ class SelfAttnFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, Wqkv, bqkv, wqn, wkn, cos, sin, Wo, bo, gate, rows_per_gate, res, key_bias, B, H, N,
-                scale):
+                scale, sp=None):
         M, D = x.shape[0], H * 64
         qkv = gemm(x, Wqkv, bias=bqkv)  # one [M,3D] GEMM against the cached [3D,D] weight concatenation
         qk = torch.empty((M, 2 * D), device=x.device, dtype=BF16)
         qknorm_rope_fwd(qkv[:, :D], qkv[:, D:2 * D], wqn, wkn, cos, sin, qk[:, :D], qk[:, D:])
-        o, lse = fa_fwd(qk[:, :D], qk[:, D:], qkv[:, 2 * D:], B, H, N, N, key_bias, scale)
+        kv = None
+        if sp is None:
+            o, lse = fa_fwd(qk[:, :D], qk[:, D:], qkv[:, 2 * D:], B, H, N, N, key_bias, scale)
+        else:  # sequence-sharded: the local queries meet every rank's keys/values around the ring
+            if key_bias is not None:
+                raise _lib.B200Error("ring attn1: a key mask on the sharded self-attention is not built")
+            from . import ring
+            o, lse, kv = ring.ring_fwd(qk[:, :D], qk[:, D:], qkv[:, 2 * D:], sp.group, B, H, N, scale, sp.impl)
         y = gemm(o, Wo, bias=bo, gate=gate, rows_per_gate=rows_per_gate, res=res)
-        ctx.save_for_backward(qkv, qk, o, lse, Wqkv, wqn, wkn, cos, sin, Wo, gate, key_bias)
-        ctx.meta = (B, H, N, scale, rows_per_gate, res is not None)
+        ctx.save_for_backward(qkv, qk, o, lse, Wqkv, wqn, wkn, cos, sin, Wo, gate, key_bias, kv)
+        ctx.meta = (B, H, N, scale, rows_per_gate, res is not None, sp)
         return y
 
     @staticmethod
     def backward(ctx, dy):
-        qkv, qk, o, lse, Wqkv, wqn, wkn, cos, sin, Wo, gate, key_bias = ctx.saved_tensors
-        B, H, N, scale, rpg, has_res = ctx.meta
+        qkv, qk, o, lse, Wqkv, wqn, wkn, cos, sin, Wo, gate, key_bias, kv = ctx.saved_tensors
+        B, H, N, scale, rpg, has_res, sp = ctx.meta
         D = H * 64
         M = qkv.shape[0]
         dy = dy if dy.stride(1) == 1 else dy.contiguous()
         g = rowscale(dy, gate, rpg) if gate is not None else dy
         do = gemm(g, Wo, b_rows_are_k=True)
         dqkv = torch.empty((M, 3 * D), device=dy.device, dtype=BF16)
-        dk_post = torch.empty((M, D), device=dy.device, dtype=BF16)
-        dq32 = fa_bwd(qk[:, :D], qk[:, D:], qkv[:, 2 * D:], o, do, lse, B, H, N, N, dk_post, dqkv[:, 2 * D:],
-                      key_bias, scale)
+        if sp is None:
+            dk_post = torch.empty((M, D), device=dy.device, dtype=BF16)
+            dq32 = fa_bwd(qk[:, :D], qk[:, D:], qkv[:, 2 * D:], o, do, lse, B, H, N, N, dk_post, dqkv[:, 2 * D:],
+                          key_bias, scale)
+        else:
+            from . import ring
+            dq32, dkv = ring.ring_bwd(qk[:, :D], kv, o, do, lse, sp.group, B, H, N, scale, sp.impl)
+            dk_post = dkv[0]  # fp32, fully reduced over the ring
+            dqkv[:, 2 * D:].copy_(dkv[1])
         qknorm_rope_bwd(dq32, dk_post, qkv[:, :D], qkv[:, D:2 * D], wqn, wkn, cos, sin, dqkv[:, :D], dqkv[:, D:2 * D])
         dx = gemm(dqkv, Wqkv, b_rows_are_k=True) if ctx.needs_input_grad[0] else None
         dres = dy if (has_res and ctx.needs_input_grad[11]) else None
-        return (dx,) + (None,) * 10 + (dres,) + (None,) * 5
+        return (dx,) + (None,) * 10 + (dres,) + (None,) * 6

@@ -1,0 +1,164 @@
+"""Sequence-sharded ring variant of attn1 for long clips (BASELINE config 5).
+
+Every rank owns a contiguous shard of N/P latent tokens.  All token-local ops (norms, projections,
+FFN, attn2 against the replicated caption tokens) need no communication; attn1 needs every key/value.
+K/V shards travel around a ring of P ranks (NCCL P2P over NVLink/NVSwitch through torch.distributed):
+at hop h a rank attends its local queries to the shard of rank (r - h) mod P while the next shard is in
+flight on the communicator's stream, and folds the partial (O, LSE) into fp32 accumulators with the
+online-softmax merge kernel.  The backward walks the ring again: dQ accumulates locally in fp32 over
+the hops (the flash backward reduces into a caller-owned buffer), while the fp32 dK/dV accumulator of
+a shard travels one hop behind its shard and arrives, fully reduced, back at the owner after P hops;
+its transfer overlaps the next hop's backward kernel.
+
+Why copy-then-compute and not peer loads inside the flash kernel: every 128-query CTA re-reads all
+keys/values of its head, i.e. N/128 passes over the shard; served from the local 126 MB L2 that is
+free, served over NVLink it would be ~48x the shard size per layer (2.5 GB at cfg5/P=2, ~2.8 ms at
+900 GB/s against 0.6 ms of math).  One DMA of the shard per hop (52 MB at P=2, 13 MB at P=8; 58 us at
+900 GB/s) hidden behind the ~0.3-1.2 ms hop kernel is the right shape.
+
+The reference has no counterpart (no sequence parallelism anywhere); numerics are
+checked against the un-sharded path."""
+from typing import Optional
+
+import torch
+import torch.distributed as dist
+
+from . import ops
+
+BF16 = torch.bfloat16
+
+
+def _peers(group):
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    nxt, prv = (rank + 1) % world, (rank - 1) % world
+    if group is not None:
+        nxt, prv = dist.get_global_rank(group, nxt), dist.get_global_rank(group, prv)
+    return nxt, prv
+
+
+def _ring_exchange(send: torch.Tensor, recv: torch.Tensor, group) -> list:
+    """Post send-to-next / recv-from-previous of one buffer; returns the work handles."""
+    nxt, prv = _peers(group)
+    return dist.batch_isend_irecv([dist.P2POp(dist.isend, send, nxt, group), dist.P2POp(dist.irecv, recv, prv, group)])
+
+
+def _wait(works):
+    for w in works:
+        w.wait()
+
+
+class LocalAttention:
+    """The per-hop kernels.  The default runs the b200 flash kernels; CPU tests inject a plain torch
+    implementation with the same methods to exercise the ring logic over gloo."""
+
+    def fwd(self, q, k, v, B, H, nq, nk, scale):
+        return ops.fa_fwd(q, k, v, B, H, nq, nk, None, scale)
+
+    def merge(self, o_acc, lse_acc, o_i, lse_i, B, H, n, first, out):
+        ops.attn_merge(o_acc, lse_acc, o_i, lse_i, B, H, n, first, out)
+
+    def delta(self, o, do, B, H, nq):
+        return ops.attn_delta(o, do, B, H, nq)
+
+    def bwd(self, q, k, v, o, do, lse, delta, dq_accum, B, H, nq, nk, scale):
+        dk = torch.empty_like(k)
+        dv = torch.empty_like(v)
+        ops.fa_bwd(q, k, v, o, do, lse, B, H, nq, nk, dk, dv, None, scale, delta=delta, dq_accum=dq_accum)
+        return dk, dv
+
+
+def ring_fwd(q, k, v, group, B, H, n_local, scale, impl: Optional[LocalAttention] = None):
+    """q/k/v: [B*n_local, >= H*64] (row-strided views allowed).  Returns (out bf16 [B*n_local, H*64],
+    lse fp32 [B,H,n_local] over ALL keys, kv = the contiguous [2, B*n_local, H*64] message buffer)."""
+    impl = impl or LocalAttention()
+    world = dist.get_world_size(group)
+    D = H * 64
+    kv = torch.stack([k, v])  # contiguous copy: one message per hop
+    o_acc = torch.empty((B * n_local, D), device=q.device, dtype=torch.float32)
+    lse_acc = torch.empty((B, H, n_local), device=q.device, dtype=torch.float32)
+    out = torch.empty((B * n_local, D), device=q.device, dtype=q.dtype)
+    cur = kv
+    for hop in range(world):
+        works, nxt = [], None
+        if hop + 1 < world:
+            nxt = torch.empty_like(kv)
+            works = _ring_exchange(cur, nxt, group)  # in flight during this hop's attention
+        o_i, lse_i = impl.fwd(q, cur[0], cur[1], B, H, n_local, n_local, scale)
+        impl.merge(o_acc, lse_acc, o_i, lse_i, B, H, n_local, hop == 0, out if hop + 1 == world else None)
+        _wait(works)
+        if nxt is not None:
+            cur = nxt
+    return out, lse_acc, kv
+
+
+def ring_bwd(q, kv, out, do, lse, group, B, H, n_local, scale, impl: Optional[LocalAttention] = None):
+    """Returns (dq fp32 [B*n_local, H*64], dkv fp32 [2, B*n_local, H*64]) for the local shard."""
+    impl = impl or LocalAttention()
+    world = dist.get_world_size(group)
+    delta = impl.delta(out, do, B, H, n_local)
+    dq = torch.zeros((B * n_local, H * 64), device=q.device, dtype=torch.float32)
+    cur_kv = kv
+    g_works, g_in = [], None
+    for hop in range(world):
+        kv_works, nxt_kv = [], None
+        if hop + 1 < world:
+            nxt_kv = torch.empty_like(kv)
+            kv_works = _ring_exchange(cur_kv, nxt_kv, group)
+        dk, dv = impl.bwd(q, cur_kv[0], cur_kv[1], out, do, lse, delta, dq, B, H, n_local, n_local, scale)
+        # the accumulator of the shard processed here was sent by the previous rank after its last hop
+        _wait(g_works)
+        if g_in is None:
+            g = torch.stack([dk, dv]).float()
+        else:
+            g = g_in
+            g[0] += dk
+            g[1] += dv
+        _wait(kv_works)
+        # ... and follows its shard to the next rank (after the last hop: back home), overlapping
+        # with the next hop's backward kernel
+        g_in = torch.empty_like(g)
+        g_works = _ring_exchange(g, g_in, group)
+        if nxt_kv is not None:
+            cur_kv = nxt_kv
+    _wait(g_works)
+    return dq, g_in
+
+
+class RingAttnFn(torch.autograd.Function):
+    """o = softmax(q [k_0 .. k_{P-1}]^T * scale) [v_0 .. v_{P-1}] for the local query shard."""
+
+    @staticmethod
+    def forward(ctx, q, k, v, group, B, H, n_local, scale, impl):
+        out, lse, kv = ring_fwd(q, k, v, group, B, H, n_local, scale, impl)
+        ctx.save_for_backward(q, kv, out, lse)
+        ctx.meta = (group, B, H, n_local, scale, impl)
+        return out
+
+    @staticmethod
+    def backward(ctx, do):
+        q, kv, out, lse = ctx.saved_tensors
+        group, B, H, n_local, scale, impl = ctx.meta
+        dq, dkv = ring_bwd(q, kv, out, do.contiguous(), lse, group, B, H, n_local, scale, impl)
+        return dq.to(q.dtype), dkv[0].to(q.dtype), dkv[1].to(q.dtype), None, None, None, None, None, None
+
+
+def ring_attention(q, k, v, group, B, H, n_local, scale, impl: Optional[LocalAttention] = None):
+    return RingAttnFn.apply(q, k, v, group, B, H, n_local, scale, impl)
+
+
+class SequenceParallel:
+    """Per-model sequence-sharding state (set by api.enable_sequence_parallel)."""
+
+    def __init__(self, group=None, impl: Optional[LocalAttention] = None):
+        self.group = group
+        self.rank = dist.get_rank(group)
+        self.world = dist.get_world_size(group)
+        self.impl = impl
+
+    def shard(self, n_total: int):
+        """(offset, length) of this rank's contiguous token shard."""
+        if n_total % self.world:
+            raise ops._lib.B200Error(f"sequence sharding needs the token count ({n_total}) to divide by the "
+                                     f"group size ({self.world})")
+        n = n_total // self.world
+        return self.rank * n, n

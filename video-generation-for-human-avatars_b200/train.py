@@ -55,6 +55,17 @@ def train_step(model, batch: dict, scheduler, patchifier, config, prompt_embeds,
         t = sample_timesteps(config, scheduler, tokens.shape, B, tokens.device)
     if noise is None:
         noise = torch.randn_like(tokens)
+    root = getattr(getattr(model, "base_model", None), "model", None) or model
+    sp = root.__dict__.get("_b200_sp")
+    if sp is not None:
+        # sequence-sharded step: every rank of the group sees the same clip and timestep and keeps its
+        # contiguous token shard; the loss is the per-shard mean (average gradients over the group)
+        torch.distributed.broadcast(t, torch.distributed.get_global_rank(sp.group, 0) if sp.group is not None else 0,
+                                    group=sp.group)
+        off, n = sp.shard(tokens.shape[1])
+        tokens = tokens[:, off:off + n].contiguous()
+        coords = coords[:, :, off:off + n].contiguous()
+        noise = noise[:, off:off + n].contiguous()
     noisy, v_target = scheduler.noise_and_target(tokens, noise.to(model_dtype), t)
     out = model(hidden_states=noisy, indices_grid=coords, ref_image_hidden_states=ref, pose_hidden_states=pose,
                 encoder_hidden_states=enc, timestep=t, attention_mask=None, encoder_attention_mask=enc_mask,
