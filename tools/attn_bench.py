@@ -1,0 +1,44 @@
+"""Micro-benchmark of the flash-attention kernels at the LTXV shapes (warm, CUDA events, L2 flushed)."""
+import os
+import sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from b200_ltx import ops
+
+dev = "cuda"
+H, D = 32, 2048
+flush = torch.empty(256 << 20, device=dev, dtype=torch.uint8)
+
+
+def timeit(fn, n=8):
+    for _ in range(2):
+        fn()
+    ts = []
+    for _ in range(n):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); fn(); e1.record(); torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    ts.sort()
+    return ts[len(ts) // 2]
+
+
+for (name, B, Nq, Nk, bias) in [("attn1 cfg2", 1, 6144, 6144, False), ("attn1 cfg3", 4, 3328, 3328, False),
+                                ("attn1 cfg5", 1, 12672, 12672, False), ("attn2 cfg2 (15/256 keys)", 1, 6144, 256, True)]:
+    g = torch.Generator(device="cpu").manual_seed(0)
+    q = torch.randn(B * Nq, D, generator=g).to(dev, torch.bfloat16)
+    k = torch.randn(B * Nk, D, generator=g).to(dev, torch.bfloat16)
+    v = torch.randn(B * Nk, D, generator=g).to(dev, torch.bfloat16)
+    do = torch.randn(B * Nq, D, generator=g).to(dev, torch.bfloat16)
+    kb = None
+    if bias:
+        kb = torch.zeros(B, Nk, device=dev)
+        kb[:, 15:] = -10000.0
+    o, lse = ops.fa_fwd(q, k, v, B, H, Nq, Nk, kb, 0.125)
+    dk, dv = torch.empty_like(k), torch.empty_like(v)
+    delta = ops.attn_delta(o, do, B, H, Nq)
+    dq = torch.zeros(B * Nq, D, device=dev)
+    tf = timeit(lambda: ops.fa_fwd(q, k, v, B, H, Nq, Nk, kb, 0.125))
+    tb = timeit(lambda: ops.fa_bwd(q, k, v, o, do, lse, B, H, Nq, Nk, dk, dv, kb, 0.125, delta=delta, dq_accum=dq))
+    fl = 4.0 * B * H * Nq * Nk * 64
+    print(f"{name:28s} fwd {tf*1e3:8.1f} us {fl/tf/1e9:7.1f} TF/s   bwd {tb*1e3:8.1f} us {2*fl/tb/1e9:7.1f} TF/s", flush=True)

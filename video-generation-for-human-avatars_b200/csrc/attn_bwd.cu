@@ -6,20 +6,33 @@
 //
 // One CTA owns one 128-key tile of one head and walks over the 128-query tiles.  Everything is
 // computed transposed (keys on TMEM lanes) so that each compute thread owns one key row:
-//   S^T  = K Q^T              (128 x 128 x 64, both operands K-major)
-//   dP^T = V dO^T             (128 x 128 x 64)
-//   P^T  = exp2(S^T*c + bias - lse) ; dS^T = P^T * (dP^T - delta) * scale    -> shared memory, bf16
-//   dV  += P^T  dO            (A = P^T  packed bf16 in TMEM,  B = dO tile read MN-major)
-//   dK  += dS^T Q             (A = dS^T K-major,            B = Q  tile read MN-major)
-//   dQ   = dS   K             (A = the same dS^T bytes read MN-major, B = K tile read MN-major)
+//   S^T  = K Q^T              (A = K  resident in TMEM,     B = Q  tile, K-major)
+//   dP^T = V dO^T             (A = V  resident in TMEM,     B = dO tile, K-major)
+//   P^T  = exp2(S^T*c + bias - lse) ; dS^T = P^T * (dP^T - delta) * scale
+//   dV  += P^T  dO            (A = P^T  packed bf16 in TMEM, B = dO tile read MN-major)
+//   dK  += dS^T Q             (A = dS^T packed bf16 in TMEM, B = Q  tile read MN-major)
+//   dQ   = dS   K             (A = dS^T bytes in shared memory read MN-major, B = K tile read MN-major)
+// The tensor pipe is fed from shared memory at well under 128 B/clk, and at head_dim 64 a 128x64x16 MMA
+// needs 6 KB of operands per 32 math cycles when both come from shared memory: operand fetch, not math,
+// was the limit of the first versions (176 KB of shared-memory operand reads per tile pair).  Hence
+// every A operand that can live in TMEM does: K and V are copied there once per CTA, P^T and dS^T
+// overwrite the S^T / dP^T columns they were computed from; only dQ reads dS^T from shared memory
+// (the transposed view needs the MN-major descriptor).  112 KB of operand reads per tile pair.
 // dV/dK accumulate in TMEM over the whole loop; dQ is a per-(q tile, k tile) partial that is
 // reduced across key-tile CTAs with TMA reduce-add (cp.reduce.async.bulk.tensor) into a caller-zeroed
-// fp32 buffer (per-lane red.global.add measured ~10 k cycles per tile: the atomics were the bottleneck).
-// TMEM: S^T 128 | dP^T 128 | dV 64 | dK 64 | dQ 64 | P^T (bf16x2) 64 = 512 columns.
+// fp32 buffer.
+// TMEM: S^T 128 | dP^T 128 | dV 64 | dK 64 | dQ 64 | K 32 | V 32 = 512 columns.
 //
-// Pipeline: P^T/dS^T are double-buffered in shared memory, so while the 8 compute warps turn
-// S^T/dP^T(i+1) into P^T/dS^T(i+1) the tensor pipe runs dV/dK/dQ(i); dQ(i-1) is drained to global
-// memory right after P^T/dS^T(i) are handed over.
+// Pipeline at HALF-tile granularity (64 queries): S^T / dP^T are two independent 64-column halves with
+// their own barriers.  While the 16 compute warps turn half h into P^T / dS^T, the tensor pipe runs
+// dV/dK of half h-1 and the scores of half h+1; the scores of half h+2 go behind dV/dK of half h (they
+// overwrite P^T/dS^T(h)).  Q/dO tiles are triple-buffered so the TMA latency never reaches the MMA warp.
+// The key-tile CTAs of a head run concurrently and all reduce their dQ partials into the same rows: CTA
+// kt therefore walks the query tiles starting at tile kt (mod T), so that at any moment the concurrent
+// reduce-adds hit different addresses (the L2 atomic unit serialises per address).
+// Four further warps do everything that is not arithmetic: they stream lse/delta into shared memory two
+// tiles ahead and drain dQ(i) (TMEM -> per-warp swizzled staging -> TMA reduce-add) without a CTA-wide
+// barrier, so the compute warps execute nothing but the element-wise math.
 #include "api_internal.h"
 #include "common.cuh"
 #include "tmap.h"
@@ -43,8 +56,9 @@ struct FaBwdParams {
   float scale, scale_log2;
 };
 
-constexpr int FA_BWD_SMEM = 16384 * 2 /*K,V*/ + 2 * 32768 /*Q,dO x2*/ + 2 * 32768 /*dS^T x2*/ +
-                            32768 /*dQ staging*/ + 2 * 2 * 512 /*lse, delta x2*/ + 128;
+constexpr int FA_BWD_QSTAGES = 3;
+constexpr int FA_BWD_SMEM = 16384 * 2 /*K,V*/ + FA_BWD_QSTAGES * 32768 /*Q,dO*/ + 2 * 32768 /*dS^T x2*/ +
+                            32768 /*dQ staging*/ + 2 * 2 * 512 /*lse, delta x2*/ + 256;
 constexpr float kLog2eB = 1.4426950408889634f;
 
 __device__ __forceinline__ float ex2_approx_b(float x) {
@@ -53,13 +67,34 @@ __device__ __forceinline__ float ex2_approx_b(float x) {
   return y;
 }
 
-__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
-  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c),
-               "f"(d)
-               : "memory");
-}
+#ifdef B200_TRACE
+__device__ unsigned long long g_bwd_trace[8192];
+#define TRACE(slot)                                                                       \
+  do {                                                                                    \
+    if (blockIdx.x == 3 && blockIdx.y == 0 && blockIdx.z == 0 && (threadIdx.x & 31) == 0) \
+      g_bwd_trace[(slot)] = clock64();                                                    \
+  } while (0)
+#else
+#define TRACE(slot) do {} while (0)
+#endif
 
-constexpr int FA_BWD_THREADS = 64 + 512;  // TMA warp, MMA warp, 16 compute warps
+// mbarrier arrivals of the compute / drain warps: per thread or one per warp (experiment switch)
+#ifdef B200_CW_PER_WARP
+#define CW_ARRIVALS 16
+#define CW_ARRIVE(bar_) do { __syncwarp(); if (lane == 0) mbar_arrive(bar_); } while (0)
+#else
+#define CW_ARRIVALS 512
+#define CW_ARRIVE(bar_) mbar_arrive(bar_)
+#endif
+#ifdef B200_DW_PER_WARP
+#define DW_ARRIVALS 4
+#define DW_ARRIVE(bar_) do { __syncwarp(); if (lane == 0) mbar_arrive(bar_); } while (0)
+#else
+#define DW_ARRIVALS 128
+#define DW_ARRIVE(bar_) mbar_arrive(bar_)
+#endif
+
+constexpr int FA_BWD_THREADS = 64 + 512 + 128;  // TMA warp, MMA warp, 16 compute warps, 4 drain/stat warps
 
 __global__ void __launch_bounds__(FA_BWD_THREADS, 1)
 fa_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
@@ -68,13 +103,14 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t sbase = smem_u32(smem_raw);
   const uint32_t sK = sbase, sV = sbase + 16384, sQdO = sbase + 32768;  // stage s: Q at +s*32768, dO at +16384
-  // dS^T is double-buffered in shared memory (buffer = tile & 1); P^T lives in TMEM (A operand of dV).
-  const uint32_t sDS = sQdO + 65536;
-  const uint32_t sStage = sDS + 65536;   // fp32 dQ staging tile for the TMA reduce-add
+  // dS^T for the dQ MMA is double-buffered in shared memory (buffer = tile & 1)
+  const uint32_t sDS = sQdO + FA_BWD_QSTAGES * 32768;
+  const uint32_t sStage = sDS + 65536;   // fp32 dQ staging: one 8 KB (32 rows x 64 fp32) region per drain warp
   const uint32_t sStat = sStage + 32768;  // [2 stages][lse 128 | delta 128] fp32
   const uint32_t bar = sStat + 2048;
-  const uint32_t kv_full = bar, qd_full0 = bar + 8, qd_empty0 = bar + 24, s_full = bar + 40,
-                 pds_full = bar + 48, mma2_done = bar + 56, dq_free = bar + 64, tmem_slot = bar + 72;
+  const uint32_t kv_full = bar, qd_full0 = bar + 8, qd_empty0 = bar + 32, s_full0 = bar + 56,
+                 pds_full0 = bar + 72, mma2_done = bar + 88, dq_free = bar + 96, stat_full0 = bar + 104,
+                 all_done = bar + 120, kv_tmem = bar + 128, tmem_slot = bar + 136;
   float* stat = reinterpret_cast<float*>(smem_raw + (sStat - sbase));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int kt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
@@ -91,14 +127,19 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
     tma_prefetch_desc(&tmdO);
     tma_prefetch_desc(&tmdQ);
     mbar_init(kv_full, 1);
-    for (int s = 0; s < 2; ++s) {
+    for (int s = 0; s < FA_BWD_QSTAGES; ++s) {
       mbar_init(qd_full0 + 8 * s, 1);
       mbar_init(qd_empty0 + 8 * s, 1);
     }
-    mbar_init(s_full, 1);
-    mbar_init(pds_full, 512);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(s_full0 + 8 * s, 1);
+      mbar_init(pds_full0 + 8 * s, CW_ARRIVALS);
+      mbar_init(stat_full0 + 8 * s, DW_ARRIVALS);
+    }
     mbar_init(mma2_done, 1);
-    mbar_init(dq_free, 512);
+    mbar_init(dq_free, DW_ARRIVALS);
+    mbar_init(all_done, 1);
+    mbar_init(kv_tmem, CW_ARRIVALS);
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -111,78 +152,99 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
   const uint32_t tSt = tmem_base, tdPt = tmem_base + 128, tdV = tmem_base + 256,
-                 tdK = tmem_base + 320, tdQ = tmem_base + 384, tPt = tmem_base + 448;
+                 tdK = tmem_base + 320, tdQ = tmem_base + 384, tK = tmem_base + 448, tV = tmem_base + 480;
 
   if (warp == 0 && lane == 0) {
     mbar_expect_tx(kv_full, 32768);
     tma_load_3d(sK, &tmK, kv_full, h * 64, kt * 128, b);
     tma_load_3d(sV, &tmV, kv_full, h * 64, kt * 128, b);
+    int s = 0;
+    uint32_t ph = 0;
     for (int i = 0; i < T; ++i) {
-      const int s = i & 1;
-      mbar_wait(qd_empty0 + 8 * s, ((i >> 1) & 1) ^ 1);
+      mbar_wait(qd_empty0 + 8 * s, ph ^ 1);
       mbar_expect_tx(qd_full0 + 8 * s, 32768);
-      tma_load_3d(sQdO + s * 32768, &tmQ, qd_full0 + 8 * s, h * 64, i * 128, b);
-      tma_load_3d(sQdO + s * 32768 + 16384, &tmdO, qd_full0 + 8 * s, h * 64, i * 128, b);
+      const int qt = (i + kt) % T;  // staggered walk, see below
+      tma_load_3d(sQdO + s * 32768, &tmQ, qd_full0 + 8 * s, h * 64, qt * 128, b);
+      tma_load_3d(sQdO + s * 32768 + 16384, &tmdO, qd_full0 + 8 * s, h * 64, qt * 128, b);
+      if (++s == FA_BWD_QSTAGES) { s = 0; ph ^= 1; }
     }
-  } else if (warp == 1 && lane == 0) {
-    const uint32_t idesc_s = make_idesc_bf16(128, 128, 0, 0);   // K-major x K-major
-    const uint32_t idesc_kv = make_idesc_bf16(128, 64, 0, 1);   // A K-major, B MN-major
+  } else if (warp == 1) {
+    // MMA warp: all 32 lanes follow the control flow (barrier waits), one elected lane issues.  Every
+    // descriptor is a constant base plus a small offset, so the instruction stream per MMA is minimal.
+    const uint32_t idesc_s = make_idesc_bf16(128, 64, 0, 0);    // A (TMEM) x B K-major, one 64-query half
+    const uint32_t idesc_kv = make_idesc_bf16(128, 64, 0, 1);   // A (TMEM), B MN-major
     const uint32_t idesc_dq = make_idesc_bf16(128, 64, 1, 1);   // A MN-major, B MN-major
-    mbar_wait(kv_full, 0);
-    // S^T / dP^T of tile i+1 are issued right behind dV/dK/dQ of tile i, so the tensor pipe keeps
-    // running while the compute warps drain dQ_i and the next S^T is ready when they come back.
-    auto issue_scores = [&](int i) {
-      const int s = i & 1;
-      const uint32_t sQ = sQdO + s * 32768, sdO = sQ + 16384;
-      mbar_wait(qd_full0 + 8 * s, (i >> 1) & 1);
-      tc_fence_after();
-#pragma unroll
-      for (int k = 0; k < 4; ++k)
-        umma_ss(tSt, make_smem_desc(sK + k * 32, 16, 1024), make_smem_desc(sQ + k * 32, 16, 1024),
-                idesc_s, k > 0 ? 1u : 0u);
-#pragma unroll
-      for (int k = 0; k < 4; ++k)
-        umma_ss(tdPt, make_smem_desc(sV + k * 32, 16, 1024), make_smem_desc(sdO + k * 32, 16, 1024),
-                idesc_s, k > 0 ? 1u : 0u);
-      umma_commit(s_full);
-    };
-    if (T > 0) issue_scores(0);
-    for (int i = 0; i < T; ++i) {
-      const int s = i & 1;
-      const uint32_t sQ = sQdO + s * 32768, sdO = sQ + 16384;
-      const uint32_t sdSt = sDS + s * 32768;
-      mbar_wait(pds_full, i & 1);  // P^T(i) is in TMEM, dS^T(i) in shared memory; S^T/dP^T are consumed
-      tc_fence_after();
-#pragma unroll
-      for (int k = 0; k < 8; ++k)  // dV += P^T dO   (A = packed bf16 P^T straight from TMEM, K = queries)
-        umma_ts(tdV, tPt + k * 8, make_smem_desc(sdO + k * 2048, 8192, 1024), idesc_kv,
-                (i > 0 || k > 0) ? 1u : 0u);
-      // S^T/dP^T(i+1) go behind dV(i): once they complete, P^T(i) has been consumed and the compute
-      // warps may overwrite it while dK/dQ(i) run below
-      if (i + 1 < T) issue_scores(i + 1);
-#pragma unroll
-      for (int k = 0; k < 8; ++k)  // dK += dS^T Q
-        umma_ss(tdK, make_smem_desc(sdSt + (k >> 2) * 16384 + (k & 3) * 32, 16, 1024),
-                make_smem_desc(sQ + k * 2048, 8192, 1024), idesc_kv, (i > 0 || k > 0) ? 1u : 0u);
-      if (i > 0) {
-        mbar_wait(dq_free, (i - 1) & 1);  // dQ(i-1) has been read out of TMEM
+    const uint64_t dQ_k = make_smem_desc(sQdO, 16, 1024), dQ_mn = make_smem_desc(sQdO, 8192, 1024);
+    const uint64_t ddS_mn = make_smem_desc(sDS, 16384, 1024), dK_mn = make_smem_desc(sK, 8192, 1024);
+    mbar_wait(kv_tmem, 0);  // K and V are resident in TMEM
+    tc_fence_after();
+    // scores of half-tile g (tile g>>1, queries [64*(g&1), +64)): S^T and dP^T into their half's columns
+    auto issue_scores = [&](int g) {
+      const int i = g >> 1, hf = g & 1, s = i % FA_BWD_QSTAGES;
+      if (hf == 0) {
+        mbar_wait(qd_full0 + 8 * s, (i / FA_BWD_QSTAGES) & 1);
         tc_fence_after();
       }
+      if (elect_one()) {
+        const uint64_t bq = desc_adv(dQ_k, s * 32768 + hf * 8192), bo = desc_adv(bq, 16384);
 #pragma unroll
-      for (int k = 0; k < 8; ++k)  // dQ = dS K      (K = keys; A = dS^T bytes read MN-major)
-        umma_ss(tdQ, make_smem_desc(sdSt + k * 2048, 16384, 1024),
-                make_smem_desc(sK + k * 2048, 8192, 1024), idesc_dq, k > 0 ? 1u : 0u);
-      umma_commit(qd_empty0 + 8 * s);
-      umma_commit(mma2_done);
+        for (int k = 0; k < 4; ++k) umma_ts(tSt + hf * 64, tK + k * 8, desc_adv(bq, k * 32), idesc_s, k > 0 ? 1u : 0u);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma_ts(tdPt + hf * 64, tV + k * 8, desc_adv(bo, k * 32), idesc_s, k > 0 ? 1u : 0u);
+        umma_commit(s_full0 + 8 * hf);
+      }
+      __syncwarp();
+    };
+    const int G = 2 * T;
+    if (G > 0) issue_scores(0);
+    if (G > 1) issue_scores(1);
+    for (int g = 0; g < G; ++g) {
+      const int i = g >> 1, hf = g & 1, s = i % FA_BWD_QSTAGES;
+      mbar_wait(pds_full0 + 8 * hf, i & 1);  // P^T(g), dS^T(g) written (TMEM + shared memory)
+      tc_fence_after();
+      TRACE(g * 4 + 0);
+      if (elect_one()) {
+        // P^T / dS^T of the 16 queries of k-step k sit in the first 8 of the 16 S^T / dP^T columns they
+        // were computed from (each compute warp overwrites only columns it has read itself)
+        const uint64_t bq = desc_adv(dQ_mn, s * 32768 + hf * 8192), bo = desc_adv(bq, 16384);
+        const uint32_t acc0 = g > 0 ? 1u : 0u;
+#pragma unroll
+        for (int k = 0; k < 4; ++k)  // dV += P^T dO   (K = 64 queries)
+          umma_ts(tdV, tSt + hf * 64 + k * 16, desc_adv(bo, k * 2048), idesc_kv, k > 0 ? 1u : acc0);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)  // dK += dS^T Q
+          umma_ts(tdK, tdPt + hf * 64 + k * 16, desc_adv(bq, k * 2048), idesc_kv, k > 0 ? 1u : acc0);
+        if (hf == 1) umma_commit(qd_empty0 + 8 * s);  // Q/dO(i) are not needed by dQ(i)
+      }
+      __syncwarp();
+      // scores(g+2) overwrite this half's columns: behind dV(g) and dK(g)
+      if (g + 2 < G) issue_scores(g + 2);
+      TRACE(g * 4 + 1);
+      if (hf == 1) {
+        if (i > 0) {
+          mbar_wait(dq_free, (i - 1) & 1);  // dQ(i-1) has been read out of TMEM
+          tc_fence_after();
+        }
+        if (elect_one()) {
+          const uint64_t da = desc_adv(ddS_mn, (i & 1) * 32768);
+#pragma unroll
+          for (int k = 0; k < 8; ++k)  // dQ = dS K      (K = keys; A = dS^T bytes read MN-major)
+            umma_ss(tdQ, desc_adv(da, k * 2048), desc_adv(dK_mn, k * 2048), idesc_dq, k > 0 ? 1u : 0u);
+          umma_commit(mma2_done);
+        }
+        __syncwarp();
+      }
+      TRACE(g * 4 + 2);
     }
-  } else if (warp >= 2) {
+    if (elect_one()) umma_commit(all_done);
+    __syncwarp();
+  } else if (warp >= 2 && warp < 18) {
     // 16 compute warps = 4 per TMEM lane quadrant (four warps per SM sub-partition hide each other's
-    // MUFU / LDS / TMEM latencies); warp `part` of a quadrant owns one 32-column chunk of the 128 query
-    // columns of S^T / dP^T and 16 of the 64 columns of the dQ / dK / dV accumulators.
+    // MUFU / LDS / TMEM latencies); warp `part` of a quadrant owns 16 of the 64 query columns of each
+    // half of S^T / dP^T and 16 of the 64 columns of the dK / dV accumulators.
     const int quad = warp & 3;
     const int part = (warp - 2) >> 2;   // 0..3
-    const int row = quad * 32 + lane;   // key row of S^T / dP^T, query row of dQ
-    const int ctid = threadIdx.x - 64;  // 0..511 among the compute threads
+    const int row = quad * 32 + lane;   // key row of S^T / dP^T
     const uint32_t lane_bits = (uint32_t)(quad * 32) << 16;
     const int key = kt * 128 + row;
     const bool key_ok = key < p.Nk;
@@ -190,66 +252,49 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
     const float kbias = !key_ok ? -INFINITY
                                 : (p.key_bias ? p.key_bias[(int64_t)b * p.Nk + key] * kLog2eB : 0.f);
     const bool has_bias = __any_sync(0xffffffffu, kbias != 0.f);  // warp-uniform fast-path switch
-    const float* stat_g = (ctid < 128 ? p.lse : p.delta) + ((int64_t)b * p.H + h) * p.Nq;
-    const float stat_mul = ctid < 128 ? kLog2eB : p.scale;   // lse -> log2 units, delta -> pre-scaled
-    const float stat_pad = ctid < 128 ? INFINITY : 0.f;      // +inf lse => P = 0 for padded queries
-    const int sq = ctid & 127;
-    const bool stat_thread = ctid < 256;
-    // lse / delta of tile i+1 are fetched one tile ahead (global-load latency off the critical path)
-    float nxt = (stat_thread && sq < p.Nq) ? stat_g[sq] * stat_mul : stat_pad;
-    // dQ(j): TMEM -> swizzled fp32 staging tile (the dead P^T buffer of tile j) -> TMA reduce-add
-    // (cp.reduce.async.bulk.tensor .add) into the fp32 dQ accumulator in global memory.
-    auto drain_dq = [&](int j) {
-      mbar_wait(mma2_done, j & 1);
-      tc_fence_after();
-      uint32_t r0[16];
-      tmem_ld16(tdQ + lane_bits + part * 16, r0);
-      tmem_ld_wait();
-      tc_fence_before();
-      mbar_arrive(dq_free);  // the dQ columns may be overwritten by dQ(j+1)
-      const uint32_t stage = sStage;
-      if (ctid == 0) tma_store_wait_read<0>();  // the previous reduce-add has finished reading the staging tile
-      named_bar_sync(2, 512);
+    {
+      // K, V rows -> TMEM (A operands of the score MMAs): this warp copies 16 of the 64 head columns,
+      // i.e. two 16-byte chunks of the swizzled 128-byte row = 8 packed bf16x2 TMEM columns
+      mbar_wait(kv_full, 0);
+      uint32_t rk[8], rv[8];
 #pragma unroll
-      for (int g = 0; g < 4; ++g)
-        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stage + (part >> 1) * 16384 +
-                                                                      sw128_off(row, (part & 1) * 4 + g)),
-                     "r"(r0[g * 4 + 0]), "r"(r0[g * 4 + 1]), "r"(r0[g * 4 + 2]), "r"(r0[g * 4 + 3])
-                     : "memory");
-      fence_proxy_async_smem();
-      named_bar_sync(3, 512);
-      if (ctid == 0) {
-        tma_reduce_add_3d(&tmdQ, stage, h * 64, j * 128, b);
-        tma_reduce_add_3d(&tmdQ, stage + 16384, h * 64 + 32, j * 128, b);
-        tma_store_commit();
+      for (int c = 0; c < 2; ++c) {
+        const uint32_t off = sw128_off(row, part * 2 + c);
+        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                     : "=r"(rk[c * 4]), "=r"(rk[c * 4 + 1]), "=r"(rk[c * 4 + 2]), "=r"(rk[c * 4 + 3])
+                     : "r"(sK + off));
+        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                     : "=r"(rv[c * 4]), "=r"(rv[c * 4 + 1]), "=r"(rv[c * 4 + 2]), "=r"(rv[c * 4 + 3])
+                     : "r"(sV + off));
       }
-    };
+      tmem_st8(tK + lane_bits + part * 8, rk);
+      tmem_st8(tV + lane_bits + part * 8, rv);
+      tmem_st_wait();
+      tc_fence_before();
+      CW_ARRIVE(kv_tmem);
+    }
     for (int i = 0; i < T; ++i) {
       const int s = i & 1;
-      const int q0 = i * 128;
-      float* st = stat + s * 256;
-      const uint32_t sdSt = sDS + s * 32768;
-      if (stat_thread) {
-        st[ctid] = nxt;  // [0,128): lse * log2e ; [128,256): delta * scale
-        const int qn = q0 + 128 + sq;
-        nxt = qn < p.Nq ? stat_g[qn] * stat_mul : stat_pad;
-      }
-      // dS^T buffer s was last read by dK/dQ(i-2); mma2_done(i-2) was awaited when dQ(i-2) was drained
-      named_bar_sync(1, 512);
-      mbar_wait(s_full, i & 1);
-      tc_fence_after();
-      {
-        const int c = part;  // this warp's 32-column chunk of the 128 query columns
-        uint32_t rs[32], rd[32];
-        tmem_ld32(tSt + lane_bits + c * 32, rs);
-        tmem_ld32(tdPt + lane_bits + c * 32, rd);
+      const float* st = stat + s * 256;
+      mbar_wait(stat_full0 + 8 * s, (i >> 1) & 1);  // lse / delta of tile i are in shared memory
+#pragma unroll 1
+      for (int hf = 0; hf < 2; ++hf) {
+        const uint32_t sdSt = sDS + s * 32768 + hf * 16384;
+        const int c0 = hf * 64 + part * 16;  // this warp's 16 query columns inside the tile
+        if (warp == 2) TRACE(2048 + (2 * i + hf) * 4 + 0);
+        mbar_wait(s_full0 + 8 * hf, i & 1);
+        tc_fence_after();
+        if (warp == 2) TRACE(2048 + (2 * i + hf) * 4 + 1);
+        uint32_t rs[16], rd[16];
+        tmem_ld16(tSt + lane_bits + c0, rs);
+        tmem_ld16(tdPt + lane_bits + c0, rd);
         tmem_ld_wait();
-        const uint32_t off0 = (c >> 1) * 16384;
-        const float4* lse4 = reinterpret_cast<const float4*>(st + c * 32);
-        const float4* del4 = reinterpret_cast<const float4*>(st + 128 + c * 32);
-        uint32_t pk[16];  // this warp's 32 query columns of P^T as packed bf16x2 -> 16 TMEM columns
+        if (warp == 2) TRACE(2048 + (2 * i + hf) * 4 + 2);
+        const float4* lse4 = reinterpret_cast<const float4*>(st + c0);
+        const float4* del4 = reinterpret_cast<const float4*>(st + 128 + c0);
+        uint32_t pk[8], dk8[8];  // 16 query columns of P^T / dS^T as packed bf16x2 -> 8 TMEM columns each
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
+        for (int g = 0; g < 2; ++g) {
           float pv[8], ds[8];
 #pragma unroll
           for (int h4 = 0; h4 < 2; ++h4) {
@@ -265,28 +310,28 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
               ds[h4 * 4 + e] = pr * fmaf(__uint_as_float(rd[j]), p.scale, -dlv[e]);
             }
           }
-          const uint32_t o = off0 + sw128_off(row, (c & 1) * 4 + g);
-          pk[g * 4 + 0] = pack_bf16x2(pv[0], pv[1]);
-          pk[g * 4 + 1] = pack_bf16x2(pv[2], pv[3]);
-          pk[g * 4 + 2] = pack_bf16x2(pv[4], pv[5]);
-          pk[g * 4 + 3] = pack_bf16x2(pv[6], pv[7]);
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sdSt + o),
-                       "r"(pack_bf16x2(ds[0], ds[1])), "r"(pack_bf16x2(ds[2], ds[3])),
-                       "r"(pack_bf16x2(ds[4], ds[5])), "r"(pack_bf16x2(ds[6], ds[7]))
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            pk[g * 4 + e] = pack_bf16x2(pv[2 * e], pv[2 * e + 1]);
+            dk8[g * 4 + e] = pack_bf16x2(ds[2 * e], ds[2 * e + 1]);
+          }
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sdSt + sw128_off(row, part * 2 + g)),
+                       "r"(dk8[g * 4 + 0]), "r"(dk8[g * 4 + 1]), "r"(dk8[g * 4 + 2]), "r"(dk8[g * 4 + 3])
                        : "memory");
         }
-        tmem_st16(tPt + lane_bits + c * 16, pk);
+        tmem_st8(tSt + lane_bits + c0, pk);    // in place: the first 8 of this warp's own 16 columns
+        tmem_st8(tdPt + lane_bits + c0, dk8);
+        fence_proxy_async_smem();
+        tmem_st_wait();
+        tc_fence_before();
+        CW_ARRIVE(pds_full0 + 8 * hf);
+        if (warp == 2) TRACE(2048 + (2 * i + hf) * 4 + 3);
       }
-      fence_proxy_async_smem();
-      tmem_st_wait();
-      tc_fence_before();
-      mbar_arrive(pds_full);
-      if (i > 0) drain_dq(i - 1);  // overlaps with S^T/dP^T(i+1) and dV/dK/dQ(i) on the tensor pipe
     }
-    if (T > 0) drain_dq(T - 1);
-    if (ctid == 0) tma_store_wait_all<0>();
     // dK, dV of this key tile: each of the 4 warps of a quadrant writes 16 of the 64 head columns
     if (T > 0) {
+      mbar_wait(all_done, 0);
+      tc_fence_after();
       bf16* dkr = p.dk + ((int64_t)b * p.Nk + key) * p.lddk + h * 64 + part * 16;
       bf16* dvr = p.dv + ((int64_t)b * p.Nk + key) * p.lddv + h * 64 + part * 16;
       uint32_t rv[16], rk[16];
@@ -310,6 +355,70 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
         }
       }
     }
+  } else if (warp >= 18) {
+    // 4 drain / stat warps, one per TMEM lane quadrant (warp % 4).
+    const int quad = warp & 3;
+    const int dt = (warp - 18) * 32 + lane;  // 0..127: the query (within a tile) whose lse/delta this thread loads
+    const uint32_t lane_bits = (uint32_t)(quad * 32) << 16;
+    const float* lse_g = p.lse + ((int64_t)b * p.H + h) * p.Nq;
+    const float* del_g = p.delta + ((int64_t)b * p.H + h) * p.Nq;
+    auto load_stats = [&](int i, float& l, float& d) {  // lse -> log2 units, delta pre-scaled; padded queries: P = 0
+      const int q = ((i + kt) % T) * 128 + dt;
+      const bool ok = i < T && q < p.Nq;
+      l = ok ? lse_g[q] * kLog2eB : INFINITY;
+      d = ok ? del_g[q] * p.scale : 0.f;
+    };
+    float l0, d0, l1, d1;
+    load_stats(0, l0, d0);
+    load_stats(1, l1, d1);
+    stat[dt] = l0; stat[128 + dt] = d0;
+    DW_ARRIVE(stat_full0);
+    if (T > 1) {
+      stat[256 + dt] = l1; stat[384 + dt] = d1;
+      DW_ARRIVE(stat_full0 + 8);
+    }
+    const uint32_t stage = sStage + (warp - 18) * 8192;
+    const int row0 = quad * 32;  // first query row (within the tile) of this warp's dQ slab
+    for (int i = 0; i < T; ++i) {
+      float ln, dn;
+      load_stats(i + 2, ln, dn);  // global-load latency hidden behind the wait below
+      mbar_wait(mma2_done, i & 1);  // dQ(i) complete; every MMA and compute warp is past tile i
+      tc_fence_after();
+      if (warp == 18) TRACE(4096 + i * 4 + 0);
+      uint32_t r0[32], r1[32];
+      tmem_ld32(tdQ + lane_bits, r0);
+      tmem_ld32(tdQ + lane_bits + 32, r1);
+      tmem_ld_wait();
+      tc_fence_before();
+      DW_ARRIVE(dq_free);  // the dQ columns may be overwritten by dQ(i+1)
+      if (warp == 18) TRACE(4096 + i * 4 + 1);
+      if (i + 2 < T) {  // stat buffer i&1 was last read for tile i
+        stat[(i & 1) * 256 + dt] = ln;
+        stat[(i & 1) * 256 + 128 + dt] = dn;
+        DW_ARRIVE(stat_full0 + 8 * (i & 1));
+      }
+      if (lane == 0) tma_store_wait_read<0>();  // this warp's previous reduce-add has read its staging slab
+      __syncwarp();
+#pragma unroll
+      for (int g = 0; g < 8; ++g) {
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stage + sw128_off(lane, g)),
+                     "r"(r0[g * 4 + 0]), "r"(r0[g * 4 + 1]), "r"(r0[g * 4 + 2]), "r"(r0[g * 4 + 3])
+                     : "memory");
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stage + 4096 + sw128_off(lane, g)),
+                     "r"(r1[g * 4 + 0]), "r"(r1[g * 4 + 1]), "r"(r1[g * 4 + 2]), "r"(r1[g * 4 + 3])
+                     : "memory");
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        const int qt = (i + kt) % T;
+        tma_reduce_add_3d(&tmdQ, stage, h * 64, qt * 128 + row0, b);
+        tma_reduce_add_3d(&tmdQ, stage + 4096, h * 64 + 32, qt * 128 + row0, b);
+        tma_store_commit();
+      }
+      if (warp == 18) TRACE(4096 + i * 4 + 2);
+    }
+    if (lane == 0) tma_store_wait_all<0>();
   }
   tc_fence_before();
   __syncthreads();
@@ -324,6 +433,12 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
 using namespace b200;
 
 static inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+#ifdef B200_TRACE
+extern "C" int b200_debug_bwd_trace(unsigned long long* host, int n) {
+  return (int)cudaMemcpyFromSymbol(host, g_bwd_trace, sizeof(unsigned long long) * n);
+}
+#endif
 
 extern "C" int b200_fa_bwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v,
                            int64_t ldv, const void* dout, int64_t lddo, const float* lse,
@@ -348,7 +463,7 @@ extern "C" int b200_fa_bwd(const void* q, int64_t ldq, const void* k, int64_t ld
   {
     uint64_t dims[3] = {(uint64_t)H * 64, (uint64_t)Nq, (uint64_t)B};
     uint64_t str[2] = {(uint64_t)lddq * 4, (uint64_t)Nq * (uint64_t)lddq * 4};
-    uint32_t box[3] = {32, 128, 1};
+    uint32_t box[3] = {32, 32, 1};
     if ((rc = make_tmap(&tmdQ, dq_accum, TM_F32, 3, dims, str, box, true)))
       return arg_error("fa_bwd: cuTensorMapEncodeTiled failed (dq)", rc);
   }

@@ -210,28 +210,39 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
       tma_load_3d(sKV + s * 32768, &tmK, kv_full0 + 8 * s, h * 64, j * 128, b);
       tma_load_3d(sKV + s * 32768 + 16384, &tmV, kv_full0 + 8 * s, h * 64, j * 128, b);
     }
-  } else if (warp == 1 && lane == 0) {
+  } else if (warp == 1) {
+    // MMA warp: every lane follows the barrier waits, one elected lane issues; descriptors are constant
+    // bases plus small offsets so that the instruction stream per MMA is minimal (the issuing thread
+    // shares its scheduler with the softmax warps of both resident CTAs).
     const uint32_t idesc_qk = make_idesc_bf16(128, 128, 0, 0);
     const uint32_t idesc_pv = make_idesc_bf16(128, 64, 0, 1);
+    const uint64_t dq0 = make_smem_desc(sQ, 16, 1024), dk0 = make_smem_desc(sKV, 16, 1024),
+                   dv0 = make_smem_desc(sKV + 16384, 8192, 1024);
     mbar_wait(q_full, 0);
     for (int j = 0; j < T; ++j) {
       const int s = j & 1;
-      const uint32_t sK = sKV + s * 32768, sV = sK + 16384;
       mbar_wait(kv_full0 + 8 * s, (j >> 1) & 1);
       tc_fence_after();
+      if (elect_one()) {
+        const uint64_t dk = desc_adv(dk0, s * 32768);
 #pragma unroll
-      for (int k = 0; k < 4; ++k)
-        umma_ss(tS, make_smem_desc(sQ + k * 32, 16, 1024), make_smem_desc(sK + k * 32, 16, 1024),
-                idesc_qk, k > 0 ? 1u : 0u);
-      umma_commit(s_full);
+        for (int k = 0; k < 4; ++k)
+          umma_ss(tS, desc_adv(dq0, k * 32), desc_adv(dk, k * 32), idesc_qk, k > 0 ? 1u : 0u);
+        umma_commit(s_full);
+      }
+      __syncwarp();
       mbar_wait(p_full, j & 1);
       tc_fence_after();
+      if (elect_one()) {
+        const uint64_t dv = desc_adv(dv0, s * 32768);
+        const uint32_t acc0 = j > 0 ? 1u : 0u;
 #pragma unroll
-      for (int k = 0; k < 8; ++k)
-        umma_ts(tO, tS + k * 8, make_smem_desc(sV + k * 2048, 8192, 1024), idesc_pv,
-                (j > 0 || k > 0) ? 1u : 0u);  // A = P (bf16x2 packed, 8 TMEM columns per K=16 step)
-      umma_commit(kv_empty0 + 8 * s);
-      umma_commit(pv_done);
+        for (int k = 0; k < 8; ++k)  // A = P (bf16x2 packed, 8 TMEM columns per K=16 step)
+          umma_ts(tO, tS + k * 8, desc_adv(dv, k * 2048), idesc_pv, k > 0 ? 1u : acc0);
+        umma_commit(kv_empty0 + 8 * s);
+        umma_commit(pv_done);
+      }
+      __syncwarp();
     }
   } else if (warp >= 2) {
     const int quad = warp & 3;

@@ -270,6 +270,13 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16
       : "memory");
 }
 
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&r)[8]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+      : "memory");
+}
+
 // ---------------------------------------------------------------------------
 // UMMA descriptors
 // ---------------------------------------------------------------------------
@@ -289,6 +296,12 @@ __host__ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint
   d |= (uint64_t)2 << 61;
   return d;
 }
+// Advance the start-address field of a descriptor by `bytes` (a multiple of 16; valid while the 14-bit
+// field does not overflow, i.e. for any offset that stays inside shared memory).  One integer add per MMA
+// instead of re-encoding the descriptor: the single MMA-issuing thread shares its scheduler with busy
+// math warps, so every instruction in its stream costs several cycles of tensor-pipe idle time.
+__host__ __device__ __forceinline__ uint64_t desc_adv(uint64_t d, uint32_t bytes) { return d + (bytes >> 4); }
+
 // Instruction descriptor (kind::f16, bf16 x bf16 -> f32):
 //   [4,6) D fmt (1=F32)  [7,10) A fmt (1=BF16)  [10,13) B fmt (1=BF16)
 //   [15] A major (0=K,1=MN)  [16] B major  [17,23) N>>3  [24,29) M>>4

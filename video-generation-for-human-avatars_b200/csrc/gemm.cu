@@ -195,9 +195,17 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
       }
     }
-  } else if (warp == 1 && lane == 0) {
+  } else if (warp == 1) {
     // ------------------------------ MMA issuer --------------------------------
+    // The whole warp follows the control flow (barrier waits); one elected lane issues.  Descriptors are
+    // a per-stage base plus a constant per K step, so the issuing thread's instruction stream per MMA is
+    // a single add: it shares its scheduler with two epilogue warps and every extra instruction is
+    // tensor-pipe idle time.
     const uint32_t idesc = make_idesc_bf16(128, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
+    const uint64_t da0 = A_MN ? make_smem_desc(sbase, 8192, 1024) : make_smem_desc(sbase, 16, 1024);
+    const uint64_t db0 = B_MN ? make_smem_desc(sbase + Cfg::A_BYTES, 8192, 1024)
+                              : make_smem_desc(sbase + Cfg::A_BYTES, 16, 1024);
+    constexpr uint32_t A_STEP = A_MN ? 2048 : 32, B_STEP = B_MN ? 2048 : 32;
     int stage = 0, acc = 0;
     uint32_t phase = 0, acc_phase = 0;
     for (int work = blockIdx.x; work < total_tiles; work += gridDim.x) {
@@ -209,19 +217,19 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       for (int kb = kb_begin; kb < kb_end; ++kb) {
         mbar_wait(full_bar(stage), phase);
         tc_fence_after();
-        const uint32_t sa = sbase + stage * Cfg::STAGE, sb = sa + Cfg::A_BYTES;
+        if (elect_one()) {
+          const uint64_t da = desc_adv(da0, stage * Cfg::STAGE), db = desc_adv(db0, stage * Cfg::STAGE);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const uint64_t da = A_MN ? make_smem_desc(sa + k * 2048, 8192, 1024)
-                                   : make_smem_desc(sa + k * 32, 16, 1024);
-          const uint64_t db = B_MN ? make_smem_desc(sb + k * 2048, 8192, 1024)
-                                   : make_smem_desc(sb + k * 32, 16, 1024);
-          umma_ss(d_tmem, da, db, idesc, (kb > kb_begin || k > 0) ? 1u : 0u);
+          for (int k = 0; k < 4; ++k)
+            umma_ss(d_tmem, desc_adv(da, k * A_STEP), desc_adv(db, k * B_STEP), idesc,
+                    (kb > kb_begin || k > 0) ? 1u : 0u);
+          umma_commit(empty_bar(stage));
         }
-        umma_commit(empty_bar(stage));
+        __syncwarp();
         if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
       }
-      umma_commit(tfull_bar(acc));
+      if (elect_one()) umma_commit(tfull_bar(acc));
+      __syncwarp();
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }

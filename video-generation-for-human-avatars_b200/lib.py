@@ -9,7 +9,7 @@ from ctypes import c_char_p, c_float, c_int, c_int64, c_void_p
 import torch  # noqa: F401  (loads libcudart.so.12 that libb200ltx links against)
 
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(PKG_DIR, "libb200ltx.so")
+LIB_PATH = os.environ.get("B200LTX_LIB") or os.path.join(PKG_DIR, "libb200ltx.so")  # env override: kernel experiments
 
 P, I, L, F = c_void_p, c_int, c_int64, c_float
 
