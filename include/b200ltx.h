@@ -76,12 +76,17 @@ int b200_attn_delta(const void* o, int64_t ldo, const void* dout, int64_t lddo, 
                     int H, int Nq, void* stream);
 
 /* Flash attention backward.  dq_accum is fp32 [B*Nq, lddq] and MUST be zeroed by the caller (key-tile
- * CTAs reduce into it with red.global.add); dk/dv are bf16.  Replaces the SDPA backward autograd
- * runs under training.py:203. */
+ * CTAs reduce into it with TMA reduce-add); dk/dv are bf16.  With few key tiles (attn2: 256 caption
+ * tokens) the query walk of a key tile is split over several CTAs whose fp32 dK/dV partials go through
+ * `workspace` (caller-owned, 16-byte aligned, >= b200_fa_bwd_workspace_bytes(B,H,Nq,Nk), may be NULL
+ * when that is 0) and are summed by a second small kernel launched by the same call.
+ * Replaces the SDPA backward autograd runs under training.py:203. */
+int64_t b200_fa_bwd_workspace_bytes(int B, int H, int Nq, int Nk);
 int b200_fa_bwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,
                 const void* dout, int64_t lddo, const float* lse, const float* delta,
                 const float* key_bias, float* dq_accum, int64_t lddq, void* dk, int64_t lddk, void* dv,
-                int64_t lddv, int B, int H, int Nq, int Nk, int head_dim, float scale, void* stream);
+                int64_t lddv, int B, int H, int Nq, int Nk, int head_dim, float scale, void* workspace,
+                int64_t workspace_bytes, void* stream);
 
 /* y = norm(x) * (1 + scale[b]) + shift[b]; RMSNorm (layernorm = 0) or LayerNorm (1), no affine.
  * scale/shift: bf16 rows of D, one per `rows_per_mod` consecutive rows, `mod_stride` elements apart

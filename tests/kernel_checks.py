@@ -219,7 +219,9 @@ def _attn_ref(q, k, v, B, H, Nq, Nk, bias, scale):
 
 
 ATTN_CASES = [(1, 2, 128, 128, False), (2, 4, 96, 96, False), (1, 2, 300, 300, False), (2, 4, 96, 24, True),
-              (1, 32, 512, 256, True), (1, 4, 1024, 1024, False), (2, 3, 200, 333, True)]
+              (1, 32, 512, 256, True), (1, 4, 1024, 1024, False), (2, 3, 200, 333, True),
+              # few key tiles, many query tiles: the backward splits the query walk over several CTAs
+              (1, 4, 1100, 256, True), (1, 32, 1536, 256, True), (2, 2, 1030, 100, False)]
 
 
 def check_attention_fwd():

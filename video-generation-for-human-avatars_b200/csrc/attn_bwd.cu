@@ -54,6 +54,9 @@ struct FaBwdParams {
   bf16* dv;
   int64_t lddv;
   float scale, scale_log2;
+  int q_splits;     // > 1: the query tiles are divided among q_splits CTAs per key tile (few key tiles: attn2)
+  float* part_dk;   // [q_splits][B*Nk][H*64] fp32 partial dK / dV, summed by fa_bwd_reduce_kernel
+  float* part_dv;
 };
 
 constexpr int FA_BWD_QSTAGES = 3;
@@ -113,8 +116,11 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
                  all_done = bar + 120, kv_tmem = bar + 128, tmem_slot = bar + 136;
   float* stat = reinterpret_cast<float*>(smem_raw + (sStat - sbase));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int kt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
-  const int T = p.q_tiles;
+  const int kt = blockIdx.x, h = blockIdx.y;
+  const int b = blockIdx.z / p.q_splits, split = blockIdx.z % p.q_splits;
+  // this CTA's query tiles: [t0, t0 + T)
+  const int t0 = (int)((int64_t)split * p.q_tiles / p.q_splits);
+  const int T = (int)((int64_t)(split + 1) * p.q_tiles / p.q_splits) - t0;
 
   if (threadIdx.x == 0) {
     if (sbase & 1023u) {
@@ -163,7 +169,7 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
     for (int i = 0; i < T; ++i) {
       mbar_wait(qd_empty0 + 8 * s, ph ^ 1);
       mbar_expect_tx(qd_full0 + 8 * s, 32768);
-      const int qt = (i + kt) % T;  // staggered walk, see below
+      const int qt = t0 + (i + kt) % T;  // staggered walk, see below
       tma_load_3d(sQdO + s * 32768, &tmQ, qd_full0 + 8 * s, h * 64, qt * 128, b);
       tma_load_3d(sQdO + s * 32768 + 16384, &tmdO, qd_full0 + 8 * s, h * 64, qt * 128, b);
       if (++s == FA_BWD_QSTAGES) { s = 0; ph ^= 1; }
@@ -332,13 +338,13 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
     if (T > 0) {
       mbar_wait(all_done, 0);
       tc_fence_after();
-      bf16* dkr = p.dk + ((int64_t)b * p.Nk + key) * p.lddk + h * 64 + part * 16;
-      bf16* dvr = p.dv + ((int64_t)b * p.Nk + key) * p.lddv + h * 64 + part * 16;
       uint32_t rv[16], rk[16];
       tmem_ld16(tdV + lane_bits + part * 16, rv);
       tmem_ld16(tdK + lane_bits + part * 16, rk);
       tmem_ld_wait();
-      if (key_ok) {
+      if (key_ok && p.q_splits == 1) {
+        bf16* dkr = p.dk + ((int64_t)b * p.Nk + key) * p.lddk + h * 64 + part * 16;
+        bf16* dvr = p.dv + ((int64_t)b * p.Nk + key) * p.lddv + h * 64 + part * 16;
 #pragma unroll
         for (int g = 0; g < 2; ++g) {
           uint4 u;
@@ -353,6 +359,17 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
           u.w = pack_bf16x2(__uint_as_float(rk[g * 8 + 6]), __uint_as_float(rk[g * 8 + 7]));
           *reinterpret_cast<uint4*>(dkr + g * 8) = u;
         }
+      } else if (key_ok) {
+        const int64_t prow = ((int64_t)split * p.B + b) * p.Nk + key;
+        float4* pk4 = reinterpret_cast<float4*>(p.part_dk + prow * (p.H * 64) + h * 64 + part * 16);
+        float4* pv4 = reinterpret_cast<float4*>(p.part_dv + prow * (p.H * 64) + h * 64 + part * 16);
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          pk4[g] = make_float4(__uint_as_float(rk[g * 4]), __uint_as_float(rk[g * 4 + 1]),
+                               __uint_as_float(rk[g * 4 + 2]), __uint_as_float(rk[g * 4 + 3]));
+          pv4[g] = make_float4(__uint_as_float(rv[g * 4]), __uint_as_float(rv[g * 4 + 1]),
+                               __uint_as_float(rv[g * 4 + 2]), __uint_as_float(rv[g * 4 + 3]));
+        }
       }
     }
   } else if (warp >= 18) {
@@ -363,7 +380,7 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
     const float* lse_g = p.lse + ((int64_t)b * p.H + h) * p.Nq;
     const float* del_g = p.delta + ((int64_t)b * p.H + h) * p.Nq;
     auto load_stats = [&](int i, float& l, float& d) {  // lse -> log2 units, delta pre-scaled; padded queries: P = 0
-      const int q = ((i + kt) % T) * 128 + dt;
+      const int q = (t0 + (i + kt) % T) * 128 + dt;
       const bool ok = i < T && q < p.Nq;
       l = ok ? lse_g[q] * kLog2eB : INFINITY;
       d = ok ? del_g[q] * p.scale : 0.f;
@@ -411,7 +428,7 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) {
-        const int qt = (i + kt) % T;
+        const int qt = t0 + (i + kt) % T;
         tma_reduce_add_3d(&tmdQ, stage, h * 64, qt * 128 + row0, b);
         tma_reduce_add_3d(&tmdQ, stage + 4096, h * 64 + 32, qt * 128 + row0, b);
         tma_store_commit();
@@ -428,6 +445,40 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
   }
 }
 
+// dk/dv (bf16) = sum over the q_splits fp32 partials; 8 columns per thread.
+__global__ void __launch_bounds__(256) fa_bwd_reduce_kernel(const float* __restrict__ part_dk,
+                                                            const float* __restrict__ part_dv, bf16* dk,
+                                                            int64_t lddk, bf16* dv, int64_t lddv, int splits,
+                                                            int64_t rows, int D) {
+  const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int per_row = D / 8;
+  if (gid >= rows * per_row) return;
+  const int64_t r = gid / per_row;
+  const int c = (int)(gid % per_row) * 8;
+  float ak[8] = {0, 0, 0, 0, 0, 0, 0, 0}, av[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  for (int s = 0; s < splits; ++s) {
+    const float4* a = reinterpret_cast<const float4*>(part_dk + ((int64_t)s * rows + r) * D + c);
+    const float4* v = reinterpret_cast<const float4*>(part_dv + ((int64_t)s * rows + r) * D + c);
+    const float4 a0 = a[0], a1 = a[1], v0 = v[0], v1 = v[1];
+    ak[0] += a0.x; ak[1] += a0.y; ak[2] += a0.z; ak[3] += a0.w; ak[4] += a1.x; ak[5] += a1.y; ak[6] += a1.z; ak[7] += a1.w;
+    av[0] += v0.x; av[1] += v0.y; av[2] += v0.z; av[3] += v0.w; av[4] += v1.x; av[5] += v1.y; av[6] += v1.z; av[7] += v1.w;
+  }
+  uint4 u;
+  u.x = pack_bf16x2(ak[0], ak[1]); u.y = pack_bf16x2(ak[2], ak[3]); u.z = pack_bf16x2(ak[4], ak[5]); u.w = pack_bf16x2(ak[6], ak[7]);
+  *reinterpret_cast<uint4*>(dk + r * lddk + c) = u;
+  u.x = pack_bf16x2(av[0], av[1]); u.y = pack_bf16x2(av[2], av[3]); u.z = pack_bf16x2(av[4], av[5]); u.w = pack_bf16x2(av[6], av[7]);
+  *reinterpret_cast<uint4*>(dv + r * lddv + c) = u;
+}
+
+// How many CTAs share one key tile's query walk: enough to cover the SMs when there are few key tiles.
+static int fa_bwd_splits(int B, int H, int Nq, int Nk) {
+  const int64_t ctas = (int64_t)((Nk + 127) / 128) * H * B;
+  const int T = (Nq + 127) / 128;
+  if (ctas <= 0 || ctas >= 120 || T < 8) return 1;
+  int s = (int)(148 / ctas);  // one wave: never more CTAs than SMs
+  return s > T / 4 ? (T / 4 > 0 ? T / 4 : 1) : s;
+}
+
 }  // namespace b200
 
 using namespace b200;
@@ -440,11 +491,18 @@ extern "C" int b200_debug_bwd_trace(unsigned long long* host, int n) {
 }
 #endif
 
+extern "C" int64_t b200_fa_bwd_workspace_bytes(int B, int H, int Nq, int Nk) {
+  if (B <= 0 || H <= 0 || Nq <= 0 || Nk <= 0) return 0;
+  const int s = fa_bwd_splits(B, H, Nq, Nk);
+  return s > 1 ? (int64_t)2 * s * B * Nk * H * 64 * (int64_t)sizeof(float) : 0;
+}
+
 extern "C" int b200_fa_bwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v,
                            int64_t ldv, const void* dout, int64_t lddo, const float* lse,
                            const float* delta, const float* key_bias, float* dq_accum, int64_t lddq,
                            void* dk, int64_t lddk, void* dv, int64_t lddv, int B, int H, int Nq, int Nk,
-                           int head_dim, float scale, void* stream) {
+                           int head_dim, float scale, void* workspace, int64_t workspace_bytes,
+                           void* stream) {
   if (!(q && k && v && dout && lse && delta && dq_accum && dk && dv)) return arg_error("fa_bwd: null pointer");
   if (head_dim != 64) return arg_error("fa_bwd: only head_dim 64 is built (LTXV-2B: 32 heads x 64)");
   if (B < 0 || H <= 0 || Nq < 0 || Nk < 0) return arg_error("fa_bwd: bad shape");
@@ -474,13 +532,27 @@ extern "C" int b200_fa_bwd(const void* q, int64_t ldq, const void* k, int64_t ld
   p.dq = dq_accum; p.lddq = lddq;
   p.dk = (bf16*)dk; p.lddk = lddk; p.dv = (bf16*)dv; p.lddv = lddv;
   p.scale = scale; p.scale_log2 = scale * kLog2eB;
+  p.q_splits = fa_bwd_splits(B, H, Nq, Nk);
+  p.part_dk = p.part_dv = nullptr;
+  if (p.q_splits > 1) {
+    const int64_t need = b200_fa_bwd_workspace_bytes(B, H, Nq, Nk);
+    if (!workspace || workspace_bytes < need || !al16(workspace))
+      return arg_error("fa_bwd: workspace too small (see b200_fa_bwd_workspace_bytes)");
+    p.part_dk = (float*)workspace;
+    p.part_dv = p.part_dk + (int64_t)p.q_splits * B * Nk * H * 64;
+  }
   static bool attr_set = false;
   if (!attr_set) {
     if (cudaFuncSetAttribute(fa_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_BWD_SMEM) != cudaSuccess)
       return launch_status("fa_bwd: cudaFuncSetAttribute");
     attr_set = true;
   }
-  dim3 grid((Nk + 127) / 128, H, B);
+  dim3 grid((Nk + 127) / 128, H, B * p.q_splits);
   fa_bwd_kernel<<<grid, FA_BWD_THREADS, FA_BWD_SMEM, (cudaStream_t)stream>>>(tmQ, tmK, tmV, tmdO, tmdQ, p);
+  if (p.q_splits > 1) {
+    const int64_t rows = (int64_t)B * Nk, threads = rows * (H * 64 / 8);
+    fa_bwd_reduce_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        p.part_dk, p.part_dv, (bf16*)dk, lddk, (bf16*)dv, lddv, p.q_splits, rows, H * 64);
+  }
   return launch_status("fa_bwd");
 }

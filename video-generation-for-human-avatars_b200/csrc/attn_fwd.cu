@@ -9,14 +9,19 @@
 // projection GEMMs write, so no head split/merge copies exist.  TMA reads 128x64 tiles straight
 // out of that layout with a 3-D tensor map (col, token, batch).
 //
-// One CTA = one 128-query tile of one head; two CTAs are resident per SM so one CTA's softmax
-// overlaps the other's MMAs.  Warp roles:
-//   warp 0 lane 0 : TMA producer (Q once; K/V tiles double-buffered)
-//   warp 1        : TMEM allocator; lane 0 issues tcgen05.mma  S = Q K^T (128x128x64) and
-//                   O += P V (128x64x128; V is the MN-major B operand)
-//   warps 2..5    : softmax, one query row per thread: tcgen05.ld S, running max with lazy
-//                   rescale (only when the max grows by > 2^8), exp2, P -> shared memory (bf16,
-//                   128B-swizzled K-major A operand), O rescale through tcgen05.ld/st.
+// One CTA = one 128-query tile of one head; two CTAs are resident per SM.  At head_dim 64 the kernel is
+// bound by the exp unit (16 ex2/clk/SM = 1024 clk per 128x128 tile against 512 clk of MMA), so the
+// design goal is that the four softmax warps never wait for the tensor pipe:
+//   warp 0 lane 0 : TMA producer (Q once; K/V tiles through a 3-stage ring)
+//   warp 1        : TMEM allocator + MMA issue (one elected lane): S = Q K^T (128x128x64) and
+//                   O += P V in two 64-key halves (V is the MN-major B operand, P the TMEM A operand)
+//   warps 2..5    : softmax, one query row per thread.  The 128 scores of the row are read out of TMEM
+//                   ONCE into registers and the S columns are handed back immediately, so Q K^T of the
+//                   next tile runs underneath the exponentials of this one.  Row max (3-input max),
+//                   lazy rescale (only when the running max grows by > 2^8), exp2, and P goes to its own
+//                   64 TMEM columns half by half; P V of the first half is issued while the second half
+//                   is still being exponentiated.
+// TMEM (256 columns per CTA): S 128 | O 64 | P 64 (bf16x2 packed: keys 0-63 | keys 64-127).
 #include "api_internal.h"
 #include "common.cuh"
 #include "tmap.h"
@@ -32,8 +37,10 @@ struct FaFwdParams {
   float scale_log2;       // softmax scale * log2(e)
 };
 
-constexpr int FA_SMEM_TILES = 16384 /*Q*/ + 2 * 32768 /*K,V x2*/ + 32768 /*P*/;
-constexpr int FA_FWD_SMEM = FA_SMEM_TILES + 128;
+constexpr int FA_KV_STAGES = 3;
+constexpr int FA_SMEM_TILES = 16384 /*Q*/ + FA_KV_STAGES * 32768 /*K,V*/;
+constexpr int FA_FWD_SMEM = FA_SMEM_TILES + 128 + 512;  // + barriers + 128 staged key-bias floats (2 CTAs/SM: <= 115712)
+static_assert(2 * (FA_FWD_SMEM + 1024) <= 233472, "two fa_fwd CTAs must fit one SM");
 constexpr float kLog2e = 1.4426950408889634f;
 
 __device__ __forceinline__ float ex2_approx(float x) {
@@ -41,121 +48,56 @@ __device__ __forceinline__ float ex2_approx(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
-
-
-// ---- fast path (no key bias, full tile): the per-element code is FMNMX / FFMA+MUFU+FADD only.  The
-// next 32-column TMEM chunk is in flight while the current one is processed.
-__device__ __forceinline__ float tile_max_fast(uint32_t t_row, float sl2) {
-  float a0 = -INFINITY, a1 = -INFINITY, a2 = -INFINITY, a3 = -INFINITY;
-  uint32_t ra[32], rb[32];
-  tmem_ld32(t_row, ra);
-  tmem_ld_wait();
-#pragma unroll
-  for (int c = 0; c < 4; ++c) {
-    uint32_t(&cur)[32] = (c & 1) ? rb : ra;
-    uint32_t(&nxt)[32] = (c & 1) ? ra : rb;
-    if (c < 3) tmem_ld32(t_row + (c + 1) * 32, nxt);
-#pragma unroll
-    for (int i = 0; i < 32; i += 4) {
-      a0 = fmaxf(a0, __uint_as_float(cur[i]));
-      a1 = fmaxf(a1, __uint_as_float(cur[i + 1]));
-      a2 = fmaxf(a2, __uint_as_float(cur[i + 2]));
-      a3 = fmaxf(a3, __uint_as_float(cur[i + 3]));
-    }
-    if (c < 3) tmem_ld_wait();
-  }
-  return fmaxf(fmaxf(a0, a1), fmaxf(a2, a3)) * sl2;
+__device__ __forceinline__ float max3(float a, float b, float c) {
+  float y;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(y) : "f"(a), "f"(b), "f"(c));
+  return y;
 }
 
-__device__ __forceinline__ void store_p8(uint32_t addr, const float (&pv)[8]) {
-  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pack_bf16x2(pv[0], pv[1])),
-               "r"(pack_bf16x2(pv[2], pv[3])), "r"(pack_bf16x2(pv[4], pv[5])),
-               "r"(pack_bf16x2(pv[6], pv[7]))
-               : "memory");
-}
-
-__device__ __forceinline__ void tile_exp_fast(uint32_t t_row, float sl2, float neg_m, float& l0, float& l1,
-                                              float& l2, float& l3) {
-  uint32_t ra[32], rb[32];
-  tmem_ld32(t_row, ra);
-  tmem_ld_wait();
+// max over one 32-column chunk held in registers, folded into four running accumulators
+__device__ __forceinline__ void chunk_max(const uint32_t (&r)[32], float& a0, float& a1, float& a2, float& a3) {
 #pragma unroll
-  for (int c = 0; c < 4; ++c) {
-    uint32_t(&cur)[32] = (c & 1) ? rb : ra;
-    uint32_t(&nxt)[32] = (c & 1) ? ra : rb;
-    if (c < 3) tmem_ld32(t_row + (c + 1) * 32, nxt);
-    // P chunk c (32 keys -> 16 packed bf16x2 columns) overwrites S columns [16c, 16c+16), which belong
-    // to S chunk c/2 <= c and have already been read.
-    uint32_t pk[16];
-#pragma unroll
-    for (int g = 0; g < 4; ++g) {
-      float pv[8];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) pv[i] = ex2_approx(fmaf(__uint_as_float(cur[g * 8 + i]), sl2, neg_m));
-      l0 += pv[0] + pv[4];
-      l1 += pv[1] + pv[5];
-      l2 += pv[2] + pv[6];
-      l3 += pv[3] + pv[7];
-      pk[g * 4 + 0] = pack_bf16x2(pv[0], pv[1]);
-      pk[g * 4 + 1] = pack_bf16x2(pv[2], pv[3]);
-      pk[g * 4 + 2] = pack_bf16x2(pv[4], pv[5]);
-      pk[g * 4 + 3] = pack_bf16x2(pv[6], pv[7]);
-    }
-    if (c < 3) tmem_ld_wait();  // chunk c+1 is in registers before any column it covers could be reused
-    tmem_st16(t_row + c * 16, pk);
+  for (int i = 0; i < 32; i += 8) {
+    a0 = max3(a0, __uint_as_float(r[i + 0]), __uint_as_float(r[i + 1]));
+    a1 = max3(a1, __uint_as_float(r[i + 2]), __uint_as_float(r[i + 3]));
+    a2 = max3(a2, __uint_as_float(r[i + 4]), __uint_as_float(r[i + 5]));
+    a3 = max3(a3, __uint_as_float(r[i + 6]), __uint_as_float(r[i + 7]));
   }
 }
 
-// ---- general path (additive key bias and/or ragged last tile): kept out of line so that it does not
-// weigh on the fast path's registers.
-__device__ __noinline__ float tile_max_general(uint32_t t_row, float sl2, const float* kb, int key0, int Nk) {
-  float mx = -INFINITY;
-#pragma unroll 1
-  for (int c = 0; c < 4; ++c) {
-    uint32_t r[32];
-    tmem_ld32(t_row + c * 32, r);
-    tmem_ld_wait();
+// P = exp2(s * mul + neg_m) for one 32-column chunk -> 16 packed bf16x2 TMEM columns; row sum into l0..l3
+__device__ __forceinline__ void chunk_exp(const uint32_t (&r)[32], float mul, float neg_m, uint32_t t_dst,
+                                          float& l0, float& l1, float& l2, float& l3) {
+  uint32_t pk[16];
 #pragma unroll
-    for (int i = 0; i < 32; ++i) {
-      const int key = key0 + c * 32 + i;
-      float sc = __uint_as_float(r[i]) * sl2;
-      if (kb != nullptr && key < Nk) sc += __ldg(kb + key) * kLog2e;
-      if (key >= Nk) sc = -INFINITY;
-      mx = fmaxf(mx, sc);
-    }
+  for (int g = 0; g < 4; ++g) {
+    float pv[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) pv[i] = ex2_approx(fmaf(__uint_as_float(r[g * 8 + i]), mul, neg_m));
+    l0 += pv[0] + pv[4];
+    l1 += pv[1] + pv[5];
+    l2 += pv[2] + pv[6];
+    l3 += pv[3] + pv[7];
+    pk[g * 4 + 0] = pack_bf16x2(pv[0], pv[1]);
+    pk[g * 4 + 1] = pack_bf16x2(pv[2], pv[3]);
+    pk[g * 4 + 2] = pack_bf16x2(pv[4], pv[5]);
+    pk[g * 4 + 3] = pack_bf16x2(pv[6], pv[7]);
   }
-  return mx;
+  tmem_st16(t_dst, pk);
 }
 
-__device__ __noinline__ float tile_exp_general(uint32_t t_row, float sl2, float neg_m, const float* kb,
-                                               int key0, int Nk) {
-  float l = 0.f;
-#pragma unroll 1
-  for (int c = 0; c < 4; ++c) {
-    uint32_t r[32];
-    tmem_ld32(t_row + c * 32, r);
-    tmem_ld_wait();
-    uint32_t pk[16];
+// bias path: x = s * sl2 + (bias * log2e | -inf past Nk), in place (the staged per-key terms are read
+// back from shared memory with broadcast LDS.128)
+__device__ __forceinline__ void chunk_add_bias(uint32_t (&r)[32], float sl2, const float* kbs) {
+  const float4* kb4 = reinterpret_cast<const float4*>(kbs);
 #pragma unroll
-    for (int g = 0; g < 4; ++g) {
-      float pv[8];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int key = key0 + c * 32 + g * 8 + i;
-        float x = __uint_as_float(r[g * 8 + i]) * sl2;
-        if (kb != nullptr && key < Nk) x += __ldg(kb + key) * kLog2e;
-        if (key >= Nk) x = -INFINITY;
-        pv[i] = ex2_approx(x + neg_m);
-        l += pv[i];
-      }
-      pk[g * 4 + 0] = pack_bf16x2(pv[0], pv[1]);
-      pk[g * 4 + 1] = pack_bf16x2(pv[2], pv[3]);
-      pk[g * 4 + 2] = pack_bf16x2(pv[4], pv[5]);
-      pk[g * 4 + 3] = pack_bf16x2(pv[6], pv[7]);
-    }
-    tmem_st16(t_row + c * 16, pk);
+  for (int i = 0; i < 8; ++i) {
+    const float4 bb = kb4[i];
+    r[4 * i + 0] = __float_as_uint(fmaf(__uint_as_float(r[4 * i + 0]), sl2, bb.x));
+    r[4 * i + 1] = __float_as_uint(fmaf(__uint_as_float(r[4 * i + 1]), sl2, bb.y));
+    r[4 * i + 2] = __float_as_uint(fmaf(__uint_as_float(r[4 * i + 2]), sl2, bb.z));
+    r[4 * i + 3] = __float_as_uint(fmaf(__uint_as_float(r[4 * i + 3]), sl2, bb.w));
   }
-  return l;
 }
 
 __global__ void __launch_bounds__(192, 2)
@@ -163,10 +105,12 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
               const __grid_constant__ CUtensorMap tmV, const __grid_constant__ FaFwdParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t sbase = smem_u32(smem_raw);
-  const uint32_t sQ = sbase, sKV = sbase + 16384, sP = sbase + 16384 + 65536;
-  const uint32_t bar = sP + 32768;
-  const uint32_t q_full = bar, kv_full0 = bar + 8, kv_empty0 = bar + 24, s_full = bar + 40,
-                 p_full = bar + 48, pv_done = bar + 56, tmem_slot = bar + 64;
+  const uint32_t sQ = sbase, sKV = sbase + 16384;
+  const uint32_t bar = sKV + FA_KV_STAGES * 32768;
+  const uint32_t q_full = bar, kv_full0 = bar + 8, kv_empty0 = bar + 32, s_full = bar + 56, s_free = bar + 64,
+                 pa_full = bar + 72, pb_full = bar + 80, pva_done = bar + 88, pv_done = bar + 96,
+                 tmem_slot = bar + 104;
+  float* kb_stage = reinterpret_cast<float*>(smem_raw + (bar + 128 - sbase));  // [128] per-key term of the current tile
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int qt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
   const int T = p.kv_tiles;
@@ -180,12 +124,15 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
     tma_prefetch_desc(&tmK);
     tma_prefetch_desc(&tmV);
     mbar_init(q_full, 1);
-    for (int s = 0; s < 2; ++s) {
+    for (int s = 0; s < FA_KV_STAGES; ++s) {
       mbar_init(kv_full0 + 8 * s, 1);
       mbar_init(kv_empty0 + 8 * s, 1);
     }
     mbar_init(s_full, 1);
-    mbar_init(p_full, 128);
+    mbar_init(s_free, 128);
+    mbar_init(pa_full, 128);
+    mbar_init(pb_full, 128);
+    mbar_init(pva_done, 1);
     mbar_init(pv_done, 1);
     fence_barrier_init();
   }
@@ -198,17 +145,19 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
-  const uint32_t tS = tmem_base, tO = tmem_base + 128;
+  const uint32_t tS = tmem_base, tO = tmem_base + 128, tP = tmem_base + 192;
 
   if (warp == 0 && lane == 0) {
     mbar_expect_tx(q_full, 16384);
     tma_load_3d(sQ, &tmQ, q_full, h * 64, qt * 128, b);
+    int s = 0;
+    uint32_t ph = 0;
     for (int j = 0; j < T; ++j) {
-      const int s = j & 1;
-      mbar_wait(kv_empty0 + 8 * s, ((j >> 1) & 1) ^ 1);
+      mbar_wait(kv_empty0 + 8 * s, ph ^ 1);
       mbar_expect_tx(kv_full0 + 8 * s, 32768);
       tma_load_3d(sKV + s * 32768, &tmK, kv_full0 + 8 * s, h * 64, j * 128, b);
       tma_load_3d(sKV + s * 32768 + 16384, &tmV, kv_full0 + 8 * s, h * 64, j * 128, b);
+      if (++s == FA_KV_STAGES) { s = 0; ph ^= 1; }
     }
   } else if (warp == 1) {
     // MMA warp: every lane follows the barrier waits, one elected lane issues; descriptors are constant
@@ -219,30 +168,47 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
     const uint64_t dq0 = make_smem_desc(sQ, 16, 1024), dk0 = make_smem_desc(sKV, 16, 1024),
                    dv0 = make_smem_desc(sKV + 16384, 8192, 1024);
     mbar_wait(q_full, 0);
-    for (int j = 0; j < T; ++j) {
-      const int s = j & 1;
-      mbar_wait(kv_full0 + 8 * s, (j >> 1) & 1);
+    int s = 0, sn = 0;          // ring stage of tile j (PV) and of the next S = Q K^T to issue
+    uint32_t phn = 0;
+    auto issue_qk = [&](int j) {  // S(j) = Q K(j)^T; the softmax warps have read S(j-1) out of TMEM
+      mbar_wait(kv_full0 + 8 * sn, phn);
+      if (j > 0) mbar_wait(s_free, (j - 1) & 1);
       tc_fence_after();
       if (elect_one()) {
-        const uint64_t dk = desc_adv(dk0, s * 32768);
+        const uint64_t dk = desc_adv(dk0, sn * 32768);
 #pragma unroll
         for (int k = 0; k < 4; ++k)
           umma_ss(tS, desc_adv(dq0, k * 32), desc_adv(dk, k * 32), idesc_qk, k > 0 ? 1u : 0u);
         umma_commit(s_full);
       }
       __syncwarp();
-      mbar_wait(p_full, j & 1);
+      if (++sn == FA_KV_STAGES) { sn = 0; phn ^= 1; }
+    };
+    if (T > 0) issue_qk(0);
+    for (int j = 0; j < T; ++j) {
+      if (j + 1 < T) issue_qk(j + 1);  // runs underneath the exponentials of tile j
+      const uint64_t dv = desc_adv(dv0, s * 32768);
+      mbar_wait(pa_full, j & 1);
       tc_fence_after();
       if (elect_one()) {
-        const uint64_t dv = desc_adv(dv0, s * 32768);
         const uint32_t acc0 = j > 0 ? 1u : 0u;
 #pragma unroll
-        for (int k = 0; k < 8; ++k)  // A = P (bf16x2 packed, 8 TMEM columns per K=16 step)
-          umma_ts(tO, tS + k * 8, desc_adv(dv, k * 2048), idesc_pv, k > 0 ? 1u : acc0);
+        for (int k = 0; k < 4; ++k)  // keys 0..63: A = P (bf16x2 packed, 8 TMEM columns per K=16 step)
+          umma_ts(tO, tP + k * 8, desc_adv(dv, k * 2048), idesc_pv, k > 0 ? 1u : acc0);
+        umma_commit(pva_done);
+      }
+      __syncwarp();
+      mbar_wait(pb_full, j & 1);
+      tc_fence_after();
+      if (elect_one()) {
+#pragma unroll
+        for (int k = 4; k < 8; ++k)  // keys 64..127
+          umma_ts(tO, tP + k * 8, desc_adv(dv, k * 2048), idesc_pv, 1u);
         umma_commit(kv_empty0 + 8 * s);
         umma_commit(pv_done);
       }
       __syncwarp();
+      if (++s == FA_KV_STAGES) s = 0;
     }
   } else if (warp >= 2) {
     const int quad = warp & 3;
@@ -255,23 +221,50 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
     for (int j = 0; j < T; ++j) {
       const int key0 = j * 128;
       const bool general = (kb != nullptr) || (key0 + 128 > p.Nk);  // bias or ragged last tile
+      if (general) {
+        // stage this tile's per-key term (first barrier: everyone has finished reading the previous tile's)
+        named_bar_sync(1, 128);
+        const int key = key0 + row;
+        kb_stage[row] = key < p.Nk ? (kb ? kb[key] * kLog2e : 0.f) : -INFINITY;
+        named_bar_sync(1, 128);
+      }
       mbar_wait(s_full, j & 1);
       tc_fence_after();
-      // pass 1: row max
-      const float mx = general ? tile_max_general(tS + lane_bits, sl2, kb, key0, p.Nk)
-                               : tile_max_fast(tS + lane_bits, sl2);
+      // the whole row of scores -> registers, then give the S columns back to the tensor pipe
+      uint32_t r0[32], r1[32], r2[32], r3[32];
+      tmem_ld32(tS + lane_bits, r0);
+      tmem_ld32(tS + lane_bits + 32, r1);
+      tmem_ld32(tS + lane_bits + 64, r2);
+      tmem_ld32(tS + lane_bits + 96, r3);
+      tmem_ld_wait();
+      tc_fence_before();
+      mbar_arrive(s_free);
+      float mul = sl2;  // scores are scaled inside the exp FFMA ...
+      if (general) {    // ... except on the bias path, where x = s * sl2 + bias is formed in place
+        chunk_add_bias(r0, sl2, kb_stage);
+        chunk_add_bias(r1, sl2, kb_stage + 32);
+        chunk_add_bias(r2, sl2, kb_stage + 64);
+        chunk_add_bias(r3, sl2, kb_stage + 96);
+        mul = 1.f;
+      }
+      float a0 = -INFINITY, a1 = -INFINITY, a2 = -INFINITY, a3 = -INFINITY;
+      chunk_max(r0, a0, a1, a2, a3);
+      chunk_max(r1, a0, a1, a2, a3);
+      chunk_max(r2, a0, a1, a2, a3);
+      chunk_max(r3, a0, a1, a2, a3);
+      const float mx = fmaxf(fmaxf(a0, a1), fmaxf(a2, a3)) * mul;
       const float m_new = fmaxf(m_used, mx);
       const bool need = m_new > m_used + 8.f;
-      const bool warp_need = __any_sync(0xffffffffu, need);
-      if (j > 0) {
-        mbar_wait(pv_done, (j - 1) & 1);  // PV_{j-1} finished: P buffer free, O consistent
-        tc_fence_after();
-      }
-      if (warp_need) {
+      bool pv_waited = false;
+      if (__any_sync(0xffffffffu, need)) {
+        // lazy rescale: O and l follow the running max only when it has grown by more than 2^8
         const float alpha = ex2_approx(m_used - m_new);  // 0 on the first tile (m_used = -inf)
         m_used = m_new;
         l0 *= alpha; l1 *= alpha; l2 *= alpha; l3 *= alpha;
         if (j > 0) {
+          mbar_wait(pv_done, (j - 1) & 1);  // P V(j-1) finished: O is consistent and idle
+          pv_waited = true;
+          tc_fence_after();
 #pragma unroll 1
           for (int c = 0; c < 2; ++c) {
             uint32_t r[32];
@@ -284,14 +277,23 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
           tmem_st_wait();
         }
       }
-      // pass 2: P = exp2(s * c - m), row sum, bf16 P into the swizzled A-operand tile
-      if (general)
-        l0 += tile_exp_general(tS + lane_bits, sl2, -m_used, kb, key0, p.Nk);
-      else
-        tile_exp_fast(tS + lane_bits, sl2, -m_used, l0, l1, l2, l3);
+      const float neg_m = -m_used;
+      // keys 0..63: P V(j-1) of the same half was issued half a tile ago
+      if (j > 0) mbar_wait(pva_done, (j - 1) & 1);
+      tc_fence_after();
+      chunk_exp(r0, mul, neg_m, tP + lane_bits, l0, l1, l2, l3);
+      chunk_exp(r1, mul, neg_m, tP + lane_bits + 16, l0, l1, l2, l3);
       tmem_st_wait();
       tc_fence_before();
-      mbar_arrive(p_full);
+      mbar_arrive(pa_full);
+      // keys 64..127
+      if (j > 0 && !pv_waited) mbar_wait(pv_done, (j - 1) & 1);
+      tc_fence_after();
+      chunk_exp(r2, mul, neg_m, tP + lane_bits + 32, l0, l1, l2, l3);
+      chunk_exp(r3, mul, neg_m, tP + lane_bits + 48, l0, l1, l2, l3);
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(pb_full);
     }
     const float l = (l0 + l1) + (l2 + l3);
     // epilogue: O / l -> bf16, lse

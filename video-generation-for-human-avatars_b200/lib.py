@@ -22,7 +22,8 @@ PROTOTYPES = {
     "b200_fa_fwd": (I, [P, L, P, L, P, L, P, L, P, P, I, I, I, I, I, F, P]),
     "b200_attn_merge": (I, [P, L, P, P, L, P, P, L, I, I, I, I, P]),
     "b200_attn_delta": (I, [P, L, P, L, P, I, I, I, P]),
-    "b200_fa_bwd": (I, [P, L, P, L, P, L, P, L, P, P, P, P, L, P, L, P, L, I, I, I, I, I, F, P]),
+    "b200_fa_bwd_workspace_bytes": (L, [I, I, I, I]),
+    "b200_fa_bwd": (I, [P, L, P, L, P, L, P, L, P, P, P, P, L, P, L, P, L, I, I, I, I, I, F, P, L, P]),
     "b200_norm_mod_fwd": (I, [P, L, P, L, P, P, L, L, I, L, F, I, P]),
     "b200_norm_mod_bwd": (I, [P, L, P, L, P, L, P, L, P, L, L, I, L, F, I, P]),
     "b200_qknorm_rope_fwd": (I, [P, L, P, L, P, P, P, P, L, P, L, P, L, L, L, I, F, P]),
