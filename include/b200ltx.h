@@ -55,6 +55,19 @@ int b200_gemm_bf16(const void* A, int64_t lda, int a_rows_are_k, const void* B, 
                    const void* res, int64_t ldres, void* aux, int64_t ldaux, int block_n,
                    int split_k, void* stream);
 
+/* Strided batch of `groups` identically shaped GEMMs in ONE launch:  C_g[M,N] = A_g * B_g^T (+ A2_g * B2_g^T)
+ * (+ bias_g).  Operand g is the sub-block of the given tensor displaced by g * (rows, cols) elements;
+ * `group_offsets` is a HOST array of 11 ints {a_rows, a_cols, b_rows, b_cols, a2_rows, a2_cols, b2_rows,
+ * b2_cols, c_rows, c_cols, bias}.  Per-group M, N, K, K2 must be multiples of 128, block_n, 64, 64 (tiles
+ * never straddle sub-blocks).  Used for everything on the attn2 key/value side that depends only on the
+ * projected caption tokens and can therefore run once for all 28 blocks (reference: the per-block
+ * to_k / to_v nn.Linear + peft LoRA calls, attention.py:999-1005). */
+int b200_gemm_bf16_batched(const void* A, int64_t lda, int a_rows_are_k, const void* B, int64_t ldb,
+                           int b_rows_are_k, const void* A2, int64_t lda2, const void* B2, int64_t ldb2,
+                           int K2, void* C, int64_t ldc, int out_is_f32, int M, int N, int K,
+                           const void* bias, int block_n, int groups, const int32_t* group_offsets,
+                           void* stream);
+
 /* Flash attention forward, head_dim 64, non-causal.  q/k/v/o token-major [B*N, ld], head h in
  * columns [64h, 64h+64).  key_bias: optional fp32 [B,Nk] additive score bias (the -10000 mask bias).
  * lse: optional fp32 [B,H,Nq] log-sum-exp for the backward.

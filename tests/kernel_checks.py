@@ -48,6 +48,40 @@ def check_gemm_layouts():
                     bb = b.t().contiguous() if b_k else b
                     out = ops.gemm(aa, bb, a_rows_are_k=a_k, b_rows_are_k=b_k, block_n=bn)
                     _assert_close(f"gemm {M}x{N}x{K} bn={bn} aK={int(a_k)} bK={int(b_k)}", out, ref, 6e-3)
+    # wgrad form with a ragged reduction (token count not a multiple of 8, nor of the 64-row k block)
+    for (M, N, K) in [(64, 2048, 210), (2048, 64, 105), (128, 136, 3)]:
+        a, b = _randn(K, M, seed=3), _randn(K, N, seed=4)
+        out = ops.gemm(a, b, a_rows_are_k=True, b_rows_are_k=True, out_dtype=torch.float32)
+        _assert_close(f"gemm [K,M]x[K,N] ragged K {M}x{N}x{K}", out, a.float().t() @ b.float(), 6e-3)
+    torch.cuda.synchronize()
+
+
+def check_gemm_batched():
+    """Strided-batch GEMM (one launch, G sub-block problems) vs per-group torch matmuls, in the four operand
+    arrangements CtxKVFn uses."""
+    from b200_ltx import ops
+    G, M, D, Dc, R = 5, 256, 512, 320, 64
+    x = _randn(M, Dc, seed=1, scale=0.5)
+    W = _randn(G * D, Dc, seed=2, scale=0.1)
+    bias = _randn(G * D, seed=3)
+    t = _randn(M, G * R, seed=4, scale=0.3)
+    sB = _randn(G * D, R, seed=5, scale=0.1)
+    kv = torch.empty(M, G * D, device="cuda", dtype=BF16)
+    ops.gemm_batched(x, W, kv, M, D, Dc, G, {"b": (D, 0), "a2": (0, R), "b2": (D, 0), "c": (0, D), "bias": D}, a2=t, b2=sB,
+                     K2=R, bias=bias)
+    ref = torch.cat([x.float() @ W[g * D:(g + 1) * D].float().T + bias[g * D:(g + 1) * D].float()
+                     + t[:, g * R:(g + 1) * R].float() @ sB[g * D:(g + 1) * D].float().T for g in range(G)], dim=1)
+    _assert_close("batched fwd (bias + second pair)", kv, ref, 6e-3)
+    dkv = _randn(M, G * D, seed=6, scale=0.2)
+    dt = torch.empty(M, G * R, device="cuda", dtype=BF16)
+    ops.gemm_batched(dkv, sB, dt, M, R, D, G, {"a": (0, D), "b": (D, 0), "c": (0, R)}, b_rows_are_k=True, block_n=64)
+    ref = torch.cat([dkv[:, g * D:(g + 1) * D].float() @ sB[g * D:(g + 1) * D].float() for g in range(G)], dim=1)
+    _assert_close("batched dt (A cols / B rows displaced)", dt, ref, 6e-3)
+    dB = torch.empty(G * D, R, device="cuda", dtype=torch.float32)
+    ops.gemm_batched(dkv, t, dB, D, R, M, G, {"a": (0, D), "b": (0, R), "c": (D, 0)}, a_rows_are_k=True, b_rows_are_k=True,
+                     block_n=64)
+    ref = torch.cat([dkv[:, g * D:(g + 1) * D].float().T @ t[:, g * R:(g + 1) * R].float() for g in range(G)], dim=0)
+    _assert_close("batched dB ([K,M] x [K,N], fp32 out, rows displaced)", dB, ref, 6e-3)
     torch.cuda.synchronize()
 
 
@@ -378,6 +412,7 @@ def check_rf_and_misc():
 GROUPS = {
     "gemm_layouts": check_gemm_layouts,
     "gemm_epilogues": check_gemm_epilogues,
+    "gemm_batched": check_gemm_batched,
     "linear_fn": check_linear_fn,
     "norm_mod": check_norm_mod,
     "qknorm_rope": check_qknorm_rope,

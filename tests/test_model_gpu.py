@@ -36,6 +36,18 @@ def test_full_width_two_blocks():
 
 
 @pytest.mark.gpu
+def test_batched_caption_kv_path():
+    """(B * caption tokens) % 128 == 0 and D % 256 == 0: the attn2 keys / values of all blocks come from one
+    strided-batched projection (ops.CtxKVFn) -- 3 blocks, 2 x 64 caption tokens with 40 valid, ragged latents."""
+    cfg = dict(rb.LTXV_2B, num_layers=3, num_attention_heads=4, cross_attention_dim=256, caption_channels=64)
+    case = dict(b=2, f=3, h=5, w=7, n_ctx=64, valid_ctx=40, lora_rank=32, seed_w=4, seed_x=11, t=[0.3, 0.8])
+    from b200_ltx import ops
+    before = ops.launch_count
+    mc.run_parity(cfg, case)
+    assert ops.launch_count > before
+
+
+@pytest.mark.gpu
 def test_zero_init_lora_b_matches_step0_state():
     """peft's real step-0 state: B = 0 => every lora_A grad is exactly 0, lora_B grads are not."""
     cfg = dict(rb.LTXV_2B, num_layers=1, num_attention_heads=4, cross_attention_dim=256, caption_channels=64)

@@ -42,6 +42,10 @@ struct GemmParams {
   bf16* aux;
   int64_t ldaux;
   int tma_store;  // bf16 outputs (C, and the GELU pre-activation) leave through smem staging + TMA stores
+  // strided batch: work item (tile, g) reads / writes sub-blocks displaced by g * (rows, cols) inside the
+  // operand tensors (groups == 1: plain GEMM).  Offsets are in elements of the tensor as stored.
+  int groups;
+  int a_gr, a_gc, b_gr, b_gc, a2_gr, a2_gc, b2_gr, b2_gc, c_gr, c_gc, bias_g;
 };
 
 __device__ __forceinline__ float tanh_fast(float x) {
@@ -64,9 +68,10 @@ __device__ __forceinline__ float gelu_tanh_grad(float x) {
 // Fused epilogue math on 8 consecutive columns of one output row: + bias -> GELU (on the bf16-rounded
 // pre-activation, which is returned in `pre`) / GELU' -> * gate -> + residual.
 __device__ __forceinline__ void epi_math8(float (&v)[8], uint4& pre, int n, bool ld_ok, const GemmParams& p,
-                                          const bf16* gate_row, const bf16* res_row, const bf16* aux_row) {
-  if (p.bias) {
-    uint4 u = __ldg(reinterpret_cast<const uint4*>(p.bias + n));
+                                          const bf16* bias, const bf16* gate_row, const bf16* res_row,
+                                          const bf16* aux_row) {
+  if (bias) {
+    uint4 u = __ldg(reinterpret_cast<const uint4*>(bias + n));
     v[0] += bf16_lo(u.x); v[1] += bf16_hi(u.x); v[2] += bf16_lo(u.y); v[3] += bf16_hi(u.y);
     v[4] += bf16_lo(u.z); v[5] += bf16_hi(u.z); v[6] += bf16_lo(u.w); v[7] += bf16_hi(u.w);
   }
@@ -159,7 +164,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
   const int tiles_mn = p.m_tiles * p.n_tiles;
-  const int total_tiles = tiles_mn * p.splits;  // work items
+  const int total_tiles = tiles_mn * p.splits * p.groups;  // work items (splits > 1 and groups > 1 exclude each other)
   const int kb_all = p.kb1 + p.kb2;
   const int kb_per = (kb_all + p.splits - 1) / p.splits;
 
@@ -168,8 +173,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     int stage = 0;
     uint32_t phase = 0;
     for (int work = blockIdx.x; work < total_tiles; work += gridDim.x) {
-      const int tile = work % tiles_mn, split = work / tiles_mn;
+      const int tile = work % tiles_mn, z = work / tiles_mn;  // z = split-K slice or batch group
       const int mt = tile % p.m_tiles, nt = tile / p.m_tiles;
+      const int split = p.groups > 1 ? 0 : z, g = p.groups > 1 ? z : 0;
       const int kb_begin = split * kb_per, kb_end = min(kb_all, kb_begin + kb_per);
       for (int kb = kb_begin; kb < kb_end; ++kb) {
         mbar_wait(empty_bar(stage), phase ^ 1);
@@ -178,19 +184,22 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         const CUtensorMap* ma = second ? &tmA2 : &tmA;
         const CUtensorMap* mb = second ? &tmB2 : &tmB;
         const int kk = (second ? kb - p.kb1 : kb) * 64;
+        // tensor (row, col) displacement of this group's sub-block
+        const int ar = g * (second ? p.a2_gr : p.a_gr), ac = g * (second ? p.a2_gc : p.a_gc);
+        const int br = g * (second ? p.b2_gr : p.b_gr), bc = g * (second ? p.b2_gc : p.b_gc);
         const uint32_t sa = sbase + stage * Cfg::STAGE, sb = sa + Cfg::A_BYTES;
         if (!A_MN) {
-          tma_load_2d(sa, ma, full_bar(stage), kk, mt * 128);
+          tma_load_2d(sa, ma, full_bar(stage), kk + ac, mt * 128 + ar);
         } else {
-          tma_load_2d(sa, ma, full_bar(stage), mt * 128, kk);
-          tma_load_2d(sa + 8192, ma, full_bar(stage), mt * 128 + 64, kk);
+          tma_load_2d(sa, ma, full_bar(stage), mt * 128 + ac, kk + ar);
+          tma_load_2d(sa + 8192, ma, full_bar(stage), mt * 128 + 64 + ac, kk + ar);
         }
         if (!B_MN) {
-          tma_load_2d(sb, mb, full_bar(stage), kk, nt * BN);
+          tma_load_2d(sb, mb, full_bar(stage), kk + bc, nt * BN + br);
         } else {
 #pragma unroll
           for (int j = 0; j < BN / 64; ++j)
-            tma_load_2d(sb + j * 8192, mb, full_bar(stage), nt * BN + j * 64, kk);
+            tma_load_2d(sb + j * 8192, mb, full_bar(stage), nt * BN + j * 64 + bc, kk + br);
         }
         if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
       }
@@ -209,7 +218,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     int stage = 0, acc = 0;
     uint32_t phase = 0, acc_phase = 0;
     for (int work = blockIdx.x; work < total_tiles; work += gridDim.x) {
-      const int split = work / tiles_mn;
+      const int split = p.groups > 1 ? 0 : work / tiles_mn;
       const int kb_begin = split * kb_per, kb_end = min(kb_all, kb_begin + kb_per);
       mbar_wait(tempty_bar(acc), acc_phase ^ 1);
       tc_fence_after();
@@ -242,10 +251,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     for (int work = blockIdx.x; work < total_tiles; work += gridDim.x) {
       const int tile = work % tiles_mn;
       const int mt = tile % p.m_tiles, nt = tile / p.m_tiles;
+      const int g = p.groups > 1 ? work / tiles_mn : 0;
+      const int crow = g * p.c_gr, ccol = g * p.c_gc;  // output displacement of this group
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
       const int64_t row = (int64_t)mt * 128 + ew * 32 + lane;
       const bool row_ok = row < p.M;
+      const bf16* bias_g = p.bias ? p.bias + g * p.bias_g : nullptr;
       const bf16* gate_row = p.gate ? p.gate + (row_ok ? row / p.rows_per_gate : 0) * p.gate_stride : nullptr;
       const bf16* res_row = p.res ? p.res + row * p.ldres : nullptr;
       bf16* aux_row = p.aux ? p.aux + row * p.ldaux : nullptr;
@@ -276,7 +288,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 #pragma unroll
                 for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[g * 8 + i]);
                 uint4 u, pre = make_uint4(0, 0, 0, 0);
-                if (n < p.N) epi_math8(v, pre, n, row_ok, p, gate_row, res_row, aux_row);
+                if (n < p.N) epi_math8(v, pre, n, row_ok, p, bias_g, gate_row, res_row, aux_row);
                 if (pass == 0) {
                   u = pre;
                 } else {
@@ -291,7 +303,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) {
-              tma_store_2d(pass == 0 ? &tmAux : &tmC, stg, n_slab, row0);
+              tma_store_2d(pass == 0 ? &tmAux : &tmC, stg, n_slab + ccol, row0 + crow);
               tma_store_commit();
             }
           }
@@ -312,8 +324,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
               float v[8];
 #pragma unroll
               for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[g * 8 + i]);
-              if (p.bias) {
-                uint4 u = __ldg(reinterpret_cast<const uint4*>(p.bias + n));
+              if (bias_g) {
+                uint4 u = __ldg(reinterpret_cast<const uint4*>(bias_g + n));
                 v[0] += bf16_lo(u.x); v[1] += bf16_hi(u.x); v[2] += bf16_lo(u.y); v[3] += bf16_hi(u.y);
                 v[4] += bf16_lo(u.z); v[5] += bf16_hi(u.z); v[6] += bf16_lo(u.w); v[7] += bf16_hi(u.w);
               }
@@ -346,7 +358,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                 v[4] += bf16_lo(u.z); v[5] += bf16_hi(u.z); v[6] += bf16_lo(u.w); v[7] += bf16_hi(u.w);
               }
               if (p.out_f32) {
-                float* o = reinterpret_cast<float*>(p.C) + row * p.ldc + n;
+                float* o = reinterpret_cast<float*>(p.C) + (row + crow) * p.ldc + n + ccol;
                 if (p.splits > 1) {  // split-K partial: accumulate into the caller-zeroed output
                   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(o), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]) : "memory");
                   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(o + 4), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7]) : "memory");
@@ -358,7 +370,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                 uint4 u;
                 u.x = pack_bf16x2(v[0], v[1]); u.y = pack_bf16x2(v[2], v[3]);
                 u.z = pack_bf16x2(v[4], v[5]); u.w = pack_bf16x2(v[6], v[7]);
-                *reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(p.C) + row * p.ldc + n) = u;
+                *reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(p.C) + (row + crow) * p.ldc + n + ccol) = u;
               }
             }
           }
@@ -403,7 +415,7 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
     if (e != cudaSuccess) return launch_status("gemm: cudaFuncSetAttribute");
     attr_set = true;
   }
-  int tiles = p.m_tiles * p.n_tiles * p.splits;
+  int tiles = p.m_tiles * p.n_tiles * p.splits * p.groups;
   int grid = tiles < num_sms() ? tiles : num_sms();
   kern<<<grid, 384, Cfg::SMEM, stream>>>(tmA, tmB, tmA2, tmB2, tmC, tmAux, p);
   return launch_status("gemm_bf16");
@@ -415,21 +427,31 @@ using namespace b200;
 
 static inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
-// See include/b200ltx.h for the contract.
-extern "C" int b200_gemm_bf16(const void* A, int64_t lda, int a_kmajor_rows_are_k, const void* B,
+// Strided-batch description (b200_gemm_bf16_batched): `groups` problems of identical shape whose operands
+// are sub-blocks of the given tensors displaced by g * (rows, cols) elements.
+struct GemmGroups {
+  int groups;
+  int a_gr, a_gc, b_gr, b_gc, a2_gr, a2_gc, b2_gr, b2_gc, c_gr, c_gc, bias_g;
+};
+
+static int gemm_impl(const void* A, int64_t lda, int a_kmajor_rows_are_k, const void* B,
                               int64_t ldb, int b_rows_are_k, const void* A2, int64_t lda2,
                               const void* B2, int64_t ldb2, int K2, void* C, int64_t ldc,
                               int out_is_f32, int M, int N, int K, int epilogue, const void* bias,
                               const void* gate, int64_t gate_stride, int64_t rows_per_gate,
                               const void* res, int64_t ldres, void* aux, int64_t ldaux,
-                              int block_n, int split_k, void* stream) {
+                              int block_n, int split_k, void* stream, const GemmGroups& gg) {
   const bool a_mn = a_kmajor_rows_are_k != 0, b_mn = b_rows_are_k != 0;
   if (!(A && B && C)) return arg_error("gemm_bf16: null operand");
   if (M < 0 || N < 0 || K < 0 || K2 < 0) return arg_error("gemm_bf16: negative dimension");
   if (M == 0 || N == 0) return 0;
   if (K == 0 && K2 == 0) return arg_error("gemm_bf16: empty reduction");
-  if (N % 8 || K % 8 || K2 % 8 || (a_mn && M % 8))
-    return arg_error("gemm_bf16: N, K, K2 (and M for a [K,M] A operand) must be multiples of 8");
+  // an extent must be a multiple of 8 only where it is the contiguous dimension of some operand: N always
+  // (C rows, bias); K / K2 unless both operands are stored [K, *] (the wgrad form: K = token count, any value,
+  // TMA zero-fills the rows past it); M for a [K, M] A operand
+  const bool k_contig = !a_mn || !b_mn;
+  if (N % 8 || (k_contig && (K % 8 || K2 % 8)) || (a_mn && M % 8))
+    return arg_error("gemm_bf16: N (and K, K2 for a K-major operand, M for a [K,M] A operand) must be multiples of 8");
   if (lda % 8 || ldb % 8 || ldc % (out_is_f32 ? 4 : 8) || !al16(A) || !al16(B) || !al16(C))
     return arg_error("gemm_bf16: operands must be 16-byte aligned with 16-byte-multiple pitches");
   if (K2 > 0 && (!(A2 && B2) || lda2 % 8 || ldb2 % 8 || !al16(A2) || !al16(B2)))
@@ -468,6 +490,20 @@ extern "C" int b200_gemm_bf16(const void* A, int64_t lda, int a_kmajor_rows_are_
     while (sp > 1 && (sp - 1) * ((kb_all + sp - 1) / sp) >= kb_all) --sp;
     p.splits = sp;
   }
+  p.groups = gg.groups < 1 ? 1 : gg.groups;
+  p.a_gr = gg.a_gr; p.a_gc = gg.a_gc; p.b_gr = gg.b_gr; p.b_gc = gg.b_gc;
+  p.a2_gr = gg.a2_gr; p.a2_gc = gg.a2_gc; p.b2_gr = gg.b2_gr; p.b2_gc = gg.b2_gc;
+  p.c_gr = gg.c_gr; p.c_gc = gg.c_gc; p.bias_g = gg.bias_g;
+  const int64_t G1 = p.groups - 1;
+  if (p.groups > 1) {
+    // tiles must not straddle sub-blocks: TMA zero-fill / store clipping only exist at the tensor edges
+    if (M % 128 || N % bn || K % 64 || K2 % 64)
+      return arg_error("gemm_bf16_batched: per-group M, N, K, K2 must be multiples of 128, block_n, 64, 64");
+    if (gate || res || aux || epilogue != EPI_NONE)
+      return arg_error("gemm_bf16_batched: only the bias epilogue is built for batches");
+    if (p.splits > 1) return arg_error("gemm_bf16_batched: split_k and batching exclude each other");
+    if (gg.c_gc % 8 || gg.bias_g % 8) return arg_error("gemm_bf16_batched: output / bias displacements must be multiples of 8");
+  }
   p.C = C; p.ldc = ldc;
   p.bias = (const bf16*)bias;
   p.gate = (const bf16*)gate; p.gate_stride = gate_stride; p.rows_per_gate = rows_per_gate > 0 ? rows_per_gate : 1;
@@ -476,17 +512,22 @@ extern "C" int b200_gemm_bf16(const void* A, int64_t lda, int a_kmajor_rows_are_
 
   CUtensorMap tmA, tmB, tmA2, tmB2;
   int rc;
-  auto mapA = [&](CUtensorMap* t, const void* ptr, int64_t ld, int kdim) {
-    return a_mn ? make_tmap_2d_bf16(t, ptr, kdim, M, ld, 64, 64) : make_tmap_2d_bf16(t, ptr, M, kdim, ld, 128, 64);
+  // tensor extents include the displaced sub-blocks of every group
+  auto mapA = [&](CUtensorMap* t, const void* ptr, int64_t ld, int kdim, int gr, int gc) {
+    return a_mn ? make_tmap_2d_bf16(t, ptr, kdim + G1 * gr, M + G1 * gc, ld, 64, 64)
+                : make_tmap_2d_bf16(t, ptr, M + G1 * gr, kdim + G1 * gc, ld, 128, 64);
   };
-  auto mapB = [&](CUtensorMap* t, const void* ptr, int64_t ld, int kdim) {
-    return b_mn ? make_tmap_2d_bf16(t, ptr, kdim, N, ld, 64, 64) : make_tmap_2d_bf16(t, ptr, N, kdim, ld, bn, 64);
+  auto mapB = [&](CUtensorMap* t, const void* ptr, int64_t ld, int kdim, int gr, int gc) {
+    return b_mn ? make_tmap_2d_bf16(t, ptr, kdim + G1 * gr, N + G1 * gc, ld, 64, 64)
+                : make_tmap_2d_bf16(t, ptr, N + G1 * gr, kdim + G1 * gc, ld, bn, 64);
   };
   if (K > 0) {
-    if ((rc = mapA(&tmA, A, lda, K)) || (rc = mapB(&tmB, B, ldb, K))) return arg_error("gemm_bf16: cuTensorMapEncodeTiled failed", rc);
+    if ((rc = mapA(&tmA, A, lda, K, gg.a_gr, gg.a_gc)) || (rc = mapB(&tmB, B, ldb, K, gg.b_gr, gg.b_gc)))
+      return arg_error("gemm_bf16: cuTensorMapEncodeTiled failed", rc);
   }
   if (K2 > 0) {
-    if ((rc = mapA(&tmA2, A2, lda2, K2)) || (rc = mapB(&tmB2, B2, ldb2, K2))) return arg_error("gemm_bf16: cuTensorMapEncodeTiled failed (pair 2)", rc);
+    if ((rc = mapA(&tmA2, A2, lda2, K2, gg.a2_gr, gg.a2_gc)) || (rc = mapB(&tmB2, B2, ldb2, K2, gg.b2_gr, gg.b2_gc)))
+      return arg_error("gemm_bf16: cuTensorMapEncodeTiled failed (pair 2)", rc);
   } else {
     tmA2 = tmA; tmB2 = tmB;
   }
@@ -496,7 +537,8 @@ extern "C" int b200_gemm_bf16(const void* A, int64_t lda, int a_kmajor_rows_are_
   CUtensorMap tmC = tmA, tmAux = tmA;
   p.tma_store = (!out_is_f32 && bn >= 128) ? 1 : 0;
   if (p.tma_store) {
-    if ((rc = make_tmap_2d_bf16(&tmC, C, M, N, ldc, 32, 64))) return arg_error("gemm_bf16: cuTensorMapEncodeTiled failed (C)", rc);
+    if ((rc = make_tmap_2d_bf16(&tmC, C, M + G1 * gg.c_gr, N + G1 * gg.c_gc, ldc, 32, 64)))
+      return arg_error("gemm_bf16: cuTensorMapEncodeTiled failed (C)", rc);
     if (epilogue == EPI_GELU && aux && (rc = make_tmap_2d_bf16(&tmAux, aux, M, N, ldaux, 32, 64)))
       return arg_error("gemm_bf16: cuTensorMapEncodeTiled failed (aux)", rc);
   }
@@ -514,4 +556,31 @@ extern "C" int b200_gemm_bf16(const void* A, int64_t lda, int a_kmajor_rows_are_
   DISPATCH(64)
 #undef DISPATCH
   return arg_error("gemm_bf16: unreachable");
+}
+
+// See include/b200ltx.h for the contracts.
+extern "C" int b200_gemm_bf16(const void* A, int64_t lda, int a_kmajor_rows_are_k, const void* B,
+                              int64_t ldb, int b_rows_are_k, const void* A2, int64_t lda2,
+                              const void* B2, int64_t ldb2, int K2, void* C, int64_t ldc,
+                              int out_is_f32, int M, int N, int K, int epilogue, const void* bias,
+                              const void* gate, int64_t gate_stride, int64_t rows_per_gate,
+                              const void* res, int64_t ldres, void* aux, int64_t ldaux,
+                              int block_n, int split_k, void* stream) {
+  GemmGroups gg = {1, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+  return gemm_impl(A, lda, a_kmajor_rows_are_k, B, ldb, b_rows_are_k, A2, lda2, B2, ldb2, K2, C, ldc, out_is_f32,
+                   M, N, K, epilogue, bias, gate, gate_stride, rows_per_gate, res, ldres, aux, ldaux, block_n,
+                   split_k, stream, gg);
+}
+
+extern "C" int b200_gemm_bf16_batched(const void* A, int64_t lda, int a_rows_are_k, const void* B, int64_t ldb,
+                                      int b_rows_are_k, const void* A2, int64_t lda2, const void* B2,
+                                      int64_t ldb2, int K2, void* C, int64_t ldc, int out_is_f32, int M, int N,
+                                      int K, const void* bias, int block_n, int groups,
+                                      const int32_t* group_offsets /* host, 11 ints */, void* stream) {
+  if (groups < 1 || !group_offsets) return arg_error("gemm_bf16_batched: bad group description");
+  const int32_t* o = group_offsets;
+  GemmGroups gg = {groups, o[0], o[1], o[2], o[3], o[4], o[5], o[6], o[7], o[8], o[9], o[10]};
+  if (block_n == 0) block_n = N >= 256 && N % 256 == 0 ? 256 : (N % 128 == 0 ? 128 : 64);
+  return gemm_impl(A, lda, a_rows_are_k, B, ldb, b_rows_are_k, A2, lda2, B2, ldb2, K2, C, ldc, out_is_f32, M, N, K,
+                   EPI_NONE, bias, nullptr, 0, 0, nullptr, 0, nullptr, 0, block_n, 1, stream, gg);
 }

@@ -84,6 +84,49 @@ def _cached_wqkv(attn):
     return cache[1], cache[2]
 
 
+def _batched_ctx_kv(model, ctx):
+    """Project the caption tokens to the attn2 keys / values of EVERY block in one strided-batched GEMM
+    (ops.CtxKVFn) and hand each block its column views.  Returns the list of attentions that were given a
+    `_b200_kv` entry (to be cleared after the forward), or [] when the layout does not allow it (then every
+    block projects for itself, exactly as the reference does: attention.py:999-1005)."""
+    blocks = list(model.transformer_blocks)
+    attns = [blk.attn2 for blk in blocks if blk.attn2 is not None]
+    if len(attns) != len(blocks) or len(attns) < 2 or ctx is None:
+        return []
+    B, L, Dc = ctx.shape
+    mods = [m for a in attns for m in (a.to_k, a.to_v)]
+    parts = [linear_parts(m) for m in mods]
+    W0 = parts[0][0]
+    D = W0.shape[0]
+    if (B * L) % 128 or D % 256 or Dc % 64:
+        return []
+    has_bias = parts[0][1] is not None
+    has_lora = parts[0][2] is not None
+    for W, b, lo in parts:
+        if W.shape != W0.shape or W.requires_grad or (b is not None) != has_bias or (b is not None and b.requires_grad) \
+                or (lo is not None) != has_lora or W.dtype != BF16:
+            return []
+    r, scaling = 0, 1.0
+    adapters = ()
+    if has_lora:
+        r, scaling = parts[0][2][0].shape[0], parts[0][2][2]
+        if any(lo[0].shape[0] != r or lo[2] != scaling for _, _, lo in parts) or r > ops.LORA_PAD:
+            return []
+        adapters = tuple(lo[0] for _, _, lo in parts) + tuple(lo[1] for _, _, lo in parts)
+    key = tuple((W.data_ptr(), W._version, None if b is None else (b.data_ptr(), b._version)) for W, b, _ in parts)
+    cache = model.__dict__.get("_b200_wkv_all")
+    if cache is None or cache[0] != key:
+        Wkv = torch.cat([W.detach() for W, _, _ in parts], dim=0).contiguous()
+        bkv = torch.cat([b.detach() for _, b, _ in parts], dim=0).contiguous() if has_bias else None
+        cache = (key, Wkv, bkv)
+        model.__dict__["_b200_wkv_all"] = cache
+    G = len(mods)
+    outs = ops.CtxKVFn.apply(ctx.reshape(B * L, Dc), cache[1], cache[2], G, float(scaling), int(r), *adapters)
+    for i, a in enumerate(attns):
+        a.__dict__["_b200_kv"] = (ctx, outs[2 * i], outs[2 * i + 1])
+    return attns
+
+
 # ---------------------------------------------------------------------------------------------
 # functional forward
 # ---------------------------------------------------------------------------------------------
@@ -138,8 +181,12 @@ def attention_forward(attn, hidden_states, freqs_cis=None, encoder_hidden_states
         raise B200Error("sequence-sharded attn1 needs frozen, adapter-free attn1 projections and no skip-layer mask")
 
     q_pre = apply_linear(attn.to_q, x2d)
-    k_pre = apply_linear(attn.to_k, src2d)
-    v = apply_linear(attn.to_v, src2d)
+    pre = attn.__dict__.get("_b200_kv") if not is_self else None
+    if pre is not None and pre[0] is encoder_hidden_states:
+        k_pre, v = pre[1], pre[2]  # projected once for all blocks by transformer_forward (ops.CtxKVFn)
+    else:
+        k_pre = apply_linear(attn.to_k, src2d)
+        v = apply_linear(attn.to_v, src2d)
     o = ops.AttnCoreFn.apply(q_pre, k_pre, v, wqn, wkn, cos, sin, kb, B, H, Nq, Nk, scale)
     if skip_layer_mask is not None and strat in (SkipLayerStrategy.AttentionSkip, SkipLayerStrategy.AttentionValues):
         m = skip_layer_mask.reshape(B, 1, 1).to(o.dtype)
@@ -295,17 +342,25 @@ def transformer_forward(model, hidden_states, indices_grid, ref_image_hidden_sta
         ctx = ops.FeedForwardFn.apply(e2d, W1, b1, W2, b2, None, 0, None).view(B, L, D)
 
     h = x.view(B, N, D)
-    for i, block in enumerate(model.transformer_blocks):
-        slm = skip_layer_mask[i] if skip_layer_mask is not None else None
-        if model.training and model.gradient_checkpointing:
-            h = torch.utils.checkpoint.checkpoint(block, h, freqs, attention_mask, ctx, encoder_attention_mask, t6,
-                                                  cross_attention_kwargs, class_labels, slm, skip_layer_strategy,
-                                                  use_reentrant=False)
-        else:
-            h = block(h, freqs_cis=freqs, attention_mask=attention_mask, encoder_hidden_states=ctx,
-                      encoder_attention_mask=encoder_attention_mask, timestep=t6,
-                      cross_attention_kwargs=cross_attention_kwargs, class_labels=class_labels,
-                      skip_layer_mask=slm, skip_layer_strategy=skip_layer_strategy)
+    checkpointing = model.training and model.gradient_checkpointing
+    # everything on the attn2 key/value side depends only on the caption tokens: one batched projection
+    # for all blocks (not under activation checkpointing, whose recomputation runs block by block)
+    shared_kv = [] if checkpointing else _batched_ctx_kv(model, ctx)
+    try:
+        for i, block in enumerate(model.transformer_blocks):
+            slm = skip_layer_mask[i] if skip_layer_mask is not None else None
+            if checkpointing:
+                h = torch.utils.checkpoint.checkpoint(block, h, freqs, attention_mask, ctx, encoder_attention_mask,
+                                                      t6, cross_attention_kwargs, class_labels, slm,
+                                                      skip_layer_strategy, use_reentrant=False)
+            else:
+                h = block(h, freqs_cis=freqs, attention_mask=attention_mask, encoder_hidden_states=ctx,
+                          encoder_attention_mask=encoder_attention_mask, timestep=t6,
+                          cross_attention_kwargs=cross_attention_kwargs, class_labels=class_labels,
+                          skip_layer_mask=slm, skip_layer_strategy=skip_layer_strategy)
+    finally:
+        for a in shared_kv:
+            a.__dict__.pop("_b200_kv", None)
 
     T = emb.shape[1]
     ss = (model.scale_shift_table[None, None] + emb[:, :, None]).reshape(B * T, 2 * D)

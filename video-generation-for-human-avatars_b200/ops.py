@@ -142,6 +142,30 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, a_rows_are_k=False, b_rows_are_k=F
     return out
 
 
+def gemm_batched(a, b, out, M, N, K, groups, offs, *, a_rows_are_k=False, b_rows_are_k=False, a2=None, b2=None,
+                 K2=0, bias=None, block_n=0):
+    """`groups` GEMMs of shape [M,N,K(+K2)] in one launch; operand g = sub-block displaced by g * offs[name]
+    (rows, cols) inside the given tensor (offs keys: a, b, a2, b2, c -> (rows, cols); bias -> elements).
+    See b200_gemm_bf16_batched in include/b200ltx.h."""
+    import ctypes
+    for t, nm in ((a, "a"), (b, "b")):
+        _chk2d(t, "gemm_batched " + nm)
+    _chk2d(out, "gemm_batched out", out.dtype)
+    if a2 is not None:
+        _chk2d(a2, "gemm_batched a2")
+        _chk2d(b2, "gemm_batched b2")
+    z = (0, 0)
+    o = [*offs.get("a", z), *offs.get("b", z), *offs.get("a2", z), *offs.get("b2", z), *offs.get("c", z),
+         offs.get("bias", 0)]
+    arr = (ctypes.c_int32 * 11)(*[int(x) for x in o])
+    _call("gemm", 2.0 * groups * M * N * (K + K2), "flop", _L().b200_gemm_bf16_batched,
+          _p(a), a.stride(0), int(a_rows_are_k), _p(b), b.stride(0), int(b_rows_are_k),
+          _p(a2), a2.stride(0) if a2 is not None else 0, _p(b2), b2.stride(0) if b2 is not None else 0, K2,
+          _p(out), out.stride(0), int(out.dtype == torch.float32), M, N, K, _p(bias), block_n, groups,
+          ctypes.cast(arr, ctypes.c_void_p), _s())
+    return out
+
+
 def norm_mod_fwd(x, scale, shift, rows_per_mod, eps, layernorm=False, out=None):
     _chk2d(x, "norm_mod x")
     rows, D = x.shape
@@ -485,6 +509,77 @@ class AttnCoreFn(torch.autograd.Function):
         dk_pre = torch.empty((B * Nk, D), device=do.device, dtype=BF16)
         qknorm_rope_bwd(dq32, dk, q_pre, k_pre, wq, wk, cos, sin, dq_pre, dk_pre)
         return dq_pre, dk_pre, dv, None, None, None, None, None, None, None, None, None, None
+
+
+class CtxKVFn(torch.autograd.Function):
+    """attn2 key / value projections (+ LoRA) of ALL blocks from the projected caption tokens, which are the
+    same for every block: 2 launches forward (LoRA down-projection, strided-batched projection with the LoRA
+    up-projection as second operand pair) and 4 backward, instead of 4 forward + 10 backward PER BLOCK of
+    latency-bound M = 256 GEMMs on 2 SMs.
+
+        kv_g = ctx W_g^T + b_g + (ctx A_g^T)(s B_g)^T        g = (block, k | v)
+
+    Returns G tensors [M, D]: column blocks of one [M, G*D] buffer.  Wkv [G*D, Dc] / bkv [G*D] are cached
+    concatenations of the frozen weights; As / Bs are the G fp32 adapters (or empty lists)."""
+
+    @staticmethod
+    def forward(ctx, x, Wkv, bkv, G, scaling, r, *adapters):
+        M, Dc = x.shape
+        D = Wkv.shape[0] // G
+        has_lora = len(adapters) > 0
+        kv = torch.empty((M, G * D), device=x.device, dtype=BF16)
+        a_st = b_st = t = None
+        if has_lora:
+            As, Bs = adapters[:G], adapters[G:]
+            a_st = torch.zeros((G, LORA_PAD, Dc), device=x.device, dtype=BF16)
+            a_st[:, :r] = torch.stack([A.detach() for A in As])
+            b_st = torch.zeros((G, D, LORA_PAD), device=x.device, dtype=BF16)
+            bs = torch.stack([B.detach() for B in Bs])
+            b_st[:, :, :r] = bs * scaling if scaling != 1.0 else bs
+            a_st, b_st = a_st.view(G * LORA_PAD, Dc), b_st.view(G * D, LORA_PAD)
+            t = gemm(x, a_st)  # [M, G*64]
+        gemm_batched(x, Wkv, kv, M, D, Dc, G, {"b": (D, 0), "a2": (0, LORA_PAD), "b2": (D, 0), "c": (0, D), "bias": D},
+                     a2=t, b2=b_st, K2=LORA_PAD if has_lora else 0, bias=bkv)
+        ctx.save_for_backward(x, Wkv, a_st, b_st, t)
+        ctx.meta = (G, D, scaling, r, has_lora)
+        return tuple(kv[:, g * D:(g + 1) * D] for g in range(G))
+
+    @staticmethod
+    def backward(ctx, *grads):
+        x, Wkv, a_st, b_st, t = ctx.saved_tensors
+        G, D, scaling, r, has_lora = ctx.meta
+        M, Dc = x.shape
+        zero = None
+        cols = []
+        for g in grads:
+            if g is None:
+                if zero is None:
+                    zero = torch.zeros((M, D), device=x.device, dtype=BF16)
+                g = zero
+            cols.append(g)
+        dkv = torch.cat(cols, dim=1)  # [M, G*D]
+        dt = None
+        if has_lora:
+            dt = torch.empty((M, G * LORA_PAD), device=x.device, dtype=BF16)
+            gemm_batched(dkv, b_st, dt, M, LORA_PAD, D, G, {"a": (0, D), "b": (D, 0), "c": (0, LORA_PAD)},
+                         b_rows_are_k=True, block_n=64)
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dx = gemm(dkv, Wkv, b_rows_are_k=True, a2=dt, b2=a_st, out_dtype=torch.float32, split_k=0).to(BF16)
+        dAs = dBs = ()
+        if has_lora:
+            dA = gemm(dt, x, a_rows_are_k=True, b_rows_are_k=True, out_dtype=torch.float32, split_k=0)
+            dA = dA.view(G, LORA_PAD, Dc)
+            dB = torch.empty((G * D, LORA_PAD), device=x.device, dtype=torch.float32)
+            gemm_batched(dkv, t, dB, D, LORA_PAD, M, G, {"a": (0, D), "b": (0, LORA_PAD), "c": (D, 0)},
+                         a_rows_are_k=True, b_rows_are_k=True, block_n=64)
+            dB = dB.view(G, D, LORA_PAD)
+            if scaling != 1.0:
+                dB = dB * scaling
+            need = ctx.needs_input_grad
+            dAs = tuple(dA[g, :r] if need[6 + g] else None for g in range(G))
+            dBs = tuple(dB[g, :, :r] if need[6 + G + g] else None for g in range(G))
+        return (dx, None, None, None, None, None) + dAs + dBs
 
 
 def linear(x, W, b=None, lora=None, gate=None, rows_per_gate=0, res=None):
