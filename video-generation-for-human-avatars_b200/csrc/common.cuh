@@ -81,7 +81,7 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
 // iteration count (each failed try_wait already sleeps ~100 cycles in hardware), so the spin loop
 // is just TRYWAIT + branch and does not steal issue slots from the math warps.
 #ifndef B200_WAIT_MAX_SPINS
-#define B200_WAIT_MAX_SPINS (1u << 22)
+#define B200_WAIT_MAX_SPINS (1u << 19)
 #endif
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
@@ -303,6 +303,59 @@ __host__ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint
   d |= (uint64_t)2 << 61;
   return d;
 }
+// ---------------------------------------------------------------------------
+// CTA pair (cta_group::2): two CTAs of a cluster on the SMs of one TPC execute ONE M = 256 MMA; each holds its
+// 128 rows of A, half of B's N rows and its 128 lanes of the accumulator.  The even CTA (rank 0) issues.
+// ---------------------------------------------------------------------------
+constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;  // shared::cluster address -> the same offset in the even CTA of the pair
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// TMA load whose transaction bytes are credited to the mbarrier of the pair's even CTA
+__device__ __forceinline__ void tma_load_2d_2sm(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes "
+      "[%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+      "l"(m), "r"(bar & kPeerBitMask), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_even_cta(uint32_t bar) {  // arrive on the even CTA's barrier (from either CTA)
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar & kPeerBitMask) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_2cta(uint32_t smem_dst, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish_2cta() {
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_2cta(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_ss_2cta(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                             uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrives on the barrier at this offset in BOTH CTAs once every MMA issued so far has completed
+__device__ __forceinline__ void umma_commit_2cta(uint32_t bar) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+      "h"((uint16_t)3)
+      : "memory");
+}
+
 // Advance the start-address field of a descriptor by `bytes` (a multiple of 16; valid while the 14-bit
 // field does not overflow, i.e. for any offset that stays inside shared memory).  One integer add per MMA
 // instead of re-encoding the descriptor: the single MMA-issuing thread shares its scheduler with busy

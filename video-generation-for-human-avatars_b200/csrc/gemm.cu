@@ -18,6 +18,8 @@
 //                   two warps per TMEM lane quadrant, each draining half of the tile's columns
 // Accumulators are double-buffered in TMEM (2 x BN columns) so the epilogue of tile i overlaps the
 // main loop of tile i+1.
+#include <cstdlib>
+
 #include "api_internal.h"
 #include "common.cuh"
 #include "tmap.h"
@@ -103,26 +105,30 @@ __device__ __forceinline__ void epi_math8(float (&v)[8], uint4& pre, int n, bool
   }
 }
 
-template <int BN>
+// CTA2: a cluster of two CTAs computes a 256 x BN tile with cta_group::2 MMAs; each CTA stages its 128 rows
+// of A and HALF of B's BN rows per k block (32 KB instead of 48 KB per 128 x 256 x 64 of math per SM).
+template <int BN, bool CTA2 = false>
 struct GemmCfg {
   static constexpr int BM = 128, BK = 64;
   static constexpr int A_BYTES = BM * BK * 2;
-  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int BN_LOCAL = CTA2 ? BN / 2 : BN;  // B rows staged by this CTA
+  static constexpr int B_BYTES = BN_LOCAL * BK * 2;
   static constexpr int STAGE = A_BYTES + B_BYTES;
-  static constexpr int NSTAGE = BN == 256 ? 4 : (BN == 128 ? 6 : 8);
+  static constexpr int NSTAGE = CTA2 ? 6 : (BN == 256 ? 4 : (BN == 128 ? 6 : 8));
   static constexpr int TMEM_COLS = 2 * BN;
   static constexpr int STAGING = 8 * 4096;  // one 32-row x 128-byte swizzled slab per epilogue warp
   static constexpr int SMEM = NSTAGE * STAGE + STAGING + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
-template <int BN, bool A_MN, bool B_MN>
+template <int BN, bool A_MN, bool B_MN, bool CTA2>
 __global__ void __launch_bounds__(384, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
             const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB2,
             const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmAux,
             const __grid_constant__ GemmParams p) {
-  using Cfg = GemmCfg<BN>;
+  using Cfg = GemmCfg<BN, CTA2>;
   constexpr int NSTAGE = Cfg::NSTAGE;
+  const int rank = CTA2 ? (int)cluster_ctarank() : 0;  // position in the CTA pair; rank 0 issues the MMAs
   extern __shared__ uint8_t smem_raw[];
   const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t stage_base = sbase + NSTAGE * Cfg::STAGE;
@@ -149,16 +155,22 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
-      mbar_init(tempty_bar(a), 8);
+      mbar_init(tempty_bar(a), CTA2 ? 16 : 8);  // pair: the epilogue warps of both CTAs arrive on rank 0's barrier
     }
     fence_barrier_init();
   }
   if (warp == 2) {
-    tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
-    tmem_relinquish();
+    if (CTA2) {
+      tmem_alloc_2cta(tmem_slot, Cfg::TMEM_COLS);
+      tmem_relinquish_2cta();
+    } else {
+      tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+      tmem_relinquish();
+    }
   }
   tc_fence_before();
   __syncthreads();
+  if (CTA2) cluster_sync_all();  // the peer's barriers exist before anything signals them
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
@@ -168,18 +180,23 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   const int kb_all = p.kb1 + p.kb2;
   const int kb_per = (kb_all + p.splits - 1) / p.splits;
 
+  // persistent walk: a CTA (or CTA pair) takes every `work_step`-th work item
+  const int work_first = CTA2 ? blockIdx.x >> 1 : blockIdx.x;
+  const int work_step = CTA2 ? gridDim.x >> 1 : gridDim.x;
+
   if (warp == 0 && lane == 0) {
     // ------------------------------ TMA producer ------------------------------
     int stage = 0;
     uint32_t phase = 0;
-    for (int work = blockIdx.x; work < total_tiles; work += gridDim.x) {
+    for (int work = work_first; work < total_tiles; work += work_step) {
       const int tile = work % tiles_mn, z = work / tiles_mn;  // z = split-K slice or batch group
-      const int mt = tile % p.m_tiles, nt = tile / p.m_tiles;
+      const int mt = (tile % p.m_tiles) * (CTA2 ? 2 : 1) + rank, nt = tile / p.m_tiles;
       const int split = p.groups > 1 ? 0 : z, g = p.groups > 1 ? z : 0;
       const int kb_begin = split * kb_per, kb_end = min(kb_all, kb_begin + kb_per);
       for (int kb = kb_begin; kb < kb_end; ++kb) {
         mbar_wait(empty_bar(stage), phase ^ 1);
-        mbar_expect_tx(full_bar(stage), Cfg::STAGE);
+        // pair: both CTAs' loads are credited to rank 0's barrier, armed by rank 0 for both
+        if (!CTA2 || rank == 0) mbar_expect_tx(full_bar(stage), (CTA2 ? 2 : 1) * Cfg::STAGE);
         const bool second = kb >= p.kb1;
         const CUtensorMap* ma = second ? &tmA2 : &tmA;
         const CUtensorMap* mb = second ? &tmB2 : &tmB;
@@ -188,36 +205,40 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         const int ar = g * (second ? p.a2_gr : p.a_gr), ac = g * (second ? p.a2_gc : p.a_gc);
         const int br = g * (second ? p.b2_gr : p.b_gr), bc = g * (second ? p.b2_gc : p.b_gc);
         const uint32_t sa = sbase + stage * Cfg::STAGE, sb = sa + Cfg::A_BYTES;
+        const int n0 = nt * BN + rank * Cfg::BN_LOCAL;  // first B row staged by this CTA
+        auto load = [&](uint32_t dst, const CUtensorMap* m, int c0, int c1) {
+          if (CTA2) tma_load_2d_2sm(dst, m, full_bar(stage), c0, c1);
+          else tma_load_2d(dst, m, full_bar(stage), c0, c1);
+        };
         if (!A_MN) {
-          tma_load_2d(sa, ma, full_bar(stage), kk + ac, mt * 128 + ar);
+          load(sa, ma, kk + ac, mt * 128 + ar);
         } else {
-          tma_load_2d(sa, ma, full_bar(stage), mt * 128 + ac, kk + ar);
-          tma_load_2d(sa + 8192, ma, full_bar(stage), mt * 128 + 64 + ac, kk + ar);
+          load(sa, ma, mt * 128 + ac, kk + ar);
+          load(sa + 8192, ma, mt * 128 + 64 + ac, kk + ar);
         }
         if (!B_MN) {
-          tma_load_2d(sb, mb, full_bar(stage), kk + bc, nt * BN + br);
+          load(sb, mb, kk + bc, n0 + br);
         } else {
 #pragma unroll
-          for (int j = 0; j < BN / 64; ++j)
-            tma_load_2d(sb + j * 8192, mb, full_bar(stage), nt * BN + j * 64 + bc, kk + br);
+          for (int j = 0; j < Cfg::BN_LOCAL / 64; ++j) load(sb + j * 8192, mb, n0 + j * 64 + bc, kk + br);
         }
         if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == 1 && rank == 0) {
     // ------------------------------ MMA issuer --------------------------------
     // The whole warp follows the control flow (barrier waits); one elected lane issues.  Descriptors are
     // a per-stage base plus a constant per K step, so the issuing thread's instruction stream per MMA is
     // a single add: it shares its scheduler with two epilogue warps and every extra instruction is
     // tensor-pipe idle time.
-    const uint32_t idesc = make_idesc_bf16(128, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
+    const uint32_t idesc = make_idesc_bf16(CTA2 ? 256 : 128, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
     const uint64_t da0 = A_MN ? make_smem_desc(sbase, 8192, 1024) : make_smem_desc(sbase, 16, 1024);
     const uint64_t db0 = B_MN ? make_smem_desc(sbase + Cfg::A_BYTES, 8192, 1024)
                               : make_smem_desc(sbase + Cfg::A_BYTES, 16, 1024);
     constexpr uint32_t A_STEP = A_MN ? 2048 : 32, B_STEP = B_MN ? 2048 : 32;
     int stage = 0, acc = 0;
     uint32_t phase = 0, acc_phase = 0;
-    for (int work = blockIdx.x; work < total_tiles; work += gridDim.x) {
+    for (int work = work_first; work < total_tiles; work += work_step) {
       const int split = p.groups > 1 ? 0 : work / tiles_mn;
       const int kb_begin = split * kb_per, kb_end = min(kb_all, kb_begin + kb_per);
       mbar_wait(tempty_bar(acc), acc_phase ^ 1);
@@ -229,15 +250,21 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         if (elect_one()) {
           const uint64_t da = desc_adv(da0, stage * Cfg::STAGE), db = desc_adv(db0, stage * Cfg::STAGE);
 #pragma unroll
-          for (int k = 0; k < 4; ++k)
-            umma_ss(d_tmem, desc_adv(da, k * A_STEP), desc_adv(db, k * B_STEP), idesc,
-                    (kb > kb_begin || k > 0) ? 1u : 0u);
-          umma_commit(empty_bar(stage));
+          for (int k = 0; k < 4; ++k) {
+            const uint32_t accum = (kb > kb_begin || k > 0) ? 1u : 0u;
+            if (CTA2) umma_ss_2cta(d_tmem, desc_adv(da, k * A_STEP), desc_adv(db, k * B_STEP), idesc, accum);
+            else umma_ss(d_tmem, desc_adv(da, k * A_STEP), desc_adv(db, k * B_STEP), idesc, accum);
+          }
+          if (CTA2) umma_commit_2cta(empty_bar(stage));  // frees the stage in both CTAs
+          else umma_commit(empty_bar(stage));
         }
         __syncwarp();
         if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
       }
-      if (elect_one()) umma_commit(tfull_bar(acc));
+      if (elect_one()) {
+        if (CTA2) umma_commit_2cta(tfull_bar(acc));
+        else umma_commit(tfull_bar(acc));
+      }
       __syncwarp();
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
@@ -248,9 +275,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     const int chalf = (warp - 4) >> 2;  // which half of the tile's columns this warp drains
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int work = blockIdx.x; work < total_tiles; work += gridDim.x) {
+    for (int work = work_first; work < total_tiles; work += work_step) {
       const int tile = work % tiles_mn;
-      const int mt = tile % p.m_tiles, nt = tile / p.m_tiles;
+      const int mt = (tile % p.m_tiles) * (CTA2 ? 2 : 1) + rank, nt = tile / p.m_tiles;
       const int g = p.groups > 1 ? work / tiles_mn : 0;
       const int crow = g * p.c_gr, ccol = g * p.c_gc;  // output displacement of this group
       mbar_wait(tfull_bar(acc), acc_phase);
@@ -378,7 +405,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(tempty_bar(acc));
+      if (lane == 0) {
+        if (CTA2) mbar_arrive_even_cta(tempty_bar(acc));
+        else mbar_arrive(tempty_bar(acc));
+      }
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
@@ -386,9 +416,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   }
   tc_fence_before();
   __syncthreads();
+  if (CTA2) cluster_sync_all();  // neither CTA leaves (or frees TMEM) while the pair's MMAs / signals are in flight
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+    if (CTA2) tmem_dealloc_2cta(tmem_base, Cfg::TMEM_COLS);
+    else tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
   }
 }
 
@@ -403,21 +435,39 @@ static int num_sms() {
   return g_num_sms;
 }
 
-template <int BN, bool A_MN, bool B_MN>
+template <int BN, bool A_MN, bool B_MN, bool CTA2 = false>
 static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmA2,
                        const CUtensorMap& tmB2, const CUtensorMap& tmC, const CUtensorMap& tmAux,
                        const GemmParams& p, cudaStream_t stream) {
-  using Cfg = GemmCfg<BN>;
+  using Cfg = GemmCfg<BN, CTA2>;
   static bool attr_set = false;
-  auto kern = gemm_kernel<BN, A_MN, B_MN>;
+  auto kern = gemm_kernel<BN, A_MN, B_MN, CTA2>;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
     if (e != cudaSuccess) return launch_status("gemm: cudaFuncSetAttribute");
     attr_set = true;
   }
-  int tiles = p.m_tiles * p.n_tiles * p.splits * p.groups;
-  int grid = tiles < num_sms() ? tiles : num_sms();
-  kern<<<grid, 384, Cfg::SMEM, stream>>>(tmA, tmB, tmA2, tmB2, tmC, tmAux, p);
+  int tiles = p.m_tiles * p.n_tiles * p.splits * p.groups;  // CTA2: m_tiles counts 256-row tile pairs
+  if (!CTA2) {
+    int grid = tiles < num_sms() ? tiles : num_sms();
+    kern<<<grid, 384, Cfg::SMEM, stream>>>(tmA, tmB, tmA2, tmB2, tmC, tmAux, p);
+    return launch_status("gemm_bf16");
+  }
+  const int pairs = num_sms() / 2;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(2 * (tiles < pairs ? tiles : pairs), 1, 1);
+  cfg.blockDim = dim3(384, 1, 1);
+  cfg.dynamicSmemBytes = Cfg::SMEM;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmA2, tmB2, tmC, tmAux, p);
+  if (e != cudaSuccess) return launch_status("gemm_bf16 (CTA pair launch)");
   return launch_status("gemm_bf16");
 }
 
@@ -473,9 +523,12 @@ static int gemm_impl(const void* A, int64_t lda, int a_kmajor_rows_are_k, const 
   }
   if (bn != 64 && bn != 128 && bn != 256) return arg_error("gemm_bf16: block_n must be 0, 64, 128 or 256");
 
+  // CTA pairs (256 x 256 tiles, cta_group::2) for the large GEMMs: a third less operand traffic per FLOP
+  const bool pair = bn == 256 && M >= 512 && split_k <= 1 && (gg.groups <= 1 || M % 256 == 0) &&
+                    !getenv("B200_GEMM_NO_PAIR");
   GemmParams p;
   p.M = M; p.N = N;
-  p.m_tiles = (M + 127) / 128;
+  p.m_tiles = pair ? (M + 255) / 256 : (M + 127) / 128;
   p.n_tiles = (N + bn - 1) / bn;
   p.kb1 = (K + 63) / 64;
   p.kb2 = (K2 + 63) / 64;
@@ -519,7 +572,7 @@ static int gemm_impl(const void* A, int64_t lda, int a_kmajor_rows_are_k, const 
   };
   auto mapB = [&](CUtensorMap* t, const void* ptr, int64_t ld, int kdim, int gr, int gc) {
     return b_mn ? make_tmap_2d_bf16(t, ptr, kdim + G1 * gr, N + G1 * gc, ld, 64, 64)
-                : make_tmap_2d_bf16(t, ptr, N + G1 * gr, kdim + G1 * gc, ld, bn, 64);
+                : make_tmap_2d_bf16(t, ptr, N + G1 * gr, kdim + G1 * gc, ld, pair ? bn / 2 : bn, 64);
   };
   if (K > 0) {
     if ((rc = mapA(&tmA, A, lda, K, gg.a_gr, gg.a_gc)) || (rc = mapB(&tmB, B, ldb, K, gg.b_gr, gg.b_gc)))
@@ -550,6 +603,12 @@ static int gemm_impl(const void* A, int64_t lda, int a_kmajor_rows_are_k, const 
     if (!a_mn && b_mn) return launch_gemm<BN_, false, true>(tmA, tmB, tmA2, tmB2, tmC, tmAux, p, st);   \
     if (a_mn && !b_mn) return launch_gemm<BN_, true, false>(tmA, tmB, tmA2, tmB2, tmC, tmAux, p, st);   \
     return launch_gemm<BN_, true, true>(tmA, tmB, tmA2, tmB2, tmC, tmAux, p, st);                       \
+  }
+  if (pair) {
+    if (!a_mn && !b_mn) return launch_gemm<256, false, false, true>(tmA, tmB, tmA2, tmB2, tmC, tmAux, p, st);
+    if (!a_mn && b_mn) return launch_gemm<256, false, true, true>(tmA, tmB, tmA2, tmB2, tmC, tmAux, p, st);
+    if (a_mn && !b_mn) return launch_gemm<256, true, false, true>(tmA, tmB, tmA2, tmB2, tmC, tmAux, p, st);
+    return launch_gemm<256, true, true, true>(tmA, tmB, tmA2, tmB2, tmC, tmAux, p, st);
   }
   DISPATCH(256)
   DISPATCH(128)
