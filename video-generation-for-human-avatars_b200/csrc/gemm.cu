@@ -294,43 +294,53 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         // buffer and hands it to the TMA (cp.async.bulk.tensor store clips rows/columns past M, N).
         const uint32_t stg = stage_base + (warp - 4) * 4096;
         const int row0 = mt * 128 + ew * 32;
-        const bool two_pass = (p.epi == EPI_GELU) && p.aux;  // pre-activation slab first, then the output
+        const bool stash = (p.epi == EPI_GELU) && p.aux;  // the bf16 pre-activation leaves through a second store
 #pragma unroll 1
         for (int c = chalf * (BN / 2); c < (chalf + 1) * (BN / 2); c += 64) {
           const int n_slab = nt * BN + c;
           if (n_slab >= p.N) break;
-#pragma unroll 1
-          for (int pass = two_pass ? 0 : 1; pass < 2; ++pass) {
-            if (lane == 0) tma_store_wait_read<0>();  // the previous slab has left the staging buffer
+          uint4 prer[8];  // pre-activation of this thread's 64 columns (stash mode), kept for the second store
+          if (lane == 0) tma_store_wait_read<0>();  // the previous slab has left the staging buffer
+          __syncwarp();
+#pragma unroll
+          for (int hc = 0; hc < 2; ++hc) {
+            uint32_t r[32];
+            tmem_ld32(t_row + c + hc * 32, r);
+            tmem_ld_wait();
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              const int n = n_slab + hc * 32 + g * 8;
+              float v[8];
+#pragma unroll
+              for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[g * 8 + i]);
+              uint4 u, pre = make_uint4(0, 0, 0, 0);
+              if (n < p.N) epi_math8(v, pre, n, row_ok, p, bias_g, gate_row, res_row, aux_row);
+              prer[hc * 4 + g] = pre;
+              u.x = pack_bf16x2(v[0], v[1]); u.y = pack_bf16x2(v[2], v[3]);
+              u.z = pack_bf16x2(v[4], v[5]); u.w = pack_bf16x2(v[6], v[7]);
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stg + sw128_off(lane, hc * 4 + g)),
+                           "r"(u.x), "r"(u.y), "r"(u.z), "r"(u.w)
+                           : "memory");
+            }
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_2d(&tmC, stg, n_slab + ccol, row0 + crow);
+            tma_store_commit();
+          }
+          if (stash) {
+            if (lane == 0) tma_store_wait_read<0>();
             __syncwarp();
 #pragma unroll
-            for (int hc = 0; hc < 2; ++hc) {
-              uint32_t r[32];
-              tmem_ld32(t_row + c + hc * 32, r);
-              tmem_ld_wait();
-#pragma unroll
-              for (int g = 0; g < 4; ++g) {
-                const int n = n_slab + hc * 32 + g * 8;
-                float v[8];
-#pragma unroll
-                for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[g * 8 + i]);
-                uint4 u, pre = make_uint4(0, 0, 0, 0);
-                if (n < p.N) epi_math8(v, pre, n, row_ok, p, bias_g, gate_row, res_row, aux_row);
-                if (pass == 0) {
-                  u = pre;
-                } else {
-                  u.x = pack_bf16x2(v[0], v[1]); u.y = pack_bf16x2(v[2], v[3]);
-                  u.z = pack_bf16x2(v[4], v[5]); u.w = pack_bf16x2(v[6], v[7]);
-                }
-                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stg + sw128_off(lane, hc * 4 + g)),
-                             "r"(u.x), "r"(u.y), "r"(u.z), "r"(u.w)
-                             : "memory");
-              }
-            }
+            for (int j = 0; j < 8; ++j)
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stg + sw128_off(lane, j)), "r"(prer[j].x),
+                           "r"(prer[j].y), "r"(prer[j].z), "r"(prer[j].w)
+                           : "memory");
             fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) {
-              tma_store_2d(pass == 0 ? &tmAux : &tmC, stg, n_slab + ccol, row0 + crow);
+              tma_store_2d(&tmAux, stg, n_slab + ccol, row0 + crow);
               tma_store_commit();
             }
           }
