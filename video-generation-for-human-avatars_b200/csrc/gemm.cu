@@ -69,9 +69,10 @@ __device__ __forceinline__ float gelu_tanh_grad(float x) {
 
 // Fused epilogue math on 8 consecutive columns of one output row: + bias -> GELU (on the bf16-rounded
 // pre-activation, which is returned in `pre`) / GELU' -> * gate -> + residual.
-__device__ __forceinline__ void epi_math8(float (&v)[8], uint4& pre, int n, bool ld_ok, const GemmParams& p,
-                                          const bf16* bias, const bf16* gate_row, const bf16* res_row,
-                                          const bf16* aux_row) {
+// `ext` = this thread's 8 values of the external row operand (residual, or the stashed pre-activation for
+// GELU'), loaded by the caller ahead of the TMEM reads so that its global-load latency is paid once per slab.
+__device__ __forceinline__ void epi_math8(float (&v)[8], uint4& pre, int n, const GemmParams& p, const bf16* bias,
+                                          const bf16* gate_row, bool has_res, const uint4& ext) {
   if (bias) {
     uint4 u = __ldg(reinterpret_cast<const uint4*>(bias + n));
     v[0] += bf16_lo(u.x); v[1] += bf16_hi(u.x); v[2] += bf16_lo(u.y); v[3] += bf16_hi(u.y);
@@ -87,7 +88,7 @@ __device__ __forceinline__ void epi_math8(float (&v)[8], uint4& pre, int n, bool
 #pragma unroll
     for (int i = 0; i < 8; ++i) v[i] = gelu_tanh(v[i]);
   } else if (p.epi == EPI_GELU_GRAD) {
-    uint4 u = ld_ok ? *reinterpret_cast<const uint4*>(aux_row + n) : make_uint4(0, 0, 0, 0);
+    const uint4 u = ext;
     float h[8] = {bf16_lo(u.x), bf16_hi(u.x), bf16_lo(u.y), bf16_hi(u.y),
                   bf16_lo(u.z), bf16_hi(u.z), bf16_lo(u.w), bf16_hi(u.w)};
 #pragma unroll
@@ -98,8 +99,8 @@ __device__ __forceinline__ void epi_math8(float (&v)[8], uint4& pre, int n, bool
     v[0] *= bf16_lo(u.x); v[1] *= bf16_hi(u.x); v[2] *= bf16_lo(u.y); v[3] *= bf16_hi(u.y);
     v[4] *= bf16_lo(u.z); v[5] *= bf16_hi(u.z); v[6] *= bf16_lo(u.w); v[7] *= bf16_hi(u.w);
   }
-  if (res_row && ld_ok) {
-    uint4 u = *reinterpret_cast<const uint4*>(res_row + n);
+  if (has_res) {
+    const uint4 u = ext;
     v[0] += bf16_lo(u.x); v[1] += bf16_hi(u.x); v[2] += bf16_lo(u.y); v[3] += bf16_hi(u.y);
     v[4] += bf16_lo(u.z); v[5] += bf16_hi(u.z); v[6] += bf16_lo(u.w); v[7] += bf16_hi(u.w);
   }
@@ -300,6 +301,17 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           const int n_slab = nt * BN + c;
           if (n_slab >= p.N) break;
           uint4 prer[8];  // pre-activation of this thread's 64 columns (stash mode), kept for the second store
+          // residual / stashed pre-activation of this thread's 64 columns: eight independent row-strided
+          // 16-byte loads in flight together, before the TMEM reads (issued one by one behind them they
+          // cost ~8 x the L2 latency per slab and made the gate+residual and GELU' epilogues the bottleneck)
+          uint4 ext[8];
+          const bf16* ext_row = p.epi == EPI_GELU_GRAD ? aux_row : res_row;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            ext[j] = make_uint4(0, 0, 0, 0);
+            if (ext_row != nullptr && row_ok && n_slab + j * 8 < p.N)
+              ext[j] = *reinterpret_cast<const uint4*>(ext_row + n_slab + j * 8);
+          }
           if (lane == 0) tma_store_wait_read<0>();  // the previous slab has left the staging buffer
           __syncwarp();
 #pragma unroll
@@ -314,7 +326,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 #pragma unroll
               for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[g * 8 + i]);
               uint4 u, pre = make_uint4(0, 0, 0, 0);
-              if (n < p.N) epi_math8(v, pre, n, row_ok, p, bias_g, gate_row, res_row, aux_row);
+              if (n < p.N) epi_math8(v, pre, n, p, bias_g, gate_row, p.res != nullptr, ext[hc * 4 + g]);
               prer[hc * 4 + g] = pre;
               u.x = pack_bf16x2(v[0], v[1]); u.y = pack_bf16x2(v[2], v[3]);
               u.z = pack_bf16x2(v[4], v[5]); u.w = pack_bf16x2(v[6], v[7]);
