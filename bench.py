@@ -291,6 +291,14 @@ def run_b200(args):
                              "avg_launch_ms": dom["ms"] / dom["launches"],
                              "time_share_by_family": share, "b200_kernel_ms_per_step": b200_kernel_ms_per_step,
                              "family_tflops": fam_tflops, "family_gbs": fam_gbs},
+                # BASELINE metric, second half: attention TFLOP/s against the bf16 tensor peak (attn1 = the
+                # 3D-RoPE self-attention flash kernels; algorithmic FLOPs 4 / 8 x B H Nq Nk 64)
+                "attention": {"attn1_fwd_tflops": fam_tflops.get("fa_fwd"), "attn1_bwd_tflops": fam_tflops.get("fa_bwd"),
+                              "attn2_fwd_tflops": fam_tflops.get("fa_fwd_attn2"),
+                              "attn2_bwd_tflops": fam_tflops.get("fa_bwd_attn2"),
+                              "attn1_fwd_frac_of_peak": round(fam_tflops.get("fa_fwd", 0.0) / peaks["tflops"], 4),
+                              "attn1_bwd_frac_of_peak": round(fam_tflops.get("fa_bwd", 0.0) / peaks["tflops"], 4),
+                              "timed": "CUDA events around every launch during the warm-up steps, inside the full train step (power-capped clocks)"},
                 "clocks": clocks, "loss": float(last)}
         if args.layers:
             line["config"]["INVALID_reduced_layers"] = True

@@ -230,7 +230,7 @@ def fa_fwd(q, k, v, B, H, Nq, Nk, key_bias=None, scale=0.125, need_lse=True):
     if key_bias is not None and (key_bias.dtype != torch.float32 or tuple(key_bias.shape) != (B, Nk)
                                  or not key_bias.is_contiguous()):
         raise _lib.B200Error("fa_fwd: key_bias must be contiguous fp32 [B, Nk]")
-    _call("fa_fwd", 4.0 * B * H * Nq * Nk * 64, "flop", _L().b200_fa_fwd, _p(q), q.stride(0), _p(k), k.stride(0), _p(v), v.stride(0), _p(o), o.stride(0),
+    _call("fa_fwd" if Nq == Nk else "fa_fwd_attn2", 4.0 * B * H * Nq * Nk * 64, "flop", _L().b200_fa_fwd, _p(q), q.stride(0), _p(k), k.stride(0), _p(v), v.stride(0), _p(o), o.stride(0),
                           _p(lse), _p(key_bias), B, H, Nq, Nk, 64, scale, _s())
     return o, lse
 
@@ -257,7 +257,7 @@ def fa_bwd(q, k, v, o, do, lse, B, H, Nq, Nk, dk, dv, key_bias=None, scale=0.125
     dq = dq_accum if dq_accum is not None else torch.zeros((B * Nq, H * 64), device=q.device, dtype=torch.float32)
     ws_bytes = _L().b200_fa_bwd_workspace_bytes(B, H, Nq, Nk)
     ws = torch.empty(ws_bytes, device=q.device, dtype=torch.uint8) if ws_bytes else None
-    _call("fa_bwd", 8.0 * B * H * Nq * Nk * 64, "flop", _L().b200_fa_bwd, _p(q), q.stride(0), _p(k), k.stride(0), _p(v), v.stride(0), _p(do), do.stride(0),
+    _call("fa_bwd" if Nq == Nk else "fa_bwd_attn2", 8.0 * B * H * Nq * Nk * 64, "flop", _L().b200_fa_bwd, _p(q), q.stride(0), _p(k), k.stride(0), _p(v), v.stride(0), _p(do), do.stride(0),
                           _p(lse), _p(delta), _p(key_bias), _p(dq), dq.stride(0), _p(dk), dk.stride(0),
                           _p(dv), dv.stride(0), B, H, Nq, Nk, 64, scale, _p(ws), ws_bytes, _s(),
                           launches=2 if ws_bytes else 1)
