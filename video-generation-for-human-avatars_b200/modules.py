@@ -216,11 +216,12 @@ def block_forward(block, hidden_states, freqs_cis=None, attention_mask=None, enc
     x2d = hidden_states.reshape(B * N, D)
     strat = _strategy_name(skip_layer_strategy)
 
-    h = ops.NormModFn.apply(x2d, scale_msa, shift_msa, rpm, 1e-6, False)
+    # the residual input leaves the norm node as its own output: its gradient is added inside norm_mod_bwd
+    h, x_res = ops.NormModResFn.apply(x2d, scale_msa, shift_msa, rpm, 1e-6, False)
     x1 = attention_forward(block.attn1, h.view(B, N, D), freqs_cis=freqs_cis,
                            encoder_hidden_states=encoder_hidden_states if block.only_cross_attention else None,
                            attention_mask=attention_mask, skip_layer_mask=skip_layer_mask,
-                           skip_layer_strategy=skip_layer_strategy, gate=gate_msa, rows_per_gate=rpm, res=x2d)
+                           skip_layer_strategy=skip_layer_strategy, gate=gate_msa, rows_per_gate=rpm, res=x_res)
     x1_2d = x1.reshape(B * N, D)
     if block.attn2 is not None:
         x2 = attention_forward(block.attn2, x1, freqs_cis=freqs_cis, encoder_hidden_states=encoder_hidden_states,
@@ -228,12 +229,12 @@ def block_forward(block, hidden_states, freqs_cis=None, attention_mask=None, enc
         x2_2d = x2.reshape(B * N, D)
     else:
         x2_2d = x1_2d
-    h2 = ops.NormModFn.apply(x2_2d, scale_mlp, shift_mlp, rpm, 1e-6, False)
+    h2, x2_res = ops.NormModResFn.apply(x2_2d, scale_mlp, shift_mlp, rpm, 1e-6, False)
     W1, b1, l1 = linear_parts(block.ff.net[0].proj)
     W2, b2, l2 = linear_parts(block.ff.net[2])
     if l1 is not None or l2 is not None:
         raise B200Error("LoRA on the feed-forward is not built (reference targets attn2 only, training.py:51-60)")
-    out = ops.FeedForwardFn.apply(h2, W1, b1, W2, b2, gate_mlp, rpm, x2_2d).view(B, N, D)
+    out = ops.FeedForwardFn.apply(h2, W1, b1, W2, b2, gate_mlp, rpm, x2_res).view(B, N, D)
     if skip_layer_mask is not None and strat == SkipLayerStrategy.TransformerBlock:
         m = skip_layer_mask.view(-1, 1, 1).to(out.dtype)
         out = out * m + hidden_states * (1.0 - m)

@@ -403,10 +403,12 @@ class LinearFn(torch.autograd.Function):
             dt = gemm(g, b_pad, b_rows_are_k=True, block_n=64)          # [M,64] = g (sB)
         if need[0]:
             dx = gemm(g, W, b_rows_are_k=True, a2=dt, b2=a_pad if has_lora else None)
+        # the rank-r column views make the GEMMs write exactly [r, K] / [N, r] tensors: autograd can take them as
+        # .grad without the copy it makes for a slice of a padded buffer
         if has_lora and need[3]:
-            dA = gemm(dt, x, a_rows_are_k=True, b_rows_are_k=True, out_dtype=torch.float32, split_k=0)[:r]
+            dA = gemm(dt[:, :r], x, a_rows_are_k=True, b_rows_are_k=True, out_dtype=torch.float32, split_k=0)
         if has_lora and need[4]:
-            dB = gemm(g, t, a_rows_are_k=True, b_rows_are_k=True, out_dtype=torch.float32, block_n=64, split_k=0)[:, :r]
+            dB = gemm(g, t[:, :r], a_rows_are_k=True, b_rows_are_k=True, out_dtype=torch.float32, block_n=64, split_k=0)
             dB = dB * scaling if scaling != 1.0 else dB
         if need[1]:
             dW = gemm(g, x, a_rows_are_k=True, b_rows_are_k=True)
@@ -472,6 +474,32 @@ class NormModFn(torch.autograd.Function):
                                  "(train_mode='full' is outside the round-1 scope)")
         dy = dy if dy.stride(1) == 1 else dy.contiguous()
         return norm_mod_bwd(dy, x, scale, rpm, eps, ln), None, None, None, None, None
+
+
+class NormModResFn(torch.autograd.Function):
+    """(y, x_res) = (norm(x) * (1 + scale) + shift, x): the residual branch leaves through the same node, so the
+    backward adds its gradient inside the norm kernel (`dres`) instead of autograd launching an add at the join."""
+
+    @staticmethod
+    def forward(ctx, x, scale, shift, rows_per_mod, eps, layernorm):
+        y = norm_mod_fwd(x, scale, shift, rows_per_mod, eps, layernorm)
+        ctx.save_for_backward(x, scale)
+        ctx.meta = (rows_per_mod, eps, layernorm)
+        return y, x.view_as(x)
+
+    @staticmethod
+    def backward(ctx, dy, dres):
+        x, scale = ctx.saved_tensors
+        rpm, eps, ln = ctx.meta
+        if ctx.needs_input_grad[1] or ctx.needs_input_grad[2]:
+            raise _lib.B200Error("NormModResFn: gradients of the AdaLN scale/shift are not built "
+                                 "(train_mode='full' is outside the round-1 scope)")
+        if dy is None:
+            return dres, None, None, None, None, None
+        dy = dy if dy.stride(1) == 1 else dy.contiguous()
+        if dres is not None and dres.stride(1) != 1:
+            dres = dres.contiguous()
+        return norm_mod_bwd(dy, x, scale, rpm, eps, ln, dres=dres), None, None, None, None, None
 
 
 class AttnCoreFn(torch.autograd.Function):
