@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py — LTXV-2B LoRA(attn2) + caption-projection rectified-flow train step, latent tokens/s.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload cfg2|cfg3|cfg1] [--impl b200|reference]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload cfg2|cfg3|cfg1|cfg4|cfg5] [--impl b200|reference]
   python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
 A step = one optimiser micro-step of the hot path on one synthetic batch per GPU: noising + velocity
@@ -32,6 +32,8 @@ WORKLOADS = {
     "cfg2": (1, 16, 16, 24, "LTXV-2B bf16 LoRA train step bs1 121x512x768 (6144 latent tokens)"),
     "cfg3": (4, 13, 16, 16, "LTXV-2B bf16 LoRA train step bs4/GPU 97x512x512 (4x3328 latent tokens)"),
     # long clip: ONE sample sequence-sharded over all ranks (ring attn1); strong scaling, not the default
+    # sampling: forward-only, 40 denoise steps per "step" of the bench; not the default workload
+    "cfg4": (1, 16, 15, 22, "LTXV-2B bf16 rectified-flow sampling bs1 121x480x704 (5280 latent tokens), 40 Euler steps, forward only"),
     "cfg5": (1, 33, 16, 24, "LTXV-2B bf16 LoRA train step bs1 257x512x768 (12672 latent tokens), sequence-sharded ring attn1"),
 }
 METRIC = "LTXV-2B train-step latent tok/s"
@@ -140,6 +142,66 @@ def run_reference(args):
 # ---------------------------------------------------------------------------------------------
 # b200 arm
 # ---------------------------------------------------------------------------------------------
+def run_sampling(args):
+    """cfg4: one bench step = one 40-step rectified-flow sampling run through api.denoise (forward-only kernels)."""
+    import torch
+    from b200_ltx import api, lib, ops
+    torch.cuda.set_device(0)
+    lib.require_device()
+    dev = torch.device("cuda", 0)
+    B, F, H, W, desc = WORKLOADS["cfg4"]
+    N, n_steps = F * H * W, 40
+    cfg = dict(api.LTXV_2B_CONFIG)
+    torch.manual_seed(0)
+    model = api.build_model(cfg, device=dev).eval()
+    g = torch.Generator(device="cpu").manual_seed(1234)
+    host = {"noise": torch.randn(B, N, 128, generator=g).bfloat16().pin_memory(),
+            "pose": torch.randn(B, 128, F, H, W, generator=g).bfloat16().pin_memory(),
+            "ref": torch.randn(B, 128, 1, H, W, generator=g).bfloat16().pin_memory()}
+    prompt = torch.randn(1, N_CTX, cfg["caption_channels"], generator=g).bfloat16().to(dev)
+    mask = torch.ones(1, N_CTX, dtype=torch.long)
+    mask[:, VALID_CTX:] = 0
+    mask = mask.to(dev)
+    coords = api.SymmetricPatchifier(1).get_latent_coords(F, H, W, B, dev).float()
+    coords[:, 0] = coords[:, 0] * (8.0 / 25)   # pixel-space fractional coordinates as the pipeline builds them
+    coords[:, 1:] = coords[:, 1:] * 32.0
+    sched = api.RectifiedFlowScheduler()
+    out_host = torch.empty(B, N, 128, dtype=torch.bfloat16).pin_memory()
+
+    def run(e2e):
+        x = host["noise"].to(dev, non_blocking=True).clone()
+        pose, ref = host["pose"].to(dev, non_blocking=True), host["ref"].to(dev, non_blocking=True)
+        x = api.denoise(model, x, coords, ref, pose, prompt, mask, sched, num_inference_steps=n_steps)
+        if e2e:
+            out_host.copy_(x, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+    for _ in range(max(1, min(args.warmup, 2))):
+        run(False)
+    sampler = ClockSampler(0)
+    sampler.start()
+    l0 = ops.launch_count
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        run(True)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / args.steps
+    clocks = sampler.stop()
+    evals = B * N * n_steps
+    line = {"metric": "LTXV-2B sampling latent token-evals/s", "value": evals / (ms / 1e3), "unit": "latent token-evals/s",
+            "n_gpus": 1, "steps": args.steps, "warmup": max(1, min(args.warmup, 2)), "ms_per_step": ms,
+            "ms_per_denoise_step": ms / n_steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": desc, "denoise_steps": n_steps, "tokens": N, "layers": cfg["num_layers"]},
+            "e2e": {"value": evals / (ms / 1e3), "unit": "latent token-evals/s",
+                    "h2d_bytes_per_step": sum(v.numel() * 2 for v in host.values()),
+                    "d2h_bytes_per_step": out_host.numel() * 2},
+            "gpu_launches": (ops.launch_count - l0) // args.steps, "clocks": clocks}
+    print(json.dumps(line), flush=True)
+
+
 def run_b200(args):
     import torch
     import torch.distributed as dist
@@ -322,6 +384,8 @@ def main():
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.workload == "cfg4":
+        run_sampling(args)
     else:
         run_b200(args)
 
