@@ -235,7 +235,8 @@ def run_b200(args):
     if seq_parallel and world > 1:
         api.enable_sequence_parallel(model)  # gradients are per-shard partial means: the bucketer averages them
     bucketer = GradBucketer(named) if world > 1 else None
-    opt = torch.optim.AdamW([p for _, p in named], lr=1e-4, fused=True)
+    use_graph = not args.no_graph
+    opt = torch.optim.AdamW([p for _, p in named], lr=1e-4, fused=True, capturable=use_graph)
     sched, patch = api.RectifiedFlowScheduler(), api.SymmetricPatchifier(1)
 
     class Cfg:
@@ -264,7 +265,7 @@ def run_b200(args):
         if bucketer is not None:
             bucketer.finish()
         opt.step()
-        return loss
+        return loss.detach()  # no reference to the autograd graph survives the step (CUDA-graph capture needs that)
 
     def sync_all():
         torch.cuda.synchronize()
@@ -301,21 +302,39 @@ def run_b200(args):
     fam_tflops = {f: round(d["work"] / d["ms"] / 1e9, 1) for f, d in fam.items() if d["unit"] == "flop"}
     fam_gbs = {f: round(d["work"] / d["ms"] / 1e6, 1) for f, d in fam.items() if d["unit"] == "byte"}
 
+    # the dominant family's launches, timed live with CUDA events (eager launches: events cannot sit inside a graph)
+    ops.timer = ops.KernelTimer([dominant], every=5)  # 1-in-5 sampling keeps the event overhead < 1 %
+    l0 = ops.launch_count
+    for _ in range(2):
+        step(resident)
+    launches = (ops.launch_count - l0) // 2
+    dom = ops.timer.summary()[dominant]
+    ops.timer = None
+
+    graphed = None
+    if use_graph:
+        # the whole micro-step (zero grads .. optimizer update, DP all-reduce included) as ONE CUDA graph
+        graphed = train.GraphedTrainStep(model, opt, sched, patch, Cfg, prompt, mask, resident, bucketer=bucketer,
+                                         device=dev)
+        launches = graphed.launches
+
     # timed region 1: device-resident inputs
     sampler = ClockSampler(torch.cuda.current_device() if "CUDA_VISIBLE_DEVICES" not in os.environ else local)
     sampler.start()
-    ops.timer = ops.KernelTimer([dominant], every=5)  # 1-in-5 sampling keeps the event overhead < 1 %
-    l0 = ops.launch_count
-    ms_total = timed(lambda: step(resident), args.steps)
-    launches = (ops.launch_count - l0) // args.steps
-    dom = ops.timer.summary()[dominant]
-    ops.timer = None
+    if graphed is not None:
+        graphed()  # first replay outside the timed region
+        ms_total = timed(lambda: graphed(), args.steps)
+        last = graphed.loss
+    else:
+        ms_total = timed(lambda: step(resident), args.steps)
     clocks = sampler.stop()
 
     # timed region 2: end to end (pinned host -> device every step, loss read back every step)
     def e2e_step():
-        batch = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
-        loss = step(batch)
+        if graphed is not None:
+            loss = graphed(host)  # pinned host -> static device buffers, then one graph replay
+        else:
+            loss = step({k: v.to(dev, non_blocking=True) for k, v in host.items()})
         loss_host.copy_(loss.detach().float(), non_blocking=True)
         torch.cuda.current_stream().synchronize()
         return float(loss_host)
@@ -343,6 +362,7 @@ def run_b200(args):
                            "valid_caption_tokens": VALID_CTX, "lora_rank": LORA_RANK, "layers": cfg["num_layers"],
                            "optimizer": "AdamW(fused) on 27.3M trainable params, inside the timed step",
                            "parallelism": f"sp{world} (ring attn1)" if seq_parallel else f"dp{world}",
+                           "launch": "whole micro-step replayed as one CUDA graph" if graphed is not None else "eager launches",
                            "l2": "not flushed: every step streams 3.85 GB of weights plus >10 GB of activations, far larger than the 126 MB L2"},
                 "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
                         "h2d_bytes_per_step": h2d_bytes * world, "d2h_bytes_per_step": 4 * world},
@@ -381,6 +401,7 @@ def main():
     ap.add_argument("--workload", default="cfg2", choices=list(WORKLOADS))
     ap.add_argument("--layers", type=int, default=0, help="debug only: fewer blocks (marks the line INVALID)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="launch the step kernel by kernel instead of replaying a CUDA graph")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

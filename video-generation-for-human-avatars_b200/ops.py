@@ -345,7 +345,7 @@ def prestage_lora(adapters) -> None:
         bs = torch.stack([B.detach() for _, B, _ in items])
         scal = [float(s) for _, _, s in items]
         if any(x != 1.0 for x in scal):
-            bs = bs * torch.tensor(scal, device=dev, dtype=bs.dtype).view(n, 1, 1)
+            bs = torch.stack([b * x for b, x in zip(bs.unbind(0), scal)])  # python scalars: graph-capturable
         b_all[:, :, :r] = bs
         for i, (A, _, _) in enumerate(items):
             _lora_stage_cache[id(A)] = (a_all[i], b_all[i], A._version)
