@@ -235,7 +235,7 @@ def run_b200(args):
     if seq_parallel and world > 1:
         api.enable_sequence_parallel(model)  # gradients are per-shard partial means: the bucketer averages them
     bucketer = GradBucketer(named) if world > 1 else None
-    use_graph = not args.no_graph
+    use_graph = not args.no_graph and args.workload != "cfg5"  # ring P2P hops are not captured
     opt = torch.optim.AdamW([p for _, p in named], lr=1e-4, fused=True, capturable=use_graph)
     sched, patch = api.RectifiedFlowScheduler(), api.SymmetricPatchifier(1)
 
@@ -288,6 +288,11 @@ def run_b200(args):
         return float(ms)
 
     resident = {k: v.to(dev) for k, v in host.items()}
+    if args.profile_steps:
+        for _ in range(2 + args.profile_steps):
+            step(resident)
+        torch.cuda.synchronize()
+        return
 
     # warm-up, with every kernel family timed to find the dominant one
     ops.timer = ops.KernelTimer()
@@ -362,7 +367,9 @@ def run_b200(args):
                            "valid_caption_tokens": VALID_CTX, "lora_rank": LORA_RANK, "layers": cfg["num_layers"],
                            "optimizer": "AdamW(fused) on 27.3M trainable params, inside the timed step",
                            "parallelism": f"sp{world} (ring attn1)" if seq_parallel else f"dp{world}",
-                           "launch": "whole micro-step replayed as one CUDA graph" if graphed is not None else "eager launches",
+                           "launch": ("eager launches" if graphed is None else
+                                      "whole micro-step replayed as one CUDA graph" if world == 1 else
+                                      "two CUDA graphs (zero+fwd+bwd | optimizer) around the eager NCCL bucket all-reduce"),
                            "l2": "not flushed: every step streams 3.85 GB of weights plus >10 GB of activations, far larger than the 126 MB L2"},
                 "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
                         "h2d_bytes_per_step": h2d_bytes * world, "d2h_bytes_per_step": 4 * world},
@@ -402,6 +409,8 @@ def main():
     ap.add_argument("--layers", type=int, default=0, help="debug only: fewer blocks (marks the line INVALID)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch the step kernel by kernel instead of replaying a CUDA graph")
+    ap.add_argument("--profile-steps", type=int, default=0,
+                    help="ncu helper: run this many eager steps after 2 warm-up steps and exit (no JSON line)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

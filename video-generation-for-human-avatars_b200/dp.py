@@ -31,6 +31,7 @@ class GradBucketer:
             cur["params"].append(p)
             cur["bytes"] += nbytes
         self._handles = []
+        self.overlap = True  # False: hooks only count (GraphedTrainStep reduces after the captured backward)
         for b in self.buckets:
             total = sum(p.numel() for p in b["params"])
             b["flat"] = torch.zeros(total, dtype=b["dtype"], device=b["device"])
@@ -45,7 +46,7 @@ class GradBucketer:
     def _on_grad(self, p):
         b = self._bucket_of[id(p)]
         b["pending"] -= 1
-        if b["pending"] == 0 and self.world > 1:
+        if b["pending"] == 0 and self.world > 1 and self.overlap:
             self._handles.append(dist.all_reduce(b["flat"], op=dist.ReduceOp.SUM, group=self.group, async_op=True))
 
     def zero_grad(self):
@@ -67,6 +68,16 @@ class GradBucketer:
             for b in self.buckets:
                 b["flat"].div_(self.world)
         self._handles = []
+
+    def reduce_now(self):
+        """All-reduce and average every bucket at once (no overlap): used between the two CUDA graphs of a
+        graph-replayed step, where the Python hooks do not run."""
+        if self.world > 1:
+            hs = [dist.all_reduce(b["flat"], op=dist.ReduceOp.SUM, group=self.group, async_op=True) for b in self.buckets]
+            for h in hs:
+                h.wait()
+            for b in self.buckets:
+                b["flat"].div_(self.world)
 
     def bytes_per_step(self) -> int:
         return sum(b["bytes"] for b in self.buckets)

@@ -96,17 +96,21 @@ class GraphedTrainStep:
         self.static = {k: v.to(device).clone() for k, v in example_batch.items()}
         args = (scheduler, patchifier, config, prompt_embeds, prompt_attention_mask)
 
-        def one_step():
+        def fwd_bwd():
             if bucketer is not None:
                 bucketer.zero_grad()
             else:
                 optimizer.zero_grad(set_to_none=True)
             loss, rel_mse, nrmse, _ = train_step(model, self.static, *args, device=device)
             loss.backward()
+            return loss.detach(), rel_mse.detach(), nrmse.detach()
+
+        def one_step():
+            out = fwd_bwd()
             if bucketer is not None:
                 bucketer.finish()
             optimizer.step()
-            return loss.detach(), rel_mse.detach(), nrmse.detach()
+            return out
 
         if ops.timer is not None:
             raise RuntimeError("GraphedTrainStep: kernel timing events cannot be captured (ops.timer must be None)")
@@ -121,12 +125,24 @@ class GraphedTrainStep:
                 one_step()
         torch.cuda.current_stream(device).wait_stream(side)
         torch.cuda.synchronize(device)
+        l0 = ops.launch_count
+        self.graph = torch.cuda.CUDAGraph()
+        self.graph_opt = None
         if bucketer is None:
             optimizer.zero_grad(set_to_none=True)  # .grad is then allocated from the graph's private pool
-        self.graph = torch.cuda.CUDAGraph()
-        l0 = ops.launch_count
-        with torch.cuda.graph(self.graph):
-            self.loss, self.rel_mse, self.nrmse = one_step()
+            with torch.cuda.graph(self.graph):
+                self.loss, self.rel_mse, self.nrmse = one_step()
+        else:
+            # data parallel: graph 1 = zero grads + forward + backward (no collective is captured: the bucket
+            # hooks only count), then the ~84 MB of gradient buckets are all-reduced eagerly over NCCL
+            # (0.3 ms at NVLink rates, not worth a capture-time dependency on the communicator), then
+            # graph 2 = the optimizer update
+            bucketer.overlap = False
+            with torch.cuda.graph(self.graph):
+                self.loss, self.rel_mse, self.nrmse = fwd_bwd()
+            self.graph_opt = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph_opt, pool=self.graph.pool()):
+                optimizer.step()
         self.launches = ops.launch_count - l0  # b200 kernel launches captured per step
 
     def load(self, batch: dict, non_blocking: bool = True):
@@ -137,4 +153,7 @@ class GraphedTrainStep:
         if batch is not None:
             self.load(batch)
         self.graph.replay()
+        if self.graph_opt is not None:
+            self.bucketer.reduce_now()
+            self.graph_opt.replay()
         return self.loss
