@@ -36,6 +36,16 @@ def test_full_width_two_blocks():
 
 
 @pytest.mark.gpu
+def test_cfg2_token_count_full_width_two_blocks():
+    """BASELINE config 2 geometry (121x512x768 -> 16x16x24 = 6144 latent tokens, 256 caption tokens with 15 valid,
+    D = 2048 / 32 heads / FF 8192) on 2 blocks: the CTA-pair GEMMs, the multi-wave attention grids and the batched
+    caption K/V path at their real sizes, against the fp32 oracle on the same GPU."""
+    cfg = dict(rb.LTXV_2B, num_layers=2)
+    case = dict(b=1, f=16, h=16, w=24, n_ctx=256, valid_ctx=15, lora_rank=32, seed_w=6, seed_x=17, t=[0.35])
+    mc.run_parity(cfg, case)
+
+
+@pytest.mark.gpu
 def test_batched_caption_kv_path():
     """(B * caption tokens) % 128 == 0 and D % 256 == 0: the attn2 keys / values of all blocks come from one
     strided-batched projection (ops.CtxKVFn) -- 3 blocks, 2 x 64 caption tokens with 40 valid, ragged latents."""
