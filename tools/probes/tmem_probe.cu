@@ -28,7 +28,10 @@ __global__ void __launch_bounds__(640, 1) probe(int nwarps, int reps, int with_m
       for (int r = 0; r < reps; ++r) {
         if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k) umma_ss(tmem_base + 256, da0 + 2 * k, db0 + 2 * k, idesc, 1u);
+          for (int k = 0; k < 4; ++k) {
+            if (with_mma == 2) umma_ts(tmem_base + 256, tmem_base + 384 + k * 8, db0 + 2 * k, idesc, 1u);
+            else umma_ss(tmem_base + 256, da0 + 2 * k, db0 + 2 * k, idesc, 1u);
+          }
         }
         __syncwarp();
       }
@@ -60,6 +63,17 @@ __global__ void __launch_bounds__(640, 1) probe(int nwarps, int reps, int with_m
         tmem_st32(tmem_base + lane_bits + col, v);
         tmem_st_wait();
         acc++;
+      } else if (MODE == 4) {
+        uint32_t a[16], b[16], c8[8];
+        tmem_ld16(tmem_base + lane_bits + (col & 127), a);
+        tmem_ld16(tmem_base + lane_bits + 128 + (col & 127), b);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 8; ++i) c8[i] = a[i] ^ b[i] ^ acc;
+        tmem_st8(tmem_base + lane_bits + (col & 127), c8);
+        tmem_st8(tmem_base + lane_bits + 128 + (col & 127), c8);
+        tmem_st_wait();
+        acc += c8[0];
       } else {
         uint32_t a[32], b[32];
         tmem_ld32(tmem_base + lane_bits + col, a);
@@ -75,6 +89,7 @@ __global__ void __launch_bounds__(640, 1) probe(int nwarps, int reps, int with_m
   if (threadIdx.x == 0 && blockIdx.x == 0) {
     long long mx = 0;
     for (int w = 0; w < nwarps; ++w) mx = t_end[w] > mx ? t_end[w] : mx;
+    if (nwarps == 0) mx = 1;
     out[0] = mx;
     out[1] = with_mma ? t_end[17] : 0;
   }
@@ -105,5 +120,10 @@ int main() {
   for (int nw : {4, 8, 16}) run<2>("st 32x32b.x32", nw, 0, 0, d);
   for (int nw : {4, 16}) for (int n : {64, 128, 256}) run<0>("ld x32 + SS mma", nw, 1, n, d);
   for (int nw : {4, 16}) run<2>("st x32 + SS mma", nw, 1, 128, d);
+  run<0>("ld x32 + TS mma N=64", 16, 2, 64, d);
+  run<4>("ld16x2+st8x2 + TS mma", 16, 2, 64, d);
+  run<4>("ld16x2+st8x2 + SS mma", 16, 1, 64, d);
+  run<4>("ld16x2+st8x2 alone", 16, 0, 0, d);
+  run<0>("(none) TS mma N=64", 0, 2, 64, d);
   return 0;
 }
