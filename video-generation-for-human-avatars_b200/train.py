@@ -87,10 +87,13 @@ class GraphedTrainStep:
     in a 95.5 ms step).  Replaying a graph removes the host from the step entirely.  Inputs live in static device
     buffers (`load()` copies a batch into them, from pinned host memory without a sync); the timestep / noise
     draws inside the graph use the graph-safe philox generator, so every replay draws fresh values.
-    The optimizer must be capturable (`torch.optim.AdamW(..., fused=True, capturable=True)`)."""
+    The optimizer must be capturable (`torch.optim.AdamW(..., fused=True, capturable=True)`).
+    Not for the sequence-parallel ring: its NCCL send/recv hops hang under stream capture (tried with both
+    capture error modes), so that path stays eager."""
 
     def __init__(self, model, optimizer, scheduler, patchifier, config, prompt_embeds, prompt_attention_mask,
-                 example_batch: dict, bucketer=None, warmup: int = 3, device=None):
+                 example_batch: dict, bucketer=None, warmup: int = 3, device=None,
+                 capture_error_mode: str = "global"):
         self.model, self.opt, self.bucketer = model, optimizer, bucketer
         device = device or next(model.parameters()).device
         self.static = {k: v.to(device).clone() for k, v in example_batch.items()}
@@ -130,7 +133,7 @@ class GraphedTrainStep:
         self.graph_opt = None
         if bucketer is None:
             optimizer.zero_grad(set_to_none=True)  # .grad is then allocated from the graph's private pool
-            with torch.cuda.graph(self.graph):
+            with torch.cuda.graph(self.graph, capture_error_mode=capture_error_mode):
                 self.loss, self.rel_mse, self.nrmse = one_step()
         else:
             # data parallel: graph 1 = zero grads + forward + backward (no collective is captured: the bucket
@@ -138,10 +141,10 @@ class GraphedTrainStep:
             # (0.3 ms at NVLink rates, not worth a capture-time dependency on the communicator), then
             # graph 2 = the optimizer update
             bucketer.overlap = False
-            with torch.cuda.graph(self.graph):
+            with torch.cuda.graph(self.graph, capture_error_mode=capture_error_mode):
                 self.loss, self.rel_mse, self.nrmse = fwd_bwd()
             self.graph_opt = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(self.graph_opt, pool=self.graph.pool()):
+            with torch.cuda.graph(self.graph_opt, pool=self.graph.pool(), capture_error_mode=capture_error_mode):
                 optimizer.step()
         self.launches = ops.launch_count - l0  # b200 kernel launches captured per step
 
