@@ -233,7 +233,8 @@ def run_b200(args):
     named = [(n, p) for n, p in model.named_parameters() if p.requires_grad]
     seq_parallel = args.workload == "cfg5"
     if seq_parallel and world > 1:
-        api.enable_sequence_parallel(model)  # gradients are per-shard partial means: the bucketer averages them
+        # gradients are per-shard partial means: the bucketer averages them
+        api.enable_sequence_parallel(model, mode=args.sp_mode)
     bucketer = GradBucketer(named) if world > 1 else None
     # the ring's NCCL send/recv hops do not survive stream capture here (the capture hangs, with either capture
     # error mode): cfg5 runs eagerly
@@ -368,7 +369,7 @@ def run_b200(args):
                            "caption_tokens": N_CTX,
                            "valid_caption_tokens": VALID_CTX, "lora_rank": LORA_RANK, "layers": cfg["num_layers"],
                            "optimizer": "AdamW(fused) on 27.3M trainable params, inside the timed step",
-                           "parallelism": f"sp{world} (ring attn1)" if seq_parallel else f"dp{world}",
+                           "parallelism": f"sp{world} ({args.sp_mode} attn1)" if seq_parallel else f"dp{world}",
                            "launch": ("eager launches" if graphed is None else
                                       "whole micro-step replayed as one CUDA graph" if world == 1 else
                                       "two CUDA graphs (zero+fwd+bwd | optimizer) around the eager NCCL bucket all-reduce"),
@@ -410,6 +411,8 @@ def main():
     ap.add_argument("--workload", default="cfg2", choices=list(WORKLOADS))
     ap.add_argument("--layers", type=int, default=0, help="debug only: fewer blocks (marks the line INVALID)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--sp-mode", default="ring", choices=["ring", "gather"],
+                    help="cfg5 under torchrun: K/V ring hops, or one all-gather + single attention launch per layer")
     ap.add_argument("--no-graph", action="store_true", help="launch the step kernel by kernel instead of replaying a CUDA graph")
     ap.add_argument("--profile-steps", type=int, default=0,
                     help="ncu helper: run this many eager steps after 2 warm-up steps and exit (no JSON line)")

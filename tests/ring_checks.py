@@ -13,7 +13,7 @@ for p in (ROOT, os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests")):
         sys.path.insert(0, p)
 
 
-def run(rank, world, verbose=True):
+def run(rank, world, verbose=True, mode="ring"):
     import model_checks as mc
     import ref_block as rb
     from b200_ltx import api
@@ -24,17 +24,18 @@ def run(rank, world, verbose=True):
     # split on frame boundaries at P=4 either
     f, h, w = 6, 4, 7 * (world // 2 if world > 2 else 1)
     P = rb.init_params(cfg, 32, seed=0)
-    batch = rb.synthetic_batch(cfg, 2, f, h, w, 24, 1234, 15)
+    nb = 1 if mode == "gather" else 2  # the all-gather mode is built for single long clips
+    batch = rb.synthetic_batch(cfg, nb, f, h, w, 24, 1234, 15)
     for k in ("latents", "pose_latents", "ref_image_latents", "prompt_embeds", "noise"):
         batch[k] = batch[k].to(torch.bfloat16).float()
     P = {k: (v if "lora_" in k else v.to(torch.bfloat16).float()) for k, v in P.items()}
-    t = torch.tensor([0.4, 0.73])
+    t = torch.tensor([0.4, 0.73][:nb])
     l32, o32, g32 = mc.oracle_loss_grads(P, cfg, batch, t, torch.float32, dev)
 
     def one(sharded):
         model = mc.build_b200_model(cfg, P, 32, dev)
         if sharded:
-            assert api.enable_sequence_parallel(model) is not None
+            assert api.enable_sequence_parallel(model, mode=mode) is not None
         holder = {}
         root = model.base_model.model
         hk = root.register_forward_hook(lambda m, a, o: holder.__setitem__("out", o.sample.detach()))
@@ -56,7 +57,7 @@ def run(rank, world, verbose=True):
     e_out = mc.rel(o_sp, o_full[:, sl])
     e_out32, e_full32 = mc.rel(o_sp, o32[:, sl]), mc.rel(o_full[:, sl], o32[:, sl])
     if verbose and rank == 0:
-        print(f"  ring P={world}: velocity shard vs un-sharded rel {e_out:.3e}; vs fp32 oracle {e_out32:.3e} "
+        print(f"  {mode} P={world}: velocity shard vs un-sharded rel {e_out:.3e}; vs fp32 oracle {e_out32:.3e} "
               f"(un-sharded {e_full32:.3e}); loss {float(lsum):.6f} vs {float(l_full):.6f} vs oracle {float(l32):.6f}")
     assert e_out32 <= max(2 * e_full32, mc.OUT_FLOOR), (e_out32, e_full32)
     assert abs(float(lsum) - float(l32)) / float(l32) < mc.OUT_FLOOR
@@ -74,6 +75,7 @@ def _spawned(rank, world, port):
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
     try:
         run(rank, world)
+        run(rank, world, verbose=False, mode="gather")
     finally:
         dist.destroy_process_group()
 
@@ -81,7 +83,8 @@ def _spawned(rank, world, port):
 if __name__ == "__main__":
     r, w = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     dist.init_process_group("nccl", device_id=torch.device("cuda", int(os.environ.get("LOCAL_RANK", r))))
-    run(int(os.environ.get("LOCAL_RANK", r)), w)
+    for m in ("ring", "gather"):
+        run(int(os.environ.get("LOCAL_RANK", r)), w, mode=m)
     dist.destroy_process_group()
     if r == 0:
         print("ring_checks ok")

@@ -638,7 +638,11 @@ class SelfAttnFn(torch.autograd.Function):
             if key_bias is not None:
                 raise _lib.B200Error("ring attn1: a key mask on the sharded self-attention is not built")
             from . import ring
-            o, lse, kv = ring.ring_fwd(qk[:, :D], qk[:, D:], qkv[:, 2 * D:], sp.group, B, H, N, scale, sp.impl)
+            if sp.mode == "gather":
+                o, lse, k_all, v_all = ring.gather_fwd(qk[:, :D], qk[:, D:], qkv[:, 2 * D:], sp.group, B, H, N, scale)
+                kv = torch.stack([k_all, v_all])  # [2, P*n, D] kept for the backward
+            else:
+                o, lse, kv = ring.ring_fwd(qk[:, :D], qk[:, D:], qkv[:, 2 * D:], sp.group, B, H, N, scale, sp.impl)
         y = gemm(o, Wo, bias=bo, gate=gate, rows_per_gate=rows_per_gate, res=res)
         ctx.save_for_backward(qkv, qk, o, lse, Wqkv, wqn, wkn, cos, sin, Wo, gate, key_bias, kv)
         ctx.meta = (B, H, N, scale, rows_per_gate, res is not None, sp)
@@ -660,9 +664,13 @@ class SelfAttnFn(torch.autograd.Function):
                           key_bias, scale)
         else:
             from . import ring
-            dq32, dkv = ring.ring_bwd(qk[:, :D], kv, o, do, lse, sp.group, B, H, N, scale, sp.impl)
-            dk_post = dkv[0]  # fp32, fully reduced over the ring
-            dqkv[:, 2 * D:].copy_(dkv[1])
+            if sp.mode == "gather":
+                dq32, dk_post, dv_loc = ring.gather_bwd(qk[:, :D], kv[0], kv[1], o, do, lse, sp.group, B, H, N, scale)
+                dqkv[:, 2 * D:].copy_(dv_loc)
+            else:
+                dq32, dkv = ring.ring_bwd(qk[:, :D], kv, o, do, lse, sp.group, B, H, N, scale, sp.impl)
+                dk_post = dkv[0]  # fp32, fully reduced over the ring
+                dqkv[:, 2 * D:].copy_(dkv[1])
         qknorm_rope_bwd(dq32, dk_post, qkv[:, :D], qkv[:, D:2 * D], wqn, wkn, cos, sin, dqkv[:, :D], dqkv[:, D:2 * D])
         dx = gemm(dqkv, Wqkv, b_rows_are_k=True) if ctx.needs_input_grad[0] else None
         dres = dy if (has_res and ctx.needs_input_grad[11]) else None

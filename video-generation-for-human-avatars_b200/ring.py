@@ -146,14 +146,52 @@ def ring_attention(q, k, v, group, B, H, n_local, scale, impl: Optional[LocalAtt
     return RingAttnFn.apply(q, k, v, group, B, H, n_local, scale, impl)
 
 
-class SequenceParallel:
-    """Per-model sequence-sharding state (set by api.enable_sequence_parallel)."""
+def gather_fwd(q, k, v, group, B, H, n_local, scale):
+    """All-gather variant: every rank collects all keys / values once (two NCCL all-gathers per layer) and runs ONE
+    flash-attention launch of its n_local queries against all N keys -- ~6 host operations per layer and direction
+    instead of ~16 P for the hop loop, which is what matters once the shards are small (P >= 4: the hop kernels take
+    0.15-0.25 ms each and the ring becomes launch bound).  No overlap of the transfer with the math (104 MB of K/V per
+    layer at cfg5, ~0.3 ms at NVLink all-gather rates, against ~1.5 ms of attention at P = 4).
+    Returns (out, lse, k_all, v_all)."""
+    world = dist.get_world_size(group)
+    D = H * 64
+    if B != 1:
+        raise ops._lib.B200Error("gather-mode sequence parallelism is built for batch 1 (long single clips)")
+    k_all = torch.empty((world * n_local, D), device=q.device, dtype=q.dtype)
+    v_all = torch.empty((world * n_local, D), device=q.device, dtype=q.dtype)
+    dist.all_gather_into_tensor(k_all, k.contiguous(), group=group)
+    dist.all_gather_into_tensor(v_all, v.contiguous(), group=group)
+    out, lse = ops.fa_fwd(q, k_all, v_all, B, H, n_local, world * n_local, None, scale)
+    return out, lse, k_all, v_all
 
-    def __init__(self, group=None, impl: Optional[LocalAttention] = None):
+
+def gather_bwd(q, k_all, v_all, out, do, lse, group, B, H, n_local, scale):
+    """Backward of gather_fwd: one flash backward against all keys, then reduce-scatter of the bf16 dK / dV partials
+    (rank r keeps the sum for its own shard).  Returns (dq fp32, dk bf16, dv bf16) for the local shard."""
+    world = dist.get_world_size(group)
+    D = H * 64
+    dk_all = torch.empty_like(k_all)
+    dv_all = torch.empty_like(v_all)
+    dq = ops.fa_bwd(q, k_all, v_all, out, do, lse, B, H, n_local, world * n_local, dk_all, dv_all, None, scale)
+    dk = torch.empty((n_local, D), device=q.device, dtype=k_all.dtype)
+    dv = torch.empty((n_local, D), device=q.device, dtype=k_all.dtype)
+    dist.reduce_scatter_tensor(dk, dk_all, op=dist.ReduceOp.SUM, group=group)
+    dist.reduce_scatter_tensor(dv, dv_all, op=dist.ReduceOp.SUM, group=group)
+    return dq, dk, dv
+
+
+class SequenceParallel:
+    """Per-model sequence-sharding state (set by api.enable_sequence_parallel).  mode: "ring" (K/V hops overlapped
+    with the per-hop attention, online-softmax merge) or "gather" (all-gather K/V, one attention launch)."""
+
+    def __init__(self, group=None, impl: Optional[LocalAttention] = None, mode: str = "ring"):
+        if mode not in ("ring", "gather"):
+            raise ValueError("sequence-parallel mode must be 'ring' or 'gather'")
         self.group = group
         self.rank = dist.get_rank(group)
         self.world = dist.get_world_size(group)
         self.impl = impl
+        self.mode = mode
 
     def shard(self, n_total: int):
         """(offset, length) of this rank's contiguous token shard."""
