@@ -411,7 +411,7 @@ def main():
     ap.add_argument("--workload", default="cfg2", choices=list(WORKLOADS))
     ap.add_argument("--layers", type=int, default=0, help="debug only: fewer blocks (marks the line INVALID)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--sp-mode", default="ring", choices=["ring", "gather"],
+    ap.add_argument("--sp-mode", default="gather", choices=["ring", "gather"],
                     help="cfg5 under torchrun: K/V ring hops, or one all-gather + single attention launch per layer")
     ap.add_argument("--no-graph", action="store_true", help="launch the step kernel by kernel instead of replaying a CUDA graph")
     ap.add_argument("--profile-steps", type=int, default=0,
