@@ -372,6 +372,36 @@ def check_key_sharded_merge():
     torch.cuda.synchronize()
 
 
+def check_empty_and_degenerate():
+    """Empty / degenerate inputs go through the C ABI without a launch fault: zero rows, zero queries, a single
+    token, one key."""
+    from b200_ltx import ops
+    z = torch.empty(0, 256, device="cuda", dtype=BF16)
+    w = _randn(512, 256, seed=1)
+    assert ops.gemm(z, w).shape == (0, 512)
+    assert ops.norm_mod_fwd(z, None, None, 1, 1e-6).shape == (0, 256)
+    q0 = torch.empty(0, 128, device="cuda", dtype=BF16)
+    k1, v1 = _randn(5, 128, seed=2), _randn(5, 128, seed=3)
+    o, _ = ops.fa_fwd(q0, k1, v1, 1, 2, 0, 5, None, 0.125)
+    assert o.shape == (0, 128)
+    # one query, one key: softmax of a single score is 1 -> o == v
+    q, k, v = _randn(1, 128, seed=4), _randn(1, 128, seed=5), _randn(1, 128, seed=6)
+    o, lse = ops.fa_fwd(q, k, v, 1, 2, 1, 1, None, 0.125)
+    _assert_close("fa_fwd 1 query x 1 key == v", o, v, 1e-6)
+    do = _randn(1, 128, seed=7)
+    dk, dv = torch.empty_like(k), torch.empty_like(v)
+    dq = ops.fa_bwd(q, k, v, o, do, lse, 1, 2, 1, 1, dk, dv, None, 0.125)
+    assert float(dq.abs().max()) < 1e-5 and float(dk.float().abs().max()) < 1e-5  # d softmax of one score is 0
+    _assert_close("fa_bwd 1x1 dv == do", dv, do, 1e-6)
+    # all keys but one masked with the reference's -10000 bias: attention collapses onto that key
+    q, k, v = _randn(130, 128, seed=8), _randn(70, 128, seed=9), _randn(70, 128, seed=10)
+    bias = torch.full((1, 70), -10000.0, device="cuda")
+    bias[0, 33] = 0.0
+    o, _ = ops.fa_fwd(q, k, v, 1, 2, 130, 70, bias, 0.125)
+    _assert_close("fa_fwd single unmasked key", o, v[33:34].expand(130, -1), 1e-6)
+    torch.cuda.synchronize()
+
+
 def check_rf_and_misc():
     from b200_ltx import ops
     B, N, C = 3, 96, 128
@@ -420,5 +450,6 @@ GROUPS = {
     "attention_bwd": check_attention_bwd,
     "attn_core_fn": check_attn_core_fn,
     "key_sharded_merge": check_key_sharded_merge,
+    "empty_and_degenerate": check_empty_and_degenerate,
     "rf_and_misc": check_rf_and_misc,
 }

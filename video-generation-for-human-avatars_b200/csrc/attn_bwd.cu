@@ -503,10 +503,10 @@ extern "C" int b200_fa_bwd(const void* q, int64_t ldq, const void* k, int64_t ld
                            void* dk, int64_t lddk, void* dv, int64_t lddv, int B, int H, int Nq, int Nk,
                            int head_dim, float scale, void* workspace, int64_t workspace_bytes,
                            void* stream) {
-  if (!(q && k && v && dout && lse && delta && dq_accum && dk && dv)) return arg_error("fa_bwd: null pointer");
   if (head_dim != 64) return arg_error("fa_bwd: only head_dim 64 is built (LTXV-2B: 32 heads x 64)");
   if (B < 0 || H <= 0 || Nq < 0 || Nk < 0) return arg_error("fa_bwd: bad shape");
   if (B == 0 || Nk == 0) return 0;
+  if (!(q && k && v && dout && lse && delta && dq_accum && dk && dv)) return arg_error("fa_bwd: null pointer");
   if (ldq % 8 || ldk % 8 || ldv % 8 || lddo % 8 || lddk % 8 || lddv % 8 || lddq % 4 || !al16(q) ||
       !al16(k) || !al16(v) || !al16(dout) || !al16(dq_accum) || !al16(dk) || !al16(dv))
     return arg_error("fa_bwd: tensors must be 16-byte aligned with 16-byte-multiple pitches");

@@ -350,10 +350,10 @@ static inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) 
 extern "C" int b200_fa_fwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v,
                            int64_t ldv, void* o, int64_t ldo, float* lse, const float* key_bias,
                            int B, int H, int Nq, int Nk, int head_dim, float scale, void* stream) {
-  if (!(q && k && v && o)) return arg_error("fa_fwd: null pointer");
   if (head_dim != 64) return arg_error("fa_fwd: only head_dim 64 is built (LTXV-2B: 32 heads x 64)");
   if (B < 0 || H <= 0 || Nq < 0 || Nk < 0) return arg_error("fa_fwd: bad shape");
-  if (B == 0 || Nq == 0) return 0;
+  if (B == 0 || Nq == 0) return 0;  // no queries: nothing to do (empty tensors carry null pointers)
+  if (!(q && k && v && o)) return arg_error("fa_fwd: null pointer");
   if (Nk == 0) return arg_error("fa_fwd: no keys");
   if (ldq % 8 || ldk % 8 || ldv % 8 || ldo % 8 || !al16(q) || !al16(k) || !al16(v) || !al16(o))
     return arg_error("fa_fwd: tensors must be 16-byte aligned with 16-byte-multiple pitches");

@@ -581,6 +581,7 @@ static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t
 extern "C" int b200_norm_mod_fwd(const void* x, int64_t ldx, void* y, int64_t ldy, const void* scale,
                                  const void* shift, int64_t mod_stride, int64_t rows, int D,
                                  int64_t rows_per_mod, float eps, int layernorm, void* stream) {
+  if (rows == 0 && D > 0) return 0;  // empty input (null data pointers)
   CHECK_ARG(x && y && rows >= 0 && D > 0, "norm_mod_fwd: null pointer or bad shape");
   CHECK_ARG(D % 8 == 0 && D <= 2048, "norm_mod_fwd: D must be a multiple of 8 and <= 2048");
   CHECK_ARG(ldx % 8 == 0 && ldy % 8 == 0 && mod_stride % 8 == 0 && aligned16(x) && aligned16(y) &&

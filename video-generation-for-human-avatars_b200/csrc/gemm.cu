@@ -514,9 +514,9 @@ static int gemm_impl(const void* A, int64_t lda, int a_kmajor_rows_are_k, const 
                               const void* res, int64_t ldres, void* aux, int64_t ldaux,
                               int block_n, int split_k, void* stream, const GemmGroups& gg) {
   const bool a_mn = a_kmajor_rows_are_k != 0, b_mn = b_rows_are_k != 0;
-  if (!(A && B && C)) return arg_error("gemm_bf16: null operand");
   if (M < 0 || N < 0 || K < 0 || K2 < 0) return arg_error("gemm_bf16: negative dimension");
-  if (M == 0 || N == 0) return 0;
+  if (M == 0 || N == 0) return 0;  // empty output: nothing to do (empty tensors carry null pointers)
+  if (!(A && B && C)) return arg_error("gemm_bf16: null operand");
   if (K == 0 && K2 == 0) return arg_error("gemm_bf16: empty reduction");
   // an extent must be a multiple of 8 only where it is the contiguous dimension of some operand: N always
   // (C rows, bias); K / K2 unless both operands are stored [K, *] (the wgrad form: K = token count, any value,
