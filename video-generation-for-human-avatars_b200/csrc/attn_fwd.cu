@@ -9,19 +9,22 @@
 // projection GEMMs write, so no head split/merge copies exist.  TMA reads 128x64 tiles straight
 // out of that layout with a 3-D tensor map (col, token, batch).
 //
-// One CTA = one 128-query tile of one head; two CTAs are resident per SM.  At head_dim 64 the kernel is
-// bound by the exp unit (16 ex2/clk/SM = 1024 clk per 128x128 tile against 512 clk of MMA), so the
-// design goal is that the four softmax warps never wait for the tensor pipe:
-//   warp 0 lane 0 : TMA producer (Q once; K/V tiles through a 3-stage ring)
-//   warp 1        : TMEM allocator + MMA issue (one elected lane): S = Q K^T (128x128x64) and
-//                   O += P V in two 64-key halves (V is the MN-major B operand, P the TMEM A operand)
-//   warps 2..5    : softmax, one query row per thread.  The 128 scores of the row are read out of TMEM
-//                   ONCE into registers and the S columns are handed back immediately, so Q K^T of the
-//                   next tile runs underneath the exponentials of this one.  Row max (3-input max),
-//                   lazy rescale (only when the running max grows by > 2^8), exp2, and P goes to its own
-//                   64 TMEM columns half by half; P V of the first half is issued while the second half
-//                   is still being exponentiated.
-// TMEM (256 columns per CTA): S 128 | O 64 | P 64 (bf16x2 packed: keys 0-63 | keys 64-127).
+// One CTA = one 128-query tile of one head, walking the keys 64 at a time; FOUR CTAs are resident per SM.
+// At head_dim 64 the exp unit (16 ex2/clk/SM measured = 1024 clk per 128 x 128 scores against 512 clk of MMA) is the
+// nominal bound, but what the measurements showed is a latency-bound kernel: with two softmax warps per scheduler
+// (2 CTAs x 128-key tiles, 168 registers) the exp unit was ~50 % busy and nothing else saturated -- offloading
+// exponentials to the FMA pipe, a speculative single pass, 8 softmax warps per CTA (pair barriers, spills) all
+// measured equal or worse (profiles/r02_probes_mma_tmem.md).  Independent CTAs are the cheap source of independent
+// warps: a 128 x 64 step needs 128 TMEM columns (S 64 | O 64, P in place), 48 KB of shared memory and, with
+// chunk-wise TMEM reads, 80 registers, so four CTAs fit an SM and every scheduler has 4 softmax warps.
+//   warp 0 lane 0 : TMA producer (Q once; K/V steps through a 2-stage ring)
+//   warp 1        : TMEM allocator + MMA issue (one elected lane): S = Q K^T (128x64x64), O += P V (128x64x64;
+//                   V is the MN-major B operand, P the TMEM A operand).  S(j+1) overwrites P(j): it is issued
+//                   behind P V(j), and the tensor pipe runs in order.
+//   warps 2..5    : softmax, one query row per thread, two passes over the 64 scores in 32-column TMEM chunks:
+//                   row max (3-input max), lazy rescale (only when the running max grows by > 2^8), exp2, packed
+//                   bf16 P written over the first half of the S columns.  Per-key bias (attn2, ragged steps) is
+//                   staged in shared memory once per step.
 #include "api_internal.h"
 #include "common.cuh"
 #include "tmap.h"
@@ -37,10 +40,20 @@ struct FaFwdParams {
   float scale_log2;       // softmax scale * log2(e)
 };
 
-constexpr int FA_KV_STAGES = 3;
-constexpr int FA_SMEM_TILES = 16384 /*Q*/ + FA_KV_STAGES * 32768 /*K,V*/;
-constexpr int FA_FWD_SMEM = FA_SMEM_TILES + 128 + 512;  // + barriers + 128 staged key-bias floats (2 CTAs/SM: <= 115712)
-static_assert(2 * (FA_FWD_SMEM + 1024) <= 233472, "two fa_fwd CTAs must fit one SM");
+// Geometry: 128 queries x 64 keys per step, FOUR CTAs per SM (TMEM 128 columns each: S 64 | O 64, P written in
+// place over the first half of S).  Measured: with one 128 x 128 tile per step and two CTAs per SM the exp unit was
+// ~50 % busy and nothing else was saturated -- two softmax warps per scheduler cannot cover each other's TMEM round
+// trips, dependent-issue stalls and barrier waits.  Halving the key tile halves every per-CTA resource (TMEM, smem,
+// registers through chunk-wise TMEM reads), so four independent CTAs = 4 softmax warps per scheduler fit, with no
+// cross-warp synchronisation added.
+constexpr int FA_BN = 64;                 // keys per step
+constexpr int FA_KV_STAGES = 2;
+constexpr int FA_KV_STAGE_BYTES = 2 * FA_BN * 128;  // K and V tile of one step
+constexpr int FA_SMEM_TILES = 16384 /*Q*/ + FA_KV_STAGES * FA_KV_STAGE_BYTES;
+constexpr int FA_FWD_SMEM = FA_SMEM_TILES + 128 + 256;  // + barriers + 64 staged key-bias floats
+constexpr int FA_FWD_THREADS = 192;       // TMA warp, MMA warp, 4 softmax warps
+constexpr int FA_CTAS_PER_SM = 4;
+static_assert(FA_CTAS_PER_SM * (FA_FWD_SMEM + 1024) <= 233472, "fa_fwd CTAs must fit one SM");
 constexpr float kLog2e = 1.4426950408889634f;
 
 __device__ __forceinline__ float ex2_approx(float x) {
@@ -100,17 +113,16 @@ __device__ __forceinline__ void chunk_add_bias(uint32_t (&r)[32], float sl2, con
   }
 }
 
-__global__ void __launch_bounds__(192, 2)
+__global__ void __launch_bounds__(FA_FWD_THREADS, FA_CTAS_PER_SM)
 fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
               const __grid_constant__ CUtensorMap tmV, const __grid_constant__ FaFwdParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t sbase = smem_u32(smem_raw);
   const uint32_t sQ = sbase, sKV = sbase + 16384;
-  const uint32_t bar = sKV + FA_KV_STAGES * 32768;
-  const uint32_t q_full = bar, kv_full0 = bar + 8, kv_empty0 = bar + 32, s_full = bar + 56, s_free = bar + 64,
-                 pa_full = bar + 72, pb_full = bar + 80, pva_done = bar + 88, pv_done = bar + 96,
-                 tmem_slot = bar + 104;
-  float* kb_stage = reinterpret_cast<float*>(smem_raw + (bar + 128 - sbase));  // [128] per-key term of the current tile
+  const uint32_t bar = sKV + FA_KV_STAGES * FA_KV_STAGE_BYTES;
+  const uint32_t q_full = bar, kv_full0 = bar + 8, kv_empty0 = bar + 24, s_full = bar + 40, p_full = bar + 48,
+                 pv_done = bar + 56, tmem_slot = bar + 64;
+  float* kb_stage = reinterpret_cast<float*>(smem_raw + (bar + 128 - sbase));  // [64] per-key term of the current step
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int qt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
   const int T = p.kv_tiles;
@@ -129,15 +141,12 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
       mbar_init(kv_empty0 + 8 * s, 1);
     }
     mbar_init(s_full, 1);
-    mbar_init(s_free, 128);
-    mbar_init(pa_full, 128);
-    mbar_init(pb_full, 128);
-    mbar_init(pva_done, 1);
+    mbar_init(p_full, 128);
     mbar_init(pv_done, 1);
     fence_barrier_init();
   }
   if (warp == 1) {
-    tmem_alloc(tmem_slot, 256);
+    tmem_alloc(tmem_slot, 128);
     tmem_relinquish();
   }
   tc_fence_before();
@@ -145,7 +154,7 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
-  const uint32_t tS = tmem_base, tO = tmem_base + 128, tP = tmem_base + 192;
+  const uint32_t tS = tmem_base, tO = tmem_base + 64;
 
   if (warp == 0 && lane == 0) {
     mbar_expect_tx(q_full, 16384);
@@ -154,117 +163,90 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
     uint32_t ph = 0;
     for (int j = 0; j < T; ++j) {
       mbar_wait(kv_empty0 + 8 * s, ph ^ 1);
-      mbar_expect_tx(kv_full0 + 8 * s, 32768);
-      tma_load_3d(sKV + s * 32768, &tmK, kv_full0 + 8 * s, h * 64, j * 128, b);
-      tma_load_3d(sKV + s * 32768 + 16384, &tmV, kv_full0 + 8 * s, h * 64, j * 128, b);
+      mbar_expect_tx(kv_full0 + 8 * s, FA_KV_STAGE_BYTES);
+      tma_load_3d(sKV + s * FA_KV_STAGE_BYTES, &tmK, kv_full0 + 8 * s, h * 64, j * FA_BN, b);
+      tma_load_3d(sKV + s * FA_KV_STAGE_BYTES + FA_BN * 128, &tmV, kv_full0 + 8 * s, h * 64, j * FA_BN, b);
       if (++s == FA_KV_STAGES) { s = 0; ph ^= 1; }
     }
   } else if (warp == 1) {
-    // MMA warp: every lane follows the barrier waits, one elected lane issues; descriptors are constant
-    // bases plus small offsets so that the instruction stream per MMA is minimal (the issuing thread
-    // shares its scheduler with the softmax warps of both resident CTAs).
-    const uint32_t idesc_qk = make_idesc_bf16(128, 128, 0, 0);
+    // MMA warp: every lane follows the barrier waits, one elected lane issues; descriptors are constant bases plus
+    // small offsets so that the instruction stream per MMA is minimal.
+    const uint32_t idesc_qk = make_idesc_bf16(128, FA_BN, 0, 0);
     const uint32_t idesc_pv = make_idesc_bf16(128, 64, 0, 1);
     const uint64_t dq0 = make_smem_desc(sQ, 16, 1024), dk0 = make_smem_desc(sKV, 16, 1024),
-                   dv0 = make_smem_desc(sKV + 16384, 8192, 1024);
+                   dv0 = make_smem_desc(sKV + FA_BN * 128, 8192, 1024);
     mbar_wait(q_full, 0);
-    int s = 0, sn = 0;          // ring stage of tile j (PV) and of the next S = Q K^T to issue
-    uint32_t phn = 0;
-    auto issue_qk = [&](int j) {  // S(j) = Q K(j)^T; the softmax warps have read S(j-1) out of TMEM
-      mbar_wait(kv_full0 + 8 * sn, phn);
-      if (j > 0) mbar_wait(s_free, (j - 1) & 1);
+    int s = 0;
+    uint32_t ph = 0;
+    for (int j = 0; j < T; ++j) {
+      // S(j) = Q K(j)^T overwrites P(j-1): issued behind P V(j-1), the tensor pipe runs in order
+      mbar_wait(kv_full0 + 8 * s, ph);
       tc_fence_after();
       if (elect_one()) {
-        const uint64_t dk = desc_adv(dk0, sn * 32768);
+        const uint64_t dk = desc_adv(dk0, s * FA_KV_STAGE_BYTES);
 #pragma unroll
         for (int k = 0; k < 4; ++k)
           umma_ss(tS, desc_adv(dq0, k * 32), desc_adv(dk, k * 32), idesc_qk, k > 0 ? 1u : 0u);
         umma_commit(s_full);
       }
       __syncwarp();
-      if (++sn == FA_KV_STAGES) { sn = 0; phn ^= 1; }
-    };
-    if (T > 0) issue_qk(0);
-    for (int j = 0; j < T; ++j) {
-      if (j + 1 < T) issue_qk(j + 1);  // runs underneath the exponentials of tile j
-      const uint64_t dv = desc_adv(dv0, s * 32768);
-      mbar_wait(pa_full, j & 1);
+      mbar_wait(p_full, j & 1);
       tc_fence_after();
       if (elect_one()) {
-        const uint32_t acc0 = j > 0 ? 1u : 0u;
+        const uint64_t dv = desc_adv(dv0, s * FA_KV_STAGE_BYTES);
 #pragma unroll
-        for (int k = 0; k < 4; ++k)  // keys 0..63: A = P (bf16x2 packed, 8 TMEM columns per K=16 step)
-          umma_ts(tO, tP + k * 8, desc_adv(dv, k * 2048), idesc_pv, k > 0 ? 1u : acc0);
-        umma_commit(pva_done);
-      }
-      __syncwarp();
-      mbar_wait(pb_full, j & 1);
-      tc_fence_after();
-      if (elect_one()) {
-#pragma unroll
-        for (int k = 4; k < 8; ++k)  // keys 64..127
-          umma_ts(tO, tP + k * 8, desc_adv(dv, k * 2048), idesc_pv, 1u);
+        for (int k = 0; k < FA_BN / 16; ++k)  // A = P (bf16x2 packed, 8 TMEM columns per K=16 step)
+          umma_ts(tO, tS + k * 8, desc_adv(dv, k * 2048), idesc_pv, (j > 0 || k > 0) ? 1u : 0u);
         umma_commit(kv_empty0 + 8 * s);
         umma_commit(pv_done);
       }
       __syncwarp();
-      if (++s == FA_KV_STAGES) s = 0;
+      if (++s == FA_KV_STAGES) { s = 0; ph ^= 1; }
     }
   } else if (warp >= 2) {
     const int quad = warp & 3;
     const int row = quad * 32 + lane;
     const uint32_t lane_bits = (uint32_t)(quad * 32) << 16;
+    const uint32_t t_row = tS + lane_bits;
     const float* kb = p.key_bias ? p.key_bias + (int64_t)b * p.Nk : nullptr;
     const float sl2 = p.scale_log2;
     float m_used = -INFINITY;
     float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;
     for (int j = 0; j < T; ++j) {
-      const int key0 = j * 128;
-      const bool general = (kb != nullptr) || (key0 + 128 > p.Nk);  // bias or ragged last tile
+      const int key0 = j * FA_BN;
+      const bool general = (kb != nullptr) || (key0 + FA_BN > p.Nk);  // bias or ragged last step
       if (general) {
-        // stage this tile's per-key term (first barrier: everyone has finished reading the previous tile's)
+        // stage this step's per-key term (first barrier: everyone has finished reading the previous step's)
         named_bar_sync(1, 128);
-        const int key = key0 + row;
-        kb_stage[row] = key < p.Nk ? (kb ? kb[key] * kLog2e : 0.f) : -INFINITY;
+        if (row < FA_BN) {
+          const int key = key0 + row;
+          kb_stage[row] = key < p.Nk ? (kb ? kb[key] * kLog2e : 0.f) : -INFINITY;
+        }
         named_bar_sync(1, 128);
       }
+      const float mul = general ? 1.f : sl2;
+      // S(j) complete also means P V(j-1) complete (the tensor pipe runs in order): O is consistent and idle
       mbar_wait(s_full, j & 1);
       tc_fence_after();
-      // the whole row of scores -> registers, then give the S columns back to the tensor pipe
-      uint32_t r0[32], r1[32], r2[32], r3[32];
-      tmem_ld32(tS + lane_bits, r0);
-      tmem_ld32(tS + lane_bits + 32, r1);
-      tmem_ld32(tS + lane_bits + 64, r2);
-      tmem_ld32(tS + lane_bits + 96, r3);
-      tmem_ld_wait();
-      tc_fence_before();
-      mbar_arrive(s_free);
-      float mul = sl2;  // scores are scaled inside the exp FFMA ...
-      if (general) {    // ... except on the bias path, where x = s * sl2 + bias is formed in place
-        chunk_add_bias(r0, sl2, kb_stage);
-        chunk_add_bias(r1, sl2, kb_stage + 32);
-        chunk_add_bias(r2, sl2, kb_stage + 64);
-        chunk_add_bias(r3, sl2, kb_stage + 96);
-        mul = 1.f;
-      }
+      // pass 1: row max, 32 columns at a time
       float a0 = -INFINITY, a1 = -INFINITY, a2 = -INFINITY, a3 = -INFINITY;
-      chunk_max(r0, a0, a1, a2, a3);
-      chunk_max(r1, a0, a1, a2, a3);
-      chunk_max(r2, a0, a1, a2, a3);
-      chunk_max(r3, a0, a1, a2, a3);
+#pragma unroll
+      for (int c = 0; c < FA_BN / 32; ++c) {
+        uint32_t r[32];
+        tmem_ld32(t_row + c * 32, r);
+        tmem_ld_wait();
+        if (general) chunk_add_bias(r, sl2, kb_stage + c * 32);
+        chunk_max(r, a0, a1, a2, a3);
+      }
       const float mx = fmaxf(fmaxf(a0, a1), fmaxf(a2, a3)) * mul;
       const float m_new = fmaxf(m_used, mx);
       const bool need = m_new > m_used + 8.f;
-      bool pv_waited = false;
       if (__any_sync(0xffffffffu, need)) {
         // lazy rescale: O and l follow the running max only when it has grown by more than 2^8
-        const float alpha = ex2_approx(m_used - m_new);  // 0 on the first tile (m_used = -inf)
+        const float alpha = ex2_approx(m_used - m_new);  // 0 on the first step (m_used = -inf)
         m_used = m_new;
         l0 *= alpha; l1 *= alpha; l2 *= alpha; l3 *= alpha;
         if (j > 0) {
-          mbar_wait(pv_done, (j - 1) & 1);  // P V(j-1) finished: O is consistent and idle
-          pv_waited = true;
-          tc_fence_after();
 #pragma unroll 1
           for (int c = 0; c < 2; ++c) {
             uint32_t r[32];
@@ -278,22 +260,19 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
         }
       }
       const float neg_m = -m_used;
-      // keys 0..63: P V(j-1) of the same half was issued half a tile ago
-      if (j > 0) mbar_wait(pva_done, (j - 1) & 1);
-      tc_fence_after();
-      chunk_exp(r0, mul, neg_m, tP + lane_bits, l0, l1, l2, l3);
-      chunk_exp(r1, mul, neg_m, tP + lane_bits + 16, l0, l1, l2, l3);
+      // pass 2: P = exp2(x - m), row sum; P chunk c (32 keys -> 16 packed columns) overwrites S columns
+      // [16c, 16c+16), which belong to S chunk c/2 <= c and have already been read in this pass
+#pragma unroll
+      for (int c = 0; c < FA_BN / 32; ++c) {
+        uint32_t r[32];
+        tmem_ld32(t_row + c * 32, r);
+        tmem_ld_wait();
+        if (general) chunk_add_bias(r, sl2, kb_stage + c * 32);
+        chunk_exp(r, mul, neg_m, t_row + c * 16, l0, l1, l2, l3);
+      }
       tmem_st_wait();
       tc_fence_before();
-      mbar_arrive(pa_full);
-      // keys 64..127
-      if (j > 0 && !pv_waited) mbar_wait(pv_done, (j - 1) & 1);
-      tc_fence_after();
-      chunk_exp(r2, mul, neg_m, tP + lane_bits + 32, l0, l1, l2, l3);
-      chunk_exp(r3, mul, neg_m, tP + lane_bits + 48, l0, l1, l2, l3);
-      tmem_st_wait();
-      tc_fence_before();
-      mbar_arrive(pb_full);
+      mbar_arrive(p_full);
     }
     const float l = (l0 + l1) + (l2 + l3);
     // epilogue: O / l -> bf16, lse
@@ -301,34 +280,31 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
     tc_fence_after();
     const int q = qt * 128 + row;
     const float inv_l = 1.f / l;
-    uint32_t r0[32], r1[32];
-    tmem_ld32(tO + lane_bits, r0);
-    tmem_ld32(tO + lane_bits + 32, r1);
-    tmem_ld_wait();
-    if (q < p.Nq) {
-      bf16* orow = p.O + ((int64_t)b * p.Nq + q) * p.ldo + h * 64;
+    if (q < p.Nq && p.lse) p.lse[((int64_t)b * p.H + h) * p.Nq + q] = (m_used + log2f(l)) * 0.6931471805599453f;
+#pragma unroll 1
+    for (int c = 0; c < 2; ++c) {
+      uint32_t r[32];
+      tmem_ld32(tO + lane_bits + c * 32, r);
+      tmem_ld_wait();
+      if (q < p.Nq) {
+        bf16* orow = p.O + ((int64_t)b * p.Nq + q) * p.ldo + h * 64 + c * 32;
 #pragma unroll
-      for (int g = 0; g < 4; ++g) {
-        uint4 u;
-        u.x = pack_bf16x2(__uint_as_float(r0[g * 8 + 0]) * inv_l, __uint_as_float(r0[g * 8 + 1]) * inv_l);
-        u.y = pack_bf16x2(__uint_as_float(r0[g * 8 + 2]) * inv_l, __uint_as_float(r0[g * 8 + 3]) * inv_l);
-        u.z = pack_bf16x2(__uint_as_float(r0[g * 8 + 4]) * inv_l, __uint_as_float(r0[g * 8 + 5]) * inv_l);
-        u.w = pack_bf16x2(__uint_as_float(r0[g * 8 + 6]) * inv_l, __uint_as_float(r0[g * 8 + 7]) * inv_l);
-        *reinterpret_cast<uint4*>(orow + g * 8) = u;
-        u.x = pack_bf16x2(__uint_as_float(r1[g * 8 + 0]) * inv_l, __uint_as_float(r1[g * 8 + 1]) * inv_l);
-        u.y = pack_bf16x2(__uint_as_float(r1[g * 8 + 2]) * inv_l, __uint_as_float(r1[g * 8 + 3]) * inv_l);
-        u.z = pack_bf16x2(__uint_as_float(r1[g * 8 + 4]) * inv_l, __uint_as_float(r1[g * 8 + 5]) * inv_l);
-        u.w = pack_bf16x2(__uint_as_float(r1[g * 8 + 6]) * inv_l, __uint_as_float(r1[g * 8 + 7]) * inv_l);
-        *reinterpret_cast<uint4*>(orow + 32 + g * 8) = u;
+        for (int g = 0; g < 4; ++g) {
+          uint4 u;
+          u.x = pack_bf16x2(__uint_as_float(r[g * 8 + 0]) * inv_l, __uint_as_float(r[g * 8 + 1]) * inv_l);
+          u.y = pack_bf16x2(__uint_as_float(r[g * 8 + 2]) * inv_l, __uint_as_float(r[g * 8 + 3]) * inv_l);
+          u.z = pack_bf16x2(__uint_as_float(r[g * 8 + 4]) * inv_l, __uint_as_float(r[g * 8 + 5]) * inv_l);
+          u.w = pack_bf16x2(__uint_as_float(r[g * 8 + 6]) * inv_l, __uint_as_float(r[g * 8 + 7]) * inv_l);
+          *reinterpret_cast<uint4*>(orow + g * 8) = u;
+        }
       }
-      if (p.lse) p.lse[((int64_t)b * p.H + h) * p.Nq + q] = (m_used + log2f(l)) * 0.6931471805599453f;
     }
   }
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 256);
+    tmem_dealloc(tmem_base, 128);
   }
 }
 
@@ -361,12 +337,12 @@ extern "C" int b200_fa_fwd(const void* q, int64_t ldq, const void* k, int64_t ld
   CUtensorMap tmQ, tmK, tmV;
   int rc;
   if ((rc = make_tmap_tokens(&tmQ, q, B, Nq, ldq, H * 64, 128)) ||
-      (rc = make_tmap_tokens(&tmK, k, B, Nk, ldk, H * 64, 128)) ||
-      (rc = make_tmap_tokens(&tmV, v, B, Nk, ldv, H * 64, 128)))
+      (rc = make_tmap_tokens(&tmK, k, B, Nk, ldk, H * 64, FA_BN)) ||
+      (rc = make_tmap_tokens(&tmV, v, B, Nk, ldv, H * 64, FA_BN)))
     return arg_error("fa_fwd: cuTensorMapEncodeTiled failed", rc);
   FaFwdParams p;
   p.B = B; p.H = H; p.Nq = Nq; p.Nk = Nk;
-  p.kv_tiles = (Nk + 127) / 128;
+  p.kv_tiles = (Nk + FA_BN - 1) / FA_BN;
   p.O = (bf16*)o; p.ldo = ldo; p.lse = lse; p.key_bias = key_bias;
   p.scale_log2 = scale * kLog2e;
   static bool attr_set = false;
@@ -377,6 +353,6 @@ extern "C" int b200_fa_fwd(const void* q, int64_t ldq, const void* k, int64_t ld
     attr_set = true;
   }
   dim3 grid((Nq + 127) / 128, H, B);
-  fa_fwd_kernel<<<grid, 192, FA_FWD_SMEM, (cudaStream_t)stream>>>(tmQ, tmK, tmV, p);
+  fa_fwd_kernel<<<grid, FA_FWD_THREADS, FA_FWD_SMEM, (cudaStream_t)stream>>>(tmQ, tmK, tmV, p);
   return launch_status("fa_fwd");
 }
