@@ -258,6 +258,56 @@ ATTN_CASES = [(1, 2, 128, 128, False), (2, 4, 96, 96, False), (1, 2, 300, 300, F
               (1, 4, 1100, 256, True), (1, 32, 1536, 256, True), (2, 2, 1030, 100, False)]
 
 
+def _mask_bias(kind, B, Nk):
+    """Key-bias patterns the masked-tile skip has to get right (reference mask: 0 / -10000, transformer3d.py:440-445)."""
+    bias = torch.full((B, Nk), -10000.0, device="cuda")
+    if kind == "prompt":          # a short prompt padded to Nk: everything past the first tile is dead
+        bias[:, :15] = 0.0
+    elif kind == "ragged":        # a different live length per batch entry
+        for b in range(B):
+            bias[b, :15 + 150 * b] = 0.0
+    elif kind == "tail":          # only a few late keys are live: leading tiles are dead, nothing may be cut off
+        bias[:, Nk - 6:Nk - 2] = 0.0
+    elif kind == "holes":         # live keys in the first and the last tile, dead tiles in between
+        bias[:, 3] = 0.0
+        bias[:, Nk - 2] = 0.5
+    elif kind == "dead":          # every key masked: the softmax is uniform, as in the reference
+        pass
+    return bias
+
+
+MASK_CASES = [(1, 32, 1536, 256, "prompt"), (2, 4, 1100, 256, "ragged"), (2, 3, 300, 256, "tail"),
+              (1, 4, 1100, 512, "holes"), (1, 2, 200, 256, "dead"), (2, 2, 130, 384, "prompt")]
+
+
+def check_attention_masked_tiles():
+    from b200_ltx import ops
+    for (B, H, Nq, Nk, kind) in MASK_CASES:
+        D = H * 64
+        q, k, v = _randn(B * Nq, D, seed=1), _randn(B * Nk, D, seed=2), _randn(B * Nk, D, seed=3)
+        do = _randn(B * Nq, D, seed=4)
+        bias = _mask_bias(kind, B, Nk)
+        o, lse = ops.fa_fwd(q, k, v, B, H, Nq, Nk, bias, 0.125)
+        dk = torch.full_like(k, float("nan"))
+        dv = torch.full_like(v, float("nan"))
+        dq = ops.fa_bwd(q, k, v, o, do, lse, B, H, Nq, Nk, dk, dv, bias, 0.125)
+        qf, kf, vf = [t.float().requires_grad_(True) for t in (q, k, v)]
+        oref, lref = _attn_ref(qf, kf, vf, B, H, Nq, Nk, bias, 0.125)
+        oref.backward(do.float())
+        tag = f"B={B} H={H} Nq={Nq} Nk={Nk} mask={kind}"
+        _assert_close("fa_fwd o " + tag, o, oref, 6e-3)
+        # lse sits near -10000 when every key is masked: compare relative to its magnitude there
+        lim = 2e-3 * max(1.0, float(lref.abs().max()) / 10.0)
+        assert (lse - lref.detach()).abs().max().item() < lim, "fa_fwd lse " + tag
+        _assert_close("fa_bwd dq " + tag, dq, qf.grad, 1.2e-2)
+        _assert_close("fa_bwd dk " + tag, dk, kf.grad, 1.2e-2)
+        _assert_close("fa_bwd dv " + tag, dv, vf.grad, 1.2e-2)
+        if kind != "dead":
+            dead = (bias <= -9000).reshape(-1)
+            assert float(dk[dead].abs().max()) == 0.0 and float(dv[dead].abs().max()) == 0.0, "masked keys: " + tag
+    torch.cuda.synchronize()
+
+
 def check_attention_fwd():
     from b200_ltx import ops
     for (B, H, Nq, Nk, use_bias) in ATTN_CASES:
@@ -448,6 +498,7 @@ GROUPS = {
     "qknorm_rope": check_qknorm_rope,
     "attention_fwd": check_attention_fwd,
     "attention_bwd": check_attention_bwd,
+    "attention_masked_tiles": check_attention_masked_tiles,
     "attn_core_fn": check_attn_core_fn,
     "key_sharded_merge": check_key_sharded_merge,
     "empty_and_degenerate": check_empty_and_degenerate,

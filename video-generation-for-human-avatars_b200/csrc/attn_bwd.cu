@@ -59,6 +59,7 @@ struct FaBwdParams {
   float* part_dv;
 };
 
+constexpr int FA_MASK_SCAN_MAX = 1024;  // key counts up to which the bias vector is scanned for masked key tiles
 constexpr int FA_BWD_QSTAGES = 3;
 constexpr int FA_BWD_SMEM = 16384 * 2 /*K,V*/ + FA_BWD_QSTAGES * 32768 /*Q,dO*/ + 2 * 32768 /*dS^T x2*/ +
                             32768 /*dQ staging*/ + 2 * 2 * 512 /*lse, delta x2*/ + 256;
@@ -121,6 +122,41 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
   // this CTA's query tiles: [t0, t0 + T)
   const int t0 = (int)((int64_t)split * p.q_tiles / p.q_splits);
   const int T = (int)((int64_t)(split + 1) * p.q_tiles / p.q_splits) - t0;
+
+  // A key tile whose keys all carry a bias <= -9000 (the reference's -10000 mask, transformer3d.py:440-445) while
+  // some other key of the batch entry is unmasked has P = 0 exactly (exp of < -900 underflows in fp32): dK = dV = 0
+  // and no contribution to dQ.  Such CTAs write their zeros and leave before touching barriers or TMEM.  (With every
+  // key masked the softmax is uniform, not zero: nothing is skipped then.)
+  if (p.key_bias != nullptr && p.Nk <= FA_MASK_SCAN_MAX) {
+    int live_tile = 0, live_batch = 0;   // block-wide votes: no shared memory to spare next to the dynamic 227 KB
+    const float* kbp = p.key_bias + (int64_t)b * p.Nk;
+    for (int key_t = threadIdx.x; key_t < p.Nk; key_t += FA_BWD_THREADS)
+      if (kbp[key_t] > -9000.f) {
+        live_batch = 1;
+        if ((key_t >> 7) == kt) live_tile = 1;
+      }
+    const int s_live_tile = __syncthreads_or(live_tile);
+    const int s_live_batch = __syncthreads_or(live_batch);
+    const bool s_any_live = s_live_tile || !s_live_batch;
+    if (!s_any_live) {
+      // 128 rows x 64 head columns of dK and dV (bf16), or of this split's fp32 partials
+      for (int idx = threadIdx.x; idx < 128 * 8; idx += FA_BWD_THREADS) {
+        const int r = idx >> 3, c8 = (idx & 7) * 8;
+        const int key_r = kt * 128 + r;
+        if (key_r >= p.Nk) continue;
+        if (p.q_splits == 1) {
+          *reinterpret_cast<uint4*>(p.dk + ((int64_t)b * p.Nk + key_r) * p.lddk + h * 64 + c8) = make_uint4(0, 0, 0, 0);
+          *reinterpret_cast<uint4*>(p.dv + ((int64_t)b * p.Nk + key_r) * p.lddv + h * 64 + c8) = make_uint4(0, 0, 0, 0);
+        } else {
+          const int64_t prow = ((int64_t)split * p.B + b) * p.Nk + key_r;
+          float4* pk4 = reinterpret_cast<float4*>(p.part_dk + prow * (p.H * 64) + h * 64 + c8);
+          float4* pv4 = reinterpret_cast<float4*>(p.part_dv + prow * (p.H * 64) + h * 64 + c8);
+          pk4[0] = pk4[1] = pv4[0] = pv4[1] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      }
+      return;
+    }
+  }
 
   if (threadIdx.x == 0) {
     if (sbase & 1023u) {
@@ -471,11 +507,14 @@ __global__ void __launch_bounds__(256) fa_bwd_reduce_kernel(const float* __restr
 }
 
 // How many CTAs share one key tile's query walk: enough to cover the SMs when there are few key tiles.
-static int fa_bwd_splits(int B, int H, int Nq, int Nk) {
+static int fa_bwd_splits(int B, int H, int Nq, int Nk, bool masked) {
   const int64_t ctas = (int64_t)((Nk + 127) / 128) * H * B;
   const int T = (Nq + 127) / 128;
   if (ctas <= 0 || ctas >= 120 || T < 8) return 1;
-  int s = (int)(148 / ctas);  // one wave: never more CTAs than SMs
+  // One wave of CTAs; with a key mask up to two waves' worth: key tiles that turn out to be fully masked leave at
+  // once (attn2 with the real prompt: half of them), and with nothing masked two waves of half-length walks cost
+  // about the same as one wave of full ones.
+  int s = (int)((masked ? 296 : 148) / ctas);
   return s > T / 4 ? (T / 4 > 0 ? T / 4 : 1) : s;
 }
 
@@ -493,7 +532,7 @@ extern "C" int b200_debug_bwd_trace(unsigned long long* host, int n) {
 
 extern "C" int64_t b200_fa_bwd_workspace_bytes(int B, int H, int Nq, int Nk) {
   if (B <= 0 || H <= 0 || Nq <= 0 || Nk <= 0) return 0;
-  const int s = fa_bwd_splits(B, H, Nq, Nk);
+  const int s = fa_bwd_splits(B, H, Nq, Nk, true);  // upper bound over both split choices
   return s > 1 ? (int64_t)2 * s * B * Nk * H * 64 * (int64_t)sizeof(float) : 0;
 }
 
@@ -532,10 +571,10 @@ extern "C" int b200_fa_bwd(const void* q, int64_t ldq, const void* k, int64_t ld
   p.dq = dq_accum; p.lddq = lddq;
   p.dk = (bf16*)dk; p.lddk = lddk; p.dv = (bf16*)dv; p.lddv = lddv;
   p.scale = scale; p.scale_log2 = scale * kLog2eB;
-  p.q_splits = fa_bwd_splits(B, H, Nq, Nk);
+  p.q_splits = fa_bwd_splits(B, H, Nq, Nk, key_bias != nullptr);
   p.part_dk = p.part_dv = nullptr;
   if (p.q_splits > 1) {
-    const int64_t need = b200_fa_bwd_workspace_bytes(B, H, Nq, Nk);
+    const int64_t need = (int64_t)2 * p.q_splits * B * Nk * H * 64 * (int64_t)sizeof(float);
     if (!workspace || workspace_bytes < need || !al16(workspace))
       return arg_error("fa_bwd: workspace too small (see b200_fa_bwd_workspace_bytes)");
     p.part_dk = (float*)workspace;

@@ -53,6 +53,7 @@ constexpr int FA_SMEM_TILES = 16384 /*Q*/ + FA_KV_STAGES * FA_KV_STAGE_BYTES;
 constexpr int FA_FWD_SMEM = FA_SMEM_TILES + 128 + 256;  // + barriers + 64 staged key-bias floats
 constexpr int FA_FWD_THREADS = 192;       // TMA warp, MMA warp, 4 softmax warps
 constexpr int FA_CTAS_PER_SM = 4;
+constexpr int FA_MASK_SCAN_MAX = 1024;   // key counts up to which the bias vector is scanned for trailing masked keys
 static_assert(FA_CTAS_PER_SM * (FA_FWD_SMEM + 1024) <= 233472, "fa_fwd CTAs must fit one SM");
 constexpr float kLog2e = 1.4426950408889634f;
 
@@ -125,7 +126,19 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
   float* kb_stage = reinterpret_cast<float*>(smem_raw + (bar + 128 - sbase));  // [64] per-key term of the current step
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int qt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
-  const int T = p.kv_tiles;
+  // Keys whose additive bias is <= -9000 (the reference masks with -10000, transformer3d.py:440-445) have weight
+  // exp(-9000) = 0 exactly in fp32: every key step past the last unmasked key is skipped -- bit-identical, and with
+  // the real prompt (~15 valid of 256 caption tokens) three of the four steps of attn2 disappear.
+  __shared__ int s_last_key;
+  if (threadIdx.x == 0) s_last_key = -1;
+  __syncthreads();
+  if (p.key_bias != nullptr && p.Nk <= FA_MASK_SCAN_MAX) {
+    const float* kbp = p.key_bias + (int64_t)b * p.Nk;
+    int last = -1;
+    for (int key = threadIdx.x; key < p.Nk; key += FA_FWD_THREADS)
+      if (kbp[key] > -9000.f) last = key;
+    if (last >= 0) atomicMax(&s_last_key, last);
+  }
 
   if (threadIdx.x == 0) {
     if (sbase & 1023u) {
@@ -155,6 +168,8 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
   const uint32_t tS = tmem_base, tO = tmem_base + 64;
+  // number of key steps: all of them, or up to the last unmasked key (none unmasked: keep all, as the reference)
+  const int T = s_last_key >= 0 ? min(p.kv_tiles, s_last_key / FA_BN + 1) : p.kv_tiles;
 
   if (warp == 0 && lane == 0) {
     mbar_expect_tx(q_full, 16384);
