@@ -145,6 +145,22 @@ int b200_rf_loss(const void* out, const void* target, void* dout, float* loss, i
 int b200_lerp_condition(void* tokens, const void* ref, const void* pose, int B, int N, int C, int HW,
                         float w_ref, float w_pose, int token_offset, int N_total, void* stream);
 
+/* Element-wise tail of one sampling step, fused: guidance combine of the model output v [conds*B, N, C] bf16 (order:
+ * (uncond,) text (, perturbed)) -- CFG `u + gs (text - u)` with u = uncond or, cfg_star, uncond scaled by
+ * <text,uncond>/(|uncond|^2 + 1e-8); STG `+ stg (text - perturbed)`; rescale `* (rs * std(text)/std(pred) + 1 - rs)`
+ * with unbiased per-sample stds -- then the Euler update x <- x - dt * pred on the fp32 running latents x [B, N, C]
+ * for the tokens with t - 1e-6 < noise_level[b, n] (all tokens when noise_level is NULL; noise_level = 1 -
+ * conditioning_mask), and the bf16 model input of the next step written n_next times back to back into x_next
+ * [n_next*B, N, C] (n_next may be 0).  dt: fp32 [1] or, dt_per_token, [N] (shared by the batch like the reference's
+ * timestep[:1]); scalars: DEVICE fp32 {guidance_scale, stg_scale, rescaling_scale, t}, so a captured step can be
+ * replayed with new values.  Workspace: b200_guidance_step_workspace_bytes(B), needed for cfg_star / rescale.
+ * Replaces pipelines/pipeline_ltx_video.py:1217-1260 (guidance), :1346-1379 (denoising_step), rf.py:305-374 (Euler). */
+int64_t b200_guidance_step_workspace_bytes(int B);
+int b200_guidance_step(const void* v, float* x, void* x_next, int n_next, const float* dt, int dt_per_token,
+                       const float* noise_level, const float* scalars, int B, int64_t N, int C, int has_cfg,
+                       int has_stg, int cfg_star, int rescale, void* workspace, int64_t workspace_bytes,
+                       void* stream);
+
 /* out[m,:] = x[m,:] * g[m / rows_per_mod,:]  (AdaLN gate applied to an incoming gradient). */
 int b200_rowscale(const void* x, int64_t ldx, const void* g, int64_t gstride, void* out, int64_t ldo,
                   int64_t rows, int D, int64_t rows_per_mod, void* stream);

@@ -489,6 +489,54 @@ def check_rf_and_misc():
     torch.cuda.synchronize()
 
 
+def check_guidance_step():
+    """Fused sampling tail (guidance combine + Euler + conditioning select + next model input) against the oracle's
+    restatement of pipeline_ltx_video.py:1217-1260, :1346-1379 in fp32."""
+    import ref_block as rb
+    import ref_sampling as rs
+    from b200_ltx import ops
+    B, N, C = 2, 333, 128
+    grid_t = rb.uniform_timesteps(8)
+    for (do_cfg, do_stg, star, rsc, per_tok, n_next) in [(False, False, False, 1.0, False, 1), (True, False, False, 1.0, False, 2),
+                                                         (True, False, True, 1.0, True, 0), (False, True, False, 0.7, False, 2),
+                                                         (True, True, True, 0.7, True, 3), (True, True, False, 1.0, False, 1)]:
+        conds = 1 + int(do_cfg) + int(do_stg)
+        g = torch.Generator(device="cpu").manual_seed(conds * 10 + int(star))
+        v = (torch.randn(conds * B, N, C, generator=g) + 0.1).to(BF16)
+        x = torch.randn(B, N, C, generator=g)
+        cm = None
+        if per_tok:
+            cm = torch.zeros(B, N)
+            cm[:, :40] = 1.0
+            cm[0, 40:90] = 0.6
+            cm[1, 40:70] = 0.3
+        t = grid_t[3]
+        gs, stg = 3.0 if do_cfg else 1.0, 1.5 if do_stg else 0.0
+        # oracle, fp32
+        pred = rs.guidance_combine(v.float(), B, conds, do_cfg, do_stg, gs, stg, rsc, star)
+        cur_t = t.view(1, 1).expand(B, 1)
+        if cm is not None:
+            cur_t = torch.min(cur_t, 1.0 - cm)
+        den = rb.rf_step(grid_t, pred, cur_t[:1], x)
+        ref = den if cm is None else torch.where((t - 1e-6 < (1.0 - cm)).unsqueeze(-1), den, x)
+        # product
+        from b200_ltx.sampling import _step_tables
+        rows, dts = _step_tables(grid_t.cuda(), None if cm is None else cm.cuda())
+        scal = torch.tensor([gs, stg, rsc, float(t)], device="cuda")
+        xg = x.cuda().clone()
+        xn = torch.full((n_next * B, N, C), float("nan"), device="cuda", dtype=BF16) if n_next else None
+        ops.guidance_step_(v.cuda(), xg, xn, dts[3], None if cm is None else (1.0 - cm).cuda().contiguous(), scal,
+                           do_cfg, do_stg, cfg_star=star, rescale=bool(do_stg and rsc != 1.0))
+        tag = f"cfg={int(do_cfg)} stg={int(do_stg)} star={int(star)} rescale={rsc} per_token={int(per_tok)}"
+        _assert_close("guidance_step x " + tag, xg.cpu(), ref, 2e-5)
+        if cm is not None:
+            assert torch.equal(xg[:, :40].cpu(), x[:, :40]), "hard-conditioned tokens moved: " + tag
+        if n_next:
+            want = xg.to(BF16).repeat(n_next, 1, 1)
+            assert torch.equal(xn, want), "next model input: " + tag
+    torch.cuda.synchronize()
+
+
 GROUPS = {
     "gemm_layouts": check_gemm_layouts,
     "gemm_epilogues": check_gemm_epilogues,
@@ -503,4 +551,5 @@ GROUPS = {
     "key_sharded_merge": check_key_sharded_merge,
     "empty_and_degenerate": check_empty_and_degenerate,
     "rf_and_misc": check_rf_and_misc,
+    "guidance_step": check_guidance_step,
 }

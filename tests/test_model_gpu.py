@@ -105,37 +105,82 @@ def test_forward_mutates_input_like_reference_and_processor_protocol():
     assert torch.equal(out, out2)
 
 
-@pytest.mark.gpu
-def test_sampling_loop_matches_oracle_loop():
-    """6 Euler steps of the rectified-flow sampler (forward-only kernels, in-place conditioning every step)
-    against the same loop over the fp32 oracle forward."""
-    from b200_ltx import api
+def _sampling_case(steps=6, B=2):
     cfg = dict(rb.LTXV_2B, num_layers=2, num_attention_heads=4, cross_attention_dim=256, caption_channels=64)
     P = rb.init_params(cfg, 0, seed=5)
     P = {k: v.to(torch.bfloat16).float() for k, v in P.items()}
     model = mc.build_b200_model(cfg, P, 0).eval()
-    b = rb.synthetic_batch(cfg, 2, 3, 4, 6, 24, 21, 15)
-    tokens, coords = rb.patchify(b["noise"].transpose(1, 2).reshape(2, -1, 3, 4, 6))
+    b = rb.synthetic_batch(cfg, B, 3, 4, 6, 24, 21, 15)
+    tokens, coords = rb.patchify(b["noise"].transpose(1, 2).reshape(B, -1, 3, 4, 6))
     fc = coords.float()
     fc[:, 0] = fc[:, 0] * (1.0 / 25)
     x0 = tokens.to(torch.bfloat16)
     ref, pose = b["ref_image_latents"].to(torch.bfloat16), b["pose_latents"].to(torch.bfloat16)
-    enc, msk = b["prompt_embeds"].to(torch.bfloat16), b["prompt_mask"]
+    enc, msk = b["prompt_embeds"].to(torch.bfloat16).expand(B, -1, -1), b["prompt_mask"].expand(B, -1)
+    return cfg, P, model, x0, fc, ref, pose, enc, msk
+
+
+@pytest.mark.gpu
+def test_sampling_loop_matches_oracle_loop():
+    """6 Euler steps of the rectified-flow sampler with one condition (inference-avatars.yaml): forward-only kernels,
+    fp32 running latents, the conditioning lerp reaching the caller's latents on the first step only -- against the
+    oracle's restatement of the pipeline loop over the fp32 oracle forward."""
+    import ref_sampling as rs
+    from b200_ltx import api
+    cfg, P, model, x0, fc, ref, pose, enc, msk = _sampling_case()
     steps = 6
     sched = api.RectifiedFlowScheduler()
-    x = api.denoise(model, x0.clone().cuda().contiguous(), fc.cuda(), ref.cuda(), pose.cuda(), enc.cuda(), msk.cuda(),
-                    sched, num_inference_steps=steps)
-    grid = rb.uniform_timesteps(steps)
-    xr = x0.float().clone()
-    with torch.no_grad():
-        for i in range(steps):
-            t = grid[i]
-            v = rb.transformer_forward(P, cfg, xr, fc, ref.float(), pose.float(), enc.float().expand(2, -1, -1),
-                                       t.expand(2)[:, None], msk.expand(2, -1))
-            xr = rb.rf_step(grid, v, t, xr)
+    lat = x0.clone().cuda().contiguous()
+    x = api.denoise(model, lat, fc.cuda(), ref.cuda(), pose.cuda(), enc.cuda(), msk.cuda(), sched,
+                    num_inference_steps=steps)
+    assert x.dtype == torch.float32 and x.data_ptr() != lat.data_ptr()
+    lat_o = x0.float().clone()
+    xr = rs.denoise_loop(P, cfg, lat_o, fc, ref.float(), pose.float(), enc.float(), msk, rb.uniform_timesteps(steps))
     err = mc.rel(x.cpu(), xr)
     print(f"  sampling loop ({steps} steps): rel err vs fp32 oracle loop {err:.3e}")
     assert err < 3e-2
+    # the first step conditioned the caller's tensor in place, exactly as the oracle's (reference's) aliasing does
+    assert not torch.equal(lat.cpu(), x0) and mc.rel(lat.cpu(), lat_o) < 1e-2
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("use_graph", [False, True])
+def test_guided_sampling_loop_matches_oracle_loop(use_graph):
+    """CFG (with the CFG* projection) + STG (attention-values skip of block 1) + std rescale, a negative prompt, a
+    conditioning mask with hard (1.0) and soft tokens, and guidance switched off for the last two steps -- eager and
+    with the captured step; against oracle/ref_sampling.py (pipeline_ltx_video.py:1089-1288)."""
+    import ref_sampling as rs
+    from b200_ltx import api, modules
+    cfg, P, model, x0, fc, ref, pose, enc, msk = _sampling_case()
+    steps = 7
+    B, N, _ = x0.shape
+    g = torch.Generator().manual_seed(3)
+    neg = torch.randn(enc.shape, generator=g).to(torch.bfloat16)
+    neg_m = torch.zeros_like(msk)
+    neg_m[:, :9] = 1
+    cm = torch.zeros(B, N)
+    cm[:, :24] = 1.0          # first latent frame: hard conditioning
+    cm[0, 24:40] = 0.5
+    gs = [3.0] * 5 + [1.0] * 2
+    stg = [1.0] * 5 + [0.0] * 2
+    rsc = [0.7] * steps
+    sampler = api.Denoiser(model, api.RectifiedFlowScheduler(), graph=use_graph)
+    kw = dict(num_inference_steps=steps, negative_prompt_embeds=neg.cuda(), negative_prompt_attention_mask=neg_m.cuda(),
+              guidance_scale=gs, stg_scale=stg, rescaling_scale=rsc, cfg_star_rescale=True, skip_block_list=[1],
+              skip_layer_strategy=modules.SkipLayerStrategy.AttentionValues, conditioning_mask=cm.cuda())
+    lat = x0.clone().cuda().contiguous()
+    x = sampler(lat, fc.cuda(), ref.cuda(), pose.cuda(), enc.cuda(), msk.cuda(), **kw)
+    # a second run through the same object (with graph=True: every guided step is now a replay, from step 0 on)
+    x_again = sampler(x0.clone().cuda().contiguous(), fc.cuda(), ref.cuda(), pose.cuda(), enc.cuda(), msk.cuda(), **kw)
+    assert mc.rel(x_again, x) < 1e-6
+    assert torch.equal(lat.cpu(), x0)   # three conditions on the first step: the caller's latents are left alone
+    xr = rs.denoise_loop(P, cfg, x0.float().clone(), fc, ref.float(), pose.float(), enc.float(), msk,
+                         rb.uniform_timesteps(steps), neg.float(), neg_m, gs, stg, rsc, True, [1],
+                         rb.STG_ATTENTION_VALUES, cm)
+    err = mc.rel(x.cpu(), xr)
+    print(f"  guided sampling loop ({steps} steps, graph={use_graph}): rel err vs fp32 oracle loop {err:.3e}")
+    assert err < 3e-2
+    assert torch.equal(x[:, :24].cpu(), x0[:, :24].float())   # hard-conditioned tokens never move
 
 
 @pytest.mark.gpu

@@ -350,6 +350,8 @@ def transformer_forward(model, hidden_states, indices_grid, ref_image_hidden_sta
     try:
         for i, block in enumerate(model.transformer_blocks):
             slm = skip_layer_mask[i] if skip_layer_mask is not None else None
+            if slm is not None and i not in getattr(skip_layer_mask, "_b200_skip_blocks", (i,)):
+                slm = None  # an all-ones row (see create_skip_layer_mask): nothing is skipped in this block
             if checkpointing:
                 h = torch.utils.checkpoint.checkpoint(block, h, freqs, attention_mask, ctx, encoder_attention_mask,
                                                       t6, cross_attention_kwargs, class_labels, slm,
@@ -637,6 +639,9 @@ class Transformer3DModel(nn.Module):
         mask = torch.ones((len(self.transformer_blocks), batch_size * num_conds), device=self.device, dtype=self.dtype)
         for block_idx in skip_block_list:
             mask[block_idx, ptb_index::num_conds] = 0
+        # host-side note of which rows differ from all-ones: the other blocks keep the fused attn1 path
+        # (o * 1 + other * 0 == o exactly) without reading the mask back from the device
+        mask._b200_skip_blocks = frozenset(int(b) % len(self.transformer_blocks) for b in skip_block_list)
         return mask
 
     def precompute_freqs_cis(self, indices_grid, spacing="exp"):

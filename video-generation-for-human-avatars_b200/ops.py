@@ -301,6 +301,40 @@ def lerp_condition_(tokens, ref, pose, w_ref=0.85, w_pose=0.5, token_offset=0):
     return tokens
 
 
+def guidance_step_(v, x, x_next, dt, noise_level, scalars, has_cfg, has_stg, cfg_star=False, rescale=False,
+                   workspace=None):
+    """One sampling step's element-wise tail, in place on the fp32 latents `x` [B,N,C]; see b200_guidance_step.
+    v: [conds*B, N, C] bf16 model output; x_next: None or [n_next*B, N, C] bf16 (next model input, one copy per
+    condition); dt: fp32 [1] or [N]; noise_level: None or fp32 [B,N]; scalars: CUDA fp32 [4]."""
+    B, N, C = x.shape
+    conds = 1 + int(bool(has_cfg)) + int(bool(has_stg))
+    if (v.dtype != BF16 or x.dtype != torch.float32 or not v.is_contiguous() or not x.is_contiguous()
+            or tuple(v.shape) != (conds * B, N, C)):
+        raise _lib.B200Error(f"guidance_step: v must be contiguous bf16 [{conds * B},{N},{C}], x contiguous fp32 [B,N,C]")
+    n_next = 0
+    if x_next is not None:
+        if x_next.dtype != BF16 or not x_next.is_contiguous() or x_next.shape[1:] != x.shape[1:] or x_next.shape[0] % B:
+            raise _lib.B200Error("guidance_step: x_next must be contiguous bf16 [n_next*B, N, C]")
+        n_next = x_next.shape[0] // B
+    if dt.dtype != torch.float32 or not dt.is_contiguous() or dt.numel() not in (1, N):
+        raise _lib.B200Error("guidance_step: dt must be fp32 with 1 or N elements")
+    if noise_level is not None and (noise_level.dtype != torch.float32 or not noise_level.is_contiguous()
+                                    or tuple(noise_level.shape) != (B, N)):
+        raise _lib.B200Error("guidance_step: noise_level must be contiguous fp32 [B,N]")
+    if scalars.dtype != torch.float32 or not scalars.is_cuda or scalars.numel() < 4 or not scalars.is_contiguous():
+        raise _lib.B200Error("guidance_step: scalars must be a CUDA fp32 tensor {guidance, stg, rescale, t}")
+    need = _L().b200_guidance_step_workspace_bytes(B)
+    if workspace is None and ((has_cfg and cfg_star) or rescale):
+        workspace = torch.empty(need, device=x.device, dtype=torch.uint8)
+    n_k = 1 + int(bool(has_cfg and cfg_star)) + int(bool(rescale))
+    _call("guidance_step", (2.0 * conds * n_k + 8.0 + 2.0 * n_next) * x.numel(), "byte", _L().b200_guidance_step,
+          _p(v), _p(x), _p(x_next) if x_next is not None else None, n_next, _p(dt), int(dt.numel() == N and N > 1),
+          _p(noise_level) if noise_level is not None else None, _p(scalars), B, N, C, int(bool(has_cfg)),
+          int(bool(has_stg)), int(bool(cfg_star)), int(bool(rescale)), _p(workspace) if workspace is not None else None,
+          workspace.numel() if workspace is not None else 0, _s(), launches=n_k)
+    return x
+
+
 def rowscale(x, g, rows_per_mod):
     _chk2d(x, "rowscale x")
     _chk2d(g, "rowscale g")
