@@ -55,6 +55,21 @@ int b200_gemm_bf16(const void* A, int64_t lda, int a_rows_are_k, const void* B, 
                    const void* res, int64_t ldres, void* aux, int64_t ldaux, int block_n,
                    int split_k, void* stream);
 
+/* b200_gemm_bf16 with a caller-owned workspace of b200_gemm_workspace_bytes() bytes that enables stream-K for the
+ * last, partial wave of output tiles: the k blocks of those tiles are dealt out evenly to all CTAs, partial fp32
+ * accumulators travel through the workspace and the CTA holding a tile's first k block runs its epilogue (same
+ * result up to fp32 summation order; deterministic).  The workspace's first 16 KB are flags: the caller zeroes them
+ * ONCE, every launch leaves them zero.  One workspace per stream: launches that may overlap must not share it.
+ * workspace = NULL behaves exactly like b200_gemm_bf16. */
+int64_t b200_gemm_workspace_bytes(void);
+int b200_gemm_bf16_ws(const void* A, int64_t lda, int a_rows_are_k, const void* B, int64_t ldb,
+                   int b_rows_are_k, const void* A2, int64_t lda2, const void* B2, int64_t ldb2,
+                   int K2, void* C, int64_t ldc, int out_is_f32, int M, int N, int K, int epilogue,
+                   const void* bias, const void* gate, int64_t gate_stride, int64_t rows_per_gate,
+                   const void* res, int64_t ldres, void* aux, int64_t ldaux, int block_n,
+                   int split_k, void* workspace, int64_t workspace_bytes,
+                     void* stream);
+
 /* Strided batch of `groups` identically shaped GEMMs in ONE launch:  C_g[M,N] = A_g * B_g^T (+ A2_g * B2_g^T)
  * (+ bias_g).  Operand g is the sub-block of the given tensor displaced by g * (rows, cols) elements;
  * `group_offsets` is a HOST array of 11 ints {a_rows, a_cols, b_rows, b_cols, a2_rows, a2_cols, b2_rows,

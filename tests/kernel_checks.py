@@ -489,6 +489,60 @@ def check_rf_and_misc():
     torch.cuda.synchronize()
 
 
+def check_gemm_stream_k():
+    """Shapes whose last wave of tiles is partial: the k blocks of those tiles are spread over all CTAs and the
+    partials meet in the owner's epilogue (b200_gemm_bf16_ws).  Against fp32 matmul, against the same GEMM with
+    stream-K switched off, and twice in a row (the flags must come back clean)."""
+    import os
+    from b200_ltx import ops
+    cases = [  # M, N, K, K2, b_rows_are_k, epilogue operands, block_n
+        (6144, 2048, 1024, 0, False, "", 0),
+        (6144, 2048, 2048, 64, False, "bias gate res", 0),
+        (6144, 2048, 2048, 0, True, "res", 0),
+        (6000, 2048, 512, 0, False, "bias", 0),
+        (6144, 8192, 512, 0, False, "gelu", 0),
+        (4096, 2048, 512, 0, False, "bias res", 128),
+    ]
+    for (M, N, K, K2, b_k, epi, bn) in cases:
+        a = _randn(M, K, seed=1, scale=0.5)
+        b = _randn(K, N, seed=2, scale=0.5) if b_k else _randn(N, K, seed=2, scale=0.5)
+        kw = dict(b_rows_are_k=b_k, block_n=bn)
+        ref = a.float() @ (b.float() if b_k else b.float().T)
+        if K2:
+            a2, b2 = _randn(M, K2, seed=3, scale=0.5), _randn(N, K2, seed=4, scale=0.5)
+            kw.update(a2=a2, b2=b2)
+            ref = ref + a2.float() @ b2.float().T
+        if "bias" in epi:
+            kw["bias"] = _randn(N, seed=5)
+            ref = ref + kw["bias"].float()
+        pre = None
+        if "gelu" in epi:
+            pre = torch.empty(M, N, device="cuda", dtype=BF16)
+            kw.update(epilogue=ops.EPI_GELU, aux=pre, bias=_randn(N, seed=5))
+            ref = F.gelu((ref + kw["bias"].float()).to(BF16).float(), approximate="tanh")
+        if "gate" in epi:
+            kw.update(gate=_randn(1, N, seed=6), rows_per_gate=M)
+            ref = ref * kw["gate"].float()
+        if "res" in epi:
+            kw["res"] = _randn(M, N, seed=7)
+            ref = ref + kw["res"].float()
+        tag = f"M={M} N={N} K={K}+{K2} b_k={int(b_k)} epi='{epi}' bn={bn}"
+        os.environ.pop("B200_GEMM_STREAMK", None)
+        plain = ops.gemm(a, b, **kw).clone()
+        os.environ["B200_GEMM_STREAMK"] = "1"   # off by default (measured neutral on this power-capped part)
+        try:
+            out1 = ops.gemm(a, b, **kw).clone()
+            out2 = ops.gemm(a, b, **kw)
+        finally:
+            os.environ.pop("B200_GEMM_STREAMK", None)
+        _assert_close("stream-K gemm " + tag, out1, ref, 6e-3)
+        _assert_close("stream-K vs whole tiles " + tag, out1, plain, 2e-3)
+        assert torch.equal(out1, out2), "stream-K not repeatable: " + tag
+    torch.cuda.synchronize()
+    ws = ops._gemm_workspace(torch.device("cuda", torch.cuda.current_device()))
+    assert int(ws[:16384].view(torch.int32).abs().sum()) == 0, "stream-K flags left set"
+
+
 def check_guidance_step():
     """Fused sampling tail (guidance combine + Euler + conditioning select + next model input) against the oracle's
     restatement of pipeline_ltx_video.py:1217-1260, :1346-1379 in fp32."""
@@ -541,6 +595,7 @@ GROUPS = {
     "gemm_layouts": check_gemm_layouts,
     "gemm_epilogues": check_gemm_epilogues,
     "gemm_batched": check_gemm_batched,
+    "gemm_stream_k": check_gemm_stream_k,
     "linear_fn": check_linear_fn,
     "norm_mod": check_norm_mod,
     "qknorm_rope": check_qknorm_rope,

@@ -48,6 +48,59 @@ struct GemmParams {
   // operand tensors (groups == 1: plain GEMM).  Offsets are in elements of the tensor as stored.
   int groups;
   int a_gr, a_gc, b_gr, b_gc, a2_gr, a2_gc, b2_gr, b2_gc, c_gr, c_gc, bias_g;
+  // stream-K for the last, partial wave (sk_tiles > 0): the k blocks of tiles [0, sk_tiles) are dealt out evenly to
+  // all CTAs (pairs) ahead of their whole tiles; a CTA whose share starts inside a tile dumps its fp32 partial into
+  // `sk_ws` and raises a flag, the CTA that holds the tile's first k block adds the partials in its epilogue.
+  int sk_tiles;
+  float* sk_ws;   // [CTA or pair][rank][BN / 4][128][4] fp32 partial accumulators
+  int* sk_flags;  // [CTA or pair][rank][8 epilogue warps], zero between launches (the consumer clears them)
+};
+
+// One unit of work of the persistent walk: k blocks [kb_begin, kb_end) of output tile `tile` (z = split-K slice or
+// batch group).  role: 0 = a whole tile, 1 = partial that is dumped for another CTA, 2 = partial that owns the tile's
+// epilogue and adds the other CTAs' partials.
+struct GemmUnit {
+  int tile, z, kb_begin, kb_end, role;
+};
+
+struct GemmWalk {
+  int w, P, tiles_mn, total, kb_all, kb_per, groups;
+  int it, it_end;    // this CTA's remaining share of the stream-K region, in k blocks
+  int64_t sk_iters;  // sk_tiles * kb_all
+  int work;          // next whole-tile work item
+
+  __device__ GemmWalk(const GemmParams& p, int w_, int P_) : w(w_), P(P_) {
+    tiles_mn = p.m_tiles * p.n_tiles;
+    total = tiles_mn * p.splits * p.groups;
+    kb_all = p.kb1 + p.kb2;
+    kb_per = (kb_all + p.splits - 1) / p.splits;
+    groups = p.groups;
+    sk_iters = (int64_t)p.sk_tiles * kb_all;
+    it = (int)share_begin(w);
+    it_end = (int)share_begin(w + 1);
+    work = p.sk_tiles + w;
+  }
+  __device__ int64_t share_begin(int cta) const { return sk_iters * cta / P; }
+  __device__ bool next(GemmUnit& u) {
+    if (it < it_end) {
+      u.tile = it / kb_all;
+      u.z = 0;
+      u.kb_begin = it - u.tile * kb_all;
+      u.kb_end = min(kb_all, u.kb_begin + (it_end - it));
+      u.role = u.kb_begin > 0 ? 1 : (u.kb_end < kb_all ? 2 : 0);
+      it += u.kb_end - u.kb_begin;
+      return true;
+    }
+    if (work >= total) return false;
+    u.tile = work % tiles_mn;
+    u.z = work / tiles_mn;
+    const int split = groups > 1 ? 0 : u.z;
+    u.kb_begin = split * kb_per;
+    u.kb_end = min(kb_all, u.kb_begin + kb_per);
+    u.role = 0;
+    work += P;
+    return true;
+  }
 };
 
 __device__ __forceinline__ float tanh_fast(float x) {
@@ -176,12 +229,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
-  const int tiles_mn = p.m_tiles * p.n_tiles;
-  const int total_tiles = tiles_mn * p.splits * p.groups;  // work items (splits > 1 and groups > 1 exclude each other)
-  const int kb_all = p.kb1 + p.kb2;
-  const int kb_per = (kb_all + p.splits - 1) / p.splits;
-
-  // persistent walk: a CTA (or CTA pair) takes every `work_step`-th work item
+  // persistent walk: a CTA (or CTA pair) first takes its share of the stream-K region (if any), then every
+  // `work_step`-th whole work item (splits > 1, groups > 1 and stream-K exclude each other)
   const int work_first = CTA2 ? blockIdx.x >> 1 : blockIdx.x;
   const int work_step = CTA2 ? gridDim.x >> 1 : gridDim.x;
 
@@ -189,12 +238,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     // ------------------------------ TMA producer ------------------------------
     int stage = 0;
     uint32_t phase = 0;
-    for (int work = work_first; work < total_tiles; work += work_step) {
-      const int tile = work % tiles_mn, z = work / tiles_mn;  // z = split-K slice or batch group
+    GemmWalk walk(p, work_first, work_step);
+    GemmUnit u;
+    while (walk.next(u)) {
+      const int tile = u.tile;
       const int mt = (tile % p.m_tiles) * (CTA2 ? 2 : 1) + rank, nt = tile / p.m_tiles;
-      const int split = p.groups > 1 ? 0 : z, g = p.groups > 1 ? z : 0;
-      const int kb_begin = split * kb_per, kb_end = min(kb_all, kb_begin + kb_per);
-      for (int kb = kb_begin; kb < kb_end; ++kb) {
+      const int g = p.groups > 1 ? u.z : 0;
+      for (int kb = u.kb_begin; kb < u.kb_end; ++kb) {
         mbar_wait(empty_bar(stage), phase ^ 1);
         // pair: both CTAs' loads are credited to rank 0's barrier, armed by rank 0 for both
         if (!CTA2 || rank == 0) mbar_expect_tx(full_bar(stage), (CTA2 ? 2 : 1) * Cfg::STAGE);
@@ -239,9 +289,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     constexpr uint32_t A_STEP = A_MN ? 2048 : 32, B_STEP = B_MN ? 2048 : 32;
     int stage = 0, acc = 0;
     uint32_t phase = 0, acc_phase = 0;
-    for (int work = work_first; work < total_tiles; work += work_step) {
-      const int split = p.groups > 1 ? 0 : work / tiles_mn;
-      const int kb_begin = split * kb_per, kb_end = min(kb_all, kb_begin + kb_per);
+    GemmWalk walk(p, work_first, work_step);
+    GemmUnit u;
+    while (walk.next(u)) {
+      const int kb_begin = u.kb_begin, kb_end = u.kb_end;
       mbar_wait(tempty_bar(acc), acc_phase ^ 1);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + acc * BN;
@@ -276,13 +327,79 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     const int chalf = (warp - 4) >> 2;  // which half of the tile's columns this warp drains
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int work = work_first; work < total_tiles; work += work_step) {
-      const int tile = work % tiles_mn;
+    GemmWalk walk(p, work_first, work_step);
+    GemmUnit u;
+    while (walk.next(u)) {
+      const int tile = u.tile;
       const int mt = (tile % p.m_tiles) * (CTA2 ? 2 : 1) + rank, nt = tile / p.m_tiles;
-      const int g = p.groups > 1 ? work / tiles_mn : 0;
+      const int g = p.groups > 1 ? u.z : 0;
       const int crow = g * p.c_gr, ccol = g * p.c_gc;  // output displacement of this group
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
+      // ---- stream-K: partial accumulators travel through global memory ----
+      int sk_from[4];  // CTAs (pairs) whose partials of this tile are added here
+      int sk_n = 0;
+      if (BN >= 128 && u.role == 1) {
+        // dump this CTA's fp32 partial, [BN / 4][128][4] so that a warp writes 512 contiguous bytes, and signal
+        float* wsb = p.sk_ws + (size_t)(work_first * 2 + rank) * 128 * BN;
+        const uint32_t t_row = tmem_base + ((uint32_t)(ew * 32) << 16) + acc * BN;
+#pragma unroll 1
+        for (int c = chalf * (BN / 2); c < (chalf + 1) * (BN / 2); c += 32) {
+          uint32_t r[32];
+          tmem_ld32(t_row + c, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int q = 0; q < 8; ++q)
+            *reinterpret_cast<float4*>(wsb + ((size_t)(c / 4 + q) * 128 + ew * 32 + lane) * 4) =
+                make_float4(__uint_as_float(r[q * 4]), __uint_as_float(r[q * 4 + 1]), __uint_as_float(r[q * 4 + 2]),
+                            __uint_as_float(r[q * 4 + 3]));
+        }
+        __threadfence();
+        __syncwarp();
+        if (lane == 0) {
+          int* f = p.sk_flags + (work_first * 2 + rank) * 8 + (warp - 4);
+          asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(f), "r"(1) : "memory");
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if (CTA2) mbar_arrive_even_cta(tempty_bar(acc));
+          else mbar_arrive(tempty_bar(acc));
+        }
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+        continue;
+      }
+      if (BN >= 128 && u.role == 2) {
+        // the rest of this tile's k blocks went to the following CTAs (their FIRST unit, so the partials are early)
+        const int64_t tile_end = (int64_t)(tile + 1) * walk.kb_all;
+        for (int w2 = work_first + 1; w2 < work_step && walk.share_begin(w2) < tile_end; ++w2) {
+          if (sk_n == 4) {  // the host bounds the shares so that this cannot happen
+            printf("b200 gemm: stream-K tile shared by more than five CTAs\n");
+            __trap();
+          }
+          sk_from[sk_n++] = w2;
+        }
+        if (lane == 0) {
+          for (int ci = 0; ci < sk_n; ++ci) {
+            const int* f = p.sk_flags + (sk_from[ci] * 2 + rank) * 8 + (warp - 4);
+            int v = 0;
+            uint32_t spins = 0;
+            do {
+              asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
+              if (!v) {
+                __nanosleep(200);
+                if (++spins > (1u << 24)) {
+                  printf("b200 gemm: stream-K partial of CTA %d never arrived\n", sk_from[ci]);
+                  __trap();
+                }
+              }
+            } while (!v);
+          }
+        }
+        __syncwarp();
+        __threadfence();
+      }
       const int64_t row = (int64_t)mt * 128 + ew * 32 + lane;
       const bool row_ok = row < p.M;
       const bf16* bias_g = p.bias ? p.bias + g * p.bias_g : nullptr;
@@ -319,6 +436,18 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             uint32_t r[32];
             tmem_ld32(t_row + c + hc * 32, r);
             tmem_ld_wait();
+            for (int ci = 0; ci < sk_n; ++ci) {
+              const float* pb = p.sk_ws + (size_t)(sk_from[ci] * 2 + rank) * 128 * BN;
+#pragma unroll
+              for (int q = 0; q < 8; ++q) {
+                const float4 a = __ldcg(reinterpret_cast<const float4*>(
+                    pb + ((size_t)((c + hc * 32) / 4 + q) * 128 + ew * 32 + lane) * 4));
+                r[q * 4 + 0] = __float_as_uint(__uint_as_float(r[q * 4 + 0]) + a.x);
+                r[q * 4 + 1] = __float_as_uint(__uint_as_float(r[q * 4 + 1]) + a.y);
+                r[q * 4 + 2] = __float_as_uint(__uint_as_float(r[q * 4 + 2]) + a.z);
+                r[q * 4 + 3] = __float_as_uint(__uint_as_float(r[q * 4 + 3]) + a.w);
+              }
+            }
 #pragma unroll
             for (int g = 0; g < 4; ++g) {
               const int n = n_slab + hc * 32 + g * 8;
@@ -425,6 +554,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           }
         }
       }
+      if (sk_n > 0) {
+        __syncwarp();
+        if (lane == 0)
+          for (int ci = 0; ci < sk_n; ++ci) p.sk_flags[(sk_from[ci] * 2 + rank) * 8 + (warp - 4)] = 0;  // consumed
+      }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {
@@ -499,6 +633,11 @@ using namespace b200;
 
 static inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
+// 16 KB of flags + one 128 x 256 fp32 partial per CTA and rank slot of the largest grid
+extern "C" int64_t b200_gemm_workspace_bytes(void) {
+  return 16384 + (int64_t)num_sms() * 2 * 128 * 256 * (int64_t)sizeof(float);
+}
+
 // Strided-batch description (b200_gemm_bf16_batched): `groups` problems of identical shape whose operands
 // are sub-blocks of the given tensors displaced by g * (rows, cols) elements.
 struct GemmGroups {
@@ -512,7 +651,8 @@ static int gemm_impl(const void* A, int64_t lda, int a_kmajor_rows_are_k, const 
                               int out_is_f32, int M, int N, int K, int epilogue, const void* bias,
                               const void* gate, int64_t gate_stride, int64_t rows_per_gate,
                               const void* res, int64_t ldres, void* aux, int64_t ldaux,
-                              int block_n, int split_k, void* stream, const GemmGroups& gg) {
+                              int block_n, int split_k, void* stream, const GemmGroups& gg,
+                              void* workspace = nullptr, int64_t workspace_bytes = 0) {
   const bool a_mn = a_kmajor_rows_are_k != 0, b_mn = b_rows_are_k != 0;
   if (M < 0 || N < 0 || K < 0 || K2 < 0) return arg_error("gemm_bf16: negative dimension");
   if (M == 0 || N == 0) return 0;  // empty output: nothing to do (empty tensors carry null pointers)
@@ -618,6 +758,24 @@ static int gemm_impl(const void* A, int64_t lda, int a_kmajor_rows_are_k, const 
       return arg_error("gemm_bf16: cuTensorMapEncodeTiled failed (aux)", rc);
   }
 
+  // stream-K over the last, partial wave of tiles (see GemmParams): worth it when that wave would leave a good part
+  // of the SMs idle, and bounded so that a tile is never shared by more than four CTAs
+  p.sk_tiles = 0;
+  p.sk_ws = nullptr;
+  p.sk_flags = nullptr;
+  if (workspace && p.tma_store && p.splits == 1 && p.groups == 1 && !getenv("B200_GEMM_NO_STREAMK")) {
+    const int P = pair ? num_sms() / 2 : num_sms();
+    const int T = p.m_tiles * p.n_tiles;
+    const int R = T % P;
+    if (T > P && R * 3 >= P && R * 10 <= 9 * P && p.kb1 + p.kb2 >= 8) {
+      if (workspace_bytes < b200_gemm_workspace_bytes() || !al16(workspace))
+        return arg_error("gemm_bf16: workspace too small or misaligned (see b200_gemm_workspace_bytes)");
+      p.sk_tiles = R;
+      p.sk_flags = (int*)workspace;   // first 16 KB: flags (zero between launches)
+      p.sk_ws = (float*)((char*)workspace + 16384);
+    }
+  }
+
   cudaStream_t st = (cudaStream_t)stream;
 #define DISPATCH(BN_)                                                                     \
   if (bn == BN_) {                                                                        \
@@ -651,6 +809,20 @@ extern "C" int b200_gemm_bf16(const void* A, int64_t lda, int a_kmajor_rows_are_
   return gemm_impl(A, lda, a_kmajor_rows_are_k, B, ldb, b_rows_are_k, A2, lda2, B2, ldb2, K2, C, ldc, out_is_f32,
                    M, N, K, epilogue, bias, gate, gate_stride, rows_per_gate, res, ldres, aux, ldaux, block_n,
                    split_k, stream, gg);
+}
+
+extern "C" int b200_gemm_bf16_ws(const void* A, int64_t lda, int a_kmajor_rows_are_k, const void* B,
+                                 int64_t ldb, int b_rows_are_k, const void* A2, int64_t lda2,
+                                 const void* B2, int64_t ldb2, int K2, void* C, int64_t ldc,
+                                 int out_is_f32, int M, int N, int K, int epilogue, const void* bias,
+                                 const void* gate, int64_t gate_stride, int64_t rows_per_gate,
+                                 const void* res, int64_t ldres, void* aux, int64_t ldaux,
+                                 int block_n, int split_k, void* workspace, int64_t workspace_bytes,
+                                 void* stream) {
+  GemmGroups gg = {1, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+  return gemm_impl(A, lda, a_kmajor_rows_are_k, B, ldb, b_rows_are_k, A2, lda2, B2, ldb2, K2, C, ldc, out_is_f32,
+                   M, N, K, epilogue, bias, gate, gate_stride, rows_per_gate, res, ldres, aux, ldaux, block_n,
+                   split_k, stream, gg, workspace, workspace_bytes);
 }
 
 extern "C" int b200_gemm_bf16_batched(const void* A, int64_t lda, int a_rows_are_k, const void* B, int64_t ldb,

@@ -19,6 +19,8 @@ PROTOTYPES = {
     "b200_last_error": (c_char_p, []),
     "b200_device_check": (I, []),
     "b200_gemm_bf16": (I, [P, L, I, P, L, I, P, L, P, L, I, P, L, I, I, I, I, I, P, P, L, L, P, L, P, L, I, I, P]),
+    "b200_gemm_workspace_bytes": (L, []),
+    "b200_gemm_bf16_ws": (I, [P, L, I, P, L, I, P, L, P, L, I, P, L, I, I, I, I, I, P, P, L, L, P, L, P, L, I, I, P, L, P]),
     "b200_gemm_bf16_batched": (I, [P, L, I, P, L, I, P, L, P, L, I, P, L, I, I, I, I, P, I, I, P, P]),
     "b200_fa_fwd": (I, [P, L, P, L, P, L, P, L, P, P, I, I, I, I, I, F, P]),
     "b200_attn_merge": (I, [P, L, P, P, L, P, P, L, I, I, I, I, P]),

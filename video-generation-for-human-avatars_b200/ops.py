@@ -2,6 +2,7 @@
 
 Every function here launches hand-written sm_100a kernels from libb200ltx.so on the current CUDA
 stream.  PyTorch supplies device memory, streams and the autograd graph only."""
+import os
 from typing import Optional, Tuple
 
 import torch
@@ -133,13 +134,33 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, a_rows_are_k=False, b_rows_are_k=F
             raise _lib.B200Error("gemm: gate shape / rows_per_gate mismatch")
     if bias is not None and (bias.dtype != BF16 or bias.numel() != N or not bias.is_contiguous()):
         raise _lib.B200Error("gemm: bias must be a contiguous bf16 vector of length N")
-    _call("gemm", 2.0 * M * N * (K + K2), "flop", _L().b200_gemm_bf16,
+    # Stream-K for the last partial wave is built and parity-tested but OFF by default: on this power-capped part the
+    # idle SMs of a partial wave hand their power budget to the busy ones, so evening out the wave measured within
+    # noise at K = 8192 and slower at K = 2048 ("what measurements changed").  B200_GEMM_STREAMK=1 enables.
+    ws = _gemm_workspace(a.device) if (M * N >= (1 << 22) and os.environ.get("B200_GEMM_STREAMK") == "1") else None
+    _call("gemm", 2.0 * M * N * (K + K2), "flop", _L().b200_gemm_bf16_ws,
         _p(a), a.stride(0), int(a_rows_are_k), _p(b), b.stride(0), int(b_rows_are_k),
         _p(a2), a2.stride(0) if a2 is not None else 0, _p(b2), b2.stride(0) if b2 is not None else 0, K2,
         _p(out), out.stride(0), int(out.dtype == torch.float32), M, N, K, epilogue,
         _p(bias), _p(gate), gate_stride, rows_per_gate, _p(res), res.stride(0) if res is not None else 0,
-        _p(aux), aux.stride(0) if aux is not None else 0, block_n, split_k, _s())
+        _p(aux), aux.stride(0) if aux is not None else 0, block_n, split_k, _p(ws), ws.numel() if ws is not None else 0,
+        _s())
     return out
+
+
+_gemm_ws = {}
+
+
+def _gemm_workspace(device):
+    """Stream-K workspace of the current stream (b200_gemm_bf16_ws: one per stream, flags zeroed once)."""
+    key = (device.index, _s())
+    ws = _gemm_ws.get(key)
+    if ws is None:
+        n = _L().b200_gemm_workspace_bytes()
+        ws = torch.empty(n, device=device, dtype=torch.uint8)
+        ws[:16384].zero_()
+        _gemm_ws[key] = ws
+    return ws
 
 
 def gemm_batched(a, b, out, M, N, K, groups, offs, *, a_rows_are_k=False, b_rows_are_k=False, a2=None, b2=None,
