@@ -176,6 +176,17 @@ int b200_guidance_step(const void* v, float* x, void* x_next, int n_next, const 
                        int has_stg, int cfg_star, int rescale, void* workspace, int64_t workspace_bytes,
                        void* stream);
 
+/* AdamW (decoupled weight decay) over a list of tensors in ONE launch.  `table`: DEVICE array of 48-byte entries
+ *   { void* param; const void* grad; void* exp_avg; void* exp_avg_sq; int64_t numel; int32_t is_bf16; int32_t pad; }
+ * (fp32 or bf16 tensors, state in the parameter's dtype, math in fp32); `block_map`: DEVICE int32 [n_blocks][2] =
+ * (entry index, chunk index), one block per b200_adamw_chunk_elems() elements of an entry; `step`: DEVICE fp32 count
+ * of completed steps, incremented by the launch; `hyper`: DEVICE fp32 {lr, beta1, beta2, eps, weight_decay};
+ * `done_counter`: DEVICE int32, zero between launches.  Everything the update depends on is in device memory, so the
+ * launch can be captured and replayed.  Replaces torch.optim.AdamW(params, lr).step(), training.py:206, 271. */
+int b200_adamw_chunk_elems(void);
+int b200_adamw_step(const void* table, const int32_t* block_map, int n_blocks, float* step, const float* hyper,
+                    int32_t* done_counter, void* stream);
+
 /* out[m,:] = x[m,:] * g[m / rows_per_mod,:]  (AdaLN gate applied to an incoming gradient). */
 int b200_rowscale(const void* x, int64_t ldx, const void* g, int64_t gstride, void* out, int64_t ldo,
                   int64_t rows, int D, int64_t rows_per_mod, void* stream);

@@ -543,6 +543,40 @@ def check_gemm_stream_k():
     assert int(ws[:16384].view(torch.int32).abs().sum()) == 0, "stream-K flags left set"
 
 
+def check_adamw():
+    """b200_ltx.optim.FusedAdamW (one launch over all tensors) against torch.optim.AdamW, 6 steps, fp32 and bf16
+    tensors, aligned and ragged sizes, a parameter without gradient, and a state_dict round trip."""
+    from b200_ltx import optim
+    shapes = [((2048, 32), torch.float32), ((32, 2048), torch.float32), ((1024, 2048), BF16), ((2048,), BF16),
+              ((1000, 3), torch.float32), ((777,), BF16), ((5,), torch.float32)]
+    g = torch.Generator(device="cpu").manual_seed(0)
+    init = [torch.randn(*s, generator=g).to("cuda", dt) for s, dt in shapes]
+    mine = [torch.nn.Parameter(t.clone()) for t in init] + [torch.nn.Parameter(torch.ones(7, device="cuda"))]
+    ref = [torch.nn.Parameter(t.clone()) for t in init] + [torch.nn.Parameter(torch.ones(7, device="cuda"))]
+    kw = dict(lr=3e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2)
+    o_mine, o_ref = optim.FusedAdamW(mine, **kw), torch.optim.AdamW(ref, fused=True, **kw)
+    for it in range(6):
+        if it == 3:   # LR schedule step + checkpoint round trip
+            for o in (o_mine, o_ref):
+                o.param_groups[0]["lr"] = 1e-3
+            sd = o_mine.state_dict()
+            o_mine = optim.FusedAdamW(mine, **kw)
+            o_mine.load_state_dict(sd)
+        for a, b in zip(mine[:-1], ref[:-1]):
+            gr = torch.randn(a.shape, generator=g).to("cuda", a.dtype)
+            a.grad, b.grad = gr.clone(), gr.clone()
+        o_mine.step()
+        o_ref.step()
+    for i, (a, b) in enumerate(zip(mine, ref)):
+        tol = 2e-6 if a.dtype == torch.float32 else 4e-3
+        _assert_close(f"adamw param {i} {tuple(a.shape)} {a.dtype}", a.detach(), b.detach(), tol)
+    assert torch.equal(mine[-1].detach(), ref[-1].detach())      # no gradient: untouched
+    st = o_mine.state[mine[0]]
+    assert float(st["step"]) == 6.0
+    _assert_close("adamw exp_avg_sq", st["exp_avg_sq"], o_ref.state[ref[0]]["exp_avg_sq"], 2e-6)
+    torch.cuda.synchronize()
+
+
 def check_guidance_step():
     """Fused sampling tail (guidance combine + Euler + conditioning select + next model input) against the oracle's
     restatement of pipeline_ltx_video.py:1217-1260, :1346-1379 in fp32."""
@@ -607,4 +641,5 @@ GROUPS = {
     "empty_and_degenerate": check_empty_and_degenerate,
     "rf_and_misc": check_rf_and_misc,
     "guidance_step": check_guidance_step,
+    "adamw": check_adamw,
 }

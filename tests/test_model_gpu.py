@@ -184,10 +184,12 @@ def test_guided_sampling_loop_matches_oracle_loop(use_graph):
 
 
 @pytest.mark.gpu
-def test_graphed_train_step_learns_and_matches_eager_shapes():
+@pytest.mark.parametrize("optimizer", ["torch_fused", "b200_fused"])
+def test_graphed_train_step_learns_and_matches_eager_shapes(optimizer):
     """train.GraphedTrainStep: the captured micro-step replays with fresh timestep / noise draws, updates the
-    LoRA + caption parameters and drives the loss down on a fixed tiny batch (functional check of the graph path)."""
-    from b200_ltx import api, train
+    LoRA + caption parameters and drives the loss down on a fixed tiny batch (functional check of the graph path),
+    with torch's fused AdamW and with the single-launch b200_ltx.optim.FusedAdamW."""
+    from b200_ltx import api, optim, train
     cfg = dict(rb.LTXV_2B, num_layers=2, num_attention_heads=4, cross_attention_dim=256, caption_channels=64)
     P = rb.init_params(cfg, 32, seed=8)
     P = {k: (v if "lora_" in k else v.to(torch.bfloat16).float()) for k, v in P.items()}
@@ -197,7 +199,10 @@ def test_graphed_train_step_learns_and_matches_eager_shapes():
     prompt, mask = b["prompt_embeds"].to(torch.bfloat16).cuda(), b["prompt_mask"].cuda()
     params = [p for p in model.parameters() if p.requires_grad]
     before = [p.detach().clone() for p in params]
-    opt = torch.optim.AdamW(params, lr=2e-3, fused=True, capturable=True)
+    if optimizer == "torch_fused":
+        opt = torch.optim.AdamW(params, lr=2e-3, fused=True, capturable=True)
+    else:
+        opt = optim.FusedAdamW(params, lr=2e-3)
 
     class Cfg:
         rf_log_normal_mu, rf_log_normal_sigma, rf_quantile_min, rf_quantile_max = -0.5, 1.0, 0.005, 0.999
@@ -210,3 +215,19 @@ def test_graphed_train_step_learns_and_matches_eager_shapes():
     assert len(set(round(x, 6) for x in losses[:5])) > 1           # fresh t / noise on every replay
     assert sum(losses[-10:]) / 10 < sum(losses[:10]) / 10          # it learns
     assert any(not torch.equal(a, p.detach()) for a, p in zip(before, params))
+
+
+@pytest.mark.gpu
+def test_lora_merge_matches_matmul():
+    """LoraLinear.merge on the device (one rank-r GEMM accumulating into the bf16 weight in place) against the fp32
+    matmul of peft's merge_and_unload (torch_utils.py:66-102)."""
+    from b200_ltx import lora
+    torch.manual_seed(0)
+    base = torch.nn.Linear(2048, 2048, device="cuda", dtype=torch.bfloat16)
+    layer = lora.LoraLinear(base, 32, 64)
+    layer.lora_B["default"].weight.data.normal_(0, 0.02)
+    w0 = base.weight.detach().float().clone()
+    want = w0 + 2.0 * (layer.lora_B["default"].weight.float() @ layer.lora_A["default"].weight.float())
+    layer.merge()
+    assert mc.rel(base.weight.float(), want) < 3e-3
+    assert mc.rel(base.weight.float() - w0, want - w0) < 0.25   # the update itself (bf16 rounding of W + dW dominates)

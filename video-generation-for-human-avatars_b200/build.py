@@ -11,7 +11,7 @@ PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG_DIR, "csrc")
 OBJ_DIR = os.path.join(PKG_DIR, "build")
 LIB_PATH = os.path.join(PKG_DIR, "libb200ltx.so")
-SOURCES = ["api.cu", "elementwise.cu", "guidance.cu", "gemm.cu", "attn_fwd.cu", "attn_bwd.cu"]
+SOURCES = ["api.cu", "elementwise.cu", "guidance.cu", "adamw.cu", "gemm.cu", "attn_fwd.cu", "attn_bwd.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "--cudart", "shared", "-Xcompiler", "-fPIC"]

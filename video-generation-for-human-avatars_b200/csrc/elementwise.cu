@@ -62,192 +62,218 @@ __device__ __forceinline__ float warp_sum(float v) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// y = norm(x) * (1 + scale[b]) + shift[b]     (ln = 0: RMSNorm, ln = 1: LayerNorm, no affine)
+// Row kernels: one 128-thread block per row, 8 (D <= 1024) or 16 elements per thread.
+//   norm_mod fwd/bwd:    y = norm(x) * (1 + scale[b]) + shift[b]   (ln = 0: RMSNorm, ln = 1: LayerNorm, no affine)
+//                        dx = dres + rstd * (g - mean(g) [ln] - xhat * mean(g * xhat)),   g = dy * (1 + scale)
+//   qknorm_rope fwd/bwd: q/k RMSNorm (affine) + RoPE, one block per (row, tensor); cos/sin may be null (attn2);
+//                        dq/dk may be fp32 (the attention backward accumulates dq in fp32) or bf16;
+//                        dx = rstd * (w*dy - xhat * mean(w*dy*xhat)),  dy = RoPE^T(dout)
+// Every thread issues ALL its 16-byte loads of the row (up to 12) before the first use, 32+ warps per SM are
+// resident and nothing is unpacked twice; the two row reductions go through shared memory.  (The first version
+// gave a whole row to one warp -- 64 elements per lane, 16 warps per SM: too few bytes in flight and ~1600
+// instructions per row in one scheduler slot; 2.1-2.6 TB/s against 4.1-4.6 TB/s now.)
 // ---------------------------------------------------------------------------------------------
-template <int NC, bool EXACT>
-__global__ void __launch_bounds__(128, 4) norm_mod_fwd_kernel(
+__device__ __forceinline__ float2 block_sum2(float a, float b, float* red) {
+  a = warp_sum(a);
+  b = warp_sum(b);
+  __syncthreads();  // the previous reduction's reads are done
+  if ((threadIdx.x & 31) == 0) {
+    red[threadIdx.x >> 5] = a;
+    red[4 + (threadIdx.x >> 5)] = b;
+  }
+  __syncthreads();
+  return make_float2(red[0] + red[1] + red[2] + red[3], red[4] + red[5] + red[6] + red[7]);
+}
+
+// Two rows per block: the forward reads 4 KB per row and would otherwise have too few bytes in flight per SM; only
+// x is held in registers while the loads are outstanding (scale / shift are L2 hits, fetched after the reduction).
+template <int NCH>
+__global__ void __launch_bounds__(128) norm_mod_fwd_row_kernel(
     const bf16* __restrict__ x, int64_t ldx, bf16* __restrict__ y, int64_t ldy,
     const bf16* __restrict__ scale, const bf16* __restrict__ shift, int64_t mod_stride,
     int64_t rows, int D, int64_t rows_per_mod, float eps, int ln) {
-  const int lane = threadIdx.x & 31;
-  for (int64_t row = (int64_t)blockIdx.x * 4 + (threadIdx.x >> 5); row < rows; row += (int64_t)gridDim.x * 4) {
-  const bf16* xr = x + row * ldx;
-  Row8 xv[NC];
-  float s1 = 0.f, s2 = 0.f;
+  __shared__ float red[8];
+  const int64_t row0 = (int64_t)blockIdx.x * 2;
+  const bool two = row0 + 1 < rows;
+  uint4 xp[2][NCH];
 #pragma unroll
-  for (int c = 0; c < NC; ++c) {
-    int col = (c * 32 + lane) * 8;
-    if (EXACT || col < D) {
-      xv[c] = ld_bf16x8(xr + col);
+  for (int r = 0; r < 2; ++r)
 #pragma unroll
-      for (int i = 0; i < 8; ++i) { s1 += xv[c].v[i]; s2 += xv[c].v[i] * xv[c].v[i]; }
+    for (int c = 0; c < NCH; ++c) {
+      const int col = (c * 128 + threadIdx.x) * 8;
+      xp[r][c] = make_uint4(0, 0, 0, 0);
+      if (col < D && (r == 0 || two)) xp[r][c] = *reinterpret_cast<const uint4*>(x + (row0 + r) * ldx + col);
     }
-  }
-  s2 = warp_sum(s2);
-  float mean = 0.f, rstd;
+  float s1[2] = {0.f, 0.f}, s2[2] = {0.f, 0.f};
+#pragma unroll
+  for (int r = 0; r < 2; ++r)
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+      const Row8 xv = unpack8(xp[r][c]);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { s1[r] += xv.v[i]; s2[r] += xv.v[i] * xv.v[i]; }
+    }
+  float mean[2] = {0.f, 0.f}, rstd[2];
   if (ln) {
-    s1 = warp_sum(s1);
-    mean = s1 / D;
-    float var = fmaxf(s2 / D - mean * mean, 0.f);
-    rstd = rsqrtf(var + eps);
-  } else {
-    rstd = rsqrtf(s2 / D + eps);
-  }
-  int64_t mb = row / rows_per_mod;
-  const bf16* sc = scale ? scale + mb * mod_stride : nullptr;
-  const bf16* sh = shift ? shift + mb * mod_stride : nullptr;
-  bf16* yr = y + row * ldy;
 #pragma unroll
-  for (int c = 0; c < NC; ++c) {
-    int col = (c * 32 + lane) * 8;
-    if (EXACT || col < D) {
-      Row8 o;
-      Row8 a, b;
-      if (sc) a = ld_bf16x8(sc + col);
-      if (sh) b = ld_bf16x8(sh + col);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        float n = (xv[c].v[i] - mean) * rstd;
-        if (sc) n *= (1.f + a.v[i]);
-        if (sh) n += b.v[i];
-        o.v[i] = n;
-      }
-      st_bf16x8(yr + col, o);
+    for (int r = 0; r < 2; ++r) {
+      const float2 t = block_sum2(s1[r], s2[r], red);
+      mean[r] = t.x / D;
+      rstd[r] = rsqrtf(fmaxf(t.y / D - mean[r] * mean[r], 0.f) + eps);
     }
+  } else {
+    const float2 t = block_sum2(s2[0], s2[1], red);
+    rstd[0] = rsqrtf(t.x / D + eps);
+    rstd[1] = rsqrtf(t.y / D + eps);
   }
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    if (r == 1 && !two) break;
+    const int64_t row = row0 + r;
+    const int64_t mb = row / rows_per_mod;
+    const bf16* sc = scale ? scale + mb * mod_stride : nullptr;
+    const bf16* sh = shift ? shift + mb * mod_stride : nullptr;
+    bf16* yr = y + row * ldy;
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+      const int col = (c * 128 + threadIdx.x) * 8;
+      if (col < D) {
+        const Row8 xv = unpack8(xp[r][c]);
+        Row8 a, b, o;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) a.v[i] = b.v[i] = 0.f;
+        if (sc) a = ld_bf16x8(sc + col);
+        if (sh) b = ld_bf16x8(sh + col);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o.v[i] = (xv.v[i] - mean[r]) * rstd[r] * (1.f + a.v[i]) + b.v[i];
+        st_bf16x8(yr + col, o);
+      }
+    }
   }
 }
 
-// dx = dres + rstd * (g - mean(g) [ln] - xhat * mean(g * xhat)),   g = dy * (1 + scale)
-template <int NC, bool EXACT>
-__global__ void __launch_bounds__(128, 4) norm_mod_bwd_kernel(
+template <int NCH>
+__global__ void __launch_bounds__(128) norm_mod_bwd_row_kernel(
     const bf16* __restrict__ dy, int64_t lddy, const bf16* __restrict__ x, int64_t ldx,
     const bf16* __restrict__ scale, int64_t mod_stride, const bf16* __restrict__ dres,
     int64_t lddres, bf16* __restrict__ dx, int64_t lddx, int64_t rows, int D,
     int64_t rows_per_mod, float eps, int ln) {
-  const int lane = threadIdx.x & 31;
-  for (int64_t row = (int64_t)blockIdx.x * 4 + (threadIdx.x >> 5); row < rows; row += (int64_t)gridDim.x * 4) {
-    const bf16* xr = x + row * ldx;
-    const bf16* gr = dy + row * lddy;
-    const int64_t mb = row / rows_per_mod;
-    const bf16* sc = scale ? scale + mb * mod_stride : nullptr;
-    // x and dy stay packed (bf16) in registers: 64 registers instead of 128, so 4 blocks fit per SM
-    uint4 xp[NC], gp[NC];
-    float s1 = 0.f, s2 = 0.f;
+  __shared__ float red[8];
+  const int64_t row = blockIdx.x;
+  const bf16* xr = x + row * ldx;
+  const bf16* gr = dy + row * lddy;
+  const bf16* sc = scale ? scale + (row / rows_per_mod) * mod_stride : nullptr;
+  const bf16* rr = dres ? dres + row * lddres : nullptr;
+  uint4 xp[NCH], gp[NCH], ap[NCH], rp[NCH];
 #pragma unroll
-    for (int c = 0; c < NC; ++c) {
-      const int col = (c * 32 + lane) * 8;
-      if (EXACT || col < D) {
-        xp[c] = *reinterpret_cast<const uint4*>(xr + col);
-        gp[c] = *reinterpret_cast<const uint4*>(gr + col);
-      }
+  for (int c = 0; c < NCH; ++c) {
+    const int col = (c * 128 + threadIdx.x) * 8;
+    xp[c] = gp[c] = ap[c] = rp[c] = make_uint4(0, 0, 0, 0);
+    if (col < D) {
+      xp[c] = *reinterpret_cast<const uint4*>(xr + col);
+      gp[c] = *reinterpret_cast<const uint4*>(gr + col);
+      if (sc) ap[c] = *reinterpret_cast<const uint4*>(sc + col);
+      if (rr) rp[c] = *reinterpret_cast<const uint4*>(rr + col);
     }
+  }
+  Row8 xv[NCH], gv[NCH];
+  float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-    for (int c = 0; c < NC; ++c) {
-      const int col = (c * 32 + lane) * 8;
-      if (EXACT || col < D) {
-        const Row8 xv = unpack8(xp[c]);
+  for (int c = 0; c < NCH; ++c) {
+    xv[c] = unpack8(xp[c]);
+    gv[c] = unpack8(gp[c]);
+    const Row8 a = unpack8(ap[c]);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) { s1 += xv.v[i]; s2 += xv.v[i] * xv.v[i]; }
-      }
+    for (int i = 0; i < 8; ++i) {
+      s1 += xv[c].v[i];
+      s2 += xv[c].v[i] * xv[c].v[i];
+      gv[c].v[i] *= (1.f + a.v[i]);
     }
-    s2 = warp_sum(s2);
-    float mean = 0.f, rstd;
-    if (ln) {
-      s1 = warp_sum(s1);
-      mean = s1 / D;
-      rstd = rsqrtf(fmaxf(s2 / D - mean * mean, 0.f) + eps);
-    } else {
-      rstd = rsqrtf(s2 / D + eps);
+  }
+  const float2 t = block_sum2(s1, s2, red);
+  float mean = 0.f, rstd;
+  if (ln) {
+    mean = t.x / D;
+    rstd = rsqrtf(fmaxf(t.y / D - mean * mean, 0.f) + eps);
+  } else {
+    rstd = rsqrtf(t.y / D + eps);
+  }
+  float gsum = 0.f, gx = 0.f;
+#pragma unroll
+  for (int c = 0; c < NCH; ++c) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      xv[c].v[i] = (xv[c].v[i] - mean) * rstd;  // xhat (0 beyond D: x = 0 there only for rms; gv = 0 anyway)
+      gsum += gv[c].v[i];
+      gx += gv[c].v[i] * xv[c].v[i];
     }
-    float gsum = 0.f, gx = 0.f;
+  }
+  const float2 u = block_sum2(gsum, gx, red);
+  gx = u.y / D;
+  gsum = ln ? u.x / D : 0.f;
+  bf16* outr = dx + row * lddx;
 #pragma unroll
-    for (int c = 0; c < NC; ++c) {
-      const int col = (c * 32 + lane) * 8;
-      if (EXACT || col < D) {
-        const Row8 xv = unpack8(xp[c]);
-        Row8 gv = unpack8(gp[c]);
-        if (sc) {
-          const Row8 a = ld_bf16x8(sc + col);
+  for (int c = 0; c < NCH; ++c) {
+    const int col = (c * 128 + threadIdx.x) * 8;
+    if (col < D) {
+      const Row8 r = unpack8(rp[c]);
+      Row8 o;
 #pragma unroll
-          for (int i = 0; i < 8; ++i) gv.v[i] *= (1.f + a.v[i]);
-        }
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          gsum += gv.v[i];
-          gx += gv.v[i] * ((xv.v[i] - mean) * rstd);
-        }
-      }
-    }
-    gx = warp_sum(gx) / D;
-    gsum = ln ? warp_sum(gsum) / D : 0.f;
-    bf16* outr = dx + row * lddx;
-    const bf16* rr = dres ? dres + row * lddres : nullptr;
-#pragma unroll
-    for (int c = 0; c < NC; ++c) {
-      const int col = (c * 32 + lane) * 8;
-      if (EXACT || col < D) {
-        const Row8 xv = unpack8(xp[c]);
-        Row8 gv = unpack8(gp[c]);
-        if (sc) {
-          const Row8 a = ld_bf16x8(sc + col);
-#pragma unroll
-          for (int i = 0; i < 8; ++i) gv.v[i] *= (1.f + a.v[i]);
-        }
-        Row8 o, r;
-        if (rr) r = ld_bf16x8(rr + col);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          float d = rstd * (gv.v[i] - gsum - (xv.v[i] - mean) * rstd * gx);
-          if (rr) d += r.v[i];
-          o.v[i] = d;
-        }
-        st_bf16x8(outr + col, o);
-      }
+      for (int i = 0; i < 8; ++i) o.v[i] = rstd * (gv[c].v[i] - gsum - xv[c].v[i] * gx) + r.v[i];
+      st_bf16x8(outr + col, o);
     }
   }
 }
 
-// ---------------------------------------------------------------------------------------------
-// q/k RMSNorm (affine) + RoPE.  One warp per (row, tensor).  cos/sin may be null (attn2).
-// ---------------------------------------------------------------------------------------------
-template <int NC, bool EXACT>
-__global__ void __launch_bounds__(128, 4) qknorm_rope_fwd_kernel(
+template <int NCH>
+__global__ void __launch_bounds__(128) qknorm_rope_fwd_row_kernel(
     const bf16* __restrict__ xq, int64_t ldq, const bf16* __restrict__ xk, int64_t ldk,
     const bf16* __restrict__ wq, const bf16* __restrict__ wk, const bf16* __restrict__ cosp,
     const bf16* __restrict__ sinp, int64_t ldcs, bf16* __restrict__ oq, int64_t ldoq,
     bf16* __restrict__ ok, int64_t ldok, int64_t rows_q, int64_t rows_k, int D, float eps) {
-  const int lane = threadIdx.x & 31;
-  for (int64_t w = (int64_t)blockIdx.x * 4 + (threadIdx.x >> 5); w < rows_q + rows_k; w += (int64_t)gridDim.x * 4) {
-  bool is_k = w >= rows_q;
-  int64_t row = is_k ? w - rows_q : w;
+  __shared__ float red[8];
+  const int64_t w = blockIdx.x;
+  const bool is_k = w >= rows_q;
+  const int64_t row = is_k ? w - rows_q : w;
   const bf16* xr = is_k ? xk + row * ldk : xq + row * ldq;
   const bf16* wt = is_k ? wk : wq;
   bf16* outr = is_k ? ok + row * ldok : oq + row * ldoq;
-  Row8 xv[NC];
-  float s2 = 0.f;
+  uint4 xp[NCH], wp[NCH], cp[NCH], sp[NCH];
 #pragma unroll
-  for (int c = 0; c < NC; ++c) {
-    int col = (c * 32 + lane) * 8;
-    if (EXACT || col < D) {
-      xv[c] = ld_bf16x8(xr + col);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) s2 += xv[c].v[i] * xv[c].v[i];
+  for (int c = 0; c < NCH; ++c) {
+    const int col = (c * 128 + threadIdx.x) * 8;
+    xp[c] = wp[c] = cp[c] = sp[c] = make_uint4(0, 0, 0, 0);
+    if (col < D) {
+      xp[c] = *reinterpret_cast<const uint4*>(xr + col);
+      wp[c] = *reinterpret_cast<const uint4*>(wt + col);
+      if (cosp) {
+        cp[c] = *reinterpret_cast<const uint4*>(cosp + row * ldcs + col);
+        sp[c] = *reinterpret_cast<const uint4*>(sinp + row * ldcs + col);
+      }
     }
   }
-  float rstd = rsqrtf(warp_sum(s2) / D + eps);
+  Row8 xv[NCH];
+  float s2 = 0.f;
 #pragma unroll
-  for (int c = 0; c < NC; ++c) {
-    int col = (c * 32 + lane) * 8;
-    if (EXACT || col < D) {
-      Row8 wv = ld_bf16x8(wt + col), o;
+  for (int c = 0; c < NCH; ++c) {
+    xv[c] = unpack8(xp[c]);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s2 += xv[c].v[i] * xv[c].v[i];
+  }
+  const float rstd = rsqrtf(block_sum2(s2, 0.f, red).x / D + eps);
+#pragma unroll
+  for (int c = 0; c < NCH; ++c) {
+    const int col = (c * 128 + threadIdx.x) * 8;
+    if (col < D) {
+      const Row8 wv = unpack8(wp[c]);
+      Row8 o;
 #pragma unroll
       for (int i = 0; i < 8; ++i) xv[c].v[i] = xv[c].v[i] * rstd * wv.v[i];
       if (cosp) {
-        Row8 cv = ld_bf16x8(cosp + row * ldcs + col), sv = ld_bf16x8(sinp + row * ldcs + col);
+        const Row8 cv = unpack8(cp[c]), sv = unpack8(sp[c]);
 #pragma unroll
         for (int i = 0; i < 8; i += 2) {
-          float a = xv[c].v[i], b = xv[c].v[i + 1];
+          const float a = xv[c].v[i], b = xv[c].v[i + 1];
           o.v[i] = a * cv.v[i] - b * sv.v[i];
           o.v[i + 1] = b * cv.v[i + 1] + a * sv.v[i + 1];
         }
@@ -257,81 +283,98 @@ __global__ void __launch_bounds__(128, 4) qknorm_rope_fwd_kernel(
       st_bf16x8(outr + col, o);
     }
   }
-  }
 }
 
-// gradient wrt the pre-norm projections.  dq/dk may be fp32 (attention backward accumulates dq in
-// fp32) or bf16.  dx = rstd * (w*dy - xhat * mean(w*dy*xhat)),  dy = RoPE^T(dout)
-template <int NC, bool EXACT>
-__global__ void __launch_bounds__(128, 4) qknorm_rope_bwd_kernel(
+template <int NCH>
+__global__ void __launch_bounds__(128) qknorm_rope_bwd_row_kernel(
     const void* __restrict__ dq, int64_t lddq, int dq_f32, const void* __restrict__ dk, int64_t lddk,
     int dk_f32, const bf16* __restrict__ xq, int64_t ldq, const bf16* __restrict__ xk, int64_t ldk,
     const bf16* __restrict__ wq, const bf16* __restrict__ wk, const bf16* __restrict__ cosp,
     const bf16* __restrict__ sinp, int64_t ldcs, bf16* __restrict__ oq, int64_t ldoq,
     bf16* __restrict__ ok, int64_t ldok, int64_t rows_q, int64_t rows_k, int D, float eps) {
-  const int lane = threadIdx.x & 31;
-  for (int64_t w = (int64_t)blockIdx.x * 4 + (threadIdx.x >> 5); w < rows_q + rows_k; w += (int64_t)gridDim.x * 4) {
-  bool is_k = w >= rows_q;
-  int64_t row = is_k ? w - rows_q : w;
+  __shared__ float red[8];
+  const int64_t w = blockIdx.x;
+  const bool is_k = w >= rows_q;
+  const int64_t row = is_k ? w - rows_q : w;
   const bf16* xr = is_k ? xk + row * ldk : xq + row * ldq;
   const bf16* wt = is_k ? wk : wq;
-  const void* gp = is_k ? dk : dq;
-  int64_t ldg = is_k ? lddk : lddq;
-  int g_f32 = is_k ? dk_f32 : dq_f32;
+  const void* gsrc = is_k ? dk : dq;
+  const int64_t ldg = is_k ? lddk : lddq;
+  const int g_f32 = is_k ? dk_f32 : dq_f32;
   bf16* outr = is_k ? ok + row * ldok : oq + row * ldoq;
-  uint4 xp[NC];  // x stays packed (bf16): 32 registers
-  Row8 gv[NC];
+  uint4 xp[NCH], wp[NCH], cp[NCH], sp[NCH], g0[NCH], g1[NCH];
+#pragma unroll
+  for (int c = 0; c < NCH; ++c) {
+    const int col = (c * 128 + threadIdx.x) * 8;
+    xp[c] = wp[c] = cp[c] = sp[c] = g0[c] = g1[c] = make_uint4(0, 0, 0, 0);
+    if (col < D) {
+      xp[c] = *reinterpret_cast<const uint4*>(xr + col);
+      wp[c] = *reinterpret_cast<const uint4*>(wt + col);
+      if (g_f32) {
+        const float* gp = reinterpret_cast<const float*>(gsrc) + row * ldg + col;
+        g0[c] = *reinterpret_cast<const uint4*>(gp);
+        g1[c] = *reinterpret_cast<const uint4*>(gp + 4);
+      } else {
+        g0[c] = *reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(gsrc) + row * ldg + col);
+      }
+      if (cosp) {
+        cp[c] = *reinterpret_cast<const uint4*>(cosp + row * ldcs + col);
+        sp[c] = *reinterpret_cast<const uint4*>(sinp + row * ldcs + col);
+      }
+    }
+  }
+  Row8 xv[NCH], gv[NCH];
   float s2 = 0.f;
 #pragma unroll
-  for (int c = 0; c < NC; ++c) {
-    int col = (c * 32 + lane) * 8;
-    if (EXACT || col < D) {
-      xp[c] = *reinterpret_cast<const uint4*>(xr + col);
-      Row8 g = g_f32 ? ld_f32x8(reinterpret_cast<const float*>(gp) + row * ldg + col)
-                     : ld_bf16x8(reinterpret_cast<const bf16*>(gp) + row * ldg + col);
-      if (cosp) {
-        Row8 cv = ld_bf16x8(cosp + row * ldcs + col), sv = ld_bf16x8(sinp + row * ldcs + col);
+  for (int c = 0; c < NCH; ++c) {
+    xv[c] = unpack8(xp[c]);
+    Row8 g;
+    if (g_f32) {
+      g.v[0] = __uint_as_float(g0[c].x); g.v[1] = __uint_as_float(g0[c].y);
+      g.v[2] = __uint_as_float(g0[c].z); g.v[3] = __uint_as_float(g0[c].w);
+      g.v[4] = __uint_as_float(g1[c].x); g.v[5] = __uint_as_float(g1[c].y);
+      g.v[6] = __uint_as_float(g1[c].z); g.v[7] = __uint_as_float(g1[c].w);
+    } else {
+      g = unpack8(g0[c]);
+    }
+    if (cosp) {
+      const Row8 cv = unpack8(cp[c]), sv = unpack8(sp[c]);
 #pragma unroll
-        for (int i = 0; i < 8; i += 2) {
-          float a = g.v[i], b = g.v[i + 1];
-          gv[c].v[i] = a * cv.v[i] + b * sv.v[i + 1];
-          gv[c].v[i + 1] = b * cv.v[i + 1] - a * sv.v[i];
-        }
-      } else {
-        gv[c] = g;
+      for (int i = 0; i < 8; i += 2) {
+        const float a = g.v[i], b = g.v[i + 1];
+        gv[c].v[i] = a * cv.v[i] + b * sv.v[i + 1];
+        gv[c].v[i + 1] = b * cv.v[i + 1] - a * sv.v[i];
       }
-      Row8 wv = ld_bf16x8(wt + col);
-      const Row8 xv = unpack8(xp[c]);
+    } else {
+      gv[c] = g;
+    }
+    const Row8 wv = unpack8(wp[c]);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        gv[c].v[i] *= wv.v[i];
-        s2 += xv.v[i] * xv.v[i];
-      }
+    for (int i = 0; i < 8; ++i) {
+      gv[c].v[i] *= wv.v[i];
+      s2 += xv[c].v[i] * xv[c].v[i];
     }
   }
-  float rstd = rsqrtf(warp_sum(s2) / D + eps);
+  const float rstd = rsqrtf(block_sum2(s2, 0.f, red).x / D + eps);
   float gx = 0.f;
 #pragma unroll
-  for (int c = 0; c < NC; ++c) {
-    int col = (c * 32 + lane) * 8;
-    if (EXACT || col < D) {
-      const Row8 xv = unpack8(xp[c]);
+  for (int c = 0; c < NCH; ++c) {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) gx += gv[c].v[i] * (xv.v[i] * rstd);
+    for (int i = 0; i < 8; ++i) {
+      xv[c].v[i] *= rstd;  // xhat
+      gx += gv[c].v[i] * xv[c].v[i];
     }
   }
-  gx = warp_sum(gx) / D;
+  gx = block_sum2(gx, 0.f, red).x / D;
 #pragma unroll
-  for (int c = 0; c < NC; ++c) {
-    int col = (c * 32 + lane) * 8;
-    if (EXACT || col < D) {
-      const Row8 xv = unpack8(xp[c]);
+  for (int c = 0; c < NCH; ++c) {
+    const int col = (c * 128 + threadIdx.x) * 8;
+    if (col < D) {
       Row8 o;
 #pragma unroll
-      for (int i = 0; i < 8; ++i) o.v[i] = rstd * (gv[c].v[i] - xv.v[i] * rstd * gx);
+      for (int i = 0; i < 8; ++i) o.v[i] = rstd * (gv[c].v[i] - xv[c].v[i] * gx);
       st_bf16x8(outr + col, o);
     }
-  }
   }
 }
 
@@ -440,20 +483,35 @@ __global__ void __launch_bounds__(256) lerp_condition_kernel(bf16* __restrict__ 
   }
 }
 
-// out[m, :] = x[m, :] * g[m / rows_per_mod, :]
+// out[m, :] = x[m, :] * g[m / rows_per_mod, :]      (four independent 16-byte vectors per thread in flight)
 __global__ void __launch_bounds__(256) rowscale_kernel(const bf16* __restrict__ x, int64_t ldx,
                                                        const bf16* __restrict__ g, int64_t gstride,
                                                        bf16* __restrict__ out, int64_t ldo,
                                                        int64_t rows, int D8, int64_t rows_per_mod) {
-  int64_t total = rows * D8;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
-       i += (int64_t)gridDim.x * blockDim.x) {
-    int64_t r = i / D8;
-    int c = (int)(i - r * D8) * 8;
-    Row8 a = ld_bf16x8(x + r * ldx + c), b = ld_bf16x8(g + (r / rows_per_mod) * gstride + c), o;
+  const int64_t total = rows * D8;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < total; i0 += 4 * stride) {
+    uint4 xp[4];
+    int64_t r[4];
+    int c[4];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) o.v[j] = a.v[j] * b.v[j];
-    st_bf16x8(out + r * ldo + c, o);
+    for (int k = 0; k < 4; ++k) {
+      const int64_t i = i0 + k * stride;
+      xp[k] = make_uint4(0, 0, 0, 0);
+      r[k] = i / D8;
+      c[k] = (int)(i - r[k] * D8) * 8;
+      if (i < total) xp[k] = *reinterpret_cast<const uint4*>(x + r[k] * ldx + c[k]);
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (i0 + k * stride < total) {
+        const Row8 a = unpack8(xp[k]), b = ld_bf16x8(g + (r[k] / rows_per_mod) * gstride + c[k]);
+        Row8 o;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o.v[j] = a.v[j] * b.v[j];
+        st_bf16x8(out + r[k] * ldo + c[k], o);
+      }
+    }
   }
 }
 
@@ -471,32 +529,49 @@ __global__ void __launch_bounds__(256) colsum_kernel(const bf16* __restrict__ x,
   if (part == 0 && c < N) out[c] = red[0][threadIdx.x] + red[1][threadIdx.x] + red[2][threadIdx.x] + red[3][threadIdx.x];
 }
 
-// delta[b, h, q] = sum_d o[b, q, h, d] * do[b, q, h, d]   (dh = 64: 8 lanes x 8 elements per head)
+// delta[b, h, q] = sum_d o[b, q, h, d] * do[b, q, h, d]   (dh = 64: 8 lanes x 8 elements per head; every thread
+// takes the same (head, slice) of two rows half the tensor apart, so four 16-byte loads are in flight per thread)
 __global__ void __launch_bounds__(256) attn_delta_kernel(const bf16* __restrict__ o, int64_t ldo,
                                                          const bf16* __restrict__ dout, int64_t lddo,
                                                          float* __restrict__ delta, int B, int H,
                                                          int Nq) {
-  int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  int64_t item = gid >> 3;  // (b, q, h)
-  int sub = gid & 7;
-  int64_t total = (int64_t)B * Nq * H;
-  float acc = 0.f;
-  if (item < total) {
-    int h = (int)(item % H);
-    int64_t bq = item / H;
-    Row8 a = ld_bf16x8(o + bq * ldo + h * 64 + sub * 8);
-    Row8 b = ld_bf16x8(dout + bq * lddo + h * 64 + sub * 8);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) acc += a.v[j] * b.v[j];
+  const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t item = gid >> 3;  // (row pair, h)
+  const int sub = gid & 7;
+  const int64_t BQ = (int64_t)B * Nq, half = (BQ + 1) / 2;
+  const int h = (int)(item % H);
+  const int64_t r0 = item / H, r1 = r0 + half;
+  const bool ok0 = r0 < half, ok1 = ok0 && r1 < BQ;
+  uint4 a0 = make_uint4(0, 0, 0, 0), b0 = a0, a1 = a0, b1 = a0;
+  if (ok0) {
+    a0 = *reinterpret_cast<const uint4*>(o + r0 * ldo + h * 64 + sub * 8);
+    b0 = *reinterpret_cast<const uint4*>(dout + r0 * lddo + h * 64 + sub * 8);
   }
-  acc += __shfl_xor_sync(0xffffffffu, acc, 4);
-  acc += __shfl_xor_sync(0xffffffffu, acc, 2);
-  acc += __shfl_xor_sync(0xffffffffu, acc, 1);
-  if (item < total && sub == 0) {
-    int h = (int)(item % H);
-    int64_t bq = item / H;
-    int64_t b = bq / Nq, q = bq - b * Nq;
-    delta[(b * H + h) * Nq + q] = acc;
+  if (ok1) {
+    a1 = *reinterpret_cast<const uint4*>(o + r1 * ldo + h * 64 + sub * 8);
+    b1 = *reinterpret_cast<const uint4*>(dout + r1 * lddo + h * 64 + sub * 8);
+  }
+  const Row8 x0 = unpack8(a0), y0 = unpack8(b0), x1 = unpack8(a1), y1 = unpack8(b1);
+  float acc0 = 0.f, acc1 = 0.f;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    acc0 += x0.v[j] * y0.v[j];
+    acc1 += x1.v[j] * y1.v[j];
+  }
+#pragma unroll
+  for (int m = 4; m > 0; m >>= 1) {
+    acc0 += __shfl_xor_sync(0xffffffffu, acc0, m);
+    acc1 += __shfl_xor_sync(0xffffffffu, acc1, m);
+  }
+  if (sub == 0) {
+    if (ok0) {
+      const int64_t b = r0 / Nq, q = r0 - b * Nq;
+      delta[(b * H + h) * Nq + q] = acc0;
+    }
+    if (ok1) {
+      const int64_t b = r1 / Nq, q = r1 - b * Nq;
+      delta[(b * H + h) * Nq + q] = acc1;
+    }
   }
 }
 
@@ -548,34 +623,12 @@ using namespace b200;
     if (!(cond)) return arg_error(msg); \
   } while (0)
 
-// Row kernels are instantiated per chunk count (D = NC * 256 exactly) so that the per-chunk code is
-// branch-free and all 16-byte loads of a row are in flight together; any other D <= 2048 takes the
-// predicated 8-chunk instantiation.
-#define ROW_DISPATCH(KERNEL, D, GRID, STREAM, ...)                                            \
-  do {                                                                                        \
-    if ((D) % 256 == 0) {                                                                     \
-      switch ((D) / 256) {                                                                    \
-        case 1: KERNEL<1, true><<<GRID, 128, 0, STREAM>>>(__VA_ARGS__); break;                \
-        case 2: KERNEL<2, true><<<GRID, 128, 0, STREAM>>>(__VA_ARGS__); break;                \
-        case 3: KERNEL<3, true><<<GRID, 128, 0, STREAM>>>(__VA_ARGS__); break;                \
-        case 4: KERNEL<4, true><<<GRID, 128, 0, STREAM>>>(__VA_ARGS__); break;                \
-        case 5: KERNEL<5, true><<<GRID, 128, 0, STREAM>>>(__VA_ARGS__); break;                \
-        case 6: KERNEL<6, true><<<GRID, 128, 0, STREAM>>>(__VA_ARGS__); break;                \
-        case 7: KERNEL<7, true><<<GRID, 128, 0, STREAM>>>(__VA_ARGS__); break;                \
-        default: KERNEL<8, true><<<GRID, 128, 0, STREAM>>>(__VA_ARGS__); break;               \
-      }                                                                                       \
-    } else {                                                                                  \
-      KERNEL<8, false><<<GRID, 128, 0, STREAM>>>(__VA_ARGS__);                                \
-    }                                                                                         \
+// block-per-row kernels: one 128-thread block per row, NCH = 1 (D <= 1024) or 2 (D <= 2048) chunks per thread
+#define ROWBLOCK_DISPATCH(KERNEL, D, ROWS, STREAM, ...)                              \
+  do {                                                                               \
+    if ((D) <= 1024) KERNEL<1><<<(unsigned)(ROWS), 128, 0, STREAM>>>(__VA_ARGS__);   \
+    else KERNEL<2><<<(unsigned)(ROWS), 128, 0, STREAM>>>(__VA_ARGS__);               \
   } while (0)
-
-// persistent row kernels: 4 rows per block per pass, a few blocks per SM, grid-stride over the rows
-static inline unsigned row_grid(int64_t rows) {
-  int64_t blocks = (rows + 3) / 4;
-  const int64_t cap = 148 * 6;
-  return (unsigned)(blocks < cap ? blocks : cap);
-}
-
 static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
 extern "C" int b200_norm_mod_fwd(const void* x, int64_t ldx, void* y, int64_t ldy, const void* scale,
@@ -589,7 +642,7 @@ extern "C" int b200_norm_mod_fwd(const void* x, int64_t ldx, void* y, int64_t ld
             "norm_mod_fwd: 16-byte alignment required");
   CHECK_ARG(rows_per_mod > 0, "norm_mod_fwd: rows_per_mod must be positive");
   if (rows == 0) return 0;
-  ROW_DISPATCH(norm_mod_fwd_kernel, D, row_grid(rows), (cudaStream_t)stream,
+  ROWBLOCK_DISPATCH(norm_mod_fwd_row_kernel, D, (rows + 1) / 2, (cudaStream_t)stream,
       (const bf16*)x, ldx, (bf16*)y, ldy, (const bf16*)scale, (const bf16*)shift, mod_stride, rows,
       D, rows_per_mod, eps, layernorm);
   return launch_status("norm_mod_fwd");
@@ -607,7 +660,7 @@ extern "C" int b200_norm_mod_bwd(const void* dy, int64_t lddy, const void* x, in
             "norm_mod_bwd: 16-byte alignment required");
   CHECK_ARG(rows_per_mod > 0, "norm_mod_bwd: rows_per_mod must be positive");
   if (rows == 0) return 0;
-  ROW_DISPATCH(norm_mod_bwd_kernel, D, row_grid(rows), (cudaStream_t)stream,
+  ROWBLOCK_DISPATCH(norm_mod_bwd_row_kernel, D, rows, (cudaStream_t)stream,
       (const bf16*)dy, lddy, (const bf16*)x, ldx, (const bf16*)scale, mod_stride,
       (const bf16*)dres, lddres, (bf16*)dx, lddx, rows, D, rows_per_mod, eps, layernorm);
   return launch_status("norm_mod_bwd");
@@ -631,7 +684,7 @@ extern "C" int b200_qknorm_rope_fwd(const void* xq, int64_t ldq, const void* xk,
             "qknorm_rope_fwd: 16-byte alignment required");
   int64_t total = rows_q + rows_k;
   if (total == 0) return 0;
-  ROW_DISPATCH(qknorm_rope_fwd_kernel, D, row_grid(total), (cudaStream_t)stream,
+  ROWBLOCK_DISPATCH(qknorm_rope_fwd_row_kernel, D, total, (cudaStream_t)stream,
       (const bf16*)xq, ldq, (const bf16*)xk, ldk, (const bf16*)wq, (const bf16*)wk,
       (const bf16*)cos_t, (const bf16*)sin_t, ldcs, (bf16*)oq, ldoq, (bf16*)ok, ldok, rows_q, rows_k,
       D, eps);
@@ -658,7 +711,7 @@ extern "C" int b200_qknorm_rope_bwd(const void* dq, int64_t lddq, int dq_is_f32,
             "qknorm_rope_bwd: 16-byte alignment required");
   int64_t total = rows_q + rows_k;
   if (total == 0) return 0;
-  ROW_DISPATCH(qknorm_rope_bwd_kernel, D, row_grid(total), (cudaStream_t)stream,
+  ROWBLOCK_DISPATCH(qknorm_rope_bwd_row_kernel, D, total, (cudaStream_t)stream,
       dq, lddq, dq_is_f32, dk, lddk, dk_is_f32, (const bf16*)xq, ldq, (const bf16*)xk, ldk,
       (const bf16*)wq, (const bf16*)wk, (const bf16*)cos_t, (const bf16*)sin_t, ldcs, (bf16*)oq, ldoq,
       (bf16*)ok, ldok, rows_q, rows_k, D, eps);
@@ -720,7 +773,8 @@ extern "C" int b200_rowscale(const void* x, int64_t ldx, const void* g, int64_t 
             "rowscale: 16-byte alignment required");
   int64_t total = rows * (D / 8);
   if (total == 0) return 0;
-  int blocks = (int)((total + 255) / 256 < 148 * 8 ? (total + 255) / 256 : 148 * 8);
+  const int64_t want = (total + 1023) / 1024;  // four vectors per thread
+  int blocks = (int)(want < 148 * 32 ? want : 148 * 32);
   rowscale_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>((const bf16*)x, ldx, (const bf16*)g,
                                                             gstride, (bf16*)out, ldo, rows, D / 8,
                                                             rows_per_mod);
@@ -751,7 +805,7 @@ extern "C" int b200_attn_delta(const void* o, int64_t ldo, const void* dout, int
   CHECK_ARG(o && dout && delta && B >= 0 && H > 0 && Nq >= 0, "attn_delta: bad arguments");
   CHECK_ARG(ldo % 8 == 0 && lddo % 8 == 0 && aligned16(o) && aligned16(dout),
             "attn_delta: 16-byte alignment required");
-  int64_t threads = (int64_t)B * Nq * H * 8;
+  int64_t threads = (((int64_t)B * Nq + 1) / 2) * H * 8;  // one thread per (row pair, head, 8-element slice)
   if (threads == 0) return 0;
   attn_delta_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
       (const bf16*)o, ldo, (const bf16*)dout, lddo, delta, B, H, Nq);

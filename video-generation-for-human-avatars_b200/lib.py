@@ -37,6 +37,8 @@ PROTOTYPES = {
     "b200_lerp_condition": (I, [P, P, P, I, I, I, I, F, F, I, I, P]),
     "b200_guidance_step_workspace_bytes": (L, [I]),
     "b200_guidance_step": (I, [P, P, P, I, P, I, P, P, I, L, I, I, I, I, I, P, L, P]),
+    "b200_adamw_chunk_elems": (I, []),
+    "b200_adamw_step": (I, [P, P, I, P, P, P, P]),
     "b200_rowscale": (I, [P, L, P, L, P, L, L, I, L, P]),
     "b200_colsum": (I, [P, L, P, L, I, P]),
 }

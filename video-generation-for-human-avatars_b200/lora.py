@@ -56,10 +56,18 @@ class LoraLinear(nn.Module):
         return modules.apply_linear(self, x.reshape(-1, shp[-1])).view(*shp[:-1], -1)
 
     def merge(self):
-        """W += scaling * B A  (peft merge_and_unload; torch_utils.py:66-102 exports merged weights)."""
+        """W += scaling * B A  (peft merge_and_unload; torch_utils.py:66-102 exports merged weights).
+        On the device this is one rank-r GEMM accumulating into the bf16 weight in place (residual epilogue):
+        a = scaling * B [out, r], b = A [r, in] stored [K, N]; on a CPU copy of the model (checkpoint export of an
+        off-loaded model) it is the plain matmul."""
         w = self.base_layer.weight
-        delta = self.lora_B["default"].weight.float() @ self.lora_A["default"].weight.float()
-        w.data += (delta * self.scaling["default"]).to(w.dtype)
+        A, B, s = self.lora_A["default"].weight, self.lora_B["default"].weight, self.scaling["default"]
+        if w.is_cuda and w.dtype == torch.bfloat16:
+            from . import ops
+            ops.gemm((B.detach().float() * s).to(torch.bfloat16).contiguous(), A.detach().to(torch.bfloat16).contiguous(),
+                     b_rows_are_k=True, res=w.data, out=w.data)
+        else:
+            w.data += ((B.float() @ A.float()) * s).to(w.dtype)
 
 
 class _LoraModel(nn.Module):
