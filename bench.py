@@ -227,7 +227,7 @@ def run_b200(args):
 
     torch.manual_seed(0)
     model = api.build_model(cfg, device=dev)
-    model = lora.apply_training_strategy(model, LORA_RANK, LORA_RANK)
+    model = lora.apply_training_strategy(model, LORA_RANK, LORA_RANK, train_mode=args.train_mode)
     g = torch.Generator(device="cpu").manual_seed(1)
     for n, p in model.named_parameters():
         if "lora_B" in n:
@@ -371,8 +371,10 @@ def run_b200(args):
                 "data": "synthetic",
                 "config": {"workload": desc, "tokens_per_gpu_step": B * N // (world if seq_parallel else 1),
                            "caption_tokens": N_CTX,
-                           "valid_caption_tokens": VALID_CTX, "lora_rank": LORA_RANK, "layers": cfg["num_layers"],
-                           "optimizer": "AdamW (b200 single-launch kernel) on 27.3M trainable params, inside the timed step",
+                           "valid_caption_tokens": VALID_CTX, "lora_rank": LORA_RANK if args.train_mode == "lora_audio" else 0,
+                           "layers": cfg["num_layers"],
+                           "optimizer": f"AdamW (b200 single-launch kernel) on {sum(p.numel() for _, p in named) / 1e6:.1f}M trainable "
+                                        "params, inside the timed step", "train_mode": args.train_mode,
                            "parallelism": f"sp{world} ({args.sp_mode} attn1)" if seq_parallel else f"dp{world}",
                            "launch": ("eager launches" if graphed is None else
                                       "whole micro-step replayed as one CUDA graph" if world == 1 else
@@ -415,6 +417,8 @@ def main():
     ap.add_argument("--workload", default="cfg2", choices=list(WORKLOADS))
     ap.add_argument("--layers", type=int, default=0, help="debug only: fewer blocks (marks the line INVALID)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--train-mode", default="lora_audio", choices=["lora_audio", "full"],
+                    help="training.py:42-91; 'full' (0.95 B trainable parameters) is not the headline workload")
     ap.add_argument("--sp-mode", default="gather", choices=["ring", "gather"],
                     help="cfg5 under torchrun: K/V ring hops, or one all-gather + single attention launch per layer")
     ap.add_argument("--no-graph", action="store_true", help="launch the step kernel by kernel instead of replaying a CUDA graph")

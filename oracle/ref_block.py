@@ -384,9 +384,12 @@ def param_shapes(cfg: dict, lora_rank: int = 0) -> Dict[str, Tuple[int, ...]]:
     return s
 
 
-def is_trainable(name: str) -> bool:
-    """lora_audio strategy (training.py:69-73)."""
-    return ("lora_" in name) or ("caption_projection" in name)
+def is_trainable(name: str, train_mode: str = "lora_audio") -> bool:
+    """lora_audio strategy (training.py:69-73); any other mode: the key list of training.py:75-91."""
+    if train_mode == "lora_audio":
+        return ("lora_" in name) or ("caption_projection" in name)
+    return any(k in name for k in ("proj_out", "scale_shift_table", "adaln_single", "caption_projection", "attn",
+                                   "attn2"))
 
 
 def init_params(cfg: dict, lora_rank: int = 32, seed: int = 0, dtype=torch.float32,

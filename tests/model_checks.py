@@ -30,12 +30,14 @@ def maxabs(a, b):
     return float((a.float() - b.float()).abs().max())
 
 
-def build_b200_model(cfg, P, lora_rank, device="cuda"):
+def build_b200_model(cfg, P, lora_rank, device="cuda", train_mode="lora_audio"):
     from b200_ltx import api, lora
     full = dict(api.LTXV_2B_CONFIG)
     full.update(cfg)
     model = api.build_model(full, device=device)
-    if lora_rank:
+    if train_mode != "lora_audio":
+        model = lora.apply_training_strategy(model, 0, 0, train_mode=train_mode)
+    elif lora_rank:
         model = lora.apply_training_strategy(model, lora_rank, lora_rank)
     sd = model.state_dict()
     mapped = {}
@@ -46,11 +48,11 @@ def build_b200_model(cfg, P, lora_rank, device="cuda"):
     return model
 
 
-def oracle_loss_grads(P, cfg, batch, t, dtype, device):
+def oracle_loss_grads(P, cfg, batch, t, dtype, device, train_mode="lora_audio"):
     Pd = {}
     for k, v in P.items():
         w = v.to(device=device, dtype=torch.float32 if ("lora_" in k or dtype == torch.float32) else dtype)
-        Pd[k] = w.clone().requires_grad_(rb.is_trainable(k))
+        Pd[k] = w.clone().requires_grad_(rb.is_trainable(k, train_mode))
     b = {k: v.to(device) for k, v in batch.items()}
     loss, out = rb.train_step_loss(Pd, cfg, b["latents"].to(dtype), b["ref_image_latents"].to(dtype),
                                    b["pose_latents"].to(dtype), b["prompt_embeds"].to(dtype), b["prompt_mask"],
@@ -93,9 +95,10 @@ def run_parity(cfg, case, verbose=True):
         batch[k] = batch[k].to(torch.bfloat16).float()
     P = {k: (v if "lora_" in k else v.to(torch.bfloat16).float()) for k, v in P.items()}
     t = torch.tensor(case["t"])
-    l32, o32, g32 = oracle_loss_grads(P, cfg, batch, t, torch.float32, dev)
-    l16, o16, g16 = oracle_loss_grads(P, cfg, batch, t, torch.bfloat16, dev)
-    model = build_b200_model(cfg, P, case["lora_rank"], dev)
+    mode = case.get("train_mode", "lora_audio")
+    l32, o32, g32 = oracle_loss_grads(P, cfg, batch, t, torch.float32, dev, mode)
+    l16, o16, g16 = oracle_loss_grads(P, cfg, batch, t, torch.bfloat16, dev, mode)
+    model = build_b200_model(cfg, P, case["lora_rank"], dev, mode)
     out_holder = {}
     root = model.base_model.model if hasattr(model, "base_model") else model
     hook = root.register_forward_hook(lambda m, a, o: out_holder.__setitem__("out", o.sample.detach()))

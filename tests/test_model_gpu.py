@@ -231,3 +231,20 @@ def test_lora_merge_matches_matmul():
     layer.merge()
     assert mc.rel(base.weight.float(), want) < 3e-3
     assert mc.rel(base.weight.float() - w0, want - w0) < 0.25   # the update itself (bf16 rounding of W + dW dominates)
+
+
+@pytest.mark.gpu
+def test_full_train_mode_gradients_vs_oracle():
+    """train_mode='full' (training.py:75-91: proj_out, scale_shift_tables, adaln_single, caption_projection and every
+    attention parameter train; no adapters): output, loss and ALL those gradients -- base weights and biases, qk-norm
+    weights, the per-block and final scale/shift/gate tables, the timestep MLP -- against the fp32 oracle, with the
+    same two-sided bf16 tolerance as the LoRA mode."""
+    cfg = dict(rb.LTXV_2B, num_layers=2, num_attention_heads=4, cross_attention_dim=256, caption_channels=64)
+    case = dict(b=2, f=3, h=4, w=8, n_ctx=24, valid_ctx=15, lora_rank=0, seed_w=3, seed_x=77, t=[0.35, 0.8],
+                train_mode="full")
+    res = mc.run_parity(cfg, case)
+    names = " ".join(res)
+    for needle in ("scale_shift_table", "adaln_single.linear.weight", "attn1.q_norm.weight", "attn2.to_k.bias",
+                   "proj_out.weight", "caption_projection.linear_1.weight"):
+        assert needle in names, needle
+    assert "ff.net" not in names and "patchify_proj" not in names

@@ -121,10 +121,17 @@ def get_peft_model(model, config: LoraConfig, **kwargs):
 
 
 def apply_training_strategy(model, lora_rank: int, lora_alpha: int, train_mode: str = "lora_audio"):
-    """training.py:42-74: LoRA on attn2.{to_q,to_k,to_v,to_out.0} of every block; LoRA +
-    caption_projection trainable, everything else frozen."""
+    """training.py:42-91.  "lora_audio": LoRA on attn2.{to_q,to_k,to_v,to_out.0} of every block; LoRA +
+    caption_projection trainable, everything else frozen.  Any other mode (the reference's "full"): no adapters;
+    proj_out, every scale_shift_table, adaln_single, caption_projection and all attention parameters train (the
+    feed-forwards and patchify_proj stay frozen).  In that mode the AdaLN modulate, the gates and the qk-norm affine
+    run un-fused so autograd sees them (ops.norm_mod / gate_residual, modules.attention_forward)."""
     if train_mode != "lora_audio":
-        raise NotImplementedError("train_mode='full' is outside the round-1 hot-path scope (SURVEY 8f-3)")
+        # training.py:75-91: no adapters; every parameter whose name contains one of these keys trains
+        keys = ("proj_out", "scale_shift_table", "adaln_single", "caption_projection", "attn", "attn2")
+        for n, p in model.named_parameters():
+            p.requires_grad = any(k in n for k in keys)
+        return model
     targets = []
     for i in range(len(model.transformer_blocks)):
         targets += [f"transformer_blocks.{i}.attn2.to_q", f"transformer_blocks.{i}.attn2.to_k",

@@ -168,6 +168,10 @@ def attention_forward(attn, hidden_states, freqs_cis=None, encoder_hidden_states
     scale = float(attn.scale)
 
     sp = attn.__dict__.get("_b200_sp") if is_self else None
+    # a trainable gate cannot ride in the GEMM epilogue (its gradient needs the un-gated output): un-fused below
+    gate_out, res_out = gate, res
+    if ops.wants_grad(gate):
+        gate, res = None, None
     fast = (is_self and skip_layer_mask is None and all(_frozen_plain(m) for m in (attn.to_q, attn.to_k, attn.to_v))
             and linear_parts(attn.to_out[0])[2] is None and not linear_parts(attn.to_out[0])[0].requires_grad
             and not wqn.requires_grad and not wkn.requires_grad)
@@ -176,6 +180,8 @@ def attention_forward(attn, hidden_states, freqs_cis=None, encoder_hidden_states
         Wqkv, bqkv = _cached_wqkv(attn)
         y = ops.SelfAttnFn.apply(x2d, Wqkv, bqkv, wqn, wkn, cos, sin, Wo, bo, gate, rows_per_gate, res, kb, B, H,
                                  Nq, scale, sp)
+        if gate is not gate_out:
+            y = ops.gate_residual(y, gate_out, rows_per_gate, res_out)
         return y.view(B, Nq, -1)
     if sp is not None:
         raise B200Error("sequence-sharded attn1 needs frozen, adapter-free attn1 projections and no skip-layer mask")
@@ -187,12 +193,24 @@ def attention_forward(attn, hidden_states, freqs_cis=None, encoder_hidden_states
     else:
         k_pre = apply_linear(attn.to_k, src2d)
         v = apply_linear(attn.to_v, src2d)
-    o = ops.AttnCoreFn.apply(q_pre, k_pre, v, wqn, wkn, cos, sin, kb, B, H, Nq, Nk, scale)
+    if ops.wants_grad(wqn, wkn):
+        # trainable qk-norm weights (train_mode='full'): RMSNorm stays a kernel, the affine weight and RoPE run as
+        # torch ops (attention.py:996-1012, 917-932) so autograd sees them; then the attention core alone
+        qn = ops.NormModFn.apply(q_pre if q_pre.stride(1) == 1 else q_pre.contiguous(), None, None, B * Nq, 1e-5, False)
+        kn = ops.NormModFn.apply(k_pre if k_pre.stride(1) == 1 else k_pre.contiguous(), None, None, B * Nk, 1e-5, False)
+        qn, kn = qn * wqn, kn * wkn
+        if use_rope:
+            qn, kn = ops.rope_torch(qn, cos, sin), ops.rope_torch(kn, cos, sin)
+        o = ops.FlashAttnFn.apply(qn, kn, v, kb, B, H, Nq, Nk, scale)
+    else:
+        o = ops.AttnCoreFn.apply(q_pre, k_pre, v, wqn, wkn, cos, sin, kb, B, H, Nq, Nk, scale)
     if skip_layer_mask is not None and strat in (SkipLayerStrategy.AttentionSkip, SkipLayerStrategy.AttentionValues):
         m = skip_layer_mask.reshape(B, 1, 1).to(o.dtype)
         other = hidden_states if strat == SkipLayerStrategy.AttentionSkip else v.view(B, Nk, D)
         o = (o.view(B, Nq, D) * m + other * (1.0 - m)).reshape(B * Nq, D)
     y = apply_linear(attn.to_out[0], o, gate, rows_per_gate, res)
+    if gate is not gate_out:
+        y = ops.gate_residual(y, gate_out, rows_per_gate, res_out)
     return y.view(B, Nq, -1)
 
 
@@ -217,7 +235,7 @@ def block_forward(block, hidden_states, freqs_cis=None, attention_mask=None, enc
     strat = _strategy_name(skip_layer_strategy)
 
     # the residual input leaves the norm node as its own output: its gradient is added inside norm_mod_bwd
-    h, x_res = ops.NormModResFn.apply(x2d, scale_msa, shift_msa, rpm, 1e-6, False)
+    h, x_res = ops.norm_mod(x2d, scale_msa, shift_msa, rpm, 1e-6, False, with_res=True)
     x1 = attention_forward(block.attn1, h.view(B, N, D), freqs_cis=freqs_cis,
                            encoder_hidden_states=encoder_hidden_states if block.only_cross_attention else None,
                            attention_mask=attention_mask, skip_layer_mask=skip_layer_mask,
@@ -229,12 +247,16 @@ def block_forward(block, hidden_states, freqs_cis=None, attention_mask=None, enc
         x2_2d = x2.reshape(B * N, D)
     else:
         x2_2d = x1_2d
-    h2, x2_res = ops.NormModResFn.apply(x2_2d, scale_mlp, shift_mlp, rpm, 1e-6, False)
+    h2, x2_res = ops.norm_mod(x2_2d, scale_mlp, shift_mlp, rpm, 1e-6, False, with_res=True)
     W1, b1, l1 = linear_parts(block.ff.net[0].proj)
     W2, b2, l2 = linear_parts(block.ff.net[2])
     if l1 is not None or l2 is not None:
         raise B200Error("LoRA on the feed-forward is not built (reference targets attn2 only, training.py:51-60)")
-    out = ops.FeedForwardFn.apply(h2, W1, b1, W2, b2, gate_mlp, rpm, x2_res).view(B, N, D)
+    if ops.wants_grad(gate_mlp):
+        out = ops.gate_residual(ops.FeedForwardFn.apply(h2, W1, b1, W2, b2, None, 0, None), gate_mlp, rpm, x2_res)
+        out = out.view(B, N, D)
+    else:
+        out = ops.FeedForwardFn.apply(h2, W1, b1, W2, b2, gate_mlp, rpm, x2_res).view(B, N, D)
     if skip_layer_mask is not None and strat == SkipLayerStrategy.TransformerBlock:
         m = skip_layer_mask.view(-1, 1, 1).to(out.dtype)
         out = out * m + hidden_states * (1.0 - m)
@@ -367,7 +389,7 @@ def transformer_forward(model, hidden_states, indices_grid, ref_image_hidden_sta
 
     T = emb.shape[1]
     ss = (model.scale_shift_table[None, None] + emb[:, :, None]).reshape(B * T, 2 * D)
-    hn = ops.NormModFn.apply(h.reshape(B * N, D), ss[:, D:], ss[:, :D], N // T, 1e-6, True)
+    hn, _ = ops.norm_mod(h.reshape(B * N, D), ss[:, D:], ss[:, :D], N // T, 1e-6, True, with_res=False)
     out = apply_linear(model.proj_out, hn).view(B, N, -1)
     if not return_dict:
         return (out,)

@@ -525,8 +525,8 @@ class NormModFn(torch.autograd.Function):
         x, scale = ctx.saved_tensors
         rpm, eps, ln = ctx.meta
         if ctx.needs_input_grad[1] or ctx.needs_input_grad[2]:
-            raise _lib.B200Error("NormModFn: gradients of the AdaLN scale/shift are not built "
-                                 "(train_mode='full' is outside the round-1 scope)")
+            raise _lib.B200Error("NormModFn: the fused kernel treats the AdaLN scale/shift as constants; "
+                                 "call ops.norm_mod(), which un-fuses the modulate when they are trainable")
         dy = dy if dy.stride(1) == 1 else dy.contiguous()
         return norm_mod_bwd(dy, x, scale, rpm, eps, ln), None, None, None, None, None
 
@@ -547,8 +547,8 @@ class NormModResFn(torch.autograd.Function):
         x, scale = ctx.saved_tensors
         rpm, eps, ln = ctx.meta
         if ctx.needs_input_grad[1] or ctx.needs_input_grad[2]:
-            raise _lib.B200Error("NormModResFn: gradients of the AdaLN scale/shift are not built "
-                                 "(train_mode='full' is outside the round-1 scope)")
+            raise _lib.B200Error("NormModResFn: the fused kernel treats the AdaLN scale/shift as constants; "
+                                 "call ops.norm_mod(), which un-fuses the modulate when they are trainable")
         if dy is None:
             return dres, None, None, None, None, None
         dy = dy if dy.stride(1) == 1 else dy.contiguous()
@@ -580,8 +580,8 @@ class AttnCoreFn(torch.autograd.Function):
         q_pre, k_pre, v, wq, wk, cos, sin, key_bias, qk, o, lse = ctx.saved_tensors
         B, H, Nq, Nk, scale = ctx.meta
         if ctx.needs_input_grad[3] or ctx.needs_input_grad[4]:
-            raise _lib.B200Error("AttnCoreFn: q_norm/k_norm weight gradients are not built "
-                                 "(train_mode='full' is outside the round-1 scope)")
+            raise _lib.B200Error("AttnCoreFn: the fused qk-norm kernel treats the norm weights as constants; "
+                                 "modules.attention_forward un-fuses norm + RoPE when they are trainable")
         D = H * 64
         q, k = qk[:B * Nq], qk[B * Nq:]
         do = do if do.stride(1) == 1 else do.contiguous()
@@ -592,6 +592,70 @@ class AttnCoreFn(torch.autograd.Function):
         dk_pre = torch.empty((B * Nk, D), device=do.device, dtype=BF16)
         qknorm_rope_bwd(dq32, dk, q_pre, k_pre, wq, wk, cos, sin, dq_pre, dk_pre)
         return dq_pre, dk_pre, dv, None, None, None, None, None, None, None, None, None, None
+
+
+class FlashAttnFn(torch.autograd.Function):
+    """o = softmax(q k^T * scale + key_bias) v on already normalised / rotated token-major q, k (the attention core
+    alone; used when the qk-norm weights are trainable and the norm + RoPE run as autograd-visible ops)."""
+
+    @staticmethod
+    def forward(ctx, q, k, v, key_bias, B, H, Nq, Nk, scale):
+        q, k, v = (t if t.stride(1) == 1 else t.contiguous() for t in (q, k, v))
+        o, lse = fa_fwd(q, k, v, B, H, Nq, Nk, key_bias, scale)
+        ctx.save_for_backward(q, k, v, key_bias, o, lse)
+        ctx.meta = (B, H, Nq, Nk, scale)
+        return o
+
+    @staticmethod
+    def backward(ctx, do):
+        q, k, v, key_bias, o, lse = ctx.saved_tensors
+        B, H, Nq, Nk, scale = ctx.meta
+        do = do if do.stride(1) == 1 else do.contiguous()
+        dk = torch.empty((B * Nk, H * 64), device=do.device, dtype=BF16)
+        dv = torch.empty((B * Nk, H * 64), device=do.device, dtype=BF16)
+        dq32 = fa_bwd(q, k, v, o, do, lse, B, H, Nq, Nk, dk, dv, key_bias, scale)
+        return dq32.to(BF16), dk, dv, None, None, None, None, None, None
+
+
+def wants_grad(*tensors) -> bool:
+    """True when autograd is recording and one of the tensors needs a gradient: the fused kernels treat AdaLN
+    modulations, gates and qk-norm weights as constants, so such a piece then runs un-fused (train_mode='full')."""
+    return torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in tensors)
+
+
+def norm_mod(x, scale, shift, rows_per_mod, eps, layernorm, with_res: bool):
+    """norm(x) * (1 + scale) + shift (+ the residual view of x).  Frozen modulation: one fused kernel with the
+    residual gradient folded into its backward.  Trainable modulation (train_mode='full', training.py:75-91): the
+    normalisation stays a kernel, the modulate runs as torch ops so autograd reduces d(scale) / d(shift)."""
+    if not wants_grad(scale, shift):
+        if with_res:
+            return NormModResFn.apply(x, scale, shift, rows_per_mod, eps, layernorm)
+        return NormModFn.apply(x, scale, shift, rows_per_mod, eps, layernorm), None
+    rows, D = x.shape
+    xhat = NormModFn.apply(x, None, None, rows, eps, layernorm)
+    g = rows // rows_per_mod
+    y = xhat.view(g, rows_per_mod, D)
+    if scale is not None:
+        y = y * (1 + scale.reshape(g, 1, D))
+    if shift is not None:
+        y = y + shift.reshape(g, 1, D)
+    return y.reshape(rows, D), (x if with_res else None)
+
+
+def gate_residual(u, gate, rows_per_gate, res):
+    """res + gate * u as torch ops (the form autograd needs when the gate is trainable)."""
+    rows, D = u.shape
+    if gate is not None:
+        g = rows // rows_per_gate
+        u = (u.view(g, rows_per_gate, D) * gate.reshape(g, 1, D)).reshape(rows, D)
+    return u + res if res is not None else u
+
+
+def rope_torch(x, cos, sin):
+    """apply_rotary_emb (attention.py:917-932): x cos + rot(x) sin with rot pairs (-x2, x1); bf16 op by op."""
+    xr = x.reshape(x.shape[0], -1, 2)
+    rot = torch.stack((-xr[..., 1], xr[..., 0]), dim=-1).reshape(x.shape)
+    return x * cos + rot * sin
 
 
 class CtxKVFn(torch.autograd.Function):
