@@ -148,3 +148,78 @@ def test_reference_train_step_rng_path(golden_dir):
     ol, _ = rb.train_step_loss(P, g["cfg"], batch["latents"], batch["ref_image_latents"], batch["pose_latents"],
                                batch["prompt_embeds"], batch["prompt_mask"], t, noise)
     assert torch.equal(loss.detach(), ol.detach())
+
+
+def _sampling_inputs():
+    cfg = dict(rb.LTXV_2B, num_layers=2, num_attention_heads=4, cross_attention_dim=256, caption_channels=64)
+    P = rb.init_params(cfg, 0, seed=5)
+    b = rb.synthetic_batch(cfg, 2, 2, 4, 4, 24, 21, 15)
+    tokens, coords = rb.patchify(b["noise"].transpose(1, 2).reshape(2, -1, 2, 4, 4))
+    fc = coords.float()
+    fc[:, 0] = fc[:, 0] * (1.0 / 25)
+    enc, msk = b["prompt_embeds"].expand(2, -1, -1), b["prompt_mask"].expand(2, -1)
+    return cfg, P, tokens, fc, b["ref_image_latents"], b["pose_latents"], enc, msk
+
+
+def test_sampling_loop_restatement_properties():
+    """oracle/ref_sampling.py restates the pipeline's guided denoising loop (pipeline_ltx_video.py:1089-1288); the
+    pipeline itself cannot be imported here, so the restatement is pinned through properties the reference's code has
+    by construction: (1) one condition == the plain Euler loop over the pinned forward and scheduler; (2) classifier-
+    free guidance with the negative prompt equal to the positive one is the identity on the prediction, with and
+    without the CFG* projection; (3) hard-conditioned tokens (mask 1.0) never move and soft ones start moving only
+    once t has dropped to 1 - mask; (4) rescaling_scale == 1 switches the std rescale off (pipeline :1093)."""
+    import ref_sampling as rs
+    cfg, P, tokens, fc, ref, pose, enc, msk = _sampling_inputs()
+    grid = rb.uniform_timesteps(4)
+    # (1)
+    x = tokens.clone()
+    with torch.no_grad():
+        for i in range(4):
+            xin = x if i == 0 else x.clone()          # bf16-model aliasing: only the first step is in place
+            v = rb.transformer_forward(P, cfg, xin, fc, ref, pose, enc, grid[i].expand(2)[:, None], msk)
+            x = rb.rf_step(grid, v, grid[i], x)
+    got = rs.denoise_loop(P, cfg, tokens.clone(), fc, ref, pose, enc, msk, grid)
+    torch.testing.assert_close(got, x, rtol=1e-5, atol=1e-6)
+    # (2): three-condition runs never alias the latents, so compare with the un-aliased single-condition loop
+    plain = rs.denoise_loop(P, cfg, tokens.clone(), fc, ref, pose, enc, msk, grid, guidance_scale=1.0,
+                            stg_scale=1e-9, skip_block_list=None)   # stg > 0 without skip list: perturbed == text
+    for star in (False, True):
+        same = rs.denoise_loop(P, cfg, tokens.clone(), fc, ref, pose, enc, msk, grid, enc, msk, guidance_scale=4.0,
+                               stg_scale=1e-9, cfg_star_rescale=star)
+        torch.testing.assert_close(same, plain, rtol=2e-4, atol=2e-5)
+    # (3)
+    cm = torch.zeros(2, tokens.shape[1])
+    cm[:, :16] = 1.0
+    cm[0, 16:20] = 0.6
+    out = rs.denoise_loop(P, cfg, tokens.clone(), fc, ref, pose, enc, msk, grid, guidance_scale=3.0, stg_scale=1.0,
+                          skip_block_list=[1], skip_layer_strategy=rb.STG_ATTENTION_VALUES, conditioning_mask=cm)
+    assert torch.equal(out[:, :16], tokens[:, :16])
+    one = rs.denoise_loop(P, cfg, tokens.clone(), fc, ref, pose, enc, msk, grid,
+                          guidance_scale=[3.0, 3.0, 1.0, 1.0], stg_scale=[1.0, 1.0, 0.0, 0.0], skip_block_list=[1],
+                          skip_layer_strategy=rb.STG_ATTENTION_VALUES, conditioning_mask=cm)
+    assert torch.equal(one[:, :16], tokens[:, :16]) and not torch.equal(one[0, 16:20], tokens[0, 16:20])
+    # soft tokens (noise level 0.4) are still frozen after the first two steps (t = 1.0, 0.75 > 0.4)
+    two = rs.denoise_loop(P, cfg, tokens.clone(), fc, ref, pose, enc, msk, grid, conditioning_mask=cm)
+    first = []
+    x2 = tokens.clone()
+    with torch.no_grad():
+        for i in range(2):
+            cur = torch.min(grid[i].expand(2)[:, None], 1.0 - cm)
+            v = rb.transformer_forward(P, cfg, x2 if i == 0 else x2.clone(), fc, ref, pose, enc, cur, msk)
+            den = rb.rf_step(grid, v, cur[:1], x2)
+            x2 = torch.where((grid[i] - 1e-6 < (1.0 - cm)).unsqueeze(-1), den, x2)
+            first.append(x2[0, 16:20].clone())
+    # the in-place conditioning lerp of step 0 touches every token; after that the soft tokens must not change
+    assert torch.equal(first[0], first[1])
+    assert two.shape == tokens.shape
+    # (4)
+    a = rs.denoise_loop(P, cfg, tokens.clone(), fc, ref, pose, enc, msk, grid, stg_scale=1.0, rescaling_scale=1.0,
+                        skip_block_list=[0], skip_layer_strategy=rb.STG_ATTENTION_SKIP)
+    v3 = torch.randn(6, 5, 8)
+    comb = rs.guidance_combine(v3, 2, 3, True, True, 3.0, 1.5, 1.0, False)
+    want = v3[:2] + 3.0 * (v3[2:4] - v3[:2]) + 1.5 * (v3[2:4] - v3[4:])
+    torch.testing.assert_close(comb, want)
+    resc = rs.guidance_combine(v3, 2, 3, True, True, 3.0, 1.5, 0.7, False)
+    f = v3[2:4].reshape(2, -1).std(dim=1) / want.reshape(2, -1).std(dim=1)
+    torch.testing.assert_close(resc, want * (0.7 * f + 0.3).view(2, 1, 1))
+    assert a.shape == tokens.shape
