@@ -296,9 +296,16 @@ def run_b200(args):
 
     resident = {k: v.to(dev) for k, v in host.items()}
     if args.profile_steps:
-        for _ in range(2 + args.profile_steps):
+        for _ in range(2):
             step(resident)
         torch.cuda.synchronize()
+        # ncu --profile-from-start off sees exactly these steps (cudaProfilerStart/Stop is process-wide: the backward
+        # kernels are launched from the autograd engine's thread, which a thread-scoped NVTX range would miss)
+        torch.cuda.profiler.start()
+        for _ in range(args.profile_steps):
+            step(resident)
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
         return
 
     # warm-up, with every kernel family timed to find the dominant one
