@@ -349,7 +349,17 @@ def transformer_forward(model, hidden_states, indices_grid, ref_image_hidden_sta
     if mult:
         timestep = mult * timestep
     cfg_theta = model.positional_embedding_theta
-    freqs = rope_table(indices_grid, D, cfg_theta, model.positional_embedding_max_pos)
+    # the table depends only on the coordinates: a caller that passes the SAME tensor again (the sampler's 40 steps)
+    # gets the cached bf16 cos / sin instead of ~10 element-wise launches over [B, N, D] fp32
+    rkey = (indices_grid.data_ptr(), indices_grid._version, tuple(indices_grid.shape), indices_grid.dtype, D)
+    rcache = model.__dict__.get("_b200_rope")
+    if rcache is not None and rcache[0] == rkey and not torch.cuda.is_current_stream_capturing():
+        freqs = rcache[1]
+    else:
+        freqs = rope_table(indices_grid, D, cfg_theta, model.positional_embedding_max_pos)
+        if not torch.cuda.is_current_stream_capturing():
+            # (indices_grid itself is kept alive so that its address cannot be reused by another tensor)
+            model.__dict__["_b200_rope"] = (rkey, freqs, indices_grid)
     t6, emb = adaln_single_forward(model.adaln_single, timestep.flatten())
     t6 = t6.view(B, -1, t6.shape[-1])
     emb = emb.view(B, -1, emb.shape[-1])
