@@ -58,9 +58,9 @@ def _require_bf16(t: torch.Tensor, what: str):
                         "path has no fp32 / CPU fallback")
 
 
-def apply_linear(mod, x2d, gate=None, rows_per_gate=0, res=None):
+def apply_linear(mod, x2d, gate=None, rows_per_gate=0, res=None, join=None, join_role=None):
     W, b, lora = linear_parts(mod)
-    return ops.linear(x2d, W, b, lora, gate, rows_per_gate, res)
+    return ops.linear(x2d, W, b, lora, gate, rows_per_gate, res, join, join_role)
 
 
 def _frozen_plain(mod) -> bool:
@@ -186,7 +186,13 @@ def attention_forward(attn, hidden_states, freqs_cis=None, encoder_hidden_states
     if sp is not None:
         raise B200Error("sequence-sharded attn1 needs frozen, adapter-free attn1 projections and no skip-layer mask")
 
-    q_pre = apply_linear(attn.to_q, x2d)
+    # attn2 of a block is y = attn(x) + x with x entering at to_q and at the residual of to_out: let the two gradients
+    # of x meet in to_q's dgrad epilogue (ops.GradJoin) instead of in an autograd add
+    join = None
+    if (not is_self and res is not None and gate is None and torch.is_grad_enabled() and x2d.requires_grad
+            and res.data_ptr() == x2d.data_ptr() and res.shape == x2d.shape and res.stride() == x2d.stride()):
+        join = ops.GradJoin()
+    q_pre = apply_linear(attn.to_q, x2d, join=join, join_role="recv")
     pre = attn.__dict__.get("_b200_kv") if not is_self else None
     if pre is not None and pre[0] is encoder_hidden_states:
         k_pre, v = pre[1], pre[2]  # projected once for all blocks by transformer_forward (ops.CtxKVFn)
@@ -208,7 +214,7 @@ def attention_forward(attn, hidden_states, freqs_cis=None, encoder_hidden_states
         m = skip_layer_mask.reshape(B, 1, 1).to(o.dtype)
         other = hidden_states if strat == SkipLayerStrategy.AttentionSkip else v.view(B, Nk, D)
         o = (o.view(B, Nq, D) * m + other * (1.0 - m)).reshape(B * Nq, D)
-    y = apply_linear(attn.to_out[0], o, gate, rows_per_gate, res)
+    y = apply_linear(attn.to_out[0], o, gate, rows_per_gate, res, join=join, join_role="send")
     if gate is not gate_out:
         y = ops.gate_residual(y, gate_out, rows_per_gate, res_out)
     return y.view(B, Nq, -1)

@@ -424,6 +424,17 @@ def stage_lora(A: torch.Tensor, B: torch.Tensor, scaling: float) -> Tuple[torch.
 # ---------------------------------------------------------------------------------------------
 # autograd Functions
 # ---------------------------------------------------------------------------------------------
+class GradJoin:
+    """Side channel for `y = f(x) + x` when f starts and ends in a LinearFn (attn2: to_q ... to_out with the residual
+    in its epilogue).  The closing node ("send") parks the residual-branch gradient here instead of returning it, the
+    opening node ("recv", which always runs later in the backward) adds it in the epilogue of its dgrad GEMM -- the two
+    gradients of x meet inside a GEMM instead of in an autograd add kernel (55 launches of 25 MB per step)."""
+    __slots__ = ("grad",)
+
+    def __init__(self):
+        self.grad = None
+
+
 class LinearFn(torch.autograd.Function):
     """y = gate * (x W^T + b + s (x A^T) B^T) + res    (every piece after x W^T optional).
 
@@ -433,7 +444,7 @@ class LinearFn(torch.autograd.Function):
     the [K,M]-layout A operand."""
 
     @staticmethod
-    def forward(ctx, x, W, b, A, B, scaling, gate, rows_per_gate, res):
+    def forward(ctx, x, W, b, A, B, scaling, gate, rows_per_gate, res, join=None, join_role=None):
         has_lora = A is not None
         t = a_pad = b_pad = None
         if has_lora:
@@ -443,6 +454,7 @@ class LinearFn(torch.autograd.Function):
         ctx.save_for_backward(x, W, t, a_pad, b_pad, gate)
         ctx.meta = (has_lora, scaling, rows_per_gate, A.shape[0] if has_lora else 0,
                     b is not None, res is not None)
+        ctx.join = (join, join_role)
         return y
 
     @staticmethod
@@ -456,8 +468,12 @@ class LinearFn(torch.autograd.Function):
         dt = None
         if has_lora and (need[0] or need[3]):
             dt = gemm(g, b_pad, b_rows_are_k=True, block_n=64)          # [M,64] = g (sB)
+        join, role = ctx.join
         if need[0]:
-            dx = gemm(g, W, b_rows_are_k=True, a2=dt, b2=a_pad if has_lora else None)
+            extra = None
+            if join is not None and role == "recv":
+                extra, join.grad = join.grad, None      # the residual branch's gradient of x, parked by the sender
+            dx = gemm(g, W, b_rows_are_k=True, a2=dt, b2=a_pad if has_lora else None, res=extra)
         # the rank-r column views make the GEMMs write exactly [r, K] / [N, r] tensors: autograd can take them as
         # .grad without the copy it makes for a slice of a padded buffer
         if has_lora and need[3]:
@@ -470,7 +486,9 @@ class LinearFn(torch.autograd.Function):
         if has_bias and need[2]:
             db = colsum(g).to(BF16)
         dres = dy if (has_res and need[8]) else None
-        return dx, dW, db, dA, dB, None, None, None, dres
+        if dres is not None and join is not None and role == "send":
+            join.grad, dres = dres, None                # delivered through the receiving node's dgrad epilogue
+        return dx, dW, db, dA, dB, None, None, None, dres, None, None
 
 
 class FeedForwardFn(torch.autograd.Function):
@@ -729,9 +747,9 @@ class CtxKVFn(torch.autograd.Function):
         return (dx, None, None, None, None, None) + dAs + dBs
 
 
-def linear(x, W, b=None, lora=None, gate=None, rows_per_gate=0, res=None):
+def linear(x, W, b=None, lora=None, gate=None, rows_per_gate=0, res=None, join=None, join_role=None):
     A, B, s = lora if lora is not None else (None, None, 1.0)
-    return LinearFn.apply(x, W, b, A, B, s, gate, rows_per_gate, res)
+    return LinearFn.apply(x, W, b, A, B, s, gate, rows_per_gate, res, join, join_role)
 
 
 class SelfAttnFn(torch.autograd.Function):
