@@ -334,7 +334,7 @@ def run_b200(args):
     if use_graph:
         # the whole micro-step (zero grads .. optimizer update, DP all-reduce included) as ONE CUDA graph
         graphed = train.GraphedTrainStep(model, opt, sched, patch, Cfg, prompt, mask, resident, bucketer=bucketer,
-                                         device=dev)
+                                         device=dev, side_work=not args.no_side_stream)
         launches = graphed.launches
 
     # timed region 1: device-resident inputs
@@ -428,6 +428,8 @@ def main():
                     help="training.py:42-91; 'full' (0.95 B trainable parameters) is not the headline workload")
     ap.add_argument("--sp-mode", default="gather", choices=["ring", "gather"],
                     help="cfg5 under torchrun: K/V ring hops, or one all-gather + single attention launch per layer")
+    ap.add_argument("--no-side-stream", action="store_true",
+                    help="captured step: keep the LoRA weight-gradient GEMMs on the main stream (A/B switch)")
     ap.add_argument("--no-graph", action="store_true", help="launch the step kernel by kernel instead of replaying a CUDA graph")
     ap.add_argument("--profile-steps", type=int, default=0,
                     help="ncu helper: run this many eager steps after 2 warm-up steps and exit (no JSON line)")

@@ -424,6 +424,39 @@ def stage_lora(A: torch.Tensor, B: torch.Tensor, scaling: float) -> Tuple[torch.
 # ---------------------------------------------------------------------------------------------
 # autograd Functions
 # ---------------------------------------------------------------------------------------------
+# A low-priority stream for work whose result only the optimizer reads (the rank-r LoRA weight gradients: 2 launches of
+# 16-144 CTAs per adapted linear, ~1.9 ms per step).  When set (train.GraphedTrainStep sets it for the capture), that
+# work forks from the main stream and runs in the SMs the big persistent kernels leave idle (tail waves, the gaps
+# between kernels); the caller joins the stream before the optimizer update.  None: everything stays on one stream.
+side_stream = None
+
+
+class _OnSideStream:
+    """with _OnSideStream(*inputs): ... -- runs the body on `side_stream` (after everything queued so far on the
+    current stream) and tells the caching allocator that `inputs` are still in use there."""
+
+    def __init__(self, *inputs):
+        self.inputs = inputs
+        self.ctx = None
+
+    def __enter__(self):
+        s = side_stream
+        if s is None:
+            return self
+        s.wait_stream(torch.cuda.current_stream())
+        for t in self.inputs:
+            if t is not None:
+                t.record_stream(s)
+        self.ctx = torch.cuda.stream(s)
+        self.ctx.__enter__()
+        return self
+
+    def __exit__(self, *exc):
+        if self.ctx is not None:
+            self.ctx.__exit__(*exc)
+        return False
+
+
 class GradJoin:
     """Side channel for `y = f(x) + x` when f starts and ends in a LinearFn (attn2: to_q ... to_out with the residual
     in its epilogue).  The closing node ("send") parks the residual-branch gradient here instead of returning it, the
@@ -476,11 +509,14 @@ class LinearFn(torch.autograd.Function):
             dx = gemm(g, W, b_rows_are_k=True, a2=dt, b2=a_pad if has_lora else None, res=extra)
         # the rank-r column views make the GEMMs write exactly [r, K] / [N, r] tensors: autograd can take them as
         # .grad without the copy it makes for a slice of a padded buffer
-        if has_lora and need[3]:
-            dA = gemm(dt[:, :r], x, a_rows_are_k=True, b_rows_are_k=True, out_dtype=torch.float32, split_k=0)
-        if has_lora and need[4]:
-            dB = gemm(g, t[:, :r], a_rows_are_k=True, b_rows_are_k=True, out_dtype=torch.float32, block_n=64, split_k=0)
-            dB = dB * scaling if scaling != 1.0 else dB
+        if has_lora and (need[3] or need[4]):
+            with _OnSideStream(g, dt, x, t):   # only the optimizer reads these: off the critical path when possible
+                if need[3]:
+                    dA = gemm(dt[:, :r], x, a_rows_are_k=True, b_rows_are_k=True, out_dtype=torch.float32, split_k=0)
+                if need[4]:
+                    dB = gemm(g, t[:, :r], a_rows_are_k=True, b_rows_are_k=True, out_dtype=torch.float32, block_n=64,
+                              split_k=0)
+                    dB = dB * scaling if scaling != 1.0 else dB
         if need[1]:
             dW = gemm(g, x, a_rows_are_k=True, b_rows_are_k=True)
         if has_bias and need[2]:

@@ -93,7 +93,7 @@ class GraphedTrainStep:
 
     def __init__(self, model, optimizer, scheduler, patchifier, config, prompt_embeds, prompt_attention_mask,
                  example_batch: dict, bucketer=None, warmup: int = 3, device=None,
-                 capture_error_mode: str = "global"):
+                 capture_error_mode: str = "global", side_work: bool = True):
         self.model, self.opt, self.bucketer = model, optimizer, bucketer
         device = device or next(model.parameters()).device
         self.static = {k: v.to(device).clone() for k, v in example_batch.items()}
@@ -106,6 +106,8 @@ class GraphedTrainStep:
                 optimizer.zero_grad(set_to_none=True)
             loss, rel_mse, nrmse, _ = train_step(model, self.static, *args, device=device)
             loss.backward()
+            if ops.side_stream is not None:   # the LoRA weight gradients queued off the critical path: join them
+                torch.cuda.current_stream(device).wait_stream(ops.side_stream)
             return loss.detach(), rel_mse.detach(), nrmse.detach()
 
         def one_step():
@@ -121,31 +123,39 @@ class GraphedTrainStep:
         # on the stream they were created on -- the default stream -- and invalidate the capture
         import gc
         gc.collect()
-        side = torch.cuda.Stream(device=device)
-        side.wait_stream(torch.cuda.current_stream(device))
-        with torch.cuda.stream(side):
-            for _ in range(max(warmup, 1)):  # allocator / lazy-init warm-up on a side stream, as torch requires
-                one_step()
-        torch.cuda.current_stream(device).wait_stream(side)
-        torch.cuda.synchronize(device)
-        l0 = ops.launch_count
-        self.graph = torch.cuda.CUDAGraph()
-        self.graph_opt = None
-        if bucketer is None:
-            optimizer.zero_grad(set_to_none=True)  # .grad is then allocated from the graph's private pool
-            with torch.cuda.graph(self.graph, capture_error_mode=capture_error_mode):
-                self.loss, self.rel_mse, self.nrmse = one_step()
-        else:
-            # data parallel: graph 1 = zero grads + forward + backward (no collective is captured: the bucket
-            # hooks only count), then the ~84 MB of gradient buckets are all-reduced eagerly over NCCL
-            # (0.3 ms at NVLink rates, not worth a capture-time dependency on the communicator), then
-            # graph 2 = the optimizer update
-            bucketer.overlap = False
-            with torch.cuda.graph(self.graph, capture_error_mode=capture_error_mode):
-                self.loss, self.rel_mse, self.nrmse = fwd_bwd()
-            self.graph_opt = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(self.graph_opt, pool=self.graph.pool(), capture_error_mode=capture_error_mode):
-                optimizer.step()
+        # Single GPU: the step is captured on a high-priority stream and the work only the optimizer consumes (LoRA
+        # weight gradients) on a default-priority one, so it fills SMs the main kernels leave idle.  With a bucketer
+        # the gradients are accumulated into bucket views by autograd on the main stream: everything stays there.
+        main = torch.cuda.Stream(device=device, priority=-1)
+        if bucketer is None and side_work:
+            ops.side_stream = torch.cuda.Stream(device=device, priority=0)
+        try:
+            main.wait_stream(torch.cuda.current_stream(device))
+            with torch.cuda.stream(main):
+                for _ in range(max(warmup, 1)):  # allocator / lazy-init warm-up on a side stream, as torch requires
+                    one_step()
+            torch.cuda.current_stream(device).wait_stream(main)
+            torch.cuda.synchronize(device)
+            l0 = ops.launch_count
+            self.graph = torch.cuda.CUDAGraph()
+            self.graph_opt = None
+            if bucketer is None:
+                optimizer.zero_grad(set_to_none=True)  # .grad is then allocated from the graph's private pool
+                with torch.cuda.graph(self.graph, stream=main, capture_error_mode=capture_error_mode):
+                    self.loss, self.rel_mse, self.nrmse = one_step()
+            else:
+                # data parallel: graph 1 = zero grads + forward + backward (no collective is captured: the bucket
+                # hooks only count), then the ~84 MB of gradient buckets are all-reduced eagerly over NCCL
+                # (0.3 ms at NVLink rates, not worth a capture-time dependency on the communicator), then
+                # graph 2 = the optimizer update
+                bucketer.overlap = False
+                with torch.cuda.graph(self.graph, capture_error_mode=capture_error_mode):
+                    self.loss, self.rel_mse, self.nrmse = fwd_bwd()
+                self.graph_opt = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(self.graph_opt, pool=self.graph.pool(), capture_error_mode=capture_error_mode):
+                    optimizer.step()
+        finally:
+            ops.side_stream = None
         self.launches = ops.launch_count - l0  # b200 kernel launches captured per step
 
     def load(self, batch: dict, non_blocking: bool = True):
