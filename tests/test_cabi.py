@@ -52,3 +52,34 @@ def test_no_cpu_fallback():
         lib.require_device()
     with pytest.raises(lib.B200Error):
         ops.gemm(torch.zeros(8, 8, dtype=torch.bfloat16), torch.zeros(8, 8, dtype=torch.bfloat16))
+
+
+def test_product_never_imports_the_oracle():
+    """The oracle is test infrastructure: no module of the product package (nor the C sources) may import, load or
+    execute anything under oracle/.  Checked on the source text and on the modules an import of the whole package
+    pulls in."""
+    import ast
+    import sys
+    pkg = os.path.join(ROOT, "video-generation-for-human-avatars_b200")
+    banned = {"ref_block", "ref_sampling", "ref_import", "make_golden", "diffusers_shim", "peft_shim", "oracle"}
+    for name in sorted(os.listdir(pkg)):
+        if not name.endswith(".py"):
+            continue
+        tree = ast.parse(open(os.path.join(pkg, name)).read())
+        for node in ast.walk(tree):
+            mods = []
+            if isinstance(node, ast.Import):
+                mods = [a.name for a in node.names]
+            elif isinstance(node, ast.ImportFrom):
+                mods = [node.module or ""]
+            for m in mods:
+                assert not (set(m.split(".")) & banned), f"{name} imports {m}"
+    for name in os.listdir(os.path.join(pkg, "csrc")):
+        text = open(os.path.join(pkg, "csrc", name)).read()
+        assert "oracle/" not in text or name.endswith(".md"), name
+    before = set(sys.modules)
+    import b200_ltx.api  # noqa: F401
+    import b200_ltx.optim  # noqa: F401
+    import b200_ltx.ring  # noqa: F401
+    pulled = {m.split(".")[0] for m in set(sys.modules) - before}
+    assert not (pulled & banned), pulled & banned
