@@ -15,7 +15,7 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, out):
+def _worker(rank, world, port, out, deferred=False):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     from b200_ltx.dp import GradBucketer
@@ -27,6 +27,7 @@ def _worker(rank, world, port, out):
     params += [(f"e.{n}", p) for n, p in extra.named_parameters()]
     bk = GradBucketer(params, bucket_bytes=2048)
     assert len(bk.buckets) >= 3
+    bk.overlap = not deferred
     for step in range(2):
         bk.zero_grad()
         x = torch.full((4, 16), float(rank + 1 + step))
@@ -35,7 +36,10 @@ def _worker(rank, world, port, out):
             h = torch.tanh(m(h))
         loss = extra(h.double()).sum()
         loss.backward()
-        bk.finish()
+        if deferred:
+            bk.reduce_now()   # the graph-replayed step: hooks only counted, one reduction after the backward
+        else:
+            bk.finish()
     flat = torch.cat([p.grad.flatten().double() for _, p in params])
     # reference: average of the per-rank grads computed without the bucketer
     ref = []
@@ -57,4 +61,12 @@ def test_bucketed_allreduce_world2():
     mgr = mp.Manager()
     out = mgr.dict()
     mp.spawn(_worker, args=(2, _free_port(), out), nprocs=2, join=True)
+    assert len(out) == 2 and all(v < 1e-6 for v in out.values()), dict(out)
+
+
+def test_deferred_allreduce_world2():
+    """overlap = False + reduce_now(): the mode train.GraphedTrainStep uses between its two CUDA graphs."""
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_worker, args=(2, _free_port(), out, True), nprocs=2, join=True)
     assert len(out) == 2 and all(v < 1e-6 for v in out.values()), dict(out)
