@@ -223,3 +223,50 @@ def test_sampling_loop_restatement_properties():
     f = v3[2:4].reshape(2, -1).std(dim=1) / want.reshape(2, -1).std(dim=1)
     torch.testing.assert_close(resc, want * (0.7 * f + 0.3).view(2, 1, 1))
     assert a.shape == tokens.shape
+
+
+@pytest.mark.skipif(not ref_import.available(), reason="reference tree not mounted")
+def test_full_train_mode_equal_to_live_reference(golden_dir):
+    """The reference's other strategy (training.py:75-91: no adapters; proj_out, scale_shift_tables, adaln_single,
+    caption_projection and every attention parameter trainable): the oracle marks the same parameters trainable and
+    its gradients -- AdaLN tables, qk-norm weights, timestep MLP, all projections -- equal the reference's own."""
+    import make_golden as mg
+    ns = ref_import.load()
+    g, _, batch, t = _tiny(golden_dir)
+    P = rb.init_params(g["cfg"], 0, seed=4)
+    model = mg.build_reference_model(ns, g["cfg"], 0, P, train_mode="full")
+    want_trainable = {n for n, p in model.named_parameters() if p.requires_grad}
+    assert want_trainable == {k for k in P if rb.is_trainable(k, "full")}
+    assert not any("ff.net" in n or "patchify_proj" in n for n in want_trainable)
+    rl, ro, rg = mg.reference_loss_and_grads(ns, model, g["cfg"], batch, t)
+    Pd = {k: v.clone().requires_grad_(rb.is_trainable(k, "full")) for k, v in P.items()}
+    loss, out = rb.train_step_loss(Pd, g["cfg"], batch["latents"], batch["ref_image_latents"], batch["pose_latents"],
+                                   batch["prompt_embeds"], batch["prompt_mask"], t, batch["noise"])
+    loss.backward()
+    torch.testing.assert_close(out.detach(), ro, **TOL)
+    torch.testing.assert_close(loss.detach(), rl, **TOL)
+    og = {k: v.grad for k, v in Pd.items() if v.grad is not None}
+    assert set(og) == set(rg)
+    for k in sorted(rg):   # (threaded CPU reductions may order their partial sums differently from run to run)
+        torch.testing.assert_close(og[k], rg[k], rtol=2e-4, atol=1e-7, msg=lambda m, k=k: f"{k}: {m}")
+
+
+def test_full_train_mode_matches_golden(golden_dir):
+    """Travels to boxes without the reference tree: the oracle's full-mode output, loss and gradient summaries against
+    the vectors oracle/make_golden.py produced from the reference's own modules and its own "full" strategy."""
+    g = torch.load(os.path.join(golden_dir, "tiny_full_mode_fp32.pt"))
+    c = g["case"]
+    P = rb.init_params(g["cfg"], 0, seed=g["seed_w"])
+    batch = rb.synthetic_batch(g["cfg"], c["b"], c["f"], c["h"], c["w"], c["n_ctx"], c["seed_x"], c["valid_ctx"])
+    Pd = {k: v.clone().requires_grad_(rb.is_trainable(k, "full")) for k, v in P.items()}
+    loss, out = rb.train_step_loss(Pd, g["cfg"], batch["latents"], batch["ref_image_latents"], batch["pose_latents"],
+                                   batch["prompt_embeds"], batch["prompt_mask"], torch.tensor(c["t"]), batch["noise"])
+    loss.backward()
+    torch.testing.assert_close(out.detach(), g["out"], **TOL)
+    torch.testing.assert_close(loss.detach(), g["loss"], **TOL)
+    grads = {k: v.grad for k, v in Pd.items() if v.grad is not None}
+    assert set(grads) == set(g["grad_stats"]) and len(grads) > 40
+    for k, (nrm, tot, head) in g["grad_stats"].items():
+        torch.testing.assert_close(grads[k].norm().double(), nrm, rtol=1e-4, atol=1e-9, msg=lambda m, k=k: f"{k}: {m}")
+        torch.testing.assert_close(grads[k].flatten()[:16], head, rtol=1e-4, atol=1e-7, msg=lambda m, k=k: f"{k}: {m}")
+        assert abs(float(grads[k].sum().double() - tot)) <= 1e-4 * (float(grads[k].abs().sum()) + 1e-9), k
