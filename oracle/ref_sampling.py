@@ -4,10 +4,14 @@ Follows pipelines/pipeline_ltx_video.py:1089-1288 (the loop), :1346-1379 (`denoi
 transformer3d.py:187-203 (`create_skip_layer_mask`) on top of ref_block.transformer_forward / rf_step.  Only tests,
 `__graft_entry__.smoke()` and bench.py's cpu_baseline leg may import this; the product never does.
 
-Parity status: the transformer forward and the Euler step underneath are pinned (tests/golden/tiny_sampling_fp32.pt,
-scheduler.pt, generated from the imported reference).  The guidance combine itself is **parity unpinned**: the
-pipeline module cannot be imported here (diffusers / imageio / the VAE stack are absent) and the reference has no
-test or golden vector for it, so this file is a line-by-line restatement only.
+Parity status: PINNED.  The reference's unmodified `LTXVideoPipeline.__call__` is driven on CPU by
+oracle/ref_pipeline.py (VAE / diffusers-pipeline stand-ins, the loop itself as written) and this restatement equals
+its output bit for bit -- single condition, CFG, CFG* + STG + std rescale with per-step guidance lists, all four
+skip-layer strategies -- and `denoising_step` with a conditioning mask (tests/test_oracle.py, live where
+/root/reference is mounted; tests/golden/tiny_guided_sampling_fp32.pt, written by oracle/make_golden.py, elsewhere).
+One deliberate difference: the reference's CFG* projection multiplies a [B, 1] alpha into a [B, N, C] prediction
+(:1238), which only broadcasts for batch size 1 (it raises for B > 1, test_oracle pins that); this file reshapes alpha
+to [B, 1, 1], identical at B = 1 and defined for B > 1.
 
 Reference behaviours kept on purpose:
 * the prompt batch order is [negative, positive, positive] and a step uses the slice its guidance flags select
@@ -74,6 +78,17 @@ def guidance_combine(noise_pred: Tensor, batch_size: int, num_conds: int, do_cfg
     return noise_pred
 
 
+def denoising_step(timesteps: Tensor, latents: Tensor, noise_pred: Tensor, cur_t: Tensor,
+                   conditioning_mask: Optional[Tensor], t: Tensor, t_eps: float = 1e-6) -> Tensor:
+    """pipeline :1346-1379: Euler step of every token, then keep the tokens whose conditioning level says they are
+    not being denoised yet (hard-conditioned tokens, mask 1.0, never move)."""
+    denoised = rb.rf_step(timesteps, noise_pred, cur_t, latents)
+    if conditioning_mask is None:
+        return denoised
+    move = (t - t_eps < (1.0 - conditioning_mask)).unsqueeze(-1)
+    return torch.where(move, denoised, latents)
+
+
 def denoise_loop(P, cfg: dict, latents: Tensor, fractional_coords: Tensor, ref: Tensor, pose: Tensor,
                  prompt_embeds: Tensor, prompt_mask: Tensor, timesteps: Tensor,
                  negative_prompt_embeds: Optional[Tensor] = None, negative_prompt_mask: Optional[Tensor] = None,
@@ -124,11 +139,5 @@ def denoise_loop(P, cfg: dict, latents: Tensor, fractional_coords: Tensor, ref: 
                 skip_layer_strategy=skip_layer_strategy)
             noise_pred = guidance_combine(noise_pred, batch_size, num_conds, do_cfg, do_stg, gs_l[i], stg_l[i], rs_l[i],
                                           cfg_star_rescale)
-            cur_t = cur_t[:1]
-            denoised = rb.rf_step(timesteps, noise_pred, cur_t, latents)
-            if conditioning_mask is None:
-                latents = denoised
-            else:
-                move = (t - 1e-6 < (1.0 - conditioning_mask)).unsqueeze(-1)
-                latents = torch.where(move, denoised, latents)
+            latents = denoising_step(timesteps, latents, noise_pred, cur_t[:1], conditioning_mask, t)
     return latents

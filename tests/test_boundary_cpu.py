@@ -1,0 +1,186 @@
+"""Boundary contract on the reference's OWN classes, on CPU.
+
+`api.install()` is applied to an instance of the reference's unmodified `Transformer3DModel` (plain and wrapped by
+the reference's own `apply_training_strategy(..., "lora_audio")`), and the product's functional forwards
+(modules.transformer_forward / block_forward / attention_forward) then run over plain-torch stand-ins of the raw
+kernels (tests/torch_kernels.py) -- so every attribute the host logic reads from the reference's modules, the peft
+attribute layout, the skip-layer paths and the gradient-checkpoint branch are exercised against the reference's own
+forward.  Survival contract (torch_utils.py:66-102): deepcopy -> merge_and_unload -> state_dict on an installed
+model.  Needs /root/reference (build container); the GPU box runs the mirror-class tests instead."""
+import copy
+import os
+import sys
+
+import pytest
+import torch
+
+import ref_block as rb
+import ref_import
+import torch_kernels as tk
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle"))
+import make_golden as mg  # noqa: E402
+
+pytestmark = pytest.mark.skipif(not ref_import.available(), reason="reference tree not mounted")
+
+BF16 = torch.bfloat16
+
+
+def _rel(a, b):
+    return float((a.float() - b.float()).norm() / (b.float().norm() + 1e-20))
+
+
+def _reference_model(lora_rank, seed=0, layers=2):
+    ns = ref_import.load()
+    cfg = dict(mg.TINY, num_layers=layers)
+    P = rb.init_params(cfg, lora_rank, seed=seed)
+    model = mg.build_reference_model(ns, cfg, lora_rank, P).to(BF16)
+    for n, p in model.named_parameters():           # peft keeps adapters in fp32 (autocast_adapter_dtype)
+        if "lora_" in n:
+            p.data = p.data.float()
+    return ns, cfg, model.eval()
+
+
+def _inputs(cfg, B=2, f=2, h=4, w=4, n_ctx=24, valid=15, seed=5, frac_coords=False):
+    b = rb.synthetic_batch(cfg, B, f, h, w, n_ctx, seed, valid)
+    tokens, coords = rb.patchify(b["latents"])
+    if frac_coords:
+        coords = coords.float()
+        coords[:, 0] = coords[:, 0] * (1.0 / 25)
+    return dict(hidden_states=tokens.to(BF16).contiguous(), indices_grid=coords,
+                ref_image_hidden_states=b["ref_image_latents"].to(BF16),
+                pose_hidden_states=b["pose_latents"].to(BF16),
+                encoder_hidden_states=b["prompt_embeds"].expand(B, -1, -1).to(BF16).contiguous(),
+                timestep=torch.tensor([0.4, 0.73][:B]),
+                encoder_attention_mask=b["prompt_mask"].expand(B, -1))
+
+
+def _run(model, inp, **kw):
+    x = {k: (v.clone() if torch.is_tensor(v) else v) for k, v in inp.items()}
+    with torch.no_grad():
+        out = model(**x, return_dict=False, **kw)[0]
+    return out, x["hidden_states"]
+
+
+@pytest.mark.parametrize("lora_rank", [0, 32])
+def test_install_on_reference_model_matches_reference_forward(lora_rank):
+    from b200_ltx import api, modules
+    ns, cfg, model = _reference_model(lora_rank)
+    inp = _inputs(cfg)
+    want, tok_ref = _run(model, inp)
+    root = model.base_model.model if hasattr(model, "base_model") else model
+    with tk.patched():
+        api.install(model)
+        assert isinstance(root.transformer_blocks[0].attn1.processor, modules.B200AttnProcessor)
+        assert isinstance(root.transformer_blocks[1].attn2.get_processor(), modules.B200AttnProcessor)
+        got, tok = _run(model, inp)
+        # return_dict=True keeps the reference's output protocol (.sample and [0])
+        x = {k: (v.clone() if torch.is_tensor(v) else v) for k, v in inp.items()}
+        with torch.no_grad():
+            o = model(**x)
+        assert torch.equal(o.sample, got) and torch.equal(o[0], got)
+    assert got.shape == want.shape and got.dtype == want.dtype
+    assert _rel(got, want) < 2e-2, _rel(got, want)
+    assert torch.equal(tok, tok_ref) or _rel(tok, tok_ref) < 4e-3     # in-place conditioning lerp
+    assert not torch.equal(tok, inp["hidden_states"])
+    # uninstall gives the reference's own forwards back, bit for bit
+    api.uninstall(model)
+    for blk in root.transformer_blocks:
+        blk.attn1.set_processor(ns.AttnProcessor2_0())
+        blk.attn2.set_processor(ns.AttnProcessor2_0())
+    again, _ = _run(model, inp)
+    assert torch.equal(again, want)
+
+
+@pytest.mark.parametrize("strategy", ["AttentionSkip", "AttentionValues", "TransformerBlock"])
+def test_skip_layer_strategies_on_reference_model(strategy):
+    """STG paths (attention.py:1071-1086, 312-319) through the host logic, sampling-style inputs: fractional
+    coordinates, per-token timesteps [B, N], two conditions with the second one perturbed in block 1."""
+    from b200_ltx import api
+    ns, cfg, model = _reference_model(0, seed=3)
+    inp = _inputs(cfg, frac_coords=True)
+    N = inp["hidden_states"].shape[1]
+    inp["timestep"] = torch.full((2, N), 0.9)
+    inp["timestep"][:, :16] = 0.0                      # conditioned first frame
+    skip = model.create_skip_layer_mask(1, 2, 1, [1])
+    strat = getattr(ns.SkipLayerStrategy, strategy)
+    want, _ = _run(model, inp, skip_layer_mask=skip, skip_layer_strategy=strat)
+    plain, _ = _run(model, inp)
+    assert not torch.equal(want[1], plain[1]) and _rel(want[0], plain[0]) < 1e-6   # only condition 1 is perturbed
+    with tk.patched():
+        api.install(model)
+        got, _ = _run(model, inp, skip_layer_mask=skip, skip_layer_strategy=strat)
+        # the mask the reference's own create_skip_layer_mask built carries no host-side note: every block applies it
+        assert _rel(got, want) < 2e-2, _rel(got, want)
+        assert _rel(got[1], want[1]) < 2e-2
+
+
+def test_gradient_checkpoint_branch_on_reference_model():
+    """transformer3d.py:503-534: training + gradient_checkpointing passes the block arguments positionally through
+    torch.utils.checkpoint; the rebound block_forward must accept exactly that order."""
+    from b200_ltx import api
+    ns, cfg, model = _reference_model(32)
+    root = model.base_model.model
+    inp = _inputs(cfg)
+    want, _ = _run(model, inp)
+    with tk.patched():
+        api.install(model)
+        model.train()
+        root.gradient_checkpointing = True
+        got, _ = _run(model, inp)
+        model.eval()
+    assert _rel(got, want) < 2e-2
+
+
+def test_installed_model_survives_deepcopy_merge_state_dict():
+    """torch_utils.py:66-102 (save_lora_merged_weights): deepcopy(model) -> merge_and_unload() -> state_dict()."""
+    from b200_ltx import api, modules
+    ns, cfg, model = _reference_model(32)
+    root = model.base_model.model
+    inp = _inputs(cfg)
+    with tk.patched():
+        api.install(model)
+        before, _ = _run(model, inp)                               # fills the weight / rope caches
+        assert modules.side(root).get("wkv_all") is None or modules.side(root)["wkv_all"][1].numel() > 0
+        assert not any(k.startswith("_b200") for k in root.__dict__)          # nothing cached on the modules
+        assert not any(k.startswith("_b200") for k in root.transformer_blocks[0].attn1.__dict__)
+        clone = copy.deepcopy(model)
+        assert not modules._side_tables.get(clone.base_model.model)            # derived state is never copied
+        merged = clone.merge_and_unload()
+        sd = merged.state_dict()
+        plain_keys = set(rb.param_shapes(cfg, 0))
+        assert set(sd) == plain_keys, set(sd) ^ plain_keys                    # no lora_ / base_layer / cache keys
+        assert all(v.dtype == BF16 for v in sd.values())
+        # the merged copy still runs on the installed forwards and reproduces the adapted model
+        out_merged, _ = _run(merged, inp)
+        assert _rel(out_merged, before) < 1.5e-2
+        # ... and the live model is untouched: same output, adapters still separate
+        after, _ = _run(model, inp)
+        assert torch.equal(after, before)
+        assert any("lora_A" in k for k in model.state_dict())
+
+
+def test_merge_then_forward_uses_merged_weights():
+    """forward -> merge -> forward on the SAME object must not reuse cached pre-merge concatenations."""
+    from b200_ltx import api, lora, modules
+    cfg = dict(mg.TINY, num_layers=2)
+    P = rb.init_params(cfg, 32, seed=1)
+    with tk.patched():
+        m = api.build_model(dict(api.LTXV_2B_CONFIG, **cfg), device="cpu")
+        m = lora.apply_training_strategy(m, 32, 32)
+        sd = {k: P[k.replace("base_model.model.", "").replace(".base_layer.", ".")].to(v.dtype)
+              for k, v in m.state_dict().items()}
+        m.load_state_dict(sd)
+        m.eval()
+        # caption tokens: B * L a multiple of 128 so that the batched K/V cache path is taken
+        inp = _inputs(cfg, B=2, n_ctx=64, valid=40)
+        with_adapters, _ = _run(m, inp)
+        assert modules.side(m.base_model.model).get("wkv_all") is not None
+        base = m.merge_and_unload()
+        merged, _ = _run(base, inp)
+        assert _rel(merged, with_adapters) < 1.5e-2, _rel(merged, with_adapters)
+        # control: dropping the adapters WITHOUT merging changes the output by much more than that
+        m2 = api.build_model(dict(api.LTXV_2B_CONFIG, **cfg), device="cpu")
+        m2.load_state_dict({k: v for k, v in P.items() if "lora_" not in k}, strict=True)
+        no_lora, _ = _run(m2.to(BF16).eval(), inp)
+        assert _rel(no_lora, with_adapters) > 3 * _rel(merged, with_adapters)

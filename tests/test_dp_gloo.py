@@ -42,6 +42,7 @@ def _worker(rank, world, port, out, deferred=False):
             bk.finish()
     flat = torch.cat([p.grad.flatten().double() for _, p in params])
     # reference: average of the per-rank grads computed without the bucketer
+    bk.close()
     ref = []
     for r in range(world):
         for _, p in params:
@@ -69,4 +70,73 @@ def test_deferred_allreduce_world2():
     mgr = mp.Manager()
     out = mgr.dict()
     mp.spawn(_worker, args=(2, _free_port(), out, True), nprocs=2, join=True)
+    assert len(out) == 2 and all(v < 1e-6 for v in out.values()), dict(out)
+
+
+def _accum_worker(rank, world, port, out):
+    """Two accumulation windows of two micro-steps each; between them the 'optimizer' drops `.grad`
+    (zero_grad(set_to_none=True), training.py:207) instead of calling the bucketer's zero_grad."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from b200_ltx.dp import GradBucketer
+    torch.manual_seed(0)
+    lin = [torch.nn.Linear(8, 8) for _ in range(4)]
+    params = [(f"l{i}.{n}", p) for i, m in enumerate(lin) for n, p in m.named_parameters()]
+    bk = GradBucketer(params, bucket_bytes=512)
+
+    def run(x):
+        h = x
+        for m in lin:
+            h = torch.tanh(m(h))
+        h.sum().backward()
+
+    def inputs(r, window):
+        return [torch.full((2, 8), float(r + 1 + 3 * window + k)) for k in range(2)]
+
+    worst = 0.0
+    for window in range(2):
+        if window == 0:
+            bk.zero_grad()
+        else:
+            for _, p in params:
+                p.grad = None          # what torch.optim's zero_grad(set_to_none=True) leaves behind
+            bk.zero_grad()             # clears the flat buckets; the hooks re-attach the views
+            for _, p in params[::2]:
+                p.grad = None          # and a caller that drops some of them again after that
+        xs = inputs(rank, window)
+        with bk.no_sync():
+            run(xs[0])
+        run(xs[1])
+        bk.finish()
+        got = torch.cat([p.grad.flatten() for _, p in params]).clone()
+        # a second synchronising backward inside the same window must raise, not double-reduce
+        if window == 0:
+            try:
+                run(xs[1])
+                raised = False
+            except RuntimeError:
+                raised = True
+            assert raised
+        # reference: plain autograd on detached copies of the layers
+        ref = 0
+        for r in range(world):
+            import copy
+            lin2 = copy.deepcopy(lin)
+            for m in lin2:
+                m.zero_grad(set_to_none=True)
+            for x in inputs(r, window):
+                h = x
+                for m in lin2:
+                    h = torch.tanh(m(h))
+                h.sum().backward()
+            ref = ref + torch.cat([p.grad.flatten() for m in lin2 for p in m.parameters()])
+        worst = max(worst, float((got - ref / world).abs().max()))
+    out[rank] = worst
+    dist.destroy_process_group()
+
+
+def test_gradient_accumulation_and_set_to_none_world2():
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_accum_worker, args=(2, _free_port(), out), nprocs=2, join=True)
     assert len(out) == 2 and all(v < 1e-6 for v in out.values()), dict(out)

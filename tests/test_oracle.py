@@ -270,3 +270,80 @@ def test_full_train_mode_matches_golden(golden_dir):
         torch.testing.assert_close(grads[k].norm().double(), nrm, rtol=1e-4, atol=1e-9, msg=lambda m, k=k: f"{k}: {m}")
         torch.testing.assert_close(grads[k].flatten()[:16], head, rtol=1e-4, atol=1e-7, msg=lambda m, k=k: f"{k}: {m}")
         assert abs(float(grads[k].sum().double() - tot)) <= 1e-4 * (float(grads[k].abs().sum()) + 1e-9), k
+
+
+def _guided_case_oracle(name, coords):
+    """oracle/ref_sampling.denoise_loop on one of make_golden.GUIDED_CASES (same seeds, same inputs)."""
+    import make_golden as mg
+    import ref_sampling as rs
+    batch, kw = mg.GUIDED_CASES[name]
+    P, b, enc, msk, neg, neg_m = mg.guided_inputs(batch)
+    f, h, w = mg.GUIDED_FHW
+    okw = {k: v for k, v in kw.items() if k not in ("negative", "skip_layer_strategy")}
+    if kw.get("negative"):
+        okw.update(negative_prompt_embeds=neg, negative_prompt_mask=neg_m)
+    if "skip_layer_strategy" in kw:
+        okw["skip_layer_strategy"] = {"AttentionValues": rb.STG_ATTENTION_VALUES, "AttentionSkip": rb.STG_ATTENTION_SKIP,
+                                      "TransformerBlock": rb.STG_TRANSFORMER_BLOCK,
+                                      "Residual": rb.STG_RESIDUAL}[kw["skip_layer_strategy"]]
+    # the pipeline draws its initial noise in the patchified shape from the generator it is given (:656-660)
+    x0 = torch.randn((batch, f * h * w, 128), generator=torch.Generator().manual_seed(mg.GUIDED_SEED))
+    got = rs.denoise_loop(P, mg.TINY, x0, coords, b["ref_image_latents"], b["pose_latents"], enc, msk,
+                          rb.uniform_timesteps(mg.GUIDED_STEPS), alias_first_step_only=False, **okw)
+    return got.reshape(batch, f, h, w, 128).permute(0, 4, 1, 2, 3)
+
+
+def test_guided_sampling_loop_matches_golden(golden_dir):
+    """The restated denoising loop against what the reference's own LTXVideoPipeline.__call__ produced
+    (tests/golden/tiny_guided_sampling_fp32.pt, oracle/make_golden.py): one condition, CFG with a negative prompt,
+    CFG* + STG(attention values) + std rescale with per-step guidance lists, STG with the transformer-block skip."""
+    import make_golden as mg
+    g = torch.load(os.path.join(golden_dir, "tiny_guided_sampling_fp32.pt"))
+    assert set(g["cases"]) == set(mg.GUIDED_CASES)
+    for name, rec in g["cases"].items():
+        got = _guided_case_oracle(name, rec["coords"])
+        torch.testing.assert_close(got, rec["out"], rtol=2e-4, atol=2e-5, msg=lambda m, n=name: f"{n}: {m}")
+
+
+@pytest.mark.skipif(not ref_import.available(), reason="reference tree not mounted")
+def test_guided_sampling_loop_bit_equal_to_live_pipeline():
+    """Same cases, live: oracle/ref_pipeline.py drives the reference's unmodified pipeline loop; plus every skip-layer
+    strategy, `denoising_step` with a soft / hard conditioning mask, and the reference's CFG* batch-size quirk."""
+    import make_golden as mg
+    import ref_pipeline as rp
+    import ref_sampling as rs
+    ns = ref_import.load()
+    for name in mg.GUIDED_CASES:
+        want, coords = mg.run_reference_pipeline(ns, name)
+        assert torch.equal(_guided_case_oracle(name, coords), want), name
+    base = dict(mg.GUIDED_CASES["cfgstar_stg_rescale"][1])
+    try:
+        for strat in ("AttentionSkip", "TransformerBlock", "Residual"):
+            mg.GUIDED_CASES["tmp"] = (1, dict(base, skip_layer_strategy=strat))
+            want, coords = mg.run_reference_pipeline(ns, "tmp")
+            assert torch.equal(_guided_case_oracle("tmp", coords), want), strat
+        # the reference's CFG* projection broadcasts a [B, 1] alpha against [B, N, C]: batch size 1 only (:1238)
+        mg.GUIDED_CASES["tmp"] = (2, dict(base))
+        with pytest.raises(RuntimeError):
+            mg.run_reference_pipeline(ns, "tmp")
+    finally:
+        mg.GUIDED_CASES.pop("tmp", None)
+    # denoising_step (:1346-1379) with per-token timesteps and a conditioning mask
+    P, b, enc, msk, _, _ = mg.guided_inputs(2)
+    model = mg.build_reference_model(ns, mg.TINY, 0, P).eval()
+    sched = ns.RectifiedFlowScheduler()
+    sched.set_timesteps(6, samples_shape=(2, 128, 3, 4, 6))
+    pipe = rp.make_pipeline(model, sched, ns.SymmetricPatchifier(patch_size=1))
+    g = torch.Generator().manual_seed(0)
+    lat, v = torch.randn(2, 72, 128, generator=g), torch.randn(2, 72, 128, generator=g)
+    cm = torch.zeros(2, 72)
+    cm[:, :24] = 1.0
+    cm[0, 24:40] = 0.5
+    cm[1, 30:33] = 0.9
+    for i in (0, 2, 3, 5):
+        t = sched.timesteps[i]
+        cur = torch.min(t[None].expand(2).unsqueeze(-1), 1.0 - cm)
+        want = pipe.denoising_step(lat, v, cur[:1], cm, t, {})
+        got = rs.denoising_step(sched.timesteps, lat, v, cur[:1], cm, t)
+        assert torch.equal(got, want), i
+        assert torch.equal(want[:, :24], lat[:, :24])

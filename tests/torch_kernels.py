@@ -1,0 +1,145 @@
+"""Plain-torch stand-ins for the raw `ops.*` kernel wrappers, with the same Python signatures.
+
+TEST INFRASTRUCTURE ONLY: lets the CPU suite run the HOST logic of the product (modules.transformer_forward /
+block_forward / attention_forward, api.install on the reference's own classes, the LoRA attribute plumbing, the
+caches) without a GPU.  Nothing in the package imports this file; on a GPU box the tests call the real C ABI."""
+import contextlib
+
+import torch
+import torch.nn.functional as F
+
+BF16 = torch.bfloat16
+
+
+def _mat(t, rows_are_k):
+    return t.float().t() if rows_are_k else t.float()
+
+
+def gemm(a, b, *, a_rows_are_k=False, b_rows_are_k=False, a2=None, b2=None, out=None, out_dtype=BF16, bias=None,
+         gate=None, rows_per_gate=0, res=None, aux=None, epilogue=0, block_n=0, split_k=1):
+    acc = _mat(a, a_rows_are_k) @ _mat(b, b_rows_are_k).t()
+    if a2 is not None:
+        acc = acc + _mat(a2, a_rows_are_k) @ _mat(b2, b_rows_are_k).t()
+    if bias is not None:
+        acc = acc + bias.float()
+    if epilogue == 1:
+        if aux is not None:
+            aux.copy_(acc.to(aux.dtype))
+        acc = F.gelu(acc, approximate="tanh")
+    elif epilogue == 2:
+        h = aux.float().requires_grad_(True)
+        with torch.enable_grad():
+            F.gelu(h, approximate="tanh").sum().backward()
+        acc = acc * h.grad
+    if gate is not None:
+        acc = acc * gate.float().repeat_interleave(rows_per_gate, 0)[:acc.shape[0]]
+    if res is not None:
+        acc = acc + res.float()
+    if out is None:
+        return acc.to(out_dtype)
+    out.copy_(acc.to(out.dtype))
+    return out
+
+
+def gemm_batched(a, b, out, M, N, K, groups, offs, *, a_rows_are_k=False, b_rows_are_k=False, a2=None, b2=None, K2=0,
+                 bias=None, block_n=0):
+    z = (0, 0)
+
+    def sub(t, name, rows, cols, g):
+        r0, c0 = offs.get(name, z)
+        return t[g * r0:g * r0 + rows, g * c0:g * c0 + cols]
+    for g in range(groups):
+        ag = sub(a, "a", K if a_rows_are_k else M, M if a_rows_are_k else K, g)
+        bg = sub(b, "b", K if b_rows_are_k else N, N if b_rows_are_k else K, g)
+        a2g = b2g = None
+        if a2 is not None:
+            a2g = sub(a2, "a2", K2 if a_rows_are_k else M, M if a_rows_are_k else K2, g)
+            b2g = sub(b2, "b2", K2 if b_rows_are_k else N, N if b_rows_are_k else K2, g)
+        bs = None
+        if bias is not None:
+            o = offs.get("bias", 0)
+            bs = bias[g * o:g * o + N]
+        gemm(ag, bg, a_rows_are_k=a_rows_are_k, b_rows_are_k=b_rows_are_k, a2=a2g, b2=b2g, bias=bs,
+             out=sub(out, "c", M, N, g))
+    return out
+
+
+def norm_mod_fwd(x, scale, shift, rows_per_mod, eps, layernorm=False, out=None):
+    xf = x.float()
+    if layernorm:
+        n = F.layer_norm(xf, (xf.shape[-1],), None, None, eps)
+    else:
+        n = xf * torch.rsqrt(xf.pow(2).mean(-1, keepdim=True) + eps)
+    rows = x.shape[0]
+    if scale is not None:
+        n = n * (1 + scale.float().repeat_interleave(rows_per_mod, 0)[:rows])
+    if shift is not None:
+        n = n + shift.float().repeat_interleave(rows_per_mod, 0)[:rows]
+    y = n.to(BF16)
+    if out is not None:
+        out.copy_(y)
+        return out
+    return y
+
+
+def _rope(x, cos, sin):
+    xr = x.reshape(x.shape[0], -1, 2)
+    rot = torch.stack((-xr[..., 1], xr[..., 0]), dim=-1).reshape(x.shape)
+    return x * cos.float() + rot * sin.float()
+
+
+def qknorm_rope_fwd(xq, xk, wq, wk, cos, sin, oq, ok, eps=1e-5):
+    for x, w, o in ((xq, wq, oq), (xk, wk, ok)):
+        if x is None:
+            continue
+        xf = x.float()
+        n = (xf * torch.rsqrt(xf.pow(2).mean(-1, keepdim=True) + eps)).to(BF16).float() * w.float()
+        if cos is not None:
+            n = _rope(n.to(BF16).float(), cos, sin)
+        o.copy_(n.to(o.dtype))
+
+
+def fa_fwd(q, k, v, B, H, Nq, Nk, key_bias=None, scale=0.125, need_lse=True):
+    D = H * 64
+    qh = q[:, :D].float().reshape(B, Nq, H, 64).transpose(1, 2)
+    kh = k[:, :D].float().reshape(B, Nk, H, 64).transpose(1, 2)
+    vh = v[:, :D].float().reshape(B, Nk, H, 64).transpose(1, 2)
+    s = qh @ kh.transpose(-1, -2) * scale
+    if key_bias is not None:
+        s = s + key_bias.float()[:, None, None, :]
+    lse = torch.logsumexp(s, dim=-1)
+    o = torch.softmax(s, dim=-1) @ vh
+    return o.transpose(1, 2).reshape(B * Nq, D).to(BF16), (lse if need_lse else None)
+
+
+def lerp_condition_(tokens, ref, pose, w_ref=0.85, w_pose=0.5, token_offset=0):
+    B, N, C = tokens.shape
+    Fr, Hh, Ww = pose.shape[2], pose.shape[3], pose.shape[4]
+    assert token_offset == 0 and N == Fr * Hh * Ww
+    v = tokens.view(B, Fr, Hh, Ww, C).permute(0, 4, 1, 2, 3)
+    v[:, :, 0:1] = torch.lerp(v[:, :, 0:1], ref, w_ref)
+    v[:, :, 1:] = torch.lerp(v[:, :, 1:], pose[:, :, 1:], w_pose)
+    return tokens
+
+
+@contextlib.contextmanager
+def patched():
+    """Run the product's host logic over these stand-ins (CPU tensors allowed, no device check)."""
+    from b200_ltx import lib, modules, ops
+    names = ["gemm", "gemm_batched", "norm_mod_fwd", "qknorm_rope_fwd", "fa_fwd", "lerp_condition_"]
+    saved = {n: getattr(ops, n) for n in names}
+    saved_req, saved_dev = modules._require_bf16, lib.require_device
+    try:
+        for n in names:
+            setattr(ops, n, globals()[n])
+
+        def req(t, what):
+            if t.dtype != BF16:
+                raise lib.B200Error(f"{what} must be bfloat16")
+        modules._require_bf16 = req
+        lib.require_device = lambda: None
+        yield
+    finally:
+        for n, f in saved.items():
+            setattr(ops, n, f)
+        modules._require_bf16, lib.require_device = saved_req, saved_dev

@@ -39,6 +39,7 @@ def install(model):
                 attn.set_processor(B200AttnProcessor())
         blk.forward = types.MethodType(modules.block_forward, blk)
     root.forward = types.MethodType(modules.transformer_forward, root)
+    modules.drop_weight_caches(root)
     return model
 
 
@@ -47,6 +48,7 @@ def uninstall(model):
     for blk in root.transformer_blocks:
         blk.__dict__.pop("forward", None)
     root.__dict__.pop("forward", None)
+    modules.drop_weight_caches(root)
     return model
 
 
@@ -60,9 +62,9 @@ def enable_sequence_parallel(model, group=None, impl=None, mode="ring"):
     sp = None
     if torch.distributed.is_initialized() and torch.distributed.get_world_size(group) > 1:
         sp = SequenceParallel(group, impl, mode)
-    root.__dict__["_b200_sp"] = sp
+    modules.side(root)["sp"] = sp
     for blk in root.transformer_blocks:
-        blk.attn1.__dict__["_b200_sp"] = sp
+        modules.side(blk.attn1)["sp"] = sp
     return sp
 
 

@@ -41,6 +41,7 @@ class LoraLinear(nn.Module):
                                                           dtype=torch.float32)})
         nn.init.kaiming_uniform_(self.lora_A["default"].weight, a=math.sqrt(5))
         nn.init.zeros_(self.lora_B["default"].weight)
+        self.merged = False
 
     @property
     def weight(self):
@@ -66,8 +67,23 @@ class LoraLinear(nn.Module):
             from . import ops
             ops.gemm((B.detach().float() * s).to(torch.bfloat16).contiguous(), A.detach().to(torch.bfloat16).contiguous(),
                      b_rows_are_k=True, res=w.data, out=w.data)
+            # the kernel wrote through the raw pointer: move the version counter so that every cache keyed on it
+            # (modules._cached_wqkv / _batched_ctx_kv) sees a new weight
+            torch.autograd.graph.increment_version(w)
         else:
-            w.data += ((B.float() @ A.float()) * s).to(w.dtype)
+            with torch.no_grad():
+                w.add_(((B.float() @ A.float()) * s).to(w.dtype))
+        self.merged = True
+
+    def unmerge(self):
+        """Inverse of merge() (peft `unmerge_adapter`): W -= scaling * B A."""
+        if not getattr(self, "merged", False):
+            return
+        w = self.base_layer.weight
+        A, B, s = self.lora_A["default"].weight, self.lora_B["default"].weight, self.scaling["default"]
+        with torch.no_grad():
+            w.sub_(((B.float() @ A.float()) * s).to(w.dtype))
+        self.merged = False
 
 
 class _LoraModel(nn.Module):
@@ -104,7 +120,9 @@ class PeftModel(nn.Module):
             return getattr(self.base_model.model, name)
 
     def merge_and_unload(self):
+        from . import modules
         model = self.base_model.model
+        modules.drop_weight_caches(model)
         for parent in model.modules():
             for cname, child in list(parent.named_children()):
                 if isinstance(child, LoraLinear):

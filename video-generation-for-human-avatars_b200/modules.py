@@ -13,6 +13,7 @@ The functions `attention_forward`, `block_forward`, `transformer_forward` only r
 the reference's names, so `install()` (api.py) can also bind them onto an instance of the
 reference's own classes (with or without peft LoRA wrappers)."""
 import math
+import weakref
 from dataclasses import dataclass
 from typing import Any, Dict, List, Optional, Tuple
 
@@ -40,16 +41,57 @@ def _strategy_name(s) -> Optional[str]:
 
 
 # ---------------------------------------------------------------------------------------------
+# derived per-module state (weight concatenations, RoPE table, sequence-parallel handle, per-forward K/V views)
+# ---------------------------------------------------------------------------------------------
+# Kept OUTSIDE the modules, keyed weakly by the module object: `copy.deepcopy(model)`, `state_dict()`, pickling and
+# `merge_and_unload()` (torch_utils.py:66-102 deep-copies the whole model for every checkpoint export) never see it --
+# as module attributes the cached concatenations alone would add 1.2 GB to each copy.
+_side_tables = weakref.WeakKeyDictionary()
+
+
+def side(mod) -> dict:
+    d = _side_tables.get(mod)
+    if d is None:
+        d = _side_tables[mod] = {}
+    return d
+
+
+def drop_weight_caches(model) -> None:
+    """Forget every cached weight concatenation / table of `model` and its sub-modules (they are re-built on the
+    next forward).  Called by install / uninstall, LoraLinear.merge and merge_and_unload: those change weights
+    through raw pointers or `.data`, which does not move the tensors' version counters."""
+    for m in model.modules():
+        d = _side_tables.get(m)
+        if d:
+            for k in ("wqkv", "wkv_all", "rope"):
+                d.pop(k, None)
+
+
+# ---------------------------------------------------------------------------------------------
 # parameter access that works for nn.Linear and for a peft lora.Linear wrapper
 # ---------------------------------------------------------------------------------------------
 def linear_parts(mod):
-    """-> (weight, bias, (A, B, scaling) | None)."""
+    """-> (weight, bias, (A, B, scaling) | None).  A wrapper whose adapter has been merged into the base weight
+    (peft `merge_adapter()` keeps the wrapper and sets `merged`) contributes no separate LoRA term."""
     if hasattr(mod, "base_layer"):
         base = mod.base_layer
+        if getattr(mod, "merged", False) or getattr(mod, "disable_adapters", False):
+            return base.weight, base.bias, None
         a = mod.lora_A["default"].weight
         b = mod.lora_B["default"].weight
         return base.weight, base.bias, (a, b, float(mod.scaling["default"]))
     return mod.weight, mod.bias, None
+
+
+def _weights_key(parts):
+    """Identity of a set of (weight, bias, lora) triples for the concatenation caches: storage address and version
+    counter of every tensor plus whether an adapter rides beside it (so unloading / merging adapters re-keys)."""
+    return tuple((w.data_ptr(), w._version, None if b is None else (b.data_ptr(), b._version), lo is not None)
+                 for w, b, lo in parts)
+
+
+def _capturing() -> bool:
+    return torch.cuda.is_available() and torch.cuda.is_current_stream_capturing()
 
 
 def _require_bf16(t: torch.Tensor, what: str):
@@ -72,22 +114,23 @@ def _cached_wqkv(attn):
     """[3D, D] concatenation of the frozen q/k/v weights (+ [3D] biases): one forward GEMM, and the
     [K,N] operand of the fused dgrad.  Re-built if the parameters are replaced or modified in place."""
     parts = [linear_parts(m) for m in (attn.to_q, attn.to_k, attn.to_v)]
-    key = tuple((w.data_ptr(), w._version, None if b is None else (b.data_ptr(), b._version)) for w, b, _ in parts)
-    cache = attn.__dict__.get("_b200_wqkv")
+    key = _weights_key(parts)
+    tab = side(attn)
+    cache = tab.get("wqkv")
     if cache is None or cache[0] != key:
         W = torch.cat([w.detach() for w, _, _ in parts], dim=0).contiguous()
         bias = None
         if parts[0][1] is not None:
             bias = torch.cat([b.detach() for _, b, _ in parts], dim=0).contiguous()
         cache = (key, W, bias)
-        attn.__dict__["_b200_wqkv"] = cache
+        tab["wqkv"] = cache
     return cache[1], cache[2]
 
 
 def _batched_ctx_kv(model, ctx):
     """Project the caption tokens to the attn2 keys / values of EVERY block in one strided-batched GEMM
     (ops.CtxKVFn) and hand each block its column views.  Returns the list of attentions that were given a
-    `_b200_kv` entry (to be cleared after the forward), or [] when the layout does not allow it (then every
+    `side(attn)["kv"]` entry (to be cleared after the forward), or [] when the layout does not allow it (then every
     block projects for itself, exactly as the reference does: attention.py:999-1005)."""
     blocks = list(model.transformer_blocks)
     attns = [blk.attn2 for blk in blocks if blk.attn2 is not None]
@@ -102,9 +145,11 @@ def _batched_ctx_kv(model, ctx):
         return []
     has_bias = parts[0][1] is not None
     has_lora = parts[0][2] is not None
+    tab = side(model)
     for W, b, lo in parts:
         if W.shape != W0.shape or W.requires_grad or (b is not None) != has_bias or (b is not None and b.requires_grad) \
                 or (lo is not None) != has_lora or W.dtype != BF16:
+            tab.pop("wkv_all", None)   # trainable weights change through raw pointers: never keep a stale copy
             return []
     r, scaling = 0, 1.0
     adapters = ()
@@ -113,17 +158,17 @@ def _batched_ctx_kv(model, ctx):
         if any(lo[0].shape[0] != r or lo[2] != scaling for _, _, lo in parts) or r > ops.LORA_PAD:
             return []
         adapters = tuple(lo[0] for _, _, lo in parts) + tuple(lo[1] for _, _, lo in parts)
-    key = tuple((W.data_ptr(), W._version, None if b is None else (b.data_ptr(), b._version)) for W, b, _ in parts)
-    cache = model.__dict__.get("_b200_wkv_all")
+    key = _weights_key(parts)
+    cache = tab.get("wkv_all")
     if cache is None or cache[0] != key:
         Wkv = torch.cat([W.detach() for W, _, _ in parts], dim=0).contiguous()
         bkv = torch.cat([b.detach() for _, b, _ in parts], dim=0).contiguous() if has_bias else None
         cache = (key, Wkv, bkv)
-        model.__dict__["_b200_wkv_all"] = cache
+        tab["wkv_all"] = cache
     G = len(mods)
     outs = ops.CtxKVFn.apply(ctx.reshape(B * L, Dc), cache[1], cache[2], G, float(scaling), int(r), *adapters)
     for i, a in enumerate(attns):
-        a.__dict__["_b200_kv"] = (ctx, outs[2 * i], outs[2 * i + 1])
+        side(a)["kv"] = (ctx, outs[2 * i], outs[2 * i + 1])
     return attns
 
 
@@ -167,7 +212,7 @@ def attention_forward(attn, hidden_states, freqs_cis=None, encoder_hidden_states
     wqn, wkn = attn.q_norm.weight, attn.k_norm.weight
     scale = float(attn.scale)
 
-    sp = attn.__dict__.get("_b200_sp") if is_self else None
+    sp = side(attn).get("sp") if is_self else None
     # a trainable gate cannot ride in the GEMM epilogue (its gradient needs the un-gated output): un-fused below
     gate_out, res_out = gate, res
     if ops.wants_grad(gate):
@@ -183,6 +228,8 @@ def attention_forward(attn, hidden_states, freqs_cis=None, encoder_hidden_states
         if gate is not gate_out:
             y = ops.gate_residual(y, gate_out, rows_per_gate, res_out)
         return y.view(B, Nq, -1)
+    if is_self:
+        side(attn).pop("wqkv", None)   # trainable / adapted projections: a cached concatenation would go stale
     if sp is not None:
         raise B200Error("sequence-sharded attn1 needs frozen, adapter-free attn1 projections and no skip-layer mask")
 
@@ -193,7 +240,7 @@ def attention_forward(attn, hidden_states, freqs_cis=None, encoder_hidden_states
             and res.data_ptr() == x2d.data_ptr() and res.shape == x2d.shape and res.stride() == x2d.stride()):
         join = ops.GradJoin()
     q_pre = apply_linear(attn.to_q, x2d, join=join, join_role="recv")
-    pre = attn.__dict__.get("_b200_kv") if not is_self else None
+    pre = side(attn).get("kv") if not is_self else None
     if pre is not None and pre[0] is encoder_hidden_states:
         k_pre, v = pre[1], pre[2]  # projected once for all blocks by transformer_forward (ops.CtxKVFn)
     else:
@@ -342,7 +389,7 @@ def transformer_forward(model, hidden_states, indices_grid, ref_image_hidden_sta
         tok = hidden_states if hidden_states.is_contiguous() else hidden_states.contiguous()
         # sequence-sharded call: `hidden_states` / `indices_grid` are this rank's contiguous token shard,
         # the conditioning latents are the whole clip
-        sp = model.__dict__.get("_b200_sp")
+        sp = side(model).get("sp")
         tok_off = sp.rank * N if sp is not None else 0
         ops.lerp_condition_(tok, ref_image_hidden_states.to(dt).contiguous(), pose_hidden_states.to(dt).contiguous(),
                             token_offset=tok_off)
@@ -358,14 +405,14 @@ def transformer_forward(model, hidden_states, indices_grid, ref_image_hidden_sta
     # the table depends only on the coordinates: a caller that passes the SAME tensor again (the sampler's 40 steps)
     # gets the cached bf16 cos / sin instead of ~10 element-wise launches over [B, N, D] fp32
     rkey = (indices_grid.data_ptr(), indices_grid._version, tuple(indices_grid.shape), indices_grid.dtype, D)
-    rcache = model.__dict__.get("_b200_rope")
-    if rcache is not None and rcache[0] == rkey and not torch.cuda.is_current_stream_capturing():
+    rcache = side(model).get("rope")
+    if rcache is not None and rcache[0] == rkey and not _capturing():
         freqs = rcache[1]
     else:
         freqs = rope_table(indices_grid, D, cfg_theta, model.positional_embedding_max_pos)
-        if not torch.cuda.is_current_stream_capturing():
+        if not _capturing():
             # (indices_grid itself is kept alive so that its address cannot be reused by another tensor)
-            model.__dict__["_b200_rope"] = (rkey, freqs, indices_grid)
+            side(model)["rope"] = (rkey, freqs, indices_grid)
     t6, emb = adaln_single_forward(model.adaln_single, timestep.flatten())
     t6 = t6.view(B, -1, t6.shape[-1])
     emb = emb.view(B, -1, emb.shape[-1])
@@ -401,7 +448,8 @@ def transformer_forward(model, hidden_states, indices_grid, ref_image_hidden_sta
                           skip_layer_mask=slm, skip_layer_strategy=skip_layer_strategy)
     finally:
         for a in shared_kv:
-            a.__dict__.pop("_b200_kv", None)
+            side(a).pop("kv", None)
+        ops.clear_lora_stage()   # the staged bf16 adapter copies are valid for this forward only
 
     T = emb.shape[1]
     ss = (model.scale_shift_table[None, None] + emb[:, :, None]).reshape(B * T, 2 * D)

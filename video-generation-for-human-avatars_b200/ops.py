@@ -406,6 +406,12 @@ def prestage_lora(adapters) -> None:
             _lora_stage_cache[id(A)] = (a_all[i], b_all[i], A._version)
 
 
+def clear_lora_stage() -> None:
+    """Drop the staged copies (modules.transformer_forward calls this when a forward ends): FusedAdamW updates the
+    adapters through raw pointers, which does not move `_version`, so a staged copy must never outlive its forward."""
+    _lora_stage_cache.clear()
+
+
 def stage_lora(A: torch.Tensor, B: torch.Tensor, scaling: float) -> Tuple[torch.Tensor, torch.Tensor]:
     """A [r, K] -> A_pad [64, K] ; B [N, r] -> (scaling * B)_pad [N, 64], both bf16."""
     hit = _lora_stage_cache.get(id(A))
@@ -435,12 +441,13 @@ class _OnSideStream:
     """with _OnSideStream(*inputs): ... -- runs the body on `side_stream` (after everything queued so far on the
     current stream) and tells the caching allocator that `inputs` are still in use there."""
 
-    def __init__(self, *inputs):
+    def __init__(self, *inputs, enabled=True):
         self.inputs = inputs
         self.ctx = None
+        self.enabled = enabled
 
     def __enter__(self):
-        s = side_stream
+        s = side_stream if self.enabled else None
         if s is None:
             return self
         s.wait_stream(torch.cuda.current_stream())
@@ -488,6 +495,7 @@ class LinearFn(torch.autograd.Function):
         ctx.meta = (has_lora, scaling, rows_per_gate, A.shape[0] if has_lora else 0,
                     b is not None, res is not None)
         ctx.join = (join, join_role)
+        ctx.adapters = (A, B)
         return y
 
     @staticmethod
@@ -510,7 +518,12 @@ class LinearFn(torch.autograd.Function):
         # the rank-r column views make the GEMMs write exactly [r, K] / [N, r] tensors: autograd can take them as
         # .grad without the copy it makes for a slice of a padded buffer
         if has_lora and (need[3] or need[4]):
-            with _OnSideStream(g, dt, x, t):   # only the optimizer reads these: off the critical path when possible
+            # The side stream is only safe when AccumulateGrad takes the returned tensors as `.grad` without touching
+            # them (it then launches nothing): with an existing `.grad` (accumulation, bucket views) autograd adds on
+            # the main stream, unordered against the side stream -- stay on the main stream in that case.
+            pA, pB = ctx.adapters
+            steal = (pA is None or pA.grad is None) and (pB is None or pB.grad is None)
+            with _OnSideStream(g, dt, x, t, enabled=steal):   # only the optimizer reads these: off the critical path
                 if need[3]:
                     dA = gemm(dt[:, :r], x, a_rows_are_k=True, b_rows_are_k=True, out_dtype=torch.float32, split_k=0)
                 if need[4]:

@@ -56,7 +56,8 @@ def train_step(model, batch: dict, scheduler, patchifier, config, prompt_embeds,
     if noise is None:
         noise = torch.randn_like(tokens)
     root = getattr(getattr(model, "base_model", None), "model", None) or model
-    sp = root.__dict__.get("_b200_sp")
+    from .modules import side
+    sp = side(root).get("sp")
     if sp is not None:
         # sequence-sharded step: every rank of the group sees the same clip and timestep and keeps its
         # contiguous token shard; the loss is the per-shard mean (average gradients over the group)
