@@ -92,51 +92,119 @@ class ClockSampler:
 # ---------------------------------------------------------------------------------------------
 # CPU reference arm: the oracle port (plain-torch restatement of the reference), fp32, host cores
 # ---------------------------------------------------------------------------------------------
-def cpu_reference(steps, warmup, quiet=True):
+def cpu_reference(steps, warmup, workload="cfg2", quiet=True):
+    """The oracle port (fp32, all host threads) on the SAME workload as the b200 arm, bounded along the depth: blocks
+    1..27 of the model are identical in shape and cost (block 0 is cheaper in the backward: nothing trainable sits
+    below its attn1, so autograd prunes that branch), so a step is timed on models of 2 and of 3 blocks at the full
+    token geometry of the workload and the whole 28-block step is t2 + 26 * (t3 - t2).  The workload's token count --
+    what the attention cost depends on quadratically -- is not reduced."""
     import torch
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import ref_block as rb
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    cfg = dict(rb.LTXV_2B)
-    b, f, h, w, _ = WORKLOADS["cfg1"]
-    P = rb.init_params(cfg, LORA_RANK, seed=0)
-    P = {k: v.requires_grad_(rb.is_trainable(k)) for k, v in P.items()}
-    batch = rb.synthetic_batch(cfg, b, f, h, w, N_CTX, 1234, VALID_CTX)
+    b, f, h, w, desc = WORKLOADS[workload]
+    forward_only = workload == "cfg4"
     t = torch.tensor([0.4] * b)
-    times = []
-    for i in range(warmup + steps):
-        for v in P.values():
-            v.grad = None
-        t0 = time.perf_counter()
-        loss, _ = rb.train_step_loss(P, cfg, batch["latents"], batch["ref_image_latents"], batch["pose_latents"],
-                                     batch["prompt_embeds"], batch["prompt_mask"], t, batch["noise"])
-        loss.backward()
-        dt = time.perf_counter() - t0
-        if i >= warmup:
-            times.append(dt)
+    per_depth = {}
+    for depth in (2, 3):
+        cfg = dict(rb.LTXV_2B, num_layers=depth)
+        P = rb.init_params(cfg, LORA_RANK, seed=0)
+        P = {k: v.requires_grad_(rb.is_trainable(k) and not forward_only) for k, v in P.items()}
+        batch = rb.synthetic_batch(cfg, b, f, h, w, N_CTX, 1234, VALID_CTX)
+        times = []
+        for i in range(warmup + steps):
+            for v in P.values():
+                v.grad = None
+            t0 = time.perf_counter()
+            if forward_only:
+                with torch.no_grad():
+                    tokens, coords = rb.patchify(batch["latents"])
+                    rb.transformer_forward(P, cfg, tokens.contiguous(), coords.float(), batch["ref_image_latents"],
+                                           batch["pose_latents"], batch["prompt_embeds"].expand(b, -1, -1),
+                                           t[:, None], batch["prompt_mask"].expand(b, -1))
+            else:
+                loss, _ = rb.train_step_loss(P, cfg, batch["latents"], batch["ref_image_latents"], batch["pose_latents"],
+                                             batch["prompt_embeds"], batch["prompt_mask"], t, batch["noise"])
+                loss.backward()
+            dt = time.perf_counter() - t0
+            if i >= warmup:
+                times.append(dt)
+        per_depth[depth] = sum(times) / len(times)
+        del P, batch
+    t_block = per_depth[3] - per_depth[2]
+    sec = per_depth[2] + 26 * t_block
+    evals = 40 if forward_only else 1     # cfg4: a bench step is 40 denoise steps
     tokens = b * f * h * w
-    sec = sum(times) / len(times)
-    return {"value": tokens / sec, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": f"BASELINE config 1: {tokens} latent tokens (25x256x256, bs1), fp32, all 28 blocks, LoRA r=32 + "
-                      f"caption projection fwd+bwd, {steps} timed step(s) after {warmup} warm-up, {sec:.2f} s/step",
-            "ms_per_step": sec * 1e3}
+    return {"value": tokens * evals / (sec * evals), "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{desc}: the full {tokens}-token geometry, fp32, sampled along the depth -- {steps} timed step(s) "
+                      f"after {warmup} warm-up on a 2-block ({per_depth[2]:.2f} s) and a 3-block ({per_depth[3]:.2f} s) model; "
+                      f"whole 28-block step = {per_depth[2]:.2f} s + 26 x {t_block:.2f} s = {sec:.1f} s",
+            "ms_per_step": sec * 1e3 * evals}
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    steps, warmup = min(args.steps, 3), min(args.warmup, 1)
-    cb = cpu_reference(steps, warmup)
+    steps, warmup = max(1, min(args.steps, 2)), max(0, min(args.warmup, 1))
+    cb = cpu_reference(steps, warmup, args.workload)
+    desc = WORKLOADS[args.workload][4]
     line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus,
             "steps": steps, "warmup": warmup, "ms_per_step": cb["ms_per_step"], "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOADS[args.workload][4], "sample": cb["sample"]},
+            "config": {"workload": desc, "sample": cb["sample"],
+                       "note": "one CPU process on the host cores whatever --gpus says (a reported baseline)"},
             "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
+    if args.workload == "cfg4":
+        line["metric"], line["unit"] = "LTXV-2B sampling latent token-evals/s", "latent token-evals/s"
+        line["e2e"]["unit"] = line["cpu_baseline"]["unit"] = line["unit"]
     print(json.dumps(line), flush=True)
+
+
+def gpu_library_baseline(workload, dev, steps=2, warmup=1):
+    """The in-situ GPU comparator BASELINE.md asks for: the reference's block path as plain PyTorch in bf16 on the
+    SAME B200 -- the oracle restatement (bit-equal to the reference's modules in this dtype flow), i.e. cuBLASLt
+    `F.linear` + `F.scaled_dot_product_attention` (attention.py:996-1064) + eager element-wise ops, forward + backward
+    of the same train step (no optimizer update, which only makes it look faster)."""
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import ref_block as rb
+    b, f, h, w, desc = WORKLOADS[workload]
+    cfg = dict(rb.LTXV_2B)
+    P = rb.init_params(cfg, LORA_RANK, seed=0)
+    P = {k: v.to(dev, torch.float32 if "lora_" in k else torch.bfloat16).requires_grad_(rb.is_trainable(k))
+         for k, v in P.items()}
+    batch = {k: v.to(dev) for k, v in rb.synthetic_batch(cfg, b, f, h, w, N_CTX, 1234, VALID_CTX).items()}
+    t = torch.tensor([0.4] * b, device=dev)
+    bf = torch.bfloat16
+
+    def step():
+        for v in P.values():
+            v.grad = None
+        loss, _ = rb.train_step_loss(P, cfg, batch["latents"].to(bf), batch["ref_image_latents"].to(bf),
+                                     batch["pose_latents"].to(bf), batch["prompt_embeds"].to(bf), batch["prompt_mask"], t,
+                                     batch["noise"].to(bf))
+        loss.backward()
+    for _ in range(warmup):
+        step()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    tokens = b * f * h * w
+    del P, batch
+    torch.cuda.empty_cache()
+    return {"value": tokens / (ms / 1e3), "unit": UNIT, "ms_per_step": ms, "steps": steps,
+            "kind": "reference block path as eager PyTorch bf16 on this GPU (oracle/ref_block.py: cuBLASLt F.linear + "
+                    "F.scaled_dot_product_attention + element-wise ATen ops), forward + backward, no optimizer update",
+            "workload": desc}
 
 
 # ---------------------------------------------------------------------------------------------
@@ -219,8 +287,6 @@ def run_b200(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
-    B, F, H, W, desc = WORKLOADS[args.workload]
-    N = F * H * W
     cfg = dict(api.LTXV_2B_CONFIG)
     if args.layers:
         cfg["num_layers"] = args.layers  # debugging only; flagged in the JSON line
@@ -234,14 +300,7 @@ def run_b200(args):
             p.data.copy_(torch.randn(p.shape, generator=g) * 0.02)  # non-zero B: dA != 0
     model.train()
     named = [(n, p) for n, p in model.named_parameters() if p.requires_grad]
-    seq_parallel = args.workload == "cfg5"
-    if seq_parallel and world > 1:
-        # gradients are per-shard partial means: the bucketer averages them
-        api.enable_sequence_parallel(model, mode=args.sp_mode)
     bucketer = GradBucketer(named) if world > 1 else None
-    # the ring's NCCL send/recv hops do not survive stream capture here (the capture hangs, with either capture
-    # error mode): cfg5 runs eagerly
-    use_graph = not args.no_graph and args.workload != "cfg5"
     from b200_ltx import optim
     opt = optim.FusedAdamW([p for _, p in named], lr=1e-4)   # training.py:271 defaults, one launch per step
     sched, patch = api.RectifiedFlowScheduler(), api.SymmetricPatchifier(1)
@@ -251,27 +310,30 @@ def run_b200(args):
         rf_quantile_min, rf_quantile_max = 0.005, 0.999
         transformer_loss_weight = 1.0
 
-    gd = torch.Generator(device="cpu").manual_seed(1234 + (0 if seq_parallel else rank))  # SP ranks share the clip
-    host = {"latents": torch.randn(B, 128, F, H, W, generator=gd).bfloat16().pin_memory(),
-            "pose_latents": torch.randn(B, 128, F, H, W, generator=gd).bfloat16().pin_memory(),
-            "ref_image_latents": torch.randn(B, 128, 1, H, W, generator=gd).bfloat16().pin_memory()}
     prompt = torch.randn(1, N_CTX, cfg["caption_channels"], generator=torch.Generator().manual_seed(5)).bfloat16().to(dev)
     mask = torch.ones(1, N_CTX, dtype=torch.long)
     mask[:, VALID_CTX:] = 0
     mask = mask.to(dev)
-    h2d_bytes = sum(v.numel() * v.element_size() for v in host.values())
     loss_host = torch.empty((), dtype=torch.float32).pin_memory()
 
-    def step(batch):
+    def host_batch(workload, shared_clip):
+        B, F, H, W, _ = WORKLOADS[workload]
+        gd = torch.Generator(device="cpu").manual_seed(1234 + (0 if shared_clip else rank))  # SP ranks share the clip
+        return {"latents": torch.randn(B, 128, F, H, W, generator=gd).bfloat16().pin_memory(),
+                "pose_latents": torch.randn(B, 128, F, H, W, generator=gd).bfloat16().pin_memory(),
+                "ref_image_latents": torch.randn(B, 128, 1, H, W, generator=gd).bfloat16().pin_memory()}
+
+    def step(batch, t=None, noise=None, update=True):
         if bucketer is not None:
             bucketer.zero_grad()
         else:
             opt.zero_grad(set_to_none=True)
-        loss, _, _, _ = train.train_step(model, batch, sched, patch, Cfg, prompt, mask, device=dev)
+        loss, _, _, _ = train.train_step(model, batch, sched, patch, Cfg, prompt, mask, device=dev, t=t, noise=noise)
         loss.backward()
         if bucketer is not None:
             bucketer.finish()
-        opt.step()
+        if update:
+            opt.step()
         return loss.detach()  # no reference to the autograd graph survives the step (CUDA-graph capture needs that)
 
     def sync_all():
@@ -294,7 +356,19 @@ def run_b200(args):
         sync_all()
         return float(ms)
 
+    seq_parallel = args.workload == "cfg5"
+    if seq_parallel and world > 1:
+        # gradients are per-shard partial means: the bucketer averages them
+        api.enable_sequence_parallel(model, mode=args.sp_mode)
+    B, F, H, W, desc = WORKLOADS[args.workload]
+    N = F * H * W
+    host = host_batch(args.workload, seq_parallel)
+    h2d_bytes = sum(v.numel() * v.element_size() for v in host.values())
     resident = {k: v.to(dev) for k, v in host.items()}
+    # the ring's NCCL send/recv hops do not survive stream capture (the capture hangs): ring mode runs eagerly; the
+    # all-gather mode (all_gather / reduce_scatter collectives) is captured like the data-parallel all-reduce
+    use_graph = not args.no_graph and not (seq_parallel and world > 1 and args.sp_mode == "ring")
+
     if args.profile_steps:
         for _ in range(2):
             step(resident)
@@ -308,34 +382,45 @@ def run_b200(args):
         torch.cuda.profiler.stop()
         return
 
-    # warm-up, with every kernel family timed to find the dominant one
+    # warm-up, with every kernel launch timed: per family (time shares) and per kernel shape (the roofline record)
     ops.timer = ops.KernelTimer()
     for _ in range(max(args.warmup, 3)):
         last = step(resident)
     fam = ops.timer.summary()
+    per_kernel = ops.timer.summary(by_kernel=True)
     ops.timer = None
-    dominant = max((f for f in fam if fam[f]["unit"] == "flop"), key=lambda f: fam[f]["ms"])
+    n_warm = max(args.warmup, 3)
     fam_total_ms = sum(x["ms"] for x in fam.values())
     share = {f: round(d["ms"] / fam_total_ms, 4) for f, d in sorted(fam.items(), key=lambda kv: -kv[1]["ms"])}
-    b200_kernel_ms_per_step = fam_total_ms / max(args.warmup, 3)
+    b200_kernel_ms_per_step = fam_total_ms / n_warm
     fam_tflops = {f: round(d["work"] / d["ms"] / 1e9, 1) for f, d in fam.items() if d["unit"] == "flop"}
     fam_gbs = {f: round(d["work"] / d["ms"] / 1e6, 1) for f, d in fam.items() if d["unit"] == "byte"}
+    # the single dominant KERNEL: one (family, launch shape) entry -- never a family of mixed shapes
+    dom_key = max(per_kernel, key=lambda k: per_kernel[k]["ms"])
+    dom_family = per_kernel[dom_key]["family"]
+    top_kernels = {k: {"share": round(d["ms"] / fam_total_ms, 4), "launches_per_step": d["launches"] // n_warm,
+                       ("tflops" if d["unit"] == "flop" else "gbs"): round(d["work"] / d["ms"] / (1e9 if d["unit"] == "flop" else 1e6), 1)}
+                   for k, d in sorted(per_kernel.items(), key=lambda kv: -kv[1]["ms"])[:8]}
 
-    # the dominant family's launches, timed live with CUDA events (eager launches: events cannot sit inside a graph)
-    ops.timer = ops.KernelTimer([dominant], every=5)  # 1-in-5 sampling keeps the event overhead < 1 %
+    # the dominant kernel's launches, timed live with CUDA events (eager launches: events cannot sit inside a graph)
+    n_dom = per_kernel[dom_key]["launches"] // n_warm
+    ops.timer = ops.KernelTimer([dom_family], every=1 if n_dom <= 200 else 5)
     l0 = ops.launch_count
     for _ in range(2):
         step(resident)
     launches = (ops.launch_count - l0) // 2
-    dom = ops.timer.summary()[dominant]
+    dom = ops.timer.summary(by_kernel=True)[dom_key]
     ops.timer = None
 
     graphed = None
+    dp_launch = "eager launches"
     if use_graph:
         # the whole micro-step (zero grads .. optimizer update, DP all-reduce included) as ONE CUDA graph
         graphed = train.GraphedTrainStep(model, opt, sched, patch, Cfg, prompt, mask, resident, bucketer=bucketer,
-                                         device=dev, side_work=not args.no_side_stream)
+                                         device=dev, side_work=not args.no_side_stream,
+                                         dp_mode=args.dp_mode)
         launches = graphed.launches
+        dp_launch = graphed.describe()
 
     # timed region 1: device-resident inputs
     sampler = ClockSampler(torch.cuda.current_device() if "CUDA_VISIBLE_DEVICES" not in os.environ else local)
@@ -365,12 +450,16 @@ def run_b200(args):
     value = tokens_step / (ms_total / args.steps / 1e3)
     e2e_value = tokens_step / (ms_e2e / args.steps / 1e3)
     peaks = load_peaks()
-    achieved = dom["work"] / (dom["ms"] / 1e3) / 1e12
-    traffic = None
+    is_flop = dom["unit"] == "flop"
+    achieved = dom["work"] / (dom["ms"] / 1e3) / (1e12 if is_flop else 1e9)
+    peak = peaks["tflops"] if is_flop else peaks["gbs"]
+    traffic, traffic_src = None, None
     tp = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tp):
-        traffic = json.load(open(tp)).get(dominant)
+        tj = json.load(open(tp))
+        traffic, traffic_src = tj.get(dom_key, tj.get(dom_family)), tj.get("_source")
 
+    line = None
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps, "higher_is_better": True,
@@ -383,19 +472,23 @@ def run_b200(args):
                            "optimizer": f"AdamW (b200 single-launch kernel) on {sum(p.numel() for _, p in named) / 1e6:.1f}M trainable "
                                         "params, inside the timed step", "train_mode": args.train_mode,
                            "parallelism": f"sp{world} ({args.sp_mode} attn1)" if seq_parallel else f"dp{world}",
-                           "launch": ("eager launches" if graphed is None else
-                                      "whole micro-step replayed as one CUDA graph" if world == 1 else
-                                      "two CUDA graphs (zero+fwd+bwd | optimizer) around the eager NCCL bucket all-reduce"),
+                           "launch": dp_launch,
                            "l2": "not flushed: every step streams 3.85 GB of weights plus >10 GB of activations, far larger than the 126 MB L2"},
                 "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
                         "h2d_bytes_per_step": h2d_bytes * world, "d2h_bytes_per_step": 4 * world},
                 "gpu_launches": launches,
-                "roofline": {"kernel": dominant, "bound": "tensor", "achieved": achieved, "peak": peaks["tflops"],
-                             "unit": "TFLOP/s", "frac": achieved / peaks["tflops"], "traffic": traffic,
-                             "peak_source": peaks["source"], "launches_timed": dom["launches"],
-                             "avg_launch_ms": dom["ms"] / dom["launches"],
-                             "time_share_by_family": share, "b200_kernel_ms_per_step": b200_kernel_ms_per_step,
-                             "family_tflops": fam_tflops, "family_gbs": fam_gbs},
+                # ONE kernel: the (family, launch shape) with the largest share of the step, from its own algorithmic
+                # work and its own CUDA-event time inside eager steps of this run
+                "roofline": {"kernel": dom_key, "bound": "tensor" if is_flop else "hbm", "achieved": achieved, "peak": peak,
+                             "unit": "TFLOP/s" if is_flop else "GB/s", "frac": achieved / peak, "traffic": traffic,
+                             "traffic_source": traffic_src, "peak_source": peaks["source"],
+                             "launches_timed": dom["launches"], "avg_launch_ms": dom["ms"] / dom["launches"],
+                             "share_of_step": top_kernels.get(dom_key, {}).get("share")},
+                # context for the record above (not the roofline claim): per kernel shape and per family
+                "kernels": {"top_by_time": top_kernels, "time_share_by_family": share,
+                            "b200_kernel_ms_per_step": b200_kernel_ms_per_step, "family_tflops": fam_tflops,
+                            "family_gbs": fam_gbs,
+                            "gemm_family_frac_of_peak": round(fam_tflops.get("gemm", 0.0) / peaks["tflops"], 4)},
                 # BASELINE metric, second half: attention TFLOP/s against the bf16 tensor peak (attn1 = the
                 # 3D-RoPE self-attention flash kernels; algorithmic FLOPs 4 / 8 x B H Nq Nk 64)
                 "attention": {"attn1_fwd_tflops": fam_tflops.get("fa_fwd"), "attn1_bwd_tflops": fam_tflops.get("fa_bwd"),
@@ -407,12 +500,111 @@ def run_b200(args):
                 "clocks": clocks, "loss": float(last)}
         if args.layers:
             line["config"]["INVALID_reduced_layers"] = True
-        if world == 1 and not args.no_cpu_baseline:
-            cb = cpu_reference(2, 1)
-            line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
-        print(json.dumps(line), flush=True)
+
+    # ---- extra records: never allowed to take the headline line down with them ----------------------------------
+    def emit(extra=None):
+        if rank == 0:
+            if extra:
+                line.update(extra)
+            print(json.dumps(line), flush=True)
+
+    watchdog = None
+    if not args.no_extras:
+        # a hung collective in an extra record must not cost the headline number: after the deadline every rank
+        # leaves, rank 0 printing what it has
+        def bail():
+            emit({"extras_error": "extra records timed out; headline line is complete"})
+            os._exit(0)
+        watchdog = threading.Timer(args.extras_timeout, bail)
+        watchdog.daemon = True
+        watchdog.start()
+    extras = {}
+    try:
+        if not args.no_extras and world == 1 and args.workload == "cfg2" and args.train_mode == "lora_audio":
+            del graphed
+            extras["gpu_library_baseline"] = gpu_library_baseline(args.workload, dev)
+        if not args.no_extras and world > 1 and args.workload == "cfg2" and args.train_mode == "lora_audio":
+            del graphed
+            extras["cfg3"] = dp_sub_record(args, world, rank, dev, model, opt, bucketer, sched, patch, Cfg, prompt, mask,
+                                           host_batch, timed, train)
+            extras["long_clip"] = long_clip_sub_record(args, world, rank, dev, model, opt, bucketer, sched, patch, Cfg,
+                                                       prompt, mask, host_batch, timed, step, api, train, dist)
+    except Exception as e:  # noqa: BLE001
+        extras["extras_error"] = f"{type(e).__name__}: {e}"[:300]
+    if watchdog is not None:
+        watchdog.cancel()
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cb = cpu_reference(1, 0, args.workload)
+        extras["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
+    emit(extras)
     if world > 1:
         dist.destroy_process_group()
+
+
+def dp_sub_record(args, world, rank, dev, model, opt, bucketer, sched, patch, Cfg, prompt, mask, host_batch, timed,
+                  train):
+    """BASELINE config 3 under the same launch: bs4 per GPU at 97x512x512 (4 x 3328 tokens), data parallel."""
+    import torch
+    B, F, H, W, desc = WORKLOADS["cfg3"]
+    host = host_batch("cfg3", False)
+    resident = {k: v.to(dev) for k, v in host.items()}
+    g = train.GraphedTrainStep(model, opt, sched, patch, Cfg, prompt, mask, resident, bucketer=bucketer, device=dev,
+                               dp_mode=args.dp_mode)
+    g()
+    steps = max(2, min(args.steps, 5))
+    ms = timed(lambda: g(), steps) / steps
+    out = {"workload": desc, "parallelism": f"dp{world}", "ms_per_step": ms,
+           "value": B * F * H * W * world / (ms / 1e3), "unit": UNIT, "steps": steps, "launch": g.describe(),
+           "loss": float(g.loss)}
+    del g
+    torch.cuda.empty_cache()
+    return out
+
+
+def long_clip_sub_record(args, world, rank, dev, model, opt, bucketer, sched, patch, Cfg, prompt, mask, host_batch,
+                         timed, step, api, train, dist):
+    """BASELINE config 5 under the same launch: ONE 257x512x768 clip (12672 tokens) sequence-sharded over all ranks,
+    against the same clip un-sharded on one GPU (every rank runs that replica, so the 1-GPU time comes from this run),
+    with the loss difference between the two as an in-run parity check."""
+    import torch
+    B, F, H, W, desc = WORKLOADS["cfg5"]
+    N = F * H * W
+    if N % world:
+        return {"workload": desc, "skipped": f"{N} tokens do not divide by {world} ranks"}
+    host = host_batch("cfg5", True)
+    resident = {k: v.to(dev) for k, v in host.items()}
+    gen = torch.Generator(device="cpu").manual_seed(77)
+    t = torch.tensor([0.45], device=dev)
+    noise = torch.randn(B, N, 128, generator=gen).bfloat16().to(dev)
+    # un-sharded replica on every rank (no gradient exchange: the bucketer would average identical gradients)
+    loss_full = step(resident, t=t, noise=noise, update=False)
+    steps = max(2, min(args.steps, 3))
+    ms_1gpu = timed(lambda: step(resident, update=False), steps) / steps
+    api.enable_sequence_parallel(model, mode=args.sp_mode)
+    try:
+        loss_sp = step(resident, t=t.clone(), noise=noise, update=False).float()   # mean over this rank's shard
+        dist.all_reduce(loss_sp)
+        loss_sp /= world
+        use_graph = args.sp_mode == "gather" and not args.no_graph
+        if use_graph:
+            g = train.GraphedTrainStep(model, opt, sched, patch, Cfg, prompt, mask, resident, bucketer=bucketer,
+                                       device=dev, dp_mode=args.dp_mode)
+            g()
+            ms = timed(lambda: g(), steps) / steps
+            launch = g.describe()
+            del g
+        else:
+            ms = timed(lambda: step(resident), steps) / steps
+            launch = "eager launches"
+    finally:
+        api.enable_sequence_parallel(model, group=None, mode=args.sp_mode, disable=True)
+    torch.cuda.empty_cache()
+    return {"workload": desc, "parallelism": f"sp{world} ({args.sp_mode} attn1)", "scaling": "strong",
+            "ms_per_step": ms, "ms_per_step_1gpu_unsharded": ms_1gpu, "value": B * N / (ms / 1e3), "unit": UNIT,
+            "strong_scaling_efficiency": ms_1gpu / (world * ms), "steps": steps, "launch": launch,
+            "parity": {"loss_unsharded": float(loss_full), "loss_sharded_mean": float(loss_sp),
+                       "rel_diff": abs(float(loss_sp) - float(loss_full)) / abs(float(loss_full)),
+                       "what": "same clip, timestep and noise; mean over ranks of the per-shard losses vs the un-sharded loss"}}
 
 
 def main():
@@ -431,6 +623,12 @@ def main():
     ap.add_argument("--no-side-stream", action="store_true",
                     help="captured step: keep the LoRA weight-gradient GEMMs on the main stream (A/B switch)")
     ap.add_argument("--no-graph", action="store_true", help="launch the step kernel by kernel instead of replaying a CUDA graph")
+    ap.add_argument("--dp-mode", default="one_graph", choices=["one_graph", "two_graphs"],
+                    help="N > 1: capture the bucket all-reduces inside the step graph (overlapped with the backward), or "
+                         "two graphs around an eager all-reduce")
+    ap.add_argument("--no-extras", action="store_true",
+                    help="skip the extra records (N = 1: GPU library baseline; N > 1: cfg3 and long-clip sub-records)")
+    ap.add_argument("--extras-timeout", type=float, default=240.0)
     ap.add_argument("--profile-steps", type=int, default=0,
                     help="ncu helper: run this many eager steps after 2 warm-up steps and exit (no JSON line)")
     args = ap.parse_args()

@@ -248,3 +248,124 @@ def test_full_train_mode_gradients_vs_oracle():
                    "proj_out.weight", "caption_projection.linear_1.weight"):
         assert needle in names, needle
     assert "ff.net" not in names and "patchify_proj" not in names
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# round 2: parity at the depths / geometries BASELINE.json names, and the branches that had no GPU test
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.gpu
+def test_cfg2_full_depth_28_blocks_6144_tokens():
+    """THE headline configuration (BASELINE config 2): LTXV-2B, all 28 blocks (transformer3d.py:501-551), 6144 latent
+    tokens, 256 caption tokens with 15 valid, LoRA r=32 on attn2 + trainable caption projection; velocity output, loss
+    and all 228 trainable gradients against the fp32 oracle run on the same GPU, two-sided bf16 tolerance."""
+    cfg = dict(rb.LTXV_2B)
+    case = dict(b=1, f=16, h=16, w=24, n_ctx=256, valid_ctx=15, lora_rank=32, seed_w=9, seed_x=23, t=[0.45])
+    res = mc.run_parity(cfg, case, verbose=False)
+    e_o, e_r, m_o, m_r = res["velocity output"]
+    grads = {k: v for k, v in res.items() if k.startswith("grad ")}
+    worst = max(grads, key=lambda k: grads[k][0] / max(2 * grads[k][1], mc.GRAD_FLOOR))
+    print(f"  28 blocks x 6144 tokens: velocity E_ours={e_o:.3e} E_ref_bf16={e_r:.3e} (maxabs {m_o:.2e} / {m_r:.2e}); "
+          f"loss E_ours={res['loss'][0]:.3e}; {len(grads)} gradients, worst ratio to its bound: {worst} "
+          f"E_ours={grads[worst][0]:.3e} E_ref={grads[worst][1]:.3e}")
+    assert len(grads) == 28 * 8 + 4
+
+
+@pytest.mark.gpu
+def test_cfg3_geometry_batch4_full_width():
+    """BASELINE config 3 per-GPU shape: batch 4 x (97x512x512 -> 13x16x16 = 3328 tokens), full width, 2 blocks."""
+    cfg = dict(rb.LTXV_2B, num_layers=2)
+    case = dict(b=4, f=13, h=16, w=16, n_ctx=256, valid_ctx=15, lora_rank=32, seed_w=10, seed_x=29,
+                t=[0.2, 0.45, 0.7, 0.93])
+    mc.run_parity(cfg, case, verbose=False)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,f,h,w", [("cfg4", 16, 15, 22), ("cfg5", 33, 16, 24)])
+def test_sampling_and_long_clip_geometries_forward(name, f, h, w):
+    """BASELINE config 4 (121x480x704 -> 16x15x22 = 5280 tokens: ragged against the 128-row tiles, fractional
+    coordinates, per-token timesteps with a conditioned first frame) and config 5 (257x512x768 -> 12672 tokens),
+    forward only, full width, 2 blocks, against the fp32 oracle."""
+    cfg = dict(rb.LTXV_2B, num_layers=2)
+    case = dict(b=1, f=f, h=h, w=w, n_ctx=256, valid_ctx=15, seed_w=11, seed_x=31, t=[0.6], per_token_t=(name == "cfg4"))
+    mc.run_forward_parity(cfg, case)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("strategy", [rb.STG_ATTENTION_SKIP, rb.STG_ATTENTION_VALUES, rb.STG_TRANSFORMER_BLOCK])
+def test_stg_skip_layer_strategies_vs_oracle(strategy):
+    """attention.py:1071-1086 / 312-319: two conditions (text, perturbed), the perturbed one skipping blocks 0 and 2
+    (block 1 keeps the fused attn1 node: create_skip_layer_mask notes host-side which rows differ from all-ones)."""
+    cfg = dict(rb.LTXV_2B, num_layers=3, num_attention_heads=4, cross_attention_dim=256, caption_channels=64)
+    case = dict(b=2, f=3, h=5, w=7, n_ctx=24, valid_ctx=15, seed_w=12, seed_x=37, t=[0.8, 0.8])
+    res = mc.run_forward_parity(cfg, case, skip_layer_strategy=strategy, skip_blocks=[0, 2])
+    plain = mc.run_forward_parity(cfg, case, verbose=False)
+    ours, _ = res["_tensors"]
+    ours_plain, _ = plain["_tensors"]
+    assert mc.rel(ours[0], ours_plain[0]) < 1e-6          # the text condition is untouched
+    assert mc.rel(ours[1], ours_plain[1]) > 1e-3          # the perturbed one is not
+
+
+@pytest.mark.gpu
+def test_gradient_checkpoint_branch_matches_plain_backward():
+    """transformer3d.py:503-534: `model.training and gradient_checkpointing` runs every block under
+    torch.utils.checkpoint(use_reentrant=False).  The recomputed forward goes through the same autograd Functions
+    (GradJoin side channel, NormModResFn's aliased residual output): loss and all gradients must equal the
+    non-checkpointed step bit for bit, and stay inside the oracle tolerance."""
+    cfg = dict(rb.LTXV_2B, num_layers=3, num_attention_heads=4, cross_attention_dim=256, caption_channels=64)
+    case = dict(b=2, f=3, h=4, w=8, n_ctx=64, valid_ctx=40, lora_rank=32, seed_w=13, seed_x=41, t=[0.3, 0.6])
+    mc.run_parity(cfg, dict(case, gradient_checkpointing=True), verbose=False)
+    P = rb.init_params(cfg, 32, seed=13)
+    P = {k: (v if "lora_" in k else v.to(torch.bfloat16).float()) for k, v in P.items()}
+    batch = rb.synthetic_batch(cfg, 2, 3, 4, 8, 64, 41, 40)
+    t = torch.tensor(case["t"])
+    model = mc.build_b200_model(cfg, P, 32).train()
+    l0, g0 = mc.b200_loss_grads(model, batch, t)
+    g0 = {k: v.clone() for k, v in g0.items()}
+    model.base_model.model.gradient_checkpointing = True
+    l1, g1 = mc.b200_loss_grads(model, batch, t)
+    assert torch.equal(l0, l1)
+    assert set(g0) == set(g1)
+    for k in g0:
+        # split-K LoRA weight gradients are fp32 atomics: equal up to summation order
+        assert mc.rel(g1[k], g0[k]) < 1e-5, (k, mc.rel(g1[k], g0[k]))
+
+
+@pytest.mark.gpu
+def test_installed_model_survives_deepcopy_merge_state_dict_and_remerge_forward():
+    """torch_utils.py:66-102: deepcopy(model) -> merge_and_unload() -> state_dict() on a model that has already run
+    (weight-concatenation / RoPE caches filled); and ADVICE r1: forward -> merge -> forward on the same object must
+    see the merged attn2 K/V weights (batched caption-K/V cache re-keyed)."""
+    import copy
+    from b200_ltx import modules
+    cfg = dict(rb.LTXV_2B, num_layers=2, num_attention_heads=4, cross_attention_dim=256, caption_channels=64)
+    P = rb.init_params(cfg, 32, seed=14)
+    P = {k: (v if "lora_" in k else v.to(torch.bfloat16).float()) for k, v in P.items()}
+    model = mc.build_b200_model(cfg, P, 32).eval()
+    b = rb.synthetic_batch(cfg, 2, 3, 4, 8, 64, 43, 40)
+    tokens, coords = rb.patchify(b["latents"])
+    args = lambda: (tokens.contiguous().cuda().bfloat16(), coords.cuda(), b["ref_image_latents"].cuda().bfloat16(),  # noqa: E731
+                    b["pose_latents"].cuda().bfloat16(), b["prompt_embeds"].expand(2, -1, -1).cuda().bfloat16(),
+                    torch.tensor([0.5, 0.5], device="cuda"))
+    kw = dict(encoder_attention_mask=b["prompt_mask"].expand(2, -1).cuda(), return_dict=False)
+    with torch.no_grad():
+        with_adapters = model(*args(), **kw)[0]
+    root = model.base_model.model
+    assert modules.side(root).get("wkv_all") is not None and modules.side(root).get("rope") is not None
+    mem0 = torch.cuda.memory_allocated()
+    clone = copy.deepcopy(model)
+    n_param_bytes = sum(p.numel() * p.element_size() for p in model.parameters())
+    assert torch.cuda.memory_allocated() - mem0 < 1.25 * n_param_bytes + (8 << 20)   # parameters only, no caches
+    merged = clone.merge_and_unload()
+    sd = merged.state_dict()
+    assert set(sd) == set(rb.param_shapes(cfg, 0))
+    with torch.no_grad():
+        out_merged = merged(*args(), **kw)[0]
+        again = model(*args(), **kw)[0]
+    assert torch.equal(again, with_adapters)
+    assert mc.rel(out_merged, with_adapters) < 1.5e-2
+    # same object: forward (caches filled above) -> merge in place -> forward
+    base = model.merge_and_unload()
+    with torch.no_grad():
+        out2 = base(*args(), **kw)[0]
+    assert mc.rel(out2, with_adapters) < 1.5e-2, mc.rel(out2, with_adapters)
+    assert torch.equal(out2, out_merged)

@@ -99,7 +99,7 @@ def qknorm_rope_fwd(xq, xk, wq, wk, cos, sin, oq, ok, eps=1e-5):
         o.copy_(n.to(o.dtype))
 
 
-def fa_fwd(q, k, v, B, H, Nq, Nk, key_bias=None, scale=0.125, need_lse=True):
+def fa_fwd(q, k, v, B, H, Nq, Nk, key_bias=None, scale=0.125, need_lse=True, attn1=None):
     D = H * 64
     qh = q[:, :D].float().reshape(B, Nq, H, 64).transpose(1, 2)
     kh = k[:, :D].float().reshape(B, Nk, H, 64).transpose(1, 2)

@@ -1,4 +1,6 @@
-"""Micro-benchmark of the flash-attention kernels at the LTXV shapes (warm, CUDA events, L2 flushed)."""
+"""Micro-benchmark of the flash-attention kernels at the LTXV shapes (warm, CUDA events, L2 flushed), with the
+library comparator on the same box and clocks: F.scaled_dot_product_attention (what the reference calls,
+attention.py:1057) through every backend this torch build offers for the shape, forward and forward+backward."""
 import os
 import sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -42,3 +44,29 @@ for (name, B, Nq, Nk, bias) in [("attn1 cfg2", 1, 6144, 6144, False), ("attn1 cf
     tb = timeit(lambda: ops.fa_bwd(q, k, v, o, do, lse, B, H, Nq, Nk, dk, dv, kb, 0.125, delta=delta, dq_accum=dq))
     fl = 4.0 * B * H * Nq * Nk * 64
     print(f"{name:28s} fwd {tf*1e3:8.1f} us {fl/tf/1e9:7.1f} TF/s   bwd {tb*1e3:8.1f} us {2*fl/tb/1e9:7.1f} TF/s", flush=True)
+    if os.environ.get("B200_NO_SDPA"):
+        continue
+    import torch.nn.functional as F
+    from torch.nn.attention import SDPBackend, sdpa_kernel
+    qh = q.view(B, Nq, H, 64).transpose(1, 2).detach().requires_grad_(True)
+    kh = k.view(B, Nk, H, 64).transpose(1, 2).detach().requires_grad_(True)
+    vh = v.view(B, Nk, H, 64).transpose(1, 2).detach().requires_grad_(True)
+    doh = do.view(B, Nq, H, 64).transpose(1, 2)
+    am = kb.to(torch.bfloat16)[:, None, None, :].expand(B, H, Nq, Nk) if kb is not None else None
+    for bname, be in (("flash", SDPBackend.FLASH_ATTENTION), ("cudnn", SDPBackend.CUDNN_ATTENTION),
+                      ("mem-efficient", SDPBackend.EFFICIENT_ATTENTION)):
+        try:
+            with sdpa_kernel([be]):
+                def fwd():
+                    with torch.no_grad():
+                        return F.scaled_dot_product_attention(qh, kh, vh, attn_mask=am)
+
+                def fwdbwd():
+                    qh.grad = kh.grad = vh.grad = None
+                    F.scaled_dot_product_attention(qh, kh, vh, attn_mask=am).backward(doh)
+                t1 = timeit(fwd, 5)
+                t2 = timeit(fwdbwd, 5)
+            print(f"    torch SDPA {bname:14s} fwd {t1*1e3:8.1f} us {fl/t1/1e9:7.1f} TF/s   bwd (fwd+bwd - fwd) "
+                  f"{(t2-t1)*1e3:8.1f} us {2*fl/max(t2-t1, 1e-6)/1e9:7.1f} TF/s", flush=True)
+        except Exception as e:  # noqa: BLE001
+            print(f"    torch SDPA {bname:14s} not available for this shape: {str(e).splitlines()[0][:90]}", flush=True)

@@ -1,4 +1,5 @@
-"""Micro-benchmark of the GEMM shapes of one LTXV-2B block at cfg2 (M = 6144), warm, CUDA events."""
+"""Micro-benchmark of the GEMM shapes of one LTXV-2B block at cfg2 (M = 6144), warm, CUDA events, L2 flushed; the last
+column is cuBLASLt (torch.matmul / F.linear, no epilogue work beyond the bias) on the same operands, same box."""
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -12,6 +13,18 @@ W_dd, W_fd, W_df, W_3d = r(D, D), r(F, D), r(D, F), r(3 * D, D)
 bias_d, bias_f, bias_3d = r(D), r(F), r(3 * D)
 gate, res, pre = r(1, D), r(M, D), r(M, F)
 big3 = r(M, 3 * D)
+import torch.nn.functional as Fnn
+lib_cases = {
+    "fwd N=2048 K=2048 bias": lambda: Fnn.linear(x, W_dd, bias_d),
+    "fwd N=2048 K=2048 bias+gate+res": lambda: Fnn.linear(x, W_dd, bias_d),
+    "fwd N=6144 K=2048 bias (qkv)": lambda: Fnn.linear(x, W_3d, bias_3d),
+    "fwd N=8192 K=2048 gelu+aux": lambda: Fnn.linear(x, W_fd, bias_f),
+    "fwd N=2048 K=8192 gate+res": lambda: Fnn.linear(xf, W_df, bias_d),
+    "dgrad N=2048 K=2048": lambda: torch.matmul(x, W_dd),
+    "dgrad N=2048 K=6144 (qkv)": lambda: torch.matmul(big3, W_3d),
+    "dgrad N=8192 K=2048 gelu'": lambda: torch.matmul(x, W_df),
+    "dgrad N=2048 K=8192": lambda: torch.matmul(xf, W_fd),
+}
 cases = [
     ("fwd N=2048 K=2048 bias", lambda bn: ops.gemm(x, W_dd, bias=bias_d, block_n=bn), 2 * M * D * D),
     ("fwd N=2048 K=2048 bias+gate+res", lambda bn: ops.gemm(x, W_dd, bias=bias_d, gate=gate, rows_per_gate=M, res=res, block_n=bn), 2 * M * D * D),
@@ -25,6 +38,16 @@ cases = [
 ]
 flush = torch.empty(256 << 20, device=dev, dtype=torch.uint8)
 for name, fn, flops in cases:
+    lf = lib_cases[name]
+    for _ in range(3): lf()
+    ts = []
+    for _ in range(10):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); lf(); e1.record(); torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    ts.sort()
+    print(f"{name:36s} cuBLASLt {ts[len(ts) // 2]*1e3:8.1f} us {flops / ts[len(ts) // 2] / 1e9:8.1f} TF/s (plain GEMM, no fused epilogue)", flush=True)
     for bn in (128, 256):
         for _ in range(3): fn(bn)
         ts = []

@@ -52,15 +52,15 @@ def uninstall(model):
     return model
 
 
-def enable_sequence_parallel(model, group=None, impl=None, mode="ring"):
+def enable_sequence_parallel(model, group=None, impl=None, mode="ring", disable=False):
     """Shard the latent tokens of every forward over the ranks of `group` (BASELINE config 5): the model
     then takes this rank's contiguous shard of `hidden_states` / `indices_grid` and attn1 runs as a
     K/V ring (ring.py; `mode="gather"`: one all-gather of K/V and a single attention launch per layer instead).  Trainable gradients come out as per-shard partial means: average them over the
-    group (dp.GradBucketer does exactly that).  `group=None` with no default group disables it."""
+    group (dp.GradBucketer does exactly that).  `group=None` with no default group, or `disable=True`, switches it off again."""
     from .ring import SequenceParallel
     root = getattr(getattr(model, "base_model", None), "model", None) or model
     sp = None
-    if torch.distributed.is_initialized() and torch.distributed.get_world_size(group) > 1:
+    if not disable and torch.distributed.is_initialized() and torch.distributed.get_world_size(group) > 1:
         sp = SequenceParallel(group, impl, mode)
     modules.side(root)["sp"] = sp
     for blk in root.transformer_blocks:

@@ -48,7 +48,7 @@ class KernelTimer:
         self.families = set(families) if families else None
         self.every = max(1, every)  # time one launch in `every` (event records cost ~2 us each)
         self._seen = 0
-        self.records = []  # (family, work, unit, start_event, end_event)
+        self.records = []  # (family, work, unit, start_event, end_event, detail)
 
     def want(self, family):
         if self.families is not None and family not in self.families:
@@ -56,11 +56,14 @@ class KernelTimer:
         self._seen += 1
         return self._seen % self.every == 0
 
-    def summary(self):
+    def summary(self, by_kernel=False):
+        """Totals per family; `by_kernel=True`: per (family, shape) -- one entry per distinct kernel launch shape, so
+        that a family of many different GEMM shapes is not averaged into one "kernel"."""
         torch.cuda.synchronize()
         out = {}
-        for fam, work, unit, e0, e1 in self.records:
-            d = out.setdefault(fam, {"ms": 0.0, "work": 0.0, "launches": 0, "unit": unit})
+        for fam, work, unit, e0, e1, detail in self.records:
+            key = fam if not by_kernel or not detail else f"{fam} {detail}"
+            d = out.setdefault(key, {"ms": 0.0, "work": 0.0, "launches": 0, "unit": unit, "family": fam})
             d["ms"] += e0.elapsed_time(e1)
             d["work"] += work
             d["launches"] += 1
@@ -70,7 +73,7 @@ class KernelTimer:
 timer: Optional[KernelTimer] = None
 
 
-def _call(family, work, unit, cfn, *args, launches=1):
+def _call(family, work, unit, cfn, *args, launches=1, detail=None):
     """Invoke one C-ABI entry point; optionally bracket it with CUDA events on the current stream."""
     t = timer
     if t is not None and t.want(family):
@@ -78,7 +81,7 @@ def _call(family, work, unit, cfn, *args, launches=1):
         e0.record()
         rc = cfn(*args)
         e1.record()
-        t.records.append((family, work, unit, e0, e1))
+        t.records.append((family, work, unit, e0, e1, detail))
     else:
         rc = cfn(*args)
     _lib.check(rc, cfn.__name__)
@@ -144,7 +147,7 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, a_rows_are_k=False, b_rows_are_k=F
         _p(out), out.stride(0), int(out.dtype == torch.float32), M, N, K, epilogue,
         _p(bias), _p(gate), gate_stride, rows_per_gate, _p(res), res.stride(0) if res is not None else 0,
         _p(aux), aux.stride(0) if aux is not None else 0, block_n, split_k, _p(ws), ws.numel() if ws is not None else 0,
-        _s())
+        _s(), detail=f"{M}x{N}x{K + K2}" + ("t" if b_rows_are_k else "") + ("T" if a_rows_are_k else ""))
     return out
 
 
@@ -242,7 +245,15 @@ def qknorm_rope_bwd(dq, dk, xq, xk, wq, wk, cos, sin, oq, ok, eps=1e-5):
         rows_q, rows_k, D, eps, _s())
 
 
-def fa_fwd(q, k, v, B, H, Nq, Nk, key_bias=None, scale=0.125, need_lse=True):
+def _fa_family(base, Nq, Nk, key_bias, attn1):
+    """attn1 (latent self-attention, also its sequence-sharded form where Nq is the local shard and Nk the shard or all
+    of the clip) vs attn2 (cross-attention to the caption tokens: a key bias, or a few hundred keys)."""
+    if attn1 is None:
+        attn1 = key_bias is None and Nk >= 1024
+    return base if attn1 else base + "_attn2"
+
+
+def fa_fwd(q, k, v, B, H, Nq, Nk, key_bias=None, scale=0.125, need_lse=True, attn1=None):
     """q [B*Nq, >=H*64], k/v [B*Nk, >=H*64] (row-strided views allowed) -> o [B*Nq, H*64], lse."""
     for t, nm in ((q, "q"), (k, "k"), (v, "v")):
         _chk2d(t, "fa_fwd " + nm)
@@ -251,8 +262,9 @@ def fa_fwd(q, k, v, B, H, Nq, Nk, key_bias=None, scale=0.125, need_lse=True):
     if key_bias is not None and (key_bias.dtype != torch.float32 or tuple(key_bias.shape) != (B, Nk)
                                  or not key_bias.is_contiguous()):
         raise _lib.B200Error("fa_fwd: key_bias must be contiguous fp32 [B, Nk]")
-    _call("fa_fwd" if Nq == Nk else "fa_fwd_attn2", 4.0 * B * H * Nq * Nk * 64, "flop", _L().b200_fa_fwd, _p(q), q.stride(0), _p(k), k.stride(0), _p(v), v.stride(0), _p(o), o.stride(0),
-                          _p(lse), _p(key_bias), B, H, Nq, Nk, 64, scale, _s())
+    _call(_fa_family("fa_fwd", Nq, Nk, key_bias, attn1), 4.0 * B * H * Nq * Nk * 64, "flop", _L().b200_fa_fwd,
+          _p(q), q.stride(0), _p(k), k.stride(0), _p(v), v.stride(0), _p(o), o.stride(0),
+          _p(lse), _p(key_bias), B, H, Nq, Nk, 64, scale, _s(), detail=f"{B}x{H}x{Nq}x{Nk}")
     return o, lse
 
 
@@ -269,7 +281,8 @@ def attn_merge(o_acc, lse_acc, o_i, lse_i, B, H, N, first, out=None):
           int(first), _s())
 
 
-def fa_bwd(q, k, v, o, do, lse, B, H, Nq, Nk, dk, dv, key_bias=None, scale=0.125, delta=None, dq_accum=None):
+def fa_bwd(q, k, v, o, do, lse, B, H, Nq, Nk, dk, dv, key_bias=None, scale=0.125, delta=None, dq_accum=None,
+           attn1=None):
     """Returns dq as fp32 [B*Nq, H*64]; writes bf16 dk/dv into the given (possibly strided) views.
     `delta` / `dq_accum` may be supplied to accumulate dq over several key shards (ring attention)."""
     _chk2d(do, "fa_bwd do")
@@ -278,10 +291,11 @@ def fa_bwd(q, k, v, o, do, lse, B, H, Nq, Nk, dk, dv, key_bias=None, scale=0.125
     dq = dq_accum if dq_accum is not None else torch.zeros((B * Nq, H * 64), device=q.device, dtype=torch.float32)
     ws_bytes = _L().b200_fa_bwd_workspace_bytes(B, H, Nq, Nk)
     ws = torch.empty(ws_bytes, device=q.device, dtype=torch.uint8) if ws_bytes else None
-    _call("fa_bwd" if Nq == Nk else "fa_bwd_attn2", 8.0 * B * H * Nq * Nk * 64, "flop", _L().b200_fa_bwd, _p(q), q.stride(0), _p(k), k.stride(0), _p(v), v.stride(0), _p(do), do.stride(0),
-                          _p(lse), _p(delta), _p(key_bias), _p(dq), dq.stride(0), _p(dk), dk.stride(0),
-                          _p(dv), dv.stride(0), B, H, Nq, Nk, 64, scale, _p(ws), ws_bytes, _s(),
-                          launches=2 if ws_bytes else 1)
+    _call(_fa_family("fa_bwd", Nq, Nk, key_bias, attn1), 8.0 * B * H * Nq * Nk * 64, "flop", _L().b200_fa_bwd,
+          _p(q), q.stride(0), _p(k), k.stride(0), _p(v), v.stride(0), _p(do), do.stride(0),
+          _p(lse), _p(delta), _p(key_bias), _p(dq), dq.stride(0), _p(dk), dk.stride(0),
+          _p(dv), dv.stride(0), B, H, Nq, Nk, 64, scale, _p(ws), ws_bytes, _s(),
+          launches=2 if ws_bytes else 1, detail=f"{B}x{H}x{Nq}x{Nk}")
     return dq
 
 
@@ -819,7 +833,7 @@ class SelfAttnFn(torch.autograd.Function):
         qknorm_rope_fwd(qkv[:, :D], qkv[:, D:2 * D], wqn, wkn, cos, sin, qk[:, :D], qk[:, D:])
         kv = None
         if sp is None:
-            o, lse = fa_fwd(qk[:, :D], qk[:, D:], qkv[:, 2 * D:], B, H, N, N, key_bias, scale)
+            o, lse = fa_fwd(qk[:, :D], qk[:, D:], qkv[:, 2 * D:], B, H, N, N, key_bias, scale, attn1=True)
         else:  # sequence-sharded: the local queries meet every rank's keys/values around the ring
             if key_bias is not None:
                 raise _lib.B200Error("ring attn1: a key mask on the sharded self-attention is not built")
@@ -847,7 +861,7 @@ class SelfAttnFn(torch.autograd.Function):
         if sp is None:
             dk_post = torch.empty((M, D), device=dy.device, dtype=BF16)
             dq32 = fa_bwd(qk[:, :D], qk[:, D:], qkv[:, 2 * D:], o, do, lse, B, H, N, N, dk_post, dqkv[:, 2 * D:],
-                          key_bias, scale)
+                          key_bias, scale, attn1=True)
         else:
             from . import ring
             if sp.mode == "gather":

@@ -52,7 +52,7 @@ class LocalAttention:
     implementation with the same methods to exercise the ring logic over gloo."""
 
     def fwd(self, q, k, v, B, H, nq, nk, scale):
-        return ops.fa_fwd(q, k, v, B, H, nq, nk, None, scale)
+        return ops.fa_fwd(q, k, v, B, H, nq, nk, None, scale, attn1=True)
 
     def merge(self, o_acc, lse_acc, o_i, lse_i, B, H, n, first, out):
         ops.attn_merge(o_acc, lse_acc, o_i, lse_i, B, H, n, first, out)
@@ -63,7 +63,7 @@ class LocalAttention:
     def bwd(self, q, k, v, o, do, lse, delta, dq_accum, B, H, nq, nk, scale):
         dk = torch.empty_like(k)
         dv = torch.empty_like(v)
-        ops.fa_bwd(q, k, v, o, do, lse, B, H, nq, nk, dk, dv, None, scale, delta=delta, dq_accum=dq_accum)
+        ops.fa_bwd(q, k, v, o, do, lse, B, H, nq, nk, dk, dv, None, scale, delta=delta, dq_accum=dq_accum, attn1=True)
         return dk, dv
 
 
@@ -161,7 +161,7 @@ def gather_fwd(q, k, v, group, B, H, n_local, scale):
     v_all = torch.empty((world * n_local, D), device=q.device, dtype=q.dtype)
     dist.all_gather_into_tensor(k_all, k.contiguous(), group=group)
     dist.all_gather_into_tensor(v_all, v.contiguous(), group=group)
-    out, lse = ops.fa_fwd(q, k_all, v_all, B, H, n_local, world * n_local, None, scale)
+    out, lse = ops.fa_fwd(q, k_all, v_all, B, H, n_local, world * n_local, None, scale, attn1=True)
     return out, lse, k_all, v_all
 
 
@@ -172,7 +172,7 @@ def gather_bwd(q, k_all, v_all, out, do, lse, group, B, H, n_local, scale):
     D = H * 64
     dk_all = torch.empty_like(k_all)
     dv_all = torch.empty_like(v_all)
-    dq = ops.fa_bwd(q, k_all, v_all, out, do, lse, B, H, n_local, world * n_local, dk_all, dv_all, None, scale)
+    dq = ops.fa_bwd(q, k_all, v_all, out, do, lse, B, H, n_local, world * n_local, dk_all, dv_all, None, scale, attn1=True)
     dk = torch.empty((n_local, D), device=q.device, dtype=k_all.dtype)
     dv = torch.empty((n_local, D), device=q.device, dtype=k_all.dtype)
     dist.reduce_scatter_tensor(dk, dk_all, op=dist.ReduceOp.SUM, group=group)

@@ -94,8 +94,9 @@ class GraphedTrainStep:
 
     def __init__(self, model, optimizer, scheduler, patchifier, config, prompt_embeds, prompt_attention_mask,
                  example_batch: dict, bucketer=None, warmup: int = 3, device=None,
-                 capture_error_mode: str = "global", side_work: bool = True):
+                 capture_error_mode: str = "global", side_work: bool = True, dp_mode: str = "one_graph"):
         self.model, self.opt, self.bucketer = model, optimizer, bucketer
+        self.mode = "single GPU: whole micro-step replayed as one CUDA graph"
         device = device or next(model.parameters()).device
         self.static = {k: v.to(device).clone() for k, v in example_batch.items()}
         args = (scheduler, patchifier, config, prompt_embeds, prompt_attention_mask)
@@ -144,20 +145,34 @@ class GraphedTrainStep:
                 optimizer.zero_grad(set_to_none=True)  # .grad is then allocated from the graph's private pool
                 with torch.cuda.graph(self.graph, stream=main, capture_error_mode=capture_error_mode):
                     self.loss, self.rel_mse, self.nrmse = one_step()
+            elif dp_mode == "one_graph":
+                # data parallel, as specified: ONE graph.  The post-accumulate-grad hooks run during the capture, so
+                # each bucket's NCCL all-reduce is recorded where its last gradient becomes ready -- on NCCL's own
+                # stream, forked from and joined back into the capture by events -- and overlaps the rest of the
+                # backward on every replay; finish() records the join and the 1/world scaling, then the optimizer.
+                # (thread_local: NCCL's watchdog thread may query events of earlier eager collectives meanwhile.)
+                bucketer.overlap = True
+                with torch.cuda.graph(self.graph, capture_error_mode="thread_local"):
+                    self.loss, self.rel_mse, self.nrmse = one_step()
+                self.mode = (f"dp{bucketer.world}: whole micro-step as one CUDA graph, the {len(bucketer.buckets)} bucket "
+                             "all-reduces captured at their gradient-ready points (overlapped with the backward)")
             else:
-                # data parallel: graph 1 = zero grads + forward + backward (no collective is captured: the bucket
-                # hooks only count), then the ~84 MB of gradient buckets are all-reduced eagerly over NCCL
-                # (0.3 ms at NVLink rates, not worth a capture-time dependency on the communicator), then
-                # graph 2 = the optimizer update
+                # fallback: graph 1 = zero grads + forward + backward (the bucket hooks only count), the gradient
+                # buckets all-reduced eagerly over NCCL, graph 2 = the optimizer update
                 bucketer.overlap = False
                 with torch.cuda.graph(self.graph, capture_error_mode=capture_error_mode):
                     self.loss, self.rel_mse, self.nrmse = fwd_bwd()
                 self.graph_opt = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(self.graph_opt, pool=self.graph.pool(), capture_error_mode=capture_error_mode):
                     optimizer.step()
+                self.mode = (f"dp{bucketer.world}: two CUDA graphs (zero+fwd+bwd | optimizer) around the eager NCCL "
+                             "bucket all-reduce")
         finally:
             ops.side_stream = None
         self.launches = ops.launch_count - l0  # b200 kernel launches captured per step
+
+    def describe(self) -> str:
+        return self.mode
 
     def load(self, batch: dict, non_blocking: bool = True):
         for k, dst in self.static.items():
