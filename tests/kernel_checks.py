@@ -255,7 +255,9 @@ def _attn_ref(q, k, v, B, H, Nq, Nk, bias, scale):
 ATTN_CASES = [(1, 2, 128, 128, False), (2, 4, 96, 96, False), (1, 2, 300, 300, False), (2, 4, 96, 24, True),
               (1, 32, 512, 256, True), (1, 4, 1024, 1024, False), (2, 3, 200, 333, True),
               # few key tiles, many query tiles: the backward splits the query walk over several CTAs
-              (1, 4, 1100, 256, True), (1, 32, 1536, 256, True), (2, 2, 1030, 100, False)]
+              (1, 4, 1100, 256, True), (1, 32, 1536, 256, True), (2, 2, 1030, 100, False),
+              # >= 512 keys: the double-buffered forward (ragged last key step, bias path, several ring wraps)
+              (2, 3, 700, 1000, False), (1, 2, 640, 1111, True), (1, 8, 2048, 1536, False), (1, 1, 130, 577, False)]
 
 
 def _mask_bias(kind, B, Nk):
@@ -324,13 +326,14 @@ def check_attention_fwd():
         tag = f"B={B} H={H} Nq={Nq} Nk={Nk} bias={int(use_bias)}"
         _assert_close("fa_fwd o " + tag, o, oref, 8e-3)
         _assert_close("fa_fwd lse " + tag, lse, lref, 1e-3)
-    # large-magnitude scores exercise the lazy rescale
-    B, H, N = 1, 2, 512
-    q, k, v = _randn(N, 128, seed=3, scale=6.0), _randn(N, 128, seed=4, scale=6.0), _randn(N, 128, seed=5)
-    o, lse = ops.fa_fwd(q, k, v, B, H, N, N, None, 0.125)
-    oref, lref = _attn_ref(q, k, v, B, H, N, N, None, 0.125)
-    _assert_close("fa_fwd o (peaked softmax)", o, oref, 1e-2)
-    _assert_close("fa_fwd lse (peaked softmax)", lse, lref, 1e-3)
+    # large-magnitude scores exercise the lazy rescale (N = 256: the few-key kernel, 512 / 1536: the double-buffered one)
+    for N in (256, 512, 1536):
+        B, H = 1, 2
+        q, k, v = _randn(N, 128, seed=3, scale=6.0), _randn(N, 128, seed=4, scale=6.0), _randn(N, 128, seed=5)
+        o, lse = ops.fa_fwd(q, k, v, B, H, N, N, None, 0.125)
+        oref, lref = _attn_ref(q, k, v, B, H, N, N, None, 0.125)
+        _assert_close(f"fa_fwd o (peaked softmax, N={N})", o, oref, 1e-2)
+        _assert_close(f"fa_fwd lse (peaked softmax, N={N})", lse, lref, 1e-3)
     torch.cuda.synchronize()
 
 

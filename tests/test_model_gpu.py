@@ -326,8 +326,10 @@ def test_gradient_checkpoint_branch_matches_plain_backward():
     assert torch.equal(l0, l1)
     assert set(g0) == set(g1)
     for k in g0:
-        # split-K LoRA weight gradients are fp32 atomics: equal up to summation order
-        assert mc.rel(g1[k], g0[k]) < 1e-5, (k, mc.rel(g1[k], g0[k]))
+        # not bit-equal by design: without checkpointing the caption keys / values of all blocks come from one batched
+        # projection whose dgrad reduces over the blocks in fp32 (ops.CtxKVFn), under checkpointing every block
+        # projects for itself and autograd sums bf16 partials; split-K weight gradients are fp32 atomics
+        assert mc.rel(g1[k], g0[k]) < 1.5e-2, (k, mc.rel(g1[k], g0[k]))
 
 
 @pytest.mark.gpu

@@ -49,5 +49,32 @@ def build(force: bool = False, verbose: bool = False) -> str:
     return LIB_PATH
 
 
+def build_variant(name: str, defines, sources=("attn_fwd.cu", "attn_bwd.cu")) -> str:
+    """Kernel experiments: libb200ltx_<name>.so = the default objects with `sources` recompiled under extra -D flags.
+    Selected at run time with B200LTX_LIB=<path> (lib.py); never loaded by default."""
+    build()
+    vdir = os.path.join(OBJ_DIR, "variant_" + name)
+    os.makedirs(vdir, exist_ok=True)
+    objs = []
+    for s in SOURCES:
+        obj = os.path.join(OBJ_DIR, s[:-3] + ".o")
+        if s in sources:
+            obj = os.path.join(vdir, s[:-3] + ".o")
+            cmd = [NVCC, *NVCC_FLAGS, *[f"-D{d}" for d in defines], "-c", os.path.join(CSRC, s), "-o", obj]
+            r = subprocess.run(cmd, capture_output=True, text=True)
+            if r.returncode != 0:
+                raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + r.stdout + r.stderr)
+        objs.append(obj)
+    out = os.path.join(PKG_DIR, f"libb200ltx_{name}.so")
+    r = subprocess.run([NVCC, "-shared", "--cudart", "shared", "-o", out, *objs, "-Xlinker", "-rpath", "-Xlinker",
+                        "/usr/local/cuda/lib64"], capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("link failed:\n" + r.stdout + r.stderr)
+    return out
+
+
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose=True))
+    if len(sys.argv) > 2 and sys.argv[1] == "variant":   # python -m b200_ltx.build variant <name> D1 D2=3 ...
+        print(build_variant(sys.argv[2], sys.argv[3:]))
+    else:
+        print(build(force="--force" in sys.argv, verbose=True))

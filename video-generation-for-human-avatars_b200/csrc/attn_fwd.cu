@@ -25,6 +25,8 @@
 //                   row max (3-input max), lazy rescale (only when the running max grows by > 2^8), exp2, packed
 //                   bf16 P written over the first half of the S columns.  Per-key bias (attn2, ragged steps) is
 //                   staged in shared memory once per step.
+#include <stdlib.h>
+
 #include "api_internal.h"
 #include "common.cuh"
 #include "tmap.h"
@@ -323,6 +325,315 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
   }
 }
 
+// =====================================================================================================================
+// fa_fwd_db_kernel — the attn1 forward (many key steps): S double-buffered in TMEM, Q resident in TMEM.
+//
+// What the round-1 profile showed for the kernel above (ncu warp-state samples, profiles/r04): the four softmax warps of
+// a CTA spend 34 % of their time parked on `s_full` -- with P written in place over S, the tensor pipe cannot start
+// Q K(j+1)^T before softmax(j) has finished and P V(j) has consumed it, so every step pays MMA latency + two barrier
+// round trips serially -- and the MMA warp waits for P 70 % of its time.  Four CTAs per SM hide part of it.
+// Here the dependency is removed instead of hidden:
+//   TMEM (256 columns, 2 CTAs / SM):  S0 64 | S1 64 | O 64 | Q 32 (packed bf16, A operand)
+//   MMA warp:  Q K(0)^T, Q K(1)^T up front; then per step j:  wait P(j) -> O += P(j) V(j) -> S(j+2) = Q K(j+2)^T
+//              into the buffer P(j) just left (in-order tensor pipe).  S(j+1) is complete before softmax(j) ends.
+//   softmax:   ONE TMEM read of the 64 scores of a row into registers (max, exp2, row sum, pack, one TMEM store).
+//   Q in TMEM: both MMAs are TS-form (32 clk at N = 64 instead of 48 for the shared-memory/shared-memory form,
+//              profiles/r02_probes_mma_tmem.md): 256 tensor clocks per 128 x 64 step against 512 of the exp unit.
+//   O rescale (lazy, rare): the softmax warp waits for P V(j-1) through `pv_done` only when it actually rescales.
+// K/V steps travel through a 4-stage TMA ring.
+// =====================================================================================================================
+#ifndef FA2_STAGES
+#define FA2_STAGES 4
+#endif
+#ifndef FA2_POLY
+#define FA2_POLY 0   // of every 8 exponentials, this many run as a degree-3 polynomial on the FMA pipe (0..4)
+#endif
+#ifndef FA2_ROWSUM_MMA
+#define FA2_ROWSUM_MMA 0   // row sums of P from the tensor pipe (a constant ones column appended to V) instead of 64 FADDs
+#endif
+constexpr int FA2_STAGE_BYTES = 2 * FA_BN * 128;                   // K and V tile of one 64-key step
+constexpr int FA2_ONES_BYTES = FA_BN * 128;                        // constant B-operand atom: column 0 = 1, the rest 0
+constexpr int FA2_SMEM = 16384 + FA2_STAGES * FA2_STAGE_BYTES + FA2_ONES_BYTES + 256 + 256;
+constexpr int FA2_THREADS = 192;
+constexpr int FA2_MIN_KEYS = 512;                                  // below: the 4-CTA kernel above (attn2)
+constexpr int FA2_O_COLS = FA2_ROWSUM_MMA ? 80 : 64;               // O | row-sum column (+15 unused) in TMEM
+
+// 2^x for x <= 0 on the FMA pipe: round-to-nearest split x = n + f, f in [-0.5, 0.5], degree-3 polynomial of 2^f
+// (max rel. error ~1e-4, far below the bf16 rounding of P), exponent added in the integer domain.
+__device__ __forceinline__ float ex2_poly(float x) {
+  x = fmaxf(x, -120.f);
+  const float t = x + 12582912.f;                // 1.5 * 2^23: the integer part lands in the low mantissa bits
+  const float f = x - (t - 12582912.f);
+  float p = fmaf(0.0555041f, f, 0.2402265f);
+  p = fmaf(p, f, 0.6931472f);
+  p = fmaf(p, f, 1.0f);
+  return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
+}
+
+// GENERAL: a per-key bias and / or a ragged last key step (the per-key term is staged in shared memory per step)
+template <bool GENERAL>
+__global__ void __launch_bounds__(FA2_THREADS, 2)
+fa_fwd_db_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                 const __grid_constant__ CUtensorMap tmV, const __grid_constant__ FaFwdParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t sbase = smem_u32(smem_raw);
+  const uint32_t sQ = sbase, sKV = sbase + 16384;
+  const uint32_t sOnes = sKV + FA2_STAGES * FA2_STAGE_BYTES;
+  const uint32_t bar = sOnes + FA2_ONES_BYTES;
+  const uint32_t q_full = bar, q_tmem = bar + 8, pv_done0 = bar + 16 /*2*/, s_full0 = bar + 32 /*2*/, p_full0 = bar + 48 /*2*/,
+                 kv_full0 = bar + 64, kv_empty0 = kv_full0 + 8 * FA2_STAGES, tmem_slot = kv_empty0 + 8 * FA2_STAGES;
+  // P V(j) completes phase (j >> 1) of pv_done[j & 1].  Two barriers because a softmax warp only looks at them when it
+  // rescales O: with one barrier its parity test could not tell "P V(j-1) done" from "P V(j-3) done, two phases behind"
+  // (seen on hardware: the epilogue read O before the last P V had landed).  With two, the previous phase of the
+  // barrier it waits on is P V(j-3), which s_full(j) already implies (the score MMA of step j is issued only after the
+  // MMA warp has observed P V(j-2), see below).
+  float* kb_stage = reinterpret_cast<float*>(smem_raw + (bar + 256 - sbase));  // [64] per-key term of the current step
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int qt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+
+  if (FA2_ROWSUM_MMA) {
+    // the ones atom, in the layout TMA gives a V tile (64 key rows of 128 swizzled bytes): element (row, column 0) = 1
+    for (int i = threadIdx.x; i < FA2_ONES_BYTES / 16; i += FA2_THREADS) {
+      const int r = i >> 3, c = i & 7;
+      const uint32_t v0 = (c == (r & 7)) ? 0x00003F80u : 0u;   // bf16 1.0 in the low half: column 0 sits in chunk 0 ^ (r & 7)
+      asm volatile("st.shared.v4.b32 [%0], {%1, %2, %2, %2};" ::"r"(sOnes + i * 16), "r"(v0), "r"(0u) : "memory");
+    }
+    fence_proxy_async_smem();
+  }
+  if (threadIdx.x == 0) {
+    if (sbase & 1023u) {
+      printf("b200 fa_fwd_db: dynamic shared memory base is not 1024-byte aligned\n");
+      __trap();
+    }
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmK);
+    tma_prefetch_desc(&tmV);
+    mbar_init(q_full, 1);
+    mbar_init(q_tmem, 128);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(pv_done0 + 8 * s, 1);
+      mbar_init(s_full0 + 8 * s, 1);
+      mbar_init(p_full0 + 8 * s, 128);
+    }
+    for (int s = 0; s < FA2_STAGES; ++s) {
+      mbar_init(kv_full0 + 8 * s, 1);
+      mbar_init(kv_empty0 + 8 * s, 1);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, 256);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  const uint32_t tS = tmem_base, tO = tmem_base + 128, tQ = tmem_base + 128 + FA2_O_COLS;
+  const int T = p.kv_tiles;
+
+  if (warp == 0 && lane == 0) {
+    mbar_expect_tx(q_full, 16384);
+    tma_load_3d(sQ, &tmQ, q_full, h * 64, qt * 128, b);
+    int s = 0;
+    uint32_t ph = 0;
+    for (int j = 0; j < T; ++j) {
+      mbar_wait(kv_empty0 + 8 * s, ph ^ 1);
+      mbar_expect_tx(kv_full0 + 8 * s, FA2_STAGE_BYTES);
+      tma_load_3d(sKV + s * FA2_STAGE_BYTES, &tmK, kv_full0 + 8 * s, h * 64, j * FA_BN, b);
+      tma_load_3d(sKV + s * FA2_STAGE_BYTES + FA_BN * 128, &tmV, kv_full0 + 8 * s, h * 64, j * FA_BN, b);
+      if (++s == FA2_STAGES) { s = 0; ph ^= 1; }
+    }
+  } else if (warp == 1) {
+    const uint32_t idesc_qk = make_idesc_bf16(128, FA_BN, 0, 0);        // A = Q (TMEM), B = K tile, K-major
+    const uint32_t idesc_pv = make_idesc_bf16(128, FA2_O_COLS, 0, 1);   // A = P (TMEM), B = [V | ones], MN-major
+    const uint64_t dk0 = make_smem_desc(sKV, 16, 1024);
+    mbar_wait(q_tmem, 0);
+    tc_fence_after();
+    int s_qk = 0;            // ring stage of the next Q K^T
+    uint32_t ph_qk = 0;
+    auto issue_qk = [&](int j) {
+      mbar_wait(kv_full0 + 8 * s_qk, ph_qk);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint64_t dk = desc_adv(dk0, s_qk * FA2_STAGE_BYTES);
+        const uint32_t d = tS + (j & 1) * 64;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma_ts(d, tQ + k * 8, desc_adv(dk, k * 32), idesc_qk, k > 0 ? 1u : 0u);
+        umma_commit(s_full0 + 8 * (j & 1));
+      }
+      __syncwarp();
+      if (++s_qk == FA2_STAGES) { s_qk = 0; ph_qk ^= 1; }
+    };
+    issue_qk(0);
+    if (T > 1) issue_qk(1);
+    int s_pv = 0;
+    for (int j = 0; j < T; ++j) {
+      mbar_wait(p_full0 + 8 * (j & 1), (j >> 1) & 1);
+      tc_fence_after();
+      if (elect_one()) {
+        // second 64-wide MN atom of the B operand (columns 64..79 of the N = 80 tile) = the constant ones atom: the
+        // leading-dimension byte offset points from this stage's V tile to it, the k advance walks both alike
+        const uint32_t sV = sKV + s_pv * FA2_STAGE_BYTES + FA_BN * 128;
+        const uint64_t dv = make_smem_desc(sV, FA2_ROWSUM_MMA ? (sOnes - sV) : 8192, 1024);
+        const uint32_t a = tS + (j & 1) * 64;
+#pragma unroll
+        for (int k = 0; k < FA_BN / 16; ++k)  // A = P (bf16x2 packed, 8 TMEM columns per K = 16 step)
+          umma_ts(tO, a + k * 8, desc_adv(dv, k * 2048), idesc_pv, (j > 0 || k > 0) ? 1u : 0u);
+        umma_commit(kv_empty0 + 8 * s_pv);
+        umma_commit(pv_done0 + 8 * (j & 1));
+      }
+      __syncwarp();
+      if (++s_pv == FA2_STAGES) s_pv = 0;
+      if (j + 2 < T) {
+        // S(j+2) overwrites P(j): the score MMA is issued once P V(j) has completed (not merely been issued).  The
+        // tensor pipe has the slack (256 of ~600 clk per step; measured: no cost), S(j+2) is still ready a whole softmax
+        // step early, and every observer of s_full(j+2) thereby knows that P V(j) is done.
+        mbar_wait(pv_done0 + 8 * (j & 1), (j >> 1) & 1);
+        issue_qk(j + 2);
+      }
+    }
+  } else if (warp >= 2) {
+    const int quad = warp & 3;
+    const int row = quad * 32 + lane;
+    const uint32_t lane_bits = (uint32_t)(quad * 32) << 16;
+    // Q row -> TMEM as the packed-bf16 A operand: 128 bytes = 8 swizzled 16-byte chunks = 32 columns
+    mbar_wait(q_full, 0);
+    {
+      uint32_t rq[32];
+#pragma unroll
+      for (int c = 0; c < 8; ++c)
+        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                     : "=r"(rq[c * 4]), "=r"(rq[c * 4 + 1]), "=r"(rq[c * 4 + 2]), "=r"(rq[c * 4 + 3])
+                     : "r"(sQ + sw128_off(row, c)));
+      tmem_st32(tQ + lane_bits, rq);
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(q_tmem);
+    }
+    const float* kb = p.key_bias ? p.key_bias + (int64_t)b * p.Nk : nullptr;
+    const float sl2 = p.scale_log2;
+    const float mul = GENERAL ? 1.f : sl2;
+    float m_used = -INFINITY;
+    float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;
+#pragma unroll 1
+    for (int j = 0; j < T; ++j) {
+      if (GENERAL) {
+        const int key0 = j * FA_BN;
+        named_bar_sync(1, 128);
+        if (row < FA_BN) {
+          const int key = key0 + row;
+          kb_stage[row] = key < p.Nk ? (kb ? kb[key] * kLog2e : 0.f) : -INFINITY;
+        }
+        named_bar_sync(1, 128);
+      }
+      const uint32_t t_row = tS + (j & 1) * 64 + lane_bits;
+      mbar_wait(s_full0 + 8 * (j & 1), (j >> 1) & 1);
+      tc_fence_after();
+      uint32_t r0[32], r1[32];
+      tmem_ld32(t_row, r0);
+      tmem_ld32(t_row + 32, r1);
+      tmem_ld_wait();
+      if (GENERAL) {
+        chunk_add_bias(r0, sl2, kb_stage);
+        chunk_add_bias(r1, sl2, kb_stage + 32);
+      }
+      float a0 = -INFINITY, a1 = -INFINITY, a2 = -INFINITY, a3 = -INFINITY;
+      chunk_max(r0, a0, a1, a2, a3);
+      chunk_max(r1, a0, a1, a2, a3);
+      const float mx = fmaxf(fmaxf(a0, a1), fmaxf(a2, a3)) * mul;
+      const float m_new = fmaxf(m_used, mx);
+      const bool need = m_new > m_used + 8.f;
+      if (__any_sync(0xffffffffu, need)) {
+        // lazy rescale: O and l follow the running max only when it has grown by more than 2^8
+        const float alpha = ex2_approx(m_used - m_new);  // 0 on the first step (m_used = -inf)
+        m_used = m_new;
+        l0 *= alpha; l1 *= alpha; l2 *= alpha; l3 *= alpha;
+        if (j > 0) {
+          // O holds P V(0 .. j-1) and the tensor pipe is not writing it
+          mbar_wait(pv_done0 + 8 * ((j - 1) & 1), ((j - 1) >> 1) & 1);
+          tc_fence_after();
+#pragma unroll 1
+          for (int c = 0; c < FA2_O_COLS / 16; ++c) {
+            uint32_t ro[16];
+            tmem_ld16(tO + lane_bits + c * 16, ro);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 16; ++i) ro[i] = __float_as_uint(__uint_as_float(ro[i]) * alpha);
+            tmem_st16(tO + lane_bits + c * 16, ro);
+          }
+        }
+      }
+      const float neg_m = -m_used;
+      uint32_t pk[32];
+#pragma unroll
+      for (int hf = 0; hf < 2; ++hf) {
+        const uint32_t (&r)[32] = hf ? r1 : r0;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          float pv[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float x = fmaf(__uint_as_float(r[g * 8 + i]), mul, neg_m);
+            pv[i] = (i < FA2_POLY) ? ex2_poly(x) : ex2_approx(x);
+          }
+          if (!FA2_ROWSUM_MMA) {
+            l0 += pv[0] + pv[4];
+            l1 += pv[1] + pv[5];
+            l2 += pv[2] + pv[6];
+            l3 += pv[3] + pv[7];
+          }
+          pk[hf * 16 + g * 4 + 0] = pack_bf16x2(pv[0], pv[1]);
+          pk[hf * 16 + g * 4 + 1] = pack_bf16x2(pv[2], pv[3]);
+          pk[hf * 16 + g * 4 + 2] = pack_bf16x2(pv[4], pv[5]);
+          pk[hf * 16 + g * 4 + 3] = pack_bf16x2(pv[6], pv[7]);
+        }
+      }
+      tmem_st32(t_row, pk);   // P(j): 64 keys as 32 packed columns over the first half of S(j)
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(p_full0 + 8 * (j & 1));
+    }
+    mbar_wait(pv_done0 + 8 * ((T - 1) & 1), ((T - 1) >> 1) & 1);
+    tc_fence_after();
+    float l = (l0 + l1) + (l2 + l3);
+    if (FA2_ROWSUM_MMA) {
+      uint32_t rl[16];
+      tmem_ld16(tO + lane_bits + 64, rl);   // column 64: sum over all keys of the bf16 P the O columns were built from
+      tmem_ld_wait();
+      l = __uint_as_float(rl[0]);
+    }
+    const int q = qt * 128 + row;
+    const float inv_l = 1.f / l;
+    if (q < p.Nq && p.lse) p.lse[((int64_t)b * p.H + h) * p.Nq + q] = (m_used + log2f(l)) * 0.6931471805599453f;
+#pragma unroll 1
+    for (int c = 0; c < 2; ++c) {
+      uint32_t r[32];
+      tmem_ld32(tO + lane_bits + c * 32, r);
+      tmem_ld_wait();
+      if (q < p.Nq) {
+        bf16* orow = p.O + ((int64_t)b * p.Nq + q) * p.ldo + h * 64 + c * 32;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          uint4 u;
+          u.x = pack_bf16x2(__uint_as_float(r[g * 8 + 0]) * inv_l, __uint_as_float(r[g * 8 + 1]) * inv_l);
+          u.y = pack_bf16x2(__uint_as_float(r[g * 8 + 2]) * inv_l, __uint_as_float(r[g * 8 + 3]) * inv_l);
+          u.z = pack_bf16x2(__uint_as_float(r[g * 8 + 4]) * inv_l, __uint_as_float(r[g * 8 + 5]) * inv_l);
+          u.w = pack_bf16x2(__uint_as_float(r[g * 8 + 6]) * inv_l, __uint_as_float(r[g * 8 + 7]) * inv_l);
+          *reinterpret_cast<uint4*>(orow + g * 8) = u;
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 256);
+  }
+}
+
 // 3-D map over a token-major [B, N, ld] bf16 tensor restricted to `width` columns: box 64 x 128 x 1.
 int make_tmap_tokens(CUtensorMap* out, const void* base, int B, int N, int64_t ld, int width,
                      int box_rows) {
@@ -337,6 +648,12 @@ int make_tmap_tokens(CUtensorMap* out, const void* base, int B, int N, int64_t l
 using namespace b200;
 
 static inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+// kernel-experiment switch (tools/attn_bench.py): B200_FA_FWD_SMALL=1 routes every shape to the 4-CTA kernel
+static const bool b200_fa_fwd_force_small = [] {
+  const char* e = getenv("B200_FA_FWD_SMALL");
+  return e && e[0] == '1';
+}();
 
 extern "C" int b200_fa_fwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v,
                            int64_t ldv, void* o, int64_t ldo, float* lse, const float* key_bias,
@@ -362,12 +679,23 @@ extern "C" int b200_fa_fwd(const void* q, int64_t ldq, const void* k, int64_t ld
   p.scale_log2 = scale * kLog2e;
   static bool attr_set = false;
   if (!attr_set) {
-    if (cudaFuncSetAttribute(fa_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_FWD_SMEM) != cudaSuccess)
+    if (cudaFuncSetAttribute(fa_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_FWD_SMEM) != cudaSuccess ||
+        cudaFuncSetAttribute(fa_fwd_db_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FA2_SMEM) != cudaSuccess ||
+        cudaFuncSetAttribute(fa_fwd_db_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FA2_SMEM) != cudaSuccess)
       return launch_status("fa_fwd: cudaFuncSetAttribute");
     cudaFuncSetAttribute(fa_fwd_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(fa_fwd_db_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(fa_fwd_db_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     attr_set = true;
   }
   dim3 grid((Nq + 127) / 128, H, B);
-  fa_fwd_kernel<<<grid, FA_FWD_THREADS, FA_FWD_SMEM, (cudaStream_t)stream>>>(tmQ, tmK, tmV, p);
+  // many key steps (attn1): S double-buffered in TMEM; a few key steps (attn2): four small CTAs per SM
+  if (Nk >= FA2_MIN_KEYS && !b200_fa_fwd_force_small) {
+    if (key_bias != nullptr || Nk % FA_BN != 0)
+      fa_fwd_db_kernel<true><<<grid, FA2_THREADS, FA2_SMEM, (cudaStream_t)stream>>>(tmQ, tmK, tmV, p);
+    else
+      fa_fwd_db_kernel<false><<<grid, FA2_THREADS, FA2_SMEM, (cudaStream_t)stream>>>(tmQ, tmK, tmV, p);
+  } else
+    fa_fwd_kernel<<<grid, FA_FWD_THREADS, FA_FWD_SMEM, (cudaStream_t)stream>>>(tmQ, tmK, tmV, p);
   return launch_status("fa_fwd");
 }
