@@ -40,7 +40,13 @@ struct FaFwdParams {
   float* lse;             // [B, H, Nq], natural log
   const float* key_bias;  // [B, Nk] additive (natural units) or null
   float scale_log2;       // softmax scale * log2(e)
+  // fa_fwd_db_kernel, last partial wave: work items (q tile, head, batch) with linear id >= n_whole are each handled by
+  // `parts` CTAs that walk disjoint ranges of the key steps and leave (O unnormalised fp32, m, l) in `part_ws`
+  // [split item][part][128 rows][FA2_PART_LD floats]; fa_fwd_merge_kernel folds the parts.  n_whole = all items: no split.
+  int q_tiles, n_whole, parts;
+  float* part_ws;
 };
+constexpr int FA2_PART_LD = 66;   // 64 O columns + running max (log2 units) + row sum
 
 // Geometry: 128 queries x 64 keys per step, FOUR CTAs per SM (TMEM 128 columns each: S 64 | O 64, P written in
 // place over the first half of S).  Measured: with one 128 x 128 tile per step and two CTAs per SM the exp unit was
@@ -346,7 +352,13 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
 #define FA2_STAGES 4
 #endif
 #ifndef FA2_POLY
-#define FA2_POLY 0   // of every 8 exponentials, this many run as a degree-3 polynomial on the FMA pipe (0..4)
+#define FA2_POLY 2   // of every 8 exponentials, this many run as a degree-3 polynomial on the FMA pipe (0..4)
+#endif
+#ifndef FA2_POLY_PAIRS
+#define FA2_POLY_PAIRS 1   // > 0: that many PAIRS of every 8 exponentials through the packed polynomial (replaces FA2_POLY)
+#endif
+#ifndef FA2_F32X2
+#define FA2_F32X2 1  // FFMA2 / FADD2 (fp32x2) for the score scaling and the row sum
 #endif
 #ifndef FA2_ROWSUM_MMA
 #define FA2_ROWSUM_MMA 0   // row sums of P from the tensor pipe (a constant ones column appended to V) instead of 64 FADDs
@@ -370,6 +382,21 @@ __device__ __forceinline__ float ex2_poly(float x) {
   return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
 }
 
+// the same for a pair, on packed fp32x2 instructions (FADD2 / FFMA2): ~6 issue slots per exponential instead of 8
+__device__ __forceinline__ float2 ex2_poly2(float2 x) {
+  x.x = fmaxf(x.x, -120.f);
+  x.y = fmaxf(x.y, -120.f);
+  const float2 magic = make_float2(12582912.f, 12582912.f), nmagic = make_float2(-12582912.f, -12582912.f);
+  const float2 t = __fadd2_rn(x, magic);
+  const float2 n = __fadd2_rn(t, nmagic);
+  const float2 f = __fadd2_rn(x, make_float2(-n.x, -n.y));
+  float2 p = __ffma2_rn(make_float2(0.0555041f, 0.0555041f), f, make_float2(0.2402265f, 0.2402265f));
+  p = __ffma2_rn(p, f, make_float2(0.6931472f, 0.6931472f));
+  p = __ffma2_rn(p, f, make_float2(1.0f, 1.0f));
+  return make_float2(__int_as_float(__float_as_int(p.x) + (__float_as_int(t.x) << 23)),
+                     __int_as_float(__float_as_int(p.y) + (__float_as_int(t.y) << 23)));
+}
+
 // GENERAL: a per-key bias and / or a ragged last key step (the per-key term is staged in shared memory per step)
 template <bool GENERAL>
 __global__ void __launch_bounds__(FA2_THREADS, 2)
@@ -389,7 +416,16 @@ fa_fwd_db_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   // MMA warp has observed P V(j-2), see below).
   float* kb_stage = reinterpret_cast<float*>(smem_raw + (bar + 256 - sbase));  // [64] per-key term of the current step
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int qt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+  // work item and key-step range of this CTA
+  int item = blockIdx.x, part = -1, j_begin = 0, j_end = p.kv_tiles;
+  if (item >= p.n_whole) {
+    const int e = item - p.n_whole;
+    item = p.n_whole + e / p.parts;
+    part = e % p.parts;
+    j_begin = (int)((int64_t)part * p.kv_tiles / p.parts);
+    j_end = (int)((int64_t)(part + 1) * p.kv_tiles / p.parts);
+  }
+  const int qt = item % p.q_tiles, h = (item / p.q_tiles) % p.H, b = item / (p.q_tiles * p.H);
 
   if (FA2_ROWSUM_MMA) {
     // the ones atom, in the layout TMA gives a V tile (64 key rows of 128 swizzled bytes): element (row, column 0) = 1
@@ -431,7 +467,7 @@ fa_fwd_db_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
   const uint32_t tS = tmem_base, tO = tmem_base + 128, tQ = tmem_base + 128 + FA2_O_COLS;
-  const int T = p.kv_tiles;
+  const int T = j_end - j_begin;   // key steps of this CTA; step j below is global step j_begin + j
 
   if (warp == 0 && lane == 0) {
     mbar_expect_tx(q_full, 16384);
@@ -441,8 +477,8 @@ fa_fwd_db_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     for (int j = 0; j < T; ++j) {
       mbar_wait(kv_empty0 + 8 * s, ph ^ 1);
       mbar_expect_tx(kv_full0 + 8 * s, FA2_STAGE_BYTES);
-      tma_load_3d(sKV + s * FA2_STAGE_BYTES, &tmK, kv_full0 + 8 * s, h * 64, j * FA_BN, b);
-      tma_load_3d(sKV + s * FA2_STAGE_BYTES + FA_BN * 128, &tmV, kv_full0 + 8 * s, h * 64, j * FA_BN, b);
+      tma_load_3d(sKV + s * FA2_STAGE_BYTES, &tmK, kv_full0 + 8 * s, h * 64, (j_begin + j) * FA_BN, b);
+      tma_load_3d(sKV + s * FA2_STAGE_BYTES + FA_BN * 128, &tmV, kv_full0 + 8 * s, h * 64, (j_begin + j) * FA_BN, b);
       if (++s == FA2_STAGES) { s = 0; ph ^= 1; }
     }
   } else if (warp == 1) {
@@ -520,7 +556,7 @@ fa_fwd_db_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
 #pragma unroll 1
     for (int j = 0; j < T; ++j) {
       if (GENERAL) {
-        const int key0 = j * FA_BN;
+        const int key0 = (j_begin + j) * FA_BN;
         named_bar_sync(1, 128);
         if (row < FA_BN) {
           const int key = key0 + row;
@@ -567,6 +603,41 @@ fa_fwd_db_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       }
       const float neg_m = -m_used;
       uint32_t pk[32];
+#if FA2_F32X2
+      // packed fp32x2 arithmetic (FFMA2 / FADD2): x = s * mul - m and the row sum take one instruction per PAIR of
+      // scores -- the softmax warps are issue-bound between their exponentials, not FMA-pipe bound
+      const float2 mul2 = make_float2(mul, mul), negm2 = make_float2(neg_m, neg_m);
+      float2 la = make_float2(l0, l1), lb = make_float2(l2, l3);
+#pragma unroll
+      for (int hf = 0; hf < 2; ++hf) {
+        const uint32_t (&r)[32] = hf ? r1 : r0;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          float2 pv[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float2 x = __ffma2_rn(make_float2(__uint_as_float(r[g * 8 + 2 * i]), __uint_as_float(r[g * 8 + 2 * i + 1])),
+                                        mul2, negm2);
+#if FA2_POLY_PAIRS
+            if (i < FA2_POLY_PAIRS) {
+              pv[i] = ex2_poly2(x);
+            } else {
+              pv[i].x = ex2_approx(x.x);
+              pv[i].y = ex2_approx(x.y);
+            }
+#else
+            pv[i].x = (2 * i < FA2_POLY) ? ex2_poly(x.x) : ex2_approx(x.x);
+            pv[i].y = (2 * i + 1 < FA2_POLY) ? ex2_poly(x.y) : ex2_approx(x.y);
+#endif
+          }
+          la = __fadd2_rn(la, __fadd2_rn(pv[0], pv[2]));
+          lb = __fadd2_rn(lb, __fadd2_rn(pv[1], pv[3]));
+#pragma unroll
+          for (int i = 0; i < 4; ++i) pk[hf * 16 + g * 4 + i] = pack_bf16x2(pv[i].x, pv[i].y);
+        }
+      }
+      l0 = la.x; l1 = la.y; l2 = lb.x; l3 = lb.y;
+#else
 #pragma unroll
       for (int hf = 0; hf < 2; ++hf) {
         const uint32_t (&r)[32] = hf ? r1 : r0;
@@ -590,6 +661,7 @@ fa_fwd_db_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
           pk[hf * 16 + g * 4 + 3] = pack_bf16x2(pv[6], pv[7]);
         }
       }
+#endif
       tmem_st32(t_row, pk);   // P(j): 64 keys as 32 packed columns over the first half of S(j)
       tmem_st_wait();
       tc_fence_before();
@@ -605,23 +677,38 @@ fa_fwd_db_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       l = __uint_as_float(rl[0]);
     }
     const int q = qt * 128 + row;
-    const float inv_l = 1.f / l;
-    if (q < p.Nq && p.lse) p.lse[((int64_t)b * p.H + h) * p.Nq + q] = (m_used + log2f(l)) * 0.6931471805599453f;
+    if (part >= 0) {
+      // one of several CTAs on this item: leave the un-normalised accumulator and the softmax state for the merge
+      float* dst = p.part_ws + ((((int64_t)(item - p.n_whole) * p.parts + part) * 128) + row) * FA2_PART_LD;
 #pragma unroll 1
-    for (int c = 0; c < 2; ++c) {
-      uint32_t r[32];
-      tmem_ld32(tO + lane_bits + c * 32, r);
-      tmem_ld_wait();
-      if (q < p.Nq) {
-        bf16* orow = p.O + ((int64_t)b * p.Nq + q) * p.ldo + h * 64 + c * 32;
+      for (int c = 0; c < 4; ++c) {
+        uint32_t r[16];
+        tmem_ld16(tO + lane_bits + c * 16, r);
+        tmem_ld_wait();
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          uint4 u;
-          u.x = pack_bf16x2(__uint_as_float(r[g * 8 + 0]) * inv_l, __uint_as_float(r[g * 8 + 1]) * inv_l);
-          u.y = pack_bf16x2(__uint_as_float(r[g * 8 + 2]) * inv_l, __uint_as_float(r[g * 8 + 3]) * inv_l);
-          u.z = pack_bf16x2(__uint_as_float(r[g * 8 + 4]) * inv_l, __uint_as_float(r[g * 8 + 5]) * inv_l);
-          u.w = pack_bf16x2(__uint_as_float(r[g * 8 + 6]) * inv_l, __uint_as_float(r[g * 8 + 7]) * inv_l);
-          *reinterpret_cast<uint4*>(orow + g * 8) = u;
+        for (int i = 0; i < 16; i += 2)
+          *reinterpret_cast<float2*>(dst + c * 16 + i) = make_float2(__uint_as_float(r[i]), __uint_as_float(r[i + 1]));
+      }
+      *reinterpret_cast<float2*>(dst + 64) = make_float2(m_used, l);
+    } else {
+      const float inv_l = 1.f / l;
+      if (q < p.Nq && p.lse) p.lse[((int64_t)b * p.H + h) * p.Nq + q] = (m_used + log2f(l)) * 0.6931471805599453f;
+#pragma unroll 1
+      for (int c = 0; c < 2; ++c) {
+        uint32_t r[32];
+        tmem_ld32(tO + lane_bits + c * 32, r);
+        tmem_ld_wait();
+        if (q < p.Nq) {
+          bf16* orow = p.O + ((int64_t)b * p.Nq + q) * p.ldo + h * 64 + c * 32;
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            uint4 u;
+            u.x = pack_bf16x2(__uint_as_float(r[g * 8 + 0]) * inv_l, __uint_as_float(r[g * 8 + 1]) * inv_l);
+            u.y = pack_bf16x2(__uint_as_float(r[g * 8 + 2]) * inv_l, __uint_as_float(r[g * 8 + 3]) * inv_l);
+            u.z = pack_bf16x2(__uint_as_float(r[g * 8 + 4]) * inv_l, __uint_as_float(r[g * 8 + 5]) * inv_l);
+            u.w = pack_bf16x2(__uint_as_float(r[g * 8 + 6]) * inv_l, __uint_as_float(r[g * 8 + 7]) * inv_l);
+            *reinterpret_cast<uint4*>(orow + g * 8) = u;
+          }
         }
       }
     }
@@ -632,6 +719,55 @@ fa_fwd_db_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     tc_fence_after();
     tmem_dealloc(tmem_base, 256);
   }
+}
+
+// Fold the `parts` partial results of every split item: one warp per query row, two output columns per lane.
+__global__ void __launch_bounds__(256) fa_fwd_merge_kernel(const FaFwdParams p, int n_split) {
+  const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (gw >= n_split * 128) return;
+  const int si = gw >> 7, row = gw & 127;
+  const int item = p.n_whole + si;
+  const int qt = item % p.q_tiles, h = (item / p.q_tiles) % p.H, b = item / (p.q_tiles * p.H);
+  const int q = qt * 128 + row;
+  if (q >= p.Nq) return;
+  const float* src = p.part_ws + (((int64_t)si * p.parts) * 128 + row) * FA2_PART_LD;
+  float M = -INFINITY;
+  for (int t = 0; t < p.parts; ++t) M = fmaxf(M, src[(int64_t)t * 128 * FA2_PART_LD + 64]);
+  float L = 0.f, o0 = 0.f, o1 = 0.f;
+  for (int t = 0; t < p.parts; ++t) {
+    const float* s = src + (int64_t)t * 128 * FA2_PART_LD;
+    const float w = exp2f(s[64] - M);
+    L = fmaf(s[65], w, L);
+    const float2 v = *reinterpret_cast<const float2*>(s + 2 * lane);
+    o0 = fmaf(v.x, w, o0);
+    o1 = fmaf(v.y, w, o1);
+  }
+  const float inv = 1.f / L;
+  *reinterpret_cast<uint32_t*>(p.O + ((int64_t)b * p.Nq + q) * p.ldo + h * 64 + 2 * lane) = pack_bf16x2(o0 * inv, o1 * inv);
+  if (lane == 0 && p.lse) p.lse[((int64_t)b * p.H + h) * p.Nq + q] = (M + log2f(L)) * 0.6931471805599453f;
+}
+
+// How the work items of the attn1 forward are dealt out: `slots` CTAs run concurrently (2 per SM); when the last wave is
+// sparsely filled (cfg2: 1536 items on 296 slots = 5.19 waves, 56 CTAs on 148 SMs for a whole CTA lifetime) its items
+// are split along the keys into `parts` CTAs each, so that the tail costs 1 / parts of a wave.
+static void fa_fwd_plan(int items, int kv_tiles, int* n_whole, int* parts) {
+  static int slots = 0;
+  if (!slots) {
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    slots = 2 * sms;
+  }
+  *n_whole = items;
+  *parts = 1;
+  const int r = items % slots;
+  if (items < slots || r == 0 || r * 4 > slots * 3) return;   // a single wave, or a well-filled last wave
+  int pr = slots / r;
+  if (pr > 8) pr = 8;
+  if (pr > kv_tiles / 8) pr = kv_tiles / 8;                   // at least 8 key steps per part
+  if (pr < 2) return;
+  *n_whole = items - r;
+  *parts = pr;
 }
 
 // 3-D map over a token-major [B, N, ld] bf16 tensor restricted to `width` columns: box 64 x 128 x 1.
@@ -655,9 +791,27 @@ static const bool b200_fa_fwd_force_small = [] {
   return e && e[0] == '1';
 }();
 
+extern "C" int64_t b200_fa_fwd_workspace_bytes(int B, int H, int Nq, int Nk) {
+  if (B <= 0 || H <= 0 || Nq <= 0 || Nk < FA2_MIN_KEYS || b200_fa_fwd_force_small) return 0;
+  int n_whole, parts;
+  const int items = ((Nq + 127) / 128) * H * B;
+  fa_fwd_plan(items, (Nk + FA_BN - 1) / FA_BN, &n_whole, &parts);
+  return (int64_t)(items - n_whole) * parts * 128 * FA2_PART_LD * (int64_t)sizeof(float);
+}
+
+extern "C" int b200_fa_fwd_ws(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, void* o,
+                              int64_t ldo, float* lse, const float* key_bias, int B, int H, int Nq, int Nk, int head_dim,
+                              float scale, void* workspace, int64_t workspace_bytes, void* stream);
+
 extern "C" int b200_fa_fwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v,
                            int64_t ldv, void* o, int64_t ldo, float* lse, const float* key_bias,
                            int B, int H, int Nq, int Nk, int head_dim, float scale, void* stream) {
+  return b200_fa_fwd_ws(q, ldq, k, ldk, v, ldv, o, ldo, lse, key_bias, B, H, Nq, Nk, head_dim, scale, nullptr, 0, stream);
+}
+
+extern "C" int b200_fa_fwd_ws(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, void* o,
+                              int64_t ldo, float* lse, const float* key_bias, int B, int H, int Nq, int Nk, int head_dim,
+                              float scale, void* workspace, int64_t workspace_bytes, void* stream) {
   if (head_dim != 64) return arg_error("fa_fwd: only head_dim 64 is built (LTXV-2B: 32 heads x 64)");
   if (B < 0 || H <= 0 || Nq < 0 || Nk < 0) return arg_error("fa_fwd: bad shape");
   if (B == 0 || Nq == 0) return 0;  // no queries: nothing to do (empty tensors carry null pointers)
@@ -691,10 +845,25 @@ extern "C" int b200_fa_fwd(const void* q, int64_t ldq, const void* k, int64_t ld
   dim3 grid((Nq + 127) / 128, H, B);
   // many key steps (attn1): S double-buffered in TMEM; a few key steps (attn2): four small CTAs per SM
   if (Nk >= FA2_MIN_KEYS && !b200_fa_fwd_force_small) {
+    const int items = (int)(grid.x * grid.y * grid.z);
+    p.q_tiles = (int)grid.x;
+    p.n_whole = items;
+    p.parts = 1;
+    p.part_ws = nullptr;
+    if (workspace != nullptr) {   // without a workspace the last wave simply runs un-split
+      fa_fwd_plan(items, p.kv_tiles, &p.n_whole, &p.parts);
+      const int64_t need = (int64_t)(items - p.n_whole) * p.parts * 128 * FA2_PART_LD * (int64_t)sizeof(float);
+      if (need > workspace_bytes || !al16(workspace)) return arg_error("fa_fwd: workspace too small (see b200_fa_fwd_workspace_bytes)");
+      p.part_ws = (float*)workspace;
+    }
+    const int n_split = items - p.n_whole;
+    const unsigned ctas = (unsigned)(p.n_whole + n_split * p.parts);
     if (key_bias != nullptr || Nk % FA_BN != 0)
-      fa_fwd_db_kernel<true><<<grid, FA2_THREADS, FA2_SMEM, (cudaStream_t)stream>>>(tmQ, tmK, tmV, p);
+      fa_fwd_db_kernel<true><<<ctas, FA2_THREADS, FA2_SMEM, (cudaStream_t)stream>>>(tmQ, tmK, tmV, p);
     else
-      fa_fwd_db_kernel<false><<<grid, FA2_THREADS, FA2_SMEM, (cudaStream_t)stream>>>(tmQ, tmK, tmV, p);
+      fa_fwd_db_kernel<false><<<ctas, FA2_THREADS, FA2_SMEM, (cudaStream_t)stream>>>(tmQ, tmK, tmV, p);
+    if (n_split > 0)
+      fa_fwd_merge_kernel<<<(n_split * 128 * 32 + 255) / 256, 256, 0, (cudaStream_t)stream>>>(p, n_split);
   } else
     fa_fwd_kernel<<<grid, FA_FWD_THREADS, FA_FWD_SMEM, (cudaStream_t)stream>>>(tmQ, tmK, tmV, p);
   return launch_status("fa_fwd");

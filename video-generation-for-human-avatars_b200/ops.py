@@ -262,9 +262,12 @@ def fa_fwd(q, k, v, B, H, Nq, Nk, key_bias=None, scale=0.125, need_lse=True, att
     if key_bias is not None and (key_bias.dtype != torch.float32 or tuple(key_bias.shape) != (B, Nk)
                                  or not key_bias.is_contiguous()):
         raise _lib.B200Error("fa_fwd: key_bias must be contiguous fp32 [B, Nk]")
-    _call(_fa_family("fa_fwd", Nq, Nk, key_bias, attn1), 4.0 * B * H * Nq * Nk * 64, "flop", _L().b200_fa_fwd,
+    ws_bytes = _L().b200_fa_fwd_workspace_bytes(B, H, Nq, Nk)   # > 0: the last wave of CTAs is split along the keys
+    ws = torch.empty(ws_bytes, device=q.device, dtype=torch.uint8) if ws_bytes else None
+    _call(_fa_family("fa_fwd", Nq, Nk, key_bias, attn1), 4.0 * B * H * Nq * Nk * 64, "flop", _L().b200_fa_fwd_ws,
           _p(q), q.stride(0), _p(k), k.stride(0), _p(v), v.stride(0), _p(o), o.stride(0),
-          _p(lse), _p(key_bias), B, H, Nq, Nk, 64, scale, _s(), detail=f"{B}x{H}x{Nq}x{Nk}")
+          _p(lse), _p(key_bias), B, H, Nq, Nk, 64, scale, _p(ws), ws_bytes, _s(), launches=2 if ws_bytes else 1,
+          detail=f"{B}x{H}x{Nq}x{Nk}")
     return o, lse
 
 
