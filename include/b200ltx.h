@@ -93,11 +93,16 @@ int b200_fa_fwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const vo
 /* The same with a caller-owned scratch buffer (16-byte aligned, >= b200_fa_fwd_workspace_bytes(B,H,Nq,Nk); 0 bytes /
  * NULL allowed).  With it, when the (query tile, head, batch) work items fill their last wave of CTAs sparsely, the
  * items of that wave are each split along the keys over several CTAs whose partial (O, max, sum) go through the
- * workspace and are folded by a second small kernel of the same call; results match b200_fa_fwd to rounding. */
+ * workspace and are folded by a second small kernel of the same call; results match b200_fa_fwd to rounding.
+ * batch_keep: optional fp32 [B]; entries equal to 0 get rows of `pass_src` (bf16 [B*Nq, ld_pass]; NULL = the value
+ * rows v, which needs Nq == Nk) as output instead of the attention result -- the spatio-temporal-guidance skips of
+ * attention.py:1071-1086 ("attention values": v, "attention skip": the attention input), mask values 0 / 1: their
+ * CTAs copy one tile and do no attention work. */
 int64_t b200_fa_fwd_workspace_bytes(int B, int H, int Nq, int Nk);
 int b200_fa_fwd_ws(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,
-                   void* o, int64_t ldo, float* lse, const float* key_bias, int B, int H, int Nq, int Nk,
-                   int head_dim, float scale, void* workspace, int64_t workspace_bytes, void* stream);
+                   void* o, int64_t ldo, float* lse, const float* key_bias, const float* batch_keep,
+                   const void* pass_src, int64_t ld_pass, int B, int H, int Nq, int Nk, int head_dim, float scale,
+                   void* workspace, int64_t workspace_bytes, void* stream);
 
 /* Online-softmax merge of a partial attention result (o_i bf16, lse_i) over a disjoint key shard into
  * fp32 accumulators (o_acc, lse_acc); first != 0 initialises them; out (bf16, may be NULL) receives the

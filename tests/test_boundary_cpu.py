@@ -184,3 +184,35 @@ def test_merge_then_forward_uses_merged_weights():
         m2.load_state_dict({k: v for k, v in P.items() if "lora_" not in k}, strict=True)
         no_lora, _ = _run(m2.to(BF16).eval(), inp)
         assert _rel(no_lora, with_adapters) > 3 * _rel(merged, with_adapters)
+
+
+@pytest.mark.parametrize("strategy", ["AttentionSkip", "AttentionValues"])
+def test_fused_stg_skip_host_logic_matches_reference(strategy):
+    """The mirror model's own create_skip_layer_mask marks its rows as 0 / 1, so the attention-level STG skips ride
+    inside the attention launch (batch_keep / pass-through source): host logic against the reference's forward."""
+    from b200_ltx import api, modules
+    ns, cfg, ref_model = _reference_model(0, seed=3, layers=3)
+    inp = _inputs(cfg, frac_coords=True)
+    want, _ = _run(ref_model, inp, skip_layer_mask=ref_model.create_skip_layer_mask(1, 2, 1, [0, 2]),
+                   skip_layer_strategy=getattr(ns.SkipLayerStrategy, strategy))
+    with tk.patched():
+        m = api.build_model(dict(api.LTXV_2B_CONFIG, **cfg), device="cpu")
+        m.load_state_dict({k: v.to(BF16) for k, v in ref_model.state_dict().items()}, strict=True)
+        m = m.eval()
+        calls = []
+        orig = tk.fa_fwd
+
+        def spy(*a, **k):
+            calls.append(k.get("batch_keep") is not None)
+            return orig(*a, **k)
+        from b200_ltx import ops
+        saved = ops.fa_fwd
+        ops.fa_fwd = spy
+        try:
+            got, _ = _run(m, inp, skip_layer_mask=m.create_skip_layer_mask(1, 2, 1, [0, 2]),
+                          skip_layer_strategy=getattr(modules.SkipLayerStrategy, strategy))
+        finally:
+            ops.fa_fwd = saved
+    assert _rel(got, want) < 2e-2, _rel(got, want)
+    # attn1 of blocks 0 and 2 took the in-launch skip, block 1 (all-ones row) and every attn2 did not
+    assert sum(calls) == 2 and len(calls) == 6

@@ -99,7 +99,8 @@ def qknorm_rope_fwd(xq, xk, wq, wk, cos, sin, oq, ok, eps=1e-5):
         o.copy_(n.to(o.dtype))
 
 
-def fa_fwd(q, k, v, B, H, Nq, Nk, key_bias=None, scale=0.125, need_lse=True, attn1=None):
+def fa_fwd(q, k, v, B, H, Nq, Nk, key_bias=None, scale=0.125, need_lse=True, attn1=None, batch_keep=None,
+           pass_src=None):
     D = H * 64
     qh = q[:, :D].float().reshape(B, Nq, H, 64).transpose(1, 2)
     kh = k[:, :D].float().reshape(B, Nk, H, 64).transpose(1, 2)
@@ -108,8 +109,11 @@ def fa_fwd(q, k, v, B, H, Nq, Nk, key_bias=None, scale=0.125, need_lse=True, att
     if key_bias is not None:
         s = s + key_bias.float()[:, None, None, :]
     lse = torch.logsumexp(s, dim=-1)
-    o = torch.softmax(s, dim=-1) @ vh
-    return o.transpose(1, 2).reshape(B * Nq, D).to(BF16), (lse if need_lse else None)
+    o = (torch.softmax(s, dim=-1) @ vh).transpose(1, 2).reshape(B * Nq, D).to(BF16)
+    if batch_keep is not None:
+        src = (pass_src if pass_src is not None else v)[:, :D].reshape(B, Nq, D)
+        o = torch.where(batch_keep.reshape(B, 1, 1) == 0, src, o.view(B, Nq, D)).reshape(B * Nq, D)
+    return o, (lse if need_lse else None)
 
 
 def lerp_condition_(tokens, ref, pose, w_ref=0.85, w_pose=0.5, token_offset=0):

@@ -45,7 +45,24 @@ struct FaFwdParams {
   // [split item][part][128 rows][FA2_PART_LD floats]; fa_fwd_merge_kernel folds the parts.  n_whole = all items: no split.
   int q_tiles, n_whole, parts;
   float* part_ws;
+  // STG "attention values" skip (attention.py:1078-1084): batch entries whose flag is 0 get their value rows as the
+  // attention output (needs Nq == Nk); their CTAs copy one V tile and leave without touching barriers or TMEM
+  const float* batch_keep;   // [B] 1 = attend, 0 = pass `pass_src` through; null = attend everywhere
+  const bf16* pass_src;      // [B*Nq, ld_pass]: the value rows ("attention values") or the attention input ("attention skip")
+  int64_t ld_pass;
 };
+
+// o[rows of this query tile, head h] = pass_src[same rows, head h]   (whole CTA, before any barrier / TMEM set-up)
+__device__ __forceinline__ void fa_copy_values(const FaFwdParams& p, int qt, int h, int b, int nthreads) {
+  for (int idx = threadIdx.x; idx < 128 * 8; idx += nthreads) {
+    const int r = idx >> 3, c8 = (idx & 7) * 8;
+    const int q = qt * 128 + r;
+    if (q >= p.Nq) continue;
+    const uint4 val = *reinterpret_cast<const uint4*>(p.pass_src + ((int64_t)b * p.Nq + q) * p.ld_pass + h * 64 + c8);
+    *reinterpret_cast<uint4*>(p.O + ((int64_t)b * p.Nq + q) * p.ldo + h * 64 + c8) = val;
+    if (p.lse && c8 == 0) p.lse[((int64_t)b * p.H + h) * p.Nq + q] = 0.f;
+  }
+}
 constexpr int FA2_PART_LD = 66;   // 64 O columns + running max (log2 units) + row sum
 
 // Geometry: 128 queries x 64 keys per step, FOUR CTAs per SM (TMEM 128 columns each: S 64 | O 64, P written in
@@ -134,6 +151,10 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
   float* kb_stage = reinterpret_cast<float*>(smem_raw + (bar + 128 - sbase));  // [64] per-key term of the current step
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int qt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+  if (p.batch_keep != nullptr && p.batch_keep[b] == 0.f) {
+    fa_copy_values(p, qt, h, b, FA_FWD_THREADS);
+    return;
+  }
   // Keys whose additive bias is <= -9000 (the reference masks with -10000, transformer3d.py:440-445) have weight
   // exp(-9000) = 0 exactly in fp32: every key step past the last unmasked key is skipped -- bit-identical, and with
   // the real prompt (~15 valid of 256 caption tokens) three of the four steps of attn2 disappear.
@@ -426,6 +447,10 @@ fa_fwd_db_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     j_end = (int)((int64_t)(part + 1) * p.kv_tiles / p.parts);
   }
   const int qt = item % p.q_tiles, h = (item / p.q_tiles) % p.H, b = item / (p.q_tiles * p.H);
+  if (p.batch_keep != nullptr && p.batch_keep[b] == 0.f) {
+    if (part <= 0) fa_copy_values(p, qt, h, b, FA2_THREADS);
+    return;
+  }
 
   if (FA2_ROWSUM_MMA) {
     // the ones atom, in the layout TMA gives a V tile (64 key rows of 128 swizzled bytes): element (row, column 0) = 1
@@ -730,6 +755,7 @@ __global__ void __launch_bounds__(256) fa_fwd_merge_kernel(const FaFwdParams p, 
   const int qt = item % p.q_tiles, h = (item / p.q_tiles) % p.H, b = item / (p.q_tiles * p.H);
   const int q = qt * 128 + row;
   if (q >= p.Nq) return;
+  if (p.batch_keep != nullptr && p.batch_keep[b] == 0.f) return;   // the values were passed through by the main kernel
   const float* src = p.part_ws + (((int64_t)si * p.parts) * 128 + row) * FA2_PART_LD;
   float M = -INFINITY;
   for (int t = 0; t < p.parts; ++t) M = fmaxf(M, src[(int64_t)t * 128 * FA2_PART_LD + 64]);
@@ -800,18 +826,21 @@ extern "C" int64_t b200_fa_fwd_workspace_bytes(int B, int H, int Nq, int Nk) {
 }
 
 extern "C" int b200_fa_fwd_ws(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, void* o,
-                              int64_t ldo, float* lse, const float* key_bias, int B, int H, int Nq, int Nk, int head_dim,
-                              float scale, void* workspace, int64_t workspace_bytes, void* stream);
+                              int64_t ldo, float* lse, const float* key_bias, const float* batch_keep, const void* pass_src,
+                              int64_t ld_pass, int B, int H, int Nq, int Nk, int head_dim, float scale, void* workspace,
+                              int64_t workspace_bytes, void* stream);
 
 extern "C" int b200_fa_fwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v,
                            int64_t ldv, void* o, int64_t ldo, float* lse, const float* key_bias,
                            int B, int H, int Nq, int Nk, int head_dim, float scale, void* stream) {
-  return b200_fa_fwd_ws(q, ldq, k, ldk, v, ldv, o, ldo, lse, key_bias, B, H, Nq, Nk, head_dim, scale, nullptr, 0, stream);
+  return b200_fa_fwd_ws(q, ldq, k, ldk, v, ldv, o, ldo, lse, key_bias, nullptr, nullptr, 0, B, H, Nq, Nk, head_dim, scale,
+                        nullptr, 0, stream);
 }
 
 extern "C" int b200_fa_fwd_ws(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, void* o,
-                              int64_t ldo, float* lse, const float* key_bias, int B, int H, int Nq, int Nk, int head_dim,
-                              float scale, void* workspace, int64_t workspace_bytes, void* stream) {
+                              int64_t ldo, float* lse, const float* key_bias, const float* batch_keep, const void* pass_src,
+                              int64_t ld_pass, int B, int H, int Nq, int Nk, int head_dim, float scale, void* workspace,
+                              int64_t workspace_bytes, void* stream) {
   if (head_dim != 64) return arg_error("fa_fwd: only head_dim 64 is built (LTXV-2B: 32 heads x 64)");
   if (B < 0 || H <= 0 || Nq < 0 || Nk < 0) return arg_error("fa_fwd: bad shape");
   if (B == 0 || Nq == 0) return 0;  // no queries: nothing to do (empty tensors carry null pointers)
@@ -831,6 +860,14 @@ extern "C" int b200_fa_fwd_ws(const void* q, int64_t ldq, const void* k, int64_t
   p.kv_tiles = (Nk + FA_BN - 1) / FA_BN;
   p.O = (bf16*)o; p.ldo = ldo; p.lse = lse; p.key_bias = key_bias;
   p.scale_log2 = scale * kLog2e;
+  p.q_tiles = (Nq + 127) / 128; p.n_whole = 0; p.parts = 1; p.part_ws = nullptr;
+  p.batch_keep = batch_keep;
+  p.pass_src = pass_src ? (const bf16*)pass_src : (const bf16*)v;   // default: the value rows (needs Nq == Nk)
+  p.ld_pass = pass_src ? ld_pass : ldv;
+  if (batch_keep != nullptr && pass_src == nullptr && Nq != Nk)
+    return arg_error("fa_fwd: batch_keep with the value rows as pass-through source needs Nq == Nk");
+  if (batch_keep != nullptr && (p.ld_pass % 8 || p.ld_pass < H * 64 || !al16(p.pass_src)))
+    return arg_error("fa_fwd: pass-through source must be 16-byte aligned with a 16-byte-multiple pitch >= H*64");
   static bool attr_set = false;
   if (!attr_set) {
     if (cudaFuncSetAttribute(fa_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_FWD_SMEM) != cudaSuccess ||

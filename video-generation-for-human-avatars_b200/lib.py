@@ -24,7 +24,7 @@ PROTOTYPES = {
     "b200_gemm_bf16_batched": (I, [P, L, I, P, L, I, P, L, P, L, I, P, L, I, I, I, I, P, I, I, P, P]),
     "b200_fa_fwd": (I, [P, L, P, L, P, L, P, L, P, P, I, I, I, I, I, F, P]),
     "b200_fa_fwd_workspace_bytes": (L, [I, I, I, I]),
-    "b200_fa_fwd_ws": (I, [P, L, P, L, P, L, P, L, P, P, I, I, I, I, I, F, P, L, P]),
+    "b200_fa_fwd_ws": (I, [P, L, P, L, P, L, P, L, P, P, P, P, L, I, I, I, I, I, F, P, L, P]),
     "b200_attn_merge": (I, [P, L, P, P, L, P, P, L, I, I, I, I, P]),
     "b200_attn_delta": (I, [P, L, P, L, P, I, I, I, P]),
     "b200_fa_bwd_workspace_bytes": (L, [I, I, I, I]),

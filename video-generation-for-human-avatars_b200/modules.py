@@ -106,8 +106,10 @@ def apply_linear(mod, x2d, gate=None, rows_per_gate=0, res=None, join=None, join
 
 
 def _frozen_plain(mod) -> bool:
+    """No adapter and no gradient wanted for weight / bias: frozen parameters, or any parameters under no_grad (a
+    freshly loaded sampling model has requires_grad = True everywhere and runs under torch.no_grad())."""
     W, b, lora = linear_parts(mod)
-    return lora is None and not W.requires_grad and (b is None or not b.requires_grad)
+    return lora is None and not ops.wants_grad(W, b)
 
 
 def _cached_wqkv(attn):
@@ -147,7 +149,7 @@ def _batched_ctx_kv(model, ctx):
     has_lora = parts[0][2] is not None
     tab = side(model)
     for W, b, lo in parts:
-        if W.shape != W0.shape or W.requires_grad or (b is not None) != has_bias or (b is not None and b.requires_grad) \
+        if W.shape != W0.shape or ops.wants_grad(W, b) or (b is not None) != has_bias \
                 or (lo is not None) != has_lora or W.dtype != BF16:
             tab.pop("wkv_all", None)   # trainable weights change through raw pointers: never keep a stale copy
             return []
@@ -217,14 +219,24 @@ def attention_forward(attn, hidden_states, freqs_cis=None, encoder_hidden_states
     gate_out, res_out = gate, res
     if ops.wants_grad(gate):
         gate, res = None, None
-    fast = (is_self and skip_layer_mask is None and all(_frozen_plain(m) for m in (attn.to_q, attn.to_k, attn.to_v))
-            and linear_parts(attn.to_out[0])[2] is None and not linear_parts(attn.to_out[0])[0].requires_grad
-            and not wqn.requires_grad and not wkn.requires_grad)
+    # STG skips of whole batch entries ("attention values" / "attention skip", attention.py:1071-1086) ride inside the
+    # attention launch when the mask is known to be 0 / 1 (built by our create_skip_layer_mask) and no gradient is
+    # recorded: the skipped entries' CTAs copy their pass-through rows and do no attention work
+    batch_keep, pass_input = None, False
+    if (is_self and skip_layer_mask is not None and getattr(skip_layer_mask, "_b200_binary", False)
+            and strat in (SkipLayerStrategy.AttentionSkip, SkipLayerStrategy.AttentionValues)
+            and not torch.is_grad_enabled() and sp is None):
+        batch_keep = skip_layer_mask.reshape(B).to(torch.float32).contiguous()
+        pass_input = strat == SkipLayerStrategy.AttentionSkip
+    fast = (is_self and (skip_layer_mask is None or batch_keep is not None)
+            and all(_frozen_plain(m) for m in (attn.to_q, attn.to_k, attn.to_v))
+            and linear_parts(attn.to_out[0])[2] is None and not ops.wants_grad(linear_parts(attn.to_out[0])[0])
+            and not ops.wants_grad(wqn, wkn))
     if fast:
         Wo, bo, _ = linear_parts(attn.to_out[0])
         Wqkv, bqkv = _cached_wqkv(attn)
         y = ops.SelfAttnFn.apply(x2d, Wqkv, bqkv, wqn, wkn, cos, sin, Wo, bo, gate, rows_per_gate, res, kb, B, H,
-                                 Nq, scale, sp)
+                                 Nq, scale, sp, batch_keep, pass_input)
         if gate is not gate_out:
             y = ops.gate_residual(y, gate_out, rows_per_gate, res_out)
         return y.view(B, Nq, -1)
@@ -437,6 +449,8 @@ def transformer_forward(model, hidden_states, indices_grid, ref_image_hidden_sta
             slm = skip_layer_mask[i] if skip_layer_mask is not None else None
             if slm is not None and i not in getattr(skip_layer_mask, "_b200_skip_blocks", (i,)):
                 slm = None  # an all-ones row (see create_skip_layer_mask): nothing is skipped in this block
+            elif slm is not None and hasattr(skip_layer_mask, "_b200_skip_blocks"):
+                slm._b200_binary = True   # our own builder: entries are exactly 0 or 1
             if checkpointing:
                 h = torch.utils.checkpoint.checkpoint(block, h, freqs, attention_mask, ctx, encoder_attention_mask,
                                                       t6, cross_attention_kwargs, class_labels, slm,

@@ -253,8 +253,11 @@ def _fa_family(base, Nq, Nk, key_bias, attn1):
     return base if attn1 else base + "_attn2"
 
 
-def fa_fwd(q, k, v, B, H, Nq, Nk, key_bias=None, scale=0.125, need_lse=True, attn1=None):
-    """q [B*Nq, >=H*64], k/v [B*Nk, >=H*64] (row-strided views allowed) -> o [B*Nq, H*64], lse."""
+def fa_fwd(q, k, v, B, H, Nq, Nk, key_bias=None, scale=0.125, need_lse=True, attn1=None, batch_keep=None,
+           pass_src=None):
+    """q [B*Nq, >=H*64], k/v [B*Nk, >=H*64] (row-strided views allowed) -> o [B*Nq, H*64], lse.
+    batch_keep: optional fp32 [B] of 0 / 1; entries with 0 get rows of `pass_src` [B*Nq, >=H*64] (default: the value
+    rows) as output and cost no attention work (the STG skips of attention.py:1071-1086)."""
     for t, nm in ((q, "q"), (k, "k"), (v, "v")):
         _chk2d(t, "fa_fwd " + nm)
     o = torch.empty((B * Nq, H * 64), device=q.device, dtype=BF16)
@@ -262,11 +265,18 @@ def fa_fwd(q, k, v, B, H, Nq, Nk, key_bias=None, scale=0.125, need_lse=True, att
     if key_bias is not None and (key_bias.dtype != torch.float32 or tuple(key_bias.shape) != (B, Nk)
                                  or not key_bias.is_contiguous()):
         raise _lib.B200Error("fa_fwd: key_bias must be contiguous fp32 [B, Nk]")
+    if batch_keep is not None and (batch_keep.dtype != torch.float32 or batch_keep.numel() != B
+                                   or not batch_keep.is_contiguous() or (pass_src is None and Nq != Nk)):
+        raise _lib.B200Error("fa_fwd: batch_keep must be contiguous fp32 [B] (and Nq == Nk unless pass_src is given)")
+    if pass_src is not None:
+        _chk2d(pass_src, "fa_fwd pass_src")
     ws_bytes = _L().b200_fa_fwd_workspace_bytes(B, H, Nq, Nk)   # > 0: the last wave of CTAs is split along the keys
     ws = torch.empty(ws_bytes, device=q.device, dtype=torch.uint8) if ws_bytes else None
     _call(_fa_family("fa_fwd", Nq, Nk, key_bias, attn1), 4.0 * B * H * Nq * Nk * 64, "flop", _L().b200_fa_fwd_ws,
           _p(q), q.stride(0), _p(k), k.stride(0), _p(v), v.stride(0), _p(o), o.stride(0),
-          _p(lse), _p(key_bias), B, H, Nq, Nk, 64, scale, _p(ws), ws_bytes, _s(), launches=2 if ws_bytes else 1,
+          _p(lse), _p(key_bias), _p(batch_keep), _p(pass_src), pass_src.stride(0) if pass_src is not None else 0,
+          B, H, Nq, Nk, 64, scale, _p(ws), ws_bytes, _s(),
+          launches=2 if ws_bytes else 1,
           detail=f"{B}x{H}x{Nq}x{Nk}")
     return o, lse
 
@@ -829,14 +839,17 @@ class SelfAttnFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, Wqkv, bqkv, wqn, wkn, cos, sin, Wo, bo, gate, rows_per_gate, res, key_bias, B, H, N,
-                scale, sp=None):
+                scale, sp=None, batch_keep=None, pass_input=False):
         M, D = x.shape[0], H * 64
         qkv = gemm(x, Wqkv, bias=bqkv)  # one [M,3D] GEMM against the cached [3D,D] weight concatenation
         qk = torch.empty((M, 2 * D), device=x.device, dtype=BF16)
         qknorm_rope_fwd(qkv[:, :D], qkv[:, D:2 * D], wqn, wkn, cos, sin, qk[:, :D], qk[:, D:])
         kv = None
         if sp is None:
-            o, lse = fa_fwd(qk[:, :D], qk[:, D:], qkv[:, 2 * D:], B, H, N, N, key_bias, scale, attn1=True)
+            # batch_keep (inference only): STG skip of some batch entries inside the attention launch -- their output is
+            # the value rows ("attention values") or the attention input x ("attention skip"), attention.py:1071-1086
+            o, lse = fa_fwd(qk[:, :D], qk[:, D:], qkv[:, 2 * D:], B, H, N, N, key_bias, scale, attn1=True,
+                            batch_keep=batch_keep, pass_src=x if (batch_keep is not None and pass_input) else None)
         else:  # sequence-sharded: the local queries meet every rank's keys/values around the ring
             if key_bias is not None:
                 raise _lib.B200Error("ring attn1: a key mask on the sharded self-attention is not built")
@@ -877,4 +890,4 @@ class SelfAttnFn(torch.autograd.Function):
         qknorm_rope_bwd(dq32, dk_post, qkv[:, :D], qkv[:, D:2 * D], wqn, wkn, cos, sin, dqkv[:, :D], dqkv[:, D:2 * D])
         dx = gemm(dqkv, Wqkv, b_rows_are_k=True) if ctx.needs_input_grad[0] else None
         dres = dy if (has_res and ctx.needs_input_grad[11]) else None
-        return (dx,) + (None,) * 10 + (dres,) + (None,) * 6
+        return (dx,) + (None,) * 10 + (dres,) + (None,) * 8
