@@ -12,6 +12,7 @@ from .scheduler import RectifiedFlowScheduler  # noqa: F401
 from .train import train_step  # noqa: F401
 from .sampling import Denoiser, denoise  # noqa: F401
 from .optim import FusedAdamW  # noqa: F401
+from .io import DeviceFeeder, LatentTripleDataset, collate_latent_triples, shard_indices  # noqa: F401
 
 LTXV_2B_CONFIG = dict(num_attention_heads=32, attention_head_dim=64, in_channels=128, out_channels=128,
                       num_layers=28, cross_attention_dim=2048, attention_bias=True,
