@@ -137,11 +137,13 @@ int b200_fa_bwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const vo
 int b200_norm_mod_fwd(const void* x, int64_t ldx, void* y, int64_t ldy, const void* scale,
                       const void* shift, int64_t mod_stride, int64_t rows, int D,
                       int64_t rows_per_mod, float eps, int layernorm, void* stream);
-/* dx = dres + d(norm_mod)/dx applied to dy  (dres may be NULL). */
+/* dx = dres + d(norm_mod)/dx applied to dy  (dres may be NULL).  prod (bf16 [rows, ldprod], may be NULL) receives
+ * dy * xhat: its column sums per modulation group are d(scale), the column sums of dy are d(shift) -- the gradients
+ * of the AdaLN tables when they train (training.py:75-91, "full" strategy); see b200_colsum_groups. */
 int b200_norm_mod_bwd(const void* dy, int64_t lddy, const void* x, int64_t ldx, const void* scale,
                       int64_t mod_stride, const void* dres, int64_t lddres, void* dx, int64_t lddx,
-                      int64_t rows, int D, int64_t rows_per_mod, float eps, int layernorm,
-                      void* stream);
+                      void* prod, int64_t ldprod, int64_t rows, int D, int64_t rows_per_mod, float eps,
+                      int layernorm, void* stream);
 
 /* q_norm / k_norm (RMSNorm over the full width with weight) followed by interleaved-pair RoPE.
  * cos/sin: bf16 [rows, D] tables (NULL for attn2: no RoPE).  q and k rows are independent row sets.
@@ -150,11 +152,14 @@ int b200_qknorm_rope_fwd(const void* xq, int64_t ldq, const void* xk, int64_t ld
                          const void* wk, const void* cos_t, const void* sin_t, int64_t ldcs, void* oq,
                          int64_t ldoq, void* ok, int64_t ldok, int64_t rows_q, int64_t rows_k, int D,
                          float eps, void* stream);
+/* prod_q / prod_k (bf16, may be NULL): (RoPE^T dq) * xhat_q and the same for k; their column sums are the gradients
+ * of q_norm.weight / k_norm.weight when those train. */
 int b200_qknorm_rope_bwd(const void* dq, int64_t lddq, int dq_is_f32, const void* dk, int64_t lddk,
                          int dk_is_f32, const void* xq, int64_t ldq, const void* xk, int64_t ldk,
                          const void* wq, const void* wk, const void* cos_t, const void* sin_t,
-                         int64_t ldcs, void* oq, int64_t ldoq, void* ok, int64_t ldok, int64_t rows_q,
-                         int64_t rows_k, int D, float eps, void* stream);
+                         int64_t ldcs, void* oq, int64_t ldoq, void* ok, int64_t ldok, void* prod_q,
+                         int64_t ldpq, void* prod_k, int64_t ldpk, int64_t rows_q, int64_t rows_k, int D,
+                         float eps, void* stream);
 
 /* Rectified flow: x_t = (1-t) x0 + t eps, v = eps - x0 (either output may be NULL); t fp32 [batch].
  * Replaces RectifiedFlowScheduler.add_noise / build_velocity_target, rf.py:376-386, 400-426. */
@@ -205,6 +210,13 @@ int b200_rowscale(const void* x, int64_t ldx, const void* g, int64_t gstride, vo
                   int64_t rows, int D, int64_t rows_per_mod, void* stream);
 /* out[n] = sum_m x[m,n]  (bias gradients of the trainable caption projection). */
 int b200_colsum(const void* x, int64_t ldx, float* out, int64_t rows, int N, void* stream);
+/* out[g, n] = sum over the rows of group g (rows_per_group consecutive rows) of a[r, n] * (b ? b[r, n] : 1), fp32
+ * (the call zeroes `out` and reduces 16-row chunks into it at the L2; workspace arguments reserved, may be NULL / 0).
+ * The gradients of whatever is broadcast over tokens when the reference's "full" strategy trains it
+ * (training.py:75-91): AdaLN shift / scale / gate per sample, q_norm / k_norm weights, projection biases. */
+int64_t b200_colsum_groups_workspace_bytes(int64_t rows, int N, int64_t rows_per_group);
+int b200_colsum_groups(const void* a, int64_t lda, const void* b, int64_t ldb, float* out, int64_t rows, int N,
+                       int64_t rows_per_group, void* workspace, int64_t workspace_bytes, void* stream);
 
 #ifdef __cplusplus
 }

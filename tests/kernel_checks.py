@@ -630,7 +630,91 @@ def check_guidance_step():
     torch.cuda.synchronize()
 
 
+def check_full_mode_pieces():
+    """Kernels behind train_mode='full' (training.py:75-91): grouped column sums (plain and of a product), the
+    dy * xhat products of the norm backward kernels, the GEMM epilogue that stashes the pre-gate output, and the
+    autograd Functions' gradients for AdaLN scale / shift / gate and the qk-norm weights."""
+    from b200_ltx import ops
+    # grouped column sums
+    for (rows, N, rpg) in [(6144, 2048, 6144), (4 * 3328, 2048, 3328), (515 * 2, 256, 515), (96, 6144, 32), (40, 64, 8)]:
+        a, b = _randn(rows, N, seed=1), _randn(rows, N, seed=2)
+        got = ops.colsum_groups(a, None, rpg)
+        _assert_close(f"colsum_groups rows={rows} N={N} rpg={rpg}", got, a.float().view(-1, rpg, N).sum(1), 2e-3)
+        got = ops.colsum_groups(a, b, rpg)
+        _assert_close(f"colsum_groups product rows={rows} N={N} rpg={rpg}", got,
+                      (a.float() * b.float()).view(-1, rpg, N).sum(1), 2e-3)
+    # GEMM: stash of the pre-gate output
+    M, N, K = 384, 512, 256
+    a, b = _randn(M, K, seed=1), _randn(N, K, seed=2, scale=0.05)
+    bias, gate, res = _randn(N, seed=5), _randn(3, N, seed=6), _randn(M, N, seed=7)
+    for bn in (0, 64, 128, 256):
+        u = torch.empty(M, N, device="cuda", dtype=BF16)
+        y = ops.gemm(a, b, bias=bias, gate=gate, rows_per_gate=128, res=res, aux=u, epilogue=ops.EPI_STASH, block_n=bn)
+        uref = a.float() @ b.float().t() + bias.float()
+        _assert_close(f"gemm stash u bn={bn}", u, uref, 6e-3)
+        _assert_close(f"gemm stash y bn={bn}", y, gate.float().repeat_interleave(128, 0) * u.float() + res.float(), 6e-3)
+    # NormModResFn with trainable scale / shift (per-sample and per-token modulation), LinearFn / FeedForwardFn gates
+    for (rows, D, rpm, ln) in [(640, 2048, 320, False), (515, 256, 515, True), (130, 2048, 1, False)]:
+        nb = rows // rpm
+        x = _randn(rows, D, seed=1, scale=2.0).requires_grad_(True)
+        ada = _randn(nb, 6 * D, seed=2, scale=0.3).requires_grad_(True)
+        y, xres = ops.NormModResFn.apply(x, ada[:, D:2 * D], ada[:, :D], rpm, 1e-6, ln)
+        dy, dres = _randn(rows, D, seed=3), _randn(rows, D, seed=4)
+        torch.autograd.backward([y, xres], [dy, dres])
+        xf, af = x.detach().float().requires_grad_(True), ada.detach().float().requires_grad_(True)
+        n = F.layer_norm(xf, (D,), None, None, 1e-6) if ln else xf * torch.rsqrt(xf.pow(2).mean(-1, keepdim=True) + 1e-6)
+        yr = n * (1 + af[:, D:2 * D].repeat_interleave(rpm, 0)) + af[:, :D].repeat_interleave(rpm, 0)
+        torch.autograd.backward([yr, xf * 1.0], [dy.float(), dres.float()])
+        tag = f"rows={rows} D={D} rpm={rpm} ln={int(ln)}"
+        _assert_close("NormModResFn dx " + tag, x.grad, xf.grad, 6e-3)
+        _assert_close("NormModResFn d(scale) " + tag, ada.grad[:, D:2 * D], af.grad[:, D:2 * D], 8e-3)
+        _assert_close("NormModResFn d(shift) " + tag, ada.grad[:, :D], af.grad[:, :D], 8e-3)
+        assert float(ada.grad[:, 2 * D:].abs().max()) == 0.0
+    M, K, N = 640, 256, 512
+    x = _randn(M, K, seed=1).requires_grad_(True)
+    W = _randn(N, K, seed=2, scale=0.06).requires_grad_(True)
+    bb = _randn(N, seed=3, scale=0.1).requires_grad_(True)
+    gate = _randn(2, 3 * N, seed=6).requires_grad_(True)
+    res = _randn(M, N, seed=7).requires_grad_(True)
+    dy = _randn(M, N, seed=8)
+    y = ops.LinearFn.apply(x, W, bb, None, None, 1.0, gate[:, N:2 * N], 320, res)
+    y.backward(dy)
+    xr, Wr, br, gr, rr = [t.detach().float().requires_grad_(True) for t in (x, W, bb, gate, res)]
+    yr = gr[:, N:2 * N].repeat_interleave(320, 0) * (xr @ Wr.t() + br) + rr
+    yr.backward(dy.float())
+    _assert_close("LinearFn (trainable gate) y", y, yr, 8e-3)
+    for nm, g, g_ in (("dx", x.grad, xr.grad), ("dW", W.grad, Wr.grad), ("db", bb.grad, br.grad),
+                      ("d(gate)", gate.grad, gr.grad), ("dres", res.grad, rr.grad)):
+        _assert_close("LinearFn (trainable gate) " + nm, g, g_, 1.5e-2)
+    # AttnCoreFn with trainable qk-norm weights: attn1 form (RoPE, paired rows) and attn2 form (no RoPE, Nq != Nk)
+    for (B, H, Nq, Nk, rope) in [(2, 4, 96, 96, True), (1, 4, 200, 72, False)]:
+        D = H * 64
+        q_pre, k_pre, v = [_randn(B * n, D, seed=i).requires_grad_(True) for i, n in ((1, Nq), (2, Nk), (3, Nk))]
+        wq = (1 + 0.1 * _randn(D, seed=4).float()).to(BF16).requires_grad_(True)
+        wk = (1 + 0.1 * _randn(D, seed=5).float()).to(BF16).requires_grad_(True)
+        cos = sin = None
+        if rope:
+            ang = torch.rand(B * Nq, D // 2, device="cuda") * 6.28
+            cos, sin = ang.cos().repeat_interleave(2, -1).to(BF16), ang.sin().repeat_interleave(2, -1).to(BF16)
+        o = ops.AttnCoreFn.apply(q_pre, k_pre, v, wq, wk, cos, sin, None, B, H, Nq, Nk, 0.125)
+        do = _randn(B * Nq, D, seed=6)
+        o.backward(do)
+        ref = [t.detach().float().requires_grad_(True) for t in (q_pre, k_pre, v, wq, wk)]
+
+        def nrm(t, w):
+            y = t * torch.rsqrt(t.pow(2).mean(-1, keepdim=True) + 1e-5) * w
+            return _rope_ref(y, cos.float(), sin.float()) if rope else y
+        oref, _ = _attn_ref(nrm(ref[0], ref[3]), nrm(ref[1], ref[4]), ref[2], B, H, Nq, Nk, None, 0.125)
+        oref.backward(do.float())
+        tag = f"B={B} Nq={Nq} Nk={Nk} rope={int(rope)}"
+        _assert_close("AttnCoreFn (trainable norms) o " + tag, o, oref, 8e-3)
+        for nm, t, tr in zip(("dq_pre", "dk_pre", "dv", "d(q_norm.w)", "d(k_norm.w)"), (q_pre, k_pre, v, wq, wk), ref):
+            _assert_close(f"AttnCoreFn (trainable norms) {nm} " + tag, t.grad, tr.grad, 2e-2)
+    torch.cuda.synchronize()
+
+
 GROUPS = {
+    "full_mode_pieces": check_full_mode_pieces,
     "gemm_layouts": check_gemm_layouts,
     "gemm_epilogues": check_gemm_epilogues,
     "gemm_batched": check_gemm_batched,

@@ -156,7 +156,7 @@ template <int NCH>
 __global__ void __launch_bounds__(128) norm_mod_bwd_row_kernel(
     const bf16* __restrict__ dy, int64_t lddy, const bf16* __restrict__ x, int64_t ldx,
     const bf16* __restrict__ scale, int64_t mod_stride, const bf16* __restrict__ dres,
-    int64_t lddres, bf16* __restrict__ dx, int64_t lddx, int64_t rows, int D,
+    int64_t lddres, bf16* __restrict__ dx, int64_t lddx, bf16* __restrict__ prod, int64_t ldprod, int64_t rows, int D,
     int64_t rows_per_mod, float eps, int ln) {
   __shared__ float red[8];
   const int64_t row = blockIdx.x;
@@ -221,6 +221,12 @@ __global__ void __launch_bounds__(128) norm_mod_bwd_row_kernel(
 #pragma unroll
       for (int i = 0; i < 8; ++i) o.v[i] = rstd * (gv[c].v[i] - gsum - xv[c].v[i] * gx) + r.v[i];
       st_bf16x8(outr + col, o);
+      if (prod) {   // dy * xhat: summed over the rows of a modulation group it is d(scale) (trainable AdaLN tables)
+        const Row8 g0 = unpack8(gp[c]);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o.v[i] = g0.v[i] * xv[c].v[i];
+        st_bf16x8(prod + row * ldprod + col, o);
+      }
     }
   }
 }
@@ -291,13 +297,15 @@ __global__ void __launch_bounds__(128) qknorm_rope_bwd_row_kernel(
     int dk_f32, const bf16* __restrict__ xq, int64_t ldq, const bf16* __restrict__ xk, int64_t ldk,
     const bf16* __restrict__ wq, const bf16* __restrict__ wk, const bf16* __restrict__ cosp,
     const bf16* __restrict__ sinp, int64_t ldcs, bf16* __restrict__ oq, int64_t ldoq,
-    bf16* __restrict__ ok, int64_t ldok, int64_t rows_q, int64_t rows_k, int D, float eps) {
+    bf16* __restrict__ ok, int64_t ldok, bf16* __restrict__ pq, int64_t ldpq, bf16* __restrict__ pk, int64_t ldpk,
+    int64_t rows_q, int64_t rows_k, int D, float eps) {
   __shared__ float red[8];
   const int64_t w = blockIdx.x;
   const bool is_k = w >= rows_q;
   const int64_t row = is_k ? w - rows_q : w;
   const bf16* xr = is_k ? xk + row * ldk : xq + row * ldq;
   const bf16* wt = is_k ? wk : wq;
+  bf16* prow = is_k ? (pk ? pk + row * ldpk : nullptr) : (pq ? pq + row * ldpq : nullptr);
   const void* gsrc = is_k ? dk : dq;
   const int64_t ldg = is_k ? lddk : lddq;
   const int g_f32 = is_k ? dk_f32 : dq_f32;
@@ -348,20 +356,26 @@ __global__ void __launch_bounds__(128) qknorm_rope_bwd_row_kernel(
     } else {
       gv[c] = g;
     }
-    const Row8 wv = unpack8(wp[c]);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      gv[c].v[i] *= wv.v[i];
-      s2 += xv[c].v[i] * xv[c].v[i];
-    }
+    for (int i = 0; i < 8; ++i) s2 += xv[c].v[i] * xv[c].v[i];
   }
   const float rstd = rsqrtf(block_sum2(s2, 0.f, red).x / D + eps);
   float gx = 0.f;
 #pragma unroll
   for (int c = 0; c < NCH; ++c) {
+    const int col = (c * 128 + threadIdx.x) * 8;
+    const Row8 wv = unpack8(wp[c]);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) xv[c].v[i] *= rstd;  // xhat
+    if (prow && col < D) {   // dy * xhat: summed over the rows it is d(weight) of the qk-norm (train_mode = "full")
+      Row8 o;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) o.v[i] = gv[c].v[i] * xv[c].v[i];
+      st_bf16x8(prow + col, o);
+    }
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      xv[c].v[i] *= rstd;  // xhat
+      gv[c].v[i] *= wv.v[i];
       gx += gv[c].v[i] * xv[c].v[i];
     }
   }
@@ -455,7 +469,8 @@ __global__ void __launch_bounds__(128) qknorm_rope_bwd_pair_kernel(
     int dk_f32, const bf16* __restrict__ xq, int64_t ldq, const bf16* __restrict__ xk, int64_t ldk,
     const bf16* __restrict__ wq, const bf16* __restrict__ wk, const bf16* __restrict__ cosp,
     const bf16* __restrict__ sinp, int64_t ldcs, bf16* __restrict__ oq, int64_t ldoq,
-    bf16* __restrict__ ok, int64_t ldok, int D, float eps) {
+    bf16* __restrict__ ok, int64_t ldok, bf16* __restrict__ pq, int64_t ldpq, bf16* __restrict__ pk, int64_t ldpk,
+    int D, float eps) {
   __shared__ float red[8];
   const int64_t row = blockIdx.x;
   uint4 qp[NCH], kp[NCH], cp[NCH], sp[NCH], gq0[NCH], gq1[NCH], gk0[NCH], gk1[NCH];
@@ -494,17 +509,8 @@ __global__ void __launch_bounds__(128) qknorm_rope_bwd_pair_kernel(
     const Row8 cv = unpack8(cp[c]), sv = unpack8(sp[c]);
     rope_bwd8(dq_f32 ? as_row8(gq0[c], gq1[c]) : unpack8(gq0[c]), cv, sv, ga[c]);
     rope_bwd8(dk_f32 ? as_row8(gk0[c], gk1[c]) : unpack8(gk0[c]), cv, sv, gb[c]);
-    Row8 wa, wb;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) wa.v[i] = wb.v[i] = 0.f;
-    if (col < D) {
-      wa = ld_bf16x8(wq + col);
-      wb = ld_bf16x8(wk + col);
-    }
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      ga[c].v[i] *= wa.v[i];
-      gb[c].v[i] *= wb.v[i];
       sq += xa[c].v[i] * xa[c].v[i];
       sk += xb[c].v[i] * xb[c].v[i];
     }
@@ -514,10 +520,32 @@ __global__ void __launch_bounds__(128) qknorm_rope_bwd_pair_kernel(
   float gxq = 0.f, gxk = 0.f;
 #pragma unroll
   for (int c = 0; c < NCH; ++c) {
+    const int col = (c * 128 + threadIdx.x) * 8;
+    Row8 wa, wb;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) wa.v[i] = wb.v[i] = 0.f;
+    if (col < D) {
+      wa = ld_bf16x8(wq + col);
+      wb = ld_bf16x8(wk + col);
+    }
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       xa[c].v[i] *= rq;  // xhat
       xb[c].v[i] *= rk;
+    }
+    if (pq && col < D) {   // dy * xhat of the q row and of the k row: column sums = d(q_norm.weight), d(k_norm.weight)
+      Row8 o;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) o.v[i] = ga[c].v[i] * xa[c].v[i];
+      st_bf16x8(pq + row * ldpq + col, o);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) o.v[i] = gb[c].v[i] * xb[c].v[i];
+      st_bf16x8(pk + row * ldpk + col, o);
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      ga[c].v[i] *= wa.v[i];
+      gb[c].v[i] *= wb.v[i];
       gxq += ga[c].v[i] * xa[c].v[i];
       gxk += gb[c].v[i] * xb[c].v[i];
     }
@@ -691,6 +719,64 @@ __global__ void __launch_bounds__(256) colsum_kernel(const bf16* __restrict__ x,
   if (part == 0 && c < N) out[c] = red[0][threadIdx.x] + red[1][threadIdx.x] + red[2][threadIdx.x] + red[3][threadIdx.x];
 }
 
+// Grouped column sums over long row ranges, optionally of an element-wise product:
+//     out[g, n] = sum over the rows r of group g of  a[r, n] * (b ? b[r, n] : 1)        (fp32, deterministic)
+// -- the gradients of everything that is broadcast over tokens in train_mode = "full": d(shift) = colsum(dy),
+// d(scale) = colsum(dy * xhat), d(gate) = colsum(dy * u), d(q_norm.weight) = colsum(dq * xhat), bias gradients.
+// One 256-thread block per (16-row chunk, 2048-column panel), 8 columns per thread, eight 16-byte loads in flight;
+// the chunk's sums are reduced into the (zeroed) output with red.global.add.v4.f32.
+constexpr int CSG_ROWS = 16;   // rows per stage-1 block: 384 blocks at 6144 rows, 8 rows x 16 bytes in flight per thread
+__global__ void __launch_bounds__(256) colsum_groups_part_kernel(const bf16* __restrict__ a, int64_t lda,
+                                                                 const bf16* __restrict__ b, int64_t ldb,
+                                                                 float* __restrict__ part, int N, int64_t rows_per_group,
+                                                                 int chunks_per_group) {
+  const int chunk = blockIdx.x, panel = blockIdx.y;
+  const int g = chunk / chunks_per_group, cg = chunk % chunks_per_group;
+  const int64_t r0 = (int64_t)g * rows_per_group + (int64_t)cg * CSG_ROWS;
+  int64_t r1 = r0 + CSG_ROWS;
+  const int64_t rend = (int64_t)(g + 1) * rows_per_group;
+  if (r1 > rend) r1 = rend;
+  const int col = panel * 2048 + threadIdx.x * 8;
+  if (col >= N) return;
+  float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  int64_t r = r0;
+  for (; r + 8 <= r1; r += 8) {   // eight rows in flight
+    uint4 av[8], bv[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      av[k] = *reinterpret_cast<const uint4*>(a + (r + k) * lda + col);
+      if (b) bv[k] = *reinterpret_cast<const uint4*>(b + (r + k) * ldb + col);
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const Row8 x = unpack8(av[k]);
+      if (b) {
+        const Row8 y = unpack8(bv[k]);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i] = fmaf(x.v[i], y.v[i], acc[i]);
+      } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i] += x.v[i];
+      }
+    }
+  }
+  for (; r < r1; ++r) {
+    const Row8 x = ld_bf16x8(a + r * lda + col);
+    if (b) {
+      const Row8 y = ld_bf16x8(b + r * ldb + col);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[i] = fmaf(x.v[i], y.v[i], acc[i]);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[i] += x.v[i];
+    }
+  }
+  // fold into the group's row with vector reductions at the L2 (a few hundred per address over the whole launch; a
+  // second pass over per-chunk partials measured 5x slower: 8-32 blocks walking 384 partials are pure latency)
+  float* dst = part + (int64_t)g * N + col;
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(acc[0]), "f"(acc[1]), "f"(acc[2]), "f"(acc[3]) : "memory");
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + 4), "f"(acc[4]), "f"(acc[5]), "f"(acc[6]), "f"(acc[7]) : "memory");
+}
 // delta[b, h, q] = sum_d o[b, q, h, d] * do[b, q, h, d]   (dh = 64: 8 lanes x 8 elements per head; every thread
 // takes the same (head, slice) of two rows half the tensor apart, so four 16-byte loads are in flight per thread)
 __global__ void __launch_bounds__(256) attn_delta_kernel(const bf16* __restrict__ o, int64_t ldo,
@@ -812,9 +898,10 @@ extern "C" int b200_norm_mod_fwd(const void* x, int64_t ldx, void* y, int64_t ld
 
 extern "C" int b200_norm_mod_bwd(const void* dy, int64_t lddy, const void* x, int64_t ldx,
                                  const void* scale, int64_t mod_stride, const void* dres,
-                                 int64_t lddres, void* dx, int64_t lddx, int64_t rows, int D,
+                                 int64_t lddres, void* dx, int64_t lddx, void* prod, int64_t ldprod, int64_t rows, int D,
                                  int64_t rows_per_mod, float eps, int layernorm, void* stream) {
   CHECK_ARG(dy && x && dx && rows >= 0 && D > 0, "norm_mod_bwd: null pointer or bad shape");
+  CHECK_ARG(!prod || (ldprod % 8 == 0 && aligned16(prod)), "norm_mod_bwd: prod must be 16-byte aligned");
   CHECK_ARG(D % 8 == 0 && D <= 2048, "norm_mod_bwd: D must be a multiple of 8 and <= 2048");
   CHECK_ARG(lddy % 8 == 0 && ldx % 8 == 0 && lddx % 8 == 0 && lddres % 8 == 0 &&
                 mod_stride % 8 == 0 && aligned16(dy) && aligned16(x) && aligned16(dx) &&
@@ -824,7 +911,7 @@ extern "C" int b200_norm_mod_bwd(const void* dy, int64_t lddy, const void* x, in
   if (rows == 0) return 0;
   ROWBLOCK_DISPATCH(norm_mod_bwd_row_kernel, D, rows, (cudaStream_t)stream,
       (const bf16*)dy, lddy, (const bf16*)x, ldx, (const bf16*)scale, mod_stride,
-      (const bf16*)dres, lddres, (bf16*)dx, lddx, rows, D, rows_per_mod, eps, layernorm);
+      (const bf16*)dres, lddres, (bf16*)dx, lddx, (bf16*)prod, ldprod, rows, D, rows_per_mod, eps, layernorm);
   return launch_status("norm_mod_bwd");
 }
 
@@ -863,9 +950,13 @@ extern "C" int b200_qknorm_rope_bwd(const void* dq, int64_t lddq, int dq_is_f32,
                                     int64_t lddk, int dk_is_f32, const void* xq, int64_t ldq,
                                     const void* xk, int64_t ldk, const void* wq, const void* wk,
                                     const void* cos_t, const void* sin_t, int64_t ldcs, void* oq,
-                                    int64_t ldoq, void* ok, int64_t ldok, int64_t rows_q,
-                                    int64_t rows_k, int D, float eps, void* stream) {
+                                    int64_t ldoq, void* ok, int64_t ldok, void* prod_q, int64_t ldpq, void* prod_k,
+                                    int64_t ldpk, int64_t rows_q, int64_t rows_k, int D, float eps, void* stream) {
   CHECK_ARG(rows_q >= 0 && rows_k >= 0 && D > 0, "qknorm_rope_bwd: bad shape");
+  CHECK_ARG((!prod_q || (ldpq % 8 == 0 && aligned16(prod_q))) && (!prod_k || (ldpk % 8 == 0 && aligned16(prod_k))),
+            "qknorm_rope_bwd: prod outputs must be 16-byte aligned");
+  CHECK_ARG(!(cos_t && rows_q == rows_k && rows_q > 0) || ((prod_q == nullptr) == (prod_k == nullptr)),
+            "qknorm_rope_bwd: the paired q/k form takes both product outputs or none");
   CHECK_ARG((rows_q == 0 || (xq && oq && wq && dq)) && (rows_k == 0 || (xk && ok && wk && dk)),
             "qknorm_rope_bwd: null pointer");
   CHECK_ARG(D % 8 == 0 && D <= 2048, "qknorm_rope_bwd: D must be a multiple of 8 and <= 2048");
@@ -882,13 +973,14 @@ extern "C" int b200_qknorm_rope_bwd(const void* dq, int64_t lddq, int dq_is_f32,
   if (cos_t && rows_q == rows_k) {
     ROWBLOCK_DISPATCH(qknorm_rope_bwd_pair_kernel, D, rows_q, (cudaStream_t)stream,
         dq, lddq, dq_is_f32, dk, lddk, dk_is_f32, (const bf16*)xq, ldq, (const bf16*)xk, ldk, (const bf16*)wq,
-        (const bf16*)wk, (const bf16*)cos_t, (const bf16*)sin_t, ldcs, (bf16*)oq, ldoq, (bf16*)ok, ldok, D, eps);
+        (const bf16*)wk, (const bf16*)cos_t, (const bf16*)sin_t, ldcs, (bf16*)oq, ldoq, (bf16*)ok, ldok,
+        (bf16*)prod_q, ldpq, (bf16*)prod_k, ldpk, D, eps);
     return launch_status("qknorm_rope_bwd");
   }
   ROWBLOCK_DISPATCH(qknorm_rope_bwd_row_kernel, D, total, (cudaStream_t)stream,
       dq, lddq, dq_is_f32, dk, lddk, dk_is_f32, (const bf16*)xq, ldq, (const bf16*)xk, ldk,
       (const bf16*)wq, (const bf16*)wk, (const bf16*)cos_t, (const bf16*)sin_t, ldcs, (bf16*)oq, ldoq,
-      (bf16*)ok, ldok, rows_q, rows_k, D, eps);
+      (bf16*)ok, ldok, (bf16*)prod_q, ldpq, (bf16*)prod_k, ldpk, rows_q, rows_k, D, eps);
   return launch_status("qknorm_rope_bwd");
 }
 
@@ -959,6 +1051,29 @@ extern "C" int b200_colsum(const void* x, int64_t ldx, float* out, int64_t rows,
   CHECK_ARG(x && out && rows >= 0 && N > 0, "colsum: bad arguments");
   colsum_kernel<<<(N + 63) / 64, 256, 0, (cudaStream_t)stream>>>((const bf16*)x, ldx, out, rows, N);
   return launch_status("colsum");
+}
+
+extern "C" int64_t b200_colsum_groups_workspace_bytes(int64_t rows, int N, int64_t rows_per_group) {
+  (void)rows; (void)N; (void)rows_per_group;
+  return 0;   // the reduction goes through L2 atomics; the workspace arguments are reserved
+}
+
+extern "C" int b200_colsum_groups(const void* a, int64_t lda, const void* b, int64_t ldb, float* out, int64_t rows, int N,
+                                  int64_t rows_per_group, void* workspace, int64_t workspace_bytes, void* stream) {
+  CHECK_ARG(a && out && rows >= 0 && N > 0 && rows_per_group > 0, "colsum_groups: bad arguments");
+  CHECK_ARG(N % 8 == 0 && lda % 8 == 0 && aligned16(a) && (!b || (ldb % 8 == 0 && aligned16(b))) && aligned16(out),
+            "colsum_groups: 16-byte alignment required (N a multiple of 8)");
+  CHECK_ARG(rows % rows_per_group == 0, "colsum_groups: rows must be a multiple of rows_per_group");
+  if (rows == 0) return 0;
+  (void)workspace; (void)workspace_bytes;
+  const int groups = (int)(rows / rows_per_group);
+  const int cpg = (int)((rows_per_group + CSG_ROWS - 1) / CSG_ROWS);
+  if (cudaMemsetAsync(out, 0, (size_t)groups * N * sizeof(float), (cudaStream_t)stream) != cudaSuccess)
+    return launch_status("colsum_groups: memset");
+  dim3 g1((unsigned)(groups * cpg), (unsigned)((N + 2047) / 2048));
+  colsum_groups_part_kernel<<<g1, 256, 0, (cudaStream_t)stream>>>((const bf16*)a, lda, (const bf16*)b, ldb, out, N,
+                                                                  rows_per_group, cpg);
+  return launch_status("colsum_groups");
 }
 
 extern "C" int b200_attn_merge(float* o_acc, int64_t ldacc, float* lse_acc, const void* o_i, int64_t ldo,

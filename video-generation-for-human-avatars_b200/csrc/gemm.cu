@@ -26,7 +26,7 @@
 
 namespace b200 {
 
-enum { EPI_NONE = 0, EPI_GELU = 1, EPI_GELU_GRAD = 2 };
+enum { EPI_NONE = 0, EPI_GELU = 1, EPI_GELU_GRAD = 2, EPI_STASH = 3 };  // STASH: aux <- bf16(acc + bias), before gate / residual
 
 struct GemmParams {
   int M, N;
@@ -146,6 +146,12 @@ __device__ __forceinline__ void epi_math8(float (&v)[8], uint4& pre, int n, cons
                   bf16_lo(u.z), bf16_hi(u.z), bf16_lo(u.w), bf16_hi(u.w)};
 #pragma unroll
     for (int i = 0; i < 8; ++i) v[i] *= gelu_tanh_grad(h[i]);
+  } else if (p.epi == EPI_STASH) {
+    // the pre-gate output leaves through the second store: a trainable AdaLN gate needs it for d(gate) = sum dy * u
+    pre.x = pack_bf16x2(v[0], v[1]); pre.y = pack_bf16x2(v[2], v[3]);
+    pre.z = pack_bf16x2(v[4], v[5]); pre.w = pack_bf16x2(v[6], v[7]);
+    v[0] = bf16_lo(pre.x); v[1] = bf16_hi(pre.x); v[2] = bf16_lo(pre.y); v[3] = bf16_hi(pre.y);
+    v[4] = bf16_lo(pre.z); v[5] = bf16_hi(pre.z); v[6] = bf16_lo(pre.w); v[7] = bf16_hi(pre.w);
   }
   if (gate_row) {
     uint4 u = __ldg(reinterpret_cast<const uint4*>(gate_row + n));
@@ -412,7 +418,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         // buffer and hands it to the TMA (cp.async.bulk.tensor store clips rows/columns past M, N).
         const uint32_t stg = stage_base + (warp - 4) * 4096;
         const int row0 = mt * 128 + ew * 32;
-        const bool stash = (p.epi == EPI_GELU) && p.aux;  // the bf16 pre-activation leaves through a second store
+        const bool stash = (p.epi == EPI_GELU || p.epi == EPI_STASH) && p.aux;  // bf16 pre-activation / pre-gate output: second store
 #pragma unroll 1
         for (int c = chalf * (BN / 2); c < (chalf + 1) * (BN / 2); c += 64) {
           const int n_slab = nt * BN + c;
@@ -524,6 +530,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                               bf16_lo(u.z), bf16_hi(u.z), bf16_lo(u.w), bf16_hi(u.w)};
 #pragma unroll
                 for (int i = 0; i < 8; ++i) v[i] *= gelu_tanh_grad(h[i]);
+              } else if (p.epi == EPI_STASH) {
+                uint4 u;
+                u.x = pack_bf16x2(v[0], v[1]); u.y = pack_bf16x2(v[2], v[3]);
+                u.z = pack_bf16x2(v[4], v[5]); u.w = pack_bf16x2(v[6], v[7]);
+                *reinterpret_cast<uint4*>(aux_row + n) = u;
+                v[0] = bf16_lo(u.x); v[1] = bf16_hi(u.x); v[2] = bf16_lo(u.y); v[3] = bf16_hi(u.y);
+                v[4] = bf16_lo(u.z); v[5] = bf16_hi(u.z); v[6] = bf16_lo(u.w); v[7] = bf16_hi(u.w);
               }
               if (gate_row) {
                 uint4 u = __ldg(reinterpret_cast<const uint4*>(gate_row + n));
@@ -668,8 +681,9 @@ static int gemm_impl(const void* A, int64_t lda, int a_kmajor_rows_are_k, const 
     return arg_error("gemm_bf16: operands must be 16-byte aligned with 16-byte-multiple pitches");
   if (K2 > 0 && (!(A2 && B2) || lda2 % 8 || ldb2 % 8 || !al16(A2) || !al16(B2)))
     return arg_error("gemm_bf16: bad second operand pair");
-  if (epilogue < EPI_NONE || epilogue > EPI_GELU_GRAD) return arg_error("gemm_bf16: unknown epilogue");
+  if (epilogue < EPI_NONE || epilogue > EPI_STASH) return arg_error("gemm_bf16: unknown epilogue");
   if (epilogue == EPI_GELU_GRAD && !aux) return arg_error("gemm_bf16: GELU_GRAD needs aux (pre-activation)");
+  if (epilogue == EPI_STASH && (!aux || out_is_f32)) return arg_error("gemm_bf16: STASH needs aux and a bf16 output");
   if ((aux && (ldaux % 8 || !al16(aux))) || (res && (ldres % 8 || !al16(res))) ||
       (bias && !al16(bias)) || (gate && (gate_stride % 8 || !al16(gate) || rows_per_gate <= 0)))
     return arg_error("gemm_bf16: epilogue operands must be 16-byte aligned");
@@ -754,7 +768,7 @@ static int gemm_impl(const void* A, int64_t lda, int a_kmajor_rows_are_k, const 
   if (p.tma_store) {
     if ((rc = make_tmap_2d_bf16(&tmC, C, M + G1 * gg.c_gr, N + G1 * gg.c_gc, ldc, 32, 64)))
       return arg_error("gemm_bf16: cuTensorMapEncodeTiled failed (C)", rc);
-    if (epilogue == EPI_GELU && aux && (rc = make_tmap_2d_bf16(&tmAux, aux, M, N, ldaux, 32, 64)))
+    if ((epilogue == EPI_GELU || epilogue == EPI_STASH) && aux && (rc = make_tmap_2d_bf16(&tmAux, aux, M, N, ldaux, 32, 64)))
       return arg_error("gemm_bf16: cuTensorMapEncodeTiled failed (aux)", rc);
   }
 

@@ -73,6 +73,7 @@ class DeviceFeeder:
         self.slots: List[Optional[Dict[str, torch.Tensor]]] = [None] * self.depth
         self.pinned: List[Optional[Dict[str, torch.Tensor]]] = [None] * self.depth
         self.done: List[Optional[torch.cuda.Event]] = [None] * self.depth   # compute finished reading slot i
+        self.copied: List[Optional[torch.cuda.Event]] = [None] * self.depth  # the H2D copies out of pinned slot i finished
         self.n = 0
         for _ in range(self.depth):
             self._stage()
@@ -97,6 +98,8 @@ class DeviceFeeder:
             return
         host = self._buffers(self.pinned, slot, batch, True)
         dev = self._buffers(self.slots, slot, batch, False)
+        if self.copied[slot] is not None:
+            self.copied[slot].synchronize()   # the pinned slot is about to be overwritten by the host: its DMA must be done
         with torch.cuda.stream(self.copy_stream):
             if self.done[slot] is not None:
                 self.copy_stream.wait_event(self.done[slot])      # the step that used this slot has finished with it
@@ -105,6 +108,7 @@ class DeviceFeeder:
                 dev[k].copy_(host[k], non_blocking=True)
             ready = torch.cuda.Event()
             ready.record(self.copy_stream)
+        self.copied[slot] = ready
         self.queue.append((dev, ready, batch.get("stem"), slot))
 
     def __iter__(self) -> Iterator[dict]:

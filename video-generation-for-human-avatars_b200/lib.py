@@ -30,9 +30,9 @@ PROTOTYPES = {
     "b200_fa_bwd_workspace_bytes": (L, [I, I, I, I]),
     "b200_fa_bwd": (I, [P, L, P, L, P, L, P, L, P, P, P, P, L, P, L, P, L, I, I, I, I, I, F, P, L, P]),
     "b200_norm_mod_fwd": (I, [P, L, P, L, P, P, L, L, I, L, F, I, P]),
-    "b200_norm_mod_bwd": (I, [P, L, P, L, P, L, P, L, P, L, L, I, L, F, I, P]),
+    "b200_norm_mod_bwd": (I, [P, L, P, L, P, L, P, L, P, L, P, L, L, I, L, F, I, P]),
     "b200_qknorm_rope_fwd": (I, [P, L, P, L, P, P, P, P, L, P, L, P, L, L, L, I, F, P]),
-    "b200_qknorm_rope_bwd": (I, [P, L, I, P, L, I, P, L, P, L, P, P, P, P, L, P, L, P, L, L, L, I, F, P]),
+    "b200_qknorm_rope_bwd": (I, [P, L, I, P, L, I, P, L, P, L, P, P, P, P, L, P, L, P, L, P, L, P, L, L, L, I, F, P]),
     "b200_rf_noise": (I, [P, P, P, P, P, L, L, P]),
     "b200_rf_loss_workspace_bytes": (L, []),
     "b200_rf_loss": (I, [P, P, P, P, L, F, P, L, P]),
@@ -43,6 +43,8 @@ PROTOTYPES = {
     "b200_adamw_step": (I, [P, P, I, P, P, P, P]),
     "b200_rowscale": (I, [P, L, P, L, P, L, L, I, L, P]),
     "b200_colsum": (I, [P, L, P, L, I, P]),
+    "b200_colsum_groups_workspace_bytes": (L, [L, I, L]),
+    "b200_colsum_groups": (I, [P, L, P, L, P, L, I, L, P, L, P]),
 }
 
 _lib = None

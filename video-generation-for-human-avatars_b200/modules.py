@@ -215,10 +215,6 @@ def attention_forward(attn, hidden_states, freqs_cis=None, encoder_hidden_states
     scale = float(attn.scale)
 
     sp = side(attn).get("sp") if is_self else None
-    # a trainable gate cannot ride in the GEMM epilogue (its gradient needs the un-gated output): un-fused below
-    gate_out, res_out = gate, res
-    if ops.wants_grad(gate):
-        gate, res = None, None
     # STG skips of whole batch entries ("attention values" / "attention skip", attention.py:1071-1086) ride inside the
     # attention launch when the mask is known to be 0 / 1 (built by our create_skip_layer_mask) and no gradient is
     # recorded: the skipped entries' CTAs copy their pass-through rows and do no attention work
@@ -228,17 +224,24 @@ def attention_forward(attn, hidden_states, freqs_cis=None, encoder_hidden_states
             and not torch.is_grad_enabled() and sp is None):
         batch_keep = skip_layer_mask.reshape(B).to(torch.float32).contiguous()
         pass_input = strat == SkipLayerStrategy.AttentionSkip
-    fast = (is_self and (skip_layer_mask is None or batch_keep is not None)
-            and all(_frozen_plain(m) for m in (attn.to_q, attn.to_k, attn.to_v))
-            and linear_parts(attn.to_out[0])[2] is None and not ops.wants_grad(linear_parts(attn.to_out[0])[0])
-            and not ops.wants_grad(wqn, wkn))
+    qkv_parts = [linear_parts(m) for m in (attn.to_q, attn.to_k, attn.to_v)]
+    no_lora = all(lo is None for _, _, lo in qkv_parts) and linear_parts(attn.to_out[0])[2] is None
+    frozen = all(_frozen_plain(m) for m in (attn.to_q, attn.to_k, attn.to_v))
+    fast = is_self and (skip_layer_mask is None or batch_keep is not None) and no_lora
+    if fast and frozen:
+        Wqkv, bqkv = _cached_wqkv(attn)   # [3D, D] concatenation of the frozen weights, built once
+    elif fast and sp is None:
+        # train_mode="full" (training.py:75-91): the projections train.  Same node, fed with an autograd-visible
+        # concatenation (25 MB per block and step; its backward hands the [3D, D] weight gradient out as three views)
+        side(attn).pop("wqkv", None)
+        Wqkv = torch.cat([w for w, _, _ in qkv_parts], dim=0)
+        bqkv = torch.cat([b for _, b, _ in qkv_parts], dim=0) if qkv_parts[0][1] is not None else None
+    else:
+        fast = False
     if fast:
         Wo, bo, _ = linear_parts(attn.to_out[0])
-        Wqkv, bqkv = _cached_wqkv(attn)
         y = ops.SelfAttnFn.apply(x2d, Wqkv, bqkv, wqn, wkn, cos, sin, Wo, bo, gate, rows_per_gate, res, kb, B, H,
                                  Nq, scale, sp, batch_keep, pass_input)
-        if gate is not gate_out:
-            y = ops.gate_residual(y, gate_out, rows_per_gate, res_out)
         return y.view(B, Nq, -1)
     if is_self:
         side(attn).pop("wqkv", None)   # trainable / adapted projections: a cached concatenation would go stale
@@ -258,24 +261,13 @@ def attention_forward(attn, hidden_states, freqs_cis=None, encoder_hidden_states
     else:
         k_pre = apply_linear(attn.to_k, src2d)
         v = apply_linear(attn.to_v, src2d)
-    if ops.wants_grad(wqn, wkn):
-        # trainable qk-norm weights (train_mode='full'): RMSNorm stays a kernel, the affine weight and RoPE run as
-        # torch ops (attention.py:996-1012, 917-932) so autograd sees them; then the attention core alone
-        qn = ops.NormModFn.apply(q_pre if q_pre.stride(1) == 1 else q_pre.contiguous(), None, None, B * Nq, 1e-5, False)
-        kn = ops.NormModFn.apply(k_pre if k_pre.stride(1) == 1 else k_pre.contiguous(), None, None, B * Nk, 1e-5, False)
-        qn, kn = qn * wqn, kn * wkn
-        if use_rope:
-            qn, kn = ops.rope_torch(qn, cos, sin), ops.rope_torch(kn, cos, sin)
-        o = ops.FlashAttnFn.apply(qn, kn, v, kb, B, H, Nq, Nk, scale)
-    else:
-        o = ops.AttnCoreFn.apply(q_pre, k_pre, v, wqn, wkn, cos, sin, kb, B, H, Nq, Nk, scale)
+    # (trainable q_norm / k_norm weights included: the backward kernel emits the products their gradients sum)
+    o = ops.AttnCoreFn.apply(q_pre, k_pre, v, wqn, wkn, cos, sin, kb, B, H, Nq, Nk, scale)
     if skip_layer_mask is not None and strat in (SkipLayerStrategy.AttentionSkip, SkipLayerStrategy.AttentionValues):
         m = skip_layer_mask.reshape(B, 1, 1).to(o.dtype)
         other = hidden_states if strat == SkipLayerStrategy.AttentionSkip else v.view(B, Nk, D)
         o = (o.view(B, Nq, D) * m + other * (1.0 - m)).reshape(B * Nq, D)
     y = apply_linear(attn.to_out[0], o, gate, rows_per_gate, res, join=join, join_role="send")
-    if gate is not gate_out:
-        y = ops.gate_residual(y, gate_out, rows_per_gate, res_out)
     return y.view(B, Nq, -1)
 
 
@@ -317,11 +309,7 @@ def block_forward(block, hidden_states, freqs_cis=None, attention_mask=None, enc
     W2, b2, l2 = linear_parts(block.ff.net[2])
     if l1 is not None or l2 is not None:
         raise B200Error("LoRA on the feed-forward is not built (reference targets attn2 only, training.py:51-60)")
-    if ops.wants_grad(gate_mlp):
-        out = ops.gate_residual(ops.FeedForwardFn.apply(h2, W1, b1, W2, b2, None, 0, None), gate_mlp, rpm, x2_res)
-        out = out.view(B, N, D)
-    else:
-        out = ops.FeedForwardFn.apply(h2, W1, b1, W2, b2, gate_mlp, rpm, x2_res).view(B, N, D)
+    out = ops.FeedForwardFn.apply(h2, W1, b1, W2, b2, gate_mlp, rpm, x2_res).view(B, N, D)
     if skip_layer_mask is not None and strat == SkipLayerStrategy.TransformerBlock:
         m = skip_layer_mask.view(-1, 1, 1).to(out.dtype)
         out = out * m + hidden_states * (1.0 - m)

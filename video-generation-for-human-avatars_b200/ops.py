@@ -9,7 +9,7 @@ import torch
 
 from . import lib as _lib
 
-EPI_NONE, EPI_GELU, EPI_GELU_GRAD = 0, 1, 2
+EPI_NONE, EPI_GELU, EPI_GELU_GRAD, EPI_STASH = 0, 1, 2, 3
 LORA_PAD = 64  # LoRA rank is zero-padded to one 64-wide k-block of the GEMM
 BF16 = torch.bfloat16
 
@@ -207,18 +207,36 @@ def norm_mod_fwd(x, scale, shift, rows_per_mod, eps, layernorm=False, out=None):
     return out
 
 
-def norm_mod_bwd(dy, x, scale, rows_per_mod, eps, layernorm=False, dres=None):
+def norm_mod_bwd(dy, x, scale, rows_per_mod, eps, layernorm=False, dres=None, want_prod=False):
+    """-> dx, or (dx, prod) with prod = dy * xhat (bf16 [rows, D]) when the AdaLN scale trains."""
     _chk2d(dy, "norm_mod_bwd dy")
     _chk2d(x, "norm_mod_bwd x")
     rows, D = x.shape
     dx = torch.empty((rows, D), device=x.device, dtype=BF16)
+    prod = torch.empty((rows, D), device=x.device, dtype=BF16) if want_prod else None
     if dres is not None:
         _chk2d(dres, "norm_mod_bwd dres")
     _call("norm_mod_bwd", (8.0 if dres is not None else 6.0) * rows * D, "byte", _L().b200_norm_mod_bwd, _p(dy), dy.stride(0), _p(x), x.stride(0), _p(scale),
                                 scale.stride(0) if scale is not None else 0, _p(dres),
-                                dres.stride(0) if dres is not None else 0, _p(dx), dx.stride(0), rows, D,
+                                dres.stride(0) if dres is not None else 0, _p(dx), dx.stride(0), _p(prod),
+                                prod.stride(0) if prod is not None else 0, rows, D,
                                 rows_per_mod, eps, int(layernorm), _s())
-    return dx
+    return (dx, prod) if want_prod else dx
+
+
+def colsum_groups(a, b=None, rows_per_group=0):
+    """out[g, n] = sum over the rows of group g of a[r, n] * (b[r, n] if b is given else 1): fp32 [groups, N]."""
+    _chk2d(a, "colsum_groups a")
+    rows, N = a.shape
+    rpg = rows_per_group or rows
+    if b is not None:
+        _chk2d(b, "colsum_groups b")
+    out = torch.empty((max(rows // max(rpg, 1), 0), N), device=a.device, dtype=torch.float32)
+    if rows == 0:
+        return out
+    _call("colsum_groups", (2.0 + (2.0 if b is not None else 0.0)) * rows * N, "byte", _L().b200_colsum_groups, _p(a),
+          a.stride(0), _p(b), b.stride(0) if b is not None else 0, _p(out), rows, N, rpg, None, 0, _s())
+    return out
 
 
 def qknorm_rope_fwd(xq, xk, wq, wk, cos, sin, oq, ok, eps=1e-5):
@@ -232,7 +250,8 @@ def qknorm_rope_fwd(xq, xk, wq, wk, cos, sin, oq, ok, eps=1e-5):
         rows_q, rows_k, D, eps, _s())
 
 
-def qknorm_rope_bwd(dq, dk, xq, xk, wq, wk, cos, sin, oq, ok, eps=1e-5):
+def qknorm_rope_bwd(dq, dk, xq, xk, wq, wk, cos, sin, oq, ok, eps=1e-5, prod_q=None, prod_k=None):
+    """prod_q / prod_k: optional bf16 outputs (RoPE^T dq) * xhat_q, (RoPE^T dk) * xhat_k (qk-norm weight gradients)."""
     rows_q = xq.shape[0] if xq is not None else 0
     rows_k = xk.shape[0] if xk is not None else 0
     D = (xq if xq is not None else xk).shape[1]
@@ -242,7 +261,8 @@ def qknorm_rope_bwd(dq, dk, xq, xk, wq, wk, cos, sin, oq, ok, eps=1e-5):
         _p(xq), xq.stride(0) if xq is not None else 0, _p(xk), xk.stride(0) if xk is not None else 0,
         _p(wq), _p(wk), _p(cos), _p(sin), cos.stride(0) if cos is not None else 0,
         _p(oq), oq.stride(0) if oq is not None else 0, _p(ok), ok.stride(0) if ok is not None else 0,
-        rows_q, rows_k, D, eps, _s())
+        _p(prod_q), prod_q.stride(0) if prod_q is not None else 0, _p(prod_k),
+        prod_k.stride(0) if prod_k is not None else 0, rows_q, rows_k, D, eps, _s())
 
 
 def _fa_family(base, Nq, Nk, key_bias, attn1):
@@ -462,6 +482,7 @@ def stage_lora(A: torch.Tensor, B: torch.Tensor, scaling: float) -> Tuple[torch.
 # work forks from the main stream and runs in the SMs the big persistent kernels leave idle (tail waves, the gaps
 # between kernels); the caller joins the stream before the optimizer update.  None: everything stays on one stream.
 side_stream = None
+side_stream_used = False   # set when work was forked onto side_stream since the caller last cleared it
 
 
 class _OnSideStream:
@@ -477,6 +498,8 @@ class _OnSideStream:
         s = side_stream if self.enabled else None
         if s is None:
             return self
+        global side_stream_used
+        side_stream_used = True
         s.wait_stream(torch.cuda.current_stream())
         for t in self.inputs:
             if t is not None:
@@ -489,6 +512,15 @@ class _OnSideStream:
         if self.ctx is not None:
             self.ctx.__exit__(*exc)
         return False
+
+
+def _group_grad(t, other, rows_per_group, like):
+    """Gradient of a per-group row vector that was broadcast over `rows_per_group` consecutive rows:
+    sum over the group's rows of t (* other).  One row per group: the product itself."""
+    if rows_per_group == 1:
+        g = t if other is None else (t.float() * other.float())
+        return g.to(like.dtype)
+    return colsum_groups(t, other, rows_per_group).to(like.dtype)
 
 
 class GradJoin:
@@ -517,8 +549,13 @@ class LinearFn(torch.autograd.Function):
         if has_lora:
             a_pad, b_pad = stage_lora(A, B, scaling)
             t = gemm(x, a_pad, block_n=64)
-        y = gemm(x, W, a2=t, b2=b_pad, bias=b, gate=gate, rows_per_gate=rows_per_gate, res=res)
-        ctx.save_for_backward(x, W, t, a_pad, b_pad, gate)
+        u = None
+        if gate is not None and ctx.needs_input_grad[6]:
+            # trainable AdaLN gate: the pre-gate output leaves through the epilogue's second store (d(gate) = sum dy * u)
+            u = torch.empty((x.shape[0], W.shape[0]), device=x.device, dtype=BF16)
+        y = gemm(x, W, a2=t, b2=b_pad, bias=b, gate=gate, rows_per_gate=rows_per_gate, res=res, aux=u,
+                 epilogue=EPI_STASH if u is not None else EPI_NONE)
+        ctx.save_for_backward(x, W, t, a_pad, b_pad, gate, u)
         ctx.meta = (has_lora, scaling, rows_per_gate, A.shape[0] if has_lora else 0,
                     b is not None, res is not None)
         ctx.join = (join, join_role)
@@ -527,11 +564,12 @@ class LinearFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dy):
-        x, W, t, a_pad, b_pad, gate = ctx.saved_tensors
+        x, W, t, a_pad, b_pad, gate, u = ctx.saved_tensors
         has_lora, scaling, rpg, r, has_bias, has_res = ctx.meta
         need = ctx.needs_input_grad
         dy = dy if dy.stride(1) == 1 else dy.contiguous()
         g = rowscale(dy, gate, rpg) if gate is not None else dy
+        dgate = _group_grad(dy, u, rpg, gate) if (need[6] and u is not None) else None
         dx = dW = db = dA = dB = None
         dt = None
         if has_lora and (need[0] or need[3]):
@@ -560,11 +598,11 @@ class LinearFn(torch.autograd.Function):
         if need[1]:
             dW = gemm(g, x, a_rows_are_k=True, b_rows_are_k=True)
         if has_bias and need[2]:
-            db = colsum(g).to(BF16)
+            db = (colsum_groups(g)[0] if g.shape[0] >= 1024 and g.shape[1] % 8 == 0 else colsum(g)).to(BF16)
         dres = dy if (has_res and need[8]) else None
         if dres is not None and join is not None and role == "send":
             join.grad, dres = dres, None                # delivered through the receiving node's dgrad epilogue
-        return dx, dW, db, dA, dB, None, None, None, dres, None, None
+        return dx, dW, db, dA, dB, None, dgate, None, dres, None, None
 
 
 class FeedForwardFn(torch.autograd.Function):
@@ -576,19 +614,24 @@ class FeedForwardFn(torch.autograd.Function):
         M = x.shape[0]
         pre = torch.empty((M, W1.shape[0]), device=x.device, dtype=BF16)
         act = gemm(x, W1, bias=b1, epilogue=EPI_GELU, aux=pre)
-        y = gemm(act, W2, bias=b2, gate=gate, rows_per_gate=rows_per_gate, res=res)
+        u = None
+        if gate is not None and ctx.needs_input_grad[5]:   # trainable AdaLN gate: stash the pre-gate output (see LinearFn)
+            u = torch.empty((M, W2.shape[0]), device=x.device, dtype=BF16)
+        y = gemm(act, W2, bias=b2, gate=gate, rows_per_gate=rows_per_gate, res=res, aux=u,
+                 epilogue=EPI_STASH if u is not None else EPI_NONE)
         train_w = W1.requires_grad or W2.requires_grad
-        ctx.save_for_backward(x, W1, W2, pre, gate, act if train_w else None)
+        ctx.save_for_backward(x, W1, W2, pre, gate, act if train_w else None, u)
         ctx.meta = (rows_per_gate, res is not None)
         return y
 
     @staticmethod
     def backward(ctx, dy):
-        x, W1, W2, pre, gate, act = ctx.saved_tensors
+        x, W1, W2, pre, gate, act, u = ctx.saved_tensors
         rpg, has_res = ctx.meta
         need = ctx.needs_input_grad
         dy = dy if dy.stride(1) == 1 else dy.contiguous()
         g = rowscale(dy, gate, rpg) if gate is not None else dy
+        dgate = _group_grad(dy, u, rpg, gate) if (need[5] and u is not None) else None
         dh = gemm(g, W2, b_rows_are_k=True, epilogue=EPI_GELU_GRAD, aux=pre)   # [M, Dff]
         dx = gemm(dh, W1, b_rows_are_k=True) if need[0] else None
         dW1 = db1 = dW2 = db2 = None
@@ -601,7 +644,22 @@ class FeedForwardFn(torch.autograd.Function):
         if need[4]:
             db2 = colsum(g).to(BF16)
         dres = dy if (has_res and need[7]) else None
-        return dx, dW1, db1, dW2, db2, None, None, dres
+        return dx, dW1, db1, dW2, db2, dgate, None, dres
+
+
+def _norm_mod_backward(ctx, dy, dres, x, scale, rpm, eps, ln):
+    """dx (+ residual gradient) and, when the AdaLN tables train (training.py:75-91), d(scale) = sum_rows dy * xhat and
+    d(shift) = sum_rows dy per modulation group -- the product leaves the same kernel, the sums are colsum_groups."""
+    need_scale, need_shift = ctx.needs_input_grad[1], ctx.needs_input_grad[2]
+    dscale = dshift = None
+    if need_scale:
+        dx, prod = norm_mod_bwd(dy, x, scale, rpm, eps, ln, dres=dres, want_prod=True)
+        dscale = _group_grad(prod, None, rpm, dy)
+    else:
+        dx = norm_mod_bwd(dy, x, scale, rpm, eps, ln, dres=dres)
+    if need_shift:
+        dshift = _group_grad(dy, None, rpm, dy)
+    return dx, dscale, dshift, None, None, None
 
 
 class NormModFn(torch.autograd.Function):
@@ -618,11 +676,8 @@ class NormModFn(torch.autograd.Function):
     def backward(ctx, dy):
         x, scale = ctx.saved_tensors
         rpm, eps, ln = ctx.meta
-        if ctx.needs_input_grad[1] or ctx.needs_input_grad[2]:
-            raise _lib.B200Error("NormModFn: the fused kernel treats the AdaLN scale/shift as constants; "
-                                 "call ops.norm_mod(), which un-fuses the modulate when they are trainable")
         dy = dy if dy.stride(1) == 1 else dy.contiguous()
-        return norm_mod_bwd(dy, x, scale, rpm, eps, ln), None, None, None, None, None
+        return _norm_mod_backward(ctx, dy, None, x, scale, rpm, eps, ln)
 
 
 class NormModResFn(torch.autograd.Function):
@@ -640,15 +695,12 @@ class NormModResFn(torch.autograd.Function):
     def backward(ctx, dy, dres):
         x, scale = ctx.saved_tensors
         rpm, eps, ln = ctx.meta
-        if ctx.needs_input_grad[1] or ctx.needs_input_grad[2]:
-            raise _lib.B200Error("NormModResFn: the fused kernel treats the AdaLN scale/shift as constants; "
-                                 "call ops.norm_mod(), which un-fuses the modulate when they are trainable")
         if dy is None:
             return dres, None, None, None, None, None
         dy = dy if dy.stride(1) == 1 else dy.contiguous()
         if dres is not None and dres.stride(1) != 1:
             dres = dres.contiguous()
-        return norm_mod_bwd(dy, x, scale, rpm, eps, ln, dres=dres), None, None, None, None, None
+        return _norm_mod_backward(ctx, dy, dres, x, scale, rpm, eps, ln)
 
 
 class AttnCoreFn(torch.autograd.Function):
@@ -673,9 +725,7 @@ class AttnCoreFn(torch.autograd.Function):
     def backward(ctx, do):
         q_pre, k_pre, v, wq, wk, cos, sin, key_bias, qk, o, lse = ctx.saved_tensors
         B, H, Nq, Nk, scale = ctx.meta
-        if ctx.needs_input_grad[3] or ctx.needs_input_grad[4]:
-            raise _lib.B200Error("AttnCoreFn: the fused qk-norm kernel treats the norm weights as constants; "
-                                 "modules.attention_forward un-fuses norm + RoPE when they are trainable")
+        train_w = ctx.needs_input_grad[3] or ctx.needs_input_grad[4]
         D = H * 64
         q, k = qk[:B * Nq], qk[B * Nq:]
         do = do if do.stride(1) == 1 else do.contiguous()
@@ -684,8 +734,12 @@ class AttnCoreFn(torch.autograd.Function):
         dq32 = fa_bwd(q, k, v, o, do, lse, B, H, Nq, Nk, dk, dv, key_bias, scale)
         dq_pre = torch.empty((B * Nq, D), device=do.device, dtype=BF16)
         dk_pre = torch.empty((B * Nk, D), device=do.device, dtype=BF16)
-        qknorm_rope_bwd(dq32, dk, q_pre, k_pre, wq, wk, cos, sin, dq_pre, dk_pre)
-        return dq_pre, dk_pre, dv, None, None, None, None, None, None, None, None, None, None
+        pq = torch.empty((B * Nq, D), device=do.device, dtype=BF16) if train_w else None
+        pk = torch.empty((B * Nk, D), device=do.device, dtype=BF16) if train_w else None
+        qknorm_rope_bwd(dq32, dk, q_pre, k_pre, wq, wk, cos, sin, dq_pre, dk_pre, prod_q=pq, prod_k=pk)
+        dwq = colsum_groups(pq)[0].to(wq.dtype) if ctx.needs_input_grad[3] else None
+        dwk = colsum_groups(pk)[0].to(wk.dtype) if ctx.needs_input_grad[4] else None
+        return dq_pre, dk_pre, dv, dwq, dwk, None, None, None, None, None, None, None, None
 
 
 class FlashAttnFn(torch.autograd.Function):
@@ -718,22 +772,12 @@ def wants_grad(*tensors) -> bool:
 
 
 def norm_mod(x, scale, shift, rows_per_mod, eps, layernorm, with_res: bool):
-    """norm(x) * (1 + scale) + shift (+ the residual view of x).  Frozen modulation: one fused kernel with the
-    residual gradient folded into its backward.  Trainable modulation (train_mode='full', training.py:75-91): the
-    normalisation stays a kernel, the modulate runs as torch ops so autograd reduces d(scale) / d(shift)."""
-    if not wants_grad(scale, shift):
-        if with_res:
-            return NormModResFn.apply(x, scale, shift, rows_per_mod, eps, layernorm)
-        return NormModFn.apply(x, scale, shift, rows_per_mod, eps, layernorm), None
-    rows, D = x.shape
-    xhat = NormModFn.apply(x, None, None, rows, eps, layernorm)
-    g = rows // rows_per_mod
-    y = xhat.view(g, rows_per_mod, D)
-    if scale is not None:
-        y = y * (1 + scale.reshape(g, 1, D))
-    if shift is not None:
-        y = y + shift.reshape(g, 1, D)
-    return y.reshape(rows, D), (x if with_res else None)
+    """norm(x) * (1 + scale) + shift (+ the residual view of x): one fused kernel forward, one backward (the residual
+    gradient folded in); when the modulation trains (train_mode='full', training.py:75-91) the backward also emits
+    dy * xhat and two grouped column sums give d(scale) / d(shift)."""
+    if with_res:
+        return NormModResFn.apply(x, scale, shift, rows_per_mod, eps, layernorm)
+    return NormModFn.apply(x, scale, shift, rows_per_mod, eps, layernorm), None
 
 
 def gate_residual(u, gate, rows_per_gate, res):
@@ -841,7 +885,7 @@ class SelfAttnFn(torch.autograd.Function):
     def forward(ctx, x, Wqkv, bqkv, wqn, wkn, cos, sin, Wo, bo, gate, rows_per_gate, res, key_bias, B, H, N,
                 scale, sp=None, batch_keep=None, pass_input=False):
         M, D = x.shape[0], H * 64
-        qkv = gemm(x, Wqkv, bias=bqkv)  # one [M,3D] GEMM against the cached [3D,D] weight concatenation
+        qkv = gemm(x, Wqkv, bias=bqkv)  # one [M,3D] GEMM against the [3D,D] weight concatenation
         qk = torch.empty((M, 2 * D), device=x.device, dtype=BF16)
         qknorm_rope_fwd(qkv[:, :D], qkv[:, D:2 * D], wqn, wkn, cos, sin, qk[:, :D], qk[:, D:])
         kv = None
@@ -859,19 +903,28 @@ class SelfAttnFn(torch.autograd.Function):
                 kv = torch.stack([k_all, v_all])  # [2, P*n, D] kept for the backward
             else:
                 o, lse, kv = ring.ring_fwd(qk[:, :D], qk[:, D:], qkv[:, 2 * D:], sp.group, B, H, N, scale, sp.impl)
-        y = gemm(o, Wo, bias=bo, gate=gate, rows_per_gate=rows_per_gate, res=res)
-        ctx.save_for_backward(qkv, qk, o, lse, Wqkv, wqn, wkn, cos, sin, Wo, gate, key_bias, kv)
+        u = None
+        if gate is not None and ctx.needs_input_grad[9]:   # trainable gate: stash the pre-gate output (see LinearFn)
+            u = torch.empty((M, Wo.shape[0]), device=x.device, dtype=BF16)
+        y = gemm(o, Wo, bias=bo, gate=gate, rows_per_gate=rows_per_gate, res=res, aux=u,
+                 epilogue=EPI_STASH if u is not None else EPI_NONE)
+        train_w = ctx.needs_input_grad[1] or ctx.needs_input_grad[2]
+        ctx.save_for_backward(qkv, qk, o, lse, Wqkv, wqn, wkn, cos, sin, Wo, gate, key_bias, kv, u, x if train_w else None)
         ctx.meta = (B, H, N, scale, rows_per_gate, res is not None, sp)
         return y
 
     @staticmethod
     def backward(ctx, dy):
-        qkv, qk, o, lse, Wqkv, wqn, wkn, cos, sin, Wo, gate, key_bias, kv = ctx.saved_tensors
+        qkv, qk, o, lse, Wqkv, wqn, wkn, cos, sin, Wo, gate, key_bias, kv, u, x = ctx.saved_tensors
         B, H, N, scale, rpg, has_res, sp = ctx.meta
+        need = ctx.needs_input_grad
         D = H * 64
         M = qkv.shape[0]
         dy = dy if dy.stride(1) == 1 else dy.contiguous()
         g = rowscale(dy, gate, rpg) if gate is not None else dy
+        dgate = _group_grad(dy, u, rpg, gate) if (need[9] and u is not None) else None
+        dWo = gemm(g, o, a_rows_are_k=True, b_rows_are_k=True) if need[7] else None
+        dbo = colsum_groups(g)[0].to(BF16) if need[8] else None
         do = gemm(g, Wo, b_rows_are_k=True)
         dqkv = torch.empty((M, 3 * D), device=dy.device, dtype=BF16)
         if sp is None:
@@ -887,7 +940,15 @@ class SelfAttnFn(torch.autograd.Function):
                 dq32, dkv = ring.ring_bwd(qk[:, :D], kv, o, do, lse, sp.group, B, H, N, scale, sp.impl)
                 dk_post = dkv[0]  # fp32, fully reduced over the ring
                 dqkv[:, 2 * D:].copy_(dkv[1])
-        qknorm_rope_bwd(dq32, dk_post, qkv[:, :D], qkv[:, D:2 * D], wqn, wkn, cos, sin, dqkv[:, :D], dqkv[:, D:2 * D])
-        dx = gemm(dqkv, Wqkv, b_rows_are_k=True) if ctx.needs_input_grad[0] else None
-        dres = dy if (has_res and ctx.needs_input_grad[11]) else None
-        return (dx,) + (None,) * 10 + (dres,) + (None,) * 8
+        train_n = need[3] or need[4]
+        pq = torch.empty((M, D), device=dy.device, dtype=BF16) if train_n else None
+        pk = torch.empty((M, D), device=dy.device, dtype=BF16) if train_n else None
+        qknorm_rope_bwd(dq32, dk_post, qkv[:, :D], qkv[:, D:2 * D], wqn, wkn, cos, sin, dqkv[:, :D], dqkv[:, D:2 * D],
+                        prod_q=pq, prod_k=pk)
+        dwqn = colsum_groups(pq)[0].to(wqn.dtype) if need[3] else None
+        dwkn = colsum_groups(pk)[0].to(wkn.dtype) if need[4] else None
+        dx = gemm(dqkv, Wqkv, b_rows_are_k=True) if need[0] else None
+        dWqkv = gemm(dqkv, x, a_rows_are_k=True, b_rows_are_k=True) if need[1] else None   # [3D, D]: q | k | v rows
+        dbqkv = colsum_groups(dqkv)[0].to(BF16) if need[2] else None
+        dres = dy if (has_res and need[11]) else None
+        return (dx, dWqkv, dbqkv, dwqn, dwkn, None, None, dWo, dbo, dgate, None, dres) + (None,) * 8

@@ -106,9 +106,12 @@ class GraphedTrainStep:
                 bucketer.zero_grad()
             else:
                 optimizer.zero_grad(set_to_none=True)
+            ops.side_stream_used = False
             loss, rel_mse, nrmse, _ = train_step(model, self.static, *args, device=device)
             loss.backward()
-            if ops.side_stream is not None:   # the LoRA weight gradients queued off the critical path: join them
+            # the LoRA weight gradients queued off the critical path: join them (a stream nothing was forked onto --
+            # train_mode="full" has no adapters -- must not be waited on inside a capture)
+            if ops.side_stream is not None and ops.side_stream_used:
                 torch.cuda.current_stream(device).wait_stream(ops.side_stream)
             return loss.detach(), rel_mse.detach(), nrmse.detach()
 
