@@ -259,7 +259,9 @@ ATTN_CASES = [(1, 2, 128, 128, False), (2, 4, 96, 96, False), (1, 2, 300, 300, F
               # >= 512 keys: the double-buffered forward (ragged last key step, bias path, several ring wraps)
               (2, 3, 700, 1000, False), (1, 2, 640, 1111, True), (1, 8, 2048, 1536, False), (1, 1, 130, 577, False),
               # 320 work items on 296 CTA slots: the 24 items of the last wave are split along the keys (3 / 2 parts)
-              (1, 32, 1280, 1536, False), (1, 32, 1200, 1111, True)]
+              (1, 32, 1280, 1536, False), (1, 32, 1200, 1111, True),
+              # backward: 320 key-tile items on 148 SMs -> the 24 items of the last wave split 2-way along the queries
+              (1, 32, 2100, 1280, False)]
 
 
 def _mask_bias(kind, B, Nk):

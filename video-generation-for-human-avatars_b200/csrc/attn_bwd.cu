@@ -33,6 +33,8 @@
 // Four further warps do everything that is not arithmetic: they stream lse/delta into shared memory two
 // tiles ahead and drain dQ(i) (TMEM -> per-warp swizzled staging -> TMA reduce-add) without a CTA-wide
 // barrier, so the compute warps execute nothing but the element-wise math.
+#include <stdlib.h>
+
 #include "api_internal.h"
 #include "common.cuh"
 #include "tmap.h"
@@ -57,6 +59,11 @@ struct FaBwdParams {
   int q_splits;     // > 1: the query tiles are divided among q_splits CTAs per key tile (few key tiles: attn2)
   float* part_dk;   // [q_splits][B*Nk][H*64] fp32 partial dK / dV, summed by fa_bwd_reduce_kernel
   float* part_dv;
+  // many key tiles (attn1): 1-D grid over the (key tile, head, batch) items; the items of a sparsely filled LAST wave
+  // (linear id >= n_whole) are each walked by `tail_parts` CTAs over disjoint query-tile ranges whose fp32 dK / dV
+  // partials go to tail_ws [(item - n_whole) * tail_parts + part][128 rows][dK 64 | dV 64] (fa_bwd_tail_reduce_kernel)
+  int k_tiles, n_whole, tail_parts;
+  float* tail_ws;
 };
 
 constexpr int FA_MASK_SCAN_MAX = 1024;  // key counts up to which the bias vector is scanned for masked key tiles
@@ -117,11 +124,29 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
                  all_done = bar + 120, kv_tmem = bar + 128, tmem_slot = bar + 136;
   float* stat = reinterpret_cast<float*>(smem_raw + (sStat - sbase));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int kt = blockIdx.x, h = blockIdx.y;
-  const int b = blockIdx.z / p.q_splits, split = blockIdx.z % p.q_splits;
+  int kt, h, b, split, splits = p.q_splits, tail_slot = -1;
+  if (p.k_tiles > 0) {   // 1-D grid (attn1)
+    int item = blockIdx.x;
+    split = 0;
+    if (item >= p.n_whole) {
+      const int e = item - p.n_whole;
+      item = p.n_whole + e / p.tail_parts;
+      split = e % p.tail_parts;
+      splits = p.tail_parts;
+      tail_slot = e;
+    }
+    kt = item % p.k_tiles;
+    h = (item / p.k_tiles) % p.H;
+    b = item / (p.k_tiles * p.H);
+  } else {
+    kt = blockIdx.x;
+    h = blockIdx.y;
+    b = blockIdx.z / p.q_splits;
+    split = blockIdx.z % p.q_splits;
+  }
   // this CTA's query tiles: [t0, t0 + T)
-  const int t0 = (int)((int64_t)split * p.q_tiles / p.q_splits);
-  const int T = (int)((int64_t)(split + 1) * p.q_tiles / p.q_splits) - t0;
+  const int t0 = (int)((int64_t)split * p.q_tiles / splits);
+  const int T = (int)((int64_t)(split + 1) * p.q_tiles / splits) - t0;
 
   // A key tile whose keys all carry a bias <= -9000 (the reference's -10000 mask, transformer3d.py:440-445) while
   // some other key of the batch entry is unmasked has P = 0 exactly (exp of < -900 underflows in fp32): dK = dV = 0
@@ -144,9 +169,12 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
         const int r = idx >> 3, c8 = (idx & 7) * 8;
         const int key_r = kt * 128 + r;
         if (key_r >= p.Nk) continue;
-        if (p.q_splits == 1) {
+        if (splits == 1) {
           *reinterpret_cast<uint4*>(p.dk + ((int64_t)b * p.Nk + key_r) * p.lddk + h * 64 + c8) = make_uint4(0, 0, 0, 0);
           *reinterpret_cast<uint4*>(p.dv + ((int64_t)b * p.Nk + key_r) * p.lddv + h * 64 + c8) = make_uint4(0, 0, 0, 0);
+        } else if (tail_slot >= 0) {
+          float4* t4 = reinterpret_cast<float4*>(p.tail_ws + ((int64_t)tail_slot * 128 + r) * 128);
+          t4[(c8 >> 2)] = t4[(c8 >> 2) + 1] = t4[16 + (c8 >> 2)] = t4[16 + (c8 >> 2) + 1] = make_float4(0.f, 0.f, 0.f, 0.f);
         } else {
           const int64_t prow = ((int64_t)split * p.B + b) * p.Nk + key_r;
           float4* pk4 = reinterpret_cast<float4*>(p.part_dk + prow * (p.H * 64) + h * 64 + c8);
@@ -378,7 +406,17 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
       tmem_ld16(tdV + lane_bits + part * 16, rv);
       tmem_ld16(tdK + lane_bits + part * 16, rk);
       tmem_ld_wait();
-      if (key_ok && p.q_splits == 1) {
+      if (tail_slot >= 0) {
+        // one of several CTAs on this key tile (sparse last wave): fp32 partials, rows past Nk included (never read)
+        float* dst = p.tail_ws + ((int64_t)tail_slot * 128 + row) * 128 + part * 16;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          *reinterpret_cast<float4*>(dst + g * 4) = make_float4(__uint_as_float(rk[g * 4]), __uint_as_float(rk[g * 4 + 1]),
+                                                                __uint_as_float(rk[g * 4 + 2]), __uint_as_float(rk[g * 4 + 3]));
+          *reinterpret_cast<float4*>(dst + 64 + g * 4) = make_float4(__uint_as_float(rv[g * 4]), __uint_as_float(rv[g * 4 + 1]),
+                                                                     __uint_as_float(rv[g * 4 + 2]), __uint_as_float(rv[g * 4 + 3]));
+        }
+      } else if (key_ok && splits == 1) {
         bf16* dkr = p.dk + ((int64_t)b * p.Nk + key) * p.lddk + h * 64 + part * 16;
         bf16* dvr = p.dv + ((int64_t)b * p.Nk + key) * p.lddv + h * 64 + part * 16;
 #pragma unroll
@@ -506,6 +544,52 @@ __global__ void __launch_bounds__(256) fa_bwd_reduce_kernel(const float* __restr
   *reinterpret_cast<uint4*>(dv + r * lddv + c) = u;
 }
 
+// dk/dv (bf16) of the split items of the last wave = sum over their `tail_parts` fp32 partials; 8 columns per thread.
+__global__ void __launch_bounds__(256) fa_bwd_tail_reduce_kernel(const FaBwdParams p, int n_split) {
+  const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;   // (split item, row, 16 groups of 8 columns)
+  if (gid >= (int64_t)n_split * 128 * 16) return;
+  const int c8 = (int)(gid & 15) * 8, row = (int)((gid >> 4) & 127), si = (int)(gid >> 11);
+  const int item = p.n_whole + si;
+  const int kt = item % p.k_tiles, h = (item / p.k_tiles) % p.H, b = item / (p.k_tiles * p.H);
+  const int key = kt * 128 + row;
+  if (key >= p.Nk) return;
+  float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  for (int t = 0; t < p.tail_parts; ++t) {
+    const float* src = p.tail_ws + (((int64_t)si * p.tail_parts + t) * 128 + row) * 128 + c8;
+    const float4 a0 = *reinterpret_cast<const float4*>(src), a1 = *reinterpret_cast<const float4*>(src + 4);
+    acc[0] += a0.x; acc[1] += a0.y; acc[2] += a0.z; acc[3] += a0.w; acc[4] += a1.x; acc[5] += a1.y; acc[6] += a1.z; acc[7] += a1.w;
+  }
+  uint4 u;
+  u.x = pack_bf16x2(acc[0], acc[1]); u.y = pack_bf16x2(acc[2], acc[3]); u.z = pack_bf16x2(acc[4], acc[5]); u.w = pack_bf16x2(acc[6], acc[7]);
+  bf16* dst = c8 < 64 ? p.dk + ((int64_t)b * p.Nk + key) * p.lddk + h * 64 + c8
+                      : p.dv + ((int64_t)b * p.Nk + key) * p.lddv + h * 64 + (c8 - 64);
+  *reinterpret_cast<uint4*>(dst) = u;
+}
+
+// attn1: one CTA per SM; 1536 items on 148 SMs are 10.4 waves, i.e. 56 CTAs alone on the machine for a whole CTA
+// lifetime.  The items of such a sparse last wave are split over `parts` CTAs along the query walk.
+static void fa_bwd_tail_plan(int items, int q_tiles, int* n_whole, int* parts) {
+  static int slots = 0;
+  if (!slots) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&slots, cudaDevAttrMultiProcessorCount, dev);
+    if (slots <= 0) slots = 148;
+  }
+  *n_whole = items;
+  *parts = 1;
+  static const bool off = [] { const char* e = getenv("B200_FA_BWD_NO_TAIL"); return e && e[0] == '1'; }();
+  if (off) return;
+  const int r = items % slots;
+  if (items < slots || r == 0 || r * 4 > slots * 3) return;
+  int pr = slots / r;
+  if (pr > 4) pr = 4;
+  if (pr > q_tiles / 8) pr = q_tiles / 8;   // at least 8 query tiles per part
+  if (pr < 2) return;
+  *n_whole = items - r;
+  *parts = pr;
+}
+
 // How many CTAs share one key tile's query walk: enough to cover the SMs when there are few key tiles.
 static int fa_bwd_splits(int B, int H, int Nq, int Nk, bool masked) {
   const int64_t ctas = (int64_t)((Nk + 127) / 128) * H * B;
@@ -533,7 +617,11 @@ extern "C" int b200_debug_bwd_trace(unsigned long long* host, int n) {
 extern "C" int64_t b200_fa_bwd_workspace_bytes(int B, int H, int Nq, int Nk) {
   if (B <= 0 || H <= 0 || Nq <= 0 || Nk <= 0) return 0;
   const int s = fa_bwd_splits(B, H, Nq, Nk, true);  // upper bound over both split choices
-  return s > 1 ? (int64_t)2 * s * B * Nk * H * 64 * (int64_t)sizeof(float) : 0;
+  if (s > 1) return (int64_t)2 * s * B * Nk * H * 64 * (int64_t)sizeof(float);
+  int n_whole, parts;
+  const int items = ((Nk + 127) / 128) * H * B;
+  fa_bwd_tail_plan(items, (Nq + 127) / 128, &n_whole, &parts);
+  return (int64_t)(items - n_whole) * parts * 128 * 128 * (int64_t)sizeof(float);
 }
 
 extern "C" int b200_fa_bwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v,
@@ -586,8 +674,26 @@ extern "C" int b200_fa_bwd(const void* q, int64_t ldq, const void* k, int64_t ld
       return launch_status("fa_bwd: cudaFuncSetAttribute");
     attr_set = true;
   }
+  p.k_tiles = 0; p.n_whole = 0; p.tail_parts = 1; p.tail_ws = nullptr;
   dim3 grid((Nk + 127) / 128, H, B * p.q_splits);
+  int n_split = 0;
+  if (p.q_splits == 1) {   // 1-D grid, the items of a sparse last wave split along the query walk (needs the workspace)
+    const int items = (int)(grid.x * grid.y * grid.z);
+    p.k_tiles = (int)grid.x;
+    p.n_whole = items;
+    if (workspace != nullptr && al16(workspace)) {
+      fa_bwd_tail_plan(items, p.q_tiles, &p.n_whole, &p.tail_parts);
+      n_split = items - p.n_whole;
+      if ((int64_t)n_split * p.tail_parts * 128 * 128 * (int64_t)sizeof(float) > workspace_bytes) {
+        p.n_whole = items; p.tail_parts = 1; n_split = 0;
+      }
+      p.tail_ws = (float*)workspace;
+    }
+    grid = dim3((unsigned)(p.n_whole + n_split * p.tail_parts), 1, 1);
+  }
   fa_bwd_kernel<<<grid, FA_BWD_THREADS, FA_BWD_SMEM, (cudaStream_t)stream>>>(tmQ, tmK, tmV, tmdO, tmdQ, p);
+  if (n_split > 0)
+    fa_bwd_tail_reduce_kernel<<<(unsigned)(((int64_t)n_split * 128 * 16 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(p, n_split);
   if (p.q_splits > 1) {
     const int64_t rows = (int64_t)B * Nk, threads = rows * (H * 64 / 8);
     fa_bwd_reduce_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
