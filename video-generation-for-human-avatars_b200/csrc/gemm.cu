@@ -31,6 +31,7 @@ enum { EPI_NONE = 0, EPI_GELU = 1, EPI_GELU_GRAD = 2, EPI_STASH = 3 };  // STASH
 struct GemmParams {
   int M, N;
   int m_tiles, n_tiles;
+  int group_m;   // tile rasterisation: groups of `group_m` tile rows x all tile columns are walked one after the other
   int kb1, kb2;  // 64-wide k blocks taken from (A,B) and from (A2,B2)
   int splits;    // split-K factor: work item = (tile, split); > 1 only for plain fp32 outputs (atomic accumulate)
   int epi, out_f32;
@@ -55,6 +56,19 @@ struct GemmParams {
   float* sk_ws;   // [CTA or pair][rank][BN / 4][128][4] fp32 partial accumulators
   int* sk_flags;  // [CTA or pair][rank][8 epilogue warps], zero between launches (the consumer clears them)
 };
+
+// Tile id -> (tile row, tile column).  Plain column-major order made every wave of CTAs touch ~3 tile columns and ALL
+// tile rows' worth of A only a few at a time: at K = 8192 the 100 MB A operand was re-streamed per tile column
+// (ncu: 339 MB of DRAM reads against 134 MB algorithmic).  Grouped order: a wave covers `group_m` tile rows x every
+// tile column, so an A tile row is read from DRAM once and re-used out of L2 by all its tile columns.
+__device__ __forceinline__ void tile_coords(const GemmParams& p, int tile, int& tm, int& tn) {
+  const int gsize = p.group_m * p.n_tiles;
+  const int gid = tile / gsize, in = tile - gid * gsize;
+  const int first = gid * p.group_m;
+  const int rows = min(p.m_tiles - first, p.group_m);
+  tn = in / rows;
+  tm = first + (in - tn * rows);
+}
 
 // One unit of work of the persistent walk: k blocks [kb_begin, kb_end) of output tile `tile` (z = split-K slice or
 // batch group).  role: 0 = a whole tile, 1 = partial that is dumped for another CTA, 2 = partial that owns the tile's
@@ -248,7 +262,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     GemmUnit u;
     while (walk.next(u)) {
       const int tile = u.tile;
-      const int mt = (tile % p.m_tiles) * (CTA2 ? 2 : 1) + rank, nt = tile / p.m_tiles;
+      int tm, nt;
+      tile_coords(p, tile, tm, nt);
+      const int mt = tm * (CTA2 ? 2 : 1) + rank;
       const int g = p.groups > 1 ? u.z : 0;
       for (int kb = u.kb_begin; kb < u.kb_end; ++kb) {
         mbar_wait(empty_bar(stage), phase ^ 1);
@@ -337,7 +353,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     GemmUnit u;
     while (walk.next(u)) {
       const int tile = u.tile;
-      const int mt = (tile % p.m_tiles) * (CTA2 ? 2 : 1) + rank, nt = tile / p.m_tiles;
+      int tm, nt;
+      tile_coords(p, tile, tm, nt);
+      const int mt = tm * (CTA2 ? 2 : 1) + rank;
       const int g = p.groups > 1 ? u.z : 0;
       const int crow = g * p.c_gr, ccol = g * p.c_gc;  // output displacement of this group
       mbar_wait(tfull_bar(acc), acc_phase);
@@ -706,6 +724,18 @@ static int gemm_impl(const void* A, int64_t lda, int a_kmajor_rows_are_k, const 
   p.M = M; p.N = N;
   p.m_tiles = pair ? (M + 255) / 256 : (M + 127) / 128;
   p.n_tiles = (N + bn - 1) / bn;
+  {
+    // one wave of concurrent CTAs (pairs) ~ group_m tile rows x all tile columns
+    static const int fixed = [] { const char* e = getenv("B200_GEMM_GROUP_M"); return e ? atoi(e) : 0; }();
+    const int conc = pair ? num_sms() / 2 : num_sms();
+    int gm = fixed > 0 ? fixed : (conc + p.n_tiles / 2) / p.n_tiles;
+    // operands that fit the 126 MB L2 together are re-used there whatever the order (measured: the plain order is
+    // ~1 % faster at K = 2048); group only when they do not (K = 8192 / 6144: 339 -> 211 MB of DRAM reads, 3-4 % faster)
+    if (fixed <= 0 && ((int64_t)M + N) * (int64_t)(K + K2) * 2 <= (int64_t)64 << 20) gm = p.m_tiles;
+    if (gm < 1) gm = 1;
+    if (gm > p.m_tiles) gm = p.m_tiles;
+    p.group_m = gm;
+  }
   p.kb1 = (K + 63) / 64;
   p.kb2 = (K2 + 63) / 64;
   p.epi = epilogue; p.out_f32 = out_is_f32;
