@@ -381,13 +381,16 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
 #ifndef FA2_F32X2
 #define FA2_F32X2 1  // FFMA2 / FADD2 (fp32x2) for the score scaling and the row sum
 #endif
+#ifndef FA2_TPR
+#define FA2_TPR 1      // threads per query row in fa_fwd_db_kernel (1 or 2; 2 measured 8 % slower: 409 vs 377 us at cfg2)
+#endif
 #ifndef FA2_ROWSUM_MMA
 #define FA2_ROWSUM_MMA 0   // row sums of P from the tensor pipe (a constant ones column appended to V) instead of 64 FADDs
 #endif
 constexpr int FA2_STAGE_BYTES = 2 * FA_BN * 128;                   // K and V tile of one 64-key step
 constexpr int FA2_ONES_BYTES = FA_BN * 128;                        // constant B-operand atom: column 0 = 1, the rest 0
-constexpr int FA2_SMEM = 16384 + FA2_STAGES * FA2_STAGE_BYTES + FA2_ONES_BYTES + 256 + 256;
-constexpr int FA2_THREADS = 192;
+constexpr int FA2_SMEM = 16384 + FA2_STAGES * FA2_STAGE_BYTES + FA2_ONES_BYTES + 256 + 256 + 2048;  // + row max / sum exchange
+constexpr int FA2_THREADS = 64 + 128 * FA2_TPR;
 constexpr int FA2_MIN_KEYS = 512;                                  // below: the 4-CTA kernel above (attn2)
 constexpr int FA2_O_COLS = FA2_ROWSUM_MMA ? 80 : 64;               // O | row-sum column (+15 unused) in TMEM
 
@@ -419,8 +422,12 @@ __device__ __forceinline__ float2 ex2_poly2(float2 x) {
 }
 
 // GENERAL: a per-key bias and / or a ragged last key step (the per-key term is staged in shared memory per step)
-template <bool GENERAL>
-__global__ void __launch_bounds__(FA2_THREADS, 2)
+//   TPR (threads per query row) = 2: eight softmax warps per CTA, the two warps of a TMEM lane quadrant each take 32 of
+//   the 64 scores of a row (row max exchanged through shared memory behind one 64-thread named barrier per step): four
+//   softmax warps per scheduler instead of two.  With one thread per row neither the exp unit (61 %) nor the issue slots
+//   (56 %) were saturated -- two warps per scheduler cannot cover each other's dependent-issue latencies.
+template <bool GENERAL, int TPR>
+__global__ void __launch_bounds__(64 + 128 * TPR, 2)
 fa_fwd_db_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                  const __grid_constant__ CUtensorMap tmV, const __grid_constant__ FaFwdParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -448,13 +455,13 @@ fa_fwd_db_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   }
   const int qt = item % p.q_tiles, h = (item / p.q_tiles) % p.H, b = item / (p.q_tiles * p.H);
   if (p.batch_keep != nullptr && p.batch_keep[b] == 0.f) {
-    if (part <= 0) fa_copy_values(p, qt, h, b, FA2_THREADS);
+    if (part <= 0) fa_copy_values(p, qt, h, b, 64 + 128 * TPR);
     return;
   }
 
   if (FA2_ROWSUM_MMA) {
     // the ones atom, in the layout TMA gives a V tile (64 key rows of 128 swizzled bytes): element (row, column 0) = 1
-    for (int i = threadIdx.x; i < FA2_ONES_BYTES / 16; i += FA2_THREADS) {
+    for (int i = threadIdx.x; i < FA2_ONES_BYTES / 16; i += 64 + 128 * TPR) {
       const int r = i >> 3, c = i & 7;
       const uint32_t v0 = (c == (r & 7)) ? 0x00003F80u : 0u;   // bf16 1.0 in the low half: column 0 sits in chunk 0 ^ (r & 7)
       asm volatile("st.shared.v4.b32 [%0], {%1, %2, %2, %2};" ::"r"(sOnes + i * 16), "r"(v0), "r"(0u) : "memory");
@@ -470,11 +477,11 @@ fa_fwd_db_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     tma_prefetch_desc(&tmK);
     tma_prefetch_desc(&tmV);
     mbar_init(q_full, 1);
-    mbar_init(q_tmem, 128);
+    mbar_init(q_tmem, 128 * TPR);
     for (int s = 0; s < 2; ++s) {
       mbar_init(pv_done0 + 8 * s, 1);
       mbar_init(s_full0 + 8 * s, 1);
-      mbar_init(p_full0 + 8 * s, 128);
+      mbar_init(p_full0 + 8 * s, 128 * TPR);
     }
     for (int s = 0; s < FA2_STAGES; ++s) {
       mbar_init(kv_full0 + 8 * s, 1);
@@ -556,19 +563,25 @@ fa_fwd_db_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       }
     }
   } else if (warp >= 2) {
+    constexpr int NC = 64 / TPR;        // scores of a row held by this thread
+    constexpr int NCH = NC / 32;        // ... in 32-column TMEM chunks
     const int quad = warp & 3;
+    const int half = TPR == 2 ? (warp - 2) >> 2 : 0;   // which 32 of the 64 key columns (TPR = 2)
     const int row = quad * 32 + lane;
+    const int st = threadIdx.x - 64;    // softmax-thread index
     const uint32_t lane_bits = (uint32_t)(quad * 32) << 16;
+    float* xch = kb_stage + 64;         // [2 steps][2 halves][128 rows] row-max / row-sum exchange (TPR = 2)
     // Q row -> TMEM as the packed-bf16 A operand: 128 bytes = 8 swizzled 16-byte chunks = 32 columns
     mbar_wait(q_full, 0);
     {
-      uint32_t rq[32];
+      uint32_t rq[32 / TPR];
 #pragma unroll
-      for (int c = 0; c < 8; ++c)
+      for (int c = 0; c < 8 / TPR; ++c)
         asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
                      : "=r"(rq[c * 4]), "=r"(rq[c * 4 + 1]), "=r"(rq[c * 4 + 2]), "=r"(rq[c * 4 + 3])
-                     : "r"(sQ + sw128_off(row, c)));
-      tmem_st32(tQ + lane_bits, rq);
+                     : "r"(sQ + sw128_off(row, half * 4 + c)));
+      if (TPR == 1) tmem_st32(tQ + lane_bits, *reinterpret_cast<uint32_t(*)[32]>(rq));
+      else tmem_st16(tQ + lane_bits + half * 16, *reinterpret_cast<uint32_t(*)[16]>(rq));
       tmem_st_wait();
       tc_fence_before();
       mbar_arrive(q_tmem);
@@ -582,32 +595,40 @@ fa_fwd_db_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     for (int j = 0; j < T; ++j) {
       if (GENERAL) {
         const int key0 = (j_begin + j) * FA_BN;
-        named_bar_sync(1, 128);
-        if (row < FA_BN) {
-          const int key = key0 + row;
-          kb_stage[row] = key < p.Nk ? (kb ? kb[key] * kLog2e : 0.f) : -INFINITY;
+        named_bar_sync(1, 128 * TPR);
+        if (st < FA_BN) {
+          const int key = key0 + st;
+          kb_stage[st] = key < p.Nk ? (kb ? kb[key] * kLog2e : 0.f) : -INFINITY;
         }
-        named_bar_sync(1, 128);
+        named_bar_sync(1, 128 * TPR);
       }
-      const uint32_t t_row = tS + (j & 1) * 64 + lane_bits;
+      const uint32_t t_buf = tS + (j & 1) * 64 + lane_bits;
       mbar_wait(s_full0 + 8 * (j & 1), (j >> 1) & 1);
       tc_fence_after();
-      uint32_t r0[32], r1[32];
-      tmem_ld32(t_row, r0);
-      tmem_ld32(t_row + 32, r1);
+      uint32_t r[NCH][32];
+#pragma unroll
+      for (int c = 0; c < NCH; ++c) tmem_ld32(t_buf + half * 32 + c * 32, r[c]);
       tmem_ld_wait();
       if (GENERAL) {
-        chunk_add_bias(r0, sl2, kb_stage);
-        chunk_add_bias(r1, sl2, kb_stage + 32);
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) chunk_add_bias(r[c], sl2, kb_stage + half * 32 + c * 32);
       }
       float a0 = -INFINITY, a1 = -INFINITY, a2 = -INFINITY, a3 = -INFINITY;
-      chunk_max(r0, a0, a1, a2, a3);
-      chunk_max(r1, a0, a1, a2, a3);
-      const float mx = fmaxf(fmaxf(a0, a1), fmaxf(a2, a3)) * mul;
+#pragma unroll
+      for (int c = 0; c < NCH; ++c) chunk_max(r[c], a0, a1, a2, a3);
+      float mx = fmaxf(fmaxf(a0, a1), fmaxf(a2, a3)) * mul;
+      if (TPR == 2) {
+        // the other half of the row lives in the partner warp of this lane quadrant
+        float* slot = xch + (j & 1) * 256;
+        slot[half * 128 + row] = mx;
+        named_bar_sync(2 + quad, 64);
+        mx = fmaxf(mx, slot[(half ^ 1) * 128 + row]);
+      }
       const float m_new = fmaxf(m_used, mx);
       const bool need = m_new > m_used + 8.f;
       if (__any_sync(0xffffffffu, need)) {
-        // lazy rescale: O and l follow the running max only when it has grown by more than 2^8
+        // lazy rescale: O and l follow the running max only when it has grown by more than 2^8 (both threads of a
+        // row see the same m_used / m_new, so both warps of a quadrant take this branch together)
         const float alpha = ex2_approx(m_used - m_new);  // 0 on the first step (m_used = -inf)
         m_used = m_new;
         l0 *= alpha; l1 *= alpha; l2 *= alpha; l3 *= alpha;
@@ -616,44 +637,38 @@ fa_fwd_db_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
           mbar_wait(pv_done0 + 8 * ((j - 1) & 1), ((j - 1) >> 1) & 1);
           tc_fence_after();
 #pragma unroll 1
-          for (int c = 0; c < FA2_O_COLS / 16; ++c) {
+          for (int c = 0; c < FA2_O_COLS / 16 / TPR; ++c) {
             uint32_t ro[16];
-            tmem_ld16(tO + lane_bits + c * 16, ro);
+            const uint32_t ta = tO + lane_bits + half * (FA2_O_COLS / 2) + c * 16;
+            tmem_ld16(ta, ro);
             tmem_ld_wait();
 #pragma unroll
             for (int i = 0; i < 16; ++i) ro[i] = __float_as_uint(__uint_as_float(ro[i]) * alpha);
-            tmem_st16(tO + lane_bits + c * 16, ro);
+            tmem_st16(ta, ro);
           }
         }
       }
       const float neg_m = -m_used;
-      uint32_t pk[32];
-#if FA2_F32X2
+      uint32_t pk[NC / 2];
       // packed fp32x2 arithmetic (FFMA2 / FADD2): x = s * mul - m and the row sum take one instruction per PAIR of
       // scores -- the softmax warps are issue-bound between their exponentials, not FMA-pipe bound
       const float2 mul2 = make_float2(mul, mul), negm2 = make_float2(neg_m, neg_m);
       float2 la = make_float2(l0, l1), lb = make_float2(l2, l3);
 #pragma unroll
-      for (int hf = 0; hf < 2; ++hf) {
-        const uint32_t (&r)[32] = hf ? r1 : r0;
+      for (int hf = 0; hf < NCH; ++hf) {
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
           float2 pv[4];
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
-            const float2 x = __ffma2_rn(make_float2(__uint_as_float(r[g * 8 + 2 * i]), __uint_as_float(r[g * 8 + 2 * i + 1])),
-                                        mul2, negm2);
-#if FA2_POLY_PAIRS
+            const float2 x = __ffma2_rn(make_float2(__uint_as_float(r[hf][g * 8 + 2 * i]),
+                                                    __uint_as_float(r[hf][g * 8 + 2 * i + 1])), mul2, negm2);
             if (i < FA2_POLY_PAIRS) {
               pv[i] = ex2_poly2(x);
             } else {
               pv[i].x = ex2_approx(x.x);
               pv[i].y = ex2_approx(x.y);
             }
-#else
-            pv[i].x = (2 * i < FA2_POLY) ? ex2_poly(x.x) : ex2_approx(x.x);
-            pv[i].y = (2 * i + 1 < FA2_POLY) ? ex2_poly(x.y) : ex2_approx(x.y);
-#endif
           }
           la = __fadd2_rn(la, __fadd2_rn(pv[0], pv[2]));
           lb = __fadd2_rn(lb, __fadd2_rn(pv[1], pv[3]));
@@ -662,32 +677,9 @@ fa_fwd_db_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         }
       }
       l0 = la.x; l1 = la.y; l2 = lb.x; l3 = lb.y;
-#else
-#pragma unroll
-      for (int hf = 0; hf < 2; ++hf) {
-        const uint32_t (&r)[32] = hf ? r1 : r0;
-#pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          float pv[8];
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const float x = fmaf(__uint_as_float(r[g * 8 + i]), mul, neg_m);
-            pv[i] = (i < FA2_POLY) ? ex2_poly(x) : ex2_approx(x);
-          }
-          if (!FA2_ROWSUM_MMA) {
-            l0 += pv[0] + pv[4];
-            l1 += pv[1] + pv[5];
-            l2 += pv[2] + pv[6];
-            l3 += pv[3] + pv[7];
-          }
-          pk[hf * 16 + g * 4 + 0] = pack_bf16x2(pv[0], pv[1]);
-          pk[hf * 16 + g * 4 + 1] = pack_bf16x2(pv[2], pv[3]);
-          pk[hf * 16 + g * 4 + 2] = pack_bf16x2(pv[4], pv[5]);
-          pk[hf * 16 + g * 4 + 3] = pack_bf16x2(pv[6], pv[7]);
-        }
-      }
-#endif
-      tmem_st32(t_row, pk);   // P(j): 64 keys as 32 packed columns over the first half of S(j)
+      // P(j): 64 keys as 32 packed columns over the first half of S(j); this thread's keys -> its NC / 2 columns
+      if (TPR == 1) tmem_st32(t_buf, *reinterpret_cast<uint32_t(*)[32]>(pk));
+      else tmem_st16(t_buf + half * 16, *reinterpret_cast<uint32_t(*)[16]>(pk));
       tmem_st_wait();
       tc_fence_before();
       mbar_arrive(p_full0 + 8 * (j & 1));
@@ -695,43 +687,44 @@ fa_fwd_db_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     mbar_wait(pv_done0 + 8 * ((T - 1) & 1), ((T - 1) >> 1) & 1);
     tc_fence_after();
     float l = (l0 + l1) + (l2 + l3);
-    if (FA2_ROWSUM_MMA) {
-      uint32_t rl[16];
-      tmem_ld16(tO + lane_bits + 64, rl);   // column 64: sum over all keys of the bf16 P the O columns were built from
-      tmem_ld_wait();
-      l = __uint_as_float(rl[0]);
+    if (TPR == 2) {   // row sum = this thread's half + the partner's
+      float* slot = xch + (T & 1) * 256;
+      slot[half * 128 + row] = l;
+      named_bar_sync(2 + quad, 64);
+      l += slot[(half ^ 1) * 128 + row];
     }
     const int q = qt * 128 + row;
+    constexpr int OC = 64 / TPR;   // O columns this thread writes out
     if (part >= 0) {
       // one of several CTAs on this item: leave the un-normalised accumulator and the softmax state for the merge
       float* dst = p.part_ws + ((((int64_t)(item - p.n_whole) * p.parts + part) * 128) + row) * FA2_PART_LD;
 #pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        uint32_t r[16];
-        tmem_ld16(tO + lane_bits + c * 16, r);
+      for (int c = 0; c < OC / 16; ++c) {
+        uint32_t ro[16];
+        tmem_ld16(tO + lane_bits + half * OC + c * 16, ro);
         tmem_ld_wait();
 #pragma unroll
         for (int i = 0; i < 16; i += 2)
-          *reinterpret_cast<float2*>(dst + c * 16 + i) = make_float2(__uint_as_float(r[i]), __uint_as_float(r[i + 1]));
+          *reinterpret_cast<float2*>(dst + half * OC + c * 16 + i) = make_float2(__uint_as_float(ro[i]), __uint_as_float(ro[i + 1]));
       }
-      *reinterpret_cast<float2*>(dst + 64) = make_float2(m_used, l);
+      if (half == 0) *reinterpret_cast<float2*>(dst + 64) = make_float2(m_used, l);
     } else {
       const float inv_l = 1.f / l;
-      if (q < p.Nq && p.lse) p.lse[((int64_t)b * p.H + h) * p.Nq + q] = (m_used + log2f(l)) * 0.6931471805599453f;
+      if (half == 0 && q < p.Nq && p.lse) p.lse[((int64_t)b * p.H + h) * p.Nq + q] = (m_used + log2f(l)) * 0.6931471805599453f;
 #pragma unroll 1
-      for (int c = 0; c < 2; ++c) {
-        uint32_t r[32];
-        tmem_ld32(tO + lane_bits + c * 32, r);
+      for (int c = 0; c < OC / 32; ++c) {
+        uint32_t ro[32];
+        tmem_ld32(tO + lane_bits + half * OC + c * 32, ro);
         tmem_ld_wait();
         if (q < p.Nq) {
-          bf16* orow = p.O + ((int64_t)b * p.Nq + q) * p.ldo + h * 64 + c * 32;
+          bf16* orow = p.O + ((int64_t)b * p.Nq + q) * p.ldo + h * 64 + half * OC + c * 32;
 #pragma unroll
           for (int g = 0; g < 4; ++g) {
             uint4 u;
-            u.x = pack_bf16x2(__uint_as_float(r[g * 8 + 0]) * inv_l, __uint_as_float(r[g * 8 + 1]) * inv_l);
-            u.y = pack_bf16x2(__uint_as_float(r[g * 8 + 2]) * inv_l, __uint_as_float(r[g * 8 + 3]) * inv_l);
-            u.z = pack_bf16x2(__uint_as_float(r[g * 8 + 4]) * inv_l, __uint_as_float(r[g * 8 + 5]) * inv_l);
-            u.w = pack_bf16x2(__uint_as_float(r[g * 8 + 6]) * inv_l, __uint_as_float(r[g * 8 + 7]) * inv_l);
+            u.x = pack_bf16x2(__uint_as_float(ro[g * 8 + 0]) * inv_l, __uint_as_float(ro[g * 8 + 1]) * inv_l);
+            u.y = pack_bf16x2(__uint_as_float(ro[g * 8 + 2]) * inv_l, __uint_as_float(ro[g * 8 + 3]) * inv_l);
+            u.z = pack_bf16x2(__uint_as_float(ro[g * 8 + 4]) * inv_l, __uint_as_float(ro[g * 8 + 5]) * inv_l);
+            u.w = pack_bf16x2(__uint_as_float(ro[g * 8 + 6]) * inv_l, __uint_as_float(ro[g * 8 + 7]) * inv_l);
             *reinterpret_cast<uint4*>(orow + g * 8) = u;
           }
         }
@@ -871,12 +864,12 @@ extern "C" int b200_fa_fwd_ws(const void* q, int64_t ldq, const void* k, int64_t
   static bool attr_set = false;
   if (!attr_set) {
     if (cudaFuncSetAttribute(fa_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_FWD_SMEM) != cudaSuccess ||
-        cudaFuncSetAttribute(fa_fwd_db_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FA2_SMEM) != cudaSuccess ||
-        cudaFuncSetAttribute(fa_fwd_db_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FA2_SMEM) != cudaSuccess)
+        cudaFuncSetAttribute(fa_fwd_db_kernel<false, FA2_TPR>, cudaFuncAttributeMaxDynamicSharedMemorySize, FA2_SMEM) != cudaSuccess ||
+        cudaFuncSetAttribute(fa_fwd_db_kernel<true, FA2_TPR>, cudaFuncAttributeMaxDynamicSharedMemorySize, FA2_SMEM) != cudaSuccess)
       return launch_status("fa_fwd: cudaFuncSetAttribute");
     cudaFuncSetAttribute(fa_fwd_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    cudaFuncSetAttribute(fa_fwd_db_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    cudaFuncSetAttribute(fa_fwd_db_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(fa_fwd_db_kernel<false, FA2_TPR>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(fa_fwd_db_kernel<true, FA2_TPR>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     attr_set = true;
   }
   dim3 grid((Nq + 127) / 128, H, B);
@@ -896,9 +889,9 @@ extern "C" int b200_fa_fwd_ws(const void* q, int64_t ldq, const void* k, int64_t
     const int n_split = items - p.n_whole;
     const unsigned ctas = (unsigned)(p.n_whole + n_split * p.parts);
     if (key_bias != nullptr || Nk % FA_BN != 0)
-      fa_fwd_db_kernel<true><<<ctas, FA2_THREADS, FA2_SMEM, (cudaStream_t)stream>>>(tmQ, tmK, tmV, p);
+      fa_fwd_db_kernel<true, FA2_TPR><<<ctas, 64 + 128 * FA2_TPR, FA2_SMEM, (cudaStream_t)stream>>>(tmQ, tmK, tmV, p);
     else
-      fa_fwd_db_kernel<false><<<ctas, FA2_THREADS, FA2_SMEM, (cudaStream_t)stream>>>(tmQ, tmK, tmV, p);
+      fa_fwd_db_kernel<false, FA2_TPR><<<ctas, 64 + 128 * FA2_TPR, FA2_SMEM, (cudaStream_t)stream>>>(tmQ, tmK, tmV, p);
     if (n_split > 0)
       fa_fwd_merge_kernel<<<(n_split * 128 * 32 + 255) / 256, 256, 0, (cudaStream_t)stream>>>(p, n_split);
   } else
