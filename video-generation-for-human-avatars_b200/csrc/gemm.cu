@@ -612,6 +612,16 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 }
 
 static int g_num_sms = 0;
+// kernel-experiment switches, read once (not per launch)
+static bool env_flag_no_pair() {
+  static const bool v = getenv("B200_GEMM_NO_PAIR") != nullptr;
+  return v;
+}
+static bool env_flag_no_streamk() {
+  static const bool v = getenv("B200_GEMM_NO_STREAMK") != nullptr;
+  return v;
+}
+
 static int num_sms() {
   if (!g_num_sms) {
     int dev = 0;
@@ -719,7 +729,7 @@ static int gemm_impl(const void* A, int64_t lda, int a_kmajor_rows_are_k, const 
 
   // CTA pairs (256 x 256 tiles, cta_group::2) for the large GEMMs: a third less operand traffic per FLOP
   const bool pair = bn == 256 && M >= 512 && split_k <= 1 && (gg.groups <= 1 || M % 256 == 0) &&
-                    !getenv("B200_GEMM_NO_PAIR");
+                    !env_flag_no_pair();
   GemmParams p;
   p.M = M; p.N = N;
   p.m_tiles = pair ? (M + 255) / 256 : (M + 127) / 128;
@@ -807,7 +817,7 @@ static int gemm_impl(const void* A, int64_t lda, int a_kmajor_rows_are_k, const 
   p.sk_tiles = 0;
   p.sk_ws = nullptr;
   p.sk_flags = nullptr;
-  if (workspace && p.tma_store && p.splits == 1 && p.groups == 1 && !getenv("B200_GEMM_NO_STREAMK")) {
+  if (workspace && p.tma_store && p.splits == 1 && p.groups == 1 && !env_flag_no_streamk()) {
     const int P = pair ? num_sms() / 2 : num_sms();
     const int T = p.m_tiles * p.n_tiles;
     const int R = T % P;
