@@ -16,6 +16,7 @@ and the AdamW update of the 27.3 M trainable parameters.  Prints ONE JSON line (
                  on a bounded sample (BASELINE config 1: 256 latent tokens)
 """
 import argparse
+import gc
 import json
 import os
 import subprocess
@@ -302,7 +303,8 @@ def run_b200(args):
     named = [(n, p) for n, p in model.named_parameters() if p.requires_grad]
     bucketer = GradBucketer(named) if world > 1 else None
     from b200_ltx import optim
-    opt = optim.FusedAdamW([p for _, p in named], lr=1e-4)   # training.py:271 defaults, one launch per step
+    # training.py:271 defaults, one launch per step; --shard-optimizer: moments kept by one rank per tensor (ZeRO-1)
+    opt = optim.FusedAdamW([p for _, p in named], lr=1e-4, shard=args.shard_optimizer and world > 1)
     sched, patch = api.RectifiedFlowScheduler(), api.SymmetricPatchifier(1)
 
     class Cfg:
@@ -470,7 +472,10 @@ def run_b200(args):
                            "valid_caption_tokens": VALID_CTX, "lora_rank": LORA_RANK if args.train_mode == "lora_audio" else 0,
                            "layers": cfg["num_layers"],
                            "optimizer": f"AdamW (b200 single-launch kernel) on {sum(p.numel() for _, p in named) / 1e6:.1f}M trainable "
-                                        "params, inside the timed step", "train_mode": args.train_mode,
+                                        "params, inside the timed step"
+                                        + (f"; moments sharded over {world} ranks ({opt.state_bytes() / 2**20:.0f} MiB on rank 0), "
+                                           "updated tensors broadcast from their owner" if args.shard_optimizer and world > 1 else ""),
+                           "train_mode": args.train_mode,
                            "parallelism": f"sp{world} ({args.sp_mode} attn1)" if seq_parallel else f"dp{world}",
                            "launch": dp_launch,
                            "l2": "not flushed: every step streams 3.85 GB of weights plus >10 GB of activations, far larger than the 126 MB L2"},
@@ -538,6 +543,10 @@ def run_b200(args):
         extras["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
     emit(extras)
     if world > 1:
+        # a live CUDA graph that holds captured NCCL kernels keeps its communicator busy: ncclCommDestroy would wait on it
+        graphed = None  # noqa: F841
+        gc.collect()
+        torch.cuda.synchronize()
         dist.destroy_process_group()
 
 
@@ -626,6 +635,8 @@ def main():
     ap.add_argument("--dp-mode", default="one_graph", choices=["one_graph", "two_graphs"],
                     help="N > 1: capture the bucket all-reduces inside the step graph (overlapped with the backward), or "
                          "two graphs around an eager all-reduce")
+    ap.add_argument("--shard-optimizer", action="store_true",
+                    help="N > 1: each rank keeps the AdamW moments of 1/N of the tensors and broadcasts its updates")
     ap.add_argument("--no-extras", action="store_true",
                     help="skip the extra records (N = 1: GPU library baseline; N > 1: cfg3 and long-clip sub-records)")
     ap.add_argument("--extras-timeout", type=float, default=240.0)

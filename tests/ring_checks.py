@@ -76,8 +76,11 @@ def _spawned(rank, world, port):
     try:
         run(rank, world)
         run(rank, world, verbose=False, mode="gather")
-    finally:
-        dist.destroy_process_group()
+    except BaseException:
+        import traceback
+        traceback.print_exc()
+        os._exit(1)     # the peer may be parked in a collective: do not wait for it in destroy_process_group
+    dist.destroy_process_group()
 
 
 if __name__ == "__main__":

@@ -140,3 +140,18 @@ def test_gradient_accumulation_and_set_to_none_world2():
     out = mgr.dict()
     mp.spawn(_accum_worker, args=(2, _free_port(), out), nprocs=2, join=True)
     assert len(out) == 2 and all(v < 1e-6 for v in out.values()), dict(out)
+
+
+def test_optimizer_state_partition_is_balanced_and_deterministic():
+    from b200_ltx.optim import partition_by_size
+    # train_mode="full" of LTXV-2B: per block 8 attention matrices [2048, 2048] + small vectors, plus a few large ones
+    sizes = []
+    for _ in range(28):
+        sizes += [2048 * 2048] * 8 + [2048] * 10 + [6 * 2048]
+    sizes += [4096 * 2048, 2048 * 2048, 2048 * 6 * 2048, 128 * 2048, 2 * 2048]
+    for world in (2, 4, 8):
+        owner = partition_by_size(sizes, world)
+        assert owner == partition_by_size(sizes, world)
+        load = [sum(s for s, o in zip(sizes, owner) if o == r) for r in range(world)]
+        assert max(load) - min(load) <= max(sizes)            # within one largest tensor of each other
+        assert max(load) <= 1.05 * sum(sizes) / world

@@ -61,19 +61,24 @@ class DeviceFeeder:
     device-resident tensors of `dtype`, `depth` batches ahead of the consumer.
 
     Per batch: host cast -> pinned staging buffer -> `copy_(non_blocking=True)` on a private copy stream into device
-    buffer `i % depth` -> event.  `__next__` makes the current stream wait on that event (no host sync).  A device
-    buffer is reused only after the consumer's stream has been told about it (`record_stream`), so a step that is
-    still reading batch i never sees batch i + depth land underneath it.  On a CPU device it degrades to a cast."""
+    buffer `i % (depth + 1)` -> event.  `__next__` makes the current stream wait on that event (no host sync).  There
+    is one buffer more than the look-ahead: the batch just handed out keeps its buffer while `depth` later ones are in
+    flight, and that buffer is refilled only behind the event the consumer records with `batch["_release"]()` after the
+    step that read it (a consumer that never releases costs a stream synchronize per batch instead of a race).  On a CPU
+    device it degrades to a cast."""
 
     def __init__(self, batches: Iterable[dict], device, dtype=torch.bfloat16, depth: int = 2):
         self.src, self.device, self.dtype, self.depth = iter(batches), torch.device(device), dtype, max(1, depth)
         self.cuda = self.device.type == "cuda"
         self.copy_stream = torch.cuda.Stream(device=self.device) if self.cuda else None
         self.queue: List[tuple] = []
-        self.slots: List[Optional[Dict[str, torch.Tensor]]] = [None] * self.depth
-        self.pinned: List[Optional[Dict[str, torch.Tensor]]] = [None] * self.depth
-        self.done: List[Optional[torch.cuda.Event]] = [None] * self.depth   # compute finished reading slot i
-        self.copied: List[Optional[torch.cuda.Event]] = [None] * self.depth  # the H2D copies out of pinned slot i finished
+        self.n_slots = self.depth + 1
+        self.slots: List[Optional[Dict[str, torch.Tensor]]] = [None] * self.n_slots
+        self.pinned: List[Optional[Dict[str, torch.Tensor]]] = [None] * self.n_slots
+        self.done: List[Optional[torch.cuda.Event]] = [None] * self.n_slots   # compute finished reading slot i
+        self.released: List[bool] = [True] * self.n_slots                      # ... and said so (`_release`)
+        self.users: List[Optional[torch.cuda.Stream]] = [None] * self.n_slots
+        self.copied: List[Optional[torch.cuda.Event]] = [None] * self.n_slots  # the H2D copies out of pinned slot i finished
         self.n = 0
         for _ in range(self.depth):
             self._stage()
@@ -91,7 +96,7 @@ class DeviceFeeder:
             batch = next(self.src)
         except StopIteration:
             return
-        slot = self.n % self.depth
+        slot = self.n % self.n_slots
         self.n += 1
         if not self.cuda:
             self.queue.append(({k: batch[k].to(self.dtype) for k in KEYS}, None, batch.get("stem"), slot))
@@ -100,6 +105,9 @@ class DeviceFeeder:
         dev = self._buffers(self.slots, slot, batch, False)
         if self.copied[slot] is not None:
             self.copied[slot].synchronize()   # the pinned slot is about to be overwritten by the host: its DMA must be done
+        if not self.released[slot] and self.users[slot] is not None:
+            self.users[slot].synchronize()                        # handed out and never released: wait for its reader
+            self.released[slot] = True
         with torch.cuda.stream(self.copy_stream):
             if self.done[slot] is not None:
                 self.copy_stream.wait_event(self.done[slot])      # the step that used this slot has finished with it
@@ -122,10 +130,14 @@ class DeviceFeeder:
             cur = torch.cuda.current_stream(self.device)
             cur.wait_event(ready)
             ev = torch.cuda.Event()
-            self.done[slot] = ev
+            self.done[slot], self.released[slot], self.users[slot] = ev, False, cur
+
+            def release(ev=ev, cur=cur, slot=slot):                    # call after the step that consumed the batch
+                ev.record(cur)
+                self.released[slot] = True
             out = dict(dev)
             out["stem"] = stem
-            out["_release"] = lambda ev=ev, cur=cur: ev.record(cur)   # call after the step that consumed the batch
+            out["_release"] = release
         else:
             out = dict(dev)
             out["stem"] = stem

@@ -6,7 +6,15 @@ parameter's dtype, `state_dict()` keys `step / exp_avg / exp_avg_sq` per paramet
 walks the 116 tensors in ~8 multi-tensor launches (0.34 ms per step in the profile); here a device table of
 (param, grad, exp_avg, exp_avg_sq) entries drives a single launch of `b200_adamw_step`.  The step counter and the
 hyper-parameters are device tensors, so `step()` can be captured in a CUDA graph (train.GraphedTrainStep); after
-changing `param_groups[i]["lr"]` (an LR schedule) under graph replay call `sync_hyperparameters()`."""
+changing `param_groups[i]["lr"]` (an LR schedule) under graph replay call `sync_hyperparameters()`.
+
+Optimizer-state sharding for data-parallel runs (the reference's configs/ds_config_zero2.json:7-15 asks DeepSpeed for it;
+`train_mode="full"` has 983 M trainable parameters = 7.9 GB of fp32 moments per replica): `FusedAdamW(params, ...,
+shard_group=group)` deals the parameter tensors out to the ranks of `group` (largest first, onto the least loaded rank),
+keeps `exp_avg` / `exp_avg_sq` only for the tensors a rank owns, updates those with the one launch, and broadcasts every
+updated tensor from its owner (one NCCL broadcast per tensor: launch cost only matters eagerly -- under
+train.GraphedTrainStep they are captured with the step).  Gradients are expected to be already averaged over the group
+(dp.GradBucketer): every rank then applies the identical update a replicated optimizer would."""
 import struct
 from typing import List
 
@@ -17,12 +25,30 @@ from . import ops
 
 
 class FusedAdamW(torch.optim.Optimizer):
-    def __init__(self, params, lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8, weight_decay: float = 1e-2):
+    def __init__(self, params, lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8, weight_decay: float = 1e-2,
+                 shard_group=None, shard: bool = False):
         if lr < 0 or eps < 0 or weight_decay < 0 or not (0 <= betas[0] < 1) or not (0 <= betas[1] < 1):
             raise ValueError("FusedAdamW: invalid hyper-parameter")
         super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay))
         self._plans = {}      # group index -> launch plan
         self._keepalive: List[torch.Tensor] = []  # pinned tables a captured graph re-reads on replay
+        # optimizer-state sharding (ZeRO-1): parameter -> owning rank of `shard_group`
+        self._shard_group, self._owner, self._rank, self._world = None, {}, 0, 1
+        if (shard or shard_group is not None) and torch.distributed.is_initialized():
+            world = torch.distributed.get_world_size(shard_group)
+            if world > 1:
+                self._shard_group, self._world = shard_group, world
+                self._rank = torch.distributed.get_rank(shard_group)
+                all_params = [p for g in self.param_groups for p in g["params"]]
+                self._owner = {id(p): r for p, r in zip(all_params, partition_by_size([p.numel() for p in all_params], world))}
+
+    def owned(self, p) -> bool:
+        return self._world == 1 or self._owner[id(p)] == self._rank
+
+    def state_bytes(self) -> int:
+        """Bytes of exp_avg + exp_avg_sq held by THIS rank."""
+        return sum(st[k].numel() * st[k].element_size() for st in self.state.values() for k in ("exp_avg", "exp_avg_sq")
+                   if k in st)
 
     # ---- state ----
     def _group_state(self, gi: int, group):
@@ -113,7 +139,7 @@ class FusedAdamW(torch.optim.Optimizer):
                 continue
             entries = []
             for p in group["params"]:
-                if p.grad is None:
+                if p.grad is None or not self.owned(p):
                     continue
                 if p.dtype not in (torch.float32, torch.bfloat16) or p.grad.dtype != p.dtype:
                     raise _lib.B200Error("FusedAdamW: fp32 or bf16 parameters with gradients of the same dtype")
@@ -145,4 +171,33 @@ class FusedAdamW(torch.optim.Optimizer):
             ops._call("adamw", 28.0 * n, "byte", _lib.load().b200_adamw_step, plan["table"].data_ptr(),
                       plan["block_map"].data_ptr(), plan["n_blocks"], plan["step"].data_ptr(), plan["hyper"].data_ptr(),
                       plan["done"].data_ptr(), ops._s())
+        if self._world > 1:
+            # every tensor travels from the rank that updated it (same order on every rank)
+            dist = torch.distributed
+            todo = []
+            for group in self.param_groups:
+                for p in group["params"]:
+                    if p.grad is None:
+                        continue
+                    src = self._owner[id(p)]
+                    if self._shard_group is not None:
+                        src = dist.get_global_rank(self._shard_group, src)
+                    todo.append((p.data, src))
+            if todo:
+                # one NCCL group call for all of them (ncclGroupStart/End): a single launch instead of one per tensor
+                with dist._coalescing_manager(group=self._shard_group, device=todo[0][0].device, async_ops=False):
+                    for t, src in todo:
+                        dist.broadcast(t, src, group=self._shard_group)
         return loss
+
+
+def partition_by_size(sizes, world: int):
+    """Owner rank per tensor: largest tensors first, each onto the currently least loaded rank (deterministic, identical
+    on every rank).  Returns a list aligned with `sizes`."""
+    load = [0] * world
+    owner = [0] * len(sizes)
+    for i in sorted(range(len(sizes)), key=lambda k: (-sizes[k], k)):
+        r = min(range(world), key=lambda k: (load[k], k))
+        owner[i] = r
+        load[r] += sizes[i]
+    return owner
