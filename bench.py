@@ -594,7 +594,7 @@ def long_clip_sub_record(args, world, rank, dev, model, opt, bucketer, sched, pa
         loss_sp = step(resident, t=t.clone(), noise=noise, update=False).float()   # mean over this rank's shard
         dist.all_reduce(loss_sp)
         loss_sp /= world
-        use_graph = args.sp_mode == "gather" and not args.no_graph
+        use_graph = args.sp_mode != "ring" and not args.no_graph
         if use_graph:
             g = train.GraphedTrainStep(model, opt, sched, patch, Cfg, prompt, mask, resident, bucketer=bucketer,
                                        device=dev, dp_mode=args.dp_mode)
@@ -627,8 +627,10 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--train-mode", default="lora_audio", choices=["lora_audio", "full"],
                     help="training.py:42-91; 'full' (0.95 B trainable parameters) is not the headline workload")
-    ap.add_argument("--sp-mode", default="gather", choices=["ring", "gather"],
-                    help="cfg5 under torchrun: K/V ring hops, or one all-gather + single attention launch per layer")
+    ap.add_argument("--sp-mode", default="auto", choices=["auto", "ring", "gather", "heads"],
+                    help="cfg5 under torchrun: K/V ring hops, one all-gather + single attention launch per layer, or the "
+                         "tokens<->heads all-to-all (every rank attends all tokens for 32/N heads).  auto = what measured "
+                         "fastest: gather on 2 GPUs (137 vs 146 ms), heads on 4 and more (48 vs 58 ms on 8)")
     ap.add_argument("--no-side-stream", action="store_true",
                     help="captured step: keep the LoRA weight-gradient GEMMs on the main stream (A/B switch)")
     ap.add_argument("--no-graph", action="store_true", help="launch the step kernel by kernel instead of replaying a CUDA graph")
@@ -643,6 +645,8 @@ def main():
     ap.add_argument("--profile-steps", type=int, default=0,
                     help="ncu helper: run this many eager steps after 2 warm-up steps and exit (no JSON line)")
     args = ap.parse_args()
+    if args.sp_mode == "auto":
+        args.sp_mode = "heads" if int(os.environ.get("WORLD_SIZE", "1")) >= 4 else "gather"
     if args.impl == "reference":
         run_reference(args)
     elif args.workload == "cfg4":

@@ -76,6 +76,7 @@ def _spawned(rank, world, port):
     try:
         run(rank, world)
         run(rank, world, verbose=False, mode="gather")
+        run(rank, world, verbose=False, mode="heads")
     except BaseException:
         import traceback
         traceback.print_exc()
@@ -86,7 +87,7 @@ def _spawned(rank, world, port):
 if __name__ == "__main__":
     r, w = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     dist.init_process_group("nccl", device_id=torch.device("cuda", int(os.environ.get("LOCAL_RANK", r))))
-    for m in ("ring", "gather"):
+    for m in ("ring", "gather", "heads"):
         run(int(os.environ.get("LOCAL_RANK", r)), w, mode=m)
     dist.destroy_process_group()
     if r == 0:

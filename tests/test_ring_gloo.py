@@ -61,11 +61,11 @@ class TorchLocalAttention:
         return back(dk), back(dv)
 
 
-def _worker(rank, world, port, out):
+def _worker(rank, world, port, out, mode="ring"):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     from b200_ltx import ring
-    B, H, n = 2, 3, 10
+    B, H, n = 2, (2 * world if mode == "heads" else 3), 10
     D, N = H * 64, n * world
     g = torch.Generator().manual_seed(7)
     q, k, v, do = (torch.randn(B, N, D, generator=g) for _ in range(4))
@@ -73,7 +73,8 @@ def _worker(rank, world, port, out):
     def shard(t):
         return t[:, rank * n:(rank + 1) * n].reshape(B * n, D).clone()
     ql, kl, vl = (shard(t).requires_grad_(True) for t in (q, k, v))
-    o = ring.ring_attention(ql, kl, vl, None, B, H, n, 0.125, TorchLocalAttention())
+    attend = ring.heads_attention if mode == "heads" else ring.ring_attention
+    o = attend(ql, kl, vl, None, B, H, n, 0.125, TorchLocalAttention())
     o.backward(shard(do))
     # un-sharded reference
     qf, kf, vf = (t.clone().requires_grad_(True) for t in (q, k, v))
@@ -93,4 +94,14 @@ def test_ring_attention_matches_unsharded(world):
     mgr = mp.Manager()
     out = mgr.dict()
     mp.spawn(_worker, args=(world, _free_port(), out), nprocs=world, join=True)
+    assert len(out) == world and all(v < 2e-5 for v in out.values()), dict(out)
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_head_exchange_attention_matches_unsharded(world):
+    """mode="heads": tokens -> heads all-to-all, un-sharded attention over H/P heads, heads -> tokens all-to-all (batch 2:
+    the exchange also has to keep the batch-major token order)."""
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_worker, args=(world, _free_port(), out, "heads"), nprocs=world, join=True)
     assert len(out) == world and all(v < 2e-5 for v in out.values()), dict(out)

@@ -13,6 +13,23 @@ flush = torch.empty(256 << 20, device=dev, dtype=torch.uint8)
 
 
 def timeit(fn, n=8):
+    if os.environ.get("B200_ATTN_GRAPH"):      # small shapes: GPU-only time from a replayed graph of 6 launches
+        for _ in range(2):
+            fn()
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            for _ in range(6):
+                fn()
+        g.replay()
+        ts = []
+        for _ in range(5):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); g.replay(); e1.record(); torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1) / 6)
+        ts.sort()
+        return ts[len(ts) // 2]
     for _ in range(2):
         fn()
     ts = []
@@ -25,8 +42,16 @@ def timeit(fn, n=8):
     return ts[len(ts) // 2]
 
 
-for (name, B, Nq, Nk, bias) in [("attn1 cfg2", 1, 6144, 6144, False), ("attn1 cfg3", 4, 3328, 3328, False),
-                                ("attn1 cfg5", 1, 12672, 12672, False), ("attn2 cfg2 (15/256 keys)", 1, 6144, 256, True)]:
+CASES = [("attn1 cfg2", 1, 6144, 6144, False, 32), ("attn1 cfg3", 4, 3328, 3328, False, 32),
+         ("attn1 cfg5", 1, 12672, 12672, False, 32), ("attn2 cfg2 (15/256 keys)", 1, 6144, 256, True, 32),
+         # sequence-parallel shapes of cfg5: head exchange (all tokens, 32/P heads) and K/V gather (N/P queries, all keys)
+         ("attn1 cfg5 heads P=8", 1, 12672, 12672, False, 4), ("attn1 cfg5 heads P=4", 1, 12672, 12672, False, 8),
+         ("attn1 cfg5 gather P=8", 1, 1584, 12672, False, 32)]
+only = os.environ.get("B200_ATTN_CASES")
+for (name, B, Nq, Nk, bias, H) in CASES:
+    if only and not any(tok in name for tok in only.split(",")):
+        continue
+    D = H * 64
     g = torch.Generator(device="cpu").manual_seed(0)
     q = torch.randn(B * Nq, D, generator=g).to(dev, torch.bfloat16)
     k = torch.randn(B * Nk, D, generator=g).to(dev, torch.bfloat16)

@@ -2,10 +2,21 @@
 column is cuBLASLt (torch.matmul / F.linear, no epilogue work beyond the bias) on the same operands, same box."""
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import argparse
 import torch
 from b200_ltx import ops
 
-M, D, F = 6144, 2048, 8192
+ap = argparse.ArgumentParser()
+ap.add_argument("--m", type=int, default=6144, help="rows (tokens): 6144 = cfg2, 1584 = cfg5 on 8 sequence-parallel ranks")
+ap.add_argument("--bn", default="128,256", help="block_n values to time (0 = the library's own choice); 256 means CTA "
+                                                "pairs unless B200_GEMM_NO_PAIR=1")
+ap.add_argument("--no-lib", action="store_true")
+ap.add_argument("--graph", action="store_true", help="time 12 launches replayed from one CUDA graph instead of single "
+                                                     "eager launches (small shapes: an eager launch is host-bound)")
+args = ap.parse_args()
+M, D, F = args.m, 2048, 8192
+BNS = [int(v) for v in args.bn.split(",")]
+print(f"M = {M}, pair kernel {'off' if os.environ.get('B200_GEMM_NO_PAIR') == '1' else 'on'}", flush=True)
 dev = "cuda"
 def r(*s): return (torch.randn(*s, device=dev) * 0.05).bfloat16()
 x, xf = r(M, D), r(M, F)
@@ -37,18 +48,56 @@ cases = [
     ("dgrad N=2048 K=8192", lambda bn: ops.gemm(xf, W_fd, b_rows_are_k=True, block_n=bn), 2 * M * F * D),
 ]
 flush = torch.empty(256 << 20, device=dev, dtype=torch.uint8)
-for name, fn, flops in cases:
-    lf = lib_cases[name]
-    for _ in range(3): lf()
+
+
+def graph_time(fn, reps=12):
+    """GPU-only time per launch: `reps` launches captured in one CUDA graph and replayed (no host launch cost between
+    them -- what a captured train step sees; the activation operand stays in L2 as it does behind its producer)."""
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        for _ in range(2):
+            fn()
+    torch.cuda.current_stream().wait_stream(s)
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        for _ in range(reps):
+            fn()
+    g.replay()
     ts = []
-    for _ in range(10):
+    for _ in range(5):
         flush.zero_()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(); lf(); e1.record(); torch.cuda.synchronize()
-        ts.append(e0.elapsed_time(e1))
+        e0.record(); g.replay(); e1.record(); torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1) / reps)
     ts.sort()
-    print(f"{name:36s} cuBLASLt {ts[len(ts) // 2]*1e3:8.1f} us {flops / ts[len(ts) // 2] / 1e9:8.1f} TF/s (plain GEMM, no fused epilogue)", flush=True)
-    for bn in (128, 256):
+    return ts[len(ts) // 2]
+
+
+if args.graph:
+    for name, fn, flops in cases:
+        if not args.no_lib:
+            t = graph_time(lib_cases[name])
+            print(f"{name:36s} cuBLASLt {t*1e3:8.1f} us {flops / t / 1e9:8.1f} TF/s (graph-replayed, plain GEMM)", flush=True)
+        for bn in BNS:
+            t = graph_time(lambda: fn(bn))
+            print(f"{name:36s} bn={bn:3d} {t*1e3:8.1f} us {flops / t / 1e9:8.1f} TF/s (graph-replayed)", flush=True)
+    sys.exit(0)
+
+for name, fn, flops in cases:
+    lf = lib_cases[name]
+    if not args.no_lib:
+        for _ in range(3): lf()
+        ts = []
+        for _ in range(10):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); lf(); e1.record(); torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        ts.sort()
+        print(f"{name:36s} cuBLASLt {ts[len(ts) // 2]*1e3:8.1f} us {flops / ts[len(ts) // 2] / 1e9:8.1f} TF/s (plain GEMM, no fused epilogue)", flush=True)
+    for bn in BNS:
         for _ in range(3): fn(bn)
         ts = []
         for _ in range(10):

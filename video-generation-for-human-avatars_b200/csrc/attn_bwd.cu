@@ -604,9 +604,15 @@ static void fa_bwd_tail_plan(int items, int q_tiles, int* n_whole, int* parts) {
   if (off) return;
   const int r = items % slots;
   if (items < slots || r == 0 || r * 4 > slots * 3) return;
-  int pr = slots / r;
-  if (pr > 4) pr = 4;
-  if (pr > q_tiles / 8) pr = q_tiles / 8;   // at least 8 query tiles per part
+  // r items as r * pr CTAs of 1/pr of the walk each: rounds of `slots` CTAs, each round 1/pr of a full CTA lifetime,
+  // plus what a part costs (K / V load, fp32 partials and their reduction); un-split = 1.0
+  int max_pr = q_tiles / 8 < 4 ? q_tiles / 8 : 4;             // at least 8 query tiles per part
+  int pr = 1;
+  double best = 1.0;
+  for (int c = 2; c <= max_pr; ++c) {
+    const double cost = (double)((r * c + slots - 1) / slots) / c + 0.015 * c;
+    if (cost < best - 1e-9) { best = cost; pr = c; }
+  }
   if (pr < 2) return;
   *n_whole = items - r;
   *parts = pr;

@@ -781,9 +781,15 @@ static void fa_fwd_plan(int items, int kv_tiles, int* n_whole, int* parts) {
   *parts = 1;
   const int r = items % slots;
   if (items < slots || r == 0 || r * 4 > slots * 3) return;   // a single wave, or a well-filled last wave
-  int pr = slots / r;
-  if (pr > 8) pr = 8;
-  if (pr > kv_tiles / 8) pr = kv_tiles / 8;                   // at least 8 key steps per part
+  // r items as r * pr CTAs of 1/pr of the keys each: rounds of `slots` CTAs, each 1/pr of a full CTA lifetime, plus
+  // what a part costs (Q load, fp32 partial and the merge); un-split = 1.0
+  int max_pr = kv_tiles / 8 < 8 ? kv_tiles / 8 : 8;           // at least 8 key steps per part
+  int pr = 1;
+  double best = 1.0;
+  for (int c = 2; c <= max_pr; ++c) {
+    const double cost = (double)((r * c + slots - 1) / slots) / c + 0.015 * c;
+    if (cost < best - 1e-9) { best = cost; pr = c; }
+  }
   if (pr < 2) return;
   *n_whole = items - r;
   *parts = pr;

@@ -888,7 +888,7 @@ class SelfAttnFn(torch.autograd.Function):
         qkv = gemm(x, Wqkv, bias=bqkv)  # one [M,3D] GEMM against the [3D,D] weight concatenation
         qk = torch.empty((M, 2 * D), device=x.device, dtype=BF16)
         qknorm_rope_fwd(qkv[:, :D], qkv[:, D:2 * D], wqn, wkn, cos, sin, qk[:, :D], qk[:, D:])
-        kv = None
+        kv = o_h = None
         if sp is None:
             # batch_keep (inference only): STG skip of some batch entries inside the attention launch -- their output is
             # the value rows ("attention values") or the attention input x ("attention skip"), attention.py:1071-1086
@@ -901,6 +901,8 @@ class SelfAttnFn(torch.autograd.Function):
             if sp.mode == "gather":
                 o, lse, k_all, v_all = ring.gather_fwd(qk[:, :D], qk[:, D:], qkv[:, 2 * D:], sp.group, B, H, N, scale)
                 kv = torch.stack([k_all, v_all])  # [2, P*n, D] kept for the backward
+            elif sp.mode == "heads":
+                o, lse, kv, o_h = ring.heads_fwd(qk[:, :D], qk[:, D:], qkv[:, 2 * D:], sp.group, B, H, N, scale, sp.impl)
             else:
                 o, lse, kv = ring.ring_fwd(qk[:, :D], qk[:, D:], qkv[:, 2 * D:], sp.group, B, H, N, scale, sp.impl)
         u = None
@@ -909,13 +911,15 @@ class SelfAttnFn(torch.autograd.Function):
         y = gemm(o, Wo, bias=bo, gate=gate, rows_per_gate=rows_per_gate, res=res, aux=u,
                  epilogue=EPI_STASH if u is not None else EPI_NONE)
         train_w = ctx.needs_input_grad[1] or ctx.needs_input_grad[2]
-        ctx.save_for_backward(qkv, qk, o, lse, Wqkv, wqn, wkn, cos, sin, Wo, gate, key_bias, kv, u, x if train_w else None)
+        heads = o_h is not None   # head-exchange mode: the backward reads q / k / v / o in the head-sharded layout
+        ctx.save_for_backward(qkv, None if heads else qk, o if (not heads or ctx.needs_input_grad[7]) else None, lse, Wqkv,
+                              wqn, wkn, cos, sin, Wo, gate, key_bias, kv, u, x if train_w else None, o_h)
         ctx.meta = (B, H, N, scale, rows_per_gate, res is not None, sp)
         return y
 
     @staticmethod
     def backward(ctx, dy):
-        qkv, qk, o, lse, Wqkv, wqn, wkn, cos, sin, Wo, gate, key_bias, kv, u, x = ctx.saved_tensors
+        qkv, qk, o, lse, Wqkv, wqn, wkn, cos, sin, Wo, gate, key_bias, kv, u, x, o_h = ctx.saved_tensors
         B, H, N, scale, rpg, has_res, sp = ctx.meta
         need = ctx.needs_input_grad
         D = H * 64
@@ -935,6 +939,9 @@ class SelfAttnFn(torch.autograd.Function):
             from . import ring
             if sp.mode == "gather":
                 dq32, dk_post, dv_loc = ring.gather_bwd(qk[:, :D], kv[0], kv[1], o, do, lse, sp.group, B, H, N, scale)
+                dqkv[:, 2 * D:].copy_(dv_loc)
+            elif sp.mode == "heads":
+                dq32, dk_post, dv_loc = ring.heads_bwd(kv, o_h, do, lse, sp.group, B, H, N, scale, sp.impl)
                 dqkv[:, 2 * D:].copy_(dv_loc)
             else:
                 dq32, dkv = ring.ring_bwd(qk[:, :D], kv, o, do, lse, sp.group, B, H, N, scale, sp.impl)

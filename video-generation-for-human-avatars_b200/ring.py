@@ -180,13 +180,115 @@ def gather_bwd(q, k_all, v_all, out, do, lse, group, B, H, n_local, scale):
     return dq, dk, dv
 
 
+# ---- head exchange: tokens <-> heads with one all-to-all each way ------------------------------------------------------
+# A rank hands every peer the slice of ITS tokens that belongs to the PEER's H/P heads and receives all N tokens of its
+# own heads: attention then runs un-sharded over N x N for H/P heads -- no partial softmax, no partial dK/dV, exactly the
+# arithmetic of the single-GPU kernel -- and a second all-to-all brings the output rows home.  Per layer and rank the
+# forward moves 4 (q, k, v, o) x (P-1)/P x n_local x D bf16 (23 MB at cfg5 / P = 8, against 91 MB of gathered K/V) and the
+# backward the same plus fp32 dQ; nothing is reduced across ranks.  Needs H % P == 0 (32 heads: P in 2, 4, 8, 16, 32).
+
+def _all_to_all(x: torch.Tensor, group) -> torch.Tensor:
+    """x [P, ...] contiguous: slice r goes to rank r; returns [P, ...] with slice r = what rank r sent here."""
+    out = torch.empty_like(x)
+    dist.all_to_all_single(out, x, group=group)
+    return out
+
+
+def tokens_to_heads(parts, group, B, n_local):
+    """parts: k tensors [B*n_local, D] of one dtype (row-strided views allowed), this rank's tokens x all heads.
+    Returns [k, B*P*n_local, D/P]: all tokens (batch-major, sequence order) x this rank's heads."""
+    P = dist.get_world_size(group)
+    k, D = len(parts), parts[0].shape[1]
+    cp = D // P
+    send = torch.empty((P, k, B * n_local, cp), device=parts[0].device, dtype=parts[0].dtype)
+    for i, t in enumerate(parts):
+        send[:, i].copy_(t.unflatten(1, (P, cp)).transpose(0, 1))
+    recv = _all_to_all(send, group)                     # [P = source rank = token chunk, k, B*n, cp]
+    return recv.view(P, k, B, n_local, cp).permute(1, 2, 0, 3, 4).reshape(k, B * P * n_local, cp)
+
+
+def heads_to_tokens(parts, group, B, n_local):
+    """Inverse of tokens_to_heads: k tensors [B*P*n_local, D/P] -> [k, B*n_local, D]."""
+    P = dist.get_world_size(group)
+    k, cp = len(parts), parts[0].shape[1]
+    send = torch.empty((P, k, B, n_local, cp), device=parts[0].device, dtype=parts[0].dtype)
+    for i, t in enumerate(parts):
+        send[:, i].copy_(t.view(B, P, n_local, cp).transpose(0, 1))
+    recv = _all_to_all(send, group)                     # [P = source rank = head chunk, k, B, n, cp]
+    return recv.view(P, k, B * n_local, cp).permute(1, 2, 0, 3).reshape(k, B * n_local, P * cp)
+
+
+def heads_fwd(q, k, v, group, B, H, n_local, scale, impl: Optional[LocalAttention] = None):
+    """Returns (out [B*n_local, H*64] for the local tokens, lse [B, H/P, N], qkv_h [3, B*N, D/P], o_h [B*N, D/P]): the
+    last three are what the backward needs, in the head-sharded layout."""
+    impl = impl or LocalAttention()
+    P = dist.get_world_size(group)
+    if H % P:
+        raise ops._lib.B200Error(f"head-exchange sequence parallelism needs the head count ({H}) to divide by the group "
+                                 f"size ({P})")
+    N = P * n_local
+    qkv_h = tokens_to_heads([q, k, v], group, B, n_local)
+    o_h, lse = impl.fwd(qkv_h[0], qkv_h[1], qkv_h[2], B, H // P, N, N, scale)
+    out = heads_to_tokens([o_h], group, B, n_local)[0]
+    return out, lse, qkv_h, o_h
+
+
+def heads_bwd(qkv_h, o_h, do, lse, group, B, H, n_local, scale, impl: Optional[LocalAttention] = None):
+    """Returns (dq fp32, dk, dv) [B*n_local, H*64] for the local tokens; every one is a complete sum (the attention ran
+    over all tokens of its heads), so nothing is reduced."""
+    impl = impl or LocalAttention()
+    P = dist.get_world_size(group)
+    hp, N = H // P, P * n_local
+    do_h = tokens_to_heads([do], group, B, n_local)[0]
+    delta = impl.delta(o_h, do_h, B, hp, N)
+    dq_h = torch.zeros((B * N, hp * 64), device=do.device, dtype=torch.float32)
+    dk_h, dv_h = impl.bwd(qkv_h[0], qkv_h[1], qkv_h[2], o_h, do_h, lse, delta, dq_h, B, hp, N, N, scale)
+    # one message for the three gradients: per destination rank [dq fp32 | dk | dv] as raw bytes
+    cp = hp * 64
+    rows = B * n_local
+    seg = rows * cp                                                   # elements per destination and tensor
+    parts = (dq_h, dk_h, dv_h)
+    offs = [0]
+    for t in parts:
+        offs.append(offs[-1] + seg * t.element_size())
+    send = torch.empty((P, offs[-1]), device=do.device, dtype=torch.uint8)
+    for i, t in enumerate(parts):
+        send[:, offs[i]:offs[i + 1]].view(t.dtype).view(P, B, n_local, cp).copy_(
+            t.view(B, P, n_local, cp).transpose(0, 1))
+    recv = _all_to_all(send, group)                                    # [P = source rank = head chunk, bytes]
+    out = [recv[:, offs[i]:offs[i + 1]].view(t.dtype).view(P, rows, cp).transpose(0, 1).reshape(rows, P * cp)
+           for i, t in enumerate(parts)]
+    return out[0], out[1], out[2]
+
+
+class HeadsAttnFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, q, k, v, group, B, H, n_local, scale, impl):
+        out, lse, qkv_h, o_h = heads_fwd(q, k, v, group, B, H, n_local, scale, impl)
+        ctx.save_for_backward(qkv_h, o_h, lse)
+        ctx.meta = (group, B, H, n_local, scale, impl)
+        return out
+
+    @staticmethod
+    def backward(ctx, do):
+        qkv_h, o_h, lse = ctx.saved_tensors
+        group, B, H, n_local, scale, impl = ctx.meta
+        dq, dk, dv = heads_bwd(qkv_h, o_h, do.contiguous(), lse, group, B, H, n_local, scale, impl)
+        return dq.to(do.dtype), dk, dv, None, None, None, None, None, None
+
+
+def heads_attention(q, k, v, group, B, H, n_local, scale, impl: Optional[LocalAttention] = None):
+    return HeadsAttnFn.apply(q, k, v, group, B, H, n_local, scale, impl)
+
+
 class SequenceParallel:
     """Per-model sequence-sharding state (set by api.enable_sequence_parallel).  mode: "ring" (K/V hops overlapped
-    with the per-hop attention, online-softmax merge) or "gather" (all-gather K/V, one attention launch)."""
+    with the per-hop attention, online-softmax merge), "gather" (all-gather K/V, one attention launch) or "heads"
+    (all-to-all: every rank attends ALL tokens for H/P heads)."""
 
     def __init__(self, group=None, impl: Optional[LocalAttention] = None, mode: str = "ring"):
-        if mode not in ("ring", "gather"):
-            raise ValueError("sequence-parallel mode must be 'ring' or 'gather'")
+        if mode not in ("ring", "gather", "heads"):
+            raise ValueError("sequence-parallel mode must be 'ring', 'gather' or 'heads'")
         self.group = group
         self.rank = dist.get_rank(group)
         self.world = dist.get_world_size(group)
