@@ -509,6 +509,17 @@ def check_gemm_stream_k():
         (6000, 2048, 512, 0, False, "bias", 0),
         (6144, 8192, 512, 0, False, "gelu", 0),
         (4096, 2048, 512, 0, False, "bias res", 128),
+        # few-wave problems with ragged M (the shards of 8 / 4 sequence-parallel ranks at cfg5)
+        (1584, 2048, 2048, 0, False, "bias gate res", 0),
+        (1584, 2048, 2048, 64, False, "bias", 0),
+        (1584, 6144, 2048, 0, False, "bias", 0),
+        (1584, 8192, 2048, 0, False, "gelu", 0),
+        (1584, 2048, 8192, 0, True, "res", 0),
+        (1584, 2048, 2048, 0, True, "", 256),
+        (3168, 2048, 2048, 0, False, "bias gate res", 0),
+        (3168, 8192, 2048, 0, False, "gelu", 0),
+        (840, 2048, 2048, 0, False, "bias", 128),
+        (256, 2048, 2048, 0, False, "bias", 0),
     ]
     for (M, N, K, K2, b_k, epi, bn) in cases:
         a = _randn(M, K, seed=1, scale=0.5)

@@ -40,6 +40,8 @@ __global__ void __launch_bounds__(256) adamw_kernel(const AdamWEntry* __restrict
                                                     const int32_t* __restrict__ block_map,
                                                     float* __restrict__ step, const float* __restrict__ hp,
                                                     int32_t* __restrict__ done) {
+  pdl_launch();
+  pdl_wait();
   __shared__ AdamWCoef sc;
   if (threadIdx.x == 0) {
     const double t = (double)step[0] + 1.0;
@@ -131,7 +133,7 @@ extern "C" int b200_adamw_step(const void* table, const int32_t* block_map, int 
   if (n_blocks == 0) return 0;
   if (!(table && block_map && step && hyper && done_counter)) return arg_error("adamw_step: null pointer");
   if (reinterpret_cast<uintptr_t>(table) & 7) return arg_error("adamw_step: table must be 8-byte aligned");
-  adamw_kernel<<<n_blocks, 256, 0, (cudaStream_t)stream>>>((const AdamWEntry*)table, block_map, step, hyper,
+  B200_LAUNCH(adamw_kernel, n_blocks, 256, 0, (cudaStream_t)stream, (const AdamWEntry*)table, block_map, step, hyper,
                                                            done_counter);
   return launch_status("adamw_step");
 }

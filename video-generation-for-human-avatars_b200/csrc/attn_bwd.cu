@@ -155,7 +155,9 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
   // some other key of the batch entry is unmasked has P = 0 exactly (exp of < -900 underflows in fp32): dK = dV = 0
   // and no contribution to dQ.  Such CTAs write their zeros and leave before touching barriers or TMEM.  (With every
   // key masked the softmax is uniform, not zero: nothing is skipped then.)
+  pdl_launch();
   if (p.key_bias != nullptr && p.Nk <= FA_MASK_SCAN_MAX) {
+    pdl_wait();   // the mask scan reads (and a dead tile writes) global memory
     int live_tile = 0, live_batch = 0;   // block-wide votes: no shared memory to spare next to the dynamic 227 KB
     const float* kbp = p.key_bias + (int64_t)b * p.Nk;
     for (int key_t = threadIdx.x; key_t < p.Nk; key_t += FA_BWD_THREADS)
@@ -226,6 +228,7 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
   const uint32_t tSt = tmem_base, tdPt = tmem_base + 128, tdV = tmem_base + 256,
                  tdK = tmem_base + 320, tdQ = tmem_base + 384, tK = tmem_base + 448, tV = tmem_base + 480;
+  pdl_wait();   // barrier init / TMEM allocation above overlapped the previous kernel's tail
 
   if (warp == 0 && lane == 0) {
     mbar_expect_tx(kv_full, 32768);
@@ -546,6 +549,8 @@ __global__ void __launch_bounds__(256) fa_bwd_reduce_kernel(const float* __restr
                                                             const float* __restrict__ part_dv, bf16* dk,
                                                             int64_t lddk, bf16* dv, int64_t lddv, int splits,
                                                             int64_t rows, int D) {
+  pdl_launch();
+  pdl_wait();
   const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int per_row = D / 8;
   if (gid >= rows * per_row) return;
@@ -568,6 +573,8 @@ __global__ void __launch_bounds__(256) fa_bwd_reduce_kernel(const float* __restr
 
 // dk/dv (bf16) of the split items of the last wave = sum over their `tail_parts` fp32 partials; 8 columns per thread.
 __global__ void __launch_bounds__(256) fa_bwd_tail_reduce_kernel(const FaBwdParams p, int n_split) {
+  pdl_launch();
+  pdl_wait();
   const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;   // (split item, row, 16 groups of 8 columns)
   if (gid >= (int64_t)n_split * 128 * 16) return;
   const int c8 = (int)(gid & 15) * 8, row = (int)((gid >> 4) & 127), si = (int)(gid >> 11);
@@ -719,13 +726,13 @@ extern "C" int b200_fa_bwd(const void* q, int64_t ldq, const void* k, int64_t ld
     }
     grid = dim3((unsigned)(p.n_whole + n_split * p.tail_parts), 1, 1);
   }
-  fa_bwd_kernel<<<grid, FA_BWD_THREADS, FA_BWD_SMEM, (cudaStream_t)stream>>>(tmQ, tmK, tmV, tmdO, tmdQ, p);
+  B200_LAUNCH(fa_bwd_kernel, grid, FA_BWD_THREADS, FA_BWD_SMEM, stream, tmQ, tmK, tmV, tmdO, tmdQ, p);
   if (n_split > 0)
-    fa_bwd_tail_reduce_kernel<<<(unsigned)(((int64_t)n_split * 128 * 16 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(p, n_split);
+    B200_LAUNCH(fa_bwd_tail_reduce_kernel, (unsigned)(((int64_t)n_split * 128 * 16 + 255) / 256), 256, 0, stream, p, n_split);
   if (p.q_splits > 1) {
     const int64_t rows = (int64_t)B * Nk, threads = rows * (H * 64 / 8);
-    fa_bwd_reduce_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
-        p.part_dk, p.part_dv, (bf16*)dk, lddk, (bf16*)dv, lddv, p.q_splits, rows, H * 64);
+    B200_LAUNCH(fa_bwd_reduce_kernel, (unsigned)((threads + 255) / 256), 256, 0, stream, p.part_dk, p.part_dv, (bf16*)dk,
+                lddk, (bf16*)dv, lddv, p.q_splits, rows, H * 64);
   }
   return launch_status("fa_bwd");
 }

@@ -151,6 +151,8 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
   float* kb_stage = reinterpret_cast<float*>(smem_raw + (bar + 128 - sbase));  // [64] per-key term of the current step
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int qt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+  pdl_launch();
+  pdl_wait();   // this kernel reads global memory (key mask, batch_keep) from its first lines on
   if (p.batch_keep != nullptr && p.batch_keep[b] == 0.f) {
     fa_copy_values(p, qt, h, b, FA_FWD_THREADS);
     return;
@@ -454,9 +456,13 @@ fa_fwd_db_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     j_end = (int)((int64_t)(part + 1) * p.kv_tiles / p.parts);
   }
   const int qt = item % p.q_tiles, h = (item / p.q_tiles) % p.H, b = item / (p.q_tiles * p.H);
-  if (p.batch_keep != nullptr && p.batch_keep[b] == 0.f) {
-    if (part <= 0) fa_copy_values(p, qt, h, b, 64 + 128 * TPR);
-    return;
+  pdl_launch();
+  if (p.batch_keep != nullptr) {
+    pdl_wait();
+    if (p.batch_keep[b] == 0.f) {
+      if (part <= 0) fa_copy_values(p, qt, h, b, 64 + 128 * TPR);
+      return;
+    }
   }
 
   if (FA2_ROWSUM_MMA) {
@@ -500,6 +506,7 @@ fa_fwd_db_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
   const uint32_t tS = tmem_base, tO = tmem_base + 128, tQ = tmem_base + 128 + FA2_O_COLS;
   const int T = j_end - j_begin;   // key steps of this CTA; step j below is global step j_begin + j
+  pdl_wait();   // barrier init / TMEM allocation above overlapped the previous kernel's tail
 
   if (warp == 0 && lane == 0) {
     mbar_expect_tx(q_full, 16384);
@@ -741,6 +748,8 @@ fa_fwd_db_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
 
 // Fold the `parts` partial results of every split item: one warp per query row, two output columns per lane.
 __global__ void __launch_bounds__(256) fa_fwd_merge_kernel(const FaFwdParams p, int n_split) {
+  pdl_launch();
+  pdl_wait();
   const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (gw >= n_split * 128) return;
   const int si = gw >> 7, row = gw & 127;
@@ -895,12 +904,12 @@ extern "C" int b200_fa_fwd_ws(const void* q, int64_t ldq, const void* k, int64_t
     const int n_split = items - p.n_whole;
     const unsigned ctas = (unsigned)(p.n_whole + n_split * p.parts);
     if (key_bias != nullptr || Nk % FA_BN != 0)
-      fa_fwd_db_kernel<true, FA2_TPR><<<ctas, 64 + 128 * FA2_TPR, FA2_SMEM, (cudaStream_t)stream>>>(tmQ, tmK, tmV, p);
+      { auto kdb = fa_fwd_db_kernel<true, FA2_TPR>; B200_LAUNCH(kdb, ctas, 64 + 128 * FA2_TPR, FA2_SMEM, stream, tmQ, tmK, tmV, p); }
     else
-      fa_fwd_db_kernel<false, FA2_TPR><<<ctas, 64 + 128 * FA2_TPR, FA2_SMEM, (cudaStream_t)stream>>>(tmQ, tmK, tmV, p);
+      { auto kdb = fa_fwd_db_kernel<false, FA2_TPR>; B200_LAUNCH(kdb, ctas, 64 + 128 * FA2_TPR, FA2_SMEM, stream, tmQ, tmK, tmV, p); }
     if (n_split > 0)
-      fa_fwd_merge_kernel<<<(n_split * 128 * 32 + 255) / 256, 256, 0, (cudaStream_t)stream>>>(p, n_split);
+      B200_LAUNCH(fa_fwd_merge_kernel, (n_split * 128 * 32 + 255) / 256, 256, 0, stream, p, n_split);
   } else
-    fa_fwd_kernel<<<grid, FA_FWD_THREADS, FA_FWD_SMEM, (cudaStream_t)stream>>>(tmQ, tmK, tmV, p);
+    B200_LAUNCH(fa_fwd_kernel, grid, FA_FWD_THREADS, FA_FWD_SMEM, stream, tmQ, tmK, tmV, p);
   return launch_status("fa_fwd");
 }

@@ -377,6 +377,61 @@ __host__ __device__ __forceinline__ uint32_t make_idesc_bf16(int M, int N, int a
   return d;
 }
 
+// ---------------------------------------------------------------------------
+// Programmatic dependent launch: a kernel launched with launch_cfg_pdl() may be scheduled while its predecessor in
+// the stream is still draining; everything it does before pdl_wait() (barrier init, TMEM allocation, descriptor
+// prefetch, index arithmetic) overlaps the predecessor's tail.  pdl_wait() returns once the predecessor grid has
+// completed and its writes are visible -- NO global memory the predecessor may write (or still read, for outputs)
+// is touched before it.  pdl_launch() lets the successor be scheduled as soon as every CTA of this grid has passed it.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+// OFF by default, B200_PDL=1 switches the launch attribute on (without it the device-side instructions are no-ops).
+// Measured: a graph-replayed chain of GEMMs gains 0.3-1 us per launch, but the whole cfg2 train step LOSES 1.2 %
+// (83.7 vs 82.6 ms, two runs each on one box): the successor's CTAs park on the SMs the current kernel's tail leaves
+// idle -- exactly the SMs the low-priority side stream (LoRA weight gradients) was filling.
+inline bool pdl_enabled() {
+  static const bool on = [] { const char* e = getenv("B200_PDL"); return e && e[0] == '1'; }();
+  return on;
+}
+
+// cudaLaunchKernelEx configuration with the programmatic-serialization attribute (and a cluster size if > 1)
+struct PdlLaunch {
+  cudaLaunchConfig_t cfg;
+  cudaLaunchAttribute attr[2];
+  PdlLaunch(dim3 grid, dim3 block, size_t smem, cudaStream_t stream, int cluster = 1) {
+    cfg = cudaLaunchConfig_t{};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    int n = 0;
+    if (cluster > 1) {
+      attr[n].id = cudaLaunchAttributeClusterDimension;
+      attr[n].val.clusterDim.x = cluster;
+      attr[n].val.clusterDim.y = 1;
+      attr[n].val.clusterDim.z = 1;
+      ++n;
+    }
+    if (pdl_enabled()) {
+      attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      attr[n].val.programmaticStreamSerializationAllowed = 1;
+      ++n;
+    }
+    cfg.attrs = attr;
+    cfg.numAttrs = n;
+  }
+};
+
+// kernel<<<grid, block, smem, stream>>>(args...) with the programmatic-serialization attribute.  KERN may not contain a
+// top-level comma (bind `auto k = kernel<A, B>;` first).
+#define B200_LAUNCH(KERN, GRID, BLOCK, SMEM, STREAM, ...)                                  \
+  do {                                                                                     \
+    b200::PdlLaunch L_(dim3(GRID), dim3(BLOCK), (size_t)(SMEM), (cudaStream_t)(STREAM));   \
+    cudaLaunchKernelEx(&L_.cfg, KERN, __VA_ARGS__);                                        \
+  } while (0)
+
 // Byte offset of 16-B chunk `c` (0..7) of row `r` inside a SW128 tile of 128-B rows.
 __device__ __forceinline__ uint32_t sw128_off(uint32_t r, uint32_t c) {
   return r * 128u + ((c ^ (r & 7u)) << 4);

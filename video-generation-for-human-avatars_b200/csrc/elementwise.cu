@@ -92,6 +92,8 @@ __global__ void __launch_bounds__(128) norm_mod_fwd_row_kernel(
     const bf16* __restrict__ x, int64_t ldx, bf16* __restrict__ y, int64_t ldy,
     const bf16* __restrict__ scale, const bf16* __restrict__ shift, int64_t mod_stride,
     int64_t rows, int D, int64_t rows_per_mod, float eps, int ln) {
+  pdl_launch();
+  pdl_wait();
   __shared__ float red[8];
   const int64_t row0 = (int64_t)blockIdx.x * 2;
   const bool two = row0 + 1 < rows;
@@ -158,6 +160,8 @@ __global__ void __launch_bounds__(128) norm_mod_bwd_row_kernel(
     const bf16* __restrict__ scale, int64_t mod_stride, const bf16* __restrict__ dres,
     int64_t lddres, bf16* __restrict__ dx, int64_t lddx, bf16* __restrict__ prod, int64_t ldprod, int64_t rows, int D,
     int64_t rows_per_mod, float eps, int ln) {
+  pdl_launch();
+  pdl_wait();
   __shared__ float red[8];
   const int64_t row = blockIdx.x;
   const bf16* xr = x + row * ldx;
@@ -237,6 +241,8 @@ __global__ void __launch_bounds__(128) qknorm_rope_fwd_row_kernel(
     const bf16* __restrict__ wq, const bf16* __restrict__ wk, const bf16* __restrict__ cosp,
     const bf16* __restrict__ sinp, int64_t ldcs, bf16* __restrict__ oq, int64_t ldoq,
     bf16* __restrict__ ok, int64_t ldok, int64_t rows_q, int64_t rows_k, int D, float eps) {
+  pdl_launch();
+  pdl_wait();
   __shared__ float red[8];
   const int64_t w = blockIdx.x;
   const bool is_k = w >= rows_q;
@@ -299,6 +305,8 @@ __global__ void __launch_bounds__(128) qknorm_rope_bwd_row_kernel(
     const bf16* __restrict__ sinp, int64_t ldcs, bf16* __restrict__ oq, int64_t ldoq,
     bf16* __restrict__ ok, int64_t ldok, bf16* __restrict__ pq, int64_t ldpq, bf16* __restrict__ pk, int64_t ldpk,
     int64_t rows_q, int64_t rows_k, int D, float eps) {
+  pdl_launch();
+  pdl_wait();
   __shared__ float red[8];
   const int64_t w = blockIdx.x;
   const bool is_k = w >= rows_q;
@@ -423,6 +431,8 @@ __global__ void __launch_bounds__(128) qknorm_rope_fwd_pair_kernel(
     const bf16* __restrict__ wq, const bf16* __restrict__ wk, const bf16* __restrict__ cosp,
     const bf16* __restrict__ sinp, int64_t ldcs, bf16* __restrict__ oq, int64_t ldoq,
     bf16* __restrict__ ok, int64_t ldok, int D, float eps) {
+  pdl_launch();
+  pdl_wait();
   __shared__ float red[8];
   const int64_t row = blockIdx.x;
   uint4 qp[NCH], kp[NCH], cp[NCH], sp[NCH];
@@ -471,6 +481,8 @@ __global__ void __launch_bounds__(128) qknorm_rope_bwd_pair_kernel(
     const bf16* __restrict__ sinp, int64_t ldcs, bf16* __restrict__ oq, int64_t ldoq,
     bf16* __restrict__ ok, int64_t ldok, bf16* __restrict__ pq, int64_t ldpq, bf16* __restrict__ pk, int64_t ldpk,
     int D, float eps) {
+  pdl_launch();
+  pdl_wait();
   __shared__ float red[8];
   const int64_t row = blockIdx.x;
   uint4 qp[NCH], kp[NCH], cp[NCH], sp[NCH], gq0[NCH], gq1[NCH], gk0[NCH], gk1[NCH];
@@ -576,6 +588,8 @@ __global__ void __launch_bounds__(256) rf_noise_kernel(const bf16* __restrict__ 
                                                        const float* __restrict__ t,
                                                        bf16* __restrict__ xt, bf16* __restrict__ v,
                                                        int64_t n8, int64_t per_sample8) {
+  pdl_launch();
+  pdl_wait();
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n8;
        i += (int64_t)gridDim.x * blockDim.x) {
     float tt = t[i / per_sample8];
@@ -597,6 +611,8 @@ __global__ void __launch_bounds__(256) rf_loss_kernel(const bf16* __restrict__ o
                                                       bf16* __restrict__ dout,
                                                       float* __restrict__ partial, int64_t n8,
                                                       float gcoef) {
+  pdl_launch();
+  pdl_wait();
   float acc = 0.f;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n8;
        i += (int64_t)gridDim.x * blockDim.x) {
@@ -622,6 +638,8 @@ __global__ void __launch_bounds__(256) rf_loss_kernel(const bf16* __restrict__ o
 __global__ void __launch_bounds__(256) rf_loss_final_kernel(const float* __restrict__ partial,
                                                             int nparts, float inv_numel,
                                                             float* __restrict__ loss) {
+  pdl_launch();
+  pdl_wait();
   float acc = 0.f;
   for (int i = threadIdx.x; i < nparts; i += 256) acc += partial[i];
   __shared__ float red[8];
@@ -645,6 +663,8 @@ __global__ void __launch_bounds__(256) lerp_condition_kernel(bf16* __restrict__ 
                                                              const bf16* __restrict__ pose, int N,
                                                              int C, int HW, float w_ref,
                                                              float w_pose, int n_off, int N_total) {
+  pdl_launch();
+  pdl_wait();
   __shared__ float tile[32][33];
   int b = blockIdx.z;
   int n0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
@@ -678,6 +698,8 @@ __global__ void __launch_bounds__(256) rowscale_kernel(const bf16* __restrict__ 
                                                        const bf16* __restrict__ g, int64_t gstride,
                                                        bf16* __restrict__ out, int64_t ldo,
                                                        int64_t rows, int D8, int64_t rows_per_mod) {
+  pdl_launch();
+  pdl_wait();
   const int64_t total = rows * D8;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < total; i0 += 4 * stride) {
@@ -708,6 +730,8 @@ __global__ void __launch_bounds__(256) rowscale_kernel(const bf16* __restrict__ 
 // out[n] = sum_m x[m, n]   (bias gradients).  grid.x tiles columns by 64, block 256 = 64 cols x 4
 __global__ void __launch_bounds__(256) colsum_kernel(const bf16* __restrict__ x, int64_t ldx,
                                                      float* __restrict__ out, int64_t rows, int N) {
+  pdl_launch();
+  pdl_wait();
   __shared__ float red[4][64];
   int c = blockIdx.x * 64 + (threadIdx.x & 63);
   int part = threadIdx.x >> 6;
@@ -730,6 +754,8 @@ __global__ void __launch_bounds__(256) colsum_groups_part_kernel(const bf16* __r
                                                                  const bf16* __restrict__ b, int64_t ldb,
                                                                  float* __restrict__ part, int N, int64_t rows_per_group,
                                                                  int chunks_per_group) {
+  pdl_launch();
+  pdl_wait();
   const int chunk = blockIdx.x, panel = blockIdx.y;
   const int g = chunk / chunks_per_group, cg = chunk % chunks_per_group;
   const int64_t r0 = (int64_t)g * rows_per_group + (int64_t)cg * CSG_ROWS;
@@ -783,6 +809,8 @@ __global__ void __launch_bounds__(256) attn_delta_kernel(const bf16* __restrict_
                                                          const bf16* __restrict__ dout, int64_t lddo,
                                                          float* __restrict__ delta, int B, int H,
                                                          int Nq) {
+  pdl_launch();
+  pdl_wait();
   const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t item = gid >> 3;  // (row pair, h)
   const int sub = gid & 7;
@@ -833,6 +861,8 @@ __global__ void __launch_bounds__(256) attn_merge_kernel(float* __restrict__ o_a
                                                          const float* __restrict__ lse_i,
                                                          bf16* __restrict__ out, int64_t ldout, int B,
                                                          int H, int N, int first) {
+  pdl_launch();
+  pdl_wait();
   int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   int64_t item = gid >> 3;
   int sub = gid & 7;
@@ -874,8 +904,8 @@ using namespace b200;
 // block-per-row kernels: one 128-thread block per row, NCH = 1 (D <= 1024) or 2 (D <= 2048) chunks per thread
 #define ROWBLOCK_DISPATCH(KERNEL, D, ROWS, STREAM, ...)                              \
   do {                                                                               \
-    if ((D) <= 1024) KERNEL<1><<<(unsigned)(ROWS), 128, 0, STREAM>>>(__VA_ARGS__);   \
-    else KERNEL<2><<<(unsigned)(ROWS), 128, 0, STREAM>>>(__VA_ARGS__);               \
+    if ((D) <= 1024) { auto k_ = KERNEL<1>; B200_LAUNCH(k_, (unsigned)(ROWS), 128, 0, STREAM, __VA_ARGS__); } \
+    else { auto k_ = KERNEL<2>; B200_LAUNCH(k_, (unsigned)(ROWS), 128, 0, STREAM, __VA_ARGS__); }             \
   } while (0)
 static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
@@ -992,7 +1022,7 @@ extern "C" int b200_rf_noise(const void* x0, const void* noise, const float* t, 
   int64_t n8 = batch * per_sample / 8;
   if (n8 == 0) return 0;
   int blocks = (int)((n8 + 255) / 256 < 148 * 8 ? (n8 + 255) / 256 : 148 * 8);
-  rf_noise_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>((const bf16*)x0, (const bf16*)noise, t,
+  B200_LAUNCH(rf_noise_kernel, blocks, 256, 0, (cudaStream_t)stream, (const bf16*)x0, (const bf16*)noise, t,
                                                             (bf16*)xt, (bf16*)v, n8, per_sample / 8);
   return launch_status("rf_noise");
 }
@@ -1008,10 +1038,10 @@ extern "C" int b200_rf_loss(const void* out, const void* target, void* dout, flo
   CHECK_ARG(workspace_bytes >= b200_rf_loss_workspace_bytes(), "rf_loss: workspace too small");
   int64_t n8 = numel / 8;
   int blocks = (int)((n8 + 255) / 256 < 148 * 8 ? (n8 + 255) / 256 : 148 * 8);
-  rf_loss_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>((const bf16*)out, (const bf16*)target,
+  B200_LAUNCH(rf_loss_kernel, blocks, 256, 0, (cudaStream_t)stream, (const bf16*)out, (const bf16*)target,
                                                            (bf16*)dout, (float*)workspace, n8,
                                                            grad_scale * 2.f / (float)numel);
-  rf_loss_final_kernel<<<1, 256, 0, (cudaStream_t)stream>>>((const float*)workspace, blocks,
+  B200_LAUNCH(rf_loss_final_kernel, 1, 256, 0, (cudaStream_t)stream, (const float*)workspace, blocks,
                                                             1.f / (float)numel, loss);
   return launch_status("rf_loss");
 }
@@ -1025,7 +1055,7 @@ extern "C" int b200_lerp_condition(void* tokens, const void* ref, const void* po
             "lerp_condition: N_total must be frames x HW and the shard must lie inside it");
   if (B == 0 || N == 0) return 0;
   dim3 grid((N + 31) / 32, (C + 31) / 32, B);
-  lerp_condition_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((bf16*)tokens, (const bf16*)ref,
+  B200_LAUNCH(lerp_condition_kernel, grid, 256, 0, (cudaStream_t)stream, (bf16*)tokens, (const bf16*)ref,
                                                                 (const bf16*)pose, N, C, HW, w_ref,
                                                                 w_pose, token_offset, N_total);
   return launch_status("lerp_condition");
@@ -1041,7 +1071,7 @@ extern "C" int b200_rowscale(const void* x, int64_t ldx, const void* g, int64_t 
   if (total == 0) return 0;
   const int64_t want = (total + 1023) / 1024;  // four vectors per thread
   int blocks = (int)(want < 148 * 32 ? want : 148 * 32);
-  rowscale_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>((const bf16*)x, ldx, (const bf16*)g,
+  B200_LAUNCH(rowscale_kernel, blocks, 256, 0, (cudaStream_t)stream, (const bf16*)x, ldx, (const bf16*)g,
                                                             gstride, (bf16*)out, ldo, rows, D / 8,
                                                             rows_per_mod);
   return launch_status("rowscale");
@@ -1049,7 +1079,7 @@ extern "C" int b200_rowscale(const void* x, int64_t ldx, const void* g, int64_t 
 
 extern "C" int b200_colsum(const void* x, int64_t ldx, float* out, int64_t rows, int N, void* stream) {
   CHECK_ARG(x && out && rows >= 0 && N > 0, "colsum: bad arguments");
-  colsum_kernel<<<(N + 63) / 64, 256, 0, (cudaStream_t)stream>>>((const bf16*)x, ldx, out, rows, N);
+  B200_LAUNCH(colsum_kernel, (N + 63) / 64, 256, 0, (cudaStream_t)stream, (const bf16*)x, ldx, out, rows, N);
   return launch_status("colsum");
 }
 
@@ -1071,7 +1101,7 @@ extern "C" int b200_colsum_groups(const void* a, int64_t lda, const void* b, int
   if (cudaMemsetAsync(out, 0, (size_t)groups * N * sizeof(float), (cudaStream_t)stream) != cudaSuccess)
     return launch_status("colsum_groups: memset");
   dim3 g1((unsigned)(groups * cpg), (unsigned)((N + 2047) / 2048));
-  colsum_groups_part_kernel<<<g1, 256, 0, (cudaStream_t)stream>>>((const bf16*)a, lda, (const bf16*)b, ldb, out, N,
+  B200_LAUNCH(colsum_groups_part_kernel, g1, 256, 0, (cudaStream_t)stream, (const bf16*)a, lda, (const bf16*)b, ldb, out, N,
                                                                   rows_per_group, cpg);
   return launch_status("colsum_groups");
 }
@@ -1084,7 +1114,7 @@ extern "C" int b200_attn_merge(float* o_acc, int64_t ldacc, float* lse_acc, cons
             "attn_merge: 16-byte alignment required");
   int64_t threads = (int64_t)B * N * H * 8;
   if (threads == 0) return 0;
-  attn_merge_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+  B200_LAUNCH(attn_merge_kernel, (unsigned)((threads + 255) / 256), 256, 0, (cudaStream_t)stream, 
       o_acc, ldacc, lse_acc, (const bf16*)o_i, ldo, lse_i, (bf16*)out, ldout, B, H, N, first);
   return launch_status("attn_merge");
 }
@@ -1096,7 +1126,7 @@ extern "C" int b200_attn_delta(const void* o, int64_t ldo, const void* dout, int
             "attn_delta: 16-byte alignment required");
   int64_t threads = (((int64_t)B * Nq + 1) / 2) * H * 8;  // one thread per (row pair, head, 8-element slice)
   if (threads == 0) return 0;
-  attn_delta_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+  B200_LAUNCH(attn_delta_kernel, (unsigned)((threads + 255) / 256), 256, 0, (cudaStream_t)stream, 
       (const bf16*)o, ldo, (const bf16*)dout, lddo, delta, B, H, Nq);
   return launch_status("attn_delta");
 }

@@ -248,6 +248,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  // everything above overlapped the previous kernel's tail; from here on its outputs are read
+  pdl_launch();
+  pdl_wait();
 
   // persistent walk: a CTA (or CTA pair) first takes its share of the stream-K region (if any), then every
   // `work_step`-th whole work item (splits > 1, groups > 1 and stream-K exclude each other)
@@ -444,7 +447,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           uint4 prer[8];  // pre-activation of this thread's 64 columns (stash mode), kept for the second store
           // residual / stashed pre-activation of this thread's 64 columns: eight independent row-strided
           // 16-byte loads in flight together, before the TMEM reads (issued one by one behind them they
-          // cost ~8 x the L2 latency per slab and made the gate+residual and GELU' epilogues the bottleneck)
+          // cost ~8 x the L2 latency per slab and made the gate+residual and GELU' epilogues the bottleneck).
+          // (A coalesced read -- quarter-warp per row, transposed through the staging buffer -- measured the same:
+          // 49.2 vs 49.5 us at N = K = 2048, 164.2 vs 164.2 us for GELU'; the loads are not what these epilogues wait for.)
           uint4 ext[8];
           const bf16* ext_row = p.epi == EPI_GELU_GRAD ? aux_row : res_row;
 #pragma unroll
@@ -645,26 +650,11 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
     attr_set = true;
   }
   int tiles = p.m_tiles * p.n_tiles * p.splits * p.groups;  // CTA2: m_tiles counts 256-row tile pairs
-  if (!CTA2) {
-    int grid = tiles < num_sms() ? tiles : num_sms();
-    kern<<<grid, 384, Cfg::SMEM, stream>>>(tmA, tmB, tmA2, tmB2, tmC, tmAux, p);
-    return launch_status("gemm_bf16");
-  }
-  const int pairs = num_sms() / 2;
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(2 * (tiles < pairs ? tiles : pairs), 1, 1);
-  cfg.blockDim = dim3(384, 1, 1);
-  cfg.dynamicSmemBytes = Cfg::SMEM;
-  cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = 2;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmA2, tmB2, tmC, tmAux, p);
-  if (e != cudaSuccess) return launch_status("gemm_bf16 (CTA pair launch)");
+  const int slots = CTA2 ? num_sms() / 2 : num_sms();
+  const int ctas = (tiles < slots ? tiles : slots) * (CTA2 ? 2 : 1);
+  PdlLaunch L(dim3(ctas, 1, 1), dim3(384, 1, 1), Cfg::SMEM, stream, CTA2 ? 2 : 1);
+  cudaError_t e = cudaLaunchKernelEx(&L.cfg, kern, tmA, tmB, tmA2, tmB2, tmC, tmAux, p);
+  if (e != cudaSuccess) return launch_status(CTA2 ? "gemm_bf16 (CTA pair launch)" : "gemm_bf16");
   return launch_status("gemm_bf16");
 }
 

@@ -83,6 +83,8 @@ __device__ __forceinline__ float cfg_star_alpha(const GuidanceParams& p, int b) 
 
 // phase 1: <text, uncond> and |uncond|^2 per sample
 __global__ void __launch_bounds__(256) guidance_dot_kernel(GuidanceParams p) {
+  pdl_launch();
+  pdl_wait();
   const int b = blockIdx.y;
   double acc[2] = {0.0, 0.0};
   const int64_t n8 = p.per / 8;
@@ -104,6 +106,8 @@ __global__ void __launch_bounds__(256) guidance_dot_kernel(GuidanceParams p) {
 
 // phase 2: sums and sums of squares of the text prediction and of the guided prediction
 __global__ void __launch_bounds__(256) guidance_std_kernel(GuidanceParams p) {
+  pdl_launch();
+  pdl_wait();
   const int b = blockIdx.y;
   const float gs = p.scalars[0], stg = p.scalars[1];
   const float alpha = cfg_star_alpha(p, b);
@@ -127,6 +131,8 @@ __global__ void __launch_bounds__(256) guidance_std_kernel(GuidanceParams p) {
 
 // phase 3: guided prediction (x std-rescale factor), Euler step, conditioning select, next model input
 __global__ void __launch_bounds__(256) guidance_apply_kernel(GuidanceParams p) {
+  pdl_launch();
+  pdl_wait();
   const int b = blockIdx.y;
   const float gs = p.scalars[0], stg = p.scalars[1], rs = p.scalars[2], t = p.scalars[3];
   const float alpha = cfg_star_alpha(p, b);
@@ -217,8 +223,8 @@ extern "C" int b200_guidance_step(const void* v, float* x, void* x_next, int n_n
     cudaError_t e = cudaMemsetAsync(workspace, 0, b200_guidance_step_workspace_bytes(B), s);
     if (e != cudaSuccess) return arg_error("guidance_step: cudaMemsetAsync failed", (int)e);
   }
-  if (p.has_cfg && p.cfg_star) guidance_dot_kernel<<<grid, 256, 0, s>>>(p);
-  if (p.rescale) guidance_std_kernel<<<grid, 256, 0, s>>>(p);
-  guidance_apply_kernel<<<grid, 256, 0, s>>>(p);
+  if (p.has_cfg && p.cfg_star) B200_LAUNCH(guidance_dot_kernel, grid, 256, 0, s, p);
+  if (p.rescale) B200_LAUNCH(guidance_std_kernel, grid, 256, 0, s, p);
+  B200_LAUNCH(guidance_apply_kernel, grid, 256, 0, s, p);
   return launch_status("guidance_step");
 }
