@@ -35,7 +35,7 @@ WORKLOADS = {
     # long clip: ONE sample sequence-sharded over all ranks (ring attn1); strong scaling, not the default
     # sampling: forward-only, 40 denoise steps per "step" of the bench; not the default workload
     "cfg4": (1, 16, 15, 22, "LTXV-2B bf16 rectified-flow sampling bs1 121x480x704 (5280 latent tokens), 40 Euler steps, forward only"),
-    "cfg5": (1, 33, 16, 24, "LTXV-2B bf16 LoRA train step bs1 257x512x768 (12672 latent tokens), sequence-sharded ring attn1"),
+    "cfg5": (1, 33, 16, 24, "LTXV-2B bf16 LoRA train step bs1 257x512x768 (12672 latent tokens), sequence-sharded attn1"),
 }
 METRIC = "LTXV-2B train-step latent tok/s"
 UNIT = "latent tokens/s"
