@@ -534,7 +534,7 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
       }
       if (warp == 18) TRACE(4096 + i * 4 + 2);
     }
-    if (lane == 0) tma_store_wait_all<0>();
+    if (lane == 0) tma_store_wait_read<0>();  // staging read; the reduce-adds themselves complete with the kernel
   }
   tc_fence_before();
   __syncthreads();

@@ -138,10 +138,14 @@ __device__ __forceinline__ float gelu_tanh_grad(float x) {
 // pre-activation, which is returned in `pre`) / GELU' -> * gate -> + residual.
 // `ext` = this thread's 8 values of the external row operand (residual, or the stashed pre-activation for
 // GELU'), loaded by the caller ahead of the TMEM reads so that its global-load latency is paid once per slab.
-__device__ __forceinline__ void epi_math8(float (&v)[8], uint4& pre, int n, const GemmParams& p, const bf16* bias,
-                                          const bf16* gate_row, bool has_res, const uint4& ext) {
-  if (bias) {
-    uint4 u = __ldg(reinterpret_cast<const uint4*>(bias + n));
+// `bias_u` / `gate_u` = the 8 bias / gate values of these columns, likewise loaded by the caller in one batch per 32
+// columns: fetched here, one 16-byte load per 8 columns between the shared-memory stores, they serialised into ~0.3 us
+// each and made the epilogue of a tile 6-8 us long (tools/gemm_trace.py) -- the fixed cost of every GEMM launch.
+__device__ __forceinline__ void epi_math8(float (&v)[8], uint4& pre, const GemmParams& p, bool has_bias,
+                                          const uint4& bias_u, bool has_gate, const uint4& gate_u, bool has_res,
+                                          const uint4& ext) {
+  if (has_bias) {
+    const uint4 u = bias_u;
     v[0] += bf16_lo(u.x); v[1] += bf16_hi(u.x); v[2] += bf16_lo(u.y); v[3] += bf16_hi(u.y);
     v[4] += bf16_lo(u.z); v[5] += bf16_hi(u.z); v[6] += bf16_lo(u.w); v[7] += bf16_hi(u.w);
   }
@@ -167,8 +171,8 @@ __device__ __forceinline__ void epi_math8(float (&v)[8], uint4& pre, int n, cons
     v[0] = bf16_lo(pre.x); v[1] = bf16_hi(pre.x); v[2] = bf16_lo(pre.y); v[3] = bf16_hi(pre.y);
     v[4] = bf16_lo(pre.z); v[5] = bf16_hi(pre.z); v[6] = bf16_lo(pre.w); v[7] = bf16_hi(pre.w);
   }
-  if (gate_row) {
-    uint4 u = __ldg(reinterpret_cast<const uint4*>(gate_row + n));
+  if (has_gate) {
+    const uint4 u = gate_u;
     v[0] *= bf16_lo(u.x); v[1] *= bf16_hi(u.x); v[2] *= bf16_lo(u.y); v[3] *= bf16_hi(u.y);
     v[4] *= bf16_lo(u.z); v[5] *= bf16_hi(u.z); v[6] *= bf16_lo(u.w); v[7] *= bf16_hi(u.w);
   }
@@ -194,6 +198,19 @@ struct GemmCfg {
   static constexpr int SMEM = NSTAGE * STAGE + STAGING + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
+#ifdef B200_TRACE
+// debug build only: per-CTA phase timestamps (globaltimer, ns) of the LAST gemm launch, read by tools/gemm_trace.py
+__device__ unsigned long long g_gemm_trace[160 * 32];
+__device__ __forceinline__ unsigned long long gtime() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#define GTRACE(slot) do { if (blockIdx.x < 160) g_gemm_trace[blockIdx.x * 32 + (slot)] = gtime(); } while (0)
+#else
+#define GTRACE(slot) do {} while (0)
+#endif
+
 template <int BN, bool A_MN, bool B_MN, bool CTA2>
 __global__ void __launch_bounds__(384, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
@@ -214,6 +231,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   const uint32_t tmem_slot = bar_base + (2 * NSTAGE + 4) * 8;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) GTRACE(0);
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
@@ -251,6 +269,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   // everything above overlapped the previous kernel's tail; from here on its outputs are read
   pdl_launch();
   pdl_wait();
+  if (threadIdx.x == 0) GTRACE(1);
 
   // persistent walk: a CTA (or CTA pair) first takes its share of the stream-K region (if any), then every
   // `work_step`-th whole work item (splits > 1, groups > 1 and stream-K exclude each other)
@@ -324,6 +343,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       for (int kb = kb_begin; kb < kb_end; ++kb) {
         mbar_wait(full_bar(stage), phase);
         tc_fence_after();
+        if (kb == kb_begin && lane == 0) GTRACE(2);   // (last tile's value survives)
         if (elect_one()) {
           const uint64_t da = desc_adv(da0, stage * Cfg::STAGE), db = desc_adv(db0, stage * Cfg::STAGE);
 #pragma unroll
@@ -343,6 +363,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         else umma_commit(tfull_bar(acc));
       }
       __syncwarp();
+      if (lane == 0) GTRACE(3);
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
@@ -363,6 +384,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       const int crow = g * p.c_gr, ccol = g * p.c_gc;  // output displacement of this group
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
+      if (warp == 4 && lane == 0) GTRACE(4);
       // ---- stream-K: partial accumulators travel through global memory ----
       int sk_from[4];  // CTAs (pairs) whose partials of this tile are added here
       int sk_n = 0;
@@ -460,11 +482,25 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           }
           if (lane == 0) tma_store_wait_read<0>();  // the previous slab has left the staging buffer
           __syncwarp();
+          if (warp == 4 && lane == 0) GTRACE(c == 0 ? 8 : 12);
 #pragma unroll
           for (int hc = 0; hc < 2; ++hc) {
             uint32_t r[32];
             tmem_ld32(t_row + c + hc * 32, r);
+            // bias and gate of these 32 columns: eight loads in flight under the TMEM read
+            uint4 bq[4], gq[4];
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              const int n = n_slab + hc * 32 + g * 8;
+              bq[g] = gq[g] = make_uint4(0, 0, 0, 0);
+              if (n < p.N) {
+                if (bias_g) bq[g] = __ldg(reinterpret_cast<const uint4*>(bias_g + n));
+                if (gate_row) gq[g] = __ldg(reinterpret_cast<const uint4*>(gate_row + n));
+              }
+            }
             tmem_ld_wait();
+            if (warp == 4 && lane == 0 && hc == 0) GTRACE(c == 0 ? 9 : 13);
+            if (warp == 4 && lane == 0) GTRACE(16 + (c == 0 ? 0 : 4) + hc * 2);
             for (int ci = 0; ci < sk_n; ++ci) {
               const float* pb = p.sk_ws + (size_t)(sk_from[ci] * 2 + rank) * 128 * BN;
 #pragma unroll
@@ -484,7 +520,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 #pragma unroll
               for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[g * 8 + i]);
               uint4 u, pre = make_uint4(0, 0, 0, 0);
-              if (n < p.N) epi_math8(v, pre, n, p, bias_g, gate_row, p.res != nullptr, ext[hc * 4 + g]);
+              if (n < p.N)
+                epi_math8(v, pre, p, bias_g != nullptr, bq[g], gate_row != nullptr, gq[g], p.res != nullptr, ext[hc * 4 + g]);
               prer[hc * 4 + g] = pre;
               u.x = pack_bf16x2(v[0], v[1]); u.y = pack_bf16x2(v[2], v[3]);
               u.z = pack_bf16x2(v[4], v[5]); u.w = pack_bf16x2(v[6], v[7]);
@@ -492,13 +529,16 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                            "r"(u.x), "r"(u.y), "r"(u.z), "r"(u.w)
                            : "memory");
             }
+            if (warp == 4 && lane == 0) GTRACE(17 + (c == 0 ? 0 : 4) + hc * 2);
           }
+          if (warp == 4 && lane == 0) GTRACE(c == 0 ? 10 : 14);
           fence_proxy_async_smem();
           __syncwarp();
           if (lane == 0) {
             tma_store_2d(&tmC, stg, n_slab + ccol, row0 + crow);
             tma_store_commit();
           }
+          if (warp == 4 && lane == 0) GTRACE(c == 0 ? 11 : 15);
           if (stash) {
             if (lane == 0) tma_store_wait_read<0>();
             __syncwarp();
@@ -604,7 +644,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
-    if (lane == 0) tma_store_wait_all<0>();
+    if (warp == 4 && lane == 0) GTRACE(5);
+    // the staging slab only has to stay valid until the TMA has READ it; the writes complete with the kernel
+    if (lane == 0) tma_store_wait_read<0>();
+    if (warp == 4 && lane == 0) GTRACE(6);
   }
   tc_fence_before();
   __syncthreads();
@@ -614,6 +657,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     if (CTA2) tmem_dealloc_2cta(tmem_base, Cfg::TMEM_COLS);
     else tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
   }
+  if (threadIdx.x == 0) GTRACE(7);
 }
 
 static int g_num_sms = 0;
@@ -840,6 +884,12 @@ static int gemm_impl(const void* A, int64_t lda, int a_kmajor_rows_are_k, const 
 #undef DISPATCH
   return arg_error("gemm_bf16: unreachable");
 }
+
+#ifdef B200_TRACE
+extern "C" int b200_debug_gemm_trace(unsigned long long* host, int n) {
+  return (int)cudaMemcpyFromSymbol(host, g_gemm_trace, sizeof(unsigned long long) * n);
+}
+#endif
 
 // See include/b200ltx.h for the contracts.
 extern "C" int b200_gemm_bf16(const void* A, int64_t lda, int a_kmajor_rows_are_k, const void* B,
