@@ -21,6 +21,8 @@
 #include <cstdlib>
 
 #include "api_internal.h"
+#include <type_traits>
+
 #include "common.cuh"
 #include "tmap.h"
 
@@ -141,6 +143,7 @@ __device__ __forceinline__ float gelu_tanh_grad(float x) {
 // `bias_u` / `gate_u` = the 8 bias / gate values of these columns, likewise loaded by the caller in one batch per 32
 // columns: fetched here, one 16-byte load per 8 columns between the shared-memory stores, they serialised into ~0.3 us
 // each and made the epilogue of a tile 6-8 us long (tools/gemm_trace.py) -- the fixed cost of every GEMM launch.
+template <int EPI>
 __device__ __forceinline__ void epi_math8(float (&v)[8], uint4& pre, const GemmParams& p, bool has_bias,
                                           const uint4& bias_u, bool has_gate, const uint4& gate_u, bool has_res,
                                           const uint4& ext) {
@@ -149,7 +152,7 @@ __device__ __forceinline__ void epi_math8(float (&v)[8], uint4& pre, const GemmP
     v[0] += bf16_lo(u.x); v[1] += bf16_hi(u.x); v[2] += bf16_lo(u.y); v[3] += bf16_hi(u.y);
     v[4] += bf16_lo(u.z); v[5] += bf16_hi(u.z); v[6] += bf16_lo(u.w); v[7] += bf16_hi(u.w);
   }
-  if (p.epi == EPI_GELU) {
+  if (EPI == EPI_GELU) {
     if (p.aux) {
       pre.x = pack_bf16x2(v[0], v[1]); pre.y = pack_bf16x2(v[2], v[3]);
       pre.z = pack_bf16x2(v[4], v[5]); pre.w = pack_bf16x2(v[6], v[7]);
@@ -158,13 +161,13 @@ __device__ __forceinline__ void epi_math8(float (&v)[8], uint4& pre, const GemmP
     }
 #pragma unroll
     for (int i = 0; i < 8; ++i) v[i] = gelu_tanh(v[i]);
-  } else if (p.epi == EPI_GELU_GRAD) {
+  } else if (EPI == EPI_GELU_GRAD) {
     const uint4 u = ext;
     float h[8] = {bf16_lo(u.x), bf16_hi(u.x), bf16_lo(u.y), bf16_hi(u.y),
                   bf16_lo(u.z), bf16_hi(u.z), bf16_lo(u.w), bf16_hi(u.w)};
 #pragma unroll
     for (int i = 0; i < 8; ++i) v[i] *= gelu_tanh_grad(h[i]);
-  } else if (p.epi == EPI_STASH) {
+  } else if (EPI == EPI_STASH) {
     // the pre-gate output leaves through the second store: a trainable AdaLN gate needs it for d(gate) = sum dy * u
     pre.x = pack_bf16x2(v[0], v[1]); pre.y = pack_bf16x2(v[2], v[3]);
     pre.z = pack_bf16x2(v[4], v[5]); pre.w = pack_bf16x2(v[6], v[7]);
@@ -461,100 +464,144 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         // buffer and hands it to the TMA (cp.async.bulk.tensor store clips rows/columns past M, N).
         const uint32_t stg = stage_base + (warp - 4) * 4096;
         const int row0 = mt * 128 + ew * 32;
-        const bool stash = (p.epi == EPI_GELU || p.epi == EPI_STASH) && p.aux;  // bf16 pre-activation / pre-gate output: second store
+        // The slab loop is compiled three times and chosen per tile: MODE 0 = nothing but the conversion, 1 = bias
+        // only, 2 = everything (gate, residual, GELU / GELU' / stash, stream-K partials).  The general code executes
+        // ~400 instructions per thread and 32 columns (ncu: 15.7 k warp instructions per 128 x 256 tile, 13 k of them
+        // here) whichever operands are present; on 8 warps that is the 5-7 us un-overlapped tail of every launch
+        // (tools/gemm_trace.py) and issue slots taken from the MMA warp while it overlaps.  Most launches of a train
+        // step (all dgrads, the q/k/v projection) need mode 0 or 1.
+        auto run_slabs = [&](auto mode_tag, auto epi_tag, auto bg_tag) {
+          constexpr int MODE = decltype(mode_tag)::value;
+          constexpr int EPI = decltype(epi_tag)::value;     // general mode: the epilogue function, compile-time
+          constexpr bool BG = decltype(bg_tag)::value;      // a bias or a gate vector is present
+          const bool stash = MODE == 2 && (EPI == EPI_GELU || EPI == EPI_STASH) && p.aux;  // second store: bf16 pre-activation / pre-gate output
 #pragma unroll 1
-        for (int c = chalf * (BN / 2); c < (chalf + 1) * (BN / 2); c += 64) {
-          const int n_slab = nt * BN + c;
-          if (n_slab >= p.N) break;
-          uint4 prer[8];  // pre-activation of this thread's 64 columns (stash mode), kept for the second store
-          // residual / stashed pre-activation of this thread's 64 columns: eight independent row-strided
-          // 16-byte loads in flight together, before the TMEM reads (issued one by one behind them they
-          // cost ~8 x the L2 latency per slab and made the gate+residual and GELU' epilogues the bottleneck).
-          // (A coalesced read -- quarter-warp per row, transposed through the staging buffer -- measured the same:
-          // 49.2 vs 49.5 us at N = K = 2048, 164.2 vs 164.2 us for GELU'; the loads are not what these epilogues wait for.)
-          uint4 ext[8];
-          const bf16* ext_row = p.epi == EPI_GELU_GRAD ? aux_row : res_row;
+          for (int c = chalf * (BN / 2); c < (chalf + 1) * (BN / 2); c += 64) {
+            const int n_slab = nt * BN + c;
+            if (n_slab >= p.N) break;
+            uint4 prer[8];  // pre-activation of this thread's 64 columns (stash mode), kept for the second store
+            // residual / stashed pre-activation of this thread's 64 columns: eight independent row-strided
+            // 16-byte loads in flight together, before the TMEM reads (issued one by one behind them they
+            // cost ~8 x the L2 latency per slab and made the gate+residual and GELU' epilogues the bottleneck).
+            // (A coalesced read -- quarter-warp per row, transposed through the staging buffer -- measured the same:
+            // 49.2 vs 49.5 us at N = K = 2048, 164.2 vs 164.2 us for GELU'; the loads are not what these epilogues wait for.)
+            uint4 ext[8];
+            if constexpr (MODE == 2) {
+              const bf16* ext_row = EPI == EPI_GELU_GRAD ? aux_row : res_row;
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            ext[j] = make_uint4(0, 0, 0, 0);
-            if (ext_row != nullptr && row_ok && n_slab + j * 8 < p.N)
-              ext[j] = *reinterpret_cast<const uint4*>(ext_row + n_slab + j * 8);
-          }
-          if (lane == 0) tma_store_wait_read<0>();  // the previous slab has left the staging buffer
-          __syncwarp();
-          if (warp == 4 && lane == 0) GTRACE(c == 0 ? 8 : 12);
-#pragma unroll
-          for (int hc = 0; hc < 2; ++hc) {
-            uint32_t r[32];
-            tmem_ld32(t_row + c + hc * 32, r);
-            // bias and gate of these 32 columns: eight loads in flight under the TMEM read
-            uint4 bq[4], gq[4];
-#pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              const int n = n_slab + hc * 32 + g * 8;
-              bq[g] = gq[g] = make_uint4(0, 0, 0, 0);
-              if (n < p.N) {
-                if (bias_g) bq[g] = __ldg(reinterpret_cast<const uint4*>(bias_g + n));
-                if (gate_row) gq[g] = __ldg(reinterpret_cast<const uint4*>(gate_row + n));
+              for (int j = 0; j < 8; ++j) {
+                ext[j] = make_uint4(0, 0, 0, 0);
+                if (ext_row != nullptr && row_ok && n_slab + j * 8 < p.N)
+                  ext[j] = *reinterpret_cast<const uint4*>(ext_row + n_slab + j * 8);
               }
             }
-            tmem_ld_wait();
-            if (warp == 4 && lane == 0 && hc == 0) GTRACE(c == 0 ? 9 : 13);
-            if (warp == 4 && lane == 0) GTRACE(16 + (c == 0 ? 0 : 4) + hc * 2);
-            for (int ci = 0; ci < sk_n; ++ci) {
-              const float* pb = p.sk_ws + (size_t)(sk_from[ci] * 2 + rank) * 128 * BN;
-#pragma unroll
-              for (int q = 0; q < 8; ++q) {
-                const float4 a = __ldcg(reinterpret_cast<const float4*>(
-                    pb + ((size_t)((c + hc * 32) / 4 + q) * 128 + ew * 32 + lane) * 4));
-                r[q * 4 + 0] = __float_as_uint(__uint_as_float(r[q * 4 + 0]) + a.x);
-                r[q * 4 + 1] = __float_as_uint(__uint_as_float(r[q * 4 + 1]) + a.y);
-                r[q * 4 + 2] = __float_as_uint(__uint_as_float(r[q * 4 + 2]) + a.z);
-                r[q * 4 + 3] = __float_as_uint(__uint_as_float(r[q * 4 + 3]) + a.w);
-              }
-            }
-#pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              const int n = n_slab + hc * 32 + g * 8;
-              float v[8];
-#pragma unroll
-              for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[g * 8 + i]);
-              uint4 u, pre = make_uint4(0, 0, 0, 0);
-              if (n < p.N)
-                epi_math8(v, pre, p, bias_g != nullptr, bq[g], gate_row != nullptr, gq[g], p.res != nullptr, ext[hc * 4 + g]);
-              prer[hc * 4 + g] = pre;
-              u.x = pack_bf16x2(v[0], v[1]); u.y = pack_bf16x2(v[2], v[3]);
-              u.z = pack_bf16x2(v[4], v[5]); u.w = pack_bf16x2(v[6], v[7]);
-              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stg + sw128_off(lane, hc * 4 + g)),
-                           "r"(u.x), "r"(u.y), "r"(u.z), "r"(u.w)
-                           : "memory");
-            }
-            if (warp == 4 && lane == 0) GTRACE(17 + (c == 0 ? 0 : 4) + hc * 2);
-          }
-          if (warp == 4 && lane == 0) GTRACE(c == 0 ? 10 : 14);
-          fence_proxy_async_smem();
-          __syncwarp();
-          if (lane == 0) {
-            tma_store_2d(&tmC, stg, n_slab + ccol, row0 + crow);
-            tma_store_commit();
-          }
-          if (warp == 4 && lane == 0) GTRACE(c == 0 ? 11 : 15);
-          if (stash) {
-            if (lane == 0) tma_store_wait_read<0>();
+            if (lane == 0) tma_store_wait_read<0>();  // the previous slab has left the staging buffer
             __syncwarp();
+            if (warp == 4 && lane == 0) GTRACE(c == 0 ? 8 : 12);
 #pragma unroll
-            for (int j = 0; j < 8; ++j)
-              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stg + sw128_off(lane, j)), "r"(prer[j].x),
-                           "r"(prer[j].y), "r"(prer[j].z), "r"(prer[j].w)
-                           : "memory");
+            for (int hc = 0; hc < 2; ++hc) {
+              uint32_t r[32];
+              tmem_ld32(t_row + c + hc * 32, r);
+              // bias and gate of these 32 columns: eight loads in flight under the TMEM read
+              uint4 bq[4], gq[4];
+              if constexpr (BG) {
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {
+                  const int n = n_slab + hc * 32 + g * 8;
+                  bq[g] = gq[g] = make_uint4(0, 0, 0, 0);
+                  if (n < p.N) {
+                    if (bias_g) bq[g] = __ldg(reinterpret_cast<const uint4*>(bias_g + n));
+                    if (MODE == 2 && gate_row) gq[g] = __ldg(reinterpret_cast<const uint4*>(gate_row + n));
+                  }
+                }
+              }
+              tmem_ld_wait();
+              if (warp == 4 && lane == 0 && hc == 0) GTRACE(c == 0 ? 9 : 13);
+              if (warp == 4 && lane == 0) GTRACE(16 + (c == 0 ? 0 : 4) + hc * 2);
+              if constexpr (MODE == 2) {
+                for (int ci = 0; ci < sk_n; ++ci) {
+                  const float* pb = p.sk_ws + (size_t)(sk_from[ci] * 2 + rank) * 128 * BN;
+#pragma unroll
+                  for (int q = 0; q < 8; ++q) {
+                    const float4 a = __ldcg(reinterpret_cast<const float4*>(
+                        pb + ((size_t)((c + hc * 32) / 4 + q) * 128 + ew * 32 + lane) * 4));
+                    r[q * 4 + 0] = __float_as_uint(__uint_as_float(r[q * 4 + 0]) + a.x);
+                    r[q * 4 + 1] = __float_as_uint(__uint_as_float(r[q * 4 + 1]) + a.y);
+                    r[q * 4 + 2] = __float_as_uint(__uint_as_float(r[q * 4 + 2]) + a.z);
+                    r[q * 4 + 3] = __float_as_uint(__uint_as_float(r[q * 4 + 3]) + a.w);
+                  }
+                }
+              }
+#pragma unroll
+              for (int g = 0; g < 4; ++g) {
+                float v[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[g * 8 + i]);
+                uint4 u;
+                if constexpr (MODE == 2) {
+                  const int n = n_slab + hc * 32 + g * 8;
+                  uint4 pre = make_uint4(0, 0, 0, 0);
+                  if (n < p.N)
+                    epi_math8<EPI>(v, pre, p, BG && bias_g != nullptr, bq[g], BG && gate_row != nullptr, gq[g],
+                                   p.res != nullptr, ext[hc * 4 + g]);
+                  prer[hc * 4 + g] = pre;
+                } else if constexpr (MODE == 1) {   // columns past N get the zero bias loaded above and are clipped by the TMA
+                  const uint4 bu = bq[g];
+                  v[0] += bf16_lo(bu.x); v[1] += bf16_hi(bu.x); v[2] += bf16_lo(bu.y); v[3] += bf16_hi(bu.y);
+                  v[4] += bf16_lo(bu.z); v[5] += bf16_hi(bu.z); v[6] += bf16_lo(bu.w); v[7] += bf16_hi(bu.w);
+                }
+                u.x = pack_bf16x2(v[0], v[1]); u.y = pack_bf16x2(v[2], v[3]);
+                u.z = pack_bf16x2(v[4], v[5]); u.w = pack_bf16x2(v[6], v[7]);
+                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stg + sw128_off(lane, hc * 4 + g)),
+                             "r"(u.x), "r"(u.y), "r"(u.z), "r"(u.w)
+                             : "memory");
+              }
+              if (warp == 4 && lane == 0) GTRACE(17 + (c == 0 ? 0 : 4) + hc * 2);
+            }
+            if (warp == 4 && lane == 0) GTRACE(c == 0 ? 10 : 14);
             fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) {
-              tma_store_2d(&tmAux, stg, n_slab + ccol, row0 + crow);
+              tma_store_2d(&tmC, stg, n_slab + ccol, row0 + crow);
               tma_store_commit();
             }
+            if (warp == 4 && lane == 0) GTRACE(c == 0 ? 11 : 15);
+            if constexpr (MODE == 2) {
+              if (stash) {
+                if (lane == 0) tma_store_wait_read<0>();
+                __syncwarp();
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stg + sw128_off(lane, j)), "r"(prer[j].x),
+                               "r"(prer[j].y), "r"(prer[j].z), "r"(prer[j].w)
+                               : "memory");
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) {
+                  tma_store_2d(&tmAux, stg, n_slab + ccol, row0 + crow);
+                  tma_store_commit();
+                }
+              }
+            }
           }
-        }
+        };
+        const bool light = p.epi == EPI_NONE && p.gate == nullptr && p.res == nullptr && p.aux == nullptr && sk_n == 0;
+        const bool bg = bias_g != nullptr || gate_row != nullptr;
+        using I0 = std::integral_constant<int, 0>;
+        using I1 = std::integral_constant<int, 1>;
+        using I2 = std::integral_constant<int, 2>;
+#define B200_GENERAL(E)                                                              \
+  do {                                                                               \
+    if (bg) run_slabs(I2{}, std::integral_constant<int, E>{}, std::true_type{});     \
+    else run_slabs(I2{}, std::integral_constant<int, E>{}, std::false_type{});       \
+  } while (0)
+        if (light && !bg) run_slabs(I0{}, std::integral_constant<int, EPI_NONE>{}, std::false_type{});
+        else if (light) run_slabs(I1{}, std::integral_constant<int, EPI_NONE>{}, std::true_type{});
+        else if (p.epi == EPI_GELU) B200_GENERAL(EPI_GELU);
+        else if (p.epi == EPI_GELU_GRAD) B200_GENERAL(EPI_GELU_GRAD);
+        else if (p.epi == EPI_STASH) B200_GENERAL(EPI_STASH);
+        else B200_GENERAL(EPI_NONE);
+#undef B200_GENERAL
       } else
 #pragma unroll 1
       for (int c = chalf * (BN / 2); c < (chalf + 1) * (BN / 2); c += 32) {
