@@ -81,3 +81,16 @@ def test_device_feeder_overlapped_copies(tmp_path):
     for s, pose, ref in acc:
         assert torch.equal(pose.cpu(), ref["pose_latents"].to(torch.bfloat16).float())
         assert abs(float(s) - 1.0 - float(ref["latents"].to(torch.bfloat16).float().sum())) < 0.5
+
+
+def test_device_feeder_reset_reuses_buffers_cpu():
+    from b200_ltx import api
+    mk = lambda v: {"latents": torch.full((1, 2, 1, 2, 2), float(v)), "pose_latents": torch.zeros(1, 2, 1, 2, 2),
+                    "ref_image_latents": torch.zeros(1, 2, 1, 2, 2)}
+    f = api.DeviceFeeder([mk(1), mk(2)], "cpu", depth=2)
+    assert [float(b["latents"].flatten()[0]) for b in f] == [1.0, 2.0]
+    assert [float(b["latents"].flatten()[0]) for b in f.reset([mk(3), mk(4), mk(5)])] == [3.0, 4.0, 5.0]
+    f.reset([mk(6)])
+    import pytest
+    with pytest.raises(RuntimeError):
+        f.reset([mk(7)])

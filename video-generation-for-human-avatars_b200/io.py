@@ -83,6 +83,16 @@ class DeviceFeeder:
         for _ in range(self.depth):
             self._stage()
 
+    def reset(self, batches: Iterable[dict]) -> "DeviceFeeder":
+        """Start over on a new source (the next epoch) with the SAME pinned and device buffers: pinning host memory is
+        a device-synchronising allocation of milliseconds, not something to repeat per epoch."""
+        if self.queue:
+            raise RuntimeError("DeviceFeeder.reset: the previous source has staged batches that were never consumed")
+        self.src = iter(batches)
+        for _ in range(self.depth):
+            self._stage()
+        return self
+
     def _buffers(self, store, slot, batch, pin):
         cur = store[slot]
         if cur is None or any(cur[k].shape != batch[k].shape for k in KEYS):
