@@ -126,6 +126,49 @@ def check_gemm_epilogues():
     # per-row gate (per-token timesteps)
     g2 = _randn(M, N, seed=10)
     _assert_close("gemm per-row gate", ops.gemm(a, b, gate=g2, rows_per_gate=1), g2.float() * base, 6e-3)
+    # every compiled variant of the slab epilogue (plain / bias / general x none, GELU, GELU', stash x bias-gate presence)
+    # on a shape ragged against every tile size, written into the middle of a sentinel-filled buffer: rows past M and
+    # columns past N must stay untouched (there is no compute-sanitizer on this pool)
+    Mr, Nr, Kr = 600, 456, 192
+    ar, br = _randn(Mr, Kr, seed=31), _randn(Nr, Kr, seed=32, scale=0.05)
+    biasr, gater, resr = _randn(Nr, seed=33), _randn(2, Nr, seed=34), _randn(Mr, Nr, seed=35)
+    baser = ar.float() @ br.float().t()
+    gfull = gater.float().repeat_interleave(300, 0)
+    hr = (baser + biasr.float()).to(BF16).float().requires_grad_(True)
+    F.gelu(hr, approximate="tanh").sum().backward()
+    variants = [
+        ("plain", {}, baser, None),
+        ("bias", dict(bias=biasr), baser + biasr.float(), None),
+        ("res", dict(res=resr), baser + resr.float(), None),
+        ("bias+gate+res", dict(bias=biasr, gate=gater, rows_per_gate=300, res=resr),
+         gfull * (baser + biasr.float()) + resr.float(), None),
+        ("gelu", dict(bias=biasr, epilogue=ops.EPI_GELU), F.gelu(hr.detach(), approximate="tanh"), hr.detach()),
+        ("gelu'", dict(epilogue=ops.EPI_GELU_GRAD, aux_in=True), baser * hr.grad, None),
+        ("stash", dict(bias=biasr, gate=gater, rows_per_gate=300, res=resr, epilogue=ops.EPI_STASH),
+         gfull * (baser + biasr.float()).to(BF16).float() + resr.float(), (baser + biasr.float())),
+    ]
+    for bn in (128, 256):
+        for name, kw, want, want_aux in variants:
+            kw = dict(kw)
+            big = torch.full((Mr + 40, Nr + 72), 7.0, device="cuda", dtype=BF16)
+            aux_big = torch.full((Mr + 40, Nr + 72), 5.0, device="cuda", dtype=BF16)
+            if kw.pop("aux_in", False):
+                aux_big[8:8 + Mr, 16:16 + Nr] = hr.detach().to(BF16)
+                kw["aux"] = aux_big[8:8 + Mr, 16:16 + Nr]
+            elif want_aux is not None:
+                kw["aux"] = aux_big[8:8 + Mr, 16:16 + Nr]
+            ops.gemm(ar, br, out=big[8:8 + Mr, 16:16 + Nr], block_n=bn, **kw)
+            _assert_close(f"gemm epilogue variant {name} bn={bn}", big[8:8 + Mr, 16:16 + Nr], want, 8e-3)
+            if want_aux is not None:
+                _assert_close(f"gemm epilogue variant {name} bn={bn} aux", aux_big[8:8 + Mr, 16:16 + Nr], want_aux, 8e-3)
+            for buf, fill in ((big, 7.0), (aux_big, 5.0)):
+                if buf is aux_big and "aux" not in kw:
+                    continue
+                if buf is aux_big and name == "gelu'":
+                    continue   # input there
+                guard = buf.clone()
+                guard[8:8 + Mr, 16:16 + Nr] = fill
+                assert bool((guard == fill).all()), f"gemm epilogue variant {name} bn={bn}: wrote outside its output"
     torch.cuda.synchronize()
 
 

@@ -14,6 +14,17 @@ x, w = r(640, 256), r(512, 256)
 ops.gemm(x, w, bias=r(512))
 ops.gemm(x, w, a2=r(640, 64), b2=r(512, 64), res=r(640, 512), gate=r(1, 512), rows_per_gate=640)
 ops.gemm(r(256, 640), r(256, 512), a_rows_are_k=True, b_rows_are_k=True, out_dtype=torch.float32, split_k=0)
+# every compiled epilogue variant of the TMA-store path, ragged M and N (block_n 128 / 256, CTA pair at M >= 512)
+xr, wr = r(600, 192), r(456, 192)
+pre = torch.empty(600, 456, device="cuda", dtype=BF16)
+for bn in (128, 256):
+    ops.gemm(xr, wr, block_n=bn)                                                     # plain
+    ops.gemm(xr, wr, bias=r(456), block_n=bn)                                        # bias only
+    ops.gemm(xr, wr, res=r(600, 456), block_n=bn)                                    # general, no bias / gate
+    ops.gemm(xr, wr, bias=r(456), gate=r(2, 456), rows_per_gate=300, res=r(600, 456), block_n=bn)
+    ops.gemm(xr, wr, bias=r(456), epilogue=ops.EPI_GELU, aux=pre, block_n=bn)
+    ops.gemm(xr, wr, epilogue=ops.EPI_GELU_GRAD, aux=pre, block_n=bn)
+    ops.gemm(xr, wr, bias=r(456), gate=r(2, 456), rows_per_gate=300, res=r(600, 456), epilogue=ops.EPI_STASH, aux=pre, block_n=bn)
 out = torch.empty(256, 3 * 256, device="cuda", dtype=BF16)
 ops.gemm_batched(r(256, 128), r(3 * 256, 128), out, 256, 256, 128, 3, {"b": (256, 0), "c": (0, 256), "bias": 256}, bias=r(768))
 # attention fwd / bwd, ragged + bias + q-split
