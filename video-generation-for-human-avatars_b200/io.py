@@ -79,6 +79,7 @@ class DeviceFeeder:
         self.released: List[bool] = [True] * self.n_slots                      # ... and said so (`_release`)
         self.users: List[Optional[torch.cuda.Stream]] = [None] * self.n_slots
         self.copied: List[Optional[torch.cuda.Event]] = [None] * self.n_slots  # the H2D copies out of pinned slot i finished
+        self.sources: List[Optional[dict]] = [None] * self.n_slots
         self.n = 0
         for _ in range(self.depth):
             self._stage()
@@ -111,9 +112,12 @@ class DeviceFeeder:
         if not self.cuda:
             self.queue.append(({k: batch[k].to(self.dtype) for k in KEYS}, None, batch.get("stem"), slot))
             return
-        host = self._buffers(self.pinned, slot, batch, True)
+        # a batch that already sits in pinned memory in the target dtype is copied from where it is (the caller keeps it
+        # unchanged until the batch has been yielded); anything else is cast into this slot's pinned staging buffers
+        direct = all(batch[k].is_pinned() and batch[k].dtype == self.dtype and batch[k].is_contiguous() for k in KEYS)
+        host = batch if direct else self._buffers(self.pinned, slot, batch, True)
         dev = self._buffers(self.slots, slot, batch, False)
-        if self.copied[slot] is not None:
+        if self.copied[slot] is not None and not direct:
             self.copied[slot].synchronize()   # the pinned slot is about to be overwritten by the host: its DMA must be done
         if not self.released[slot] and self.users[slot] is not None:
             self.users[slot].synchronize()                        # handed out and never released: wait for its reader
@@ -122,11 +126,13 @@ class DeviceFeeder:
             if self.done[slot] is not None:
                 self.copy_stream.wait_event(self.done[slot])      # the step that used this slot has finished with it
             for k in KEYS:
-                host[k].copy_(batch[k])                            # cast on the host, into pinned memory
+                if not direct:
+                    host[k].copy_(batch[k])                        # cast on the host, into pinned memory
                 dev[k].copy_(host[k], non_blocking=True)
             ready = torch.cuda.Event()
             ready.record(self.copy_stream)
         self.copied[slot] = ready
+        self.sources[slot] = batch if direct else None   # keeps a directly copied source alive while its DMA is in flight
         self.queue.append((dev, ready, batch.get("stem"), slot))
 
     def __iter__(self) -> Iterator[dict]:
