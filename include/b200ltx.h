@@ -115,6 +115,11 @@ int b200_attn_merge(float* o_acc, int64_t ldacc, float* lse_acc, const void* o_i
 /* delta[b,h,q] = sum_d o * do  (backward pre-pass). */
 int b200_attn_delta(const void* o, int64_t ldo, const void* dout, int64_t lddo, float* delta, int B,
                     int H, int Nq, void* stream);
+/* The same pass, also clearing the fp32 dQ accumulator [B*Nq, lddq] (first H*64 columns of every row) that
+ * b200_fa_bwd reduces into: one launch instead of the pre-pass plus a fill (the reference's SDPA backward,
+ * attention.py:1057, owns both inside the library). dq_zero may be NULL. */
+int b200_attn_delta_zero(const void* o, int64_t ldo, const void* dout, int64_t lddo, float* delta,
+                         float* dq_zero, int64_t lddq, int B, int H, int Nq, void* stream);
 
 /* Flash attention backward.  dq_accum is fp32 [B*Nq, lddq] and MUST be zeroed by the caller (key-tile
  * CTAs reduce into it with TMA reduce-add); dk/dv are bf16.  With few key tiles (attn2: 256 caption

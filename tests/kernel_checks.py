@@ -458,8 +458,12 @@ def check_key_sharded_merge():
         _assert_close("merged o " + tag, out, oref, 8e-3)
         _assert_close("merged o (fp32 acc) " + tag, o_acc, oref, 8e-3)
         _assert_close("merged lse " + tag, lse_acc, lref, 1e-3)
-        delta = ops.attn_delta(out, do, B, H, Nq)
-        dq = torch.zeros(B * Nq, D, device="cuda")
+        # the pre-pass clears the dQ accumulator on its way (a pitched buffer: the columns beside it stay untouched)
+        wide = torch.full((B * Nq, D + 8), 3.0, device="cuda")
+        dq = wide[:, :D]
+        delta = ops.attn_delta(out, do, B, H, Nq, zero=dq)
+        assert float(dq.abs().max()) == 0.0 and bool((wide[:, D:] == 3.0).all()), "attn_delta zeroing " + tag
+        assert torch.equal(delta, ops.attn_delta(out, do, B, H, Nq)), "attn_delta with / without zeroing " + tag
         dks, dvs = [], []
         for i in range(shards):
             dk, dv = torch.empty_like(ks[i]), torch.empty_like(vs[i])

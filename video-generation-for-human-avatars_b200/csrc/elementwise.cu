@@ -807,8 +807,8 @@ __global__ void __launch_bounds__(256) colsum_groups_part_kernel(const bf16* __r
 // takes the same (head, slice) of two rows half the tensor apart, so four 16-byte loads are in flight per thread)
 __global__ void __launch_bounds__(256) attn_delta_kernel(const bf16* __restrict__ o, int64_t ldo,
                                                          const bf16* __restrict__ dout, int64_t lddo,
-                                                         float* __restrict__ delta, int B, int H,
-                                                         int Nq) {
+                                                         float* __restrict__ delta, float* __restrict__ dq_zero,
+                                                         int64_t lddq, int B, int H, int Nq) {
   pdl_launch();
   pdl_wait();
   const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -826,6 +826,19 @@ __global__ void __launch_bounds__(256) attn_delta_kernel(const bf16* __restrict_
   if (ok1) {
     a1 = *reinterpret_cast<const uint4*>(o + r1 * ldo + h * 64 + sub * 8);
     b1 = *reinterpret_cast<const uint4*>(dout + r1 * lddo + h * 64 + sub * 8);
+  }
+  if (dq_zero != nullptr) {
+    // the fp32 dQ accumulator the attention backward reduce-adds into starts at zero: cleared here, on the same
+    // (row, head, slice) walk, instead of by a separate fill launch per layer
+    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (ok0) {
+      float4* d = reinterpret_cast<float4*>(dq_zero + r0 * lddq + h * 64 + sub * 8);
+      d[0] = z; d[1] = z;
+    }
+    if (ok1) {
+      float4* d = reinterpret_cast<float4*>(dq_zero + r1 * lddq + h * 64 + sub * 8);
+      d[0] = z; d[1] = z;
+    }
   }
   const Row8 x0 = unpack8(a0), y0 = unpack8(b0), x1 = unpack8(a1), y1 = unpack8(b1);
   float acc0 = 0.f, acc1 = 0.f;
@@ -1119,14 +1132,24 @@ extern "C" int b200_attn_merge(float* o_acc, int64_t ldacc, float* lse_acc, cons
   return launch_status("attn_merge");
 }
 
+extern "C" int b200_attn_delta_zero(const void* o, int64_t ldo, const void* dout, int64_t lddo, float* delta,
+                                    float* dq_zero, int64_t lddq, int B, int H, int Nq, void* stream);
+
 extern "C" int b200_attn_delta(const void* o, int64_t ldo, const void* dout, int64_t lddo,
                                float* delta, int B, int H, int Nq, void* stream) {
+  return b200_attn_delta_zero(o, ldo, dout, lddo, delta, nullptr, 0, B, H, Nq, stream);
+}
+
+extern "C" int b200_attn_delta_zero(const void* o, int64_t ldo, const void* dout, int64_t lddo, float* delta,
+                                    float* dq_zero, int64_t lddq, int B, int H, int Nq, void* stream) {
   CHECK_ARG(o && dout && delta && B >= 0 && H > 0 && Nq >= 0, "attn_delta: bad arguments");
   CHECK_ARG(ldo % 8 == 0 && lddo % 8 == 0 && aligned16(o) && aligned16(dout),
             "attn_delta: 16-byte alignment required");
+  CHECK_ARG(dq_zero == nullptr || (lddq % 4 == 0 && lddq >= (int64_t)H * 64 && aligned16(dq_zero)),
+            "attn_delta: the dQ accumulator must be 16-byte aligned with a pitch >= H * 64");
   int64_t threads = (((int64_t)B * Nq + 1) / 2) * H * 8;  // one thread per (row pair, head, 8-element slice)
   if (threads == 0) return 0;
   B200_LAUNCH(attn_delta_kernel, (unsigned)((threads + 255) / 256), 256, 0, (cudaStream_t)stream, 
-      (const bf16*)o, ldo, (const bf16*)dout, lddo, delta, B, H, Nq);
+      (const bf16*)o, ldo, (const bf16*)dout, lddo, delta, dq_zero, lddq, B, H, Nq);
   return launch_status("attn_delta");
 }

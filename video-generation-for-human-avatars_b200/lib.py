@@ -27,6 +27,7 @@ PROTOTYPES = {
     "b200_fa_fwd_ws": (I, [P, L, P, L, P, L, P, L, P, P, P, P, L, I, I, I, I, I, F, P, L, P]),
     "b200_attn_merge": (I, [P, L, P, P, L, P, P, L, I, I, I, I, P]),
     "b200_attn_delta": (I, [P, L, P, L, P, I, I, I, P]),
+    "b200_attn_delta_zero": (I, [P, L, P, L, P, P, L, I, I, I, P]),
     "b200_fa_bwd_workspace_bytes": (L, [I, I, I, I]),
     "b200_fa_bwd": (I, [P, L, P, L, P, L, P, L, P, P, P, P, L, P, L, P, L, I, I, I, I, I, F, P, L, P]),
     "b200_norm_mod_fwd": (I, [P, L, P, L, P, P, L, L, I, L, F, I, P]),

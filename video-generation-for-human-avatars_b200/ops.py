@@ -301,9 +301,14 @@ def fa_fwd(q, k, v, B, H, Nq, Nk, key_bias=None, scale=0.125, need_lse=True, att
     return o, lse
 
 
-def attn_delta(o, do, B, H, Nq):
+def attn_delta(o, do, B, H, Nq, zero=None):
+    """delta [B, H, Nq] fp32; `zero` (fp32 [B*Nq, >= H*64]): the dQ accumulator of the backward, cleared in the same pass."""
     delta = torch.empty((B, H, Nq), device=o.device, dtype=torch.float32)
-    _call("attn_delta", 4.0 * B * Nq * H * 64, "byte", _L().b200_attn_delta, _p(o), o.stride(0), _p(do), do.stride(0), _p(delta), B, H, Nq, _s())
+    if zero is not None and (zero.dtype != torch.float32 or zero.stride(1) != 1 or zero.shape[0] != B * Nq):
+        raise _lib.B200Error("attn_delta: the accumulator to clear must be fp32 [B*Nq, >= H*64], unit column stride")
+    _call("attn_delta", (4.0 + (4.0 if zero is not None else 0.0)) * B * Nq * H * 64, "byte", _L().b200_attn_delta_zero,
+          _p(o), o.stride(0), _p(do), do.stride(0), _p(delta), _p(zero), zero.stride(0) if zero is not None else 0,
+          B, H, Nq, _s())
     return delta
 
 
@@ -319,9 +324,15 @@ def fa_bwd(q, k, v, o, do, lse, B, H, Nq, Nk, dk, dv, key_bias=None, scale=0.125
     """Returns dq as fp32 [B*Nq, H*64]; writes bf16 dk/dv into the given (possibly strided) views.
     `delta` / `dq_accum` may be supplied to accumulate dq over several key shards (ring attention)."""
     _chk2d(do, "fa_bwd do")
+    dq = dq_accum
     if delta is None:
-        delta = attn_delta(o, do, B, H, Nq)
-    dq = dq_accum if dq_accum is not None else torch.zeros((B * Nq, H * 64), device=q.device, dtype=torch.float32)
+        if dq is None:   # the pre-pass clears the accumulator on its way: no separate fill launch
+            dq = torch.empty((B * Nq, H * 64), device=q.device, dtype=torch.float32)
+            delta = attn_delta(o, do, B, H, Nq, zero=dq)
+        else:
+            delta = attn_delta(o, do, B, H, Nq)
+    elif dq is None:
+        dq = torch.zeros((B * Nq, H * 64), device=q.device, dtype=torch.float32)
     ws_bytes = _L().b200_fa_bwd_workspace_bytes(B, H, Nq, Nk)
     ws = torch.empty(ws_bytes, device=q.device, dtype=torch.uint8) if ws_bytes else None
     _call(_fa_family("fa_bwd", Nq, Nk, key_bias, attn1), 8.0 * B * H * Nq * Nk * 64, "flop", _L().b200_fa_bwd,
