@@ -15,13 +15,17 @@ w = (torch.randn(N, K, device="cuda") * 0.05).bfloat16()
 bias = None if "nobias" in sys.argv else torch.zeros(N, device="cuda", dtype=torch.bfloat16)
 hot = "hot" in sys.argv   # do not flush L2 before the traced launch
 flush = torch.empty(256 << 20, device="cuda", dtype=torch.uint8)
+kw = dict(bias=bias)
+if "gateres" in sys.argv:   # the out-projection epilogue: gate * (acc + bias) + residual
+    kw.update(gate=(torch.randn(1, N, device="cuda") * 0.1).bfloat16(), rows_per_gate=M,
+              res=(torch.randn(M, N, device="cuda") * 0.1).bfloat16())
 for _ in range(3):
-    ops.gemm(a, w, bias=bias)
+    ops.gemm(a, w, **kw)
 if not hot:
     flush.zero_()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 torch.cuda.synchronize()
-e0.record(); ops.gemm(a, w, bias=bias); e1.record()
+e0.record(); ops.gemm(a, w, **kw); e1.record()
 torch.cuda.synchronize()
 L = lib.load()
 buf = (ctypes.c_ulonglong * (160 * 32))()
