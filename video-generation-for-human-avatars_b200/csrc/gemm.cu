@@ -486,17 +486,48 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             // (A coalesced read -- quarter-warp per row, transposed through the staging buffer -- measured the same:
             // 49.2 vs 49.5 us at N = K = 2048, 164.2 vs 164.2 us for GELU'; the loads are not what these epilogues wait for.)
             uint4 ext[8];
+            const bf16* ext_base = nullptr;
             if constexpr (MODE == 2) {
-              const bf16* ext_row = EPI == EPI_GELU_GRAD ? aux_row : res_row;
+              // Coalesced: a quarter-warp per row, four rows (four full 128-byte lines) per request, eight requests in
+              // flight; thread-per-row loads of the same 4 KB were 32 lines per request and 1.2-1.7 us per slab of LSU
+              // issue time (tools/gemm_trace.py).  The slab then passes through the staging buffer to the
+              // thread-per-row layout of the accumulator.
+              ext_base = EPI == EPI_GELU_GRAD ? p.aux : p.res;
+              const int64_t ext_ld = EPI == EPI_GELU_GRAD ? p.ldaux : p.ldres;
+              if (ext_base != nullptr) {
+                const int er = lane >> 3, ec = lane & 7;
 #pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                ext[j] = make_uint4(0, 0, 0, 0);
-                if (ext_row != nullptr && row_ok && n_slab + j * 8 < p.N)
-                  ext[j] = *reinterpret_cast<const uint4*>(ext_row + n_slab + j * 8);
+                for (int j = 0; j < 8; ++j) {
+                  const int64_t rr = (int64_t)row0 + j * 4 + er;
+                  ext[j] = make_uint4(0, 0, 0, 0);
+                  if (rr < p.M && n_slab + ec * 8 < p.N)
+                    ext[j] = *reinterpret_cast<const uint4*>(ext_base + rr * ext_ld + n_slab + ec * 8);
+                }
+              } else {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) ext[j] = make_uint4(0, 0, 0, 0);
               }
             }
             if (lane == 0) tma_store_wait_read<0>();  // the previous slab has left the staging buffer
             __syncwarp();
+            if constexpr (MODE == 2) {
+              if (ext_base != nullptr) {
+                const int er = lane >> 3, ec = lane & 7;
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stg + sw128_off(j * 4 + er, ec)),
+                               "r"(ext[j].x), "r"(ext[j].y), "r"(ext[j].z), "r"(ext[j].w)
+                               : "memory");
+                __syncwarp();
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                               : "=r"(ext[j].x), "=r"(ext[j].y), "=r"(ext[j].z), "=r"(ext[j].w)
+                               : "r"(stg + sw128_off(lane, j))
+                               : "memory");
+                __syncwarp();   // every lane holds its row before any lane overwrites the slab with outputs
+              }
+            }
             if (warp == 4 && lane == 0) GTRACE(c == 0 ? 8 : 12);
 #pragma unroll
             for (int hc = 0; hc < 2; ++hc) {
