@@ -147,10 +147,19 @@ template <int EPI>
 __device__ __forceinline__ void epi_math8(float (&v)[8], uint4& pre, const GemmParams& p, bool has_bias,
                                           const uint4& bias_u, bool has_gate, const uint4& gate_u, bool has_res,
                                           const uint4& ext) {
+  // packed fp32x2 adds / multiplies (one instruction per PAIR of columns): the slab loop is issue bound
+  auto pair = [](uint32_t w) { return make_float2(bf16_lo(w), bf16_hi(w)); };
+  auto add2 = [&](int i, uint32_t w) {
+    const float2 r = __fadd2_rn(make_float2(v[i], v[i + 1]), pair(w));
+    v[i] = r.x; v[i + 1] = r.y;
+  };
+  auto mul2 = [&](int i, uint32_t w) {
+    const float2 r = __fmul2_rn(make_float2(v[i], v[i + 1]), pair(w));
+    v[i] = r.x; v[i + 1] = r.y;
+  };
   if (has_bias) {
     const uint4 u = bias_u;
-    v[0] += bf16_lo(u.x); v[1] += bf16_hi(u.x); v[2] += bf16_lo(u.y); v[3] += bf16_hi(u.y);
-    v[4] += bf16_lo(u.z); v[5] += bf16_hi(u.z); v[6] += bf16_lo(u.w); v[7] += bf16_hi(u.w);
+    add2(0, u.x); add2(2, u.y); add2(4, u.z); add2(6, u.w);
   }
   if (EPI == EPI_GELU) {
     if (p.aux) {
@@ -176,13 +185,11 @@ __device__ __forceinline__ void epi_math8(float (&v)[8], uint4& pre, const GemmP
   }
   if (has_gate) {
     const uint4 u = gate_u;
-    v[0] *= bf16_lo(u.x); v[1] *= bf16_hi(u.x); v[2] *= bf16_lo(u.y); v[3] *= bf16_hi(u.y);
-    v[4] *= bf16_lo(u.z); v[5] *= bf16_hi(u.z); v[6] *= bf16_lo(u.w); v[7] *= bf16_hi(u.w);
+    mul2(0, u.x); mul2(2, u.y); mul2(4, u.z); mul2(6, u.w);
   }
   if (has_res) {
     const uint4 u = ext;
-    v[0] += bf16_lo(u.x); v[1] += bf16_hi(u.x); v[2] += bf16_lo(u.y); v[3] += bf16_hi(u.y);
-    v[4] += bf16_lo(u.z); v[5] += bf16_hi(u.z); v[6] += bf16_lo(u.w); v[7] += bf16_hi(u.w);
+    add2(0, u.x); add2(2, u.y); add2(4, u.z); add2(6, u.w);
   }
 }
 
@@ -577,9 +584,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                                    p.res != nullptr, ext[hc * 4 + g]);
                   prer[hc * 4 + g] = pre;
                 } else if constexpr (MODE == 1) {   // columns past N get the zero bias loaded above and are clipped by the TMA
-                  const uint4 bu = bq[g];
-                  v[0] += bf16_lo(bu.x); v[1] += bf16_hi(bu.x); v[2] += bf16_lo(bu.y); v[3] += bf16_hi(bu.y);
-                  v[4] += bf16_lo(bu.z); v[5] += bf16_hi(bu.z); v[6] += bf16_lo(bu.w); v[7] += bf16_hi(bu.w);
+                  const uint32_t bw[4] = {bq[g].x, bq[g].y, bq[g].z, bq[g].w};
+#pragma unroll
+                  for (int i = 0; i < 4; ++i) {   // packed fp32x2: one add per pair of columns
+                    const float2 r2 = __fadd2_rn(make_float2(v[2 * i], v[2 * i + 1]), make_float2(bf16_lo(bw[i]), bf16_hi(bw[i])));
+                    v[2 * i] = r2.x; v[2 * i + 1] = r2.y;
+                  }
                 }
                 u.x = pack_bf16x2(v[0], v[1]); u.y = pack_bf16x2(v[2], v[3]);
                 u.z = pack_bf16x2(v[4], v[5]); u.w = pack_bf16x2(v[6], v[7]);
