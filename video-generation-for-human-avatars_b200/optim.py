@@ -14,7 +14,9 @@ shard_group=group)` deals the parameter tensors out to the ranks of `group` (lar
 keeps `exp_avg` / `exp_avg_sq` only for the tensors a rank owns, updates those with the one launch, and broadcasts every
 updated tensor from its owner (one NCCL broadcast per tensor: launch cost only matters eagerly -- under
 train.GraphedTrainStep they are captured with the step).  Gradients are expected to be already averaged over the group
-(dp.GradBucketer): every rank then applies the identical update a replicated optimizer would."""
+(dp.GradBucketer): every rank then applies the identical update a replicated optimizer would.  `state_dict()` of a sharded
+optimizer holds the moments of the tensors THIS rank owns (a checkpoint is one file per rank, as with ZeRO); parameters
+themselves are identical on every rank after each step."""
 import struct
 from typing import List
 
