@@ -48,3 +48,15 @@ tot = sum(r[1] for r in kern)
 print(f"total device kernel time {tot / 1e3:.2f} ms over {sum(r[2] for r in kern)} launches")
 for k, t, c in sorted(kern, key=lambda r: -r[1])[:40]:
     print(f"{t / 1e3:8.3f} ms {100 * t / tot:5.1f}%  n={c:4d}  avg {t / c:8.1f} us  {k[:110]}")
+
+# which aten ops (with input shapes) launch the torch-side copy / fill / add kernels
+if os.environ.get("B200_PROF_OPS"):
+    with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU], record_shapes=True) as prof2:
+        step()
+        torch.cuda.synchronize()
+    print("\naten ops with device time, grouped by input shapes:")
+    ops_rows = [e for e in prof2.key_averages(group_by_input_shape=True) if e.key.startswith("aten::")
+                and (getattr(e, "self_device_time_total", 0) or getattr(e, "self_cuda_time_total", 0)) > 0]
+    for e in sorted(ops_rows, key=lambda e: -(getattr(e, "self_device_time_total", 0) or getattr(e, "self_cuda_time_total", 0)))[:40]:
+        t = getattr(e, "self_device_time_total", 0) or getattr(e, "self_cuda_time_total", 0)
+        print(f"{t / 1e3:8.3f} ms  n={e.count:4d}  {e.key:28s} {str(e.input_shapes)[:150]}")
