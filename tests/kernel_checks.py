@@ -175,24 +175,29 @@ def check_gemm_epilogues():
 def check_linear_fn():
     """LinearFn / FeedForwardFn forward + backward vs autograd on the same math in fp32."""
     from b200_ltx import ops
-    M, K, N, r, s = 320, 256, 512, 32, 0.5
-    x = _randn(M, K, seed=1).requires_grad_(True)
-    W = _randn(N, K, seed=2, scale=0.06).requires_grad_(True)
-    b = _randn(N, seed=3, scale=0.1).requires_grad_(True)
-    A = (_randn(r, K, seed=4, scale=0.06).float()).requires_grad_(True)
-    B = (_randn(N, r, seed=5, scale=0.06).float()).requires_grad_(True)
-    gate = _randn(2, N, seed=6)
-    res = _randn(M, N, seed=7).requires_grad_(True)
-    dy = _randn(M, N, seed=8)
-    y = ops.LinearFn.apply(x, W, b, A, B, s, gate, 160, res)
-    y.backward(dy)
-    xr, Wr, br, Ar, Br, rr = [t.detach().float().requires_grad_(True) for t in (x, W, b, A, B, res)]
-    yr = gate.float().repeat_interleave(160, 0) * (xr @ Wr.t() + br + s * (xr @ Ar.t()) @ Br.t()) + rr
-    yr.backward(dy.float())
-    _assert_close("LinearFn y", y, yr, 8e-3)
-    for nm, g, gr in (("dx", x.grad, xr.grad), ("dW", W.grad, Wr.grad), ("db", b.grad, br.grad),
-                      ("dA", A.grad, Ar.grad), ("dB", B.grad, Br.grad), ("dres", res.grad, rr.grad)):
-        _assert_close("LinearFn " + nm, g, gr, 1.5e-2)
+    # LoRA ranks: the train config's 32, the config default 8 (config.py:22), 12 (not a multiple of 8: padded GEMM
+    # extents, sliced gradients) and 96 (more than one 64-wide k block)
+    for r in (32, 8, 12, 96):
+        M, K, N, s = 320, 256, 512, 0.5
+        x = _randn(M, K, seed=1).requires_grad_(True)
+        W = _randn(N, K, seed=2, scale=0.06).requires_grad_(True)
+        b = _randn(N, seed=3, scale=0.1).requires_grad_(True)
+        A = (_randn(r, K, seed=4, scale=0.06).float()).requires_grad_(True)
+        B = (_randn(N, r, seed=5, scale=0.06).float()).requires_grad_(True)
+        gate = _randn(2, N, seed=6)
+        res = _randn(M, N, seed=7).requires_grad_(True)
+        dy = _randn(M, N, seed=8)
+        y = ops.LinearFn.apply(x, W, b, A, B, s, gate, 160, res)
+        y.backward(dy)
+        xr, Wr, br, Ar, Br, rr = [t.detach().float().requires_grad_(True) for t in (x, W, b, A, B, res)]
+        yr = gate.float().repeat_interleave(160, 0) * (xr @ Wr.t() + br + s * (xr @ Ar.t()) @ Br.t()) + rr
+        yr.backward(dy.float())
+        _assert_close(f"LinearFn r={r} y", y, yr, 8e-3)
+        assert A.grad.shape == A.shape and B.grad.shape == B.shape
+        for nm, g, gr in (("dx", x.grad, xr.grad), ("dW", W.grad, Wr.grad), ("db", b.grad, br.grad),
+                          ("dA", A.grad, Ar.grad), ("dB", B.grad, Br.grad), ("dres", res.grad, rr.grad)):
+            _assert_close(f"LinearFn r={r} " + nm, g, gr, 1.5e-2)
+    M, K = 320, 256
     # feed-forward
     Dff = 1024
     W1 = _randn(Dff, K, seed=11, scale=0.06).requires_grad_(True)

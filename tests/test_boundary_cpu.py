@@ -62,7 +62,7 @@ def _run(model, inp, **kw):
     return out, x["hidden_states"]
 
 
-@pytest.mark.parametrize("lora_rank", [0, 32])
+@pytest.mark.parametrize("lora_rank", [0, 32, 12, 96])
 def test_install_on_reference_model_matches_reference_forward(lora_rank):
     from b200_ltx import api, modules
     ns, cfg, model = _reference_model(lora_rank)

@@ -46,11 +46,14 @@ def test_cfg2_token_count_full_width_two_blocks():
 
 
 @pytest.mark.gpu
-def test_batched_caption_kv_path():
+@pytest.mark.parametrize("lora_rank", [32, 8, 12, 96])
+def test_batched_caption_kv_path(lora_rank):
     """(B * caption tokens) % 128 == 0 and D % 256 == 0: the attn2 keys / values of all blocks come from one
-    strided-batched projection (ops.CtxKVFn) -- 3 blocks, 2 x 64 caption tokens with 40 valid, ragged latents."""
+    strided-batched projection (ops.CtxKVFn) -- 3 blocks, 2 x 64 caption tokens with 40 valid, ragged latents.
+    `config.lora_rank` is free (config.py:22 defaults to 8, train-avatars.yaml:36 sets 32): also a rank that is not a
+    multiple of 8 and one wider than a 64-wide k block, through the whole train step."""
     cfg = dict(rb.LTXV_2B, num_layers=3, num_attention_heads=4, cross_attention_dim=256, caption_channels=64)
-    case = dict(b=2, f=3, h=5, w=7, n_ctx=64, valid_ctx=40, lora_rank=32, seed_w=4, seed_x=11, t=[0.3, 0.8])
+    case = dict(b=2, f=3, h=5, w=7, n_ctx=64, valid_ctx=40, lora_rank=lora_rank, seed_w=4, seed_x=11, t=[0.3, 0.8])
     from b200_ltx import ops
     before = ops.launch_count
     mc.run_parity(cfg, case)
@@ -218,13 +221,14 @@ def test_graphed_train_step_learns_and_matches_eager_shapes(optimizer):
 
 
 @pytest.mark.gpu
-def test_lora_merge_matches_matmul():
+@pytest.mark.parametrize("rank", [32, 12])
+def test_lora_merge_matches_matmul(rank):
     """LoraLinear.merge on the device (one rank-r GEMM accumulating into the bf16 weight in place) against the fp32
     matmul of peft's merge_and_unload (torch_utils.py:66-102)."""
     from b200_ltx import lora
     torch.manual_seed(0)
     base = torch.nn.Linear(2048, 2048, device="cuda", dtype=torch.bfloat16)
-    layer = lora.LoraLinear(base, 32, 64)
+    layer = lora.LoraLinear(base, rank, 2 * rank)
     layer.lora_B["default"].weight.data.normal_(0, 0.02)
     w0 = base.weight.detach().float().clone()
     want = w0 + 2.0 * (layer.lora_B["default"].weight.float() @ layer.lora_A["default"].weight.float())

@@ -15,8 +15,45 @@ def _mat(t, rows_are_k):
     return t.float().t() if rows_are_k else t.float()
 
 
+def _contract(ok, what):
+    if not ok:
+        raise AssertionError("b200_gemm_bf16 would reject this call (csrc/gemm.cu gemm_impl): " + what)
+
+
+def _aligned(t):
+    return t is None or (t.storage_offset() * t.element_size()) % 16 == 0
+
+
+def _gemm_contract(a, b, a_mn, b_mn, a2, b2, out, out_dtype, bias, gate, res, aux, groups_block=None):
+    """The argument contract of the C ABI (gemm.cu: gemm_impl), so that host code which would be refused on the device
+    fails here too: contiguous extents in multiples of 8 elements, 16-byte aligned pointers and pitches."""
+    M, K = (a.shape[1], a.shape[0]) if a_mn else a.shape
+    N = b.shape[1] if b_mn else b.shape[0]
+    K2 = 0 if a2 is None else (a2.shape[0] if a_mn else a2.shape[1])
+    if M == 0 or N == 0:
+        return
+    _contract(N % 8 == 0, f"N = {N} is not a multiple of 8")
+    if not a_mn or not b_mn:
+        _contract(K % 8 == 0 and K2 % 8 == 0, f"K = {K} / K2 = {K2} must be multiples of 8 for a K-major operand")
+    if a_mn:
+        _contract(M % 8 == 0, f"M = {M} must be a multiple of 8 for a [K, M] A operand")
+    f32 = (out.dtype if out is not None else out_dtype) == torch.float32
+    for t, nm in ((a, "A"), (b, "B"), (a2, "A2"), (b2, "B2"), (res, "res"), (aux, "aux"), (gate, "gate")):
+        if t is not None:
+            _contract(t.stride(1) == 1 and t.stride(0) % 8 == 0 and _aligned(t), f"{nm}: pitch {t.stride()} / alignment")
+    if out is not None:
+        _contract(out.stride(1) == 1 and out.stride(0) % (4 if f32 else 8) == 0 and _aligned(out), "C: pitch / alignment")
+    _contract(_aligned(bias), "bias alignment")
+    if groups_block is not None:
+        bn, Mg, Ng, Kg, K2g = groups_block
+        _contract(Mg % 128 == 0 and Ng % bn == 0 and Kg % 64 == 0 and K2g % 64 == 0,
+                  f"batched: per-group M, N, K, K2 = {Mg}, {Ng}, {Kg}, {K2g} vs 128, {bn}, 64, 64")
+
+
 def gemm(a, b, *, a_rows_are_k=False, b_rows_are_k=False, a2=None, b2=None, out=None, out_dtype=BF16, bias=None,
-         gate=None, rows_per_gate=0, res=None, aux=None, epilogue=0, block_n=0, split_k=1):
+         gate=None, rows_per_gate=0, res=None, aux=None, epilogue=0, block_n=0, split_k=1, _checked=False):
+    if not _checked:
+        _gemm_contract(a, b, a_rows_are_k, b_rows_are_k, a2, b2, out, out_dtype, bias, gate, res, aux)
     acc = _mat(a, a_rows_are_k) @ _mat(b, b_rows_are_k).t()
     if a2 is not None:
         acc = acc + _mat(a2, a_rows_are_k) @ _mat(b2, b_rows_are_k).t()
@@ -44,6 +81,8 @@ def gemm(a, b, *, a_rows_are_k=False, b_rows_are_k=False, a2=None, b2=None, out=
 def gemm_batched(a, b, out, M, N, K, groups, offs, *, a_rows_are_k=False, b_rows_are_k=False, a2=None, b2=None, K2=0,
                  bias=None, block_n=0):
     z = (0, 0)
+    bn = block_n or (256 if N >= 256 and N % 256 == 0 else (128 if N % 128 == 0 else 64))
+    _gemm_contract(a, b, a_rows_are_k, b_rows_are_k, a2, b2, out, out.dtype, bias, None, None, None, (bn, M, N, K, K2))
 
     def sub(t, name, rows, cols, g):
         r0, c0 = offs.get(name, z)
@@ -60,7 +99,7 @@ def gemm_batched(a, b, out, M, N, K, groups, offs, *, a_rows_are_k=False, b_rows
             o = offs.get("bias", 0)
             bs = bias[g * o:g * o + N]
         gemm(ag, bg, a_rows_are_k=a_rows_are_k, b_rows_are_k=b_rows_are_k, a2=a2g, b2=b2g, bias=bs,
-             out=sub(out, "c", M, N, g))
+             out=sub(out, "c", M, N, g), _checked=True)
     return out
 
 

@@ -65,8 +65,13 @@ class LoraLinear(nn.Module):
         A, B, s = self.lora_A["default"].weight, self.lora_B["default"].weight, self.scaling["default"]
         if w.is_cuda and w.dtype == torch.bfloat16:
             from . import ops
-            ops.gemm((B.detach().float() * s).to(torch.bfloat16).contiguous(), A.detach().to(torch.bfloat16).contiguous(),
-                     b_rows_are_k=True, res=w.data, out=w.data)
+            a = (B.detach().float() * s).to(torch.bfloat16)
+            b = A.detach().to(torch.bfloat16)
+            if a.shape[1] % 8:   # the reduction extent of a GEMM is a multiple of 8: zero-pad the rank
+                pad = 8 - a.shape[1] % 8
+                a = torch.nn.functional.pad(a, (0, pad))
+                b = torch.nn.functional.pad(b, (0, 0, 0, pad))
+            ops.gemm(a.contiguous(), b.contiguous(), b_rows_are_k=True, res=w.data, out=w.data)
             # the kernel wrote through the raw pointer: move the version counter so that every cache keyed on it
             # (modules._cached_wqkv / _batched_ctx_kv) sees a new weight
             torch.autograd.graph.increment_version(w)

@@ -157,7 +157,7 @@ def _batched_ctx_kv(model, ctx):
     adapters = ()
     if has_lora:
         r, scaling = parts[0][2][0].shape[0], parts[0][2][2]
-        if any(lo[0].shape[0] != r or lo[2] != scaling for _, _, lo in parts) or r > ops.LORA_PAD:
+        if any(lo[0].shape[0] != r or lo[2] != scaling for _, _, lo in parts):
             return []
         adapters = tuple(lo[0] for _, _, lo in parts) + tuple(lo[1] for _, _, lo in parts)
     key = _weights_key(parts)

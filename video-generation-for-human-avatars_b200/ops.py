@@ -10,7 +10,16 @@ import torch
 from . import lib as _lib
 
 EPI_NONE, EPI_GELU, EPI_GELU_GRAD, EPI_STASH = 0, 1, 2, 3
-LORA_PAD = 64  # LoRA rank is zero-padded to one 64-wide k-block of the GEMM
+LORA_PAD = 64  # LoRA ranks are zero-padded to whole 64-wide k-blocks of the GEMM
+
+
+def lora_pad(r: int) -> int:
+    """Padded rank: the adapters enter the GEMMs as whole 64-wide k blocks (config.lora_rank is free, config.py:22)."""
+    if r < 1:
+        raise _lib.B200Error(f"LoRA rank {r}")
+    return (r + LORA_PAD - 1) // LORA_PAD * LORA_PAD
+
+
 BF16 = torch.bfloat16
 
 # counts kernels launched through the C ABI (bench.py reports it as gpu_launches)
@@ -441,7 +450,7 @@ def prestage_lora(adapters) -> None:
     """Stage all LoRA adapters of a model with a handful of launches instead of ~5 per adapter.
 
     `adapters`: list of (A [r,K] fp32, B [N,r] fp32, scaling).  Adapters of equal shape are stacked,
-    cast to bf16 and zero-padded to rank 64 together; LinearFn.forward picks its views from the cache."""
+    cast to bf16 and zero-padded to a multiple of 64 together; LinearFn.forward picks its views from the cache."""
     _lora_stage_cache.clear()
     groups = {}
     for A, B, s in adapters:
@@ -449,11 +458,10 @@ def prestage_lora(adapters) -> None:
     for (ashape, bshape, dev), items in groups.items():
         r, K = ashape
         N = bshape[0]
-        if r > LORA_PAD:
-            raise _lib.B200Error(f"LoRA rank {r} > {LORA_PAD} is not built")
+        pad = lora_pad(r)
         n = len(items)
-        a_all = torch.zeros((n, LORA_PAD, K), device=dev, dtype=BF16)
-        b_all = torch.zeros((n, N, LORA_PAD), device=dev, dtype=BF16)
+        a_all = torch.zeros((n, pad, K), device=dev, dtype=BF16)
+        b_all = torch.zeros((n, N, pad), device=dev, dtype=BF16)
         a_all[:, :r] = torch.stack([A.detach() for A, _, _ in items])
         bs = torch.stack([B.detach() for _, B, _ in items])
         scal = [float(s) for _, _, s in items]
@@ -471,16 +479,15 @@ def clear_lora_stage() -> None:
 
 
 def stage_lora(A: torch.Tensor, B: torch.Tensor, scaling: float) -> Tuple[torch.Tensor, torch.Tensor]:
-    """A [r, K] -> A_pad [64, K] ; B [N, r] -> (scaling * B)_pad [N, 64], both bf16."""
+    """A [r, K] -> A_pad [pad, K] ; B [N, r] -> (scaling * B)_pad [N, pad], both bf16, pad = lora_pad(r)."""
     hit = _lora_stage_cache.get(id(A))
     if hit is not None and hit[2] == A._version:
         return hit[0], hit[1]
     r = A.shape[0]
-    if r > LORA_PAD:
-        raise _lib.B200Error(f"LoRA rank {r} > {LORA_PAD} is not built")
-    a_pad = torch.zeros((LORA_PAD, A.shape[1]), device=A.device, dtype=BF16)
+    pad = lora_pad(r)
+    a_pad = torch.zeros((pad, A.shape[1]), device=A.device, dtype=BF16)
     a_pad[:r] = A.detach()
-    b_pad = torch.zeros((B.shape[0], LORA_PAD), device=B.device, dtype=BF16)
+    b_pad = torch.zeros((B.shape[0], pad), device=B.device, dtype=BF16)
     b_pad[:, :r] = B.detach() * scaling
     return a_pad, b_pad
 
@@ -592,7 +599,9 @@ class LinearFn(torch.autograd.Function):
                 extra, join.grad = join.grad, None      # the residual branch's gradient of x, parked by the sender
             dx = gemm(g, W, b_rows_are_k=True, a2=dt, b2=a_pad if has_lora else None, res=extra)
         # the rank-r column views make the GEMMs write exactly [r, K] / [N, r] tensors: autograd can take them as
-        # .grad without the copy it makes for a slice of a padded buffer
+        # .grad without the copy it makes for a slice of a padded buffer.  (A rank that is not a multiple of 8 cannot be
+        # a GEMM extent: the next multiple is computed -- the extra rows / columns come out zero -- and sliced.)
+        rr = r if r % 8 == 0 else (r + 7) // 8 * 8
         if has_lora and (need[3] or need[4]):
             # The side stream is only safe when AccumulateGrad takes the returned tensors as `.grad` without touching
             # them (it then launches nothing): with an existing `.grad` (accumulation, bucket views) autograd adds on
@@ -601,11 +610,13 @@ class LinearFn(torch.autograd.Function):
             steal = (pA is None or pA.grad is None) and (pB is None or pB.grad is None)
             with _OnSideStream(g, dt, x, t, enabled=steal):   # only the optimizer reads these: off the critical path
                 if need[3]:
-                    dA = gemm(dt[:, :r], x, a_rows_are_k=True, b_rows_are_k=True, out_dtype=torch.float32, split_k=0)
+                    dA = gemm(dt[:, :rr], x, a_rows_are_k=True, b_rows_are_k=True, out_dtype=torch.float32, split_k=0)
+                    dA = dA if rr == r else dA[:r]
                 if need[4]:
-                    dB = gemm(g, t[:, :r], a_rows_are_k=True, b_rows_are_k=True, out_dtype=torch.float32, block_n=64,
+                    dB = gemm(g, t[:, :rr], a_rows_are_k=True, b_rows_are_k=True, out_dtype=torch.float32, block_n=64,
                               split_k=0)
                     dB = dB * scaling if scaling != 1.0 else dB
+                    dB = dB if rr == r else dB[:, :r]
         if need[1]:
             dW = gemm(g, x, a_rows_are_k=True, b_rows_are_k=True)
         if has_bias and need[2]:
@@ -827,15 +838,17 @@ class CtxKVFn(torch.autograd.Function):
         a_st = b_st = t = None
         if has_lora:
             As, Bs = adapters[:G], adapters[G:]
-            a_st = torch.zeros((G, LORA_PAD, Dc), device=x.device, dtype=BF16)
+            pad = lora_pad(r)
+            a_st = torch.zeros((G, pad, Dc), device=x.device, dtype=BF16)
             a_st[:, :r] = torch.stack([A.detach() for A in As])
-            b_st = torch.zeros((G, D, LORA_PAD), device=x.device, dtype=BF16)
+            b_st = torch.zeros((G, D, pad), device=x.device, dtype=BF16)
             bs = torch.stack([B.detach() for B in Bs])
             b_st[:, :, :r] = bs * scaling if scaling != 1.0 else bs
-            a_st, b_st = a_st.view(G * LORA_PAD, Dc), b_st.view(G * D, LORA_PAD)
-            t = gemm(x, a_st)  # [M, G*64]
-        gemm_batched(x, Wkv, kv, M, D, Dc, G, {"b": (D, 0), "a2": (0, LORA_PAD), "b2": (D, 0), "c": (0, D), "bias": D},
-                     a2=t, b2=b_st, K2=LORA_PAD if has_lora else 0, bias=bkv)
+            a_st, b_st = a_st.view(G * pad, Dc), b_st.view(G * D, pad)
+            t = gemm(x, a_st)  # [M, G*pad]
+        pad = lora_pad(r) if has_lora else 0
+        gemm_batched(x, Wkv, kv, M, D, Dc, G, {"b": (D, 0), "a2": (0, pad), "b2": (D, 0), "c": (0, D), "bias": D},
+                     a2=t, b2=b_st, K2=pad, bias=bkv)
         ctx.save_for_backward(x, Wkv, a_st, b_st, t)
         ctx.meta = (G, D, scaling, r, has_lora)
         return tuple(kv[:, g * D:(g + 1) * D] for g in range(G))
@@ -855,9 +868,10 @@ class CtxKVFn(torch.autograd.Function):
             cols.append(g)
         dkv = torch.cat(cols, dim=1)  # [M, G*D]
         dt = None
+        pad = lora_pad(r) if has_lora else 0
         if has_lora:
-            dt = torch.empty((M, G * LORA_PAD), device=x.device, dtype=BF16)
-            gemm_batched(dkv, b_st, dt, M, LORA_PAD, D, G, {"a": (0, D), "b": (D, 0), "c": (0, LORA_PAD)},
+            dt = torch.empty((M, G * pad), device=x.device, dtype=BF16)
+            gemm_batched(dkv, b_st, dt, M, pad, D, G, {"a": (0, D), "b": (D, 0), "c": (0, pad)},
                          b_rows_are_k=True, block_n=64)
         dx = None
         if ctx.needs_input_grad[0]:
@@ -865,11 +879,11 @@ class CtxKVFn(torch.autograd.Function):
         dAs = dBs = ()
         if has_lora:
             dA = gemm(dt, x, a_rows_are_k=True, b_rows_are_k=True, out_dtype=torch.float32, split_k=0)
-            dA = dA.view(G, LORA_PAD, Dc)
-            dB = torch.empty((G * D, LORA_PAD), device=x.device, dtype=torch.float32)
-            gemm_batched(dkv, t, dB, D, LORA_PAD, M, G, {"a": (0, D), "b": (0, LORA_PAD), "c": (D, 0)},
+            dA = dA.view(G, pad, Dc)
+            dB = torch.empty((G * D, pad), device=x.device, dtype=torch.float32)
+            gemm_batched(dkv, t, dB, D, pad, M, G, {"a": (0, D), "b": (0, pad), "c": (D, 0)},
                          a_rows_are_k=True, b_rows_are_k=True, block_n=64)
-            dB = dB.view(G, D, LORA_PAD)
+            dB = dB.view(G, D, pad)
             if scaling != 1.0:
                 dB = dB * scaling
             need = ctx.needs_input_grad
