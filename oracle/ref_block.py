@@ -293,8 +293,10 @@ def rf_velocity_target(x0: Tensor, noise: Tensor, t: Tensor) -> Tensor:
     return a_dot * x0 + s_dot * noise
 
 
-def rf_step(timesteps_grid: Tensor, model_output: Tensor, timestep: Tensor, sample: Tensor) -> Tensor:
-    """Deterministic Euler step; `timesteps_grid` is scheduler.timesteps (descending)."""
+def rf_step(timesteps_grid: Tensor, model_output: Tensor, timestep: Tensor, sample: Tensor,
+            stochastic_sampling: bool = False) -> Tensor:
+    """Euler step (rf.py:305-374); `timesteps_grid` is scheduler.timesteps (descending).  stochastic_sampling: the x0
+    estimate re-noised to the next level with a draw from the global generator (rf.py:362-365)."""
     eps = 1e-6
     grid = torch.cat([timesteps_grid, torch.zeros(1, device=timesteps_grid.device)])
     if timestep.ndim == 0:
@@ -305,6 +307,11 @@ def rf_step(timesteps_grid: Tensor, model_output: Tensor, timestep: Tensor, samp
         below = grid[:, None, None] < timestep[None] - eps
         lower, _ = (below * grid[:, None, None]).max(dim=0)
         dt = (timestep - lower)[..., None]
+    if stochastic_sampling:
+        x0 = sample - timestep[..., None] * model_output
+        nxt = timestep[..., None] - dt
+        nxt = nxt.reshape(nxt.shape + (1,) * (sample.ndim - nxt.ndim))     # append_dims, torch_utils.py:16
+        return (1 - nxt) * x0 + nxt * torch.randn_like(sample)
     return sample - dt * model_output
 
 

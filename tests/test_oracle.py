@@ -88,6 +88,62 @@ def test_scheduler_matches_golden_and_closed_form(golden_dir, sampler):
         torch.testing.assert_close(got[:, 0], lat[:, 0], rtol=0, atol=1e-6)
 
 
+@pytest.mark.parametrize("stochastic", [False, True])
+def test_scheduler_step_product_equals_oracle_and_closed_form(stochastic):
+    """The product's RectifiedFlowScheduler.step (host element-wise ops, sampling only) == the oracle restatement, bit
+    for bit, for the global and the per-token timestep forms, deterministic and stochastic (rf.py:305-374); the
+    stochastic step is the x0 estimate re-noised to the next grid level with the draw the global generator gives."""
+    from b200_ltx.scheduler import RectifiedFlowScheduler
+    sch = RectifiedFlowScheduler(sampler="LinearQuadratic")
+    sch.set_timesteps(12, samples_shape=(2, 64, 8))
+    gen = torch.Generator().manual_seed(3)
+    lat, v = torch.randn(2, 64, 8, generator=gen), torch.randn(2, 64, 8, generator=gen)
+    tok = sch.timesteps[4].expand(2, 64).clone()
+    tok[:, :5] = 0.0          # hard-conditioned tokens: never move
+    tok[1, 7] = 0.31          # off-grid value
+    for t in (sch.timesteps[4], tok):
+        torch.manual_seed(11)
+        got = sch.step(v, t, lat, return_dict=False, stochastic_sampling=stochastic)[0]
+        torch.manual_seed(11)
+        want = rb.rf_step(sch.timesteps, v, t, lat, stochastic_sampling=stochastic)
+        assert torch.equal(got, want)
+        torch.manual_seed(11)
+        eps = torch.randn_like(lat)
+        grid = torch.cat([sch.timesteps, torch.zeros(1)])
+        tt = t.expand(2, 64) if t.ndim == 0 else t
+        nxt = torch.stack([torch.stack([grid[grid < x - 1e-6][0] if bool((grid < x - 1e-6).any()) else grid[-1]
+                                        for x in row]) for row in tt])[..., None]
+        if stochastic:
+            closed = (1 - nxt) * (lat - tt[..., None] * v) + nxt * eps
+        else:
+            closed = lat - (tt[..., None] - nxt) * v
+        torch.testing.assert_close(got, closed, rtol=0, atol=1e-6)
+
+
+@pytest.mark.skipif(not ref_import.available(), reason="reference tree not mounted")
+@pytest.mark.parametrize("stochastic", [False, True])
+def test_scheduler_step_bit_equal_to_live_reference(stochastic):
+    ns = ref_import.load()
+    from b200_ltx.scheduler import RectifiedFlowScheduler
+    ref = ns.RectifiedFlowScheduler(sampler="LinearQuadratic")
+    ours = RectifiedFlowScheduler(sampler="LinearQuadratic")
+    ref.set_timesteps(12, samples_shape=(2, 64, 8))
+    ours.set_timesteps(12, samples_shape=(2, 64, 8))
+    assert torch.equal(ref.timesteps, ours.timesteps)
+    gen = torch.Generator().manual_seed(5)
+    lat, v = torch.randn(2, 64, 8, generator=gen), torch.randn(2, 64, 8, generator=gen)
+    tok = ref.timesteps[6].expand(2, 64).clone()
+    tok[:, :9] = 0.0
+    for t in (ref.timesteps[6], ref.timesteps[-1], tok):
+        torch.manual_seed(2)
+        want = ref.step(v, t, lat, return_dict=False, stochastic_sampling=stochastic)[0]
+        torch.manual_seed(2)
+        got = ours.step(v, t, lat, return_dict=False, stochastic_sampling=stochastic)[0]
+        assert torch.equal(got, want)
+        torch.manual_seed(2)
+        assert torch.equal(rb.rf_step(ref.timesteps, v, t, lat, stochastic_sampling=stochastic), want)
+
+
 def test_rf_noise_and_target():
     g = torch.Generator().manual_seed(0)
     x0, n = torch.randn(2, 5, 4, generator=g), torch.randn(2, 5, 4, generator=g)

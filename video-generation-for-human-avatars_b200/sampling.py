@@ -84,8 +84,13 @@ class Denoiser:
                  negative_prompt_attention_mask: Optional[torch.Tensor] = None, guidance_scale: Scale = 1.0,
                  stg_scale: Scale = 0.0, rescaling_scale: Scale = 1.0, cfg_star_rescale: bool = False,
                  skip_block_list=None, skip_layer_strategy=None,
-                 conditioning_mask: Optional[torch.Tensor] = None) -> torch.Tensor:
+                 conditioning_mask: Optional[torch.Tensor] = None, stochastic_sampling: bool = False) -> torch.Tensor:
         model, scheduler = self.model, self.scheduler
+        if stochastic_sampling:
+            # the fused tail is the deterministic Euler step both shipped configs use (inference-avatars.yaml:14);
+            # the re-noising variant exists as RectifiedFlowScheduler.step(..., stochastic_sampling=True)
+            raise B200Error("denoise: stochastic_sampling is not part of the fused loop; drive the model with "
+                            "RectifiedFlowScheduler.step(..., stochastic_sampling=True) instead")
         if latents.dtype != torch.bfloat16 or not latents.is_cuda or latents.dim() != 3 or not latents.is_contiguous():
             raise B200Error("denoise: latents must be contiguous CUDA bfloat16 tokens [B, N, C]")
         dev = latents.device

@@ -121,8 +121,6 @@ class RectifiedFlowScheduler:
     def step(self, model_output, timestep, sample, return_dict=True, stochastic_sampling=False, **kwargs):
         if self.num_inference_steps is None:
             raise ValueError("Number of inference steps is 'None', you need to run 'set_timesteps' after creating the scheduler")
-        if stochastic_sampling:
-            raise B200Error("stochastic_sampling is not built")
         eps = 1e-6
         grid = torch.cat([self.timesteps, torch.zeros(1, device=self.timesteps.device)])
         if timestep.ndim == 0:
@@ -133,5 +131,13 @@ class RectifiedFlowScheduler:
             below = grid[:, None, None] < timestep[None] - eps
             lower, _ = (below * grid[:, None, None]).max(dim=0)
             dt = (timestep - lower)[..., None]
-        prev = sample - dt * model_output
+        if stochastic_sampling:
+            # rf.py:362-365: re-noise the x0 estimate to the next level (off in both shipped configs,
+            # inference-avatars.yaml:14; element-wise torch ops, drawn from the global generator as the reference does)
+            x0 = sample - timestep[..., None] * model_output
+            nxt = timestep[..., None] - dt
+            nxt = nxt.reshape(nxt.shape + (1,) * (sample.ndim - nxt.ndim))
+            prev = (1 - nxt) * x0 + nxt * torch.randn_like(sample)
+        else:
+            prev = sample - dt * model_output
         return (prev,) if not return_dict else type("RectifiedFlowSchedulerOutput", (), {"prev_sample": prev})()
