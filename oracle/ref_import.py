@@ -16,6 +16,7 @@ import types
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 REFERENCE_ROOT = os.environ.get("B200LTX_REFERENCE_ROOT", "/root/reference")
+SHIMMED = {}   # package -> True when the stand-in under oracle/ is what the reference imported
 
 
 def available() -> bool:
@@ -25,8 +26,17 @@ def available() -> bool:
 def _prepare():
     if not available():
         raise RuntimeError(f"reference tree not found at {REFERENCE_ROOT}")
-    for p in (os.path.join(HERE, "peft_shim"), os.path.join(HERE, "diffusers_shim")):
-        if p not in sys.path:
+    # A stand-in is used only for a package that is NOT installed: wherever the real diffusers / peft exist, the
+    # reference imports them and every test of this tier pins the third-party leaves too (B200LTX_FORCE_SHIMS=1
+    # keeps the stand-ins regardless).
+    import importlib.util
+    for pkg in ("peft", "diffusers"):
+        p = os.path.join(HERE, pkg + "_shim")
+        if p in sys.path:
+            continue
+        real = os.environ.get("B200LTX_FORCE_SHIMS") != "1" and importlib.util.find_spec(pkg) is not None
+        SHIMMED[pkg] = not real
+        if not real:
             sys.path.insert(0, p)
     if REFERENCE_ROOT not in sys.path:
         sys.path.append(REFERENCE_ROOT)
