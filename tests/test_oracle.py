@@ -230,6 +230,47 @@ def test_reference_train_step_rng_path(golden_dir):
     assert torch.equal(loss.detach(), ol.detach())
 
 
+@pytest.mark.skipif(not ref_import.available(), reason="reference tree not mounted")
+@pytest.mark.parametrize("shifting", [None, "SD3", "SimpleDiffusion"])
+@pytest.mark.parametrize("B", [2, 5, 33])
+def test_product_timestep_sampling_equals_the_references_draw(shifting, B):
+    """train.sample_timesteps (LogNormal -> t / (1 + t) -> quantile clamp -> resolution shift, without the reference's
+    two host synchronisations) hands the model the timesteps the reference's own train_step draws from the same
+    generator state (training.py:124-136): a stub model records what each receives."""
+    from b200_ltx.scheduler import RectifiedFlowScheduler
+    from b200_ltx.train import sample_timesteps
+    ns = ref_import.load()
+    tr = ref_import.load_training()
+    seen = {}
+
+    class Stub(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.w = torch.nn.Parameter(torch.zeros(1))
+
+        def forward(self, hidden_states=None, timestep=None, **kw):
+            seen["t"] = timestep.detach().clone()
+            return type("O", (), {"sample": hidden_states * self.w})()
+
+    class Cfg:
+        rf_log_normal_mu, rf_log_normal_sigma = -0.5, 1.0
+        rf_quantile_min, rf_quantile_max = 0.005, 0.999
+        transformer_loss_weight = 1.0
+    kw = dict(shifting=shifting) if shifting else {}
+    if shifting == "SD3":
+        kw["target_shift_terminal"] = 0.1
+    g = torch.Generator().manual_seed(B)
+    batch = {"latents": torch.randn(B, 8, 3, 4, 4, generator=g), "ref_image_latents": torch.randn(B, 8, 1, 4, 4, generator=g),
+             "pose_latents": torch.randn(B, 8, 3, 4, 4, generator=g)}
+    torch.manual_seed(5)
+    tr.train_step(Stub(), batch, ns.RectifiedFlowScheduler(**kw), ns.SymmetricPatchifier(patch_size=1), Cfg(),
+                  torch.zeros(1, 4, 8), torch.ones(1, 4), device=torch.device("cpu"))
+    torch.manual_seed(5)
+    ours = sample_timesteps(Cfg(), RectifiedFlowScheduler(**kw), (B, 48, 8), B, torch.device("cpu"))
+    assert ours.shape == seen["t"].shape == (B,)
+    assert torch.equal(ours, seen["t"]), (ours - seen["t"]).abs().max()
+
+
 def _sampling_inputs():
     cfg = dict(rb.LTXV_2B, num_layers=2, num_attention_heads=4, cross_attention_dim=256, caption_channels=64)
     P = rb.init_params(cfg, 0, seed=5)
