@@ -216,3 +216,88 @@ def test_fused_stg_skip_host_logic_matches_reference(strategy):
     assert _rel(got, want) < 2e-2, _rel(got, want)
     # attn1 of blocks 0 and 2 took the in-launch skip, block 1 (all-ones row) and every attn2 did not
     assert sum(calls) == 2 and len(calls) == 6
+
+
+@pytest.mark.parametrize("B", [1, 2])
+def test_product_train_step_on_reference_model_matches_reference_train_step(B):
+    """The product's train_step (train.py) driving an INSTALLED instance of the reference's own peft-wrapped model, with
+    the product's scheduler and patchifier, against the reference's own train_step (training.py:94-166) on the same
+    model, batch and generator state: same four return values (loss, rel_mse, nrmse, {"transformer_mse"}) within the
+    bf16 tolerance -- timestep draw, noise draw, noising, velocity target, the in-place conditioning of the noisy
+    tokens and the metrics all follow the reference's order."""
+    from b200_ltx import api
+    from b200_ltx.modules import SymmetricPatchifier
+    from b200_ltx.scheduler import RectifiedFlowScheduler
+    from b200_ltx.train import train_step
+    ns, cfg, model = _reference_model(32)
+    tr = ref_import.load_training()
+    b = rb.synthetic_batch(cfg, B, 2, 4, 4, 24, 9, 15)
+    batch = {k: b[k] for k in ("latents", "ref_image_latents", "pose_latents")}
+
+    class Cfg:
+        rf_log_normal_mu, rf_log_normal_sigma = -0.5, 1.0
+        rf_quantile_min, rf_quantile_max = 0.005, 0.999
+        transformer_loss_weight = 0.75
+    model.train()
+    torch.manual_seed(21)
+    want = tr.train_step(model, batch, ns.RectifiedFlowScheduler(), ns.SymmetricPatchifier(patch_size=1), Cfg(),
+                         b["prompt_embeds"], b["prompt_mask"], device=torch.device("cpu"))
+    with tk.patched():
+        api.install(model)
+        torch.manual_seed(21)
+        got = train_step(model, batch, RectifiedFlowScheduler(), SymmetricPatchifier(1), Cfg(), b["prompt_embeds"],
+                         b["prompt_mask"], device=torch.device("cpu"))
+        api.uninstall(model)
+    assert len(got) == len(want) == 4 and set(got[3]) == set(want[3]) == {"transformer_mse"}
+    assert all(x.dim() == 0 for x in got[:3])
+    for name, g, w in (("loss", got[0], want[0]), ("rel_mse", got[1], want[1]), ("nrmse", got[2], want[2]),
+                       ("transformer_mse", got[3]["transformer_mse"], want[3]["transformer_mse"])):
+        # (the reference's dict value is a python float -- an .item() host sync per step, training.py:162; the product
+        # keeps a 0-d tensor, which the caller's `float(v)` at logging time, training.py:218-219, accepts)
+        g, w = [float(x.detach()) if torch.is_tensor(x) else float(x) for x in (g, w)]
+        assert abs(g - w) <= 2e-2 * abs(w), (name, g, w)
+
+
+@pytest.mark.parametrize("train_mode,lora_rank", [("lora_audio", 32), ("lora_audio", 12), ("full", 0)])
+def test_product_backward_on_reference_model_matches_reference_autograd(train_mode, lora_rank):
+    """Forward AND backward of the installed path on the reference's own model instance (the reference's own
+    apply_training_strategy decides what trains): every gradient the reference's autograd produces is produced by the
+    product's autograd Functions (LinearFn / CtxKVFn / SelfAttnFn / FeedForwardFn / NormMod*Fn with their side channels)
+    with the same name, shape and dtype, and agrees within the bf16 tolerance.  Kernels = plain-torch stand-ins."""
+    from b200_ltx import api
+    from b200_ltx.train import rf_mse_loss
+    ns = ref_import.load()
+    cfg = dict(mg.TINY, num_layers=2)
+    P = rb.init_params(cfg, lora_rank, seed=2)
+    model = mg.build_reference_model(ns, cfg, lora_rank, P, train_mode=train_mode).to(BF16)
+    for n, p in model.named_parameters():
+        if "lora_" in n:
+            p.data = p.data.float()
+    model.train()
+    inp = _inputs(cfg, seed=8)
+    target = torch.randn(inp["hidden_states"].shape, generator=torch.Generator().manual_seed(3)).to(BF16)
+
+    def grads(loss_fn):
+        model.zero_grad(set_to_none=True)
+        x = {k: (v.clone() if torch.is_tensor(v) else v) for k, v in inp.items()}
+        out = model(**x, return_dict=False)[0]
+        loss_fn(out, target).backward()
+        return out.detach(), {n: p.grad.detach().clone() for n, p in model.named_parameters() if p.grad is not None}
+    want_out, want = grads(torch.nn.functional.mse_loss)
+    with tk.patched():
+        api.install(model)
+        got_out, got = grads(rf_mse_loss)
+        api.uninstall(model)
+    assert _rel(got_out, want_out) < 2e-2
+    assert set(got) == set(want) and len(want) >= 8
+    worst = ("", 0.0)
+    for n in want:
+        assert got[n].shape == want[n].shape and got[n].dtype == want[n].dtype, n
+        wn = float(want[n].float().norm())
+        if wn == 0.0:
+            assert float(got[n].float().norm()) == 0.0, n
+            continue
+        e = _rel(got[n], want[n])
+        worst = max(worst, (n, e), key=lambda t: t[1])
+    print(f"worst gradient: {worst[0]} rel err {worst[1]:.3e} over {len(want)} gradients")
+    assert worst[1] < 5e-2, worst

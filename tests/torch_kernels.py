@@ -165,11 +165,105 @@ def lerp_condition_(tokens, ref, pose, w_ref=0.85, w_pose=0.5, token_offset=0):
     return tokens
 
 
+# ---- backward kernels: fp32 autograd through the same math, rounded where the kernels round ----
+def norm_mod_bwd(dy, x, scale, rows_per_mod, eps, layernorm=False, dres=None, want_prod=False):
+    rows = x.shape[0]
+    xf = x.float().detach().requires_grad_(True)
+    with torch.enable_grad():
+        if layernorm:
+            n = F.layer_norm(xf, (xf.shape[-1],), None, None, eps)
+        else:
+            n = xf * torch.rsqrt(xf.pow(2).mean(-1, keepdim=True) + eps)
+        y = n if scale is None else n * (1 + scale.detach().float().repeat_interleave(rows_per_mod, 0)[:rows])
+        y.backward(dy.float())
+    dx = xf.grad if dres is None else xf.grad + dres.float()
+    dx = dx.to(BF16)
+    return (dx, (dy.float() * n.detach()).to(BF16)) if want_prod else dx
+
+
+def colsum_groups(a, b=None, rows_per_group=0):
+    rows, N = a.shape
+    rpg = rows_per_group or rows
+    if rows == 0:
+        return torch.empty((0, N), dtype=torch.float32)
+    assert rows % rpg == 0, "colsum_groups: rows must be a multiple of rows_per_group"
+    v = a.float() if b is None else a.float() * b.float()
+    return v.view(rows // rpg, rpg, N).sum(1)
+
+
+def colsum(x):
+    return x.float().sum(0)
+
+
+def rowscale(x, g, rows_per_mod):
+    return (x.float() * g.float().repeat_interleave(rows_per_mod, 0)[:x.shape[0]]).to(BF16)
+
+
+def qknorm_rope_bwd(dq, dk, xq, xk, wq, wk, cos, sin, oq, ok, eps=1e-5, prod_q=None, prod_k=None):
+    for d, x, w, o, prod in ((dq, xq, wq, oq, prod_q), (dk, xk, wk, ok, prod_k)):
+        if x is None:
+            continue
+        xf = x.float().detach().requires_grad_(True)
+        wf = w.float().detach().requires_grad_(True)
+        with torch.enable_grad():
+            xhat = xf * torch.rsqrt(xf.pow(2).mean(-1, keepdim=True) + eps)
+            n = xhat * wf
+            if cos is not None:
+                n = _rope(n, cos, sin)
+            n.backward(d.float())
+        o.copy_(xf.grad.to(o.dtype))
+        if prod is not None:   # (RoPE^T d) * xhat: its column sum is the gradient of the norm weight
+            with torch.enable_grad():
+                z = torch.zeros_like(xf, requires_grad=True)
+                (_rope(z, cos, sin) if cos is not None else z).backward(d.float())
+            prod.copy_((z.grad * xhat.detach()).to(prod.dtype))
+
+
+def fa_bwd(q, k, v, o, do, lse, B, H, Nq, Nk, dk, dv, key_bias=None, scale=0.125, delta=None, dq_accum=None, attn1=None):
+    D = H * 64
+    leaves = []
+    for t, n in ((q, Nq), (k, Nk), (v, Nk)):
+        leaves.append(t[:, :D].float().detach().reshape(B, n, H, 64).transpose(1, 2).requires_grad_(True))
+    qh, kh, vh = leaves
+    with torch.enable_grad():
+        s = qh @ kh.transpose(-1, -2) * scale
+        if key_bias is not None:
+            s = s + key_bias.float()[:, None, None, :]
+        out = (torch.softmax(s, dim=-1) @ vh).transpose(1, 2).reshape(B * Nq, D)
+        out.backward(do[:, :D].float())
+    flat = [t.grad.transpose(1, 2).reshape(-1, D) for t in leaves]
+    dk.copy_(flat[1].to(dk.dtype))
+    dv.copy_(flat[2].to(dv.dtype))
+    if dq_accum is not None:
+        dq_accum[:, :D] += flat[0]
+        return dq_accum
+    return flat[0].contiguous()
+
+
+def rf_noise(x0, noise, t, want_xt=True, want_v=True):
+    """x_t = (1 - t) x0 + t eps and v = eps - x0 in fp32, rounded once (csrc/elementwise.cu rf_noise_kernel)."""
+    if x0.dtype != BF16 or noise.dtype != BF16 or not x0.is_contiguous() or not noise.is_contiguous():
+        raise AssertionError("rf_noise: contiguous bf16 tensors required")
+    tt = t.float().reshape(-1, *([1] * (x0.dim() - 1)))
+    xt = ((1 - tt) * x0.float() + tt * noise.float()).to(BF16) if want_xt else None
+    v = (noise.float() - x0.float()).to(BF16) if want_v else None
+    return xt, v
+
+
+def rf_loss(out, target, grad_scale=1.0, want_grad=True):
+    """mean((out - target)^2) in fp32 and its gradient 2 (out - target) / numel * grad_scale in bf16."""
+    d = out.float() - target.float()
+    loss = (d * d).mean()
+    dout = (d * (2.0 * grad_scale / d.numel())).to(BF16) if want_grad else None
+    return loss, dout
+
+
 @contextlib.contextmanager
 def patched():
     """Run the product's host logic over these stand-ins (CPU tensors allowed, no device check)."""
     from b200_ltx import lib, modules, ops
-    names = ["gemm", "gemm_batched", "norm_mod_fwd", "qknorm_rope_fwd", "fa_fwd", "lerp_condition_"]
+    names = ["gemm", "gemm_batched", "norm_mod_fwd", "qknorm_rope_fwd", "fa_fwd", "lerp_condition_", "rf_noise", "rf_loss",
+             "norm_mod_bwd", "colsum_groups", "colsum", "rowscale", "qknorm_rope_bwd", "fa_bwd"]
     saved = {n: getattr(ops, n) for n in names}
     saved_req, saved_dev = modules._require_bf16, lib.require_device
     try:
