@@ -301,3 +301,36 @@ def test_product_backward_on_reference_model_matches_reference_autograd(train_mo
         worst = max(worst, (n, e), key=lambda t: t[1])
     print(f"worst gradient: {worst[0]} rel err {worst[1]:.3e} over {len(want)} gradients")
     assert worst[1] < 5e-2, worst
+
+
+def test_gradient_checkpoint_backward_on_reference_model_equals_plain_backward():
+    """transformer3d.py:503-534 with training + gradient_checkpointing: torch.utils.checkpoint(use_reentrant=False)
+    re-runs every block's forward during the backward.  The fused path hands gradients around outside autograd's view
+    (GradJoin parks the attn2 residual-branch gradient between two LinearFn nodes; NormModResFn returns the residual as
+    an aliased second output): the recomputation must not double-count or lose any of it.  Same gradients, to the last
+    bit, with and without checkpointing, on the reference's own model class."""
+    from b200_ltx import api
+    from b200_ltx.train import rf_mse_loss
+    ns, cfg, model = _reference_model(32, seed=4)
+    root = model.base_model.model
+    model.train()
+    inp = _inputs(cfg, seed=6)
+    target = torch.randn(inp["hidden_states"].shape, generator=torch.Generator().manual_seed(1)).to(BF16)
+
+    def grads():
+        model.zero_grad(set_to_none=True)
+        x = {k: (v.clone() if torch.is_tensor(v) else v) for k, v in inp.items()}
+        out = model(**x, return_dict=False)[0]
+        rf_mse_loss(out, target).backward()
+        return out.detach(), {n: p.grad.detach().clone() for n, p in model.named_parameters() if p.grad is not None}
+    with tk.patched():
+        api.install(model)
+        out_plain, plain = grads()
+        root.gradient_checkpointing = True
+        out_ckpt, ckpt = grads()
+        root.gradient_checkpointing = False
+        api.uninstall(model)
+    assert torch.equal(out_plain, out_ckpt)
+    assert set(plain) == set(ckpt) and len(plain) == 20
+    for n in plain:
+        assert torch.equal(plain[n], ckpt[n]), (n, _rel(ckpt[n], plain[n]))
