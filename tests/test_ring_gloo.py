@@ -105,3 +105,67 @@ def test_head_exchange_attention_matches_unsharded(world):
     out = mgr.dict()
     mp.spawn(_worker, args=(world, _free_port(), out, "heads"), nprocs=world, join=True)
     assert len(out) == world and all(v < 2e-5 for v in out.values()), dict(out)
+
+
+def _model_worker(rank, world, port, out, mode):
+    """Whole train step of the mirror model, sequence-sharded over `world` gloo ranks (tokens, coordinates and noise
+    sharded inside train_step, timestep broadcast, conditioning lerp at the shard's token offset, attn1 through the ring /
+    the head exchange, everything else token-local) against the same step un-sharded: the mean of the per-shard losses
+    is the loss, the average of the per-shard gradients is the gradient."""
+    import sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    for p in (here, os.path.join(os.path.dirname(here), "oracle")):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import model_checks as mc
+    import ref_block as rb
+    import torch_kernels as tk
+    from b200_ltx import api
+    torch.set_num_threads(2)
+    cfg = dict(rb.LTXV_2B, num_layers=2, num_attention_heads=2, cross_attention_dim=128, caption_channels=64)
+    P = rb.init_params(cfg, 8, seed=5)
+    b = rb.synthetic_batch(cfg, 1, 3, 2, 2 * world, 16, 77, 9)      # 3 frames x 2 x 2P tokens: frame 0 ends inside rank 0's shard
+
+    class Cfg:
+        rf_log_normal_mu, rf_log_normal_sigma = -0.5, 1.0
+        rf_quantile_min, rf_quantile_max = 0.005, 0.999
+        transformer_loss_weight = 1.0
+
+    def step(model):
+        for p in model.parameters():
+            p.grad = None
+        t = torch.tensor([0.37]) if rank == 0 else torch.tensor([0.99])     # rank 0's value must win (broadcast)
+        loss = api.train_step(model, {n: b[n] for n in ("latents", "ref_image_latents", "pose_latents")},
+                              api.RectifiedFlowScheduler(), api.SymmetricPatchifier(1), Cfg(), b["prompt_embeds"],
+                              b["prompt_mask"], device=torch.device("cpu"), t=t, noise=b["noise"].to(torch.bfloat16))[0]
+        loss.backward()
+        return loss.detach().float(), {n: p.grad.detach().float().clone() for n, p in model.named_parameters()
+                                       if p.grad is not None}
+
+    with tk.patched():
+        model = mc.build_b200_model(cfg, P, 8, device="cpu").train()
+        sp = api.enable_sequence_parallel(model, None, TorchLocalAttention(), mode)
+        assert sp is not None and sp.world == world
+        loss_s, grads_s = step(model)
+        dist.all_reduce(loss_s)
+        for g in grads_s.values():
+            dist.all_reduce(g)
+        api.enable_sequence_parallel(model, disable=True)
+        loss_f, grads_f = step(model) if rank == 0 else (None, None)
+    if rank == 0:
+        worst = abs(float(loss_s) / world - float(loss_f)) / float(loss_f)
+        assert set(grads_s) == set(grads_f) and len(grads_f) == 20
+        for n in grads_f:
+            worst = max(worst, float((grads_s[n] / world - grads_f[n]).norm()) / (float(grads_f[n].norm()) + 1e-20))
+        out[0] = worst
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("mode", ["ring", "heads"])
+def test_whole_model_sequence_parallel_train_step_world2(mode):
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_model_worker, args=(2, _free_port(), out, mode), nprocs=2, join=True)
+    assert len(out) == 1 and out[0] < 2e-2, dict(out)

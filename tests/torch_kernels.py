@@ -156,12 +156,19 @@ def fa_fwd(q, k, v, B, H, Nq, Nk, key_bias=None, scale=0.125, need_lse=True, att
 
 
 def lerp_condition_(tokens, ref, pose, w_ref=0.85, w_pose=0.5, token_offset=0):
+    """In-place conditioning of transformer3d.py:447-466 on a contiguous shard [token_offset, token_offset + N) of the
+    clip's tokens: frame 0 lerps towards the reference image (0.85), later frames towards the pose latents (0.5)."""
     B, N, C = tokens.shape
     Fr, Hh, Ww = pose.shape[2], pose.shape[3], pose.shape[4]
-    assert token_offset == 0 and N == Fr * Hh * Ww
-    v = tokens.view(B, Fr, Hh, Ww, C).permute(0, 4, 1, 2, 3)
-    v[:, :, 0:1] = torch.lerp(v[:, :, 0:1], ref, w_ref)
-    v[:, :, 1:] = torch.lerp(v[:, :, 1:], pose[:, :, 1:], w_pose)
+    HW = Hh * Ww
+    assert 0 <= token_offset and token_offset + N <= Fr * HW
+    # whole-clip conditioning tokens [B, F*HW, C]: frame 0 from `ref`, the rest from `pose`
+    cond = pose.reshape(B, C, Fr * HW).transpose(1, 2).clone()
+    cond[:, :HW] = ref.reshape(B, C, HW).transpose(1, 2)
+    w = torch.full((Fr * HW, 1), w_pose)
+    w[:HW] = w_ref
+    sl = slice(token_offset, token_offset + N)
+    tokens.copy_(torch.lerp(tokens.float(), cond[:, sl].float(), w[sl]).to(tokens.dtype))
     return tokens
 
 
