@@ -83,6 +83,28 @@ def test_header_definitions_and_ctypes_prototypes_agree():
         assert [ctype_kind[t] for t in argtypes] == args, (name, [ctype_kind[t] for t in argtypes], args)
 
 
+def test_integration_doc_matches_the_abi():
+    """INTEGRATION.md is what a maintainer copies from: every entry point it names exists in the header (the `fwd/bwd`
+    shorthand of its table expanded), and the ctypes stub it prints carries the argument list lib.py binds."""
+    from b200_ltx import lib
+    doc = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    names = set(_header_symbols())
+    mentioned = set()
+    for m in re.finditer(r"`(b200_[a-z0-9_]+)((?:/[a-z0-9_]+)*)`", doc):
+        base, alts = m.group(1), [a for a in m.group(2).split("/") if a]
+        mentioned.add(base)
+        for a in alts:                       # `b200_norm_mod_fwd/bwd` -> b200_norm_mod_bwd
+            mentioned.add(base[:base.rfind("_") + 1] + a)
+    mentioned = {n for n in mentioned if not n.startswith("b200_ltx")}     # the Python package name
+    assert mentioned and mentioned <= names, sorted(mentioned - names)
+    assert len(mentioned) >= 25
+    short = {"P": lib.P, "I": lib.I, "L": lib.L, "F": lib.F}
+    stubs = re.findall(r"lib\.(b200_[a-z0-9_]+)\.argtypes = \[([^\]]*)\]", doc)
+    assert stubs
+    for name, args in stubs:
+        assert [short[a.strip()] for a in args.split(",")] == lib.PROTOTYPES[name][1], name
+
+
 def test_argument_contract_rejected_before_launch():
     from b200_ltx import lib
     h = lib.load()
