@@ -396,8 +396,11 @@ constexpr int FA2_THREADS = 64 + 128 * FA2_TPR;
 constexpr int FA2_MIN_KEYS = 512;                                  // below: the 4-CTA kernel above (attn2)
 constexpr int FA2_O_COLS = FA2_ROWSUM_MMA ? 80 : 64;               // O | row-sum column (+15 unused) in TMEM
 
-// 2^x for x <= 0 on the FMA pipe: round-to-nearest split x = n + f, f in [-0.5, 0.5], degree-3 polynomial of 2^f
-// (max rel. error ~1e-4, far below the bf16 rounding of P), exponent added in the integer domain.
+// 2^x for x <= 0 on the FMA pipe: round-to-nearest split x = n + f, f in [-0.5, 0.5], degree-3 polynomial of 2^f,
+// exponent added in the integer domain.  The coefficients are the Taylor ones (ln2, ln2^2/2, ln2^3/6): max rel. error
+// 7.9e-4 at |f| = 0.5, always low, against the 2e-3 bf16 rounding of P it feeds (tests/test_device_math_host.py runs
+// this function on the host).  The minimax fit with the constant pinned at 1 -- 0.69328293, 0.24221096, 0.05500893 --
+// gives 1.0e-4 for the same instructions; not swapped in without a GPU run of the parity tests behind it.
 __device__ __forceinline__ float ex2_poly(float x) {
   x = fmaxf(x, -120.f);
   const float t = x + 12582912.f;                // 1.5 * 2^23: the integer part lands in the low mantissa bits
