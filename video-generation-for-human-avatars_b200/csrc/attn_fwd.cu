@@ -400,13 +400,18 @@ constexpr int FA2_O_COLS = FA2_ROWSUM_MMA ? 80 : 64;               // O | row-su
 // exponent added in the integer domain.  The coefficients are the Taylor ones (ln2, ln2^2/2, ln2^3/6): max rel. error
 // 7.9e-4 at |f| = 0.5, always low, against the 2e-3 bf16 rounding of P it feeds (tests/test_device_math_host.py runs
 // this function on the host).  The minimax fit with the constant pinned at 1 -- 0.69328293, 0.24221096, 0.05500893 --
-// gives 1.0e-4 for the same instructions; not swapped in without a GPU run of the parity tests behind it.
+// gives 1.0e-4 for the same instructions (-DB200_EX2_MINIMAX); not the default without a GPU run of the parity tests behind it.
+#ifdef B200_EX2_MINIMAX   // experiment switch (build.py variant): the minimax constants, 1.0e-4
+constexpr float EX2_C1 = 0.69328293f, EX2_C2 = 0.24221096f, EX2_C3 = 0.05500893f;
+#else
+constexpr float EX2_C1 = 0.6931472f, EX2_C2 = 0.2402265f, EX2_C3 = 0.0555041f;
+#endif
 __device__ __forceinline__ float ex2_poly(float x) {
   x = fmaxf(x, -120.f);
   const float t = x + 12582912.f;                // 1.5 * 2^23: the integer part lands in the low mantissa bits
   const float f = x - (t - 12582912.f);
-  float p = fmaf(0.0555041f, f, 0.2402265f);
-  p = fmaf(p, f, 0.6931472f);
+  float p = fmaf(EX2_C3, f, EX2_C2);
+  p = fmaf(p, f, EX2_C1);
   p = fmaf(p, f, 1.0f);
   return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
 }
@@ -419,8 +424,8 @@ __device__ __forceinline__ float2 ex2_poly2(float2 x) {
   const float2 t = __fadd2_rn(x, magic);
   const float2 n = __fadd2_rn(t, nmagic);
   const float2 f = __fadd2_rn(x, make_float2(-n.x, -n.y));
-  float2 p = __ffma2_rn(make_float2(0.0555041f, 0.0555041f), f, make_float2(0.2402265f, 0.2402265f));
-  p = __ffma2_rn(p, f, make_float2(0.6931472f, 0.6931472f));
+  float2 p = __ffma2_rn(make_float2(EX2_C3, EX2_C3), f, make_float2(EX2_C2, EX2_C2));
+  p = __ffma2_rn(p, f, make_float2(EX2_C1, EX2_C1));
   p = __ffma2_rn(p, f, make_float2(1.0f, 1.0f));
   return make_float2(__int_as_float(__float_as_int(p.x) + (__float_as_int(t.x) << 23)),
                      __int_as_float(__float_as_int(p.y) + (__float_as_int(t.y) << 23)));
