@@ -144,6 +144,41 @@ def test_scheduler_step_bit_equal_to_live_reference(stochastic):
         assert torch.equal(rb.rf_step(ref.timesteps, v, t, lat, stochastic_sampling=stochastic), want)
 
 
+@pytest.mark.skipif(not ref_import.available(), reason="reference tree not mounted")
+@pytest.mark.parametrize("sampler", ["Uniform", "LinearQuadratic", "Constant"])
+@pytest.mark.parametrize("shifting", [None, "SD3", "SimpleDiffusion"])
+def test_scheduler_grids_bit_equal_to_live_reference(sampler, shifting):
+    """RectifiedFlowScheduler.set_timesteps of the mirror == the reference's (rf.py:176-303) for every sampler x
+    resolution-shift combination, step counts 1..1000 and three latent geometries (the shift depends on the token count),
+    plus caller-provided timesteps and the constructor's initial grid."""
+    from b200_ltx.scheduler import RectifiedFlowScheduler
+    ns = ref_import.load()
+    kw = dict(sampler=sampler)
+    if shifting:
+        kw["shifting"] = shifting
+    if shifting == "SD3":
+        kw["target_shift_terminal"] = 0.1
+    if sampler == "Constant":
+        kw["shift"] = 3.0
+    ref, ours = ns.RectifiedFlowScheduler(**kw), RectifiedFlowScheduler(**kw)
+    assert torch.equal(ref.timesteps, ours.timesteps)
+    for shape in ((1, 256, 128), (2, 6144, 128), (1, 12672, 128)):
+        for n in (1, 2, 3, 5, 8, 20, 40, 100, 1000):
+            ref.set_timesteps(n, samples_shape=shape)
+            ours.set_timesteps(n, samples_shape=shape)
+            assert ours.num_inference_steps == ref.num_inference_steps
+            # (one step with the SD3 terminal stretch is 0 / 0 in the reference, rf.py: its NaN is reproduced)
+            same = lambda a, b: torch.equal(torch.nan_to_num(a, nan=-7.0), torch.nan_to_num(b, nan=-7.0))  # noqa: E731
+            assert same(ref.timesteps, ours.timesteps), (shape, n, (ref.timesteps - ours.timesteps).abs().max())
+            assert same(ref.sigmas, ours.sigmas)
+    given = [1.0, 0.7, 0.33, 0.05]
+    ref.set_timesteps(timesteps=given, samples_shape=(1, 256, 128))
+    ours.set_timesteps(timesteps=given, samples_shape=(1, 256, 128))
+    assert torch.equal(ref.timesteps, ours.timesteps) and ours.num_inference_steps == ref.num_inference_steps == 4
+    with pytest.raises(ValueError):
+        ours.set_timesteps(4, timesteps=given)
+
+
 def test_rf_noise_and_target():
     g = torch.Generator().manual_seed(0)
     x0, n = torch.randn(2, 5, 4, generator=g), torch.randn(2, 5, 4, generator=g)
