@@ -179,6 +179,29 @@ def test_scheduler_grids_bit_equal_to_live_reference(sampler, shifting):
         ours.set_timesteps(4, timesteps=given)
 
 
+@pytest.mark.skipif(not ref_import.available(), reason="reference tree not mounted")
+@pytest.mark.parametrize("shape", [(1, 128, 4, 8, 8), (2, 16, 3, 5, 7), (4, 128, 13, 16, 16), (1, 8, 1, 1, 1)])
+def test_patchifier_mirror_equals_reference(shape):
+    """SymmetricPatchifier (symmetric_patchifier.py:33-84, patch size 1): tokens, coordinates and the unpatchified VIEW
+    (the forward's in-place conditioning writes through it, transformer3d.py:447-466) equal the reference's, including
+    dtype, token order (f, then h, then w) and that un-patchify shares storage with the tokens."""
+    from b200_ltx.modules import SymmetricPatchifier
+    ns = ref_import.load()
+    ref, ours = ns.SymmetricPatchifier(patch_size=1), SymmetricPatchifier(1)
+    assert tuple(ours.patch_size) == tuple(ref.patch_size)
+    lat = torch.randn(*shape, generator=torch.Generator().manual_seed(0))
+    b, c, f, h, w = shape
+    rt, rc = ref.patchify(lat)
+    ot, oc = ours.patchify(lat)
+    assert torch.equal(rt, ot) and torch.equal(rc, oc) and rc.dtype == oc.dtype and rc.shape == (b, 3, f * h * w)
+    assert torch.equal(ref.get_latent_coords(f, h, w, b, "cpu"), ours.get_latent_coords(f, h, w, b, "cpu"))
+    tok = ot.contiguous()
+    ru, ou = ref.unpatchify(tok, h, w, c), ours.unpatchify(tok, h, w, c)
+    assert torch.equal(ru, ou) and torch.equal(ou, lat)
+    ou[:, :, 0:1] = 7.0                                   # a write through the view lands in the tokens
+    assert bool((tok[:, :h * w] == 7.0).all()) and ou.data_ptr() == tok.data_ptr()
+
+
 def test_rf_noise_and_target():
     g = torch.Generator().manual_seed(0)
     x0, n = torch.randn(2, 5, 4, generator=g), torch.randn(2, 5, 4, generator=g)
