@@ -202,6 +202,32 @@ def test_patchifier_mirror_equals_reference(shape):
     assert bool((tok[:, :h * w] == 7.0).all()) and ou.data_ptr() == tok.data_ptr()
 
 
+@pytest.mark.skipif(not ref_import.available(), reason="reference tree not mounted")
+@pytest.mark.parametrize("dim,max_pos", [(2048, [20, 2048, 2048]), (256, [20, 2048, 2048]), (192, [120, 1, 1])])
+def test_product_rope_table_bit_equal_to_live_reference(dim, max_pos):
+    """modules.rope_table (torch ops on the product path, SURVEY Q11: the fp32 op order must be the reference's because
+    the angles reach 1.5e4 rad) == Transformer3DModel.precompute_freqs_cis (transformer3d.py:209-277) called on a bf16
+    model: integer training coordinates, the sampler's fractional pixel coordinates, widths with 2, 4 and 0 padded
+    columns (dim % 6), and the reference's own test-fixture max_pos."""
+    import types
+    from b200_ltx.modules import rope_table
+    ns = ref_import.load()
+    T3D = ns.Transformer3DModel
+    fake = types.SimpleNamespace(dtype=torch.bfloat16, inner_dim=dim, positional_embedding_theta=10000.0,
+                                 positional_embedding_max_pos=max_pos)
+    fake.get_fractional_positions = lambda g: T3D.get_fractional_positions(fake, g)
+    coords = rb.latent_coords(5, 6, 7, 2)
+    frac = coords.float()
+    frac[:, 0] = frac[:, 0] * (8.0 / 25.0)          # pipeline: latent frame -> seconds at frame_rate 25
+    frac[:, 1:] = frac[:, 1:] * 32.0 + 0.5
+    for grid in (coords, frac):
+        want_c, want_s = T3D.precompute_freqs_cis(fake, grid)
+        got_c, got_s = rope_table(grid, dim, 10000.0, max_pos)
+        assert got_c.dtype == want_c.dtype == torch.bfloat16 and got_c.shape == want_c.shape == (2, 210, dim)
+        assert torch.equal(got_c, want_c) and torch.equal(got_s, want_s)
+        assert got_c.is_contiguous() and got_s.is_contiguous()
+
+
 def test_rf_noise_and_target():
     g = torch.Generator().manual_seed(0)
     x0, n = torch.randn(2, 5, 4, generator=g), torch.randn(2, 5, 4, generator=g)
