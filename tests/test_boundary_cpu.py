@@ -334,3 +334,33 @@ def test_gradient_checkpoint_backward_on_reference_model_equals_plain_backward()
     assert set(plain) == set(ckpt) and len(plain) == 20
     for n in plain:
         assert torch.equal(plain[n], ckpt[n]), (n, _rel(ckpt[n], plain[n]))
+
+
+@pytest.mark.parametrize("train_mode,lora_rank", [("lora_audio", 32), ("lora_audio", 8), ("full", 0)])
+def test_mirror_training_strategy_names_shapes_and_trainable_set_equal_the_references(train_mode, lora_rank):
+    """What a checkpoint, an optimizer and a `"lora_" in name` filter see: the mirror model after the product's
+    apply_training_strategy (lora.py) against the reference's model after its own apply_training_strategy
+    (training.py:42-91, peft stand-in): identical parameter names (incl. the `base_model.model.` prefix and
+    `.base_layer.` / `.lora_A.default.` parts), shapes, dtypes after `.to(bfloat16)` (adapters stay fp32), the same
+    trainable set, the same state_dict keys, and strict loading of each other's state dict."""
+    from b200_ltx import api, lora
+    ns = ref_import.load()
+    cfg = dict(mg.TINY, num_layers=2)
+    P = rb.init_params(cfg, lora_rank, seed=0)
+    ref_model = mg.build_reference_model(ns, cfg, lora_rank, P, train_mode=train_mode).to(BF16)
+    for n, p in ref_model.named_parameters():
+        if "lora_" in n:
+            p.data = p.data.float()
+    mirror = api.build_model(dict(api.LTXV_2B_CONFIG, **cfg), device="cpu")
+    mirror = lora.apply_training_strategy(mirror, lora_rank, lora_rank, train_mode=train_mode)
+    want = {n: (tuple(p.shape), p.dtype, p.requires_grad) for n, p in ref_model.named_parameters()}
+    got = {n: (tuple(p.shape), p.dtype, p.requires_grad) for n, p in mirror.named_parameters()}
+    assert set(got) == set(want), sorted(set(got) ^ set(want))[:6]
+    for n in want:
+        assert got[n] == want[n], (n, got[n], want[n])
+    assert list(dict(mirror.named_parameters())) == list(dict(ref_model.named_parameters()))     # same ORDER too
+    assert set(mirror.state_dict()) == set(ref_model.state_dict())
+    mirror.load_state_dict(ref_model.state_dict(), strict=True)
+    ref_model.load_state_dict(mirror.state_dict(), strict=True)
+    n_train = sum(r for _, _, r in want.values())
+    assert n_train == (20 if train_mode == "lora_audio" else 55)
