@@ -265,12 +265,38 @@ def rf_loss(out, target, grad_scale=1.0, want_grad=True):
     return loss, dout
 
 
+def guidance_step_(v, x, x_next, dt, noise_level, scalars, has_cfg, has_stg, cfg_star=False, rescale=False,
+                   workspace=None):
+    """The element-wise tail of a sampling step (csrc/guidance.cu), in place on the fp32 latents: guidance combine as the
+    oracle restates pipeline_ltx_video.py:1217-1260, Euler update, conditioning select (:1346-1379), and the next
+    step's bf16 model input, one copy per condition."""
+    import ref_sampling as rs
+    B, N, C = x.shape
+    conds = 1 + int(bool(has_cfg)) + int(bool(has_stg))
+    gs, stg, rsc, t = [float(s) for s in scalars[:4]]
+    pred = rs.guidance_combine(v.float(), B, conds, bool(has_cfg), bool(has_stg), gs, stg, rsc if rescale else 1.0,
+                               bool(cfg_star))
+    den = x - dt.reshape(1, -1, 1) * pred
+    if noise_level is not None:
+        den = torch.where((t - 1e-6 < noise_level).unsqueeze(-1), den, x)
+    x.copy_(den)
+    if x_next is not None:
+        x_next.copy_(x.to(BF16).repeat(x_next.shape[0] // B, 1, 1))
+    return x
+
+
+class AsIfOnDevice(torch.Tensor):
+    """A CPU tensor that answers `is_cuda` with True: lets entry points that insist on device tensors (sampling.Denoiser)
+    run their host logic over the stand-ins."""
+    is_cuda = property(lambda self: True)
+
+
 @contextlib.contextmanager
 def patched():
     """Run the product's host logic over these stand-ins (CPU tensors allowed, no device check)."""
     from b200_ltx import lib, modules, ops
     names = ["gemm", "gemm_batched", "norm_mod_fwd", "qknorm_rope_fwd", "fa_fwd", "lerp_condition_", "rf_noise", "rf_loss",
-             "norm_mod_bwd", "colsum_groups", "colsum", "rowscale", "qknorm_rope_bwd", "fa_bwd"]
+             "norm_mod_bwd", "colsum_groups", "colsum", "rowscale", "qknorm_rope_bwd", "fa_bwd", "guidance_step_"]
     saved = {n: getattr(ops, n) for n in names}
     saved_req, saved_dev = modules._require_bf16, lib.require_device
     try:
