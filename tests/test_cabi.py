@@ -229,6 +229,20 @@ def test_empty_problems_are_a_successful_no_op():
     assert h.b200_adamw_chunk_elems() > 0 and h.b200_guidance_step_workspace_bytes(4) > 0
 
 
+@pytest.mark.skipif(torch.cuda.is_available(), reason="only where no launch can happen (stand-in addresses)")
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_random_arguments_never_crash_the_host_side(seed):
+    """8000 random argument lists per seed over twelve entry points (tests/native/abi_fuzz.py, in a subprocess so that a
+    crash is a test failure, not the end of the run): only contract violations, empty no-ops and 'no device' errors."""
+    import subprocess
+    import sys
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "native", "abi_fuzz.py"), str(seed), "8000"],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, (r.returncode, r.stderr[-800:])
+    counts = eval(r.stdout.strip().splitlines()[-1])     # {'neg': .., 'zero': .., 'pos': ..}
+    assert sum(counts.values()) == 8000 and counts["neg"] > 6000 and counts["zero"] > 100 and counts["pos"] > 50, counts
+
+
 @pytest.mark.skipif(torch.cuda.is_available(), reason="CPU-only behaviour")
 def test_no_cpu_fallback():
     from b200_ltx import lib, ops
